@@ -1,0 +1,915 @@
+// C ABI of libcorleone_b200.so (include/corleone_b200.h): handle, table upload, evaluation pipeline,
+// epilogue kernels (defects / objective / gradient / Fisher information), layout conversion.
+#include "../../include/corleone_b200.h"
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "common.cuh"
+
+using namespace cb200;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+static int fail(int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+#define CUDA_TRY(expr)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e_ = (expr);                                                                         \
+        if (e_ != cudaSuccess)                                                                           \
+            return fail(CB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
+                        __LINE__);                                                                       \
+    } while (0)
+
+// ------------------------------------------------------------------ epilogue tables
+struct DefectEntry {
+    int a_kind;   // 0: xend row, 1: ps variable
+    int a_idx;
+    int b_kind;   // 1: ps variable, 2: constant
+    int b_idx;
+    double b_const;
+    int pos_kind;   // position in shooting_constraints (kind-major)
+    int pos_stage;  // position in stage_ordered_shooting_constraints
+};
+
+struct GradEntry {   // grad[var] = sens[src] (src >= 0) or 1.0 (src == -1)
+    int var;
+    long long src;
+};
+
+// ------------------------------------------------------------------ kernels
+// K3: shooting defects, both orderings (src/multiple_shooting.jl:150-163, 229-295). One thread per
+// (defect, candidate), candidate fastest -> coalesced.
+__global__ void defects_kernel(const DefectEntry *__restrict__ tab, int ndef, const double *__restrict__ xend,
+                               const double *__restrict__ ps, long long ldb, long long ldx, long long B,
+                               double *__restrict__ dk, double *__restrict__ dst, long long ldo)
+{
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tid >= (long long)ndef * B) return;
+    const int e = (int)(tid / B);
+    const long long b = tid - (long long)e * B;
+    const DefectEntry t = tab[e];
+    const double a = t.a_kind == 0 ? xend[(long long)t.a_idx * ldx + b] : ps[(long long)t.a_idx * ldb + b];
+    const double c = t.b_kind == 1 ? ps[(long long)t.b_idx * ldb + b] : t.b_const;
+    const double d = a - c;
+    if (dk) dk[(long long)t.pos_kind * ldo + b] = d;
+    if (dst) dst[(long long)t.pos_stage * ldo + b] = d;
+}
+
+// objective = last(getsym(traj))  (src/dynprob.jl:70-71): one row of the last merged sample; a quadrature
+// row carries the running sum over intervals (src/multiple_shooting.jl:171-177).
+__global__ void objective_kernel(const double *__restrict__ xend, long long ldx, const double *__restrict__ ps,
+                                 long long ldb, long long B, int nx, int I, int state_k, int is_quad,
+                                 int ctrl_var, double *__restrict__ obj)
+{
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double v;
+    if (state_k >= 0) {
+        v = 0.0;
+        if (is_quad) {
+            v = xend[(long long)state_k * ldx + b];  // q_prev = us[1][end][q]; then += across intervals in order
+            for (int i = 1; i < I; i++) v = xend[((long long)i * nx + state_k) * ldx + b] + v;
+        } else {
+            v = xend[((long long)(I - 1) * nx + state_k) * ldx + b];
+        }
+    } else {
+        v = ps[(long long)ctrl_var * ldb + b];
+    }
+    obj[b] = v;
+}
+
+__global__ void grad_kernel(const GradEntry *__restrict__ tab, int n, const double *__restrict__ sens,
+                            long long lds, long long B, double *__restrict__ grad, long long ldo)
+{
+    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (tid >= (long long)n * B) return;
+    const int e = (int)(tid / B);
+    const long long b = tid - (long long)e * B;
+    const GradEntry t = tab[e];
+    grad[(long long)t.var * ldo + b] = t.src >= 0 ? sens[t.src * lds + b] : 1.0;
+}
+
+// quadrature accumulation on the merged trajectory (src/multiple_shooting.jl:171-177)
+__global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const double *__restrict__ xend,
+                                 long long ldx, long long B, int nx, int nrow, int I, const int *__restrict__ samp_off,
+                                 const int *__restrict__ M, const int *__restrict__ quad, int nquad)
+{
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int q = 0; q < nquad; q++) {
+        const int k = quad[q];
+        double run = xend[(long long)k * ldx + b];
+        for (int i = 1; i < I; i++) {
+            const int nsmp = M[i] + (i == I - 1 ? 1 : 0);
+            for (int j = 0; j < nsmp; j++) traj[((long long)(samp_off[i] + j) * nrow + k) * ldo + b] += run;
+            run += xend[((long long)i * nx + k) * ldx + b];
+        }
+    }
+}
+
+// K4 read-out: F = F_init + Symmetric(F_triu(t_end)) per candidate (lib/CorleoneOED/src/oed.jl:388-398,
+// augmentation.jl:233) and its sum over the candidates of this launch: warp-shuffle + one atomicAdd per
+// warp and matrix entry.
+__global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long long B, int nx, int I, int f_off,
+                           int n, const double *__restrict__ finit, double *__restrict__ fim, long long ldo,
+                           double *__restrict__ fsum)
+{
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = b < B;
+    for (int c = 0; c < n; c++)
+        for (int r = 0; r < n; r++) {
+            const int a = r < c ? r : c, bb = r < c ? c : r;  // upper-triangle entry (a, bb), a <= bb
+            const int q = bb * (bb + 1) / 2 + a;             // column-major triu position
+            double v = 0.0;
+            if (live) {
+                v = xend[((long long)(I - 1) * nx + f_off + q) * ldx + b] + (finit ? finit[r + n * c] : 0.0);
+                if (fim) fim[(long long)(r + n * c) * ldo + b] = v;
+            }
+            if (fsum) {
+                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+                if ((threadIdx.x & 31) == 0) atomicAdd(fsum + r + n * c, v);
+            }
+        }
+}
+
+// tiled transpose: in[r*ld_in + c] (nr x nc) -> out[c*ld_out + r]
+__global__ void transpose_kernel(const double *__restrict__ in, long long ld_in, double *__restrict__ out,
+                                 long long ld_out, long long nr, long long nc)
+{
+    __shared__ double tile[32][33];
+    const long long c0 = blockIdx.x * 32LL, r0 = blockIdx.y * 32LL;
+    for (int rr = threadIdx.y; rr < 32; rr += 8) {
+        const long long r = r0 + rr, c = c0 + threadIdx.x;
+        if (r < nr && c < nc) tile[rr][threadIdx.x] = in[r * ld_in + c];
+    }
+    __syncthreads();
+    for (int cc = threadIdx.y; cc < 32; cc += 8) {
+        const long long c = c0 + cc, r = r0 + threadIdx.x;
+        if (r < nr && c < nc) out[c * ld_out + r] = tile[threadIdx.x][cc];
+    }
+}
+
+// FP64 peak probe: 8 independent DFMA chains per thread
+__global__ void dfma_probe_kernel(double *out, int iters, double seed)
+{
+    double a0 = seed + threadIdx.x, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5, a6 = a0 + 6,
+           a7 = a0 + 7;
+    const double m = 0.999999, c = 1e-9;
+    for (int i = 0; i < iters; i++) {
+        a0 = fma(a0, m, c);
+        a1 = fma(a1, m, c);
+        a2 = fma(a2, m, c);
+        a3 = fma(a3, m, c);
+        a4 = fma(a4, m, c);
+        a5 = fma(a5, m, c);
+        a6 = fma(a6, m, c);
+        a7 = fma(a7, m, c);
+    }
+    out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// ------------------------------------------------------------------ handle
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes)
+    {
+        if (bytes <= cap) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = bytes + bytes / 8;
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e != cudaSuccess) {
+            e = cudaMalloc(&p, bytes);
+            want = bytes;
+        }
+        if (e != cudaSuccess) return (int)e;
+        cap = want;
+        return 0;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct cb200_handle {
+    std::mutex mu;
+    int device = 0;
+    int model = 0, method = 0;
+    DevLayer L{};
+    int nquad = 0;
+    std::vector<int> quad0;           // 0-based quadrature states
+    std::vector<int> ns;              // directions per interval
+    std::vector<int> h_M, h_var_off, h_n_u0, h_n_c, h_samp_off, h_piece_off;
+    std::vector<long long> h_sens_off;
+    std::vector<int> h_cidx, h_ic_src;
+    std::vector<DefectEntry> defects;
+    std::vector<long long> jac_rows, jac_cols, jac_src;
+    long long n_sens = 0;
+    int n_samples = 0;
+    int max_ns = 0;
+    int fim_off = -1, fim_n = 0;
+    int G_sens = 2;                   // sensitivity directions per thread
+    void *tables = nullptr;           // one device allocation holding every table
+    DefectEntry *d_defects = nullptr;
+    int *d_quad = nullptr;
+    GradEntry *d_grad = nullptr;      // scratch table for the current objective row
+    int grad_cap = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    bool timed = false;
+    long long launches = 0;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out;
+};
+
+static int default_G(int model)
+{
+    switch (model) {
+    case CB200_MODEL_LQR: return 2;
+    case CB200_MODEL_LOTKA3: return 2;
+    case CB200_MODEL_LOTKA2: return 2;
+    case CB200_MODEL_LIN1D: return 4;
+    case CB200_MODEL_EGERSTEDT: return 2;
+    case CB200_MODEL_DENSE20: return 1;
+    default: return 0;
+    }
+}
+
+static int model_dims(int model, int *nx, int *np)
+{
+    switch (model) {
+    case CB200_MODEL_LOTKA3: *nx = 3; *np = 3; return 0;
+    case CB200_MODEL_LQR: *nx = 2; *np = 3; return 0;
+    case CB200_MODEL_LOTKA2: *nx = 2; *np = 3; return 0;
+    case CB200_MODEL_LOTKA2_OED: *nx = 9; *np = 5; return 0;
+    case CB200_MODEL_LIN1D: *nx = 1; *np = 1; return 0;
+    case CB200_MODEL_LIN1D_OED: *nx = 3; *np = 2; return 0;
+    case CB200_MODEL_DENSE20: *nx = 20; *np = 1; return 0;
+    case CB200_MODEL_EGERSTEDT: *nx = 3; *np = 3; return 0;
+    default: return -1;
+    }
+}
+
+static int launch_model(int model, int G, int method, const DevLayer &L, const double *ps, long long ldb,
+                        long long B, const ShootOut &o, cudaStream_t s)
+{
+    switch (model) {
+    case CB200_MODEL_LOTKA3: return launch_lotka3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LQR: return launch_lqr(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKA2: return launch_lotka2(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKA2_OED: return launch_lotka2_oed(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LIN1D: return launch_lin1d(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LIN1D_OED: return launch_lin1d_oed(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DENSE20: return launch_dense20(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_EGERSTEDT: return launch_egerstedt(G, method, L, ps, ldb, B, o, s);
+    default: return -1000;
+    }
+}
+
+extern "C" int cb200_version(void) { return CB200_VERSION; }
+extern "C" const char *cb200_last_error(void) { return g_err.c_str(); }
+
+template <class T>
+static size_t push(std::vector<char> &blob, const std::vector<T> &v)
+{
+    size_t off = (blob.size() + 15) & ~size_t(15);
+    blob.resize(off + sizeof(T) * std::max<size_t>(v.size(), 1));
+    if (!v.empty()) memcpy(blob.data() + off, v.data(), sizeof(T) * v.size());
+    return off;
+}
+
+extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
+{
+    if (!d || !out) return fail(CB200_ERR_ARG, "null argument");
+    *out = nullptr;
+    if (d->struct_size != (int32_t)sizeof(cb200_desc))
+        return fail(CB200_ERR_ARG, "cb200_desc.struct_size %d != %d", d->struct_size, (int)sizeof(cb200_desc));
+    int mnx = 0, mnp = 0;
+    if (model_dims(d->model, &mnx, &mnp)) return fail(CB200_ERR_UNSUPPORTED, "unknown model id %d", d->model);
+    if (d->nx != mnx || d->np_all != mnp)
+        return fail(CB200_ERR_ARG, "model %d expects nx=%d, np=%d; got nx=%d, np=%d", d->model, mnx, mnp, d->nx,
+                    d->np_all);
+    if (d->method != CB200_TSIT5 && d->method != CB200_RK4) return fail(CB200_ERR_UNSUPPORTED, "unknown method");
+    if (d->steps_per_piece < 1) return fail(CB200_ERR_ARG, "steps_per_piece must be >= 1");
+    if (d->n_intervals < 1) return fail(CB200_ERR_ARG, "n_intervals must be >= 1");
+    if (d->n_controls < 0 || d->n_controls > MAX_CTRL) return fail(CB200_ERR_ARG, "n_controls out of range");
+    if (d->np_all > MAX_NP) return fail(CB200_ERR_ARG, "np_all too large");
+    if (d->n_tunable_p + d->n_controls != d->np_all)
+        return fail(CB200_ERR_ARG, "n_tunable_p + n_controls must equal np_all (every p entry is a parameter or a control)");
+
+    int ndev = 0;
+    cudaError_t ce = cudaGetDeviceCount(&ndev);
+    if (ce != cudaSuccess || ndev == 0)
+        return fail(CB200_ERR_CUDA, "no CUDA device (%s); libcorleone_b200 has no CPU fallback",
+                    ce != cudaSuccess ? cudaGetErrorString(ce) : "device count 0");
+    if (d->device < 0 || d->device >= ndev) return fail(CB200_ERR_ARG, "device ordinal %d out of range", d->device);
+    CUDA_TRY(cudaSetDevice(d->device));
+
+    cb200_handle *h = new (std::nothrow) cb200_handle();
+    if (!h) return fail(CB200_ERR_NOMEM, "out of host memory");
+    h->device = d->device;
+    h->model = d->model;
+    h->method = d->method;
+    DevLayer &L = h->L;
+    const int nx = d->nx, I = d->n_intervals, nact = d->n_controls, ntp = d->n_tunable_p;
+    L.nx = nx;
+    L.np_all = d->np_all;
+    L.nact = nact;
+    L.ntp = ntp;
+    L.I = I;
+    L.K = d->steps_per_piece;
+    L.R = 1;
+
+    // scatter maps A, B (src/single_shooting.jl:306-318): column ids in ascending p index
+    {
+        int pid = 0, cid = 0;
+        for (int q = 1; q <= d->np_all; q++) {
+            bool is_c = false;
+            for (int r = 0; r < nact; r++) is_c |= (d->control_indices[r] == q);
+            if (is_c) {
+                L.pmap_kind[q - 1] = 1;
+                L.pmap_idx[q - 1] = cid;
+                L.row_to_p[cid] = q - 1;
+                cid++;
+            } else {
+                if (pid >= ntp || d->tunable_p[pid] != q) {
+                    delete h;
+                    return fail(CB200_ERR_ARG, "tunable_p is not setdiff(eachindex(p), control_indices)");
+                }
+                L.pmap_kind[q - 1] = 0;
+                L.pmap_idx[q - 1] = pid;
+                L.tunable_p0[pid] = q - 1;
+                pid++;
+            }
+        }
+        if (cid != nact) {
+            delete h;
+            return fail(CB200_ERR_ARG, "control_indices must be distinct and within 1..np_all");
+        }
+    }
+    h->nquad = d->n_quadrature;
+    for (int k = 0; k < d->n_quadrature; k++) h->quad0.push_back((int)d->quadrature_indices[k] - 1);
+    if (d->fim_offset > 0) {
+        h->fim_off = d->fim_offset - 1;
+        h->fim_n = d->fim_n;
+        if (h->fim_off + h->fim_n * (h->fim_n + 1) / 2 > nx) {
+            delete h;
+            return fail(CB200_ERR_ARG, "Fisher block exceeds the state vector");
+        }
+    }
+
+    // per-interval tables
+    std::vector<double> pt0, pt1, ic_fix;
+    int po = 0, vo = 0, so = 0, co = 0, sio = 0;
+    long long seo = 0;
+    long long igo = 0;
+    std::vector<int> sidx_off(I + 1, 0);
+    for (int i = 0; i < I; i++) {
+        const int M = d->n_pieces[i];
+        if (M < 1) {
+            delete h;
+            return fail(CB200_ERR_ARG, "interval %d has no pieces", i + 1);
+        }
+        h->h_M.push_back(M);
+        h->h_piece_off.push_back(po);
+        h->h_var_off.push_back(vo);
+        h->h_n_u0.push_back(d->n_u0[i]);
+        h->h_n_c.push_back(d->n_local_controls[i]);
+        h->h_samp_off.push_back(so);
+        h->h_sens_off.push_back(seo);
+        const int nsi = d->n_u0[i] + ntp + d->n_local_controls[i];
+        h->ns.push_back(nsi);
+        h->max_ns = std::max(h->max_ns, nsi);
+        for (int j = 0; j < M; j++) {
+            pt0.push_back(d->tspans[2 * (size_t)(po + j)]);
+            pt1.push_back(d->tspans[2 * (size_t)(po + j) + 1]);
+            for (int r = 0; r < nact; r++) {
+                const long long ci = d->index_grid[igo + r + (long long)nact * j] - 1;
+                if (ci < 0 || ci >= d->n_local_controls[i]) {
+                    delete h;
+                    return fail(CB200_ERR_ARG, "index_grid entry out of range in interval %d", i + 1);
+                }
+                h->h_cidx.push_back((int)ci);
+            }
+        }
+        // InitialConditionRemaker (src/single_shooting.jl:260-266)
+        const int ncon = d->ic_n_constants[i], nu0 = d->n_u0[i];
+        for (int k = 0; k < nx; k++) {
+            int src = -1;
+            double fix = 0.0;
+            if (nu0 == 0) {
+                fix = d->is_shooting[i] ? 0.0 : d->u0[k];
+            } else {
+                if (ncon + nu0 != nx) {
+                    delete h;
+                    return fail(CB200_ERR_ARG, "interval %d: constants + tunables != nx", i + 1);
+                }
+                const int pos = (int)d->ic_sorting[(size_t)i * nx + k] - 1;
+                if (pos < 0 || pos >= nx) {
+                    delete h;
+                    return fail(CB200_ERR_ARG, "ic_sorting out of range");
+                }
+                if (pos < ncon)
+                    fix = d->is_shooting[i] ? 0.0 : d->u0[d->ic_constants[co + pos] - 1];
+                else
+                    src = pos - ncon;
+            }
+            h->h_ic_src.push_back(src);
+            ic_fix.push_back(fix);
+        }
+        co += ncon;
+        sidx_off[i + 1] = sidx_off[i] + d->n_shooting_indices[i];
+        sio += d->n_shooting_indices[i];
+        po += M;
+        igo += (long long)nact * M;
+        vo += nsi;
+        so += M;
+        seo += (long long)nx * nsi;
+    }
+    (void)sio;
+    L.nvars = vo;
+    h->n_sens = seo;
+    h->n_samples = so + 1;
+
+    // defect table + Jacobian structure (src/multiple_shooting.jl:150-163, 281-295)
+    {
+        int n_u = 0, n_p = 0, n_c = 0;
+        for (int i = 1; i < I; i++) {
+            for (int q = sidx_off[i]; q < sidx_off[i + 1]; q++) (d->shooting_indices[q] <= nx ? n_u : n_c)++;
+            n_p += ntp;
+        }
+        int ou = 0, op = n_u, oc = n_u + n_p, os = 0;
+        auto ctrl_var = [&](int iv, int piece, int r) {
+            return h->h_var_off[iv] + h->h_n_u0[iv] + ntp + h->h_cidx[(size_t)(h->h_piece_off[iv] + piece) * nact + r];
+        };
+        for (int i = 1; i < I; i++) {
+            for (int pass = 0; pass < 3; pass++) {
+                if (pass == 1) {
+                    for (int k = 0; k < ntp; k++) {
+                        DefectEntry e{1, h->h_var_off[i - 1] + h->h_n_u0[i - 1] + k, 1,
+                                      h->h_var_off[i] + h->h_n_u0[i] + k, 0.0, op, os};
+                        h->defects.push_back(e);
+                        h->jac_rows.push_back(op + 1); h->jac_cols.push_back(e.a_idx + 1); h->jac_src.push_back(-1);
+                        h->jac_rows.push_back(op + 1); h->jac_cols.push_back(e.b_idx + 1); h->jac_src.push_back(-2);
+                        op++;
+                        os++;
+                    }
+                    continue;
+                }
+                for (int q = sidx_off[i]; q < sidx_off[i + 1]; q++) {
+                    const int rI = (int)d->shooting_indices[q] - 1;
+                    if ((pass == 0) != (rI < nx)) continue;
+                    DefectEntry e{};
+                    int &o = (pass == 0) ? ou : oc;
+                    e.pos_kind = o;
+                    e.pos_stage = os;
+                    if (rI < nx) {
+                        e.a_kind = 0;
+                        e.a_idx = (i - 1) * nx + rI;
+                        const int src = h->h_ic_src[(size_t)i * nx + rI];
+                        if (src >= 0) {
+                            e.b_kind = 1;
+                            e.b_idx = h->h_var_off[i] + src;
+                        } else {
+                            e.b_kind = 2;
+                            e.b_const = ic_fix[(size_t)i * nx + rI];
+                        }
+                        for (int dd = 0; dd < h->ns[i - 1]; dd++) {
+                            h->jac_rows.push_back(o + 1);
+                            h->jac_cols.push_back(h->h_var_off[i - 1] + dd + 1);
+                            h->jac_src.push_back(h->h_sens_off[i - 1] + (long long)dd * nx + rI);
+                        }
+                        if (e.b_kind == 1) {
+                            h->jac_rows.push_back(o + 1); h->jac_cols.push_back(e.b_idx + 1); h->jac_src.push_back(-2);
+                        }
+                    } else {
+                        const int r = rI - nx;
+                        if (r >= nact) {
+                            delete h;
+                            return fail(CB200_ERR_ARG, "shooting index beyond [states; controls]");
+                        }
+                        e.a_kind = 1;
+                        e.a_idx = ctrl_var(i - 1, h->h_M[i - 1] - 1, r);
+                        e.b_kind = 1;
+                        e.b_idx = ctrl_var(i, 0, r);
+                        h->jac_rows.push_back(o + 1); h->jac_cols.push_back(e.a_idx + 1); h->jac_src.push_back(-1);
+                        h->jac_rows.push_back(o + 1); h->jac_cols.push_back(e.b_idx + 1); h->jac_src.push_back(-2);
+                    }
+                    h->defects.push_back(e);
+                    o++;
+                    os++;
+                }
+            }
+        }
+    }
+
+    // upload
+    std::vector<char> blob;
+    const size_t o_M = push(blob, h->h_M), o_po = push(blob, h->h_piece_off), o_t0 = push(blob, pt0),
+                 o_t1 = push(blob, pt1), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
+                 o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
+                 o_if = push(blob, ic_fix), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
+                 o_de = push(blob, h->defects), o_q = push(blob, h->quad0);
+    const size_t o_gr = (blob.size() + 15) & ~size_t(15);
+    h->grad_cap = std::max(1, L.nvars);
+    blob.resize(o_gr + sizeof(GradEntry) * (size_t)h->grad_cap);
+    auto bail = [&](const char *what, cudaError_t e) {
+        int rc = fail(CB200_ERR_CUDA, "%s failed: %s", what, cudaGetErrorString(e));
+        cb200_destroy(h);
+        return rc;
+    };
+    cudaError_t e = cudaMalloc(&h->tables, blob.size());
+    if (e != cudaSuccess) return bail("cudaMalloc(tables)", e);
+    e = cudaMemcpy(h->tables, blob.data(), blob.size(), cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) return bail("cudaMemcpy(tables)", e);
+    char *base = (char *)h->tables;
+    L.M = (const int *)(base + o_M);
+    L.piece_off = (const int *)(base + o_po);
+    L.pt0 = (const double *)(base + o_t0);
+    L.pt1 = (const double *)(base + o_t1);
+    L.cidx = (const int *)(base + o_ci);
+    L.var_off = (const int *)(base + o_vo);
+    L.n_u0 = (const int *)(base + o_nu);
+    L.n_c = (const int *)(base + o_nc);
+    L.ic_src = (const int *)(base + o_is);
+    L.ic_fix = (const double *)(base + o_if);
+    L.sens_off = (const long long *)(base + o_se);
+    L.samp_off = (const int *)(base + o_so);
+    h->d_defects = (DefectEntry *)(base + o_de);
+    h->d_quad = (int *)(base + o_q);
+    h->d_grad = (GradEntry *)(base + o_gr);
+
+    if (d->model == CB200_MODEL_DENSE20) {
+        if (!d->model_data || d->model_data_len != 420) {
+            cb200_destroy(h);
+            return fail(CB200_ERR_ARG, "DENSE20 needs model_data of 420 doubles (W row-major, then b)");
+        }
+        int rc = dense20_set_data(d->model_data, d->model_data_len);
+        if (rc != 0) return bail("cudaMemcpyToSymbol(dense20)", (cudaError_t)rc);
+    }
+    e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) return bail("cudaStreamCreate", e);
+    h->own_stream = true;
+    e = cudaEventCreate(&h->ev0);
+    if (e != cudaSuccess) return bail("cudaEventCreate", e);
+    e = cudaEventCreate(&h->ev1);
+    if (e != cudaSuccess) return bail("cudaEventCreate", e);
+    h->G_sens = default_G(d->model);
+    if (const char *env = getenv("CB200_DIRS_PER_THREAD")) {
+        int g = atoi(env);
+        if (g > 0) h->G_sens = g;
+    }
+    *out = h;
+    return CB200_OK;
+}
+
+extern "C" int cb200_destroy(cb200_handle *h)
+{
+    if (!h) return CB200_OK;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
+                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out})
+        b->release();
+    if (h->tables) cudaFree(h->tables);
+    if (h->ev0) cudaEventDestroy(h->ev0);
+    if (h->ev1) cudaEventDestroy(h->ev1);
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return CB200_OK;
+}
+
+extern "C" int cb200_get_sizes(const cb200_handle *h, cb200_sizes *s)
+{
+    if (!h || !s) return fail(CB200_ERR_ARG, "null argument");
+    s->nvars = h->L.nvars;
+    s->n_defects = (int64_t)h->defects.size();
+    s->n_samples = h->n_samples;
+    s->n_row = h->L.nx + h->L.nact;
+    s->n_sens = h->n_sens;
+    s->n_units = h->L.I;
+    s->jac_nnz = (int64_t)h->jac_rows.size();
+    return CB200_OK;
+}
+
+extern "C" int cb200_block_structure(const cb200_handle *h, int64_t *blocks)
+{
+    if (!h || !blocks) return fail(CB200_ERR_ARG, "null argument");
+    for (int i = 0; i < h->L.I; i++) blocks[i] = h->h_var_off[i];
+    blocks[h->L.I] = h->L.nvars;
+    return CB200_OK;
+}
+
+extern "C" int cb200_set_stream(cb200_handle *h, void *stream)
+{
+    if (!h) return fail(CB200_ERR_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    if (h->own_stream && h->stream) {
+        cudaStreamSynchronize(h->stream);
+        cudaStreamDestroy(h->stream);
+    }
+    h->stream = (cudaStream_t)stream;
+    h->own_stream = false;
+    return CB200_OK;
+}
+
+extern "C" int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int64_t *src)
+{
+    if (!h) return fail(CB200_ERR_ARG, "null handle");
+    for (size_t k = 0; k < h->jac_rows.size(); k++) {
+        if (rows) rows[k] = h->jac_rows[k];
+        if (cols) cols[k] = h->jac_cols[k];
+        if (src) src[k] = h->jac_src[k];
+    }
+    return CB200_OK;
+}
+
+extern "C" float cb200_last_kernel_ms(const cb200_handle *h)
+{
+    if (!h || !h->timed) return -1.0f;
+    float ms = -1.0f;
+    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
+    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+    return ms;
+}
+
+extern "C" int64_t cb200_launch_count(const cb200_handle *h) { return h ? h->launches : 0; }
+
+static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
+
+static int transpose(cb200_handle *h, const double *in, long long ld_in, double *out, long long ld_out, long long nr,
+                     long long nc)
+{
+    if (nr <= 0 || nc <= 0) return 0;
+    // grid.y is limited to 65535 blocks: split rows
+    const long long max_rows = 65535LL * 32;
+    for (long long r0 = 0; r0 < nr; r0 += max_rows) {
+        const long long rows = std::min(max_rows, nr - r0);
+        dim3 grid((unsigned)((nc + 31) / 32), (unsigned)((rows + 31) / 32));
+        transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(in + r0 * ld_in, ld_in, out + r0, ld_out, rows, nc);
+        h->launches++;
+    }
+    return (int)cudaGetLastError();
+}
+
+// deliver a device SoA result [n x B] (ld B) to the caller according to flags
+static int deliver(cb200_handle *h, const double *dev_soa, double *user, long long n, long long B, uint32_t flags)
+{
+    if (!user || dev_soa == user) return CB200_OK;
+    const bool dev = flags & CB200_MEM_DEVICE, soa = flags & CB200_OUT_SOA;
+    const size_t bytes = sizeof(double) * (size_t)n * (size_t)B;
+    if (soa) {
+        CUDA_TRY(cudaMemcpyAsync(user, dev_soa, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
+        return CB200_OK;
+    }
+    if (dev) {
+        int rc = transpose(h, dev_soa, B, user, n, n, B);
+        if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        return CB200_OK;
+    }
+    // the staging buffer is reused per output; stream order keeps the copies safe
+    if (h->ws_out.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (%zu bytes staging)", bytes);
+    int rc = transpose(h, dev_soa, B, (double *)h->ws_out.p, n, n, B);
+    if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    CUDA_TRY(cudaMemcpyAsync(user, h->ws_out.p, bytes, cudaMemcpyDeviceToHost, h->stream));
+    // one staging buffer: wait before the next deliver() overwrites it
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CB200_OK;
+}
+
+extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t ldb, uint32_t want, uint32_t flags,
+                          const cb200_out *out)
+{
+    if (!h || !out) return fail(CB200_ERR_ARG, "null argument");
+    if (B < 0) return fail(CB200_ERR_ARG, "negative batch");
+    if (B == 0) return CB200_OK;
+    if (!ps && h->L.nvars > 0) return fail(CB200_ERR_ARG, "null ps");
+    std::lock_guard<std::mutex> lk(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const DevLayer &L0 = h->L;
+    const int nx = L0.nx, I = L0.I, nvars = L0.nvars;
+    const bool dev = flags & CB200_MEM_DEVICE, ps_soa = flags & CB200_PS_SOA, out_soa = flags & CB200_OUT_SOA;
+    const bool direct = dev && out_soa;  // kernels may write straight into the caller's buffers
+    if (ps_soa ? (ldb < B) : (ldb < nvars)) return fail(CB200_ERR_ARG, "ldb too small");
+    const long long nrow = nx + L0.nact;
+    const long long ndef = (long long)h->defects.size();
+
+    const bool w_sens = (want & CB200_WANT_SENS) && out->sens, w_grad = (want & CB200_WANT_GRAD) && out->grad;
+    const bool w_traj = (want & CB200_WANT_TRAJ) && out->traj, w_xend = (want & CB200_WANT_XEND) && out->xend;
+    const bool w_def = (want & CB200_WANT_DEFECTS) && (out->defects_kind || out->defects_stage);
+    const bool w_obj = (want & CB200_WANT_OBJ) && out->objective;
+    const bool w_fim = (want & CB200_WANT_FIM) && (out->fim || out->fim_sum);
+    const bool need_sens = w_sens || w_grad;
+    if (w_fim && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
+    int obj_state = -1, obj_ctrl_var = -1, obj_quad = 0;
+    if (w_obj || w_grad) {
+        const int row = out->objective_row;
+        if (row < 1 || row > nrow) return fail(CB200_ERR_ARG, "objective_row out of range");
+        if (row <= nx) {
+            obj_state = row - 1;
+            for (int q : h->quad0) obj_quad |= (q == obj_state);
+        } else {
+            const int r = row - nx - 1;
+            obj_ctrl_var = h->h_var_off[I - 1] + h->h_n_u0[I - 1] + L0.ntp +
+                           h->h_cidx[(size_t)(h->h_piece_off[I - 1] + h->h_M[I - 1] - 1) * L0.nact + r];
+        }
+    }
+
+    // ---- stage ps as device SoA [v*B + b]
+    const double *d_ps = nullptr;
+    long long d_ldb = B;
+    if (nvars > 0) {
+        if (dev && ps_soa) {
+            d_ps = ps;
+            d_ldb = ldb;
+        } else {
+            const size_t bytes = sizeof(double) * (size_t)nvars * (size_t)B;
+            if (h->ws_ps.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (ps, %zu bytes)", bytes);
+            if (ps_soa) {  // host, variable-major
+                CUDA_TRY(cudaMemcpy2DAsync(h->ws_ps.p, sizeof(double) * B, ps, sizeof(double) * ldb, sizeof(double) * B,
+                                           nvars, cudaMemcpyHostToDevice, h->stream));
+            } else if (dev) {
+                int rc = transpose(h, ps, ldb, (double *)h->ws_ps.p, B, B, nvars);
+                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            } else {  // host, candidate-major (Julia nvars x B matrix)
+                if (h->ws_in.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+                CUDA_TRY(cudaMemcpy2DAsync(h->ws_in.p, sizeof(double) * nvars, ps, sizeof(double) * ldb,
+                                           sizeof(double) * nvars, B, cudaMemcpyHostToDevice, h->stream));
+                int rc = transpose(h, (const double *)h->ws_in.p, nvars, (double *)h->ws_ps.p, B, B, nvars);
+                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            }
+            d_ps = (const double *)h->ws_ps.p;
+        }
+    }
+
+    // ---- device SoA result buffers
+    auto buf = [&](DevBuf &ws, double *user, long long n, bool wanted, bool needed, double **dst) -> int {
+        *dst = nullptr;
+        if (!wanted && !needed) return 0;
+        if (wanted && direct) {
+            *dst = user;
+            return 0;
+        }
+        if (ws.reserve(sizeof(double) * (size_t)n * (size_t)B)) return 1;
+        *dst = (double *)ws.p;
+        return 0;
+    };
+    double *d_xend, *d_sens, *d_traj, *d_dk, *d_ds, *d_obj, *d_grad, *d_fim;
+    const bool need_xend = w_def || w_obj || w_fim || (w_traj && h->nquad > 0);
+    int oom = 0;
+    oom |= buf(h->ws_xend, out->xend, (long long)nx * I, w_xend, need_xend, &d_xend);
+    oom |= buf(h->ws_sens, out->sens, h->n_sens, w_sens, need_sens, &d_sens);
+    oom |= buf(h->ws_traj, out->traj, nrow * h->n_samples, w_traj, false, &d_traj);
+    oom |= buf(h->ws_dk, out->defects_kind, ndef, w_def && out->defects_kind, false, &d_dk);
+    oom |= buf(h->ws_ds, out->defects_stage, ndef, w_def && out->defects_stage, false, &d_ds);
+    oom |= buf(h->ws_obj, out->objective, 1, w_obj, false, &d_obj);
+    oom |= buf(h->ws_grad, out->grad, nvars, w_grad, false, &d_grad);
+    oom |= buf(h->ws_fim, out->fim, (long long)h->fim_n * h->fim_n, w_fim && out->fim, false, &d_fim);
+    if (oom) return fail(CB200_ERR_NOMEM, "device out of memory for result buffers (B=%lld)", (long long)B);
+
+    // ---- K1/K2: integrate every (interval, candidate) unit
+    DevLayer L = L0;
+    int G = 0;
+    if (need_sens) {
+        G = h->G_sens;
+        if (G <= 0) return fail(CB200_ERR_UNSUPPORTED, "model %d has no sensitivity kernel", h->model);
+        L.R = (h->max_ns + G - 1) / G;
+        if (L.R < 1) L.R = 1;
+    }
+    ShootOut so{d_xend, d_sens, d_traj, B};
+    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, h->stream);
+    if (rc == -1000)
+        return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
+                    h->method);
+    if (rc) return fail(CB200_ERR_CUDA, "shoot kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    h->launches++;
+    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+    h->timed = true;
+
+    // ---- K3: defects / objective / gradient / trajectory quadratures / FIM
+    if (w_def && ndef > 0) {
+        defects_kernel<<<nblk(ndef * B, 256), 256, 0, h->stream>>>(h->d_defects, (int)ndef, d_xend, d_ps, d_ldb, B, B,
+                                                                 d_dk, d_ds, B);
+        h->launches++;
+    }
+    if (w_obj) {
+        objective_kernel<<<nblk(B, 256), 256, 0, h->stream>>>(d_xend, B, d_ps, d_ldb, B, nx, I, obj_state, obj_quad,
+                                                            obj_ctrl_var, d_obj);
+        h->launches++;
+    }
+    if (w_grad) {
+        CUDA_TRY(cudaMemsetAsync(d_grad, 0, sizeof(double) * (size_t)nvars * (size_t)B, h->stream));
+        std::vector<GradEntry> g;
+        if (obj_state >= 0) {
+            for (int i = obj_quad ? 0 : I - 1; i < I; i++)
+                for (int dd = 0; dd < h->ns[i]; dd++)
+                    g.push_back({h->h_var_off[i] + dd, h->h_sens_off[i] + (long long)dd * nx + obj_state});
+        } else {
+            g.push_back({obj_ctrl_var, -1});
+        }
+        if (!g.empty()) {
+            CUDA_TRY(cudaMemcpyAsync(h->d_grad, g.data(), sizeof(GradEntry) * g.size(), cudaMemcpyHostToDevice, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));  // g is a stack vector
+            grad_kernel<<<nblk((long long)g.size() * B, 256), 256, 0, h->stream>>>(h->d_grad, (int)g.size(), d_sens, B, B,
+                                                                                d_grad, B);
+            h->launches++;
+        }
+    }
+    if (w_traj && h->nquad > 0 && I > 1) {
+        traj_quad_kernel<<<nblk(B, 128), 128, 0, h->stream>>>(d_traj, B, d_xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
+                                                            h->d_quad, h->nquad);
+        h->launches++;
+    }
+    double *d_fsum = nullptr;
+    if (w_fim) {
+        const int n2 = h->fim_n * h->fim_n;
+        const double *d_finit = nullptr;
+        if (out->fim_init) {
+            if (h->ws_finit.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
+            CUDA_TRY(cudaMemcpyAsync(h->ws_finit.p, out->fim_init, sizeof(double) * n2,
+                                     dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+            d_finit = (const double *)h->ws_finit.p;
+        }
+        if (out->fim_sum) {
+            if (dev) {
+                d_fsum = out->fim_sum;
+            } else {
+                if (h->ws_fsum.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
+                d_fsum = (double *)h->ws_fsum.p;
+            }
+            CUDA_TRY(cudaMemsetAsync(d_fsum, 0, sizeof(double) * n2, h->stream));
+        }
+        fim_kernel<<<nblk(B, 128), 128, 0, h->stream>>>(d_xend, B, B, nx, I, h->fim_off, h->fim_n, d_finit, d_fim, B, d_fsum);
+        h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
+
+    // ---- deliver
+    if (!direct) {
+        int r2 = 0;
+        if (w_xend) r2 |= deliver(h, d_xend, out->xend, (long long)nx * I, B, flags);
+        if (w_sens) r2 |= deliver(h, d_sens, out->sens, h->n_sens, B, flags);
+        if (w_traj) r2 |= deliver(h, d_traj, out->traj, nrow * h->n_samples, B, flags);
+        if (w_def && out->defects_kind) r2 |= deliver(h, d_dk, out->defects_kind, ndef, B, flags);
+        if (w_def && out->defects_stage) r2 |= deliver(h, d_ds, out->defects_stage, ndef, B, flags);
+        if (w_obj) r2 |= deliver(h, d_obj, out->objective, 1, B, flags);
+        if (w_grad) r2 |= deliver(h, d_grad, out->grad, nvars, B, flags);
+        if (w_fim && out->fim) r2 |= deliver(h, d_fim, out->fim, (long long)h->fim_n * h->fim_n, B, flags);
+        if (r2) return r2;
+    }
+    if (w_fim && out->fim_sum && !dev)
+        CUDA_TRY(cudaMemcpyAsync(out->fim_sum, d_fsum, sizeof(double) * h->fim_n * h->fim_n, cudaMemcpyDeviceToHost,
+                                 h->stream));
+    if (!dev) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CB200_OK;
+}
+
+extern "C" double cb200_probe_fp64_tflops(int device, int iters)
+{
+    if (cudaSetDevice(device) != cudaSuccess) return -1.0;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
+    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    double *out = nullptr;
+    if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) return -1.0;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    dfma_probe_kernel<<<blocks, threads>>>(out, iters / 4 + 1, 1.0);  // warm-up
+    double best = -1.0;
+    for (int rep = 0; rep < 3; rep++) {
+        cudaEventRecord(e0);
+        dfma_probe_kernel<<<blocks, threads>>>(out, iters, 1.0 + rep);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) break;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        best = std::max(best, flops / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(out);
+    return best;
+}

@@ -1,0 +1,62 @@
+// Shared device-side layer description and launch interfaces.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace cb200 {
+
+constexpr int MAX_NP = 16;
+constexpr int MAX_CTRL = 8;
+
+// Static tables of one layer, resident in HBM (tiny; L1/L2 cached).  Built once in cb200_create from the
+// reference's `st` (src/single_shooting.jl:343-351), converted to 0-based.
+struct DevLayer {
+    int nx, np_all, nact, ntp, I, K;
+    int R;            // direction groups per unit = max_i ceil(ns_i / G); 1 when G == 0
+    int nvars;
+    int pmap_kind[MAX_NP];   // p_full[q] = kind ? controls_j[idx] : ps.p[idx]   (A, B of single_shooting.jl:306-323)
+    int pmap_idx[MAX_NP];
+    int tunable_p0[MAX_NP];  // 0-based p index of tunable parameter m
+    int row_to_p[MAX_CTRL];  // 0-based p index fed by control row r
+    const int *M;            // [I] pieces
+    const int *piece_off;    // [I] offset into the piece arrays
+    const double *pt0;       // [sum M] piece start
+    const double *pt1;       // [sum M] piece end
+    const int *cidx;         // [sum M * nact] 0-based local control index of (piece, row)
+    const int *var_off;      // [I] offset of the interval's block in the flat ps
+    const int *n_u0;         // [I]
+    const int *n_c;          // [I]
+    const int *ic_src;       // [I*nx] >= 0: index into the interval's ps.u0; -1: fixed value
+    const double *ic_fix;    // [I*nx]
+    const long long *sens_off;  // [I] first row of the interval's block in `sens`
+    const int *samp_off;     // [I] first merged-trajectory sample of the interval
+};
+
+struct ShootOut {
+    double *xend;  // [(i*nx + k) * ldo + b]
+    double *sens;  // [(sens_off[i] + d*nx + k) * ldo + b]
+    double *traj;  // [((samp_off[i] + j) * nrow + r) * ldo + b]
+    long long ldo;
+};
+
+// launchers, one per model translation unit; return cudaError_t as int, or -1000 if (G, method) is not
+// instantiated for the model
+int launch_lotka3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                  const ShootOut &o, cudaStream_t s);
+int launch_lotka2(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                  const ShootOut &o, cudaStream_t s);
+int launch_lqr(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+               const ShootOut &o, cudaStream_t s);
+int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                 const ShootOut &o, cudaStream_t s);
+int launch_egerstedt(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                     const ShootOut &o, cudaStream_t s);
+int launch_lotka2_oed(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                      const ShootOut &o, cudaStream_t s);
+int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                     const ShootOut &o, cudaStream_t s);
+int launch_dense20(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+                   const ShootOut &o, cudaStream_t s);
+int dense20_set_data(const double *host_data, long long n);
+
+}  // namespace cb200

@@ -1,0 +1,21 @@
+// Instantiations of the shooting kernel for model Dense20 (see shoot.cuh).
+#define CB200_NEED_DENSE20_DATA 1
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_dense20(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Dense20, 0)
+        CB200_DISPATCH_G(Dense20, 1)
+    default:
+        return -1000;
+    }
+}
+int dense20_set_data(const double *host_data, long long n)
+{
+    if (n != 420) return -1;
+    return (int)cudaMemcpyToSymbol(c_dense20, host_data, sizeof(double) * 420);
+}
+}  // namespace cb200

@@ -1,0 +1,17 @@
+// Instantiations of the shooting kernel for model Lin1d (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Lin1d, 0)
+        CB200_DISPATCH_G(Lin1d, 1)
+        CB200_DISPATCH_G(Lin1d, 2)
+        CB200_DISPATCH_G(Lin1d, 4)
+    default:
+        return -1000;
+    }
+}
+}  // namespace cb200

@@ -1,0 +1,14 @@
+// Instantiations of the shooting kernel for model Lin1dOed (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Lin1dOed, 0)
+    default:
+        return -1000;
+    }
+}
+}  // namespace cb200

@@ -1,0 +1,18 @@
+// Instantiations of the shooting kernel for model Lotka2 (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_lotka2(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Lotka2, 0)
+        CB200_DISPATCH_G(Lotka2, 1)
+        CB200_DISPATCH_G(Lotka2, 2)
+        CB200_DISPATCH_G(Lotka2, 3)
+        CB200_DISPATCH_G(Lotka2, 4)
+    default:
+        return -1000;
+    }
+}
+}  // namespace cb200

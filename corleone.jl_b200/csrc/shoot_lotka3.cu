@@ -1,0 +1,18 @@
+// Instantiations of the shooting kernel for model Lotka3 (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_lotka3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Lotka3, 0)
+        CB200_DISPATCH_G(Lotka3, 1)
+        CB200_DISPATCH_G(Lotka3, 2)
+        CB200_DISPATCH_G(Lotka3, 3)
+        CB200_DISPATCH_G(Lotka3, 5)
+    default:
+        return -1000;
+    }
+}
+}  // namespace cb200

@@ -1,0 +1,234 @@
+"""ctypes binding of libcorleone_b200.so (include/corleone_b200.h) -- the only compute path.
+
+There is deliberately no fallback: if the shared library is missing, or no CUDA device is present,
+loading / handle creation raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcorleone_b200.so")
+_lib = None
+
+WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM = 1, 2, 4, 8, 16, 32, 64
+MEM_DEVICE, PS_SOA, OUT_SOA = 1, 2, 4
+
+EXPORTS = (
+    "cb200_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_sizes",
+    "cb200_block_structure", "cb200_set_stream", "cb200_eval", "cb200_jac_structure",
+    "cb200_last_kernel_ms", "cb200_launch_count", "cb200_probe_fp64_tflops",
+)
+
+_dp = C.POINTER(C.c_double)
+_i32p = C.POINTER(C.c_int32)
+_i64p = C.POINTER(C.c_int64)
+
+
+class Desc(C.Structure):
+    _fields_ = [
+        ("struct_size", C.c_int32), ("model", C.c_int32), ("method", C.c_int32), ("steps_per_piece", C.c_int32),
+        ("nx", C.c_int32), ("np_all", C.c_int32), ("n_controls", C.c_int32), ("n_tunable_p", C.c_int32),
+        ("n_intervals", C.c_int32), ("n_quadrature", C.c_int32), ("device", C.c_int32),
+        ("fim_offset", C.c_int32), ("fim_n", C.c_int32), ("reserved", C.c_int32),
+        ("u0", _dp), ("tunable_p", _i64p), ("control_indices", _i64p), ("quadrature_indices", _i64p),
+        ("n_pieces", _i32p), ("tspans", _dp), ("index_grid", _i64p), ("n_u0", _i32p),
+        ("n_local_controls", _i32p), ("is_shooting", _i32p), ("ic_sorting", _i64p),
+        ("ic_n_constants", _i32p), ("ic_constants", _i64p), ("n_shooting_indices", _i32p),
+        ("shooting_indices", _i64p), ("model_data", _dp), ("model_data_len", C.c_int64),
+    ]
+
+
+class Out(C.Structure):
+    _fields_ = [
+        ("xend", C.c_void_p), ("sens", C.c_void_p), ("traj", C.c_void_p), ("defects_kind", C.c_void_p),
+        ("defects_stage", C.c_void_p), ("objective", C.c_void_p), ("grad", C.c_void_p), ("fim", C.c_void_p),
+        ("fim_sum", C.c_void_p), ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class Sizes(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in
+                ("nvars", "n_defects", "n_samples", "n_row", "n_sens", "n_units", "jac_nnz")]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def lib():
+    """Load libcorleone_b200.so; raises if it has not been built (python corleone.jl_b200/build.py)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise NativeError(f"{LIB_PATH} not found: build it with `python corleone.jl_b200/build.py` "
+                              "(there is no CPU fallback)")
+        L = C.CDLL(LIB_PATH)
+        L.cb200_version.restype = C.c_int
+        L.cb200_last_error.restype = C.c_char_p
+        L.cb200_create.argtypes = [C.POINTER(Desc), C.POINTER(C.c_void_p)]
+        L.cb200_destroy.argtypes = [C.c_void_p]
+        L.cb200_get_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
+        L.cb200_block_structure.argtypes = [C.c_void_p, _i64p]
+        L.cb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.cb200_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
+                                 C.POINTER(Out)]
+        L.cb200_jac_structure.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
+        L.cb200_last_kernel_ms.argtypes = [C.c_void_p]
+        L.cb200_last_kernel_ms.restype = C.c_float
+        L.cb200_launch_count.argtypes = [C.c_void_p]
+        L.cb200_launch_count.restype = C.c_int64
+        L.cb200_probe_fp64_tflops.argtypes = [C.c_int, C.c_int]
+        L.cb200_probe_fp64_tflops.restype = C.c_double
+        _lib = L
+    return _lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise NativeError(f"{what} failed ({rc}): {lib().cb200_last_error().decode()}")
+
+
+def _arr(a, dtype):
+    return np.ascontiguousarray(a, dtype=dtype)
+
+
+class NativeLayer:
+    """Owns one cb200_handle built from a layer's static tables (the reference's `st`)."""
+
+    def __init__(self, *, model_id, method, steps_per_piece, nx, np_all, u0, tunable_p, control_indices,
+                 quadrature_indices, intervals, device=0, fim_offset=0, fim_n=0, model_data=None):
+        """intervals: list of dicts with tspans [(t0,t1)...], index_grid (n_controls x M int64 1-based),
+        n_u0, n_c, is_shooting, sorting, constants, shooting_indices (all 1-based as the reference)."""
+        L = lib()
+        nact = len(control_indices)
+        keep = {}
+        d = Desc()
+        d.struct_size = C.sizeof(Desc)
+        d.model, d.method, d.steps_per_piece = model_id, method, steps_per_piece
+        d.nx, d.np_all, d.n_controls, d.n_tunable_p = nx, np_all, nact, len(tunable_p)
+        d.n_intervals, d.n_quadrature, d.device = len(intervals), len(quadrature_indices), device
+        d.fim_offset, d.fim_n = fim_offset, fim_n
+
+        def put(name, values, dtype, ptr):
+            a = _arr(values if len(values) else [0], dtype)
+            keep[name] = a
+            setattr(d, name, a.ctypes.data_as(ptr))
+
+        put("u0", u0, np.float64, _dp)
+        put("tunable_p", tunable_p, np.int64, _i64p)
+        put("control_indices", control_indices, np.int64, _i64p)
+        put("quadrature_indices", quadrature_indices, np.int64, _i64p)
+        put("n_pieces", [len(iv["tspans"]) for iv in intervals], np.int32, _i32p)
+        put("tspans", [x for iv in intervals for ts in iv["tspans"] for x in ts], np.float64, _dp)
+        ig = [np.asarray(iv["index_grid"], dtype=np.int64).reshape(nact, -1).ravel(order="F") for iv in intervals]
+        put("index_grid", np.concatenate(ig) if ig else [], np.int64, _i64p)
+        put("n_u0", [iv["n_u0"] for iv in intervals], np.int32, _i32p)
+        put("n_local_controls", [iv["n_c"] for iv in intervals], np.int32, _i32p)
+        put("is_shooting", [int(iv["is_shooting"]) for iv in intervals], np.int32, _i32p)
+        put("ic_sorting", [x for iv in intervals for x in iv["sorting"]], np.int64, _i64p)
+        put("ic_n_constants", [len(iv["constants"]) for iv in intervals], np.int32, _i32p)
+        put("ic_constants", [x for iv in intervals for x in iv["constants"]], np.int64, _i64p)
+        put("n_shooting_indices", [len(iv["shooting_indices"]) for iv in intervals], np.int32, _i32p)
+        put("shooting_indices", [x for iv in intervals for x in iv["shooting_indices"]], np.int64, _i64p)
+        if model_data is not None:
+            put("model_data", model_data, np.float64, _dp)
+            d.model_data_len = len(model_data)
+        self._h = C.c_void_p()
+        _check(L.cb200_create(C.byref(d), C.byref(self._h)), "cb200_create")
+        s = Sizes()
+        _check(L.cb200_get_sizes(self._h, C.byref(s)), "cb200_get_sizes")
+        self.sizes = s
+        self.nx, self.I, self.nvars = nx, len(intervals), int(s.nvars)
+        self.n_defects, self.n_samples, self.n_row = int(s.n_defects), int(s.n_samples), int(s.n_row)
+        self.n_sens, self.jac_nnz = int(s.n_sens), int(s.jac_nnz)
+        self.fim_n = fim_n
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            lib().cb200_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- queries
+    def block_structure(self) -> np.ndarray:
+        b = np.zeros(self.I + 1, dtype=np.int64)
+        _check(lib().cb200_block_structure(self._h, b.ctypes.data_as(_i64p)), "cb200_block_structure")
+        return b
+
+    def jac_structure(self):
+        r, c, s = (np.zeros(max(self.jac_nnz, 1), dtype=np.int64) for _ in range(3))
+        _check(lib().cb200_jac_structure(self._h, r.ctypes.data_as(_i64p), c.ctypes.data_as(_i64p),
+                                         s.ctypes.data_as(_i64p)), "cb200_jac_structure")
+        n = self.jac_nnz
+        return r[:n], c[:n], s[:n]
+
+    def set_stream(self, cuda_stream: int):
+        _check(lib().cb200_set_stream(self._h, C.c_void_p(cuda_stream)), "cb200_set_stream")
+
+    def last_kernel_ms(self) -> float:
+        return float(lib().cb200_last_kernel_ms(self._h))
+
+    def launch_count(self) -> int:
+        return int(lib().cb200_launch_count(self._h))
+
+    # ---- evaluation
+    def out_sizes(self):
+        return dict(xend=self.nx * self.I, sens=self.n_sens, traj=self.n_row * self.n_samples,
+                    defects_kind=self.n_defects, defects_stage=self.n_defects, objective=1, grad=self.nvars,
+                    fim=self.fim_n * self.fim_n)
+
+    def eval_raw(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1):
+        """Raw pointer call (host or device pointers as `flags` says). ptrs: field name -> int address."""
+        o = Out()
+        for k, v in ptrs.items():
+            setattr(o, k, v)
+        o.objective_row = objective_row
+        _check(lib().cb200_eval(self._h, C.c_void_p(ps_ptr), B, ldb, want, flags, C.byref(o)), "cb200_eval")
+
+    def eval_host(self, ps, want: int, objective_row: int = 1, fim_init=None, pinned_out: dict | None = None):
+        """ps: (B, nvars) C-contiguous float64 == a Julia nvars x B matrix. Returns dict of (B, n) arrays."""
+        ps = np.ascontiguousarray(ps, dtype=np.float64)
+        if ps.ndim == 1:
+            ps = ps[None, :]
+        B = ps.shape[0]
+        assert ps.shape[1] == self.nvars, (ps.shape, self.nvars)
+        sz = self.out_sizes()
+        fields = []
+        if want & WANT_XEND: fields.append("xend")
+        if want & WANT_SENS: fields.append("sens")
+        if want & WANT_TRAJ: fields.append("traj")
+        if want & WANT_DEFECTS: fields += ["defects_kind", "defects_stage"]
+        if want & WANT_OBJ: fields.append("objective")
+        if want & WANT_GRAD: fields.append("grad")
+        if want & WANT_FIM: fields.append("fim")
+        res = {}
+        for f in fields:
+            if pinned_out is not None and f in pinned_out:
+                res[f] = pinned_out[f]
+            else:
+                res[f] = np.empty((B, sz[f]), dtype=np.float64)
+        ptrs = {f: res[f].ctypes.data for f in fields}
+        if want & WANT_FIM:
+            res["fim_sum"] = np.zeros(sz["fim"], dtype=np.float64)
+            ptrs["fim_sum"] = res["fim_sum"].ctypes.data
+            if fim_init is not None:
+                fi = np.asfortranarray(fim_init, dtype=np.float64)
+                ptrs["fim_init"] = fi.ctypes.data
+        if self.nvars == 0:  # nothing tunable: still one candidate per row
+            ps = np.zeros((B, 1))
+        self.eval_raw(ps.ctypes.data, B, max(self.nvars, 1), want, 0, ptrs, objective_row)
+        return res
+
+
+def probe_fp64_tflops(device: int = 0, iters: int = 20000) -> float:
+    return float(lib().cb200_probe_fp64_tflops(device, iters))

@@ -1,0 +1,74 @@
+"""ODEProblem / algorithm stand-ins for the SciMLBase objects the reference layers are built from.
+
+The reference integrates arbitrary Julia closures with OrdinaryDiffEq (src/single_shooting.jl:443-453).
+Here the right-hand side is one of the models compiled into libcorleone_b200.so (csrc/models.cuh) and the
+algorithm is a fixed-tableau explicit RK run with a fixed number of steps per control piece -- the
+`adaptive=false, dt=h` mode of the reference.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+# name -> (cb200_model id, nx, np_all)
+MODEL_REGISTRY = {
+    "lotka3": (0, 3, 3),
+    "lqr": (1, 2, 3),
+    "lotka2": (2, 2, 3),
+    "lotka2_oed": (3, 9, 5),
+    "lin1d": (4, 1, 1),
+    "lin1d_oed": (5, 3, 2),
+    "dense20": (6, 20, 1),
+    "egerstedt": (7, 3, 3),
+}
+
+# base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)
+OED_AUGMENTED = {
+    "lotka2": ("lotka2_oed", (2, 3), 2),
+    "lin1d": ("lin1d_oed", (1,), 1),
+}
+
+
+@dataclass
+class ODEProblem:
+    """ODEProblem(f, u0, tspan, p): `model` names the compiled-in right-hand side."""
+    model: str
+    u0: np.ndarray
+    tspan: tuple
+    p: np.ndarray
+    model_data: np.ndarray | None = None
+    kwargs: dict = field(default_factory=dict)
+
+    def __post_init__(self):
+        if self.model not in MODEL_REGISTRY:
+            raise KeyError(f"unknown model {self.model!r}; compiled-in models: {sorted(MODEL_REGISTRY)}")
+        self.u0 = np.array(self.u0, dtype=np.float64).ravel()
+        self.p = np.array(self.p, dtype=np.float64).ravel()
+        self.tspan = (float(self.tspan[0]), float(self.tspan[1]))
+        _, nx, npar = MODEL_REGISTRY[self.model]
+        if len(self.u0) != nx or len(self.p) != npar:
+            raise ValueError(f"model {self.model!r} has {nx} states and {npar} parameters; "
+                             f"got {len(self.u0)} and {len(self.p)}")
+        if self.model_data is not None:
+            self.model_data = np.ascontiguousarray(self.model_data, dtype=np.float64).ravel()
+
+    def remake(self, **kw):
+        d = dict(model=self.model, u0=self.u0.copy(), tspan=self.tspan, p=self.p.copy(),
+                 model_data=self.model_data, kwargs=dict(self.kwargs))
+        d.update(kw)
+        return ODEProblem(**d)
+
+
+@dataclass(frozen=True)
+class Tsit5:
+    """Tsitouras 5(4), fixed step: `steps_per_piece` steps h = (t1-t0)/K on every control piece."""
+    steps_per_piece: int = 1
+    method_id: int = 0
+
+
+@dataclass(frozen=True)
+class RK4:
+    """Classical Runge-Kutta 4, fixed step."""
+    steps_per_piece: int = 1
+    method_id: int = 1

@@ -1,0 +1,194 @@
+/*
+ * corleone_b200.h -- C ABI of libcorleone_b200.so: the B200-native replacement of Corleone.jl's
+ * data-parallel hot path (batched integration of every multiple-shooting interval with forward
+ * sensitivities, for a whole batch of candidates).
+ *
+ * The reference has no FFI; its plug-in points are Julia dispatch hooks.  Each entry point below names
+ * the reference code it replaces (paths relative to SciML/Corleone.jl):
+ *
+ *   cb200_create   <- LuxCore.initialstates(rng, layer): the static `st` tables
+ *                     (src/single_shooting.jl:274-352, src/multiple_shooting.jl:107-116) are passed in
+ *                     as Julia produced them (Int64, 1-based) and uploaded once.
+ *   cb200_eval     <- (shooting::MultipleShootingLayer)(u0, ps, st) = _parallel_solve + Trajectory merge
+ *                     (src/multiple_shooting.jl:118-182), i.e. mythreadmap over intervals
+ *                     (src/Corleone.jl:22-24) of _sequential_solve (src/single_shooting.jl:421-471),
+ *                     for B candidates at once; plus what the NLP closures derive from the trajectory:
+ *                     objective (src/dynprob.jl:68-73), shooting_constraints! (src/multiple_shooting.jl:
+ *                     289-295), the ForwardDiff derivatives of both (src/dynprob.jl:143-164), and the
+ *                     continuous Fisher information (lib/CorleoneOED/src/oed.jl:381-398).
+ *   cb200_jac_structure <- sparsity of cons_j in get_block_structure order (src/multiple_shooting.jl:320-328).
+ *   cb200_destroy, cb200_last_error, cb200_version, cb200_set_stream: lifetime / plumbing (new).
+ *
+ * Conventions
+ *   - plain C, no exceptions cross the boundary; every call returns 0 or a negative cb200_status;
+ *     cb200_last_error() gives the thread-local message.
+ *   - the caller owns every buffer it passes; the library never retains a caller pointer after return
+ *     and owns all device memory behind the opaque handle.
+ *   - there is NO CPU fallback: without a CUDA device cb200_create fails with CB200_ERR_CUDA.
+ *   - all floating point data are FP64; index tables are Int64 and 1-based exactly as Julia holds them.
+ */
+#ifndef CORLEONE_B200_H
+#define CORLEONE_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CB200_VERSION 100
+
+typedef enum {
+    CB200_OK = 0,
+    CB200_ERR_ARG = -1,      /* bad descriptor / argument */
+    CB200_ERR_CUDA = -2,     /* CUDA runtime failure (message has the CUDA error string) */
+    CB200_ERR_UNSUPPORTED = -3, /* model/method/feature combination not compiled in */
+    CB200_ERR_NOMEM = -4
+} cb200_status;
+
+/* compiled-in model registry (the reference integrates arbitrary Julia closures; a C-ABI CUDA library
+ * cannot -- see DESIGN.md "user RHS") */
+typedef enum {
+    CB200_MODEL_LOTKA3 = 0,     /* Lotka fishing + Lagrange state; examples/lotka_fishing_optimal_control/main.jl:38-42 */
+    CB200_MODEL_LQR = 1,        /* examples/linear_quadratic/main.jl:45-50 */
+    CB200_MODEL_LOTKA2 = 2,     /* lib/CorleoneOED/examples/lotka_oed/main.jl:61-65 */
+    CB200_MODEL_LOTKA2_OED = 3, /* [x; G; F_triu] augmentation, params=[2,3], observed=u[1:2] (augmentation.jl:131-253) */
+    CB200_MODEL_LIN1D = 4,      /* lib/CorleoneOED/test/core/1d_oed.jl:11-13 */
+    CB200_MODEL_LIN1D_OED = 5,
+    CB200_MODEL_DENSE20 = 6,    /* synthetic BASELINE config 4: x' = W x - x^3 + b u */
+    CB200_MODEL_EGERSTEDT = 7   /* test/core/local_controls.jl:46-52 */
+} cb200_model;
+
+typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;
+
+/*
+ * Static description of one layer == the reference's `st` (one entry per shooting interval; a
+ * SingleShootingLayer is n_intervals == 1).  Per-interval arrays are concatenated in interval order.
+ */
+typedef struct {
+    int32_t struct_size;        /* sizeof(cb200_desc), for ABI checking */
+    int32_t model;              /* cb200_model */
+    int32_t method;             /* cb200_method: alg of the layer (Tsit5() / RK4()) */
+    int32_t steps_per_piece;    /* K: fixed steps per control piece, h = (t1-t0)/K  (adaptive=false, dt=h) */
+    int32_t nx;                 /* length(problem.u0) */
+    int32_t np_all;             /* length(problem.p), controls included */
+    int32_t n_controls;         /* active controls = rows of index_grid */
+    int32_t n_tunable_p;        /* length(ps.p) */
+    int32_t n_intervals;        /* I */
+    int32_t n_quadrature;       /* length(quadrature_indices) */
+    int32_t device;             /* CUDA ordinal */
+    int32_t fim_offset;         /* 1-based state index of the first F_triu state, 0 = no Fisher block */
+    int32_t fim_n;              /* n: F is n x n, stored as n(n+1)/2 column-major upper-triangle states */
+    int32_t reserved;
+    const double *u0;                   /* [nx] problem.u0 (fixval of the first interval, single_shooting.jl:359) */
+    const int64_t *tunable_p;           /* [n_tunable_p] 1-based indices into problem.p (single_shooting.jl:109) */
+    const int64_t *control_indices;     /* [n_controls] 1-based p index per control, user order (layer.control_indices) */
+    const int64_t *quadrature_indices;  /* [n_quadrature] 1-based */
+    /* per interval */
+    const int32_t *n_pieces;            /* [I] M_i = length(st.tspans) (chunks flattened) */
+    const double *tspans;               /* [sum M_i][2] st.tspans as (t0,t1) pairs */
+    const int64_t *index_grid;          /* [sum n_controls*M_i] st.index_grid, column-major n_controls x M_i, 1-based */
+    const int32_t *n_u0;                /* [I] length(ps.interval_i.u0) */
+    const int32_t *n_local_controls;    /* [I] length(ps.interval_i.controls) */
+    const int32_t *is_shooting;         /* [I] shooting_layer flag (fixval = zeros) */
+    const int64_t *ic_sorting;          /* [I*nx] InitialConditionRemaker.sorting, 1-based */
+    const int32_t *ic_n_constants;      /* [I] */
+    const int64_t *ic_constants;        /* [sum ic_n_constants] InitialConditionRemaker.constants, 1-based */
+    const int32_t *n_shooting_indices;  /* [I] */
+    const int64_t *shooting_indices;    /* [sum] st.shooting_indices, 1-based over [states; controls] */
+    const double *model_data;           /* model constants (DENSE20: W row-major 20x20, then b[20]) or NULL */
+    int64_t model_data_len;
+} cb200_desc;
+
+/* what cb200_eval should produce (bit mask) */
+#define CB200_WANT_XEND 0x001u      /* raw end state of every interval */
+#define CB200_WANT_SENS 0x002u      /* d x_end(i) / d (u0_i, p_i, controls_i) */
+#define CB200_WANT_TRAJ 0x004u      /* merged Trajectory samples, quadratures accumulated */
+#define CB200_WANT_DEFECTS 0x008u   /* shooting constraints, both orderings */
+#define CB200_WANT_OBJ 0x010u       /* last(traj)[objective_row] per candidate */
+#define CB200_WANT_GRAD 0x020u      /* d objective / d ps */
+#define CB200_WANT_FIM 0x040u       /* F_init + symmetric F(t_end) per candidate, and its sum over candidates */
+
+/* memory / layout flags */
+#define CB200_MEM_DEVICE 0x1u       /* ps and all outputs are device pointers (default: host pointers) */
+#define CB200_PS_SOA 0x2u           /* ps is variable-major: ps[v*ldb + b]   (default candidate-major
+                                       ps[b*ldb + v], i.e. a Julia nvars x B Matrix with leading dim ldb) */
+#define CB200_OUT_SOA 0x4u          /* outputs are quantity-major out[q*B + b] (default candidate-major
+                                       out[b*n + q], i.e. Julia n x B matrices) */
+
+/*
+ * Output buffers; NULL = not wanted.  Sizes in doubles, n = the leading count, per candidate:
+ *   xend           n = nx*I            [k + nx*i]
+ *   sens           n = cb200_sizes.n_sens   rows ordered interval, then direction d (order u0,p,controls
+ *                                           of the interval = its block of the flat ps), then state k
+ *   traj           n = nrow*nsamples   [r + nrow*sample], nrow = nx + n_controls (single_shooting.jl:456)
+ *   defects_kind   n = n_defects       shooting_constraints order  (multiple_shooting.jl:281-295)
+ *   defects_stage  n = n_defects       stage_ordered_shooting_constraints order (:229,249-252)
+ *   objective      n = 1
+ *   grad           n = nvars
+ *   fim            n = fim_n*fim_n     column-major symmetric matrix
+ *   fim_sum        fim_n*fim_n doubles total: sum over the B candidates of `fim` (+ nothing else)
+ */
+typedef struct {
+    double *xend;
+    double *sens;
+    double *traj;
+    double *defects_kind;
+    double *defects_stage;
+    double *objective;
+    double *grad;
+    double *fim;
+    double *fim_sum;
+    const double *fim_init;     /* [fim_n*fim_n] st.F_init or NULL = zeros (oed.jl:309-315) */
+    int32_t objective_row;      /* 1-based row of a trajectory sample: state k or nx + control r */
+    int32_t reserved;
+} cb200_out;
+
+typedef struct {
+    int64_t nvars;          /* LuxCore.parameterlength(layer) */
+    int64_t n_defects;      /* get_number_of_shooting_constraints */
+    int64_t n_samples;      /* samples of the merged trajectory */
+    int64_t n_row;          /* nx + n_controls */
+    int64_t n_sens;         /* sum_i nx * ns_i */
+    int64_t n_units;        /* I: (interval) units per candidate */
+    int64_t jac_nnz;        /* nonzeros of d(shooting_constraints)/d(ps) */
+} cb200_sizes;
+
+typedef struct cb200_handle cb200_handle;
+
+int cb200_version(void);
+const char *cb200_last_error(void);
+
+int cb200_create(const cb200_desc *desc, cb200_handle **out);
+int cb200_destroy(cb200_handle *h);
+int cb200_get_sizes(const cb200_handle *h, cb200_sizes *sizes);
+
+/* block offsets of the flat variable vector, I+1 entries, 0-based offsets as get_block_structure returns */
+int cb200_block_structure(const cb200_handle *h, int64_t *blocks);
+
+/* optional: run on a caller-provided cudaStream_t (default: a private non-blocking stream). */
+int cb200_set_stream(cb200_handle *h, void *cuda_stream);
+
+/* Evaluate B candidates.  ldb: leading dimension of ps (>= nvars candidate-major, >= B variable-major).
+ * Returns after the results are in the caller's buffers (host pointers) or after the work has been
+ * enqueued on the handle's stream (device pointers). */
+int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t ldb, uint32_t want, uint32_t flags,
+               const cb200_out *out);
+
+/* Sparsity of d(shooting_constraints kind-major)/d(ps): nnz triplets (1-based row, col) and, per entry,
+ * src >= 0: 0-based row into `sens`;  src == -1: constant +1;  src == -2: constant -1. */
+int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int64_t *src);
+
+/* Device time of the last cb200_eval's integration kernel(s) in milliseconds (CUDA events on the
+ * handle's stream); < 0 if none. */
+float cb200_last_kernel_ms(const cb200_handle *h);
+/* kernels launched by this handle since creation */
+int64_t cb200_launch_count(const cb200_handle *h);
+
+/* FP64 FMA-chain peak probe: runs `iters` dependent DFMA chains on every SM, returns TFLOP/s (<0 on error) */
+double cb200_probe_fp64_tflops(int device, int iters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

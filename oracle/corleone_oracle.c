@@ -1,0 +1,876 @@
+/*
+ * corleone_oracle.c -- CPU restatement of Corleone.jl's shooting hot path (see corleone_oracle.h).
+ * TEST INFRASTRUCTURE ONLY: checker and CPU baseline, never the product path.
+ *
+ * What is restated, and from where (paths relative to /root/reference):
+ *   control grid restriction / index grid / tspans   src/local_controls.jl:53-57,120-195
+ *   InitialConditionRemaker, parameter scatter       src/single_shooting.jl:255-270,306-323,357-362
+ *   piece loop and save semantics                    src/single_shooting.jl:421-471
+ *   interval split, merge, defects, quadratures      src/multiple_shooting.jl:86-95,139-182,229-310
+ *   default / forward node initialisation            src/multiple_shooting.jl:45-55, src/node_initialization.jl:152-170
+ *   OED augmentation [x; G; F_triu]                  lib/CorleoneOED/src/augmentation.jl:131-159,206-253
+ * Third-party arithmetic the reference calls but does not contain:
+ *   OrdinaryDiffEqTsit5 (Project.toml:44, compat "1, 2", unpinned -- no Manifest): explicit 7-stage FSAL
+ *   Tsitouras 5(4) scheme, published tableau (Tsitouras 2011); run with adaptive=false, so only the
+ *   propagation weights are used.  ForwardDiff (dual numbers through `solve`): restated as `dual` below.
+ */
+#include "corleone_oracle.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdio.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+#include <time.h>
+
+/* ------------------------------------------------------------------ duals */
+typedef struct {
+    double v;
+    double d[CO_ND];
+} dual;
+
+static _Thread_local int g_nd = 0;
+
+static inline dual dconst(double c)
+{
+    dual r;
+    r.v = c;
+    for (int k = 0; k < g_nd; k++) r.d[k] = 0.0;
+    return r;
+}
+static inline dual dadd(dual a, dual b)
+{
+    dual r;
+    r.v = a.v + b.v;
+    for (int k = 0; k < g_nd; k++) r.d[k] = a.d[k] + b.d[k];
+    return r;
+}
+static inline dual dsub(dual a, dual b)
+{
+    dual r;
+    r.v = a.v - b.v;
+    for (int k = 0; k < g_nd; k++) r.d[k] = a.d[k] - b.d[k];
+    return r;
+}
+static inline dual dmul(dual a, dual b)
+{
+    dual r;
+    r.v = a.v * b.v;
+    for (int k = 0; k < g_nd; k++) r.d[k] = a.d[k] * b.v + a.v * b.d[k];
+    return r;
+}
+static inline dual dscale(dual a, double c)
+{
+    dual r;
+    r.v = a.v * c;
+    for (int k = 0; k < g_nd; k++) r.d[k] = a.d[k] * c;
+    return r;
+}
+static inline dual daddc(dual a, double c)
+{
+    a.v += c;
+    return a;
+}
+static inline dual dneg(dual a) { return dscale(a, -1.0); }
+/* r += c * a */
+static inline void daxpy(dual *r, double c, const dual *a)
+{
+    r->v += c * a->v;
+    for (int k = 0; k < g_nd; k++) r->d[k] += c * a->d[k];
+}
+
+/* ------------------------------------------------------------------ models */
+typedef struct {
+    int model;
+    const double *data; /* dense20: W row-major 20x20, then b[20] */
+} model_ctx;
+
+/* Lotka fishing with Lagrange term; test/core/multiple_shooting.jl:11-17 */
+static void rhs_lotka3(const dual *u, const dual *p, dual *du)
+{
+    dual u12 = dmul(u[0], u[1]);
+    du[0] = dsub(dsub(u[0], dmul(p[1], u12)), dscale(dmul(p[0], u[0]), 0.4));
+    du[1] = dsub(dadd(dneg(u[1]), dmul(p[2], u12)), dscale(dmul(p[0], u[1]), 0.2));
+    dual a = daddc(u[0], -1.0), b = daddc(u[1], -1.0);
+    du[2] = dadd(dmul(a, a), dmul(b, b));
+}
+/* lib/CorleoneOED/test/core/lotka_oed.jl:15-20 */
+static void rhs_lotka2(const dual *u, const dual *p, dual *du)
+{
+    dual u12 = dmul(u[0], u[1]);
+    du[0] = dsub(dsub(u[0], dmul(p[1], u12)), dscale(dmul(p[0], u[0]), 0.4));
+    du[1] = dsub(dadd(dneg(u[1]), dmul(p[2], u12)), dscale(dmul(p[0], u[1]), 0.2));
+}
+/* Jacobians of lotka2: Jx row-major 2x2; Jp columns for params [2,3] (row-major 2x2) */
+static void jac_lotka2(const dual *u, const dual *p, dual *Jx, dual *Jp)
+{
+    /* f1 = u1 - p2 u1 u2 - 0.4 p1 u1 ; f2 = -u2 + p3 u1 u2 - 0.2 p1 u2 */
+    Jx[0] = dsub(dsub(dconst(1.0), dmul(p[1], u[1])), dscale(p[0], 0.4));
+    Jx[1] = dneg(dmul(p[1], u[0]));
+    Jx[2] = dmul(p[2], u[1]);
+    Jx[3] = dsub(daddc(dmul(p[2], u[0]), -1.0), dscale(p[0], 0.2));
+    dual u12 = dmul(u[0], u[1]);
+    Jp[0] = dneg(u12);
+    Jp[1] = dconst(0.0);
+    Jp[2] = dconst(0.0);
+    Jp[3] = u12;
+}
+/* examples/linear_quadratic/main.jl:45-50 ; p = (a, b, u) */
+static void rhs_lqr(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dadd(dmul(p[0], x[0]), dmul(p[1], p[2]));
+    dual e = daddc(x[0], -3.0);
+    du[1] = dadd(dscale(dmul(e, e), 10.0), dscale(dmul(p[2], p[2]), 0.1));
+}
+/* lib/CorleoneOED/test/core/1d_oed.jl:11-13 */
+static void rhs_lin1d(const dual *u, const dual *p, dual *du) { du[0] = dmul(p[0], u[0]); }
+static void jac_lin1d(const dual *u, const dual *p, dual *Jx, dual *Jp)
+{
+    Jx[0] = p[0];
+    Jp[0] = u[0];
+}
+/* test/core/local_controls.jl:46-52 */
+static void rhs_egerstedt(const dual *u, const dual *p, dual *du)
+{
+    dual x = u[0], y = u[1];
+    dual xpy = dadd(x, y), xmy = dsub(x, y);
+    du[0] = dadd(dadd(dneg(dmul(x, p[0])), dmul(xpy, p[1])), dmul(xmy, p[2]));
+    dual x2y = dadd(x, dscale(y, 2.0)), xm2y = dsub(x, dscale(y, 2.0));
+    du[1] = dadd(dadd(dmul(x2y, p[0]), dmul(xm2y, p[1])), dmul(xpy, p[2]));
+    du[2] = dadd(dmul(x, x), dmul(y, y));
+}
+/* synthetic BASELINE config 4: x' = W x - x.^3 + b u ; p = (u) */
+static void rhs_dense20(const dual *x, const dual *p, dual *du, const double *data)
+{
+    const double *W = data, *b = data + 400;
+    for (int i = 0; i < 20; i++) {
+        dual acc = dscale(p[0], b[i]);
+        for (int j = 0; j < 20; j++) daxpy(&acc, W[i * 20 + j], &x[j]);
+        dual x3 = dmul(dmul(x[i], x[i]), x[i]);
+        du[i] = dsub(acc, x3);
+    }
+}
+
+/*
+ * OED augmentation, ContinuousSampled non-fixed variant (augmentation.jl:206-253 with measurements):
+ *   state  = [x (nx); vec(G) column-major nx x nF; F[triu] column-major]           (:239, selector :211)
+ *   params = [base p; w_1..w_nobs]                                                 (:228-230)
+ *   G'     = f_x G + f_p[:, params]                                                (:147-154)
+ *   F'     = sum_i w_i (h_x[i,:] G)' (h_x[i,:] G), upper triangle                  (:222-233)
+ * observed = leading nobs states (u[1:2] for Lotka, [u[1]] for the 1-D problem), so h_x rows are unit rows.
+ */
+typedef void (*rhs_fn)(const dual *, const dual *, dual *);
+typedef void (*jac_fn)(const dual *, const dual *, dual *, dual *);
+static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, const dual *u, const dual *p,
+                    dual *du)
+{
+    dual Jx[CO_MAX_NX], Jp[CO_MAX_NX];
+    f(u, p, du);
+    jac(u, p, Jx, Jp);
+    const dual *G = u + nx; /* G[r + nx*c] */
+    dual *dG = du + nx;
+    for (int c = 0; c < nF; c++)
+        for (int r = 0; r < nx; r++) {
+            dual acc = Jp[r * nF + c];
+            for (int k = 0; k < nx; k++) acc = dadd(acc, dmul(Jx[r * nx + k], G[k + nx * c]));
+            dG[r + nx * c] = acc;
+        }
+    dual *dF = du + nx + nx * nF;
+    const dual *w = p + npb;
+    int q = 0;
+    for (int b = 0; b < nF; b++)
+        for (int a = 0; a <= b; a++) {
+            dual acc = dconst(0.0);
+            for (int i = 0; i < nobs; i++) acc = dadd(acc, dmul(w[i], dmul(G[i + nx * a], G[i + nx * b])));
+            dF[q++] = acc;
+        }
+}
+
+static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du)
+{
+    switch (m->model) {
+    case CO_LOTKA3: rhs_lotka3(u, p, du); break;
+    case CO_LQR: rhs_lqr(u, p, du); break;
+    case CO_LOTKA2: rhs_lotka2(u, p, du); break;
+    case CO_LOTKA2_OED: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, u, p, du); break;
+    case CO_LIN1D: rhs_lin1d(u, p, du); break;
+    case CO_LIN1D_OED: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, u, p, du); break;
+    case CO_DENSE20: rhs_dense20(u, p, du, m->data); break;
+    case CO_EGERSTEDT: rhs_egerstedt(u, p, du); break;
+    default: break;
+    }
+}
+
+/* ------------------------------------------------------------------ fixed-step RK */
+/* Tsit5 propagation tableau (OrdinaryDiffEqTsit5 constant cache) */
+static const double TS_A[7][6] = {
+    {0, 0, 0, 0, 0, 0},
+    {0.161, 0, 0, 0, 0, 0},
+    {-0.008480655492356989, 0.335480655492357, 0, 0, 0, 0},
+    {2.8971530571054935, -6.359448489975075, 4.3622954328695815, 0, 0, 0},
+    {5.325864828439257, -11.748883564062828, 7.4955393428898365, -0.09249506636175525, 0, 0},
+    {5.86145544294642, -12.92096931784711, 8.159367898576159, -0.071584973281401, -0.028269050394068383, 0},
+    {0.09646076681806523, 0.01, 0.4798896504144996, 1.379008574103742, -3.290069515436081,
+     2.324710524099774}};
+
+/* one control piece: K steps of h = (t1-t0)/K; k1 is re-evaluated at the piece start because every piece is
+ * a fresh `solve` in the reference (src/single_shooting.jl:443-453); FSAL inside the piece. */
+static void integrate_piece(const model_ctx *m, int nx, dual *x, const dual *p, double t0, double t1, int K,
+                            int method)
+{
+    dual k[7][CO_MAX_NX], tmp[CO_MAX_NX];
+    double h = (t1 - t0) / (double)K;
+    if (method == CO_TSIT5) {
+        model_rhs(m, x, p, k[0]);
+        for (int s = 0; s < K; s++) {
+            for (int st = 1; st < 7; st++) {
+                for (int c = 0; c < nx; c++) {
+                    dual acc = x[c];
+                    for (int j = 0; j < st; j++) daxpy(&acc, h * TS_A[st][j], &k[j][c]);
+                    tmp[c] = acc;
+                }
+                if (st == 6)
+                    for (int c = 0; c < nx; c++) x[c] = tmp[c];
+                model_rhs(m, tmp, p, k[st]);
+            }
+            for (int c = 0; c < nx; c++) k[0][c] = k[6][c];
+        }
+    } else { /* classical RK4 */
+        for (int s = 0; s < K; s++) {
+            model_rhs(m, x, p, k[0]);
+            for (int c = 0; c < nx; c++) {
+                tmp[c] = x[c];
+                daxpy(&tmp[c], 0.5 * h, &k[0][c]);
+            }
+            model_rhs(m, tmp, p, k[1]);
+            for (int c = 0; c < nx; c++) {
+                tmp[c] = x[c];
+                daxpy(&tmp[c], 0.5 * h, &k[1][c]);
+            }
+            model_rhs(m, tmp, p, k[2]);
+            for (int c = 0; c < nx; c++) {
+                tmp[c] = x[c];
+                daxpy(&tmp[c], h, &k[2][c]);
+            }
+            model_rhs(m, tmp, p, k[3]);
+            for (int c = 0; c < nx; c++) {
+                daxpy(&x[c], h / 6.0, &k[0][c]);
+                daxpy(&x[c], h / 3.0, &k[1][c]);
+                daxpy(&x[c], h / 3.0, &k[2][c]);
+                daxpy(&x[c], h / 6.0, &k[3][c]);
+            }
+        }
+    }
+}
+
+/* ------------------------------------------------------------------ index logic */
+int co_restrict_grid(const double *t, int nt, double t0, double t1, int *pos)
+{
+    int n = 0;
+    for (int k = 0; k < nt; k++)
+        if (t0 <= t[k] && t[k] < t1) pos[n++] = k; /* local_controls.jl:55 */
+    return n;
+}
+
+static int cmp_double(const void *a, const void *b)
+{
+    double x = *(const double *)a, y = *(const double *)b;
+    return (x > y) - (x < y);
+}
+
+/* Julia searchsortedlast: last index k (1-based) with a[k] <= x, 0 if none */
+static int searchsortedlast(const double *a, int n, double x)
+{
+    int lo = 0, hi = n + 1;
+    while (lo < hi - 1) {
+        int mid = lo + ((hi - lo) >> 1);
+        if (x < a[mid - 1])
+            hi = mid;
+        else
+            lo = mid;
+    }
+    return lo;
+}
+/* Julia clamp(x, lo, hi) = ifelse(x > hi, hi, ifelse(x < lo, lo, x)) */
+static int64_t jl_clamp(int64_t x, int64_t lo, int64_t hi) { return x > hi ? hi : (x < lo ? lo : x); }
+
+int co_build_index_grid(int nc, const double *const *t, const int *nt, double t0, double t1, int64_t *idx,
+                        double *grid, int cap_pieces)
+{
+    int total = 2;
+    for (int i = 0; i < nc; i++) total += nt[i];
+    double *all = (double *)malloc(sizeof(double) * (size_t)total);
+    double **ts = (double **)malloc(sizeof(double *) * (size_t)(nc > 0 ? nc : 1));
+    int *nts = (int *)malloc(sizeof(int) * (size_t)(nc > 0 ? nc : 1));
+    int n = 0;
+    for (int i = 0; i < nc; i++) {
+        ts[i] = (double *)malloc(sizeof(double) * (size_t)(nt[i] > 0 ? nt[i] : 1));
+        nts[i] = 0;
+        for (int k = 0; k < nt[i]; k++)
+            if (t0 <= t[i][k] && t[i][k] < t1) {
+                ts[i][nts[i]++] = t[i][k];
+                all[n++] = t[i][k];
+            }
+    }
+    all[n++] = t0;
+    all[n++] = t1;
+    qsort(all, (size_t)n, sizeof(double), cmp_double);
+    int ng = 0;
+    for (int k = 0; k < n; k++) { /* unique! then filter!(isfinite) (:153) */
+        if (k > 0 && all[k] == all[k - 1]) continue;
+        if (!isfinite(all[k])) continue;
+        if (ng < cap_pieces + 1) grid[ng] = all[k];
+        ng++;
+    }
+    int M = ng - 1;
+    if (M > cap_pieces) {
+        M = -M; /* caller's buffers too small */
+        goto done;
+    }
+    for (int i = 0; i < nc; i++)
+        for (int j = 0; j < M; j++)
+            idx[i + (size_t)nc * j] = jl_clamp(searchsortedlast(ts[i], nts[i], grid[j]), 1, nts[i]); /* :156-159 */
+    for (int i = 1; i < nc; i++) { /* :162-168, uses the already offset previous row */
+        int64_t mx = idx[(i - 1)];
+        for (int j = 1; j < M; j++)
+            if (idx[(i - 1) + (size_t)nc * j] > mx) mx = idx[(i - 1) + (size_t)nc * j];
+        if (M == 0) mx = 0;
+        for (int j = 0; j < M; j++) idx[i + (size_t)nc * j] += mx;
+    }
+    if (nc > 0 && M > 0) { /* :172 */
+        int64_t mn = idx[0];
+        for (int q = 0; q < nc * M; q++)
+            if (idx[q] < mn) mn = idx[q];
+        for (int q = 0; q < nc * M; q++) idx[q] -= mn - 1;
+    }
+done:
+    for (int i = 0; i < nc; i++) free(ts[i]);
+    free(ts);
+    free(nts);
+    free(all);
+    return M;
+}
+
+int co_subvector_indices(int M, int L, int *ss)
+{
+    int N = M / L, n = 0;
+    for (int i = 1; i <= N; i++) {
+        ss[2 * n] = (i - 1) * L + 1;
+        ss[2 * n + 1] = i * L;
+        n++;
+    }
+    if (M - N * L > 0) {
+        ss[2 * n] = N * L + 1;
+        ss[2 * n + 1] = M;
+        n++;
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------------ layer */
+typedef struct {
+    double t0, t1;
+    int shooting; /* i > 1 */
+    int M;
+    double *grid;  /* M+1 */
+    int64_t *idx;  /* nact x M col-major, 1-based */
+    int n_u0, n_c; /* lengths of ps.u0 and ps.controls of this interval */
+    int n_const;
+    int ic_constants[CO_MAX_NX]; /* 1-based */
+    int ic_sorting[CO_MAX_NX];   /* 1-based */
+    int n_sidx;
+    int sidx[CO_MAX_NX + CO_MAX_CTRL]; /* shooting_indices, 1-based over [states; controls] */
+    int var_off;                       /* offset of the block in the flat ps */
+    double *c_init;                    /* default local controls */
+} interval;
+
+struct co_layer {
+    model_ctx m;
+    int nx, np_all;
+    double u0[CO_MAX_NX], p0[CO_MAX_NP];
+    double tspan[2];
+    int nact;                     /* active controls (control_indices <= np_all), user order kept */
+    int cidx[CO_MAX_CTRL];        /* 1-based p index of active control r */
+    int ntp;                      /* tunable parameters */
+    int tunable_p[CO_MAX_NP];     /* 1-based, ascending: setdiff(eachindex(p), control_indices) */
+    int pmap_kind[CO_MAX_NP];     /* p_full[q]: 0 -> ps.p[pmap_idx], 1 -> controls_j[pmap_idx] (scatter A,B :306-323) */
+    int pmap_idx[CO_MAX_NP];
+    int n_tic, tic[CO_MAX_NX];
+    int nquad, quad[CO_MAX_NX];
+    int I;
+    interval *iv;
+    int nvars, ndef, nsamples;
+};
+
+static int in_list(const int *l, int n, int v)
+{
+    for (int k = 0; k < n; k++)
+        if (l[k] == v) return 1;
+    return 0;
+}
+
+/* sortperm(vcat(constants, tunables)) -- stable, all entries distinct */
+static void sortperm_cat(const int *a, int na, const int *b, int nb, int *perm)
+{
+    int n = na + nb, v[2 * CO_MAX_NX];
+    for (int k = 0; k < na; k++) v[k] = a[k];
+    for (int k = 0; k < nb; k++) v[na + k] = b[k];
+    for (int k = 0; k < n; k++) perm[k] = k + 1;
+    for (int i = 1; i < n; i++) { /* insertion sort by key */
+        int pi = perm[i], j = i - 1;
+        while (j >= 0 && v[perm[j] - 1] > v[pi - 1]) {
+            perm[j + 1] = perm[j];
+            j--;
+        }
+        perm[j + 1] = pi;
+    }
+}
+
+co_layer *co_layer_create(const co_problem *P)
+{
+    co_layer *L = (co_layer *)calloc(1, sizeof(co_layer));
+    L->m.model = P->model;
+    L->m.data = P->model_data;
+    L->nx = P->nx;
+    L->np_all = P->np_all;
+    memcpy(L->u0, P->u0, sizeof(double) * (size_t)P->nx);
+    memcpy(L->p0, P->p0, sizeof(double) * (size_t)P->np_all);
+    L->tspan[0] = P->tspan[0];
+    L->tspan[1] = P->tspan[1];
+    L->n_tic = P->n_tunable_ic;
+    for (int k = 0; k < L->n_tic; k++) L->tic[k] = P->tunable_ic[k];
+    L->nquad = P->nquad;
+    for (int k = 0; k < L->nquad; k++) L->quad[k] = P->quad_idx[k];
+
+    /* active controls: control_indices .<= lastindex(p_vec) (single_shooting.jl:302-304) */
+    const double *act_t[CO_MAX_CTRL], *act_u[CO_MAX_CTRL];
+    int act_nt[CO_MAX_CTRL];
+    int allc[CO_MAX_CTRL];
+    for (int r = 0; r < P->ncontrols; r++) {
+        allc[r] = P->control_indices[r];
+        if (P->control_indices[r] <= P->np_all) {
+            L->cidx[L->nact] = P->control_indices[r];
+            act_t[L->nact] = P->ctrl_t[r];
+            act_u[L->nact] = P->ctrl_u ? P->ctrl_u[r] : NULL;
+            act_nt[L->nact] = P->ctrl_nt[r];
+            L->nact++;
+        }
+    }
+    /* tunable_p = setdiff(eachindex(p_vec), control_indices) (:109); scatter matrices A, B (:306-318):
+     * column ids are handed out in ascending p index, for parameters and for controls alike */
+    int pid = 0, cid = 0;
+    for (int q = 1; q <= P->np_all; q++) {
+        if (in_list(L->cidx, L->nact, q)) {
+            L->pmap_kind[q - 1] = 1;
+            L->pmap_idx[q - 1] = cid++;
+        } else {
+            L->pmap_kind[q - 1] = 0;
+            L->pmap_idx[q - 1] = pid++;
+            L->tunable_p[L->ntp++] = q;
+        }
+    }
+    (void)allc;
+
+    /* shooting intervals: sort!(unique!(vcat(tpoints, tspan))) -> consecutive pairs (multiple_shooting.jl:86-90) */
+    double pts[4096];
+    int np = 0;
+    for (int k = 0; k < P->n_shoot; k++) pts[np++] = P->shoot_pts[k];
+    pts[np++] = P->tspan[0];
+    pts[np++] = P->tspan[1];
+    qsort(pts, (size_t)np, sizeof(double), cmp_double);
+    int nu = 0;
+    for (int k = 0; k < np; k++)
+        if (k == 0 || pts[k] != pts[k - 1]) pts[nu++] = pts[k];
+    L->I = (P->n_shoot > 0) ? nu - 1 : 1;
+    L->iv = (interval *)calloc((size_t)L->I, sizeof(interval));
+
+    int off = 0;
+    for (int i = 0; i < L->I; i++) {
+        interval *it = &L->iv[i];
+        it->t0 = (P->n_shoot > 0) ? pts[i] : P->tspan[0];
+        it->t1 = (P->n_shoot > 0) ? pts[i + 1] : P->tspan[1];
+        it->shooting = (i > 0);
+        /* pieces */
+        if (L->nact > 0) {
+            int cap = 2;
+            for (int r = 0; r < L->nact; r++) cap += act_nt[r];
+            it->grid = (double *)malloc(sizeof(double) * (size_t)(cap + 1));
+            it->idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(L->nact * cap));
+            it->M = co_build_index_grid(L->nact, act_t, act_nt, it->t0, it->t1, it->idx, it->grid, cap);
+        } else {
+            /* no controls: tspans = (problem.tspan,) -- the *problem's* span, also on sub-intervals
+             * (single_shooting.jl:329-332; reference quirk kept) */
+            it->M = 1;
+            it->grid = (double *)malloc(sizeof(double) * 2);
+            it->grid[0] = P->tspan[0];
+            it->grid[1] = P->tspan[1];
+            it->idx = NULL;
+        }
+        /* InitialConditionRemaker (:284-295) */
+        int tun[CO_MAX_NX], ntun = 0;
+        it->n_const = 0;
+        if (!it->shooting) {
+            for (int k = 1; k <= L->nx; k++)
+                if (!in_list(L->tic, L->n_tic, k)) it->ic_constants[it->n_const++] = k;
+            for (int k = 0; k < L->n_tic; k++) tun[ntun++] = L->tic[k];
+        } else {
+            for (int k = 0; k < L->nquad; k++) it->ic_constants[it->n_const++] = L->quad[k];
+            for (int k = 1; k <= L->nx; k++)
+                if (!in_list(L->quad, L->nquad, k)) tun[ntun++] = k;
+        }
+        sortperm_cat(it->ic_constants, it->n_const, tun, ntun, it->ic_sorting);
+        it->n_u0 = ntun;
+        /* local controls (collect_local_controls, local_controls.jl:201-207) */
+        it->n_c = 0;
+        for (int r = 0; r < L->nact; r++)
+            for (int k = 0; k < act_nt[r]; k++)
+                if (it->t0 <= act_t[r][k] && act_t[r][k] < it->t1) it->n_c++;
+        it->c_init = (double *)malloc(sizeof(double) * (size_t)(it->n_c > 0 ? it->n_c : 1));
+        int q = 0;
+        for (int r = 0; r < L->nact; r++)
+            for (int k = 0; k < act_nt[r]; k++)
+                if (it->t0 <= act_t[r][k] && act_t[r][k] < it->t1) it->c_init[q++] = act_u[r] ? act_u[r][k] : 0.0;
+        /* shooting_indices (:333-340): non-quadrature states; controls with no grid point at the interval start */
+        it->n_sidx = 0;
+        if (it->shooting) {
+            for (int k = 1; k <= L->nx; k++)
+                if (!in_list(L->quad, L->nquad, k)) it->sidx[it->n_sidx++] = k;
+            for (int r = 0; r < L->nact; r++) {
+                int found = 0; /* find_shooting_indices: any(first(tspan) .== control.t), local_controls.jl:180 */
+                for (int k = 0; k < act_nt[r]; k++)
+                    if (act_t[r][k] == it->grid[0]) found = 1;
+                if (!found) it->sidx[it->n_sidx++] = L->nx + r + 1;
+            }
+        }
+        it->var_off = off;
+        off += it->n_u0 + L->ntp + it->n_c;
+    }
+    L->nvars = off;
+    L->ndef = 0;
+    L->nsamples = 1;
+    for (int i = 0; i < L->I; i++) {
+        L->nsamples += L->iv[i].M;
+        if (i > 0) L->ndef += L->iv[i].n_sidx + L->ntp;
+    }
+    return L;
+}
+
+void co_layer_destroy(co_layer *L)
+{
+    if (!L) return;
+    for (int i = 0; i < L->I; i++) {
+        free(L->iv[i].grid);
+        free(L->iv[i].idx);
+        free(L->iv[i].c_init);
+    }
+    free(L->iv);
+    free(L);
+}
+
+int co_n_intervals(const co_layer *L) { return L->I; }
+int co_nvars(const co_layer *L) { return L->nvars; }
+int co_nrow(const co_layer *L) { return L->nx + L->nact; }
+int co_n_defects(const co_layer *L) { return L->ndef; }
+int co_n_samples(const co_layer *L) { return L->nsamples; }
+
+void co_block_structure(const co_layer *L, int *blocks)
+{
+    blocks[0] = 0;
+    for (int i = 0; i < L->I; i++) blocks[i + 1] = L->iv[i].var_off + L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
+}
+
+void co_interval_info(const co_layer *L, int i, double *ts, int *M, int *n_u0, int *n_p, int *n_c, int *n_sidx)
+{
+    const interval *it = &L->iv[i];
+    ts[0] = it->t0;
+    ts[1] = it->t1;
+    *M = it->M;
+    *n_u0 = it->n_u0;
+    *n_p = L->ntp;
+    *n_c = it->n_c;
+    *n_sidx = it->n_sidx;
+}
+
+void co_interval_tables(const co_layer *L, int i, int64_t *idx, double *grid, int *sidx, int *sorting,
+                        int *constants, int *n_constants)
+{
+    const interval *it = &L->iv[i];
+    if (idx && it->idx) memcpy(idx, it->idx, sizeof(int64_t) * (size_t)(L->nact * it->M));
+    if (grid) memcpy(grid, it->grid, sizeof(double) * (size_t)(it->M + 1));
+    if (sidx) memcpy(sidx, it->sidx, sizeof(int) * (size_t)it->n_sidx);
+    if (sorting) memcpy(sorting, it->ic_sorting, sizeof(int) * (size_t)L->nx);
+    if (constants) memcpy(constants, it->ic_constants, sizeof(int) * (size_t)it->n_const);
+    if (n_constants) *n_constants = it->n_const;
+}
+
+/* default_initialization (multiple_shooting.jl:45-55) -> __initialparameters (single_shooting.jl:170-201);
+ * bounds are infinite here, so the clamps of default_u0/default_p0 are the identity */
+void co_default_ps(const co_layer *L, double *ps)
+{
+    for (int i = 0; i < L->I; i++) {
+        const interval *it = &L->iv[i];
+        double *v = ps + it->var_off;
+        if (!it->shooting)
+            for (int k = 0; k < L->n_tic; k++) *v++ = L->u0[L->tic[k] - 1];
+        else
+            for (int k = 1; k <= L->nx; k++)
+                if (!in_list(L->quad, L->nquad, k)) *v++ = L->u0[k - 1];
+        for (int k = 0; k < L->ntp; k++) *v++ = L->p0[L->tunable_p[k] - 1];
+        for (int k = 0; k < it->n_c; k++) *v++ = it->c_init[k];
+    }
+}
+
+/* one interval: (layer::SingleShootingLayer)(::Any, ps, st, shooting_layer) (single_shooting.jl:357-374)
+ * followed by _sequential_solve (:421-471).  samples: (M+1) x nrow, sample-major. */
+static void solve_interval(const co_layer *L, int i, const dual *vars, int method, int K, dual *samples,
+                           double *tsamp, int shooting_flag)
+{
+    const interval *it = &L->iv[i];
+    const int nx = L->nx, nrow = nx + L->nact;
+    const dual *v_u0 = vars, *v_p = vars + it->n_u0, *v_c = v_p + L->ntp;
+    dual x[CO_MAX_NX], cat[2 * CO_MAX_NX], pfull[CO_MAX_NP], ctrl[CO_MAX_CTRL];
+    /* u0 = initial_condition(ps.u0, fixval); fixval = zeros for shooting layers (:359) */
+    if (it->n_u0 == 0) {
+        for (int k = 0; k < nx; k++) x[k] = dconst(shooting_flag ? 0.0 : L->u0[k]);
+    } else {
+        for (int k = 0; k < it->n_const; k++)
+            cat[k] = dconst(shooting_flag ? 0.0 : L->u0[it->ic_constants[k] - 1]);
+        for (int k = 0; k < it->n_u0; k++) cat[it->n_const + k] = v_u0[k];
+        for (int k = 0; k < nx; k++) x[k] = cat[it->ic_sorting[k] - 1];
+    }
+    for (int j = 0; j < it->M; j++) {
+        for (int r = 0; r < L->nact; r++) ctrl[r] = v_c[it->idx[r + (size_t)L->nact * j] - 1]; /* :439 */
+        for (int q = 0; q < L->np_all; q++)
+            pfull[q] = L->pmap_kind[q] ? ctrl[L->pmap_idx[q]] : v_p[L->pmap_idx[q]]; /* A*p + B*controls */
+        if (j == 0) { /* save_start = (j == 1) */
+            for (int k = 0; k < nx; k++) samples[k] = x[k];
+            for (int r = 0; r < L->nact; r++) samples[nx + r] = ctrl[r];
+            if (tsamp) tsamp[0] = it->grid[0];
+        }
+        integrate_piece(&L->m, nx, x, pfull, it->grid[j], it->grid[j + 1], K, method);
+        dual *s = samples + (size_t)(j + 1) * nrow; /* save_end; u = vcat(x, p_j) (:456) */
+        for (int k = 0; k < nx; k++) s[k] = x[k];
+        for (int r = 0; r < L->nact; r++) s[nx + r] = ctrl[r];
+        if (tsamp) tsamp[j + 1] = it->grid[j + 1];
+    }
+}
+
+int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int method, int K, double *t_out,
+            double *u_out, double *xend, double *dxend, double *defk, double *ddefk, double *defs,
+            double *ddefs, double *last, double *dlast)
+{
+    if (nd > CO_ND) return -1;
+    g_nd = nd;
+    const int nx = L->nx, nrow = nx + L->nact, I = L->I;
+    int maxM = 0, maxv = 0;
+    for (int i = 0; i < I; i++) {
+        if (L->iv[i].M > maxM) maxM = L->iv[i].M;
+        int nv = L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
+        if (nv > maxv) maxv = nv;
+    }
+    dual **S = (dual **)malloc(sizeof(dual *) * (size_t)I);
+    double *ts = (double *)malloc(sizeof(double) * (size_t)(maxM + 1));
+    dual *vars = (dual *)malloc(sizeof(dual) * (size_t)(maxv > 0 ? maxv : 1));
+    int so = 0;
+    for (int i = 0; i < I; i++) {
+        const interval *it = &L->iv[i];
+        int nv = it->n_u0 + L->ntp + it->n_c;
+        for (int k = 0; k < nv; k++) {
+            vars[k].v = ps[it->var_off + k];
+            for (int d = 0; d < nd; d++) vars[k].d[d] = dps[(size_t)d * L->nvars + it->var_off + k];
+        }
+        S[i] = (dual *)malloc(sizeof(dual) * (size_t)((it->M + 1) * nrow));
+        solve_interval(L, i, vars, method, K, S[i], ts, it->shooting);
+        if (t_out) /* drop the duplicated boundary point of all but the last interval (:145-147) */
+            for (int j = 0; j < it->M + (i == I - 1); j++) t_out[so + j] = ts[j];
+        if (xend)
+            for (int k = 0; k < nx; k++) {
+                xend[k + nx * i] = S[i][(size_t)it->M * nrow + k].v;
+                if (dxend)
+                    for (int d = 0; d < nd; d++)
+                        dxend[k + nx * i + (size_t)d * nx * I] = S[i][(size_t)it->M * nrow + k].d[d];
+            }
+        so += it->M;
+    }
+    /* shooting defects (multiple_shooting.jl:150-163) */
+    if (defk || defs) {
+        int n_u = 0, n_p = 0;
+        for (int i = 1; i < I; i++) {
+            for (int q = 0; q < L->iv[i].n_sidx; q++)
+                if (L->iv[i].sidx[q] <= nx) n_u++;
+            n_p += L->ntp;
+        }
+        int ou = 0, op = n_u, oc = n_u + n_p, os = 0;
+        for (int i = 1; i < I; i++) {
+            const interval *prev = &L->iv[i - 1], *it = &L->iv[i];
+            const dual *lastp = S[i - 1] + (size_t)prev->M * nrow, *first = S[i];
+            /* u0 matchings, then p, then controls within the stage */
+            for (int pass = 0; pass < 3; pass++) {
+                if (pass == 1) {
+                    for (int k = 0; k < L->ntp; k++) {
+                        double v = ps[prev->var_off + prev->n_u0 + k] - ps[it->var_off + it->n_u0 + k];
+                        if (defk) defk[op] = v;
+                        if (defs) defs[os] = v;
+                        for (int d = 0; d < nd; d++) {
+                            double dv = dps[(size_t)d * L->nvars + prev->var_off + prev->n_u0 + k] -
+                                        dps[(size_t)d * L->nvars + it->var_off + it->n_u0 + k];
+                            if (ddefk) ddefk[op + (size_t)d * L->ndef] = dv;
+                            if (ddefs) ddefs[os + (size_t)d * L->ndef] = dv;
+                        }
+                        op++;
+                        os++;
+                    }
+                    continue;
+                }
+                for (int q = 0; q < it->n_sidx; q++) {
+                    int r = it->sidx[q] - 1;
+                    if ((pass == 0) != (r < nx)) continue;
+                    dual df = dsub(lastp[r], first[r]);
+                    int *o = (pass == 0) ? &ou : &oc;
+                    if (defk) defk[*o] = df.v;
+                    if (defs) defs[os] = df.v;
+                    for (int d = 0; d < nd; d++) {
+                        if (ddefk) ddefk[*o + (size_t)d * L->ndef] = df.d[d];
+                        if (ddefs) ddefs[os + (size_t)d * L->ndef] = df.d[d];
+                    }
+                    (*o)++;
+                    os++;
+                }
+            }
+        }
+    }
+    /* quadrature accumulation (:171-177), then concatenation (:178-180) */
+    for (int i = 1; i < I; i++) {
+        const interval *prev = &L->iv[i - 1], *it = &L->iv[i];
+        for (int q = 0; q < L->nquad; q++) {
+            int r = L->quad[q] - 1;
+            dual qp = S[i - 1][(size_t)prev->M * nrow + r];
+            for (int j = 0; j <= it->M; j++) S[i][(size_t)j * nrow + r] = dadd(S[i][(size_t)j * nrow + r], qp);
+        }
+    }
+    so = 0;
+    for (int i = 0; i < I; i++) {
+        const interval *it = &L->iv[i];
+        if (u_out)
+            for (int j = 0; j < it->M + (i == I - 1); j++)
+                for (int r = 0; r < nrow; r++) u_out[r + (size_t)nrow * (so + j)] = S[i][(size_t)j * nrow + r].v;
+        so += it->M;
+    }
+    if (last) {
+        const dual *l = S[I - 1] + (size_t)L->iv[I - 1].M * nrow;
+        for (int r = 0; r < nrow; r++) {
+            last[r] = l[r].v;
+            if (dlast)
+                for (int d = 0; d < nd; d++) dlast[r + (size_t)d * nrow] = l[r].d[d];
+        }
+    }
+    for (int i = 0; i < I; i++) free(S[i]);
+    free(S);
+    free(ts);
+    free(vars);
+    g_nd = 0;
+    return 0;
+}
+
+int co_forward_init(const co_layer *L, double *ps, const int *fixed, int nfixed, int method, int K)
+{
+    g_nd = 0;
+    const int nx = L->nx, nrow = nx + L->nact;
+    double carry[CO_MAX_NX + CO_MAX_CTRL];
+    int ncarry = L->iv[0].n_u0; /* u0s = [first(ps).u0] */
+    for (int k = 0; k < ncarry; k++) carry[k] = ps[L->iv[0].var_off + k];
+    for (int i = 0; i < L->I; i++) {
+        const interval *it = &L->iv[i];
+        int nv = it->n_u0 + L->ntp + it->n_c;
+        int is_fixed = in_list(fixed, nfixed, i + 1);
+        if (!is_fixed) {
+            if (ncarry < it->n_u0) return -2; /* BoundsError in the reference */
+            for (int k = 0; k < it->n_u0; k++) ps[it->var_off + k] = carry[k]; /* u0[eachindex(sps.u0)] */
+        }
+        dual *vars = (dual *)malloc(sizeof(dual) * (size_t)(nv > 0 ? nv : 1));
+        for (int k = 0; k < nv; k++) vars[k] = dconst(ps[it->var_off + k]);
+        dual *S = (dual *)malloc(sizeof(dual) * (size_t)((it->M + 1) * nrow));
+        /* layer(nothing, sps, sst): the shooting flag is NOT passed here, so fixval = problem.u0 (:165) */
+        solve_interval(L, i, vars, method, K, S, NULL, 0);
+        for (int r = 0; r < nrow; r++) carry[r] = S[(size_t)it->M * nrow + r].v; /* pred.u[end] */
+        ncarry = nrow;
+        free(S);
+        free(vars);
+    }
+    return 0;
+}
+
+int co_max_threads(void)
+{
+#ifdef _OPENMP
+    return omp_get_max_threads();
+#else
+    return 1;
+#endif
+}
+
+static double now_s(void)
+{
+    struct timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+double co_bench_units(const co_layer *L, const double *ps_batch, int64_t B, int64_t b0, int64_t b1, int method,
+                      int K, int with_sens, int nthreads, double *checksum)
+{
+    (void)B;
+    const int I = L->I, nx = L->nx, nrow = nx + L->nact;
+    int maxM = 0, maxv = 0;
+    for (int i = 0; i < I; i++) {
+        if (L->iv[i].M > maxM) maxM = L->iv[i].M;
+        int nv = L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
+        if (nv > maxv) maxv = nv;
+    }
+    double sum = 0.0;
+    double t0 = now_s();
+    int64_t nunits = (b1 - b0) * I;
+#ifdef _OPENMP
+    if (nthreads > 0) omp_set_num_threads(nthreads);
+#else
+    (void)nthreads;
+#endif
+#pragma omp parallel reduction(+ : sum)
+    {
+        dual *vars = (dual *)malloc(sizeof(dual) * (size_t)(maxv > 0 ? maxv : 1));
+        dual *S = (dual *)malloc(sizeof(dual) * (size_t)((maxM + 1) * nrow));
+#pragma omp for schedule(static)
+        for (int64_t u = 0; u < nunits; u++) {
+            int64_t b = b0 + u / I;
+            int i = (int)(u % I);
+            const interval *it = &L->iv[i];
+            int nv = it->n_u0 + L->ntp + it->n_c;
+            const double *psb = ps_batch + (size_t)b * L->nvars + it->var_off;
+            int npass = with_sens ? (nv + CO_ND - 1) / CO_ND : 1;
+            if (npass < 1) npass = 1;
+            for (int pass = 0; pass < npass; pass++) {
+                int d0 = pass * CO_ND, nd = with_sens ? (nv - d0 < CO_ND ? nv - d0 : CO_ND) : 0;
+                if (nd < 0) nd = 0;
+                g_nd = nd;
+                for (int k = 0; k < nv; k++) {
+                    vars[k].v = psb[k];
+                    for (int d = 0; d < nd; d++) vars[k].d[d] = (k == d0 + d) ? 1.0 : 0.0;
+                }
+                solve_interval(L, i, vars, method, K, S, NULL, it->shooting);
+                const dual *e = S + (size_t)it->M * nrow;
+                for (int k = 0; k < nx; k++) {
+                    sum += e[k].v;
+                    for (int d = 0; d < nd; d++) sum += e[k].d[d];
+                }
+            }
+        }
+        free(vars);
+        free(S);
+        g_nd = 0;
+    }
+    double t1 = now_s();
+    if (checksum) *checksum = sum;
+    return t1 - t0;
+}

@@ -1,0 +1,126 @@
+/*
+ * corleone_oracle.h -- CPU restatement of Corleone.jl's shooting hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing under oracle/ is part of the product:
+ * only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+ * --impl reference legs may load it, and only as the checker / CPU baseline.
+ *
+ * Parity status: the real reference (Julia + un-vendored OrdinaryDiffEq /
+ * ForwardDiff) cannot run in the build container.  This restatement is pinned
+ * against every golden value the reference's own tests hold for the path
+ * (G1..G9 in SURVEY.md section 8c; see tests/test_oracle_golden.py) at the
+ * tolerance a converged fixed-step Tsit5 reaches against those adaptive
+ * goldens (<= 1e-10 abs for G1/G4, 1e-9..1e-7 for G3/G7), and against closed
+ * forms (LQR, 1-D OED).  The reference has no fixed-step test, so the
+ * fixed-step 1e-10 contract itself is "parity unpinned" by reference output;
+ * it is enforced oracle <-> CUDA on identical fixed-step inputs.
+ *
+ * All reference citations are relative to /root/reference.
+ */
+#ifndef CORLEONE_ORACLE_H
+#define CORLEONE_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* forward-mode tangent lanes carried per pass (ForwardDiff-style chunk) */
+#define CO_ND 16
+#define CO_MAX_NX 32
+#define CO_MAX_NP 16
+#define CO_MAX_CTRL 8
+
+enum co_model {
+    CO_LOTKA3 = 0,      /* Lotka fishing + Lagrange state, test/core/multiple_shooting.jl:11-17 */
+    CO_LQR = 1,         /* examples/linear_quadratic/main.jl:45-50 */
+    CO_LOTKA2 = 2,      /* lib/CorleoneOED/test/core/lotka_oed.jl:15-20 */
+    CO_LOTKA2_OED = 3,  /* [x; G; F_triu] augmentation of CO_LOTKA2, params=[2,3], observed=u[1:2] */
+    CO_LIN1D = 4,       /* lib/CorleoneOED/test/core/1d_oed.jl:11-13 */
+    CO_LIN1D_OED = 5,   /* augmentation of CO_LIN1D, params=[1], observed=[u[1]] */
+    CO_DENSE20 = 6,     /* synthetic BASELINE config 4: x' = W x - x^3 + b u */
+    CO_EGERSTEDT = 7    /* test/core/local_controls.jl:46-52 */
+};
+
+enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };
+
+typedef struct {
+    int model;
+    int nx, np_all;                 /* states, length of problem.p (controls included) */
+    const double *u0;               /* nx */
+    const double *p0;               /* np_all */
+    double tspan[2];
+    int ncontrols;                  /* as the user passed them (order kept) */
+    const int *control_indices;     /* 1-based index into problem.p, per control */
+    const double *const *ctrl_t;    /* per control: time grid */
+    const double *const *ctrl_u;    /* per control: initial values (same length) or NULL -> zeros */
+    const int *ctrl_nt;
+    int n_tunable_ic;
+    const int *tunable_ic;          /* 1-based */
+    int nquad;
+    const int *quad_idx;            /* 1-based quadrature_indices */
+    int n_shoot;                    /* 0 -> single shooting */
+    const double *shoot_pts;        /* tpoints of MultipleShootingLayer */
+    const double *model_data;       /* CO_DENSE20: W (20x20 row-major) then b (20) */
+} co_problem;
+
+typedef struct co_layer co_layer;
+
+/* ---- index logic, callable on its own (src/local_controls.jl) ---- */
+/* get_timegrid (:53-57): indices k with t0 <= t[k] < t1; returns count, writes 0-based positions */
+int co_restrict_grid(const double *t, int nt, double t0, double t1, int *pos);
+/* build_index_grid (:149-178) + collect_tspans (:183-195), unchunked.  idx is column-major
+ * ncontrols x M, 1-based exactly as Julia returns it; grid has M+1 points.  Returns M. */
+int co_build_index_grid(int ncontrols, const double *const *t, const int *nt, double t0, double t1,
+                        int64_t *idx, double *grid, int cap_pieces);
+/* get_subvector_indices (:120-147): writes 1-based (start,stop) pairs, returns chunk count */
+int co_subvector_indices(int M, int L, int *start_stop);
+
+/* ---- layer = SingleShootingLayer or MultipleShootingLayer + its `st` ---- */
+co_layer *co_layer_create(const co_problem *prob);
+void co_layer_destroy(co_layer *L);
+int co_n_intervals(const co_layer *L);
+int co_nvars(const co_layer *L);                    /* LuxCore.parameterlength */
+int co_nrow(const co_layer *L);                     /* nx + active controls: rows of a trajectory sample */
+void co_block_structure(const co_layer *L, int *blocks /* I+1 */);
+void co_interval_info(const co_layer *L, int i, double *tspan2, int *M, int *n_u0, int *n_p, int *n_c,
+                      int *n_shooting_idx);
+void co_interval_tables(const co_layer *L, int i, int64_t *idx /* nact x M */, double *grid /* M+1 */,
+                        int *shooting_indices /* 1-based */, int *ic_sorting, int *ic_constants,
+                        int *n_constants);
+void co_default_ps(const co_layer *L, double *ps);  /* default_initialization, flat (u0,p,controls) per interval */
+int co_n_defects(const co_layer *L);                /* get_number_of_shooting_constraints */
+int co_n_samples(const co_layer *L);                /* samples of the merged Trajectory */
+
+/* ---- evaluation with up to CO_ND tangent directions ----
+ * ps: nvars values; dps: nvars x nd column-major tangents (may be NULL when nd == 0).
+ * K fixed RK steps per control piece, h = (t1 - t0)/K.
+ * Outputs (any may be NULL); tangent outputs have nd trailing columns (column-major):
+ *   t_out   [nsamples], u_out [nrow x nsamples] column-major (merged Trajectory, quadratures accumulated)
+ *   xend    [nx x I] raw end state of every interval (before quadrature accumulation)
+ *   defk    [ndef] kind-major shooting_constraints (multiple_shooting.jl:281-295)
+ *   defs    [ndef] stage-major stage_ordered_shooting_constraints (:229,249-252)
+ *   last    [nrow] last sample of the merged trajectory (objective = one row of it, dynprob.jl:70-71)
+ */
+int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int method, int K,
+            double *t_out, double *u_out, double *xend, double *dxend, double *defk, double *ddefk,
+            double *defs, double *ddefs, double *last, double *dlast);
+
+/* forward_initialization (src/node_initialization.jl:152-170): overwrites the u0 entries of ps in place */
+int co_forward_init(const co_layer *L, double *ps, const int *fixed_indices, int nfixed, int method, int K);
+
+/* ---- CPU baseline: every (interval, candidate) unit with its own local sensitivities ----
+ * ps_batch: nvars x B column-major (candidate per column).  Integrates each unit with identity seeds on
+ * its (u0,p,controls) block, in ceil(ns_i/CO_ND) passes, OpenMP over units (EnsembleThreads analogue,
+ * src/Corleone.jl:23).  Returns seconds; checksum guards against dead-code elimination.
+ * sens_out (optional): per unit nx*ns_i doubles packed, interval-major then candidate, row-major [dir][state]. */
+double co_bench_units(const co_layer *L, const double *ps_batch, int64_t B, int64_t b_begin, int64_t b_end,
+                      int method, int K, int with_sens, int nthreads, double *checksum);
+
+int co_max_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

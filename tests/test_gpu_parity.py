@@ -1,0 +1,209 @@
+"""Parity of the CUDA path (through the C ABI) against the CPU oracle on identical fixed-step inputs.
+
+Tolerance (BASELINE.json north_star): <= 1e-10 relative in FP64 for states, defects, objective and
+sensitivities; index-derived quantities (orderings, structure) bit-exact.
+"""
+import numpy as np
+import pytest
+
+import problems as P
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-10
+
+
+def rel_err(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
+    return float(np.max(np.abs(a - b))) / scale if a.size else 0.0
+
+
+def batch_ps(layer_o, B, rng, scale=0.05):
+    ps0 = layer_o.default_ps()
+    return ps0[None, :] + scale * rng.standard_normal((B, layer_o.nvars))
+
+
+def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    from oracle import pyoracle as po
+
+    O = po.OracleLayer(spec)
+    lay = P.product_layer(spec, alg)
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    method = "tsit5" if alg.method_id == 0 else "rk4"
+    K = alg.steps_per_piece
+    assert N.nvars == O.nvars and N.n_defects == O.ndef and N.n_samples == O.nsamples and N.n_row == O.nrow
+    assert np.array_equal(N.block_structure(), O.block_structure())
+    ps = batch_ps(O, B, rng) if ps is None else ps
+    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    if check_traj:
+        want |= nat.WANT_TRAJ
+    r = N.eval_host(ps, want, objective_row=objective_row)
+    blocks = O.block_structure()
+    nx, I = O.nx, O.I
+    errs = dict(xend=0.0, defk=0.0, defs=0.0, obj=0.0, traj=0.0, sens=0.0, grad=0.0)
+    rows, cols, src = N.jac_structure()
+    for b in range(B):
+        o = O.eval(ps[b], method=method, K=K)
+        errs["xend"] = max(errs["xend"], rel_err(r["xend"][b].reshape(I, nx).T, o["xend"]))
+        errs["defk"] = max(errs["defk"], rel_err(r["defects_kind"][b], o["defk"]))
+        errs["defs"] = max(errs["defs"], rel_err(r["defects_stage"][b], o["defs"]))
+        errs["obj"] = max(errs["obj"], rel_err(r["objective"][b], o["last"][objective_row - 1]))
+        if check_traj:
+            errs["traj"] = max(errs["traj"], rel_err(r["traj"][b].reshape(O.nsamples, O.nrow).T, o["u"]))
+        if b < 3:  # dense oracle Jacobians are the slow part
+            Jx, Jd, Jl = O.jacobians(ps[b], method=method, K=K)
+            off = 0
+            for i in range(I):
+                ns = blocks[i + 1] - blocks[i]
+                S = r["sens"][b][off:off + nx * ns].reshape(ns, nx).T          # [k, d]
+                errs["sens"] = max(errs["sens"], rel_err(S, Jx[nx * i:nx * (i + 1), blocks[i]:blocks[i + 1]]))
+                off += nx * ns
+            errs["grad"] = max(errs["grad"], rel_err(r["grad"][b], Jl[objective_row - 1]))
+            # Jacobian of the kind-major constraints assembled from the structure + sens
+            J = np.zeros((O.ndef, O.nvars))
+            vals = np.where(src >= 0, r["sens"][b][np.maximum(src, 0)], np.where(src == -1, 1.0, -1.0))
+            np.add.at(J, (rows - 1, cols - 1), vals)
+            errs["jac"] = max(errs.get("jac", 0.0), rel_err(J, Jd))
+    return errs
+
+
+def assert_ok(errs):
+    bad = {k: v for k, v in errs.items() if not v <= RTOL}
+    assert not bad, f"parity errors above {RTOL}: {bad} (all: {errs})"
+
+
+def test_lotka_ms4_reference_golden():
+    """G1: the reference's own 15-element defect vector (test/core/multiple_shooting.jl:54-72, atol 1e-10)."""
+    import corleone_b200 as cb
+    lay = P.product_layer(P.lotka_spec(), cb.Tsit5(8))
+    ps, st = cb.setup(None, lay)
+    traj, _ = lay(None, ps, st)
+    G1 = np.array([1.375754960969482, 0.22357357513551113, 1.2417260108009396] * 3 + [0.0] * 6)
+    assert cb.is_shooting_solution(traj)
+    assert np.allclose(cb.shooting_constraints(traj), G1, atol=1e-10, rtol=0)
+    assert len(cb.shooting_constraints(traj)) == cb.get_number_of_shooting_constraints(lay, ps, st) == 15
+    assert traj.u.shape == (121, 4) and len(np.unique(traj.t)) == 121
+    assert list(traj.shooting_indices) == [31, 62, 93]
+    # MS objective golden (test/examples/lotka_ms.jl:45)
+    assert abs(traj["x₃"][-1] - 1.2417260108009376) < 1e-9
+
+
+@pytest.mark.parametrize("method", ["tsit5", "rk4"])
+def test_lotka_ms4_parity(method):
+    import corleone_b200 as cb
+    alg = cb.Tsit5(2) if method == "tsit5" else cb.RK4(3)
+    rng = np.random.default_rng(20261019)
+    assert_ok(full_compare(P.lotka_spec(controls=rng.uniform(0, 1, 120)), alg, 5, rng, objective_row=3))
+
+
+def test_lotka_ms4_quadrature_parity():
+    import corleone_b200 as cb
+    rng = np.random.default_rng(7)
+    spec = P.lotka_spec(controls=rng.uniform(0, 1, 120), quadrature=True)
+    assert_ok(full_compare(spec, cb.Tsit5(2), 4, rng, objective_row=3))
+
+
+def test_lotka_ss_chunked_parity():
+    """single shooting over 120 pieces (> subdivide = 100, so the reference chunks the tables)"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(3)
+    spec = P.lotka_spec(shooting_points=None, controls=rng.uniform(0, 1, 120), tunable_ic=[2, 1])
+    assert_ok(full_compare(spec, cb.Tsit5(1), 3, rng, objective_row=3))
+
+
+def test_lotka_ms24_config1():
+    import corleone_b200 as cb
+    rng = np.random.default_rng(20261019 + 1)
+    assert_ok(full_compare(P.lotka_ms24_spec(rng), cb.Tsit5(4), 1, rng, objective_row=3))
+
+
+def test_lqr_config2_small_batch():
+    import corleone_b200 as cb
+    rng = np.random.default_rng(20261019 + 2)
+    assert_ok(full_compare(P.lqr_spec(100, rng), cb.Tsit5(2), 33, rng, objective_row=2, check_traj=True))
+
+
+def test_egerstedt_three_controls_permuted():
+    import corleone_b200 as cb
+    rng = np.random.default_rng(5)
+    assert_ok(full_compare(P.egerstedt_spec(), cb.Tsit5(2), 3, rng, objective_row=3))
+
+
+def test_dense20_parity_small():
+    import corleone_b200 as cb
+    rng = np.random.default_rng(20261019 + 4)
+    spec = P.dense20_spec(4, rng)
+    assert_ok(full_compare(spec, cb.Tsit5(2), 3, rng, objective_row=1, check_traj=False))
+
+
+def test_lotka_oed_fim_parity():
+    """states-only integration of [x; G; F_triu]; FIM read-out (oed.jl:388-398) and its sum over candidates"""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(11)
+    for sp in (None, [0.0, 3.0, 6.0, 9.0]):
+        spec = P.lotka_oed_spec(shooting_points=sp, fishing=rng.uniform(0, 1, 48))
+        O = po.OracleLayer(spec)
+        lay = P.product_layer(spec, cb.Tsit5(2))
+        ps_t, st = cb.setup(None, lay)
+        (st if sp is None else st["interval_1"])["_fim"] = (7, 2)
+        N = lay._native(st, ps_t)
+        B = 37
+        ps = batch_ps(O, B, rng, 0.02)
+        r = N.eval_host(ps, nat.WANT_XEND | nat.WANT_FIM | nat.WANT_DEFECTS)
+        Fsum = np.zeros(4)
+        for b in range(B):
+            o = O.eval(ps[b], K=2)
+            F = o["xend"][6:9, -1]
+            Fm = np.array([F[0], F[1], F[1], F[2]])
+            assert rel_err(r["fim"][b], Fm) <= RTOL
+            assert rel_err(r["defects_kind"][b], o["defk"]) <= RTOL
+            Fsum += Fm
+        assert rel_err(r["fim_sum"], Fsum) <= 1e-12 * B + RTOL
+
+
+def test_empty_batch_and_errors():
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    lay = P.product_layer(P.lotka_spec(), cb.Tsit5(1))
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    r = N.eval_host(np.zeros((0, N.nvars)), nat.WANT_XEND)
+    assert r["xend"].shape == (0, 12)
+    with pytest.raises(nat.NativeError):
+        N.eval_host(np.zeros((1, N.nvars)), nat.WANT_OBJ, objective_row=99)
+    with pytest.raises(nat.NativeError):
+        N.eval_host(np.zeros((1, N.nvars)), nat.WANT_FIM)
+
+
+def test_device_resident_soa_path():
+    """device pointers, SoA in and out (the layout the kernels use natively) == host candidate-major path"""
+    torch = pytest.importorskip("torch")
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    rng = np.random.default_rng(2)
+    spec = P.lqr_spec(100, rng)
+    lay = P.product_layer(spec, cb.Tsit5(2))
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    B = 257
+    ps = cb.to_vec(ps_t)[None, :] + 0.1 * rng.standard_normal((B, N.nvars))
+    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    ref = N.eval_host(ps, want, objective_row=2)
+    dev = torch.device("cuda:0")
+    d_ps = torch.from_numpy(np.ascontiguousarray(ps.T)).to(dev)           # [nvars, B]
+    sz = N.out_sizes()
+    outs = {k: torch.empty((sz[k], B), dtype=torch.float64, device=dev)
+            for k in ("xend", "sens", "defects_kind", "defects_stage", "objective", "grad")}
+    N.set_stream(torch.cuda.current_stream().cuda_stream)
+    N.eval_raw(d_ps.data_ptr(), B, B, want, nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA,
+               {k: v.data_ptr() for k, v in outs.items()}, objective_row=2)
+    torch.cuda.synchronize()
+    for k, v in outs.items():
+        assert np.array_equal(v.cpu().numpy().T, ref[k]), k
+    assert N.last_kernel_ms() > 0
