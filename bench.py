@@ -1,0 +1,321 @@
+#!/usr/bin/env python
+"""bench.py -- shooting-interval solves + sensitivities per second (FP64) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun)
+    python bench.py --impl reference --gpus N --steps K ...   the restated reference CPU path on the host cores
+
+Workload (N=1): BASELINE.json configs[1] = `lqr_ms100_b4096`: linear-quadratic regulator, 100 shooting
+intervals x 4096 candidates, Tsit5 with 2 fixed steps per control piece (M = 4 pieces per interval), full
+forward sensitivities (ns = 8 directions per interval).  One unit = one (interval, candidate) system.
+A step = one pass of the hot path over the batch: integration + sensitivities of every unit, shooting
+defects (both orderings), objective and objective gradient.  Weak scaling: every rank owns B candidates;
+only the cross-candidate sums (objective, gradient) are all-reduced (DESIGN.md "multi-GPU").
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = "lqr_ms100_b4096"
+I_INTERVALS, B_PER_GPU, K_STEPS_PER_PIECE, M_PIECES, NS_DIRS, NX = 100, 4096, 2, 4, 8, 2
+OBJECTIVE_ROW = 2   # x2 = accumulated cost (examples/linear_quadratic/main.jl:49, loss = :x2)
+
+# Algorithmic work per unit (DESIGN.md "roofline"):
+#   E = M (6K + 1) RHS evaluations (Tsit5, FSAL re-seeded at every piece start)
+#   W = E (C_f + C_JS) + M K 42 nz,  nz = nx (1 + ns);   LQR: C_f = 10, C_JS = 2 nnz(J) ns + nnz(f_p,f_u) = 36
+E_EVALS = M_PIECES * (6 * K_STEPS_PER_PIECE + 1)
+NZ = NX * (1 + NS_DIRS)
+FLOPS_PER_UNIT = E_EVALS * (10 + 36) + M_PIECES * K_STEPS_PER_PIECE * 42 * NZ      # 8440
+#   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic
+BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                                # 240
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d.get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._read, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_inputs(nvars, ps0, B, rng):
+    """candidate matrix (B, nvars): nodes x ~ U[0,4], cost node 0, controls N(0,1)"""
+    ps = np.tile(ps0, (B, 1))
+    # layout per interval (u0 (0 or 2), p (2), controls (4)); interval 1 has no u0
+    off = 0
+    for i in range(I_INTERVALS):
+        nu0 = 0 if i == 0 else 2
+        if nu0:
+            ps[:, off] = rng.uniform(0, 4, B)
+            ps[:, off + 1] = 0.0
+        ps[:, off + nu0 + 2: off + nu0 + 6] = rng.standard_normal((B, 4))
+        off += nu0 + 6
+    assert off == nvars
+    return ps
+
+
+def cpu_baseline(spec, ps, seconds_target=12.0, nthreads=0):
+    """The oracle port timed on the host cores on a bounded sample of the same workload."""
+    from oracle import pyoracle as po
+    O = po.OracleLayer(spec)
+    nthreads = nthreads or po.max_threads()
+    # calibrate on a few candidates, then size the sample for ~seconds_target
+    t, u, _ = O.bench_units(ps[:8], K=K_STEPS_PER_PIECE, with_sens=True, nthreads=nthreads)
+    rate = u / max(t, 1e-9)
+    nb = int(min(ps.shape[0], max(8, rate * seconds_target / I_INTERVALS)))
+    t, u, _ = O.bench_units(ps[:nb], K=K_STEPS_PER_PIECE, with_sens=True, nthreads=nthreads)
+    return u / t, nthreads, f"{nb} of {ps.shape[0]} candidates x {I_INTERVALS} intervals ({u} units), {t:.2f} s"
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The real
+    reference is Julia (absent here), so this is the oracle port with all host threads (kind = "port")."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from corleone_b200 import configs
+    from oracle import pyoracle as po
+    spec = configs.config2_lqr()
+    O = po.OracleLayer(spec)
+    rng = np.random.default_rng(configs.SEED0 + 2)
+    B = B_PER_GPU * args.gpus
+    nthreads = po.max_threads()
+    # each step = a bounded sample of the workload, sized so the whole run stays within a few minutes
+    t, u, _ = O.bench_units(make_inputs(O.nvars, O.default_ps(), 8, rng), K=K_STEPS_PER_PIECE, nthreads=nthreads)
+    rate = u / max(t, 1e-9)
+    budget = 120.0 / max(1, args.steps + args.warmup)
+    nb = int(min(B, max(8, rate * min(budget, 10.0) / I_INTERVALS)))
+    ps = make_inputs(O.nvars, O.default_ps(), nb, rng)
+    for _ in range(args.warmup):
+        O.bench_units(ps, K=K_STEPS_PER_PIECE, nthreads=nthreads)
+    tot_t, tot_u = 0.0, 0
+    for _ in range(args.steps):
+        t, u, _ = O.bench_units(ps, K=K_STEPS_PER_PIECE, nthreads=nthreads)
+        tot_t += t
+        tot_u += u
+    value = tot_u / tot_t
+    sample = f"{nb} of {B} candidates x {I_INTERVALS} intervals per step"
+    print(json.dumps({
+        "impl": "reference", "metric": "shooting-interval solves+sensitivities/sec (FP64)", "value": value,
+        "unit": "units/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "intervals": I_INTERVALS, "candidates_per_gpu": B_PER_GPU,
+                   "method": "tsit5", "steps_per_piece": K_STEPS_PER_PIECE, "pieces_per_interval": M_PIECES,
+                   "sens_directions": NS_DIRS, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "units/s", "cores": nthreads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 20)")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+    from corleone_b200 import Tsit5, configs, native as nat
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
+
+    spec = configs.config2_lqr()
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(K_STEPS_PER_PIECE), device=local_rank)
+    from corleone_b200 import to_vec
+    B = B_PER_GPU
+    nvars = N.nvars
+    rng = np.random.default_rng(configs.SEED0 + 2 + 1000 * rank)
+    ps_host = make_inputs(nvars, to_vec(ps_t), B, rng)                      # (B, nvars) candidate-major
+    stream = torch.cuda.current_stream()
+    N.set_stream(stream.cuda_stream)
+
+    # ---- device-resident arm: rotate over buffer sets whose total footprint exceeds L2 (126 MB)
+    sz = N.out_sizes()
+    fields = ("sens", "defects_kind", "defects_stage", "objective", "grad")
+    set_bytes = 8 * B * (nvars + sum(sz[f] for f in fields))
+    nsets = max(2, int(np.ceil(3 * 126e6 / set_bytes)))
+    d_ps, d_out, d_sums = [], [], []
+    for s in range(nsets):
+        d_ps.append(torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev))   # [nvars, B] SoA
+        d_out.append({f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields})
+        d_sums.append(torch.zeros(nvars + 1, dtype=torch.float64, device=dev))
+    want = nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
+
+    def step(s):
+        k = s % nsets
+        ptrs = {f: d_out[k][f].data_ptr() for f in fields}
+        ptrs["objective_sum"] = d_sums[k].data_ptr()
+        ptrs["grad_sum"] = d_sums[k].data_ptr() + 8
+        N.eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, OBJECTIVE_ROW)
+        if world > 1:   # the path's only exchange: cross-candidate partial sums (1 + nvars doubles)
+            dist.all_reduce(d_sums[k])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for s in range(max(3, args.warmup)):
+        step(s)
+    barrier()
+    launches0 = N.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local_rank) as clk:
+        barrier()
+        ev0.record(stream)
+        for s in range(args.steps):
+            step(s)
+        ev1.record(stream)
+        barrier()
+        ms_total = ev0.elapsed_time(ev1)
+        # keep the sampler alive for at least ~0.5 s of load so it sees the clocks under load
+        t_end = time.time() + 0.6
+        s2 = 0
+        while time.time() < t_end:
+            step(s2)
+            s2 += 1
+        torch.cuda.synchronize()
+    launches = N.launch_count() - launches0
+    extra_launch = s2 * (launches // max(1, args.steps))
+    launches_timed = launches - extra_launch
+    # kernel durations of the timed steps (event pairs recorded by the library around the integration kernel)
+    hist = N.kernel_ms_history(min(256, args.steps + s2))
+    kern_ms = float(np.mean(hist[s2:s2 + args.steps])) if len(hist) > s2 else float("nan")
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    units_per_step = I_INTERVALS * B * world
+    value = units_per_step * args.steps / (ms_total * 1e-3)
+
+    # ---- end-to-end arm: the public host API (Julia-style candidate-major matrices in pinned host memory)
+    e2e_steps = args.e2e_steps or min(args.steps, 20)
+    pin_ps = torch.from_numpy(ps_host).pin_memory()
+    pin_out = {f: torch.empty((B, sz[f]), dtype=torch.float64).pin_memory() for f in fields}
+    pinned = {f: v.numpy() for f, v in pin_out.items()}
+    ps_np = pin_ps.numpy()
+    for _ in range(3):
+        N.eval_host(ps_np, want, OBJECTIVE_ROW, pinned_out=pinned)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        N.eval_host(ps_np, want, OBJECTIVE_ROW, pinned_out=pinned)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = units_per_step * e2e_steps / float(t.item())
+    h2d = 8 * B * nvars
+    d2h = 8 * B * sum(sz[f] for f in fields)
+
+    if rank == 0:
+        hbm_peak, hbm_src = load_peaks()
+        fp64_peak = nat.probe_fp64_tflops(local_rank, 40000)
+        ach_tflops = FLOPS_PER_UNIT * I_INTERVALS * B / (kern_ms * 1e-3) / 1e12
+        ach_gbs = BYTES_PER_UNIT * I_INTERVALS * B / (kern_ms * 1e-3) / 1e9
+        line = {
+            "metric": "shooting-interval solves+sensitivities/sec (FP64)", "value": value, "unit": "units/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "intervals": I_INTERVALS, "candidates_per_gpu": B,
+                       "method": "tsit5", "steps_per_piece": K_STEPS_PER_PIECE, "pieces_per_interval": M_PIECES,
+                       "sens_directions": NS_DIRS, "units_per_step": units_per_step,
+                       "l2": f"inputs larger than L2: {nsets} rotating buffer sets of {set_bytes / 1e6:.0f} MB",
+                       "parallelism": f"batch-sharded x{world}, allreduce(objective_sum, grad_sum)" if world > 1 else "single GPU"},
+            "e2e": {"value": e2e_value, "unit": "units/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "api": "cb200_eval with pinned host buffers, candidate-major (Julia layout)"},
+            "gpu_launches": int(launches_timed),
+            "clocks": clk.summary(),
+            "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
+                         "frac": ach_tflops / fp64_peak if fp64_peak > 0 else None, "traffic": None,
+                         "kernel": "shoot_kernel<Lqr,G,Tsit5>", "kernel_ms": kern_ms,
+                         "flops_per_unit": FLOPS_PER_UNIT, "bytes_per_unit": BYTES_PER_UNIT,
+                         "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                                 "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, cores, sample = cpu_baseline(spec, ps_host)
+            line["cpu_baseline"] = {"value": v, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample}
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

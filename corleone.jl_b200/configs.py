@@ -1,0 +1,125 @@
+"""The named BASELINE.json configs as concrete synthetic problems.
+
+A spec is plain data (model, u0, p0, tspan, controls=[(p_index_1based, grid, values)], tunable_ic,
+quadrature_indices, shooting_points, model_data) so that the product layers and the test oracle are built
+from the same description.  Seeds: numpy default_rng(20261019 + config number).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .controls import ControlParameter
+from .multiple_shooting import MultipleShootingLayer
+from .problem import ODEProblem
+from .single_shooting import SingleShootingLayer
+
+SEED0 = 20261019
+
+
+def lotka_spec(shooting_points=(0.0, 3.0, 6.0, 9.0), controls=None, quadrature=False, tunable_ic=()):
+    """Lotka fishing problem of the reference tests (test/core/multiple_shooting.jl:11-37)."""
+    cgrid = np.arange(120) / 10.0   # 0.0:0.1:11.9 as Julia's range produces it (k/10 correctly rounded)
+    return dict(model="lotka3", u0=[0.5, 0.7, 0.0], p0=[0.0, 1.0, 1.0], tspan=(0.0, 12.0),
+                controls=[(1, cgrid, np.zeros(120) if controls is None else np.asarray(controls, float))],
+                tunable_ic=list(tunable_ic), quadrature_indices=[3] if quadrature else [],
+                shooting_points=None if shooting_points is None else list(shooting_points))
+
+
+def config1_lotka_ms24(rng=None):
+    """config 1: Lotka fishing, 24 intervals of 0.5, control grid k/10 (M = 5), controls U[0,1]."""
+    rng = np.random.default_rng(SEED0 + 1) if rng is None else rng
+    return lotka_spec(shooting_points=[0.5 * k for k in range(24)], controls=rng.uniform(0, 1, 120))
+
+
+def config2_lqr(n_intervals=100, rng=None):
+    """config 2: LQR (examples/linear_quadratic/main.jl:45-68), 100 intervals of 0.12, control step 0.03
+    (M = 4 pieces per interval, 400 control values N(0,1))."""
+    rng = np.random.default_rng(SEED0 + 2) if rng is None else rng
+    nctl = 4 * n_intervals
+    t = 3.0 * np.arange(nctl) / 100.0                     # k * 0.03 correctly rounded
+    return dict(model="lqr", u0=[1.0, 0.0], p0=[-1.0, 1.0, 0.0], tspan=(0.0, 3.0 * nctl / 100.0),
+                controls=[(3, t, rng.standard_normal(nctl))], tunable_ic=[], quadrature_indices=[],
+                shooting_points=[3.0 * (4 * k) / 100.0 for k in range(n_intervals)])
+
+
+def lotka_oed_spec(shooting_points=None, fishing=None, w=1.0, grids=None):
+    """Augmented Lotka OED [x; G; F_triu] with controls (fishing, w1, w2)
+    (lib/CorleoneOED/test/core/lotka_oed.jl:15-48 by default)."""
+    if grids is None:
+        cg, g1, g2 = 0.25 * np.arange(48), 0.5 * np.arange(24), 3.0 * np.arange(79) / 20.0
+    else:
+        cg, g1, g2 = grids
+    return dict(model="lotka2_oed", u0=[0.5, 0.7] + [0.0] * 7, p0=[0.0, 1.0, 1.0, 1.0, 1.0], tspan=(0.0, 12.0),
+                controls=[(1, cg, np.zeros(len(cg)) if fishing is None else np.asarray(fishing, float)),
+                          (4, g1, np.full(len(g1), w)), (5, g2, np.full(len(g2), w))],
+                tunable_ic=[], quadrature_indices=[],
+                shooting_points=None if shooting_points is None else list(shooting_points), fim=(7, 2))
+
+
+def config3_lotka_oed(n_intervals=64, rng=None):
+    """config 3: 64 intervals of 3/16, every grid with step 3/32 (M = 2), fishing U[0,1], w = 1."""
+    rng = np.random.default_rng(SEED0 + 3) if rng is None else rng
+    n = 2 * n_intervals
+    g = 3.0 * np.arange(n) / 32.0
+    s = lotka_oed_spec(shooting_points=[3.0 * (2 * k) / 32.0 for k in range(n_intervals)],
+                       fishing=rng.uniform(0, 1, n), grids=(g, g, g))
+    s["tspan"] = (0.0, 3.0 * n / 32.0)
+    return s
+
+
+def dense20_data(seed=SEED0 + 4):
+    rng = np.random.default_rng(seed)
+    W = 0.5 * rng.standard_normal((20, 20)) / np.sqrt(20.0)
+    return np.concatenate([W.ravel(), rng.standard_normal(20)])
+
+
+def config4_dense20(n_intervals=256, rng=None):
+    """config 4 (synthetic): x' = W x - x^3 + b u, 20 states, M = 4 pieces per interval of length 0.5."""
+    rng = np.random.default_rng(SEED0 + 4) if rng is None else rng
+    nctl = 4 * n_intervals
+    t = np.arange(nctl) / 8.0
+    return dict(model="dense20", u0=list(rng.uniform(-1, 1, 20)), p0=[0.0], tspan=(0.0, nctl / 8.0),
+                controls=[(1, t, rng.uniform(-1, 1, nctl))], tunable_ic=[], quadrature_indices=[],
+                shooting_points=[(4 * k) / 8.0 for k in range(n_intervals)], model_data=dense20_data())
+
+
+def lin1d_oed_spec():
+    """lib/CorleoneOED/test/core/1d_oed.jl:11-31"""
+    t = np.arange(100) / 100.0
+    return dict(model="lin1d_oed", u0=[1.0, 0.0, 0.0], p0=[-2.0, 1.0], tspan=(0.0, 1.0),
+                controls=[(2, t, np.ones(100))], tunable_ic=[], quadrature_indices=[], shooting_points=None,
+                fim=(3, 1))
+
+
+def egerstedt_spec():
+    """test/core/local_controls.jl:45-79: three controls passed in the order [2, 3, 1]"""
+    N = 20
+    cgrid = np.linspace(0.0, 1.0, N + 1)[:-1]
+    c1, c2, c3 = np.linspace(0.0, 0.2, N), np.linspace(0.3, 0.5, N), np.linspace(0.6, 0.8, N)
+    return dict(model="egerstedt", u0=[0.5, 0.5, 0.0], p0=[1 / 3] * 3, tspan=(0.0, 1.0),
+                controls=[(2, cgrid, c2), (3, cgrid, c3), (1, cgrid, c1)], control_names=["con2", "con3", "con1"],
+                tunable_ic=[], quadrature_indices=[], shooting_points=None)
+
+
+def layer_from_spec(spec, alg, **kw):
+    """Build the SingleShootingLayer / MultipleShootingLayer a spec describes."""
+    prob = ODEProblem(spec["model"], spec["u0"], spec["tspan"], spec["p0"], model_data=spec.get("model_data"))
+    names = spec.get("control_names") or [f"u{k + 1}" for k in range(len(spec["controls"]))]
+    ctr = [(ci, ControlParameter(t, name=n, controls=(np.zeros(len(t)) if u is None else u)))
+           for (ci, t, u), n in zip(spec["controls"], names)]
+    args = dict(controls=ctr, tunable_ic=spec.get("tunable_ic", []),
+                quadrature_indices=spec.get("quadrature_indices", []))
+    args.update(kw)
+    if spec.get("shooting_points") is None:
+        return SingleShootingLayer(prob, alg, **args)
+    return MultipleShootingLayer(prob, alg, *spec["shooting_points"], **args)
+
+
+def native_from_spec(spec, alg, device=0):
+    """(layer, ps template, st, NativeLayer) for a spec; the Fisher block, if any, is registered."""
+    lay = layer_from_spec(spec, alg, device=device)
+    ps, st = lay.initialparameters(None), lay.initialstates(None)
+    first = st if "tspans" in st else next(iter(st.values()))
+    if spec.get("fim"):
+        first["_fim"] = tuple(spec["fim"])
+    return lay, ps, st, lay._native(st, ps)

@@ -74,13 +74,12 @@ __global__ void defects_kernel(const DefectEntry *__restrict__ tab, int ndef, co
 // row carries the running sum over intervals (src/multiple_shooting.jl:171-177).
 __global__ void objective_kernel(const double *__restrict__ xend, long long ldx, const double *__restrict__ ps,
                                  long long ldb, long long B, int nx, int I, int state_k, int is_quad,
-                                 int ctrl_var, double *__restrict__ obj)
+                                 int ctrl_var, double *__restrict__ obj, double *__restrict__ obj_sum)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    double v;
+    double v = 0.0;
+    if (b < B) {
     if (state_k >= 0) {
-        v = 0.0;
         if (is_quad) {
             v = xend[(long long)state_k * ldx + b];  // q_prev = us[1][end][q]; then += across intervals in order
             for (int i = 1; i < I; i++) v = xend[((long long)i * nx + state_k) * ldx + b] + v;
@@ -90,18 +89,33 @@ __global__ void objective_kernel(const double *__restrict__ xend, long long ldx,
     } else {
         v = ps[(long long)ctrl_var * ldb + b];
     }
-    obj[b] = v;
+    if (obj) obj[b] = v;
+    }
+    if (obj_sum) {  // whole warps reach this point: warp-shuffle tree, one atomic per warp
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+        if ((threadIdx.x & 31) == 0) atomicAdd(obj_sum, v);
+    }
 }
 
 __global__ void grad_kernel(const GradEntry *__restrict__ tab, int n, const double *__restrict__ sens,
-                            long long lds, long long B, double *__restrict__ grad, long long ldo)
+                            long long lds, long long B, double *__restrict__ grad, long long ldo,
+                            double *__restrict__ grad_sum)
 {
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (tid >= (long long)n * B) return;
-    const int e = (int)(tid / B);
-    const long long b = tid - (long long)e * B;
-    const GradEntry t = tab[e];
-    grad[(long long)t.var * ldo + b] = t.src >= 0 ? sens[t.src * lds + b] : 1.0;
+    // grid.x tiles the candidates, grid.y strides the entries: a warp never straddles two entries, so
+    // the per-entry sum over candidates is a warp-shuffle tree + one atomicAdd per warp
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    for (int e = blockIdx.y; e < n; e += gridDim.y) {
+        const GradEntry t = tab[e];
+        double v = 0.0;
+        if (b < B) {
+            v = t.src >= 0 ? sens[t.src * lds + b] : 1.0;
+            if (grad) grad[(long long)t.var * ldo + b] = v;
+        }
+        if (grad_sum) {
+            for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+            if ((threadIdx.x & 31) == 0) atomicAdd(grad_sum + t.var, v);
+        }
+    }
 }
 
 // quadrature accumulation on the merged trajectory (src/multiple_shooting.jl:171-177)
@@ -232,14 +246,18 @@ struct cb200_handle {
     void *tables = nullptr;           // one device allocation holding every table
     DefectEntry *d_defects = nullptr;
     int *d_quad = nullptr;
-    GradEntry *d_grad = nullptr;      // scratch table for the current objective row
+    GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row
     int grad_cap = 0;
+    int grad_row = -1, grad_n = 0;    // objective_row the table was built for
+    std::vector<GradEntry> h_grad;
+    size_t out_off = 0;               // bump offset into ws_out during one eval
     cudaStream_t stream = nullptr;
     bool own_stream = false;
-    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
-    bool timed = false;
+    static constexpr int EV_RING = 256;   // event pairs around the integration kernel of the last 256 evals
+    cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
+    long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums;
 };
 
 static int default_G(int model)
@@ -570,10 +588,12 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail("cudaStreamCreate", e);
     h->own_stream = true;
-    e = cudaEventCreate(&h->ev0);
-    if (e != cudaSuccess) return bail("cudaEventCreate", e);
-    e = cudaEventCreate(&h->ev1);
-    if (e != cudaSuccess) return bail("cudaEventCreate", e);
+    for (int k = 0; k < cb200_handle::EV_RING; k++) {
+        e = cudaEventCreate(&h->ev0[k]);
+        if (e != cudaSuccess) return bail("cudaEventCreate", e);
+        e = cudaEventCreate(&h->ev1[k]);
+        if (e != cudaSuccess) return bail("cudaEventCreate", e);
+    }
     h->G_sens = default_G(d->model);
     if (const char *env = getenv("CB200_DIRS_PER_THREAD")) {
         int g = atoi(env);
@@ -589,11 +609,13 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out})
+                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums})
         b->release();
     if (h->tables) cudaFree(h->tables);
-    if (h->ev0) cudaEventDestroy(h->ev0);
-    if (h->ev1) cudaEventDestroy(h->ev1);
+    for (int k = 0; k < cb200_handle::EV_RING; k++) {
+        if (h->ev0[k]) cudaEventDestroy(h->ev0[k]);
+        if (h->ev1[k]) cudaEventDestroy(h->ev1[k]);
+    }
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CB200_OK;
@@ -646,11 +668,22 @@ extern "C" int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t
 
 extern "C" float cb200_last_kernel_ms(const cb200_handle *h)
 {
-    if (!h || !h->timed) return -1.0f;
     float ms = -1.0f;
-    if (cudaEventSynchronize(h->ev1) != cudaSuccess) return -1.0f;
-    if (cudaEventElapsedTime(&ms, h->ev0, h->ev1) != cudaSuccess) return -1.0f;
+    if (cb200_kernel_ms_history(h, &ms, 1) != 1) return -1.0f;
     return ms;
+}
+
+extern "C" int cb200_kernel_ms_history(const cb200_handle *h, float *ms, int n)
+{
+    if (!h || !ms || n <= 0) return 0;
+    const long long have = std::min<long long>(h->n_timed, cb200_handle::EV_RING);
+    const int m = (int)std::min<long long>(n, have);
+    for (int k = 0; k < m; k++) {  // ms[0] = newest
+        const int slot = (int)((h->n_timed - 1 - k) % cb200_handle::EV_RING);
+        if (cudaEventSynchronize(h->ev1[slot]) != cudaSuccess) return k;
+        if (cudaEventElapsedTime(&ms[k], h->ev0[slot], h->ev1[slot]) != cudaSuccess) return k;
+    }
+    return m;
 }
 
 extern "C" int64_t cb200_launch_count(const cb200_handle *h) { return h ? h->launches : 0; }
@@ -687,13 +720,14 @@ static int deliver(cb200_handle *h, const double *dev_soa, double *user, long lo
         if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
         return CB200_OK;
     }
-    // the staging buffer is reused per output; stream order keeps the copies safe
-    if (h->ws_out.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (%zu bytes staging)", bytes);
-    int rc = transpose(h, dev_soa, B, (double *)h->ws_out.p, n, n, B);
+    // every output of one eval gets its own slice of the staging buffer (reserved up front by cb200_eval),
+    // so all transposes and copies queue on the stream and the caller waits once
+    double *stage = (double *)((char *)h->ws_out.p + h->out_off);
+    h->out_off += (bytes + 255) & ~size_t(255);
+    if (h->out_off > h->ws_out.cap) return fail(CB200_ERR_NOMEM, "internal: staging buffer too small");
+    int rc = transpose(h, dev_soa, B, stage, n, n, B);
     if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    CUDA_TRY(cudaMemcpyAsync(user, h->ws_out.p, bytes, cudaMemcpyDeviceToHost, h->stream));
-    // one staging buffer: wait before the next deliver() overwrites it
-    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    CUDA_TRY(cudaMemcpyAsync(user, stage, bytes, cudaMemcpyDeviceToHost, h->stream));
     return CB200_OK;
 }
 
@@ -719,10 +753,12 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     const bool w_def = (want & CB200_WANT_DEFECTS) && (out->defects_kind || out->defects_stage);
     const bool w_obj = (want & CB200_WANT_OBJ) && out->objective;
     const bool w_fim = (want & CB200_WANT_FIM) && (out->fim || out->fim_sum);
-    const bool need_sens = w_sens || w_grad;
+    const bool w_osum = (want & CB200_WANT_OBJ) && out->objective_sum;
+    const bool w_gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
+    const bool need_sens = w_sens || w_grad || w_gsum;
     if (w_fim && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
     int obj_state = -1, obj_ctrl_var = -1, obj_quad = 0;
-    if (w_obj || w_grad) {
+    if (w_obj || w_grad || w_osum || w_gsum) {
         const int row = out->objective_row;
         if (row < 1 || row > nrow) return fail(CB200_ERR_ARG, "objective_row out of range");
         if (row <= nx) {
@@ -775,7 +811,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         return 0;
     };
     double *d_xend, *d_sens, *d_traj, *d_dk, *d_ds, *d_obj, *d_grad, *d_fim;
-    const bool need_xend = w_def || w_obj || w_fim || (w_traj && h->nquad > 0);
+    const bool need_xend = w_def || w_obj || w_osum || w_fim || (w_traj && h->nquad > 0);
     int oom = 0;
     oom |= buf(h->ws_xend, out->xend, (long long)nx * I, w_xend, need_xend, &d_xend);
     oom |= buf(h->ws_sens, out->sens, h->n_sens, w_sens, need_sens, &d_sens);
@@ -797,15 +833,16 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (L.R < 1) L.R = 1;
     }
     ShootOut so{d_xend, d_sens, d_traj, B};
-    CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+    const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
+    CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], h->stream));
     int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, h->stream);
     if (rc == -1000)
         return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
                     h->method);
     if (rc) return fail(CB200_ERR_CUDA, "shoot kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     h->launches++;
-    CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
-    h->timed = true;
+    CUDA_TRY(cudaEventRecord(h->ev1[ev_slot], h->stream));
+    h->n_timed++;
 
     // ---- K3: defects / objective / gradient / trajectory quadratures / FIM
     if (w_def && ndef > 0) {
@@ -813,26 +850,45 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
                                                                  d_dk, d_ds, B);
         h->launches++;
     }
-    if (w_obj) {
+    // cross-candidate sums (expectation-type objective / gradient): accumulate on the device, deliver 1 + nvars doubles
+    double *d_osum = nullptr, *d_gsum = nullptr;
+    if (w_osum || w_gsum) {
+        if (dev) {
+            d_osum = w_osum ? out->objective_sum : nullptr;
+            d_gsum = w_gsum ? out->grad_sum : nullptr;
+        } else {
+            if (h->ws_sums.reserve(sizeof(double) * (size_t)(nvars + 1))) return fail(CB200_ERR_NOMEM, "device out of memory");
+            d_osum = w_osum ? (double *)h->ws_sums.p : nullptr;
+            d_gsum = w_gsum ? (double *)h->ws_sums.p + 1 : nullptr;
+        }
+        if (d_osum) CUDA_TRY(cudaMemsetAsync(d_osum, 0, sizeof(double), h->stream));
+        if (d_gsum) CUDA_TRY(cudaMemsetAsync(d_gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
+    }
+    if (w_obj || w_osum) {
         objective_kernel<<<nblk(B, 256), 256, 0, h->stream>>>(d_xend, B, d_ps, d_ldb, B, nx, I, obj_state, obj_quad,
-                                                            obj_ctrl_var, d_obj);
+                                                            obj_ctrl_var, d_obj, d_osum);
         h->launches++;
     }
-    if (w_grad) {
-        CUDA_TRY(cudaMemsetAsync(d_grad, 0, sizeof(double) * (size_t)nvars * (size_t)B, h->stream));
-        std::vector<GradEntry> g;
-        if (obj_state >= 0) {
-            for (int i = obj_quad ? 0 : I - 1; i < I; i++)
-                for (int dd = 0; dd < h->ns[i]; dd++)
-                    g.push_back({h->h_var_off[i] + dd, h->h_sens_off[i] + (long long)dd * nx + obj_state});
-        } else {
-            g.push_back({obj_ctrl_var, -1});
+    if (w_grad || w_gsum) {
+        if (d_grad) CUDA_TRY(cudaMemsetAsync(d_grad, 0, sizeof(double) * (size_t)nvars * (size_t)B, h->stream));
+        if (h->grad_row != out->objective_row) {  // gather table: built once per objective row, kept in the handle
+            h->h_grad.clear();
+            if (obj_state >= 0) {
+                for (int i = obj_quad ? 0 : I - 1; i < I; i++)
+                    for (int dd = 0; dd < h->ns[i]; dd++)
+                        h->h_grad.push_back({h->h_var_off[i] + dd, h->h_sens_off[i] + (long long)dd * nx + obj_state});
+            } else {
+                h->h_grad.push_back({obj_ctrl_var, -1});
+            }
+            h->grad_n = (int)h->h_grad.size();
+            if (h->grad_n > 0)
+                CUDA_TRY(cudaMemcpyAsync(h->d_grad, h->h_grad.data(), sizeof(GradEntry) * h->h_grad.size(),
+                                         cudaMemcpyHostToDevice, h->stream));
+            h->grad_row = out->objective_row;
         }
-        if (!g.empty()) {
-            CUDA_TRY(cudaMemcpyAsync(h->d_grad, g.data(), sizeof(GradEntry) * g.size(), cudaMemcpyHostToDevice, h->stream));
-            CUDA_TRY(cudaStreamSynchronize(h->stream));  // g is a stack vector
-            grad_kernel<<<nblk((long long)g.size() * B, 256), 256, 0, h->stream>>>(h->d_grad, (int)g.size(), d_sens, B, B,
-                                                                                d_grad, B);
+        if (h->grad_n > 0) {
+            dim3 grid(nblk(B, 128), (unsigned)std::min(h->grad_n, 16384));
+            grad_kernel<<<grid, 128, 0, h->stream>>>(h->d_grad, h->grad_n, d_sens, B, B, d_grad, B, d_gsum);
             h->launches++;
         }
     }
@@ -868,6 +924,15 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     // ---- deliver
     if (!direct) {
         int r2 = 0;
+        if (!dev && !out_soa) {  // reserve one staging slice per host output
+            size_t tot = 0;
+            auto add = [&](bool w, long long n) { if (w) tot += ((sizeof(double) * (size_t)n * (size_t)B) + 255) & ~size_t(255); };
+            add(w_xend, (long long)nx * I); add(w_sens, h->n_sens); add(w_traj, nrow * h->n_samples);
+            add(w_def && out->defects_kind, ndef); add(w_def && out->defects_stage, ndef); add(w_obj, 1);
+            add(w_grad, nvars); add(w_fim && out->fim, (long long)h->fim_n * h->fim_n);
+            if (h->ws_out.reserve(tot)) return fail(CB200_ERR_NOMEM, "device out of memory (%zu bytes staging)", tot);
+            h->out_off = 0;
+        }
         if (w_xend) r2 |= deliver(h, d_xend, out->xend, (long long)nx * I, B, flags);
         if (w_sens) r2 |= deliver(h, d_sens, out->sens, h->n_sens, B, flags);
         if (w_traj) r2 |= deliver(h, d_traj, out->traj, nrow * h->n_samples, B, flags);
@@ -878,6 +943,9 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (w_fim && out->fim) r2 |= deliver(h, d_fim, out->fim, (long long)h->fim_n * h->fim_n, B, flags);
         if (r2) return r2;
     }
+    if (!dev && w_osum) CUDA_TRY(cudaMemcpyAsync(out->objective_sum, d_osum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (!dev && w_gsum)
+        CUDA_TRY(cudaMemcpyAsync(out->grad_sum, d_gsum, sizeof(double) * (size_t)nvars, cudaMemcpyDeviceToHost, h->stream));
     if (w_fim && out->fim_sum && !dev)
         CUDA_TRY(cudaMemcpyAsync(out->fim_sum, d_fsum, sizeof(double) * h->fim_n * h->fim_n, cudaMemcpyDeviceToHost,
                                  h->stream));

@@ -20,7 +20,7 @@ MEM_DEVICE, PS_SOA, OUT_SOA = 1, 2, 4
 EXPORTS = (
     "cb200_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_sizes",
     "cb200_block_structure", "cb200_set_stream", "cb200_eval", "cb200_jac_structure",
-    "cb200_last_kernel_ms", "cb200_launch_count", "cb200_probe_fp64_tflops",
+    "cb200_last_kernel_ms", "cb200_kernel_ms_history", "cb200_launch_count", "cb200_probe_fp64_tflops",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -46,7 +46,8 @@ class Out(C.Structure):
     _fields_ = [
         ("xend", C.c_void_p), ("sens", C.c_void_p), ("traj", C.c_void_p), ("defects_kind", C.c_void_p),
         ("defects_stage", C.c_void_p), ("objective", C.c_void_p), ("grad", C.c_void_p), ("fim", C.c_void_p),
-        ("fim_sum", C.c_void_p), ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
+        ("fim_sum", C.c_void_p), ("objective_sum", C.c_void_p), ("grad_sum", C.c_void_p),
+        ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
     ]
 
 
@@ -79,6 +80,8 @@ def lib():
         L.cb200_jac_structure.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
         L.cb200_last_kernel_ms.argtypes = [C.c_void_p]
         L.cb200_last_kernel_ms.restype = C.c_float
+        L.cb200_kernel_ms_history.argtypes = [C.c_void_p, C.POINTER(C.c_float), C.c_int]
+        L.cb200_kernel_ms_history.restype = C.c_int
         L.cb200_launch_count.argtypes = [C.c_void_p]
         L.cb200_launch_count.restype = C.c_int64
         L.cb200_probe_fp64_tflops.argtypes = [C.c_int, C.c_int]
@@ -177,6 +180,11 @@ class NativeLayer:
 
     def last_kernel_ms(self) -> float:
         return float(lib().cb200_last_kernel_ms(self._h))
+
+    def kernel_ms_history(self, n: int) -> np.ndarray:
+        buf = (C.c_float * max(n, 1))()
+        m = lib().cb200_kernel_ms_history(self._h, buf, n)
+        return np.array(buf[:m], dtype=np.float64)
 
     def launch_count(self) -> int:
         return int(lib().cb200_launch_count(self._h))

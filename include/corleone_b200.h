@@ -127,7 +127,10 @@ typedef struct {
  *   objective      n = 1
  *   grad           n = nvars
  *   fim            n = fim_n*fim_n     column-major symmetric matrix
- *   fim_sum        fim_n*fim_n doubles total: sum over the B candidates of `fim` (+ nothing else)
+ *   fim_sum        fim_n*fim_n doubles total: sum over the B candidates of `fim`
+ *   objective_sum  1 double total: sum over the B candidates of `objective`   (expectation-type objectives;
+ *   grad_sum       nvars doubles total: sum over the B candidates of `grad`    the per-rank partial sums that
+ *                                                                              are all-reduced across GPUs)
  */
 typedef struct {
     double *xend;
@@ -139,6 +142,8 @@ typedef struct {
     double *grad;
     double *fim;
     double *fim_sum;
+    double *objective_sum;
+    double *grad_sum;
     const double *fim_init;     /* [fim_n*fim_n] st.F_init or NULL = zeros (oed.jl:309-315) */
     int32_t objective_row;      /* 1-based row of a trajectory sample: state k or nx + control r */
     int32_t reserved;
@@ -182,6 +187,9 @@ int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int
 /* Device time of the last cb200_eval's integration kernel(s) in milliseconds (CUDA events on the
  * handle's stream); < 0 if none. */
 float cb200_last_kernel_ms(const cb200_handle *h);
+/* Device times of the integration kernel of the last n cb200_eval calls (newest first, at most 256 kept);
+ * returns how many were written.  Synchronises on the recorded events only. */
+int cb200_kernel_ms_history(const cb200_handle *h, float *ms, int n);
 /* kernels launched by this handle since creation */
 int64_t cb200_launch_count(const cb200_handle *h);
 

@@ -1,0 +1,72 @@
+"""The C-ABI shared library loads on a CPU-only box and exports every symbol include/corleone_b200.h declares;
+without a GPU the product path fails loudly (no CPU fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import corleone_b200 as cb
+import problems as P
+from corleone_b200 import native
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "corleone_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(cb200_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    names = _declared()
+    assert len(names) >= 12
+    L = ctypes.CDLL(native.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), f"{n} declared in include/corleone_b200.h but not exported"
+    assert set(names) == set(native.EXPORTS)
+    assert native.lib().cb200_version() == 100
+
+
+def test_struct_layouts_match_header():
+    assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8
+    assert ctypes.sizeof(native.Out) == 12 * 8 + 8
+    assert ctypes.sizeof(native.Sizes) == 7 * 8
+
+
+def test_bad_descriptor_is_rejected_before_any_device_work():
+    L = native.lib()
+    d = native.Desc()
+    h = ctypes.c_void_p()
+    d.struct_size = 4
+    assert L.cb200_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b"struct_size" in L.cb200_last_error()
+    d.struct_size = ctypes.sizeof(native.Desc)
+    d.model = 99
+    assert L.cb200_create(ctypes.byref(d), ctypes.byref(h)) == -3
+
+
+def test_no_cpu_fallback():
+    try:
+        import torch
+        has_gpu = torch.cuda.is_available()
+    except Exception:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("GPU present")
+    lay = P.product_layer(P.lotka_spec(), cb.Tsit5(1))
+    ps, st = cb.setup(None, lay)
+    with pytest.raises(native.NativeError, match="no CPU fallback"):
+        lay(None, ps, st)
+    assert native.probe_fp64_tflops(0, 10) < 0
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "corleone.jl_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "oracle" not in txt.lower() or f == "configs.py", f"{f} mentions the oracle"
