@@ -54,7 +54,7 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+        self.rows, self.proc, self.index, self.start = [], None, index, 0
 
     def __enter__(self):
         try:
@@ -66,6 +66,15 @@ class ClockSampler:
         except Exception:
             self.proc = None
         return self
+
+    def wait_first(self, timeout=5.0):
+        t_end = time.time() + timeout
+        while self.proc and not self.rows and time.time() < t_end:
+            time.sleep(0.02)
+
+    def mark(self):
+        """samples taken from now on are the ones reported (the GPU is under load from here)"""
+        self.start = len(self.rows)
 
     def _read(self):
         for line in self.proc.stdout:
@@ -82,7 +91,7 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], 0.0, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in self.rows[self.start:]:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
@@ -230,29 +239,34 @@ def main():
     for s in range(max(3, args.warmup)):
         step(s)
     barrier()
-    launches0 = N.launch_count()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local_rank) as clk:
+        clk.wait_first()
+        # put the GPU under the same load for ~0.7 s before the timed region so that the sampler (100 ms
+        # period) sees the clocks this workload actually runs at; these steps are extra warm-up
+        t_end, s2 = time.time() + 0.7, 0
+        clk.mark()
+        while time.time() < t_end:
+            step(s2)
+            s2 += 1
+            if s2 % 64 == 0:
+                torch.cuda.synchronize()
         barrier()
+        launches0 = N.launch_count()
         ev0.record(stream)
         for s in range(args.steps):
             step(s)
         ev1.record(stream)
         barrier()
         ms_total = ev0.elapsed_time(ev1)
-        # keep the sampler alive for at least ~0.5 s of load so it sees the clocks under load
-        t_end = time.time() + 0.6
-        s2 = 0
+        launches_timed = N.launch_count() - launches0
+        # kernel durations of the timed steps (event pairs the library records around the integration kernel)
+        hist = N.kernel_ms_history(min(256, args.steps))
+        kern_ms = float(np.mean(hist)) if len(hist) else float("nan")
+        t_end = time.time() + 0.3
         while time.time() < t_end:
-            step(s2)
-            s2 += 1
+            step(0)
         torch.cuda.synchronize()
-    launches = N.launch_count() - launches0
-    extra_launch = s2 * (launches // max(1, args.steps))
-    launches_timed = launches - extra_launch
-    # kernel durations of the timed steps (event pairs recorded by the library around the integration kernel)
-    hist = N.kernel_ms_history(min(256, args.steps + s2))
-    kern_ms = float(np.mean(hist[s2:s2 + args.steps])) if len(hist) > s2 else float("nan")
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

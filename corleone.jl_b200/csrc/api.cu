@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "common.cuh"
+#include "tableau.cuh"
 
 using namespace cb200;
 
@@ -263,7 +264,7 @@ struct cb200_handle {
 static int default_G(int model)
 {
     switch (model) {
-    case CB200_MODEL_LQR: return 2;
+    case CB200_MODEL_LQR: return 8;
     case CB200_MODEL_LOTKA3: return 2;
     case CB200_MODEL_LOTKA2: return 2;
     case CB200_MODEL_LIN1D: return 4;
@@ -397,7 +398,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     }
 
     // per-interval tables
-    std::vector<double> pt0, pt1, ic_fix;
+    std::vector<double> pt0, pt1, ph, ic_fix;
     int po = 0, vo = 0, so = 0, co = 0, sio = 0;
     long long seo = 0;
     long long igo = 0;
@@ -421,6 +422,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         for (int j = 0; j < M; j++) {
             pt0.push_back(d->tspans[2 * (size_t)(po + j)]);
             pt1.push_back(d->tspans[2 * (size_t)(po + j) + 1]);
+            ph.push_back((pt1.back() - pt0.back()) / (double)d->steps_per_piece);
             for (int r = 0; r < nact; r++) {
                 const long long ci = d->index_grid[igo + r + (long long)nact * j] - 1;
                 if (ci < 0 || ci >= d->n_local_controls[i]) {
@@ -544,7 +546,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     // upload
     std::vector<char> blob;
     const size_t o_M = push(blob, h->h_M), o_po = push(blob, h->h_piece_off), o_t0 = push(blob, pt0),
-                 o_t1 = push(blob, pt1), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
+                 o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
                  o_if = push(blob, ic_fix), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
                  o_de = push(blob, h->defects), o_q = push(blob, h->quad0);
@@ -565,6 +567,21 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.piece_off = (const int *)(base + o_po);
     L.pt0 = (const double *)(base + o_t0);
     L.pt1 = (const double *)(base + o_t1);
+    L.ph = (const double *)(base + o_ph);
+    L.uniform_h = 1;
+    for (double hh : ph) L.uniform_h &= (hh == ph[0]);
+    for (int k = 0; k < 21; k++) L.hA[k] = 0.0;
+    if (d->method == CB200_TSIT5) {
+        using namespace cb200::ts5;
+        const double a[21] = {a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65,
+                              a71, a72, a73, a74, a75, a76};
+        for (int k = 0; k < 21; k++) L.hA[k] = ph[0] * a[k];
+    } else {
+        L.hA[0] = 0.5 * ph[0];
+        L.hA[1] = ph[0];
+        L.hA[2] = ph[0] / 6.0;
+        L.hA[3] = ph[0] / 3.0;
+    }
     L.cidx = (const int *)(base + o_ci);
     L.var_off = (const int *)(base + o_vo);
     L.n_u0 = (const int *)(base + o_nu);

@@ -14,6 +14,9 @@ struct DevLayer {
     int nx, np_all, nact, ntp, I, K;
     int R;            // direction groups per unit = max_i ceil(ns_i / G); 1 when G == 0
     int nvars;
+    int flat;                // launch mapping: 1 = flat thread index (tiny batches), 0 = grid (b-tiles, i, r)
+    int uniform_h;           // every piece of the layer has the same step size h = (t1 - t0)/K
+    double hA[21];           // uniform_h: h * a_ij (Tsit5, slots as tsit5_coeffs) or the 4 RK4 factors
     int pmap_kind[MAX_NP];   // p_full[q] = kind ? controls_j[idx] : ps.p[idx]   (A, B of single_shooting.jl:306-323)
     int pmap_idx[MAX_NP];
     int tunable_p0[MAX_NP];  // 0-based p index of tunable parameter m
@@ -22,6 +25,7 @@ struct DevLayer {
     const int *piece_off;    // [I] offset into the piece arrays
     const double *pt0;       // [sum M] piece start
     const double *pt1;       // [sum M] piece end
+    const double *ph;        // [sum M] step size of the piece, (t1 - t0)/K
     const int *cidx;         // [sum M * nact] 0-based local control index of (piece, row)
     const int *var_off;      // [I] offset of the interval's block in the flat ps
     const int *n_u0;         // [I]

@@ -1,11 +1,19 @@
 // Device model registry: right-hand sides and their directional derivatives.
 //
 // The reference integrates arbitrary Julia closures (src/single_shooting.jl:443-453) and differentiates
-// them with ForwardDiff; a C-ABI CUDA library needs the RHS compiled in.  Every model gives
-//   f(x, p, dx)                      dx = f(x, p)
-//   jvp(x, p, v, pcol, dv)           dv = f_x(x, p) v + (pcol >= 0 ? f_p(x, p)[:, pcol] : 0)
-// where p is the FULL problem.p vector (controls scattered in, src/single_shooting.jl:306-323) and pcol is
-// a 0-based column of it.  All loops are unrolled and all arrays live in registers.
+// them with ForwardDiff; a C-ABI CUDA library needs the RHS compiled in.  State vectors are ordered
+// [NXD dynamic states; NQ quadrature states]: quadrature states (Lagrange terms, Fisher-information
+// entries) never enter a right-hand side, so the integrator needs no stage storage for them.
+//
+// Every model gives
+//   f(x, p, dx, ctx)                 dx[0..NX) = f(x, p); x holds the NXD dynamic states only;
+//                                    ctx keeps what the Jacobian-vector products of the same stage reuse
+//   make_force(pcol, p)              per control piece: the p-direction of a sensitivity column
+//                                    (pcol = 0-based column of the FULL problem.p, -1 = none)
+//   jvp(x, p, ctx, v, F, dv)         dv[0..NX) = f_x(x, p) v + f_p(x, p)[:, pcol]; v holds NXD entries
+// p is the full parameter vector with the controls scattered in (src/single_shooting.jl:306-323).
+// The p-direction is applied through precomputed weights (Force), not branches: the step body is one
+// straight-line block of FP64 instructions.
 #pragma once
 #include <cuda_runtime.h>
 
@@ -13,150 +21,174 @@ namespace cb200 {
 
 #define CB_DEV static __device__ __forceinline__
 
-// model constants for DENSE20 (W row-major 20x20, then b[20]); one copy per translation unit that uses it
 #ifdef CB200_NEED_DENSE20_DATA
+// model constants for DENSE20 (W row-major 20x20, then b[20]); constant-bank operands of the FMAs
 __constant__ double c_dense20[420];
 #endif
 
 // ---- Lotka-Volterra fishing with Lagrange state (examples/lotka_fishing_optimal_control/main.jl:38-42)
 struct Lotka3 {
-    static constexpr int NX = 3, NP = 3;
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 3;
     static constexpr bool HAS_JVP = true;
-    CB_DEV void f(const double *x, const double *p, double *dx)
+    struct Ctx {
+        double j00, j01, j10, j11, x12, q0, q1;
+    };
+    struct Force {
+        double c00, c01, c10, c11;  // d0 += c00 x0 + c01 x0 x1 ; d1 += c10 x1 + c11 x0 x1
+    };
+    CB_DEV void f(const double *x, const double *p, double *dx, Ctx &c)
     {
-        const double x12 = x[0] * x[1];
-        dx[0] = x[0] - p[1] * x12 - 0.4 * p[0] * x[0];
-        dx[1] = -x[1] + p[2] * x12 - 0.2 * p[0] * x[1];
+        c.x12 = x[0] * x[1];
+        c.j00 = 1.0 - p[1] * x[1] - 0.4 * p[0];
+        c.j01 = -p[1] * x[0];
+        c.j10 = p[2] * x[1];
+        c.j11 = -1.0 + p[2] * x[0] - 0.2 * p[0];
+        dx[0] = x[0] - p[1] * c.x12 - 0.4 * p[0] * x[0];
+        dx[1] = -x[1] + p[2] * c.x12 - 0.2 * p[0] * x[1];
         const double a = x[0] - 1.0, b = x[1] - 1.0;
+        c.q0 = 2.0 * a;
+        c.q1 = 2.0 * b;
         dx[2] = a * a + b * b;
     }
-    CB_DEV void jvp(const double *x, const double *p, const double *v, int pcol, double *dv)
+    CB_DEV Force make_force(int pcol, const double *)
     {
-        const double j00 = 1.0 - p[1] * x[1] - 0.4 * p[0], j01 = -p[1] * x[0];
-        const double j10 = p[2] * x[1], j11 = -1.0 + p[2] * x[0] - 0.2 * p[0];
-        double d0 = j00 * v[0] + j01 * v[1];
-        double d1 = j10 * v[0] + j11 * v[1];
-        const double d2 = 2.0 * (x[0] - 1.0) * v[0] + 2.0 * (x[1] - 1.0) * v[1];
+        Force F{0.0, 0.0, 0.0, 0.0};
         if (pcol == 0) {
-            d0 -= 0.4 * x[0];
-            d1 -= 0.2 * x[1];
+            F.c00 = -0.4;
+            F.c10 = -0.2;
         } else if (pcol == 1) {
-            d0 -= x[0] * x[1];
+            F.c01 = -1.0;
         } else if (pcol == 2) {
-            d1 += x[0] * x[1];
+            F.c11 = 1.0;
         }
-        dv[0] = d0;
-        dv[1] = d1;
-        dv[2] = d2;
+        return F;
+    }
+    CB_DEV void jvp(const double *x, const double *, const Ctx &c, const double *v, const Force &F, double *dv)
+    {
+        dv[0] = fma(c.j00, v[0], fma(c.j01, v[1], fma(F.c00, x[0], F.c01 * c.x12)));
+        dv[1] = fma(c.j10, v[0], fma(c.j11, v[1], fma(F.c10, x[1], F.c11 * c.x12)));
+        dv[2] = fma(c.q0, v[0], c.q1 * v[1]);
     }
 };
 
 // ---- Lotka-Volterra without the Lagrange state (lib/CorleoneOED/examples/lotka_oed/main.jl:61-65)
 struct Lotka2 {
-    static constexpr int NX = 2, NP = 3;
+    static constexpr int NX = 2, NXD = 2, NQ = 0, NP = 3;
     static constexpr bool HAS_JVP = true;
-    CB_DEV void f(const double *x, const double *p, double *dx)
+    struct Ctx {
+        double j00, j01, j10, j11, x12;
+    };
+    using Force = Lotka3::Force;
+    CB_DEV void f(const double *x, const double *p, double *dx, Ctx &c)
     {
-        const double x12 = x[0] * x[1];
-        dx[0] = x[0] - p[1] * x12 - 0.4 * p[0] * x[0];
-        dx[1] = -x[1] + p[2] * x12 - 0.2 * p[0] * x[1];
+        c.x12 = x[0] * x[1];
+        c.j00 = 1.0 - p[1] * x[1] - 0.4 * p[0];
+        c.j01 = -p[1] * x[0];
+        c.j10 = p[2] * x[1];
+        c.j11 = -1.0 + p[2] * x[0] - 0.2 * p[0];
+        dx[0] = x[0] - p[1] * c.x12 - 0.4 * p[0] * x[0];
+        dx[1] = -x[1] + p[2] * c.x12 - 0.2 * p[0] * x[1];
     }
-    CB_DEV void jvp(const double *x, const double *p, const double *v, int pcol, double *dv)
+    CB_DEV Force make_force(int pcol, const double *p) { return Lotka3::make_force(pcol, p); }
+    CB_DEV void jvp(const double *x, const double *, const Ctx &c, const double *v, const Force &F, double *dv)
     {
-        const double j00 = 1.0 - p[1] * x[1] - 0.4 * p[0], j01 = -p[1] * x[0];
-        const double j10 = p[2] * x[1], j11 = -1.0 + p[2] * x[0] - 0.2 * p[0];
-        double d0 = j00 * v[0] + j01 * v[1];
-        double d1 = j10 * v[0] + j11 * v[1];
-        if (pcol == 0) {
-            d0 -= 0.4 * x[0];
-            d1 -= 0.2 * x[1];
-        } else if (pcol == 1) {
-            d0 -= x[0] * x[1];
-        } else if (pcol == 2) {
-            d1 += x[0] * x[1];
-        }
-        dv[0] = d0;
-        dv[1] = d1;
+        dv[0] = fma(c.j00, v[0], fma(c.j01, v[1], fma(F.c00, x[0], F.c01 * c.x12)));
+        dv[1] = fma(c.j10, v[0], fma(c.j11, v[1], fma(F.c10, x[1], F.c11 * c.x12)));
     }
 };
 
 // ---- linear-quadratic regulator (examples/linear_quadratic/main.jl:45-50), p = (a, b, u)
 struct Lqr {
-    static constexpr int NX = 2, NP = 3;
+    static constexpr int NX = 2, NXD = 1, NQ = 1, NP = 3;
     static constexpr bool HAS_JVP = true;
-    CB_DEV void f(const double *x, const double *p, double *dx)
+    struct Ctx {
+        double j10;
+    };
+    struct Force {
+        double a0, b0, b1;  // d0 += a0 x0 + b0 ; d1 += b1
+    };
+    CB_DEV void f(const double *x, const double *p, double *dx, Ctx &c)
     {
-        dx[0] = p[0] * x[0] + p[1] * p[2];
+        dx[0] = fma(p[0], x[0], p[1] * p[2]);
         const double e = x[0] - 3.0;
-        dx[1] = 10.0 * e * e + 0.1 * p[2] * p[2];
+        c.j10 = 20.0 * e;
+        dx[1] = fma(10.0 * e, e, 0.1 * (p[2] * p[2]));
     }
-    CB_DEV void jvp(const double *x, const double *p, const double *v, int pcol, double *dv)
+    CB_DEV Force make_force(int pcol, const double *p)
     {
-        double d0 = p[0] * v[0];
-        double d1 = 20.0 * (x[0] - 3.0) * v[0];
+        Force F{0.0, 0.0, 0.0};
         if (pcol == 0) {
-            d0 += x[0];
+            F.a0 = 1.0;  // d f / d a = (x, 0)
         } else if (pcol == 1) {
-            d0 += p[2];
+            F.b0 = p[2];  // d f / d b = (u, 0)
         } else if (pcol == 2) {
-            d0 += p[1];
-            d1 += 0.2 * p[2];
+            F.b0 = p[1];  // d f / d u = (b, 0.2 u)
+            F.b1 = 0.2 * p[2];
         }
-        dv[0] = d0;
-        dv[1] = d1;
+        return F;
+    }
+    CB_DEV void jvp(const double *x, const double *p, const Ctx &c, const double *v, const Force &F, double *dv)
+    {
+        dv[0] = fma(p[0], v[0], fma(F.a0, x[0], F.b0));
+        dv[1] = fma(c.j10, v[0], F.b1);
     }
 };
 
 // ---- 1-D linear problem (lib/CorleoneOED/test/core/1d_oed.jl:11-13)
 struct Lin1d {
-    static constexpr int NX = 1, NP = 1;
+    static constexpr int NX = 1, NXD = 1, NQ = 0, NP = 1;
     static constexpr bool HAS_JVP = true;
-    CB_DEV void f(const double *x, const double *p, double *dx) { dx[0] = p[0] * x[0]; }
-    CB_DEV void jvp(const double *x, const double *p, const double *v, int pcol, double *dv)
+    struct Ctx {};
+    struct Force {
+        double w;
+    };
+    CB_DEV void f(const double *x, const double *p, double *dx, Ctx &) { dx[0] = p[0] * x[0]; }
+    CB_DEV Force make_force(int pcol, const double *) { return Force{pcol == 0 ? 1.0 : 0.0}; }
+    CB_DEV void jvp(const double *x, const double *p, const Ctx &, const double *v, const Force &F, double *dv)
     {
-        dv[0] = p[0] * v[0] + (pcol == 0 ? x[0] : 0.0);
+        dv[0] = fma(p[0], v[0], F.w * x[0]);
     }
 };
 
 // ---- Egerstedt switching problem (test/core/local_controls.jl:46-52)
 struct Egerstedt {
-    static constexpr int NX = 3, NP = 3;
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 3;
     static constexpr bool HAS_JVP = true;
-    CB_DEV void f(const double *u, const double *p, double *du)
+    struct Ctx {};
+    struct Force {
+        double w0, w1, w2;
+    };
+    CB_DEV void f(const double *u, const double *p, double *du, Ctx &)
     {
         const double x = u[0], y = u[1];
         du[0] = -x * p[0] + (x + y) * p[1] + (x - y) * p[2];
         du[1] = (x + 2.0 * y) * p[0] + (x - 2.0 * y) * p[1] + (x + y) * p[2];
         du[2] = x * x + y * y;
     }
-    CB_DEV void jvp(const double *u, const double *p, const double *v, int pcol, double *dv)
+    CB_DEV Force make_force(int pcol, const double *)
+    {
+        return Force{pcol == 0 ? 1.0 : 0.0, pcol == 1 ? 1.0 : 0.0, pcol == 2 ? 1.0 : 0.0};
+    }
+    CB_DEV void jvp(const double *u, const double *p, const Ctx &, const double *v, const Force &F, double *dv)
     {
         const double x = u[0], y = u[1];
-        double d0 = (-p[0] + p[1] + p[2]) * v[0] + (p[1] - p[2]) * v[1];
-        double d1 = (p[0] + p[1] + p[2]) * v[0] + (2.0 * p[0] - 2.0 * p[1] + p[2]) * v[1];
-        const double d2 = 2.0 * x * v[0] + 2.0 * y * v[1];
-        if (pcol == 0) {
-            d0 -= x;
-            d1 += x + 2.0 * y;
-        } else if (pcol == 1) {
-            d0 += x + y;
-            d1 += x - 2.0 * y;
-        } else if (pcol == 2) {
-            d0 += x - y;
-            d1 += x + y;
-        }
-        dv[0] = d0;
-        dv[1] = d1;
-        dv[2] = d2;
+        dv[0] = (-p[0] + p[1] + p[2]) * v[0] + (p[1] - p[2]) * v[1] + F.w0 * (-x) + F.w1 * (x + y) + F.w2 * (x - y);
+        dv[1] = (p[0] + p[1] + p[2]) * v[0] + (2.0 * p[0] - 2.0 * p[1] + p[2]) * v[1] + F.w0 * (x + 2.0 * y) +
+                F.w1 * (x - 2.0 * y) + F.w2 * (x + y);
+        dv[2] = 2.0 * x * v[0] + 2.0 * y * v[1];
     }
 };
 
 #ifdef CB200_NEED_DENSE20_DATA
 // ---- synthetic 20-state problem of BASELINE config 4: x' = W x - x.^3 + b u, p = (u)
 struct Dense20 {
-    static constexpr int NX = 20, NP = 1;
+    static constexpr int NX = 20, NXD = 20, NQ = 0, NP = 1;
     static constexpr bool HAS_JVP = true;
-    CB_DEV void f(const double *x, const double *p, double *dx)
+    struct Ctx {};
+    struct Force {
+        double w;
+    };
+    CB_DEV void f(const double *x, const double *p, double *dx, Ctx &)
     {
 #pragma unroll
         for (int i = 0; i < 20; i++) {
@@ -166,11 +198,12 @@ struct Dense20 {
             dx[i] = acc - x[i] * x[i] * x[i];
         }
     }
-    CB_DEV void jvp(const double *x, const double *p, const double *v, int pcol, double *dv)
+    CB_DEV Force make_force(int pcol, const double *) { return Force{pcol == 0 ? 1.0 : 0.0}; }
+    CB_DEV void jvp(const double *x, const double *, const Ctx &, const double *v, const Force &F, double *dv)
     {
 #pragma unroll
         for (int i = 0; i < 20; i++) {
-            double acc = (pcol == 0) ? c_dense20[400 + i] : 0.0;
+            double acc = F.w * c_dense20[400 + i];
 #pragma unroll
             for (int j = 0; j < 20; j++) acc = fma(c_dense20[i * 20 + j], v[j], acc);
             dv[i] = fma(-3.0 * x[i] * x[i], v[i], acc);
@@ -183,21 +216,26 @@ struct Dense20 {
 //   state  [x; vec(G) column-major nx x NF; F[triu] column-major]     (:239, selector :211)
 //   params [base p; w_1..w_NOBS]                                       (:228-230)
 //   G' = f_x G + f_p[:, params]  (:147-154),  F' = sum_i w_i (h_x[i,:] G)'(h_x[i,:] G)  (:222-233)
-// observed = the leading NOBS states, so h_x rows are unit rows.  Traits::PCOL(c) gives the 0-based p
-// column of Fisher parameter c.
+// observed = the leading NOBS states, so h_x rows are unit rows.  Traits::pcol(c) is the 0-based p column
+// of Fisher parameter c.  x and G are dynamic states; the F entries are quadratures.
 template <class Base, class Traits>
 struct OedAug {
+    static_assert(Base::NQ == 0, "OED base model must not carry quadrature states");
     static constexpr int BX = Base::NX, NF = Traits::NF, NOBS = Traits::NOBS;
-    static constexpr int NX = BX + BX * NF + NF * (NF + 1) / 2, NP = Base::NP + NOBS;
+    static constexpr int NXD = BX + BX * NF, NQ = NF * (NF + 1) / 2, NX = NXD + NQ, NP = Base::NP + NOBS;
     static constexpr bool HAS_JVP = false;
-    CB_DEV void f(const double *y, const double *p, double *dy)
+    struct Ctx {};
+    struct Force {};
+    CB_DEV void f(const double *y, const double *p, double *dy, Ctx &)
     {
-        Base::f(y, p, dy);
+        typename Base::Ctx c;
+        Base::f(y, p, dy, c);
 #pragma unroll
-        for (int c = 0; c < NF; c++) Base::jvp(y, p, y + BX + BX * c, Traits::pcol(c), dy + BX + BX * c);
+        for (int k = 0; k < NF; k++)
+            Base::jvp(y, p, c, y + BX + BX * k, Base::make_force(Traits::pcol(k), p), dy + BX + BX * k);
         const double *G = y + BX;
         const double *w = p + Base::NP;
-        double *dF = dy + BX + BX * NF;
+        double *dF = dy + NXD;
         int q = 0;
 #pragma unroll
         for (int b = 0; b < NF; b++)
@@ -209,7 +247,8 @@ struct OedAug {
                 dF[q++] = acc;
             }
     }
-    CB_DEV void jvp(const double *, const double *, const double *, int, double *) {}
+    CB_DEV Force make_force(int, const double *) { return Force{}; }
+    CB_DEV void jvp(const double *, const double *, const Ctx &, const double *, const Force &, double *) {}
 };
 struct LotkaOedTraits {
     static constexpr int NF = 2, NOBS = 2;
