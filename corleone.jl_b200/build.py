@@ -12,8 +12,9 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OBJ = os.path.join(HERE, "build")
-LIB = os.path.join(HERE, "libcorleone_b200.so")
+OBJ = os.path.join(HERE, os.environ.get("CB200_OBJ_DIR", "build"))
+LIB = os.path.join(HERE, os.environ.get("CB200_LIB_NAME", "libcorleone_b200.so"))
+EXTRA = os.environ.get("CB200_NVCC_EXTRA", "").split()   # tuning builds, e.g. -DCB200_MINB=4 (with CB200_OBJ_DIR)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -36,7 +37,7 @@ def build(force: bool = False, ptxas_v: bool = False) -> str:
     for src in sources:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
+            cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
             jobs.append((src, cmd))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

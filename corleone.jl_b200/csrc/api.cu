@@ -3,6 +3,7 @@
 #include "../../include/corleone_b200.h"
 
 #include <algorithm>
+#include <cmath>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -53,44 +54,27 @@ struct GradEntry {   // grad[var] = sens[src] (src >= 0) or 1.0 (src == -1)
 };
 
 // ------------------------------------------------------------------ kernels
-// K3: shooting defects, both orderings (src/multiple_shooting.jl:150-163, 229-295). One thread per
-// (defect, candidate), candidate fastest -> coalesced.
-__global__ void defects_kernel(const DefectEntry *__restrict__ tab, int ndef, const double *__restrict__ xend,
-                               const double *__restrict__ ps, long long ldb, long long ldx, long long B,
-                               double *__restrict__ dk, double *__restrict__ dst, long long ldo)
-{
-    const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (tid >= (long long)ndef * B) return;
-    const int e = (int)(tid / B);
-    const long long b = tid - (long long)e * B;
-    const DefectEntry t = tab[e];
-    const double a = t.a_kind == 0 ? xend[(long long)t.a_idx * ldx + b] : ps[(long long)t.a_idx * ldb + b];
-    const double c = t.b_kind == 1 ? ps[(long long)t.b_idx * ldb + b] : t.b_const;
-    const double d = a - c;
-    if (dk) dk[(long long)t.pos_kind * ldo + b] = d;
-    if (dst) dst[(long long)t.pos_stage * ldo + b] = d;
-}
-
-// objective = last(getsym(traj))  (src/dynprob.jl:70-71): one row of the last merged sample; a quadrature
-// row carries the running sum over intervals (src/multiple_shooting.jl:171-177).
-__global__ void objective_kernel(const double *__restrict__ xend, long long ldx, const double *__restrict__ ps,
-                                 long long ldb, long long B, int nx, int I, int state_k, int is_quad,
-                                 int ctrl_var, double *__restrict__ obj, double *__restrict__ obj_sum)
+// objective = last(getsym(traj))  (src/dynprob.jl:70-71): one row of the last merged sample.  col[i*ldc + b] is
+// the end value of that state on interval i (written by the shooting kernel); a quadrature row carries the
+// running sum over intervals in interval order (src/multiple_shooting.jl:171-177).
+__global__ void objective_kernel(const double *__restrict__ col, long long ldc, const double *__restrict__ ps,
+                                 long long ldb, long long B, int I, int has_state, int is_quad, int ctrl_var,
+                                 double *__restrict__ obj, double *__restrict__ obj_sum)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     double v = 0.0;
     if (b < B) {
-    if (state_k >= 0) {
-        if (is_quad) {
-            v = xend[(long long)state_k * ldx + b];  // q_prev = us[1][end][q]; then += across intervals in order
-            for (int i = 1; i < I; i++) v = xend[((long long)i * nx + state_k) * ldx + b] + v;
+        if (has_state) {
+            if (is_quad) {
+                v = col[b];  // q_prev = us[1][end][q]; then += across intervals in order
+                for (int i = 1; i < I; i++) v = col[(long long)i * ldc + b] + v;
+            } else {
+                v = col[(long long)(I - 1) * ldc + b];
+            }
         } else {
-            v = xend[((long long)(I - 1) * nx + state_k) * ldx + b];
+            v = ps[(long long)ctrl_var * ldb + b];
         }
-    } else {
-        v = ps[(long long)ctrl_var * ldb + b];
-    }
-    if (obj) obj[b] = v;
+        if (obj) obj[b] = v;
     }
     if (obj_sum) {  // whole warps reach this point: warp-shuffle tree, one atomic per warp
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
@@ -238,6 +222,8 @@ struct cb200_handle {
     std::vector<long long> h_sens_off;
     std::vector<int> h_cidx, h_ic_src;
     std::vector<DefectEntry> defects;
+    std::vector<int> dpos_kind, dpos_stage, oth_off;
+    std::vector<MatchEntry> oth;
     std::vector<long long> jac_rows, jac_cols, jac_src;
     long long n_sens = 0;
     int n_samples = 0;
@@ -249,7 +235,6 @@ struct cb200_handle {
     int *d_quad = nullptr;
     GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row
     int grad_cap = 0;
-    int grad_row = -1, grad_n = 0;    // objective_row the table was built for
     std::vector<GradEntry> h_grad;
     size_t out_off = 0;               // bump offset into ws_out during one eval
     cudaStream_t stream = nullptr;
@@ -258,13 +243,13 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq;
 };
 
 static int default_G(int model)
 {
     switch (model) {
-    case CB200_MODEL_LQR: return 8;
+    case CB200_MODEL_LQR: return 4;   // profiles/: G=4 at 4 blocks/SM beats G=8 at 2 (register-bound occupancy)
     case CB200_MODEL_LOTKA3: return 2;
     case CB200_MODEL_LOTKA2: return 2;
     case CB200_MODEL_LIN1D: return 4;
@@ -358,6 +343,11 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.I = I;
     L.K = d->steps_per_piece;
     L.R = 1;
+    h->G_sens = default_G(d->model);
+    if (const char *env = getenv("CB200_DIRS_PER_THREAD")) {
+        int g = atoi(env);
+        if (g > 0 && g <= 32) h->G_sens = g;
+    }
 
     // scatter maps A, B (src/single_shooting.jl:306-318): column ids in ascending p index
     {
@@ -471,6 +461,33 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     h->n_sens = seo;
     h->n_samples = so + 1;
 
+    // direction tables of the sensitivity kernel: the p column every local variable perturbs and, per piece
+    // and direction group, the mask of directions whose forcing term f_p / f_u is switched on
+    std::vector<signed char> dir_pcol((size_t)std::max(1, L.nvars), (signed char)-1);
+    const int Gs = h->G_sens;
+    const int Rmask = Gs > 0 ? std::max(1, (h->max_ns + Gs - 1) / Gs) : 1;
+    std::vector<unsigned> act_mask((size_t)po * Rmask, 0u);
+    for (int i = 0; i < I; i++) {
+        const int nu0 = h->h_n_u0[i], nc = h->h_n_c[i], M = h->h_M[i], pof = h->h_piece_off[i], vof = h->h_var_off[i];
+        std::vector<int> crow((size_t)std::max(1, nc), -1);
+        for (int j = 0; j < M; j++)
+            for (int r = 0; r < nact; r++) crow[h->h_cidx[(size_t)(pof + j) * nact + r]] = r;
+        for (int dd = 0; dd < h->ns[i]; dd++) {
+            int pc = -1;
+            if (dd >= nu0 && dd < nu0 + ntp)
+                pc = L.tunable_p0[dd - nu0];
+            else if (dd >= nu0 + ntp && crow[dd - nu0 - ntp] >= 0)
+                pc = L.row_to_p[crow[dd - nu0 - ntp]];
+            dir_pcol[(size_t)vof + dd] = (signed char)pc;
+            if (Gs <= 0 || pc < 0) continue;
+            for (int j = 0; j < M; j++) {
+                const bool on = (dd < nu0 + ntp) ||
+                                h->h_cidx[(size_t)(pof + j) * nact + crow[dd - nu0 - ntp]] == dd - nu0 - ntp;
+                if (on) act_mask[(size_t)(pof + j) * Rmask + dd / Gs] |= 1u << (dd % Gs);
+            }
+        }
+    }
+
     // defect table + Jacobian structure (src/multiple_shooting.jl:150-163, 281-295)
     {
         int n_u = 0, n_p = 0, n_c = 0;
@@ -478,6 +495,9 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
             for (int q = sidx_off[i]; q < sidx_off[i + 1]; q++) (d->shooting_indices[q] <= nx ? n_u : n_c)++;
             n_p += ntp;
         }
+        h->dpos_kind.assign((size_t)I * nx, -1);
+        h->dpos_stage.assign((size_t)I * nx, -1);
+        h->oth_off.assign((size_t)I + 1, 0);
         int ou = 0, op = n_u, oc = n_u + n_p, os = 0;
         auto ctrl_var = [&](int iv, int piece, int r) {
             return h->h_var_off[iv] + h->h_n_u0[iv] + ntp + h->h_cidx[(size_t)(h->h_piece_off[iv] + piece) * nact + r];
@@ -489,6 +509,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                         DefectEntry e{1, h->h_var_off[i - 1] + h->h_n_u0[i - 1] + k, 1,
                                       h->h_var_off[i] + h->h_n_u0[i] + k, 0.0, op, os};
                         h->defects.push_back(e);
+                        h->oth.push_back(MatchEntry{e.a_idx, e.b_idx, op, os});
                         h->jac_rows.push_back(op + 1); h->jac_cols.push_back(e.a_idx + 1); h->jac_src.push_back(-1);
                         h->jac_rows.push_back(op + 1); h->jac_cols.push_back(e.b_idx + 1); h->jac_src.push_back(-2);
                         op++;
@@ -506,6 +527,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                     if (rI < nx) {
                         e.a_kind = 0;
                         e.a_idx = (i - 1) * nx + rI;
+                        h->dpos_kind[(size_t)(i - 1) * nx + rI] = o;
+                        h->dpos_stage[(size_t)(i - 1) * nx + rI] = os;
                         const int src = h->h_ic_src[(size_t)i * nx + rI];
                         if (src >= 0) {
                             e.b_kind = 1;
@@ -532,6 +555,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                         e.a_idx = ctrl_var(i - 1, h->h_M[i - 1] - 1, r);
                         e.b_kind = 1;
                         e.b_idx = ctrl_var(i, 0, r);
+                        h->oth.push_back(MatchEntry{e.a_idx, e.b_idx, o, os});
                         h->jac_rows.push_back(o + 1); h->jac_cols.push_back(e.a_idx + 1); h->jac_src.push_back(-1);
                         h->jac_rows.push_back(o + 1); h->jac_cols.push_back(e.b_idx + 1); h->jac_src.push_back(-2);
                     }
@@ -540,7 +564,9 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                     os++;
                 }
             }
+            h->oth_off[i] = (int)h->oth.size();   // boundary i-1 owns oth[oth_off[i-1], oth_off[i])
         }
+        for (int i = std::max(I, 1); i <= I; i++) h->oth_off[i] = (int)h->oth.size();
     }
 
     // upload
@@ -549,7 +575,9 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
                  o_if = push(blob, ic_fix), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
-                 o_de = push(blob, h->defects), o_q = push(blob, h->quad0);
+                 o_de = push(blob, h->defects), o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol),
+                 o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
+                 o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth);
     const size_t o_gr = (blob.size() + 15) & ~size_t(15);
     h->grad_cap = std::max(1, L.nvars);
     blob.resize(o_gr + sizeof(GradEntry) * (size_t)h->grad_cap);
@@ -568,19 +596,32 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.pt0 = (const double *)(base + o_t0);
     L.pt1 = (const double *)(base + o_t1);
     L.ph = (const double *)(base + o_ph);
+    // One step size for the whole layer when every piece has the same h = (t1 - t0)/K up to the rounding of
+    // the grid points (a few ulp of the
+    // grid points t0, t1 themselves): the reference's `adaptive = false, dt = h` is a single dt for
+    // all pieces too.  The coefficient products h*a_ij then are kernel-parameter constants.
+    double h_ref = ph[0];
+    {
+        std::vector<double> srt(ph);
+        std::nth_element(srt.begin(), srt.begin() + srt.size() / 2, srt.end());
+        h_ref = srt[srt.size() / 2];
+    }
     L.uniform_h = 1;
-    for (double hh : ph) L.uniform_h &= (hh == ph[0]);
+    for (size_t q = 0; q < ph.size(); q++) {
+        // t1 - t0 carries the rounding of the grid points themselves: a few ulp of max(|t0|, |t1|)
+        const double tol = 4.0 * 2.220446049250313e-16 * std::max(fabs(pt0[q]), fabs(pt1[q])) / (double)d->steps_per_piece;
+        L.uniform_h &= (fabs(ph[q] - h_ref) <= tol + 8.0 * 2.220446049250313e-16 * fabs(h_ref));
+    }
+    if (getenv("CB200_EXACT_PIECE_STEPS")) {
+        L.uniform_h = 1;
+        for (double hh : ph) L.uniform_h &= (hh == ph[0]);
+        h_ref = ph[0];
+    }
     for (int k = 0; k < 21; k++) L.hA[k] = 0.0;
     if (d->method == CB200_TSIT5) {
-        using namespace cb200::ts5;
-        const double a[21] = {a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65,
-                              a71, a72, a73, a74, a75, a76};
-        for (int k = 0; k < 21; k++) L.hA[k] = ph[0] * a[k];
+        tsit5_coeffs(h_ref, L.hA);
     } else {
-        L.hA[0] = 0.5 * ph[0];
-        L.hA[1] = ph[0];
-        L.hA[2] = ph[0] / 6.0;
-        L.hA[3] = ph[0] / 3.0;
+        rk4_coeffs(h_ref, L.hA);
     }
     L.cidx = (const int *)(base + o_ci);
     L.var_off = (const int *)(base + o_vo);
@@ -590,6 +631,12 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.ic_fix = (const double *)(base + o_if);
     L.sens_off = (const long long *)(base + o_se);
     L.samp_off = (const int *)(base + o_so);
+    L.dir_pcol = (const signed char *)(base + o_dp);
+    L.act_mask = (const unsigned *)(base + o_am);
+    L.dpos_kind = (const int *)(base + o_dk);
+    L.dpos_stage = (const int *)(base + o_dst);
+    L.oth_off = (const int *)(base + o_oo);
+    L.oth = (const MatchEntry *)(base + o_ot);
     h->d_defects = (DefectEntry *)(base + o_de);
     h->d_quad = (int *)(base + o_q);
     h->d_grad = (GradEntry *)(base + o_gr);
@@ -611,11 +658,6 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         e = cudaEventCreate(&h->ev1[k]);
         if (e != cudaSuccess) return bail("cudaEventCreate", e);
     }
-    h->G_sens = default_G(d->model);
-    if (const char *env = getenv("CB200_DIRS_PER_THREAD")) {
-        int g = atoi(env);
-        if (g > 0) h->G_sens = g;
-    }
     *out = h;
     return CB200_OK;
 }
@@ -626,7 +668,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums})
+                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq})
         b->release();
     if (h->tables) cudaFree(h->tables);
     for (int k = 0; k < cb200_handle::EV_RING; k++) {
@@ -772,7 +814,6 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     const bool w_fim = (want & CB200_WANT_FIM) && (out->fim || out->fim_sum);
     const bool w_osum = (want & CB200_WANT_OBJ) && out->objective_sum;
     const bool w_gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
-    const bool need_sens = w_sens || w_grad || w_gsum;
     if (w_fim && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
     int obj_state = -1, obj_ctrl_var = -1, obj_quad = 0;
     if (w_obj || w_grad || w_osum || w_gsum) {
@@ -828,10 +869,17 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         return 0;
     };
     double *d_xend, *d_sens, *d_traj, *d_dk, *d_ds, *d_obj, *d_grad, *d_fim;
-    const bool need_xend = w_def || w_obj || w_osum || w_fim || (w_traj && h->nquad > 0);
+    const bool need_xend = w_fim || (w_traj && h->nquad > 0);
+    const bool fused_grad = (w_grad || w_gsum) && obj_state >= 0;   // gradient written by the shooting kernel
+    const bool need_sens = w_sens || fused_grad;                    // sensitivity directions are integrated
+    double *d_objq = nullptr;
+    if ((w_obj || w_osum) && obj_state >= 0) {
+        if (h->ws_objq.reserve(sizeof(double) * (size_t)I * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
+        d_objq = (double *)h->ws_objq.p;
+    }
     int oom = 0;
     oom |= buf(h->ws_xend, out->xend, (long long)nx * I, w_xend, need_xend, &d_xend);
-    oom |= buf(h->ws_sens, out->sens, h->n_sens, w_sens, need_sens, &d_sens);
+    oom |= buf(h->ws_sens, out->sens, h->n_sens, w_sens, false, &d_sens);
     oom |= buf(h->ws_traj, out->traj, nrow * h->n_samples, w_traj, false, &d_traj);
     oom |= buf(h->ws_dk, out->defects_kind, ndef, w_def && out->defects_kind, false, &d_dk);
     oom |= buf(h->ws_ds, out->defects_stage, ndef, w_def && out->defects_stage, false, &d_ds);
@@ -849,25 +897,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         L.R = (h->max_ns + G - 1) / G;
         if (L.R < 1) L.R = 1;
     }
-    ShootOut so{d_xend, d_sens, d_traj, B};
-    const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
-    CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], h->stream));
-    int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, h->stream);
-    if (rc == -1000)
-        return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
-                    h->method);
-    if (rc) return fail(CB200_ERR_CUDA, "shoot kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    h->launches++;
-    CUDA_TRY(cudaEventRecord(h->ev1[ev_slot], h->stream));
-    h->n_timed++;
-
-    // ---- K3: defects / objective / gradient / trajectory quadratures / FIM
-    if (w_def && ndef > 0) {
-        defects_kernel<<<nblk(ndef * B, 256), 256, 0, h->stream>>>(h->d_defects, (int)ndef, d_xend, d_ps, d_ldb, B, B,
-                                                                 d_dk, d_ds, B);
-        h->launches++;
-    }
-    // cross-candidate sums (expectation-type objective / gradient): accumulate on the device, deliver 1 + nvars doubles
+    // cross-candidate sums (expectation-type objective / gradient): accumulated on the device, 1 + nvars doubles
     double *d_osum = nullptr, *d_gsum = nullptr;
     if (w_osum || w_gsum) {
         if (dev) {
@@ -881,33 +911,41 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (d_osum) CUDA_TRY(cudaMemsetAsync(d_osum, 0, sizeof(double), h->stream));
         if (d_gsum) CUDA_TRY(cudaMemsetAsync(d_gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
     }
+    ShootOut so{};
+    so.xend = d_xend;
+    so.sens = d_sens;
+    so.traj = d_traj;
+    so.ldo = B;
+    so.dk = (w_def && ndef > 0) ? d_dk : nullptr;
+    so.dst = (w_def && ndef > 0) ? d_ds : nullptr;
+    so.objq = d_objq;
+    so.grad = fused_grad ? d_grad : nullptr;
+    so.grad_sum = fused_grad ? d_gsum : nullptr;
+    so.obj_state = obj_state;
+    so.obj_all = obj_quad;
+    const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
+    CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], h->stream));
+    int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, h->stream);
+    if (rc == -1000)
+        return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
+                    h->method);
+    if (rc) return fail(CB200_ERR_CUDA, "shoot kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    h->launches++;
+    CUDA_TRY(cudaEventRecord(h->ev1[ev_slot], h->stream));
+    h->n_timed++;
+
+    // ---- K3 remainder: objective sum over intervals, control-row gradient, trajectory quadratures, FIM
     if (w_obj || w_osum) {
-        objective_kernel<<<nblk(B, 256), 256, 0, h->stream>>>(d_xend, B, d_ps, d_ldb, B, nx, I, obj_state, obj_quad,
+        objective_kernel<<<nblk(B, 256), 256, 0, h->stream>>>(d_objq, B, d_ps, d_ldb, B, I, obj_state >= 0, obj_quad,
                                                             obj_ctrl_var, d_obj, d_osum);
         h->launches++;
     }
-    if (w_grad || w_gsum) {
+    if ((w_grad || w_gsum) && !fused_grad) {  // objective = a control row: the gradient is a unit vector
         if (d_grad) CUDA_TRY(cudaMemsetAsync(d_grad, 0, sizeof(double) * (size_t)nvars * (size_t)B, h->stream));
-        if (h->grad_row != out->objective_row) {  // gather table: built once per objective row, kept in the handle
-            h->h_grad.clear();
-            if (obj_state >= 0) {
-                for (int i = obj_quad ? 0 : I - 1; i < I; i++)
-                    for (int dd = 0; dd < h->ns[i]; dd++)
-                        h->h_grad.push_back({h->h_var_off[i] + dd, h->h_sens_off[i] + (long long)dd * nx + obj_state});
-            } else {
-                h->h_grad.push_back({obj_ctrl_var, -1});
-            }
-            h->grad_n = (int)h->h_grad.size();
-            if (h->grad_n > 0)
-                CUDA_TRY(cudaMemcpyAsync(h->d_grad, h->h_grad.data(), sizeof(GradEntry) * h->h_grad.size(),
-                                         cudaMemcpyHostToDevice, h->stream));
-            h->grad_row = out->objective_row;
-        }
-        if (h->grad_n > 0) {
-            dim3 grid(nblk(B, 128), (unsigned)std::min(h->grad_n, 16384));
-            grad_kernel<<<grid, 128, 0, h->stream>>>(h->d_grad, h->grad_n, d_sens, B, B, d_grad, B, d_gsum);
-            h->launches++;
-        }
+        h->h_grad.assign(1, GradEntry{obj_ctrl_var, -1});
+        CUDA_TRY(cudaMemcpyAsync(h->d_grad, h->h_grad.data(), sizeof(GradEntry), cudaMemcpyHostToDevice, h->stream));
+        grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, h->stream>>>(h->d_grad, 1, d_sens, B, B, d_grad, B, d_gsum);
+        h->launches++;
     }
     if (w_traj && h->nquad > 0 && I > 1) {
         traj_quad_kernel<<<nblk(B, 128), 128, 0, h->stream>>>(d_traj, B, d_xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,

@@ -34,6 +34,17 @@ struct DevLayer {
     const double *ic_fix;    // [I*nx]
     const long long *sens_off;  // [I] first row of the interval's block in `sens`
     const int *samp_off;     // [I] first merged-trajectory sample of the interval
+    const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
+    const unsigned *act_mask;     // [sum M][R] bit g: direction r*G+g is forced during the piece (G = handle's group size)
+    // shooting defects of the boundary between interval i and i+1 (src/multiple_shooting.jl:150-163)
+    const int *dpos_kind;    // [I*nx] position of the state matching of state k in shooting_constraints, -1: none
+    const int *dpos_stage;   // [I*nx] same, in stage_ordered_shooting_constraints
+    const int *oth_off;      // [I+1] range of the boundary's parameter / control matchings in `oth`
+    const struct MatchEntry *oth;
+};
+
+struct MatchEntry {  // defect = ps[a] - ps[b]  (parameter and control matchings)
+    int a, b, pos_kind, pos_stage;
 };
 
 struct ShootOut {
@@ -41,6 +52,14 @@ struct ShootOut {
     double *sens;  // [(sens_off[i] + d*nx + k) * ldo + b]
     double *traj;  // [((samp_off[i] + j) * nrow + r) * ldo + b]
     long long ldo;
+    // fused epilogue (K3): defects in both orderings, the objective state of every interval, objective gradient
+    double *dk;        // [pos_kind * ldo + b]
+    double *dst;       // [pos_stage * ldo + b]
+    double *objq;      // [i * ldo + b] end value of state obj_state on interval i
+    double *grad;      // [var * ldo + b]
+    double *grad_sum;  // [var] sum over the candidates of this launch (atomicAdd of warp partial sums)
+    int obj_state;     // 0-based state row of the objective, -1: none
+    int obj_all;       // 1: every interval contributes to the objective (quadrature state), 0: last interval only
 };
 
 // launchers, one per model translation unit; return cudaError_t as int, or -1000 if (G, method) is not

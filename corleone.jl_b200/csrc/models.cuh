@@ -52,16 +52,8 @@ struct Lotka3 {
     }
     CB_DEV Force make_force(int pcol, const double *)
     {
-        Force F{0.0, 0.0, 0.0, 0.0};
-        if (pcol == 0) {
-            F.c00 = -0.4;
-            F.c10 = -0.2;
-        } else if (pcol == 1) {
-            F.c01 = -1.0;
-        } else if (pcol == 2) {
-            F.c11 = 1.0;
-        }
-        return F;
+        // selects, not branches: the piece prologue stays straight-line
+        return Force{pcol == 0 ? -0.4 : 0.0, pcol == 1 ? -1.0 : 0.0, pcol == 0 ? -0.2 : 0.0, pcol == 2 ? 1.0 : 0.0};
     }
     CB_DEV void jvp(const double *x, const double *, const Ctx &c, const double *v, const Force &F, double *dv)
     {
@@ -116,15 +108,12 @@ struct Lqr {
     }
     CB_DEV Force make_force(int pcol, const double *p)
     {
-        Force F{0.0, 0.0, 0.0};
-        if (pcol == 0) {
-            F.a0 = 1.0;  // d f / d a = (x, 0)
-        } else if (pcol == 1) {
-            F.b0 = p[2];  // d f / d b = (u, 0)
-        } else if (pcol == 2) {
-            F.b0 = p[1];  // d f / d u = (b, 0.2 u)
-            F.b1 = 0.2 * p[2];
-        }
+        // d f/d a = (x, 0); d f/d b = (u, 0); d f/d u = (b, 0.2 u) -- selects, not branches
+        Force F;
+        F.a0 = pcol == 0 ? 1.0 : 0.0;
+        F.b0 = pcol == 1 ? p[2] : 0.0;
+        F.b0 = pcol == 2 ? p[1] : F.b0;
+        F.b1 = pcol == 2 ? 0.2 * p[2] : 0.0;
         return F;
     }
     CB_DEV void jvp(const double *x, const double *p, const Ctx &c, const double *v, const Force &F, double *dv)

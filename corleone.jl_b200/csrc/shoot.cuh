@@ -57,23 +57,6 @@ __device__ __forceinline__ void rhs_all(const double *td, const double *p, const
     }
 }
 
-// Tsit5 coefficient slots: cf[0]=h a21; [1..2]=h a31,a32; [3..5]=h a4.; [6..9]=h a5.; [10..14]=h a6.; [15..20]=h a7.
-__host__ __device__ inline void tsit5_coeffs(double h, double *cf)
-{
-    using namespace ts5;
-    const double a[21] = {a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65,
-                          a71, a72, a73, a74, a75, a76};
-    for (int k = 0; k < 21; k++) cf[k] = h * a[k];
-}
-// RK4 coefficient slots: cf[0]=h/2, cf[1]=h, cf[2]=h/6, cf[3]=h/3
-__host__ __device__ inline void rk4_coeffs(double h, double *cf)
-{
-    cf[0] = 0.5 * h;
-    cf[1] = h;
-    cf[2] = h / 6.0;
-    cf[3] = h / 3.0;
-}
-
 template <class Mdl, int G, int METHOD>
 __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const double *p, const typename Mdl::Force *F,
                                                 const double *cf, int K)
@@ -82,49 +65,69 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
     constexpr int NQR = Mdl::NQ * (1 + G);
     double kq[NQ];
     if constexpr (METHOD == 0) {
-        double k1[ND], k2[ND], k3[ND], k4[ND], k5[ND], k6[ND], td[ND];
-        rhs_all<Mdl, G>(yd, p, F, k1, kq);
-#pragma unroll
-        for (int c = 0; c < NQR; c++) yq[c] = fma(cf[15], kq[c], yq[c]);
+        // Accumulator form of the 7-stage scheme: as soon as a stage derivative k_j is known it is folded into
+        // the pending stage inputs s_i = y + h sum_{l<=j} a_il k_l (i > j) and into the new state (row 7), in the
+        // same left-to-right order as the textbook sums -- bitwise the same result, but only the five pending
+        // inputs and one k are live instead of six k's, y and a stage input.
+        double k[ND], s2[ND], s3[ND], s4[ND], s5[ND], s6[ND];
+        rhs_all<Mdl, G>(yd, p, F, k, kq);
         for (int s = 0; s < K; s++) {
 #pragma unroll
-            for (int c = 0; c < ND; c++) td[c] = fma(cf[0], k1[c], yd[c]);
-            rhs_all<Mdl, G>(td, p, F, k2, kq);
+            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[15], kq[c], yq[c]);
+#pragma unroll
+            for (int c = 0; c < ND; c++) {
+                s2[c] = fma(cf[0], k[c], yd[c]);
+                s3[c] = fma(cf[1], k[c], yd[c]);
+                s4[c] = fma(cf[3], k[c], yd[c]);
+                s5[c] = fma(cf[6], k[c], yd[c]);
+                s6[c] = fma(cf[10], k[c], yd[c]);
+                yd[c] = fma(cf[15], k[c], yd[c]);
+            }
+            rhs_all<Mdl, G>(s2, p, F, k, kq);
 #pragma unroll
             for (int c = 0; c < NQR; c++) yq[c] = fma(cf[16], kq[c], yq[c]);
 #pragma unroll
-            for (int c = 0; c < ND; c++) td[c] = fma(cf[2], k2[c], fma(cf[1], k1[c], yd[c]));
-            rhs_all<Mdl, G>(td, p, F, k3, kq);
+            for (int c = 0; c < ND; c++) {
+                s3[c] = fma(cf[2], k[c], s3[c]);
+                s4[c] = fma(cf[4], k[c], s4[c]);
+                s5[c] = fma(cf[7], k[c], s5[c]);
+                s6[c] = fma(cf[11], k[c], s6[c]);
+                yd[c] = fma(cf[16], k[c], yd[c]);
+            }
+            rhs_all<Mdl, G>(s3, p, F, k, kq);
 #pragma unroll
             for (int c = 0; c < NQR; c++) yq[c] = fma(cf[17], kq[c], yq[c]);
 #pragma unroll
-            for (int c = 0; c < ND; c++) td[c] = fma(cf[5], k3[c], fma(cf[4], k2[c], fma(cf[3], k1[c], yd[c])));
-            rhs_all<Mdl, G>(td, p, F, k4, kq);
+            for (int c = 0; c < ND; c++) {
+                s4[c] = fma(cf[5], k[c], s4[c]);
+                s5[c] = fma(cf[8], k[c], s5[c]);
+                s6[c] = fma(cf[12], k[c], s6[c]);
+                yd[c] = fma(cf[17], k[c], yd[c]);
+            }
+            rhs_all<Mdl, G>(s4, p, F, k, kq);
 #pragma unroll
             for (int c = 0; c < NQR; c++) yq[c] = fma(cf[18], kq[c], yq[c]);
 #pragma unroll
-            for (int c = 0; c < ND; c++)
-                td[c] = fma(cf[9], k4[c], fma(cf[8], k3[c], fma(cf[7], k2[c], fma(cf[6], k1[c], yd[c]))));
-            rhs_all<Mdl, G>(td, p, F, k5, kq);
+            for (int c = 0; c < ND; c++) {
+                s5[c] = fma(cf[9], k[c], s5[c]);
+                s6[c] = fma(cf[13], k[c], s6[c]);
+                yd[c] = fma(cf[18], k[c], yd[c]);
+            }
+            rhs_all<Mdl, G>(s5, p, F, k, kq);
 #pragma unroll
             for (int c = 0; c < NQR; c++) yq[c] = fma(cf[19], kq[c], yq[c]);
 #pragma unroll
-            for (int c = 0; c < ND; c++)
-                td[c] = fma(cf[14], k5[c],
-                            fma(cf[13], k4[c], fma(cf[12], k3[c], fma(cf[11], k2[c], fma(cf[10], k1[c], yd[c])))));
-            rhs_all<Mdl, G>(td, p, F, k6, kq);
+            for (int c = 0; c < ND; c++) {
+                s6[c] = fma(cf[14], k[c], s6[c]);
+                yd[c] = fma(cf[19], k[c], yd[c]);
+            }
+            rhs_all<Mdl, G>(s6, p, F, k, kq);
 #pragma unroll
             for (int c = 0; c < NQR; c++) yq[c] = fma(cf[20], kq[c], yq[c]);
 #pragma unroll
-            for (int c = 0; c < ND; c++)
-                yd[c] = fma(cf[20], k6[c],
-                            fma(cf[19], k5[c],
-                                fma(cf[18], k4[c], fma(cf[17], k3[c], fma(cf[16], k2[c], fma(cf[15], k1[c], yd[c]))))));
-            if (s + 1 < K) {  // FSAL: k7 of this step is k1 of the next; after the last step it is never used
-                rhs_all<Mdl, G>(yd, p, F, k1, kq);
-#pragma unroll
-                for (int c = 0; c < NQR; c++) yq[c] = fma(cf[15], kq[c], yq[c]);
-            }
+            for (int c = 0; c < ND; c++) yd[c] = fma(cf[20], k[c], yd[c]);
+            if (s + 1 < K)  // FSAL: k7 of this step is k1 of the next; after the last step it is never used
+                rhs_all<Mdl, G>(yd, p, F, k, kq);
         }
     } else {
         double k[ND], acc[ND], td[ND];
@@ -162,8 +165,26 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
     }
 }
 
-template <class Mdl, int G, int METHOD, bool UNI>
-__global__ void __launch_bounds__(128)
+// one merged-trajectory sample: [x(t); controls of the piece in layer row order] (src/single_shooting.jl:456)
+template <class Mdl>
+__device__ __forceinline__ void save_sample(const DevLayer &L, const ShootOut &o, long long sample, int nrow, long long b,
+                                         const double *yd, const double *yq, const double *p)
+{
+    constexpr int NX = Mdl::NX, NXD = Mdl::NXD, NP = Mdl::NP;
+    double *t = o.traj + (sample * nrow) * o.ldo + b;
+#pragma unroll
+    for (int k = 0; k < NX; k++) t[(long long)k * o.ldo] = (k < NXD) ? yd[k < NXD ? k : 0] : yq[k >= NXD ? k - NXD : 0];
+    // control row r of a sample is fed from p slot row_to_p[r]; walking the p slots keeps every register
+    // index static (pmap_idx[q] is the row of control slot q)
+#pragma unroll
+    for (int q = 0; q < NP; q++)
+        if (L.pmap_kind[q] == 1) t[(long long)(NX + L.pmap_idx[q]) * o.ldo] = p[q];
+}
+
+// MINB: resident blocks of 128 threads per SM the register allocation must allow (__launch_bounds__); chosen
+// per (model, G) in the model's dispatch table from ptxas -v (largest value without spills in the step loop).
+template <class Mdl, int G, int METHOD, bool UNI, int MINB>
+__global__ void __launch_bounds__(128, MINB)
 shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B, const ShootOut o)
 {
     constexpr int NX = Mdl::NX, NXD = Mdl::NXD, NQ = Mdl::NQ, NP = Mdl::NP;
@@ -175,10 +196,10 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
     if (!L.flat) {
         // regular launch: grid.x tiles the candidates, grid.y = interval, grid.z = direction group --
         // no integer divisions, and (i, r) is block-uniform
+        // (lanes beyond B redo candidate B-1 without storing, so that warps stay whole for the shuffles)
         b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
         i = blockIdx.y;
         r = blockIdx.z;
-        if (b >= B) return;
     } else {
         // flat launch for tiny batches (B < 32): lanes of a warp span intervals and direction groups
         const long long nsys = B * L.I;
@@ -190,18 +211,18 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         b = rem - (long long)i * B;
     }
 
+    const bool live = b < B;
+    if (!live) b = B - 1;
     const int nu0 = __ldg(L.n_u0 + i), nc = __ldg(L.n_c + i);
     const int ns = nu0 + L.ntp + nc;
     const int d0 = r * G;
     if (r > 0 && d0 >= ns) return;
-    const double *__restrict__ v = ps + (long long)__ldg(L.var_off + i) * ldb + b;  // v[k*ldb]: local variable k
+    const int voff = __ldg(L.var_off + i);
+    const double *__restrict__ v = ps + (long long)voff * ldb + b;  // v[k*ldb]: local variable k
 
     // ---- initial state: InitialConditionRemaker (src/single_shooting.jl:260-266), fixval per :359;
     //      sensitivity seeds: e_k for the u0 direction that feeds state k
     double yd[ND], yq[NQA];
-    int pcol[G1], cloc[G1];
-#pragma unroll
-    for (int g = 0; g < G1; g++) pcol[g] = cloc[g] = -1;
 #pragma unroll
     for (int k = 0; k < NX; k++) {
         const int src = __ldg(L.ic_src + i * NX + k);
@@ -221,15 +242,14 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
             }
         }
     }
+    // p column each direction perturbs (static per interval: host table, -1 for u0 directions and padding)
+    int pcol[G1];
+#pragma unroll
+    for (int g = 0; g < G1; g++) pcol[g] = -1;
     if constexpr (G > 0) {
 #pragma unroll
-        for (int g = 0; g < G; g++) {
-            const int d = d0 + g;
-            if (d >= nu0 && d < nu0 + L.ntp)
-                pcol[g] = L.tunable_p0[d - nu0];
-            else if (d >= nu0 + L.ntp && d < ns)
-                cloc[g] = d - nu0 - L.ntp;
-        }
+        for (int g = 0; g < G; g++)
+            if (d0 + g < ns) pcol[g] = (int)L.dir_pcol[voff + d0 + g];
     }
     // ---- parameters: p_full = A*p + B*controls_j (src/single_shooting.jl:319-323)
     double p[NP];
@@ -244,56 +264,35 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
     const double *__restrict__ vc = v + (long long)(nu0 + L.ntp) * ldb;
 
     // controls of a piece: ps.controls[index_grid[:, j]] (src/single_shooting.jl:439).  The index and the
-    // value it points to are two dependent global loads; they are issued one piece ahead so that their
-    // latency hides behind the integration of the current piece.
-    int ci_nx[NP];
-    double cv_nx[NP];
+    // value it points to are two dependent global loads; they are issued one piece ahead, together with
+    // the piece's forcing mask, so that their latency hides behind the integration of the current piece.
+    double pv_nx[NP];
+    unsigned mask_nx = 0;
 #pragma unroll
-    for (int rr = 0; rr < NP; rr++) {
-        ci_nx[rr] = -1;
-        cv_nx[rr] = 0.0;
-        if (rr < L.nact) {
-            ci_nx[rr] = __ldg(L.cidx + (long long)po * L.nact + rr);
-            cv_nx[rr] = vc[(long long)ci_nx[rr] * ldb];
-        }
+    for (int q = 0; q < NP; q++) {
+        pv_nx[q] = 0.0;
+        if (L.pmap_kind[q] == 1) pv_nx[q] = vc[(long long)__ldg(L.cidx + (long long)po * L.nact + L.pmap_idx[q]) * ldb];
     }
+    if constexpr (G > 0) mask_nx = __ldg(L.act_mask + (long long)po * L.R + r);
     for (int j = 0; j < M; j++) {
-        int pc[G1];
 #pragma unroll
-        for (int g = 0; g < G1; g++) pc[g] = pcol[g];
-        double cval[NP];
+        for (int q = 0; q < NP; q++)
+            if (L.pmap_kind[q] == 1) p[q] = pv_nx[q];
+        const unsigned mask = mask_nx;
+        if (j + 1 < M) {
 #pragma unroll
-        for (int rr = 0; rr < NP; rr++) {
-            cval[rr] = cv_nx[rr];
-            if (rr < L.nact) {
-                const int ci = ci_nx[rr];
-#pragma unroll
-                for (int q = 0; q < NP; q++)
-                    if (L.row_to_p[rr] == q) p[q] = cval[rr];
-                if constexpr (G > 0) {
-#pragma unroll
-                    for (int g = 0; g < G; g++)
-                        if (cloc[g] == ci) pc[g] = L.row_to_p[rr];
-                }
-                if (j + 1 < M) {
-                    ci_nx[rr] = __ldg(L.cidx + (long long)(po + j + 1) * L.nact + rr);
-                    cv_nx[rr] = vc[(long long)ci_nx[rr] * ldb];
-                }
-            }
+            for (int q = 0; q < NP; q++)
+                if (L.pmap_kind[q] == 1)
+                    pv_nx[q] = vc[(long long)__ldg(L.cidx + (long long)(po + j + 1) * L.nact + L.pmap_idx[q]) * ldb];
+            if constexpr (G > 0) mask_nx = __ldg(L.act_mask + (long long)(po + j + 1) * L.R + r);
         }
         typename Mdl::Force F[G1];
         if constexpr (G > 0) {
 #pragma unroll
-            for (int g = 0; g < G; g++) F[g] = Mdl::make_force(pc[g], p);
+            for (int g = 0; g < G; g++) F[g] = Mdl::make_force(pcol[g] | -(int)(((mask >> g) & 1u) ^ 1u), p);  // off -> -1
         }
-        if (o.traj && r == 0 && j == 0) {  // save_start = (j == 1)
-            double *t = o.traj + ((long long)so * nrow) * o.ldo + b;
-#pragma unroll
-            for (int k = 0; k < NX; k++) t[(long long)k * o.ldo] = (k < NXD) ? yd[k < NXD ? k : 0] : yq[k >= NXD ? k - NXD : 0];
-#pragma unroll
-            for (int rr = 0; rr < NP; rr++)
-                if (rr < L.nact) t[(long long)(NX + rr) * o.ldo] = cval[rr];
-        }
+        if (o.traj && live && r == 0 && j == 0)  // save_start = (j == 1)
+            save_sample<Mdl>(L, o, (long long)so, nrow, b, yd, yq, p);
         if constexpr (UNI) {
             integrate_piece<Mdl, G, METHOD>(yd, yq, p, F, L.hA, L.K);
         } else {
@@ -306,35 +305,87 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
             integrate_piece<Mdl, G, METHOD>(yd, yq, p, F, cf, L.K);
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
-        if (o.traj && r == 0 && (j + 1 < M || last_interval)) {
-            double *t = o.traj + ((long long)(so + j + 1) * nrow) * o.ldo + b;
+        if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
+            save_sample<Mdl>(L, o, (long long)(so + j + 1), nrow, b, yd, yq, p);
+    }
+    // ---- results.  xs(k): end state component k (compile-time k)
+#define CB200_XS(k) ((k) < NXD ? yd[(k) < NXD ? (k) : 0] : yq[(k) >= NXD ? (k)-NXD : 0])
+#define CB200_SS(g, k) ((k) < NXD ? yd[NXD * (1 + (g)) + ((k) < NXD ? (k) : 0)] : yq[NQ * (1 + (g)) + ((k) >= NXD ? (k)-NXD : 0)])
+    if (r == 0 && live) {
+        if (o.xend) {
 #pragma unroll
-            for (int k = 0; k < NX; k++) t[(long long)k * o.ldo] = (k < NXD) ? yd[k < NXD ? k : 0] : yq[k >= NXD ? k - NXD : 0];
+            for (int k = 0; k < NX; k++) o.xend[((long long)i * NX + k) * o.ldo + b] = CB200_XS(k);
+        }
+        if (o.objq) {  // objective = one state row of the last sample (src/dynprob.jl:70-71)
+            double val = 0.0;
 #pragma unroll
-            for (int rr = 0; rr < NP; rr++)
-                if (rr < L.nact) t[(long long)(NX + rr) * o.ldo] = cval[rr];
+            for (int k = 0; k < NX; k++) val = (k == o.obj_state) ? CB200_XS(k) : val;
+            o.objq[(long long)i * o.ldo + b] = val;
+        }
+        // shooting defects of the boundary (i, i+1), both orderings (src/multiple_shooting.jl:150-163, 229-295):
+        // state matchings straight from the end state in registers, before any quadrature accumulation
+        if ((o.dk || o.dst) && i + 1 < L.I) {
+            const int vn = __ldg(L.var_off + i + 1);
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const int pk = __ldg(L.dpos_kind + i * NX + k);
+                if (pk >= 0) {
+                    const int src = __ldg(L.ic_src + (i + 1) * NX + k);
+                    const double nxt = (src >= 0) ? ps[(long long)(vn + src) * ldb + b] : __ldg(L.ic_fix + (i + 1) * NX + k);
+                    const double dd = CB200_XS(k) - nxt;
+                    if (o.dk) o.dk[(long long)pk * o.ldo + b] = dd;
+                    if (o.dst) o.dst[(long long)__ldg(L.dpos_stage + i * NX + k) * o.ldo + b] = dd;
+                }
+            }
+            const int e1 = __ldg(L.oth_off + i + 1);
+            for (int e = __ldg(L.oth_off + i); e < e1; e++) {  // parameter and control matchings
+                const MatchEntry t = L.oth[e];
+                const double dd = ps[(long long)t.a * ldb + b] - ps[(long long)t.b * ldb + b];
+                if (o.dk) o.dk[(long long)t.pos_kind * o.ldo + b] = dd;
+                if (o.dst) o.dst[(long long)t.pos_stage * o.ldo + b] = dd;
+            }
         }
     }
-    if (o.xend && r == 0) {
-#pragma unroll
-        for (int k = 0; k < NX; k++)
-            o.xend[((long long)i * NX + k) * o.ldo + b] = (k < NXD) ? yd[k < NXD ? k : 0] : yq[k >= NXD ? k - NXD : 0];
-    }
     if constexpr (G > 0) {
-        if (o.sens) {
+        if (o.sens && live) {
             const long long s0 = __ldg(L.sens_off + i);
 #pragma unroll
             for (int g = 0; g < G; g++) {
                 const int d = d0 + g;
                 if (d < ns) {
 #pragma unroll
-                    for (int k = 0; k < NX; k++)
-                        o.sens[(s0 + (long long)d * NX + k) * o.ldo + b] =
-                            (k < NXD) ? yd[NXD * (1 + g) + (k < NXD ? k : 0)] : yq[NQ * (1 + g) + (k >= NXD ? k - NXD : 0)];
+                    for (int k = 0; k < NX; k++) o.sens[(s0 + (long long)d * NX + k) * o.ldo + b] = CB200_SS(g, k);
+                }
+            }
+        }
+        // objective gradient: variable voff + d is direction d of this interval, so every thread owns the
+        // gradient entries of its directions (zero when the interval does not reach the objective)
+        if (o.grad || o.grad_sum) {
+            const bool inc = o.obj_all || i == L.I - 1;
+#pragma unroll
+            for (int g = 0; g < G; g++) {
+                const int d = d0 + g;
+                if (d < ns) {
+                    double val = 0.0;
+#pragma unroll
+                    for (int k = 0; k < NX; k++) val = (inc && k == o.obj_state) ? CB200_SS(g, k) : val;
+                    if (o.grad && live) o.grad[(long long)(voff + d) * o.ldo + b] = val;
+                    if (o.grad_sum) {
+                        if (!live) val = 0.0;
+                        if (!L.flat) {  // whole warp shares (i, r): shuffle tree, one atomic per warp
+#pragma unroll
+                            for (int w = 16; w > 0; w >>= 1) val += __shfl_down_sync(0xffffffffu, val, w);
+                            if ((threadIdx.x & 31) == 0) atomicAdd(o.grad_sum + voff + d, val);
+                        } else {
+                            atomicAdd(o.grad_sum + voff + d, val);
+                        }
+                    }
                 }
             }
         }
     }
+#undef CB200_XS
+#undef CB200_SS
 }
 
 // threads per block of the shooting kernel (<= 128, the __launch_bounds__); small blocks shorten the tail
@@ -349,7 +400,7 @@ inline int launch_block_size()
     return bs;
 }
 
-template <class Mdl, int G, int METHOD>
+template <class Mdl, int G, int METHOD, int MINB>
 int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, const ShootOut &o, cudaStream_t s)
 {
     const long long nthreads = B * L.I * (long long)L.R;
@@ -363,15 +414,20 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
     else
         grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.I, (unsigned)L.R);
     if (L.uniform_h)
-        shoot_kernel<Mdl, G, METHOD, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+        shoot_kernel<Mdl, G, METHOD, true, MINB><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
     else
-        shoot_kernel<Mdl, G, METHOD, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+        shoot_kernel<Mdl, G, METHOD, false, MINB><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
     return (int)cudaGetLastError();
 }
 
-#define CB200_DISPATCH_G(Mdl, Gv)                                                           \
+#ifdef CB200_MINB   // tuning builds: one value for every instantiation
+#define CB200_MB(v) CB200_MINB
+#else
+#define CB200_MB(v) v
+#endif
+#define CB200_DISPATCH_G(Mdl, Gv, MBv)                                                      \
     case Gv:                                                                                \
-        return method == 0 ? launch_one<Mdl, Gv, 0>(L, ps, ldb, B, o, s)                   \
-                           : launch_one<Mdl, Gv, 1>(L, ps, ldb, B, o, s);
+        return method == 0 ? launch_one<Mdl, Gv, 0, CB200_MB(MBv)>(L, ps, ldb, B, o, s)   \
+                           : launch_one<Mdl, Gv, 1, CB200_MB(MBv)>(L, ps, ldb, B, o, s);
 
 }  // namespace cb200

@@ -7,8 +7,8 @@ int launch_dense20(int G, int method, const DevLayer &L, const double *ps, long 
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Dense20, 0)
-        CB200_DISPATCH_G(Dense20, 1)
+        CB200_DISPATCH_G(Dense20, 0, 1)
+        CB200_DISPATCH_G(Dense20, 1, 1)
     default:
         return -1000;
     }

@@ -6,10 +6,10 @@ int launch_egerstedt(int G, int method, const DevLayer &L, const double *ps, lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Egerstedt, 0)
-        CB200_DISPATCH_G(Egerstedt, 1)
-        CB200_DISPATCH_G(Egerstedt, 2)
-        CB200_DISPATCH_G(Egerstedt, 3)
+        CB200_DISPATCH_G(Egerstedt, 0, 1)
+        CB200_DISPATCH_G(Egerstedt, 1, 1)
+        CB200_DISPATCH_G(Egerstedt, 2, 1)
+        CB200_DISPATCH_G(Egerstedt, 3, 1)
     default:
         return -1000;
     }

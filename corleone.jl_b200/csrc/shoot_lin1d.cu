@@ -6,10 +6,10 @@ int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long lo
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lin1d, 0)
-        CB200_DISPATCH_G(Lin1d, 1)
-        CB200_DISPATCH_G(Lin1d, 2)
-        CB200_DISPATCH_G(Lin1d, 4)
+        CB200_DISPATCH_G(Lin1d, 0, 1)
+        CB200_DISPATCH_G(Lin1d, 1, 1)
+        CB200_DISPATCH_G(Lin1d, 2, 1)
+        CB200_DISPATCH_G(Lin1d, 4, 1)
     default:
         return -1000;
     }

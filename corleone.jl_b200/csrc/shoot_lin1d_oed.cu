@@ -6,7 +6,7 @@ int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lin1dOed, 0)
+        CB200_DISPATCH_G(Lin1dOed, 0, 1)
     default:
         return -1000;
     }

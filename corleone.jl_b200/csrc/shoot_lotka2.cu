@@ -6,11 +6,11 @@ int launch_lotka2(int G, int method, const DevLayer &L, const double *ps, long l
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lotka2, 0)
-        CB200_DISPATCH_G(Lotka2, 1)
-        CB200_DISPATCH_G(Lotka2, 2)
-        CB200_DISPATCH_G(Lotka2, 3)
-        CB200_DISPATCH_G(Lotka2, 4)
+        CB200_DISPATCH_G(Lotka2, 0, 1)
+        CB200_DISPATCH_G(Lotka2, 1, 1)
+        CB200_DISPATCH_G(Lotka2, 2, 1)
+        CB200_DISPATCH_G(Lotka2, 3, 1)
+        CB200_DISPATCH_G(Lotka2, 4, 1)
     default:
         return -1000;
     }

@@ -6,11 +6,11 @@ int launch_lotka3(int G, int method, const DevLayer &L, const double *ps, long l
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lotka3, 0)
-        CB200_DISPATCH_G(Lotka3, 1)
-        CB200_DISPATCH_G(Lotka3, 2)
-        CB200_DISPATCH_G(Lotka3, 3)
-        CB200_DISPATCH_G(Lotka3, 5)
+        CB200_DISPATCH_G(Lotka3, 0, 1)
+        CB200_DISPATCH_G(Lotka3, 1, 1)
+        CB200_DISPATCH_G(Lotka3, 2, 1)
+        CB200_DISPATCH_G(Lotka3, 3, 1)
+        CB200_DISPATCH_G(Lotka3, 5, 1)
     default:
         return -1000;
     }

@@ -6,11 +6,11 @@ int launch_lqr(int G, int method, const DevLayer &L, const double *ps, long long
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lqr, 0)
-        CB200_DISPATCH_G(Lqr, 1)
-        CB200_DISPATCH_G(Lqr, 2)
-        CB200_DISPATCH_G(Lqr, 4)
-        CB200_DISPATCH_G(Lqr, 8)
+        CB200_DISPATCH_G(Lqr, 0, 1)
+        CB200_DISPATCH_G(Lqr, 1, 1)
+        CB200_DISPATCH_G(Lqr, 2, 1)
+        CB200_DISPATCH_G(Lqr, 4, 4)  // 127 registers, no spills: 16 warps/SM (ptxas -v); best of the G x MINB sweep
+        CB200_DISPATCH_G(Lqr, 8, 1)
     default:
         return -1000;
     }

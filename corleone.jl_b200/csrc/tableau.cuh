@@ -15,4 +15,22 @@ constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.15936
 constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996, a74 = 1.379008574103742,
                  a75 = -3.290069515436081, a76 = 2.324710524099774;
 }  // namespace ts5
+
+// Tsit5 coefficient slots: cf[0]=h a21; [1..2]=h a31,a32; [3..5]=h a4.; [6..9]=h a5.; [10..14]=h a6.; [15..20]=h a7.
+__host__ __device__ inline void tsit5_coeffs(double h, double *cf)
+{
+    using namespace ts5;
+    const double a[21] = {a21, a31, a32, a41, a42, a43, a51, a52, a53, a54, a61, a62, a63, a64, a65,
+                          a71, a72, a73, a74, a75, a76};
+    for (int k = 0; k < 21; k++) cf[k] = h * a[k];
+}
+// RK4 coefficient slots: cf[0]=h/2, cf[1]=h, cf[2]=h/6, cf[3]=h/3
+__host__ __device__ inline void rk4_coeffs(double h, double *cf)
+{
+    cf[0] = 0.5 * h;
+    cf[1] = h;
+    cf[2] = h / 6.0;
+    cf[3] = h / 3.0;
+}
+
 }  // namespace cb200

@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcorleone_b200.so")
+LIB_PATH = os.environ.get("CORLEONE_B200_LIB") or os.path.join(_HERE, "libcorleone_b200.so")
 _lib = None
 
 WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM = 1, 2, 4, 8, 16, 32, 64
