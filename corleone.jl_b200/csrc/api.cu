@@ -236,9 +236,11 @@ struct cb200_handle {
     GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row
     int grad_cap = 0;
     std::vector<GradEntry> h_grad;
-    size_t out_off = 0;               // bump offset into ws_out during one eval
     cudaStream_t stream = nullptr;
     bool own_stream = false;
+    static constexpr int NAUX = 2;        // extra streams of the chunked host path (copy/compute overlap)
+    cudaStream_t aux[NAUX] = {};
+    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
     static constexpr int EV_RING = 256;   // event pairs around the integration kernel of the last 256 evals
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
@@ -652,6 +654,14 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail("cudaStreamCreate", e);
     h->own_stream = true;
+    for (int k = 0; k < cb200_handle::NAUX; k++) {
+        e = cudaStreamCreateWithFlags(&h->aux[k], cudaStreamNonBlocking);
+        if (e != cudaSuccess) return bail("cudaStreamCreate", e);
+        e = cudaEventCreateWithFlags(&h->ev_join[k], cudaEventDisableTiming);
+        if (e != cudaSuccess) return bail("cudaEventCreate", e);
+    }
+    e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e != cudaSuccess) return bail("cudaEventCreate", e);
     for (int k = 0; k < cb200_handle::EV_RING; k++) {
         e = cudaEventCreate(&h->ev0[k]);
         if (e != cudaSuccess) return bail("cudaEventCreate", e);
@@ -675,6 +685,14 @@ extern "C" int cb200_destroy(cb200_handle *h)
         if (h->ev0[k]) cudaEventDestroy(h->ev0[k]);
         if (h->ev1[k]) cudaEventDestroy(h->ev1[k]);
     }
+    for (int k = 0; k < cb200_handle::NAUX; k++) {
+        if (h->aux[k]) {
+            cudaStreamSynchronize(h->aux[k]);
+            cudaStreamDestroy(h->aux[k]);
+        }
+        if (h->ev_join[k]) cudaEventDestroy(h->ev_join[k]);
+    }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
     delete h;
     return CB200_OK;
@@ -749,8 +767,8 @@ extern "C" int64_t cb200_launch_count(const cb200_handle *h) { return h ? h->lau
 
 static inline unsigned nblk(long long n, int bs) { return (unsigned)((n + bs - 1) / bs); }
 
-static int transpose(cb200_handle *h, const double *in, long long ld_in, double *out, long long ld_out, long long nr,
-                     long long nc)
+static int transpose(cb200_handle *h, cudaStream_t st, const double *in, long long ld_in, double *out, long long ld_out,
+                     long long nr, long long nc)
 {
     if (nr <= 0 || nc <= 0) return 0;
     // grid.y is limited to 65535 blocks: split rows
@@ -758,35 +776,87 @@ static int transpose(cb200_handle *h, const double *in, long long ld_in, double 
     for (long long r0 = 0; r0 < nr; r0 += max_rows) {
         const long long rows = std::min(max_rows, nr - r0);
         dim3 grid((unsigned)((nc + 31) / 32), (unsigned)((rows + 31) / 32));
-        transpose_kernel<<<grid, dim3(32, 8), 0, h->stream>>>(in + r0 * ld_in, ld_in, out + r0, ld_out, rows, nc);
+        transpose_kernel<<<grid, dim3(32, 8), 0, st>>>(in + r0 * ld_in, ld_in, out + r0, ld_out, rows, nc);
         h->launches++;
     }
     return (int)cudaGetLastError();
 }
 
-// deliver a device SoA result [n x B] (ld B) to the caller according to flags
-static int deliver(cb200_handle *h, const double *dev_soa, double *user, long long n, long long B, uint32_t flags)
+// what one evaluation produces, resolved from (want, out)
+struct EvalPlan {
+    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum;
+    bool fused_grad, need_sens, need_xend;
+    int obj_state, obj_ctrl_var, obj_quad, objective_row;
+};
+
+// device SoA buffers of one batch (or one chunk of it), leading dimension = its candidate count
+struct DevSet {
+    double *xend = nullptr, *sens = nullptr, *traj = nullptr, *dk = nullptr, *ds = nullptr, *obj = nullptr,
+           *grad = nullptr, *fim = nullptr, *objq = nullptr;
+    double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // shared by all chunks (atomic accumulation)
+    const double *finit = nullptr;
+};
+
+// The device pipeline of one batch on one stream: K1/K2 with the fused K3 epilogue, then the small kernels.
+static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long long d_ldb, long long B, const EvalPlan &pl,
+                     const DevSet &d)
 {
-    if (!user || dev_soa == user) return CB200_OK;
-    const bool dev = flags & CB200_MEM_DEVICE, soa = flags & CB200_OUT_SOA;
-    const size_t bytes = sizeof(double) * (size_t)n * (size_t)B;
-    if (soa) {
-        CUDA_TRY(cudaMemcpyAsync(user, dev_soa, bytes, dev ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, h->stream));
-        return CB200_OK;
+    const DevLayer &L0 = h->L;
+    const int nx = L0.nx, I = L0.I;
+    const long long nrow = nx + L0.nact;
+    const long long ndef = (long long)h->defects.size();
+    DevLayer L = L0;
+    int G = 0;
+    if (pl.need_sens) {
+        G = h->G_sens;
+        if (G <= 0) return fail(CB200_ERR_UNSUPPORTED, "model %d has no sensitivity kernel", h->model);
+        L.R = (h->max_ns + G - 1) / G;
+        if (L.R < 1) L.R = 1;
     }
-    if (dev) {
-        int rc = transpose(h, dev_soa, B, user, n, n, B);
-        if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-        return CB200_OK;
+    ShootOut so{};
+    so.xend = d.xend;
+    so.sens = d.sens;
+    so.traj = d.traj;
+    so.ldo = B;
+    so.dk = ndef > 0 ? d.dk : nullptr;
+    so.dst = ndef > 0 ? d.ds : nullptr;
+    so.objq = d.objq;
+    so.grad = pl.fused_grad ? d.grad : nullptr;
+    so.grad_sum = pl.fused_grad ? d.gsum : nullptr;
+    so.obj_state = pl.obj_state;
+    so.obj_all = pl.obj_quad;
+    const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
+    CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], st));
+    int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, st);
+    if (rc == -1000)
+        return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
+                    h->method);
+    if (rc) return fail(CB200_ERR_CUDA, "shoot kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    h->launches++;
+    CUDA_TRY(cudaEventRecord(h->ev1[ev_slot], st));
+    h->n_timed++;
+
+    // ---- K3 remainder: objective sum over intervals, control-row gradient, trajectory quadratures, FIM
+    if (pl.obj || pl.osum) {
+        objective_kernel<<<nblk(B, 256), 256, 0, st>>>(d.objq, B, d_ps, d_ldb, B, I, pl.obj_state >= 0, pl.obj_quad,
+                                                     pl.obj_ctrl_var, d.obj, d.osum);
+        h->launches++;
     }
-    // every output of one eval gets its own slice of the staging buffer (reserved up front by cb200_eval),
-    // so all transposes and copies queue on the stream and the caller waits once
-    double *stage = (double *)((char *)h->ws_out.p + h->out_off);
-    h->out_off += (bytes + 255) & ~size_t(255);
-    if (h->out_off > h->ws_out.cap) return fail(CB200_ERR_NOMEM, "internal: staging buffer too small");
-    int rc = transpose(h, dev_soa, B, stage, n, n, B);
-    if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    CUDA_TRY(cudaMemcpyAsync(user, stage, bytes, cudaMemcpyDeviceToHost, h->stream));
+    if ((pl.grad || pl.gsum) && !pl.fused_grad) {  // objective = a control row: the gradient is a unit vector
+        if (d.grad) CUDA_TRY(cudaMemsetAsync(d.grad, 0, sizeof(double) * (size_t)L0.nvars * (size_t)B, st));
+        grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
+        h->launches++;
+    }
+    if (pl.traj && h->nquad > 0 && I > 1) {
+        traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, d.xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
+                                                     h->d_quad, h->nquad);
+        h->launches++;
+    }
+    if (pl.fim || pl.fsum) {
+        fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, B, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, B, d.fsum);
+        h->launches++;
+    }
+    CUDA_TRY(cudaGetLastError());
     return CB200_OK;
 }
 
@@ -802,209 +872,211 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     const DevLayer &L0 = h->L;
     const int nx = L0.nx, I = L0.I, nvars = L0.nvars;
     const bool dev = flags & CB200_MEM_DEVICE, ps_soa = flags & CB200_PS_SOA, out_soa = flags & CB200_OUT_SOA;
-    const bool direct = dev && out_soa;  // kernels may write straight into the caller's buffers
     if (ps_soa ? (ldb < B) : (ldb < nvars)) return fail(CB200_ERR_ARG, "ldb too small");
     const long long nrow = nx + L0.nact;
     const long long ndef = (long long)h->defects.size();
+    const int n2 = h->fim_n * h->fim_n;
 
-    const bool w_sens = (want & CB200_WANT_SENS) && out->sens, w_grad = (want & CB200_WANT_GRAD) && out->grad;
-    const bool w_traj = (want & CB200_WANT_TRAJ) && out->traj, w_xend = (want & CB200_WANT_XEND) && out->xend;
-    const bool w_def = (want & CB200_WANT_DEFECTS) && (out->defects_kind || out->defects_stage);
-    const bool w_obj = (want & CB200_WANT_OBJ) && out->objective;
-    const bool w_fim = (want & CB200_WANT_FIM) && (out->fim || out->fim_sum);
-    const bool w_osum = (want & CB200_WANT_OBJ) && out->objective_sum;
-    const bool w_gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
-    if (w_fim && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
-    int obj_state = -1, obj_ctrl_var = -1, obj_quad = 0;
-    if (w_obj || w_grad || w_osum || w_gsum) {
+    EvalPlan pl{};
+    pl.sens = (want & CB200_WANT_SENS) && out->sens;
+    pl.grad = (want & CB200_WANT_GRAD) && out->grad;
+    pl.traj = (want & CB200_WANT_TRAJ) && out->traj;
+    pl.xend = (want & CB200_WANT_XEND) && out->xend;
+    pl.dk = (want & CB200_WANT_DEFECTS) && out->defects_kind;
+    pl.ds = (want & CB200_WANT_DEFECTS) && out->defects_stage;
+    pl.obj = (want & CB200_WANT_OBJ) && out->objective;
+    pl.fim = (want & CB200_WANT_FIM) && out->fim;
+    pl.fsum = (want & CB200_WANT_FIM) && out->fim_sum;
+    pl.osum = (want & CB200_WANT_OBJ) && out->objective_sum;
+    pl.gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
+    if ((pl.fim || pl.fsum) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
+    pl.obj_state = pl.obj_ctrl_var = -1;
+    pl.objective_row = out->objective_row;
+    if (pl.obj || pl.grad || pl.osum || pl.gsum) {
         const int row = out->objective_row;
         if (row < 1 || row > nrow) return fail(CB200_ERR_ARG, "objective_row out of range");
         if (row <= nx) {
-            obj_state = row - 1;
-            for (int q : h->quad0) obj_quad |= (q == obj_state);
+            pl.obj_state = row - 1;
+            for (int q : h->quad0) pl.obj_quad |= (q == pl.obj_state);
         } else {
             const int r = row - nx - 1;
-            obj_ctrl_var = h->h_var_off[I - 1] + h->h_n_u0[I - 1] + L0.ntp +
-                           h->h_cidx[(size_t)(h->h_piece_off[I - 1] + h->h_M[I - 1] - 1) * L0.nact + r];
+            pl.obj_ctrl_var = h->h_var_off[I - 1] + h->h_n_u0[I - 1] + L0.ntp +
+                              h->h_cidx[(size_t)(h->h_piece_off[I - 1] + h->h_M[I - 1] - 1) * L0.nact + r];
         }
     }
-
-    // ---- stage ps as device SoA [v*B + b]
-    const double *d_ps = nullptr;
-    long long d_ldb = B;
-    if (nvars > 0) {
-        if (dev && ps_soa) {
-            d_ps = ps;
-            d_ldb = ldb;
-        } else {
-            const size_t bytes = sizeof(double) * (size_t)nvars * (size_t)B;
-            if (h->ws_ps.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (ps, %zu bytes)", bytes);
-            if (ps_soa) {  // host, variable-major
-                CUDA_TRY(cudaMemcpy2DAsync(h->ws_ps.p, sizeof(double) * B, ps, sizeof(double) * ldb, sizeof(double) * B,
-                                           nvars, cudaMemcpyHostToDevice, h->stream));
-            } else if (dev) {
-                int rc = transpose(h, ps, ldb, (double *)h->ws_ps.p, B, B, nvars);
-                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-            } else {  // host, candidate-major (Julia nvars x B matrix)
-                if (h->ws_in.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
-                CUDA_TRY(cudaMemcpy2DAsync(h->ws_in.p, sizeof(double) * nvars, ps, sizeof(double) * ldb,
-                                           sizeof(double) * nvars, B, cudaMemcpyHostToDevice, h->stream));
-                int rc = transpose(h, (const double *)h->ws_in.p, nvars, (double *)h->ws_ps.p, B, B, nvars);
-                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-            }
-            d_ps = (const double *)h->ws_ps.p;
-        }
-    }
-
-    // ---- device SoA result buffers
-    auto buf = [&](DevBuf &ws, double *user, long long n, bool wanted, bool needed, double **dst) -> int {
-        *dst = nullptr;
-        if (!wanted && !needed) return 0;
-        if (wanted && direct) {
-            *dst = user;
-            return 0;
-        }
-        if (ws.reserve(sizeof(double) * (size_t)n * (size_t)B)) return 1;
-        *dst = (double *)ws.p;
-        return 0;
-    };
-    double *d_xend, *d_sens, *d_traj, *d_dk, *d_ds, *d_obj, *d_grad, *d_fim;
-    const bool need_xend = w_fim || (w_traj && h->nquad > 0);
-    const bool fused_grad = (w_grad || w_gsum) && obj_state >= 0;   // gradient written by the shooting kernel
-    const bool need_sens = w_sens || fused_grad;                    // sensitivity directions are integrated
-    double *d_objq = nullptr;
-    if ((w_obj || w_osum) && obj_state >= 0) {
-        if (h->ws_objq.reserve(sizeof(double) * (size_t)I * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
-        d_objq = (double *)h->ws_objq.p;
-    }
-    int oom = 0;
-    oom |= buf(h->ws_xend, out->xend, (long long)nx * I, w_xend, need_xend, &d_xend);
-    oom |= buf(h->ws_sens, out->sens, h->n_sens, w_sens, false, &d_sens);
-    oom |= buf(h->ws_traj, out->traj, nrow * h->n_samples, w_traj, false, &d_traj);
-    oom |= buf(h->ws_dk, out->defects_kind, ndef, w_def && out->defects_kind, false, &d_dk);
-    oom |= buf(h->ws_ds, out->defects_stage, ndef, w_def && out->defects_stage, false, &d_ds);
-    oom |= buf(h->ws_obj, out->objective, 1, w_obj, false, &d_obj);
-    oom |= buf(h->ws_grad, out->grad, nvars, w_grad, false, &d_grad);
-    oom |= buf(h->ws_fim, out->fim, (long long)h->fim_n * h->fim_n, w_fim && out->fim, false, &d_fim);
-    if (oom) return fail(CB200_ERR_NOMEM, "device out of memory for result buffers (B=%lld)", (long long)B);
-
-    // ---- K1/K2: integrate every (interval, candidate) unit
-    DevLayer L = L0;
-    int G = 0;
-    if (need_sens) {
-        G = h->G_sens;
-        if (G <= 0) return fail(CB200_ERR_UNSUPPORTED, "model %d has no sensitivity kernel", h->model);
-        L.R = (h->max_ns + G - 1) / G;
-        if (L.R < 1) L.R = 1;
-    }
-    // cross-candidate sums (expectation-type objective / gradient): accumulated on the device, 1 + nvars doubles
-    double *d_osum = nullptr, *d_gsum = nullptr;
-    if (w_osum || w_gsum) {
-        if (dev) {
-            d_osum = w_osum ? out->objective_sum : nullptr;
-            d_gsum = w_gsum ? out->grad_sum : nullptr;
-        } else {
-            if (h->ws_sums.reserve(sizeof(double) * (size_t)(nvars + 1))) return fail(CB200_ERR_NOMEM, "device out of memory");
-            d_osum = w_osum ? (double *)h->ws_sums.p : nullptr;
-            d_gsum = w_gsum ? (double *)h->ws_sums.p + 1 : nullptr;
-        }
-        if (d_osum) CUDA_TRY(cudaMemsetAsync(d_osum, 0, sizeof(double), h->stream));
-        if (d_gsum) CUDA_TRY(cudaMemsetAsync(d_gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
-    }
-    ShootOut so{};
-    so.xend = d_xend;
-    so.sens = d_sens;
-    so.traj = d_traj;
-    so.ldo = B;
-    so.dk = (w_def && ndef > 0) ? d_dk : nullptr;
-    so.dst = (w_def && ndef > 0) ? d_ds : nullptr;
-    so.objq = d_objq;
-    so.grad = fused_grad ? d_grad : nullptr;
-    so.grad_sum = fused_grad ? d_gsum : nullptr;
-    so.obj_state = obj_state;
-    so.obj_all = obj_quad;
-    const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
-    CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], h->stream));
-    int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, h->stream);
-    if (rc == -1000)
-        return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
-                    h->method);
-    if (rc) return fail(CB200_ERR_CUDA, "shoot kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-    h->launches++;
-    CUDA_TRY(cudaEventRecord(h->ev1[ev_slot], h->stream));
-    h->n_timed++;
-
-    // ---- K3 remainder: objective sum over intervals, control-row gradient, trajectory quadratures, FIM
-    if (w_obj || w_osum) {
-        objective_kernel<<<nblk(B, 256), 256, 0, h->stream>>>(d_objq, B, d_ps, d_ldb, B, I, obj_state >= 0, obj_quad,
-                                                            obj_ctrl_var, d_obj, d_osum);
-        h->launches++;
-    }
-    if ((w_grad || w_gsum) && !fused_grad) {  // objective = a control row: the gradient is a unit vector
-        if (d_grad) CUDA_TRY(cudaMemsetAsync(d_grad, 0, sizeof(double) * (size_t)nvars * (size_t)B, h->stream));
-        h->h_grad.assign(1, GradEntry{obj_ctrl_var, -1});
+    pl.fused_grad = (pl.grad || pl.gsum) && pl.obj_state >= 0;   // gradient written by the shooting kernel
+    pl.need_sens = pl.sens || pl.fused_grad;                     // sensitivity directions are integrated
+    pl.need_xend = pl.xend || pl.fim || pl.fsum || (pl.traj && h->nquad > 0);
+    const bool need_objq = (pl.obj || pl.osum) && pl.obj_state >= 0;
+    if ((pl.grad || pl.gsum) && !pl.fused_grad) {
+        h->h_grad.assign(1, GradEntry{pl.obj_ctrl_var, -1});
         CUDA_TRY(cudaMemcpyAsync(h->d_grad, h->h_grad.data(), sizeof(GradEntry), cudaMemcpyHostToDevice, h->stream));
-        grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, h->stream>>>(h->d_grad, 1, d_sens, B, B, d_grad, B, d_gsum);
-        h->launches++;
     }
-    if (w_traj && h->nquad > 0 && I > 1) {
-        traj_quad_kernel<<<nblk(B, 128), 128, 0, h->stream>>>(d_traj, B, d_xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
-                                                            h->d_quad, h->nquad);
-        h->launches++;
-    }
-    double *d_fsum = nullptr;
-    if (w_fim) {
-        const int n2 = h->fim_n * h->fim_n;
-        const double *d_finit = nullptr;
-        if (out->fim_init) {
+
+    // per-candidate sizes (doubles) of every SoA result
+    struct Item { bool on; long long n; DevBuf *ws; double *user; double *DevSet::*slot; };
+    const Item items[] = {
+        {pl.need_xend, (long long)nx * I, &h->ws_xend, pl.xend ? out->xend : nullptr, &DevSet::xend},
+        {pl.sens, h->n_sens, &h->ws_sens, out->sens, &DevSet::sens},
+        {pl.traj, nrow * h->n_samples, &h->ws_traj, out->traj, &DevSet::traj},
+        {pl.dk, ndef, &h->ws_dk, out->defects_kind, &DevSet::dk},
+        {pl.ds, ndef, &h->ws_ds, out->defects_stage, &DevSet::ds},
+        {pl.obj, 1, &h->ws_obj, out->objective, &DevSet::obj},
+        {pl.grad, nvars, &h->ws_grad, out->grad, &DevSet::grad},
+        {pl.fim, n2, &h->ws_fim, out->fim, &DevSet::fim},
+        {need_objq, I, &h->ws_objq, nullptr, &DevSet::objq},
+    };
+
+    // ---- cross-candidate sums (expectation-type objective / gradient, FIM): accumulated on the device
+    DevSet shared{};
+    {
+        if (dev) {
+            shared.osum = pl.osum ? out->objective_sum : nullptr;
+            shared.gsum = pl.gsum ? out->grad_sum : nullptr;
+            shared.fsum = pl.fsum ? out->fim_sum : nullptr;
+        } else if (pl.osum || pl.gsum || pl.fsum) {
+            if (h->ws_sums.reserve(sizeof(double) * (size_t)(nvars + 1 + n2))) return fail(CB200_ERR_NOMEM, "device out of memory");
+            double *base = (double *)h->ws_sums.p;
+            shared.osum = pl.osum ? base : nullptr;
+            shared.gsum = pl.gsum ? base + 1 : nullptr;
+            shared.fsum = pl.fsum ? base + 1 + nvars : nullptr;
+        }
+        if (shared.osum) CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double), h->stream));
+        if (shared.gsum) CUDA_TRY(cudaMemsetAsync(shared.gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
+        if (shared.fsum) CUDA_TRY(cudaMemsetAsync(shared.fsum, 0, sizeof(double) * n2, h->stream));
+        if (out->fim_init && (pl.fim || pl.fsum)) {
             if (h->ws_finit.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
             CUDA_TRY(cudaMemcpyAsync(h->ws_finit.p, out->fim_init, sizeof(double) * n2,
                                      dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-            d_finit = (const double *)h->ws_finit.p;
+            shared.finit = (const double *)h->ws_finit.p;
         }
-        if (out->fim_sum) {
-            if (dev) {
-                d_fsum = out->fim_sum;
-            } else {
-                if (h->ws_fsum.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
-                d_fsum = (double *)h->ws_fsum.p;
-            }
-            CUDA_TRY(cudaMemsetAsync(d_fsum, 0, sizeof(double) * n2, h->stream));
-        }
-        fim_kernel<<<nblk(B, 128), 128, 0, h->stream>>>(d_xend, B, B, nx, I, h->fim_off, h->fim_n, d_finit, d_fim, B, d_fsum);
-        h->launches++;
     }
-    CUDA_TRY(cudaGetLastError());
 
-    // ---- deliver
-    if (!direct) {
-        int r2 = 0;
-        if (!dev && !out_soa) {  // reserve one staging slice per host output
-            size_t tot = 0;
-            auto add = [&](bool w, long long n) { if (w) tot += ((sizeof(double) * (size_t)n * (size_t)B) + 255) & ~size_t(255); };
-            add(w_xend, (long long)nx * I); add(w_sens, h->n_sens); add(w_traj, nrow * h->n_samples);
-            add(w_def && out->defects_kind, ndef); add(w_def && out->defects_stage, ndef); add(w_obj, 1);
-            add(w_grad, nvars); add(w_fim && out->fim, (long long)h->fim_n * h->fim_n);
-            if (h->ws_out.reserve(tot)) return fail(CB200_ERR_NOMEM, "device out of memory (%zu bytes staging)", tot);
-            h->out_off = 0;
+    // =================================================================== device pointers: one pass
+    if (dev) {
+        const bool direct = out_soa;   // kernels write straight into the caller's buffers
+        const double *d_ps = ps;
+        long long d_ldb = ldb;
+        if (nvars > 0 && !ps_soa) {
+            if (h->ws_ps.reserve(sizeof(double) * (size_t)nvars * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory (ps)");
+            int rc = transpose(h, h->stream, ps, ldb, (double *)h->ws_ps.p, B, B, nvars);
+            if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            d_ps = (const double *)h->ws_ps.p;
+            d_ldb = B;
         }
-        if (w_xend) r2 |= deliver(h, d_xend, out->xend, (long long)nx * I, B, flags);
-        if (w_sens) r2 |= deliver(h, d_sens, out->sens, h->n_sens, B, flags);
-        if (w_traj) r2 |= deliver(h, d_traj, out->traj, nrow * h->n_samples, B, flags);
-        if (w_def && out->defects_kind) r2 |= deliver(h, d_dk, out->defects_kind, ndef, B, flags);
-        if (w_def && out->defects_stage) r2 |= deliver(h, d_ds, out->defects_stage, ndef, B, flags);
-        if (w_obj) r2 |= deliver(h, d_obj, out->objective, 1, B, flags);
-        if (w_grad) r2 |= deliver(h, d_grad, out->grad, nvars, B, flags);
-        if (w_fim && out->fim) r2 |= deliver(h, d_fim, out->fim, (long long)h->fim_n * h->fim_n, B, flags);
-        if (r2) return r2;
+        DevSet d = shared;
+        for (const Item &it : items) {
+            if (!it.on) continue;
+            if (it.user && direct) {
+                d.*(it.slot) = it.user;
+            } else {
+                if (it.ws->reserve(sizeof(double) * (size_t)it.n * (size_t)B))
+                    return fail(CB200_ERR_NOMEM, "device out of memory for result buffers (B=%lld)", (long long)B);
+                d.*(it.slot) = (double *)it.ws->p;
+            }
+        }
+        int rc = eval_core(h, h->stream, d_ps, d_ldb, B, pl, d);
+        if (rc) return rc;
+        if (!direct) {
+            for (const Item &it : items) {
+                if (!it.on || !it.user) continue;
+                rc = transpose(h, h->stream, d.*(it.slot), B, it.user, it.n, it.n, B);
+                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            }
+        }
+        return CB200_OK;   // enqueued on the handle's stream
     }
-    if (!dev && w_osum) CUDA_TRY(cudaMemcpyAsync(out->objective_sum, d_osum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-    if (!dev && w_gsum)
-        CUDA_TRY(cudaMemcpyAsync(out->grad_sum, d_gsum, sizeof(double) * (size_t)nvars, cudaMemcpyDeviceToHost, h->stream));
-    if (w_fim && out->fim_sum && !dev)
-        CUDA_TRY(cudaMemcpyAsync(out->fim_sum, d_fsum, sizeof(double) * h->fim_n * h->fim_n, cudaMemcpyDeviceToHost,
-                                 h->stream));
-    if (!dev) CUDA_TRY(cudaStreamSynchronize(h->stream));
+
+    // =================================================================== host pointers: chunked, pipelined
+    // The batch is cut into chunks of candidates; chunk c runs on stream c % NS: host->device copy, layout
+    // conversion, the kernels, conversion back and device->host copies.  With pinned caller buffers the copy
+    // engines (one per direction) and the SMs overlap across chunks; the caller's buffers are chunk-contiguous
+    // in the candidate-major (Julia) layout, so every copy is one contiguous cudaMemcpyAsync.
+    long long Bc = B;
+    if (!ps_soa && !out_soa && B >= 1024) {
+        Bc = ((B + 7) / 8 + 31) / 32 * 32;   // ~8 chunks, multiples of a warp
+        if (Bc < 256) Bc = 256;
+    }
+    if (const char *e = getenv("CB200_HOST_CHUNK")) {
+        const long long v = atoll(e);
+        if (v > 0 && !ps_soa && !out_soa) Bc = std::min<long long>(B, (v + 31) / 32 * 32);
+    }
+    const int nchunks = (int)((B + Bc - 1) / Bc);
+    // workspaces for the whole batch; chunk c owns the slice starting at b0 * n
+    if (nvars > 0) {
+        const size_t bytes = sizeof(double) * (size_t)nvars * (size_t)B;
+        if (h->ws_ps.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (ps, %zu bytes)", bytes);
+        if (!ps_soa && h->ws_in.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+    }
+    size_t stage_per_cand = 0;
+    for (const Item &it : items) {
+        if (!it.on) continue;
+        if (it.ws->reserve(sizeof(double) * (size_t)it.n * (size_t)B))
+            return fail(CB200_ERR_NOMEM, "device out of memory for result buffers (B=%lld)", (long long)B);
+        if (it.user && !out_soa) stage_per_cand += (size_t)it.n;
+    }
+    if (stage_per_cand && h->ws_out.reserve(sizeof(double) * stage_per_cand * (size_t)B))
+        return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+
+    cudaStream_t streams[cb200_handle::NAUX + 1];
+    int ns_used = 1;
+    streams[0] = h->stream;
+    if (nchunks > 1) {
+        for (int k = 0; k < cb200_handle::NAUX; k++) streams[ns_used++] = h->aux[k];
+        CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));   // memsets / tables above are ordered before the chunks
+        for (int k = 1; k < ns_used; k++) CUDA_TRY(cudaStreamWaitEvent(streams[k], h->ev_fork, 0));
+    }
+    for (int c = 0; c < nchunks; c++) {
+        const long long b0 = (long long)c * Bc, bn = std::min(Bc, B - b0);
+        cudaStream_t st = streams[c % ns_used];
+        const double *d_ps = nullptr;
+        if (nvars > 0) {
+            double *soa = (double *)h->ws_ps.p + (size_t)b0 * nvars;   // chunk SoA block [nvars][bn]
+            if (ps_soa) {  // host, variable-major (single chunk)
+                CUDA_TRY(cudaMemcpy2DAsync(soa, sizeof(double) * bn, ps + b0, sizeof(double) * ldb, sizeof(double) * bn,
+                                           nvars, cudaMemcpyHostToDevice, st));
+            } else {       // host, candidate-major (Julia nvars x B matrix)
+                double *stg = (double *)h->ws_in.p + (size_t)b0 * nvars;
+                if (ldb == nvars)
+                    CUDA_TRY(cudaMemcpyAsync(stg, ps + (size_t)b0 * ldb, sizeof(double) * (size_t)nvars * (size_t)bn,
+                                             cudaMemcpyHostToDevice, st));
+                else
+                    CUDA_TRY(cudaMemcpy2DAsync(stg, sizeof(double) * nvars, ps + (size_t)b0 * ldb, sizeof(double) * ldb,
+                                               sizeof(double) * nvars, bn, cudaMemcpyHostToDevice, st));
+                int rc = transpose(h, st, stg, nvars, soa, bn, bn, nvars);
+                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            }
+            d_ps = soa;
+        }
+        DevSet d = shared;
+        for (const Item &it : items)
+            if (it.on) d.*(it.slot) = (double *)it.ws->p + (size_t)b0 * (size_t)it.n;
+        int rc = eval_core(h, st, d_ps, bn, bn, pl, d);
+        if (rc) return rc;
+        size_t stage_off = (size_t)b0 * stage_per_cand;
+        for (const Item &it : items) {
+            if (!it.on || !it.user) continue;
+            const size_t bytes = sizeof(double) * (size_t)it.n * (size_t)bn;
+            if (out_soa) {  // quantity-major host output (single chunk): rows are contiguous
+                CUDA_TRY(cudaMemcpyAsync(it.user, d.*(it.slot), bytes, cudaMemcpyDeviceToHost, st));
+            } else {
+                double *stg = (double *)h->ws_out.p + stage_off;
+                stage_off += (size_t)it.n * (size_t)bn;
+                rc = transpose(h, st, d.*(it.slot), bn, stg, it.n, it.n, bn);
+                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+                CUDA_TRY(cudaMemcpyAsync(it.user + (size_t)b0 * (size_t)it.n, stg, bytes, cudaMemcpyDeviceToHost, st));
+            }
+        }
+    }
+    for (int k = 1; k < ns_used; k++) {   // join
+        CUDA_TRY(cudaEventRecord(h->ev_join[k - 1], streams[k]));
+        CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[k - 1], 0));
+    }
+    if (pl.osum) CUDA_TRY(cudaMemcpyAsync(out->objective_sum, shared.osum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (pl.gsum)
+        CUDA_TRY(cudaMemcpyAsync(out->grad_sum, shared.gsum, sizeof(double) * (size_t)nvars, cudaMemcpyDeviceToHost, h->stream));
+    if (pl.fsum) CUDA_TRY(cudaMemcpyAsync(out->fim_sum, shared.fsum, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
     return CB200_OK;
 }
 

@@ -203,7 +203,8 @@ class NativeLayer:
         o.objective_row = objective_row
         _check(lib().cb200_eval(self._h, C.c_void_p(ps_ptr), B, ldb, want, flags, C.byref(o)), "cb200_eval")
 
-    def eval_host(self, ps, want: int, objective_row: int = 1, fim_init=None, pinned_out: dict | None = None):
+    def eval_host(self, ps, want: int, objective_row: int = 1, fim_init=None, pinned_out: dict | None = None,
+                  with_sums: bool = False):
         """ps: (B, nvars) C-contiguous float64 == a Julia nvars x B matrix. Returns dict of (B, n) arrays."""
         ps = np.ascontiguousarray(ps, dtype=np.float64)
         if ps.ndim == 1:
@@ -232,6 +233,13 @@ class NativeLayer:
             if fim_init is not None:
                 fi = np.asfortranarray(fim_init, dtype=np.float64)
                 ptrs["fim_init"] = fi.ctypes.data
+        if with_sums:   # cross-candidate sums accumulated on the device (the per-rank partials of a sharded run)
+            if want & WANT_OBJ:
+                res["objective_sum"] = np.zeros(1, dtype=np.float64)
+                ptrs["objective_sum"] = res["objective_sum"].ctypes.data
+            if want & WANT_GRAD:
+                res["grad_sum"] = np.zeros(max(self.nvars, 1), dtype=np.float64)[: self.nvars]
+                ptrs["grad_sum"] = res["grad_sum"].ctypes.data
         if self.nvars == 0:  # nothing tunable: still one candidate per row
             ps = np.zeros((B, 1))
         self.eval_raw(ps.ctypes.data, B, max(self.nvars, 1), want, 0, ptrs, objective_row)

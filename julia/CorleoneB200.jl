@@ -109,11 +109,12 @@ mutable struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     fim::Tuple{Int, Int}                 # (1-based offset of the first F_triu state, n) or (0, 0)
     handle::Ptr{Cvoid}
     sizes::Sizes
+    nx::Int
 end
 function EnsembleB200(; model::Symbol, steps_per_piece = 1, method = :tsit5, device = 0,
         model_data = Float64[], fim = (0, 0))
     e = EnsembleB200(model, steps_per_piece, method, device, collect(Float64, model_data), fim, C_NULL,
-        Sizes(0, 0, 0, 0, 0, 0, 0))
+        Sizes(0, 0, 0, 0, 0, 0, 0), 0)
     finalizer(e) do x
         x.handle == C_NULL || ccall((:cb200_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle)
     end
@@ -168,6 +169,7 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
     s = Ref(Sizes(0, 0, 0, 0, 0, 0, 0))
     check(ccall((:cb200_get_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{Sizes}), e.handle, s), "cb200_get_sizes")
     e.sizes = s[]
+    e.nx = nx
     return e.handle
 end
 
@@ -175,7 +177,7 @@ end
 flatten(ps::NamedTuple) = reduce(vcat, (vcat(p.u0, p.p, p.controls) for p in values(ps)))
 
 """
-    evaluate(e, shooting, P, st; want, objective_row = 1)
+    evaluate(e, P; want, objective_row = 1)   (after `handle!(e, shooting, ps, st)`)
 
 Batched evaluation -- the axis the reference does not have.  `P` is an `nvars x B` Matrix, one flat
 candidate per column.  Returns a NamedTuple of `n x B` matrices (host memory, owned by Julia).
@@ -185,7 +187,7 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     s = e.sizes
     B = size(P, 2)
     alloc(flag, n) = (want & flag) != 0 ? Matrix{Float64}(undef, n, B) : Matrix{Float64}(undef, 0, 0)
-    xend = alloc(WANT_XEND, Int(s.n_units) * (Int(s.n_row) - 0))           # nx*I <= n_row*I; trimmed below
+    xend = alloc(WANT_XEND, e.nx * s.n_units)
     sens = alloc(WANT_SENS, s.n_sens)
     traj = alloc(WANT_TRAJ, s.n_row * s.n_samples)
     dk = alloc(WANT_DEFECTS, s.n_defects)
