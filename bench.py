@@ -306,12 +306,30 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = units_per_step * e2e_steps / float(t.item())
+    # context for e2e: the same bytes as plain pinned copies, both directions concurrently on two streams
+    d_in = torch.empty(B * nvars, dtype=torch.float64, device=dev)
+    d_res = torch.empty(B * sum(sz[f] for f in fields), dtype=torch.float64, device=dev)
+    h_res = torch.empty(d_res.shape, dtype=torch.float64).pin_memory()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(5):
+        with torch.cuda.stream(s_in):
+            d_in.copy_(pin_ps.view(-1), non_blocking=True)
+        with torch.cuda.stream(s_out):
+            h_res.copy_(d_res, non_blocking=True)
+    torch.cuda.synchronize()
+    copy_ms = (time.perf_counter() - t0) / 5 * 1e3
+    del d_in, d_res, h_res
     h2d = 8 * B * nvars
     d2h = 8 * B * sum(sz[f] for f in fields)
 
     if rank == 0:
         hbm_peak, hbm_src = load_peaks()
-        fp64_peak = nat.probe_fp64_tflops(local_rank, 40000)
+        # FP64 roof: DFMA and DMMA share one datapath on B200 (tools/dmma_micro.cu); the higher probe is the peak
+        peak_dfma = nat.probe_fp64_tflops(local_rank, 40000)
+        peak_dmma = nat.probe_fp64_mma_tflops(local_rank, 20000)
+        fp64_peak = max(peak_dfma, peak_dmma)
         ach_tflops = FLOPS_PER_UNIT * I_INTERVALS * B / (kern_ms * 1e-3) / 1e12
         ach_gbs = BYTES_PER_UNIT * I_INTERVALS * B / (kern_ms * 1e-3) / 1e9
         line = {
@@ -325,7 +343,9 @@ def main():
                        "l2": f"inputs larger than L2: {nsets} rotating buffer sets of {set_bytes / 1e6:.0f} MB",
                        "parallelism": f"batch-sharded x{world}, allreduce(objective_sum, grad_sum)" if world > 1 else "single GPU"},
             "e2e": {"value": e2e_value, "unit": "units/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "api": "cb200_eval with pinned host buffers, candidate-major (Julia layout)"},
+                    "steps": e2e_steps, "ms_per_step": 1e3 * units_per_step / e2e_value,
+                    "pcie_copy_only_ms": copy_ms,
+                    "api": "cb200_eval with pinned host buffers, candidate-major (Julia layout), 8 chunks on 3 streams"},
             "gpu_launches": int(launches_timed),
             "clocks": clk.summary(),
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
@@ -333,7 +353,9 @@ def main():
                          "kernel": "shoot_kernel<Lqr,G=4,Tsit5,uniform,4 blocks/SM> incl. fused defect/gradient epilogue",
                          "kernel_ms": kern_ms,
                          "flops_per_unit": FLOPS_PER_UNIT, "bytes_per_unit": BYTES_PER_UNIT,
-                         "peak_source": "DFMA-chain probe measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                         "peak_source": "FP64 probes measured in this run, max of DFMA chains "
+                                        f"({peak_dfma:.2f}) and mma.sync.m8n8k4.f64 ({peak_dmma:.2f}) TFLOP/s; "
+                                        "MEASURED_PEAKS.json has no FP64 figure",
                          "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
                                  "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}},
         }

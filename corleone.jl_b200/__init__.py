@@ -15,11 +15,14 @@ from .multiple_shooting import (MultipleShootingLayer, control_matchings, defaul
                                 stage_ordered_shooting_constraints, stage_ordered_shooting_constraints_,
                                 state_matchings)
 from .node_initialization import (constant_initialization, custom_initialization, forward_initialization,
+                                  forward_initialization_batch,
                                   hybrid_initialization, linear_initialization, random_initialization)
 from .problem import MODEL_REGISTRY, ODEProblem, RK4, Tsit5
 from .single_shooting import InitialConditionRemaker, SingleShootingLayer, from_vec, to_vec
 from .trajectory import Trajectory, is_shooting_solution, shooting_violations
 from . import native
+from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion, FisherECriterion,
+                       batched_criteria)
 
 
 def setup(rng, layer):

@@ -48,6 +48,11 @@ struct DefectEntry {
     int pos_stage;  // position in stage_ordered_shooting_constraints
 };
 
+struct JacConst {   // jac[slot] = value (the matching conditions' constant +-1 entries)
+    int slot;
+    double value;
+};
+
 struct GradEntry {   // grad[var] = sens[src] (src >= 0) or 1.0 (src == -1)
     int var;
     long long src;
@@ -103,6 +108,14 @@ __global__ void grad_kernel(const GradEntry *__restrict__ tab, int n, const doub
     }
 }
 
+// K5: the constant +-1 entries of cons_j (state / parameter / control matchings w.r.t. the next interval's variables)
+__global__ void jac_const_kernel(const JacConst *__restrict__ tab, int n, long long B, double *__restrict__ jac, long long ldo)
+{
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    for (int e = blockIdx.y; e < n; e += gridDim.y) jac[(long long)tab[e].slot * ldo + b] = tab[e].value;
+}
+
 // quadrature accumulation on the merged trajectory (src/multiple_shooting.jl:171-177)
 __global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const double *__restrict__ xend,
                                  long long ldx, long long B, int nx, int nrow, int I, const int *__restrict__ samp_off,
@@ -124,12 +137,17 @@ __global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const
 // K4 read-out: F = F_init + Symmetric(F_triu(t_end)) per candidate (lib/CorleoneOED/src/oed.jl:388-398,
 // augmentation.jl:233) and its sum over the candidates of this launch: warp-shuffle + one atomicAdd per
 // warp and matrix entry.
+// With `crit` the six optimality criteria of lib/CorleoneOED/src/criteria.jl:33-63 are evaluated per candidate on
+// Symmetric(F) (rows of crit: A = tr(inv F), D = 1/det F, E = max eig(inv F), FisherA = -tr F, FisherD = -det F,
+// FisherE = -min eig F) from the eigenvalues of F (cyclic Jacobi, n <= CB200_MAX_FIM).
+constexpr int CB200_MAX_FIM = 8;
 __global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long long B, int nx, int I, int f_off,
                            int n, const double *__restrict__ finit, double *__restrict__ fim, long long ldo,
-                           double *__restrict__ fsum)
+                           double *__restrict__ fsum, double *__restrict__ crit)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const bool live = b < B;
+    double A[CB200_MAX_FIM][CB200_MAX_FIM];
     for (int c = 0; c < n; c++)
         for (int r = 0; r < n; r++) {
             const int a = r < c ? r : c, bb = r < c ? c : r;  // upper-triangle entry (a, bb), a <= bb
@@ -139,11 +157,58 @@ __global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long 
                 v = xend[((long long)(I - 1) * nx + f_off + q) * ldx + b] + (finit ? finit[r + n * c] : 0.0);
                 if (fim) fim[(long long)(r + n * c) * ldo + b] = v;
             }
+            if (crit) A[r][c] = v;
             if (fsum) {
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
                 if ((threadIdx.x & 31) == 0) atomicAdd(fsum + r + n * c, v);
             }
         }
+    if (!crit || !live) return;
+    double tr = 0.0;
+    for (int k = 0; k < n; k++) tr += A[k][k];
+    for (int sweep = 0; sweep < 40; sweep++) {   // cyclic Jacobi on the symmetric matrix; eigenvalues end on the diagonal
+        double off = 0.0, dia = 0.0;
+        for (int p = 0; p < n; p++) {
+            dia += A[p][p] * A[p][p];
+            for (int q = p + 1; q < n; q++) off += A[p][q] * A[p][q];
+        }
+        if (off <= 1e-32 * dia || off == 0.0) break;
+        for (int p = 0; p < n; p++)
+            for (int q = p + 1; q < n; q++) {
+                const double apq = A[p][q];
+                if (apq == 0.0) continue;
+                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
+                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
+                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
+                for (int k = 0; k < n; k++) {   // A <- A J
+                    const double akp = A[k][p], akq = A[k][q];
+                    A[k][p] = c * akp - sn * akq;
+                    A[k][q] = sn * akp + c * akq;
+                }
+                for (int k = 0; k < n; k++) {   // A <- J' A
+                    const double apk = A[p][k], aqk = A[q][k];
+                    A[p][k] = c * apk - sn * aqk;
+                    A[q][k] = sn * apk + c * aqk;
+                }
+            }
+    }
+    double det = 1.0, trinv = 0.0, lmin = A[0][0];
+    for (int k = 0; k < n; k++) {
+        const double l = A[k][k];
+        det *= l;
+        trinv += 1.0 / l;
+        lmin = fmin(lmin, l);
+    }
+    // max eig(inv F) = 1 / (smallest eigenvalue of F) for positive definite F; for an indefinite F the largest
+    // reciprocal is taken, as eigvals(inv(F)) would give
+    double einv = 1.0 / A[0][0];
+    for (int k = 1; k < n; k++) einv = fmax(einv, 1.0 / A[k][k]);
+    crit[0 * ldo + b] = trinv;
+    crit[1 * ldo + b] = 1.0 / det;
+    crit[2 * ldo + b] = einv;
+    crit[3 * ldo + b] = -tr;
+    crit[4 * ldo + b] = -det;
+    crit[5 * ldo + b] = -lmin;
 }
 
 // tiled transpose: in[r*ld_in + c] (nr x nc) -> out[c*ld_out + r]
@@ -180,6 +245,26 @@ __global__ void dfma_probe_kernel(double *out, int iters, double seed)
         a7 = fma(a7, m, c);
     }
     out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+// FP64 tensor-path probe: 4 independent mma.sync.m8n8k4.f64 accumulator chains per warp.  On B200 DMMA and DFMA
+// share one FP64 datapath (tools/dmma_micro.cu: the mixed rate never exceeds either alone); DMMA reaches the
+// nominal 64 FMA/clk/SM, DFMA ~58, so the higher of the two probes is the FP64 roof.
+__global__ void dmma_probe_kernel(double *out, int iters, double seed)
+{
+    double c[8];
+    for (int i = 0; i < 8; i++) c[i] = seed + 1e-3 * threadIdx.x + i;
+    const double a = 1.0 + 1e-9 * threadIdx.x, b = 1e-6;
+    for (int it = 0; it < iters; it++) {
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                         : "+d"(c[2 * i]), "+d"(c[2 * i + 1])
+                         : "d"(a), "d"(b));
+    }
+    double s = 0.0;
+    for (int i = 0; i < 8; i++) s += c[i];
+    out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = s;
 }
 
 // ------------------------------------------------------------------ handle
@@ -222,7 +307,9 @@ struct cb200_handle {
     std::vector<long long> h_sens_off;
     std::vector<int> h_cidx, h_ic_src;
     std::vector<DefectEntry> defects;
-    std::vector<int> dpos_kind, dpos_stage, oth_off;
+    std::vector<int> dpos_kind, dpos_stage, oth_off, jpos;
+    std::vector<JacConst> jac_const;   // the +-1 entries of cons_j
+    JacConst *d_jac_const = nullptr;
     std::vector<MatchEntry> oth;
     std::vector<long long> jac_rows, jac_cols, jac_src;
     long long n_sens = 0;
@@ -245,7 +332,7 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed;
 };
 
 static int default_G(int model)
@@ -288,6 +375,22 @@ static int launch_model(int model, int G, int method, const DevLayer &L, const d
     case CB200_MODEL_LIN1D_OED: return launch_lin1d_oed(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_DENSE20: return launch_dense20(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_EGERSTEDT: return launch_egerstedt(G, method, L, ps, ldb, B, o, s);
+    default: return -1000;
+    }
+}
+
+static int forward_model(int model, int method, const DevLayer &L, double *ps, long long ldb, long long B,
+                         const unsigned char *fixed, cudaStream_t s)
+{
+    switch (model) {
+    case CB200_MODEL_LOTKA3: return forward_lotka3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LQR: return forward_lqr(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKA2: return forward_lotka2(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKA2_OED: return forward_lotka2_oed(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LIN1D: return forward_lin1d(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LIN1D_OED: return forward_lin1d_oed(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DENSE20: return forward_dense20(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_EGERSTEDT: return forward_egerstedt(method, L, ps, ldb, B, fixed, s);
     default: return -1000;
     }
 }
@@ -390,7 +493,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     }
 
     // per-interval tables
-    std::vector<double> pt0, pt1, ph, ic_fix;
+    std::vector<double> pt0, pt1, ph, ic_fix, ic_fix0;
     int po = 0, vo = 0, so = 0, co = 0, sio = 0;
     long long seo = 0;
     long long igo = 0;
@@ -448,6 +551,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
             }
             h->h_ic_src.push_back(src);
             ic_fix.push_back(fix);
+            // the forward sweep calls the layer without the shooting flag: fixval = problem.u0 (node_initialization.jl:165)
+            ic_fix0.push_back(src >= 0 ? 0.0 : (nu0 == 0 ? d->u0[k] : d->u0[d->ic_constants[co + ((int)d->ic_sorting[(size_t)i * nx + k] - 1)] - 1]));
         }
         co += ncon;
         sidx_off[i + 1] = sidx_off[i] + d->n_shooting_indices[i];
@@ -497,6 +602,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
             for (int q = sidx_off[i]; q < sidx_off[i + 1]; q++) (d->shooting_indices[q] <= nx ? n_u : n_c)++;
             n_p += ntp;
         }
+        h->jpos.assign((size_t)I * nx, -1);
         h->dpos_kind.assign((size_t)I * nx, -1);
         h->dpos_stage.assign((size_t)I * nx, -1);
         h->oth_off.assign((size_t)I + 1, 0);
@@ -539,6 +645,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                             e.b_kind = 2;
                             e.b_const = ic_fix[(size_t)i * nx + rI];
                         }
+                        h->jpos[(size_t)(i - 1) * nx + rI] = (int)h->jac_rows.size();
                         for (int dd = 0; dd < h->ns[i - 1]; dd++) {
                             h->jac_rows.push_back(o + 1);
                             h->jac_cols.push_back(h->h_var_off[i - 1] + dd + 1);
@@ -571,15 +678,18 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         for (int i = std::max(I, 1); i <= I; i++) h->oth_off[i] = (int)h->oth.size();
     }
 
+    for (size_t k = 0; k < h->jac_src.size(); k++)
+        if (h->jac_src[k] < 0) h->jac_const.push_back(JacConst{(int)k, h->jac_src[k] == -1 ? 1.0 : -1.0});
     // upload
     std::vector<char> blob;
     const size_t o_M = push(blob, h->h_M), o_po = push(blob, h->h_piece_off), o_t0 = push(blob, pt0),
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
-                 o_if = push(blob, ic_fix), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
+                 o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
                  o_de = push(blob, h->defects), o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol),
                  o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
-                 o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth);
+                 o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos),
+                 o_jc = push(blob, h->jac_const);
     const size_t o_gr = (blob.size() + 15) & ~size_t(15);
     h->grad_cap = std::max(1, L.nvars);
     blob.resize(o_gr + sizeof(GradEntry) * (size_t)h->grad_cap);
@@ -631,6 +741,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.n_c = (const int *)(base + o_nc);
     L.ic_src = (const int *)(base + o_is);
     L.ic_fix = (const double *)(base + o_if);
+    L.ic_fix0 = (const double *)(base + o_if0);
     L.sens_off = (const long long *)(base + o_se);
     L.samp_off = (const int *)(base + o_so);
     L.dir_pcol = (const signed char *)(base + o_dp);
@@ -639,6 +750,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.dpos_stage = (const int *)(base + o_dst);
     L.oth_off = (const int *)(base + o_oo);
     L.oth = (const MatchEntry *)(base + o_ot);
+    L.jpos = (const int *)(base + o_jp);
+    h->d_jac_const = (JacConst *)(base + o_jc);
     h->d_defects = (DefectEntry *)(base + o_de);
     h->d_quad = (int *)(base + o_q);
     h->d_grad = (GradEntry *)(base + o_gr);
@@ -678,7 +791,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq})
+                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed})
         b->release();
     if (h->tables) cudaFree(h->tables);
     for (int k = 0; k < cb200_handle::EV_RING; k++) {
@@ -784,7 +897,7 @@ static int transpose(cb200_handle *h, cudaStream_t st, const double *in, long lo
 
 // what one evaluation produces, resolved from (want, out)
 struct EvalPlan {
-    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum;
+    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum, jac, crit;
     bool fused_grad, need_sens, need_xend;
     int obj_state, obj_ctrl_var, obj_quad, objective_row;
 };
@@ -792,7 +905,7 @@ struct EvalPlan {
 // device SoA buffers of one batch (or one chunk of it), leading dimension = its candidate count
 struct DevSet {
     double *xend = nullptr, *sens = nullptr, *traj = nullptr, *dk = nullptr, *ds = nullptr, *obj = nullptr,
-           *grad = nullptr, *fim = nullptr, *objq = nullptr;
+           *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr;
     double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // shared by all chunks (atomic accumulation)
     const double *finit = nullptr;
 };
@@ -823,6 +936,7 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     so.objq = d.objq;
     so.grad = pl.fused_grad ? d.grad : nullptr;
     so.grad_sum = pl.fused_grad ? d.gsum : nullptr;
+    so.jac = d.jac;
     so.obj_state = pl.obj_state;
     so.obj_all = pl.obj_quad;
     const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
@@ -847,13 +961,18 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
         grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
         h->launches++;
     }
+    if (pl.jac && !h->jac_const.empty()) {
+        const int nc = (int)h->jac_const.size();
+        jac_const_kernel<<<dim3(nblk(B, 128), (unsigned)std::min(nc, 4096)), 128, 0, st>>>(h->d_jac_const, nc, B, d.jac, B);
+        h->launches++;
+    }
     if (pl.traj && h->nquad > 0 && I > 1) {
         traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, d.xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
                                                      h->d_quad, h->nquad);
         h->launches++;
     }
-    if (pl.fim || pl.fsum) {
-        fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, B, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, B, d.fsum);
+    if (pl.fim || pl.fsum || pl.crit) {
+        fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, B, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, B, d.fsum, d.crit);
         h->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -889,7 +1008,10 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     pl.fsum = (want & CB200_WANT_FIM) && out->fim_sum;
     pl.osum = (want & CB200_WANT_OBJ) && out->objective_sum;
     pl.gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
-    if ((pl.fim || pl.fsum) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
+    pl.jac = (want & CB200_WANT_JAC) && out->jac_vals;
+    pl.crit = (want & CB200_WANT_CRIT) && out->criteria;
+    if ((pl.fim || pl.fsum || pl.crit) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
+    if (pl.crit && h->fim_n > CB200_MAX_FIM) return fail(CB200_ERR_UNSUPPORTED, "criteria need fim_n <= %d", CB200_MAX_FIM);
     pl.obj_state = pl.obj_ctrl_var = -1;
     pl.objective_row = out->objective_row;
     if (pl.obj || pl.grad || pl.osum || pl.gsum) {
@@ -905,8 +1027,8 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         }
     }
     pl.fused_grad = (pl.grad || pl.gsum) && pl.obj_state >= 0;   // gradient written by the shooting kernel
-    pl.need_sens = pl.sens || pl.fused_grad;                     // sensitivity directions are integrated
-    pl.need_xend = pl.xend || pl.fim || pl.fsum || (pl.traj && h->nquad > 0);
+    pl.need_sens = pl.sens || pl.fused_grad || pl.jac;           // sensitivity directions are integrated
+    pl.need_xend = pl.xend || pl.fim || pl.fsum || pl.crit || (pl.traj && h->nquad > 0);
     const bool need_objq = (pl.obj || pl.osum) && pl.obj_state >= 0;
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {
         h->h_grad.assign(1, GradEntry{pl.obj_ctrl_var, -1});
@@ -925,6 +1047,8 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         {pl.grad, nvars, &h->ws_grad, out->grad, &DevSet::grad},
         {pl.fim, n2, &h->ws_fim, out->fim, &DevSet::fim},
         {need_objq, I, &h->ws_objq, nullptr, &DevSet::objq},
+        {pl.jac, (long long)h->jac_rows.size(), &h->ws_jac, out->jac_vals, &DevSet::jac},
+        {pl.crit, 6, &h->ws_crit, out->criteria, &DevSet::crit},
     };
 
     // ---- cross-candidate sums (expectation-type objective / gradient, FIM): accumulated on the device
@@ -944,7 +1068,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (shared.osum) CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double), h->stream));
         if (shared.gsum) CUDA_TRY(cudaMemsetAsync(shared.gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
         if (shared.fsum) CUDA_TRY(cudaMemsetAsync(shared.fsum, 0, sizeof(double) * n2, h->stream));
-        if (out->fim_init && (pl.fim || pl.fsum)) {
+        if (out->fim_init && (pl.fim || pl.fsum || pl.crit)) {
             if (h->ws_finit.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
             CUDA_TRY(cudaMemcpyAsync(h->ws_finit.p, out->fim_init, sizeof(double) * n2,
                                      dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
@@ -1080,27 +1204,102 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     return CB200_OK;
 }
 
-extern "C" double cb200_probe_fp64_tflops(int device, int iters)
+// forward_initialization(rng, shooting; ps, fixed_indices) (src/node_initialization.jl:152-170) for B candidates:
+// ps is updated in place (only the u0 entries of the intervals change).
+extern "C" int cb200_forward_init(cb200_handle *h, double *ps, int64_t B, int64_t ldb, uint32_t flags,
+                                  const int32_t *fixed_indices, int32_t n_fixed)
+{
+    if (!h || (!ps && h->L.nvars > 0)) return fail(CB200_ERR_ARG, "null argument");
+    if (B < 0 || n_fixed < 0 || (n_fixed > 0 && !fixed_indices)) return fail(CB200_ERR_ARG, "bad argument");
+    if (B == 0 || h->L.nvars == 0) return CB200_OK;
+    std::lock_guard<std::mutex> lk(h->mu);
+    CUDA_TRY(cudaSetDevice(h->device));
+    const int I = h->L.I, nvars = h->L.nvars;
+    const bool dev = flags & CB200_MEM_DEVICE, soa = flags & CB200_PS_SOA;
+    if (soa ? (ldb < B) : (ldb < nvars)) return fail(CB200_ERR_ARG, "ldb too small");
+    std::vector<unsigned char> fx((size_t)I, 0);
+    for (int k = 0; k < n_fixed; k++) {
+        if (fixed_indices[k] < 1 || fixed_indices[k] > I) return fail(CB200_ERR_ARG, "fixed_indices entry out of 1..I");
+        fx[fixed_indices[k] - 1] = 1;
+    }
+    if (h->ws_fixed.reserve((size_t)I)) return fail(CB200_ERR_NOMEM, "device out of memory");
+    CUDA_TRY(cudaMemcpyAsync(h->ws_fixed.p, fx.data(), (size_t)I, cudaMemcpyHostToDevice, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));   // fx is a stack-lifetime buffer
+    double *d_ps = ps;
+    long long d_ldb = ldb;
+    const size_t bytes = sizeof(double) * (size_t)nvars * (size_t)B;
+    if (!(dev && soa)) {
+        if (h->ws_ps.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (ps)");
+        d_ps = (double *)h->ws_ps.p;
+        d_ldb = B;
+        if (soa) {  // host, variable-major
+            CUDA_TRY(cudaMemcpy2DAsync(d_ps, sizeof(double) * B, ps, sizeof(double) * ldb, sizeof(double) * B, nvars,
+                                       cudaMemcpyHostToDevice, h->stream));
+        } else {
+            const double *cm = ps;
+            long long ldc = ldb;
+            if (!dev) {  // host, candidate-major
+                if (h->ws_in.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+                CUDA_TRY(cudaMemcpy2DAsync(h->ws_in.p, sizeof(double) * nvars, ps, sizeof(double) * ldb,
+                                           sizeof(double) * nvars, B, cudaMemcpyHostToDevice, h->stream));
+                cm = (const double *)h->ws_in.p;
+                ldc = nvars;
+            }
+            int rc = transpose(h, h->stream, cm, ldc, d_ps, B, B, nvars);
+            if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        }
+    }
+    int rc = forward_model(h->model, h->method, h->L, d_ps, d_ldb, B, (const unsigned char *)h->ws_fixed.p, h->stream);
+    if (rc == -1000) return fail(CB200_ERR_UNSUPPORTED, "model %d has no forward-sweep kernel", h->model);
+    if (rc) return fail(CB200_ERR_CUDA, "forward kernel launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+    h->launches++;
+    if (!(dev && soa)) {
+        if (soa) {
+            CUDA_TRY(cudaMemcpy2DAsync(ps, sizeof(double) * ldb, d_ps, sizeof(double) * B, sizeof(double) * B, nvars,
+                                       cudaMemcpyDeviceToHost, h->stream));
+        } else if (dev) {
+            rc = transpose(h, h->stream, d_ps, B, ps, ldb, nvars, B);
+            if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+        } else {
+            rc = transpose(h, h->stream, d_ps, B, (double *)h->ws_in.p, nvars, nvars, B);
+            if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
+            CUDA_TRY(cudaMemcpy2DAsync(ps, sizeof(double) * ldb, h->ws_in.p, sizeof(double) * nvars, sizeof(double) * nvars,
+                                       B, cudaMemcpyDeviceToHost, h->stream));
+        }
+    }
+    if (!dev) CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return CB200_OK;
+}
+
+static double probe_fp64(int device, int iters, bool mma)
 {
     if (cudaSetDevice(device) != cudaSuccess) return -1.0;
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return -1.0;
-    const int blocks = prop.multiProcessorCount * 8, threads = 256;
+    const int blocks = prop.multiProcessorCount * (mma ? 2 : 8), threads = 256;
     double *out = nullptr;
     if (cudaMalloc(&out, sizeof(double) * (size_t)blocks * threads) != cudaSuccess) return -1.0;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0);
     cudaEventCreate(&e1);
-    dfma_probe_kernel<<<blocks, threads>>>(out, iters / 4 + 1, 1.0);  // warm-up
+    auto launch = [&](int n, double seed) {
+        if (mma)
+            dmma_probe_kernel<<<blocks, threads>>>(out, n, seed);
+        else
+            dfma_probe_kernel<<<blocks, threads>>>(out, n, seed);
+    };
+    launch(iters / 4 + 1, 1.0);  // warm-up
     double best = -1.0;
     for (int rep = 0; rep < 3; rep++) {
         cudaEventRecord(e0);
-        dfma_probe_kernel<<<blocks, threads>>>(out, iters, 1.0 + rep);
+        launch(iters, 1.0 + rep);
         cudaEventRecord(e1);
         if (cudaEventSynchronize(e1) != cudaSuccess) break;
         float ms = 0.f;
         cudaEventElapsedTime(&ms, e0, e1);
-        const double flops = 2.0 * 8.0 * (double)iters * (double)blocks * threads;
+        // per thread and iteration: 8 DFMA, or 4 DMMA of 8*8*4 FMA shared by the 32 lanes of a warp
+        const double fma_per_thread_iter = mma ? 4.0 * 256.0 / 32.0 : 8.0;
+        const double flops = 2.0 * fma_per_thread_iter * (double)iters * (double)blocks * threads;
         best = std::max(best, flops / (ms * 1e-3) / 1e12);
     }
     cudaEventDestroy(e0);
@@ -1108,3 +1307,6 @@ extern "C" double cb200_probe_fp64_tflops(int device, int iters)
     cudaFree(out);
     return best;
 }
+
+extern "C" double cb200_probe_fp64_tflops(int device, int iters) { return probe_fp64(device, iters, false); }
+extern "C" double cb200_probe_fp64_mma_tflops(int device, int iters) { return probe_fp64(device, iters, true); }

@@ -32,6 +32,7 @@ struct DevLayer {
     const int *n_c;          // [I]
     const int *ic_src;       // [I*nx] >= 0: index into the interval's ps.u0; -1: fixed value
     const double *ic_fix;    // [I*nx]
+    const double *ic_fix0;   // [I*nx] the same with fixval = problem.u0 on every interval (forward sweep)
     const long long *sens_off;  // [I] first row of the interval's block in `sens`
     const int *samp_off;     // [I] first merged-trajectory sample of the interval
     const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
@@ -39,6 +40,8 @@ struct DevLayer {
     // shooting defects of the boundary between interval i and i+1 (src/multiple_shooting.jl:150-163)
     const int *dpos_kind;    // [I*nx] position of the state matching of state k in shooting_constraints, -1: none
     const int *dpos_stage;   // [I*nx] same, in stage_ordered_shooting_constraints
+    const int *jpos;         // [I*nx] first cons_j value slot of (boundary i, state k): its ns_i entries follow in
+                             //        direction order (cb200_jac_structure order), -1: state not matched
     const int *oth_off;      // [I+1] range of the boundary's parameter / control matchings in `oth`
     const struct MatchEntry *oth;
 };
@@ -58,6 +61,7 @@ struct ShootOut {
     double *objq;      // [i * ldo + b] end value of state obj_state on interval i
     double *grad;      // [var * ldo + b]
     double *grad_sum;  // [var] sum over the candidates of this launch (atomicAdd of warp partial sums)
+    double *jac;       // [slot * ldo + b] values of d(shooting_constraints)/d(ps) in cb200_jac_structure order
     int obj_state;     // 0-based state row of the objective, -1: none
     int obj_all;       // 1: every interval contributes to the objective (quadrature state), 0: last interval only
 };
@@ -80,6 +84,22 @@ int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, lon
                      const ShootOut &o, cudaStream_t s);
 int launch_dense20(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
                    const ShootOut &o, cudaStream_t s);
+int forward_lotka3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_lotka2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_lqr(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_lin1d(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_egerstedt(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_lotka2_oed(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_lin1d_oed(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int forward_dense20(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
 
 }  // namespace cb200

@@ -358,6 +358,19 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
                 }
             }
         }
+        // K5: constraint-Jacobian values.  d defect(i, k) / d (variable d of interval i) = S[k, d]; its slot in
+        // cb200_jac_structure order is jpos[i, k] + d, so the Jacobian is written without a gather pass
+        if (o.jac && live && i + 1 < L.I) {
+#pragma unroll
+            for (int k = 0; k < NX; k++) {
+                const int jp = __ldg(L.jpos + i * NX + k);
+                if (jp >= 0) {
+#pragma unroll
+                    for (int g = 0; g < G; g++)
+                        if (d0 + g < ns) o.jac[(long long)(jp + d0 + g) * o.ldo + b] = CB200_SS(g, k);
+                }
+            }
+        }
         // objective gradient: variable voff + d is direction d of this interval, so every thread owns the
         // gradient entries of its directions (zero when the interval does not reach the objective)
         if (o.grad || o.grad_sum) {
@@ -386,6 +399,91 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
     }
 #undef CB200_XS
 #undef CB200_SS
+}
+
+// Forward initialisation sweep (src/node_initialization.jl:152-170): one thread per candidate walks the intervals
+// in order, overwrites the node values ps.interval_i.u0 with the leading entries of the previous interval's end
+// sample (unless the interval is listed in fixed_indices) and integrates on.  As in the reference the sweep calls
+// the layer WITHOUT the shooting flag, so non-tunable states restart from problem.u0 (table ic_fix0), not from 0.
+template <class Mdl, int METHOD>
+__global__ void __launch_bounds__(128)
+forward_kernel(const __grid_constant__ DevLayer L, double *__restrict__ ps, long long ldb, long long B,
+               const unsigned char *__restrict__ fixed)
+{
+    constexpr int NX = Mdl::NX, NXD = Mdl::NXD, NQ = Mdl::NQ, NP = Mdl::NP;
+    constexpr int NQA = NQ > 0 ? NQ : 1, NCF = METHOD == 0 ? 21 : 4;
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    double carry[NX];
+#pragma unroll
+    for (int k = 0; k < NX; k++) carry[k] = 0.0;
+    for (int i = 0; i < L.I; i++) {
+        const int nu0 = __ldg(L.n_u0 + i), voff = __ldg(L.var_off + i);
+        double *v = ps + (long long)voff * ldb + b;
+        const bool keep = (i == 0) || fixed[i];
+        if (!keep) {  // sps.u0 .= u0[eachindex(sps.u0)]
+#pragma unroll
+            for (int m = 0; m < NX; m++)
+                if (m < nu0) v[(long long)m * ldb] = carry[m];
+        }
+        double yd[NXD], yq[NQA];
+#pragma unroll
+        for (int k = 0; k < NX; k++) {
+            const int src = __ldg(L.ic_src + i * NX + k);
+            double val = __ldg(L.ic_fix0 + i * NX + k);
+            if (src >= 0) {
+                if (keep) {
+                    val = v[(long long)src * ldb];
+                } else {
+#pragma unroll
+                    for (int m = 0; m < NX; m++) val = (m == src) ? carry[m] : val;
+                }
+            }
+            if (k < NXD)
+                yd[k < NXD ? k : 0] = val;
+            else
+                yq[k >= NXD ? k - NXD : 0] = val;
+        }
+        double p[NP];
+#pragma unroll
+        for (int q = 0; q < NP; q++) p[q] = (L.pmap_kind[q] == 0) ? v[(long long)(nu0 + L.pmap_idx[q]) * ldb] : 0.0;
+        const int M = __ldg(L.M + i), po = __ldg(L.piece_off + i);
+        const double *vc = v + (long long)(nu0 + L.ntp) * ldb;
+        for (int j = 0; j < M; j++) {
+#pragma unroll
+            for (int q = 0; q < NP; q++)
+                if (L.pmap_kind[q] == 1)
+                    p[q] = vc[(long long)__ldg(L.cidx + (long long)(po + j) * L.nact + L.pmap_idx[q]) * ldb];
+            double cf[NCF];
+            if (L.uniform_h) {
+#pragma unroll
+                for (int c = 0; c < NCF; c++) cf[c] = L.hA[c];
+            } else {
+                const double h = __ldg(L.ph + po + j);
+                if constexpr (METHOD == 0)
+                    tsit5_coeffs(h, cf);
+                else
+                    rk4_coeffs(h, cf);
+            }
+            typename Mdl::Force F[1];
+            integrate_piece<Mdl, 0, METHOD>(yd, yq, p, F, cf, L.K);
+        }
+#pragma unroll
+        for (int k = 0; k < NX; k++) carry[k] = (k < NXD) ? yd[k < NXD ? k : 0] : yq[k >= NXD ? k - NXD : 0];
+    }
+}
+
+template <class Mdl>
+int launch_forward(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+                   cudaStream_t s)
+{
+    if (B <= 0) return 0;
+    const unsigned grid = (unsigned)((B + 63) / 64);
+    if (method == 0)
+        forward_kernel<Mdl, 0><<<grid, 64, 0, s>>>(L, ps, ldb, B, fixed);
+    else
+        forward_kernel<Mdl, 1><<<grid, 64, 0, s>>>(L, ps, ldb, B, fixed);
+    return (int)cudaGetLastError();
 }
 
 // threads per block of the shooting kernel (<= 128, the __launch_bounds__); small blocks shorten the tail

@@ -18,4 +18,9 @@ int dense20_set_data(const double *host_data, long long n)
     if (n != 420) return -1;
     return (int)cudaMemcpyToSymbol(c_dense20, host_data, sizeof(double) * 420);
 }
+int forward_dense20(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Dense20>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

@@ -14,4 +14,9 @@ int launch_egerstedt(int G, int method, const DevLayer &L, const double *ps, lon
         return -1000;
     }
 }
+int forward_egerstedt(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Egerstedt>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

@@ -14,4 +14,9 @@ int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long lo
         return -1000;
     }
 }
+int forward_lin1d(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lin1d>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

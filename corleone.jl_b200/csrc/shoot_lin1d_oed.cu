@@ -11,4 +11,9 @@ int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, lon
         return -1000;
     }
 }
+int forward_lin1d_oed(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lin1dOed>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

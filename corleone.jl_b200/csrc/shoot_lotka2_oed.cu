@@ -11,4 +11,9 @@ int launch_lotka2_oed(int G, int method, const DevLayer &L, const double *ps, lo
         return -1000;
     }
 }
+int forward_lotka2_oed(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lotka2Oed>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

@@ -15,4 +15,9 @@ int launch_lotka3(int G, int method, const DevLayer &L, const double *ps, long l
         return -1000;
     }
 }
+int forward_lotka3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lotka3>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

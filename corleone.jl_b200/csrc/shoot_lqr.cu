@@ -15,4 +15,9 @@ int launch_lqr(int G, int method, const DevLayer &L, const double *ps, long long
         return -1000;
     }
 }
+int forward_lqr(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lqr>(method, L, ps, ldb, B, fixed, s);
+}
 }  // namespace cb200

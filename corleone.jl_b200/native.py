@@ -14,13 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CORLEONE_B200_LIB") or os.path.join(_HERE, "libcorleone_b200.so")
 _lib = None
 
-WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM = 1, 2, 4, 8, 16, 32, 64
+WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT = 1, 2, 4, 8, 16, 32, 64, 128, 256
 MEM_DEVICE, PS_SOA, OUT_SOA = 1, 2, 4
 
 EXPORTS = (
     "cb200_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_sizes",
     "cb200_block_structure", "cb200_set_stream", "cb200_eval", "cb200_jac_structure",
     "cb200_last_kernel_ms", "cb200_kernel_ms_history", "cb200_launch_count", "cb200_probe_fp64_tflops",
+    "cb200_probe_fp64_mma_tflops", "cb200_forward_init",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -48,6 +49,7 @@ class Out(C.Structure):
         ("defects_stage", C.c_void_p), ("objective", C.c_void_p), ("grad", C.c_void_p), ("fim", C.c_void_p),
         ("fim_sum", C.c_void_p), ("objective_sum", C.c_void_p), ("grad_sum", C.c_void_p),
         ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
+        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p),
     ]
 
 
@@ -77,6 +79,7 @@ def lib():
         L.cb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
         L.cb200_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
                                  C.POINTER(Out)]
+        L.cb200_forward_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, _i32p, C.c_int32]
         L.cb200_jac_structure.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
         L.cb200_last_kernel_ms.argtypes = [C.c_void_p]
         L.cb200_last_kernel_ms.restype = C.c_float
@@ -86,6 +89,8 @@ def lib():
         L.cb200_launch_count.restype = C.c_int64
         L.cb200_probe_fp64_tflops.argtypes = [C.c_int, C.c_int]
         L.cb200_probe_fp64_tflops.restype = C.c_double
+        L.cb200_probe_fp64_mma_tflops.argtypes = [C.c_int, C.c_int]
+        L.cb200_probe_fp64_mma_tflops.restype = C.c_double
         _lib = L
     return _lib
 
@@ -189,11 +194,21 @@ class NativeLayer:
     def launch_count(self) -> int:
         return int(lib().cb200_launch_count(self._h))
 
+    def forward_init(self, ps, fixed_indices=()):
+        """forward_initialization for a batch: ps (B, nvars) candidate-major; returns the updated copy."""
+        ps = np.array(ps, dtype=np.float64, order="C", copy=True)
+        if ps.ndim == 1:
+            ps = ps[None, :]
+        fx = _arr(list(fixed_indices) if len(fixed_indices) else [0], np.int32)
+        _check(lib().cb200_forward_init(self._h, C.c_void_p(ps.ctypes.data), ps.shape[0], max(self.nvars, 1), 0,
+                                        fx.ctypes.data_as(_i32p), len(fixed_indices)), "cb200_forward_init")
+        return ps
+
     # ---- evaluation
     def out_sizes(self):
         return dict(xend=self.nx * self.I, sens=self.n_sens, traj=self.n_row * self.n_samples,
                     defects_kind=self.n_defects, defects_stage=self.n_defects, objective=1, grad=self.nvars,
-                    fim=self.fim_n * self.fim_n)
+                    fim=self.fim_n * self.fim_n, jac_vals=self.jac_nnz, criteria=6)
 
     def eval_raw(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1):
         """Raw pointer call (host or device pointers as `flags` says). ptrs: field name -> int address."""
@@ -220,6 +235,8 @@ class NativeLayer:
         if want & WANT_OBJ: fields.append("objective")
         if want & WANT_GRAD: fields.append("grad")
         if want & WANT_FIM: fields.append("fim")
+        if want & WANT_JAC: fields.append("jac_vals")
+        if want & WANT_CRIT: fields.append("criteria")
         res = {}
         for f in fields:
             if pinned_out is not None and f in pinned_out:
@@ -230,9 +247,9 @@ class NativeLayer:
         if want & WANT_FIM:
             res["fim_sum"] = np.zeros(sz["fim"], dtype=np.float64)
             ptrs["fim_sum"] = res["fim_sum"].ctypes.data
-            if fim_init is not None:
-                fi = np.asfortranarray(fim_init, dtype=np.float64)
-                ptrs["fim_init"] = fi.ctypes.data
+        if (want & (WANT_FIM | WANT_CRIT)) and fim_init is not None:
+            fi = np.asfortranarray(fim_init, dtype=np.float64)   # kept alive until the call returns
+            ptrs["fim_init"] = fi.ctypes.data
         if with_sums:   # cross-candidate sums accumulated on the device (the per-rank partials of a sharded run)
             if want & WANT_OBJ:
                 res["objective_sum"] = np.zeros(1, dtype=np.float64)
@@ -248,3 +265,7 @@ class NativeLayer:
 
 def probe_fp64_tflops(device: int = 0, iters: int = 20000) -> float:
     return float(lib().cb200_probe_fp64_tflops(device, iters))
+
+
+def probe_fp64_mma_tflops(device: int = 0, iters: int = 20000) -> float:
+    return float(lib().cb200_probe_fp64_mma_tflops(device, iters))

@@ -84,17 +84,23 @@ def custom_initialization(rng, shooting: MultipleShootingLayer, ps=None, u0s=(),
 
 def forward_initialization(rng, shooting: MultipleShootingLayer, ps=None, fixed_indices=(), **kw):
     """node_initialization.jl:152-170: sequential forward sweep through the intervals; intervals listed in
-    fixed_indices (1-based) keep their node."""
+    fixed_indices (1-based) keep their node.  The sweep runs on the GPU (cb200_forward_init): one thread per
+    candidate walks the intervals, calling the layer without the shooting flag as the reference does (:165)."""
+    from .single_shooting import from_vec, to_vec
     ps = default_initialization(rng, shooting) if ps is None else ps
     st = shooting.initialstates(rng)
-    keys = list(ps.keys())
-    carry = ps[keys[0]]["u0"]
-    for i, k in enumerate(keys):
-        u0 = ps[k]["u0"] if (i + 1) in fixed_indices else carry
-        ps[k]["u0"][...] = np.asarray(u0)[: len(ps[k]["u0"])]
-        pred, _ = shooting.layer(None, ps[k], st[k])   # no shooting flag: fixval = problem.u0 (:165)
-        carry = pred.u[-1]
+    nat = shooting._native(st, ps)
+    new = from_vec(nat.forward_init(to_vec(ps)[None, :], fixed_indices)[0], ps)
+    for k in ps:   # in place, like the reference (sps.u0 .= ...)
+        ps[k]["u0"][...] = new[k]["u0"]
     return ps
+
+
+def forward_initialization_batch(shooting: MultipleShootingLayer, ps_batch, ps_like, st=None, fixed_indices=()):
+    """The batch axis the reference does not have: ps_batch is (B, nvars), one flat candidate per row; returns the
+    forward-initialised copy (only node values change)."""
+    st = shooting.initialstates(None) if st is None else st
+    return shooting._native(st, ps_like).forward_init(ps_batch, fixed_indices)
 
 
 def constant_initialization(rng, shooting: MultipleShootingLayer, ps=None, u0=None, **kw):

@@ -108,6 +108,8 @@ typedef struct {
 #define CB200_WANT_OBJ 0x010u       /* last(traj)[objective_row] per candidate */
 #define CB200_WANT_GRAD 0x020u      /* d objective / d ps */
 #define CB200_WANT_FIM 0x040u       /* F_init + symmetric F(t_end) per candidate, and its sum over candidates */
+#define CB200_WANT_CRIT 0x100u      /* the six OED criteria of Symmetric(F) per candidate (criteria.jl:33-63) */
+#define CB200_WANT_JAC 0x080u       /* values of d(shooting_constraints)/d(ps), cb200_jac_structure order (cons_j) */
 
 /* memory / layout flags */
 #define CB200_MEM_DEVICE 0x1u       /* ps and all outputs are device pointers (default: host pointers) */
@@ -127,6 +129,8 @@ typedef struct {
  *   objective      n = 1
  *   grad           n = nvars
  *   fim            n = fim_n*fim_n     column-major symmetric matrix
+ *   criteria       n = 6               A, D, E, FisherA, FisherD, FisherE of F = F_init + F(t_end)
+ *   jac_vals       n = jac_nnz         nonzeros of the constraint Jacobian, triplet order of cb200_jac_structure
  *   fim_sum        fim_n*fim_n doubles total: sum over the B candidates of `fim`
  *   objective_sum  1 double total: sum over the B candidates of `objective`   (expectation-type objectives;
  *   grad_sum       nvars doubles total: sum over the B candidates of `grad`    the per-rank partial sums that
@@ -147,6 +151,8 @@ typedef struct {
     const double *fim_init;     /* [fim_n*fim_n] st.F_init or NULL = zeros (oed.jl:309-315) */
     int32_t objective_row;      /* 1-based row of a trajectory sample: state k or nx + control r */
     int32_t reserved;
+    double *jac_vals;
+    double *criteria;
 } cb200_out;
 
 typedef struct {
@@ -180,6 +186,13 @@ int cb200_set_stream(cb200_handle *h, void *cuda_stream);
 int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t ldb, uint32_t want, uint32_t flags,
                const cb200_out *out);
 
+/* forward_initialization(rng, shooting; ps, fixed_indices) (src/node_initialization.jl:152-170) for B candidates at
+ * once: walks the intervals in order and overwrites each interval's node values ps.interval_i.u0 in place with the
+ * previous interval's end state; intervals listed in fixed_indices (1-based) keep their nodes.  flags: CB200_MEM_DEVICE
+ * and CB200_PS_SOA as for cb200_eval. */
+int cb200_forward_init(cb200_handle *h, double *ps, int64_t B, int64_t ldb, uint32_t flags,
+                       const int32_t *fixed_indices, int32_t n_fixed);
+
 /* Sparsity of d(shooting_constraints kind-major)/d(ps): nnz triplets (1-based row, col) and, per entry,
  * src >= 0: 0-based row into `sens`;  src == -1: constant +1;  src == -2: constant -1. */
 int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int64_t *src);
@@ -195,6 +208,8 @@ int64_t cb200_launch_count(const cb200_handle *h);
 
 /* FP64 FMA-chain peak probe: runs `iters` dependent DFMA chains on every SM, returns TFLOP/s (<0 on error) */
 double cb200_probe_fp64_tflops(int device, int iters);
+/* same through the FP64 tensor path (mma.sync.m8n8k4.f64); on B200 both share one datapath, the roof is the max */
+double cb200_probe_fp64_mma_tflops(int device, int iters);
 
 #ifdef __cplusplus
 }

@@ -70,6 +70,8 @@ struct Out                       # cb200_out
     fim_init::Ptr{Float64}
     objective_row::Int32
     reserved::Int32
+    jac_vals::Ptr{Float64}
+    criteria::Ptr{Float64}
 end
 
 struct Sizes                     # cb200_sizes
@@ -83,7 +85,7 @@ struct Sizes                     # cb200_sizes
 end
 
 const WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS = 0x001, 0x002, 0x004, 0x008
-const WANT_OBJ, WANT_GRAD, WANT_FIM = 0x010, 0x020, 0x040
+const WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT = 0x010, 0x020, 0x040, 0x080, 0x100
 
 const MODELS = Dict(:lotka3 => 0, :lqr => 1, :lotka2 => 2, :lotka2_oed => 3, :lin1d => 4, :lin1d_oed => 5,
                     :dense20 => 6, :egerstedt => 7)
@@ -196,17 +198,19 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     grad = alloc(WANT_GRAD, s.nvars)
     nf = e.fim[2]
     fim = alloc(WANT_FIM, nf * nf)
+    jac = alloc(WANT_JAC, s.jac_nnz)
+    crit = alloc(WANT_CRIT, 6)
     fsum = zeros(nf, nf)
     ptr(a) = isempty(a) ? Ptr{Float64}(C_NULL) : pointer(a)
-    GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init begin
+    GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init jac crit begin
         o = Out(ptr(xend), ptr(sens), ptr(traj), ptr(dk), ptr(ds), ptr(obj), ptr(grad), ptr(fim),
             (want & WANT_FIM) != 0 ? pointer(fsum) : Ptr{Float64}(C_NULL), C_NULL, C_NULL,
-            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0)
+            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit))
         check(ccall((:cb200_eval, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, UInt32, UInt32, Ref{Out}),
                 e.handle, P, B, size(P, 1), want, 0, o), "cb200_eval")
     end
-    return (; xend, sens, traj, defects_kind = dk, defects_stage = ds, objective = obj, grad, fim, fim_sum = fsum)
+    return (; xend, sens, traj, defects_kind = dk, defects_stage = ds, objective = obj, grad, fim, fim_sum = fsum, jac_vals = jac, criteria = crit)
 end
 
 # ---------------------------------------------------------------- drop-in: layer(nothing, ps, st) on the GPU
@@ -260,12 +264,12 @@ function jac_structure(e::EnsembleB200)
 end
 
 function b200_cons_j(e::EnsembleB200)
-    rows, cols, src = jac_structure(e)
-    return function (J, x, st)
-        S = vec(evaluate(e, reshape(collect(x), :, 1); want = WANT_SENS).sens)
+    rows, cols, _ = jac_structure(e)
+    return function (J, x, st)                          # rows of the shooting block follow the point constraints
+        vals = vec(evaluate(e, reshape(collect(x), :, 1); want = WANT_JAC).jac_vals)
         fill!(J, 0)
-        for k in eachindex(rows)                       # rows of the shooting block follow the point constraints
-            J[rows[k], cols[k]] += src[k] >= 0 ? S[src[k] + 1] : (src[k] == -1 ? 1.0 : -1.0)
+        for k in eachindex(rows)
+            J[rows[k], cols[k]] += vals[k]               # already assembled on the device (K5), triplet order
         end
         return J
     end

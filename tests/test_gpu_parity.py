@@ -38,7 +38,7 @@ def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
     assert N.nvars == O.nvars and N.n_defects == O.ndef and N.n_samples == O.nsamples and N.n_row == O.nrow
     assert np.array_equal(N.block_structure(), O.block_structure())
     ps = batch_ps(O, B, rng) if ps is None else ps
-    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_JAC
     if check_traj:
         want |= nat.WANT_TRAJ
     r = N.eval_host(ps, want, objective_row=objective_row)
@@ -68,6 +68,8 @@ def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
             vals = np.where(src >= 0, r["sens"][b][np.maximum(src, 0)], np.where(src == -1, 1.0, -1.0))
             np.add.at(J, (rows - 1, cols - 1), vals)
             errs["jac"] = max(errs.get("jac", 0.0), rel_err(J, Jd))
+            # the same values assembled on the device (K5, WANT_JAC): bit-identical to the gather from sens
+            assert np.array_equal(r["jac_vals"][b], vals), "device cons_j values differ from sens gather"
     return errs
 
 
@@ -207,3 +209,52 @@ def test_device_resident_soa_path():
     for k, v in outs.items():
         assert np.array_equal(v.cpu().numpy().T, ref[k]), k
     assert N.last_kernel_ms() > 0
+
+
+def test_forward_initialization_batch_vs_oracle():
+    """cb200_forward_init (device sweep over intervals) == oracle restatement of node_initialization.jl:152-170,
+    incl. fixed_indices; defects of a forward-initialised candidate vanish (test/core/multiple_shooting.jl:131-152)."""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(17)
+    for spec, K in ((P.lotka_spec(controls=rng.uniform(0, 1, 120), quadrature=True), 2),
+                    (P.lotka_spec(controls=rng.uniform(0, 1, 120)), 2),
+                    (P.lqr_spec(20, rng), 2)):
+        O = po.OracleLayer(spec)
+        lay = P.product_layer(spec, cb.Tsit5(K))
+        ps_t, st = cb.setup(None, lay)
+        N = lay._native(st, ps_t)
+        B = 7
+        ps = batch_ps(O, B, rng)
+        for fixed in ((), (3,)):
+            got = N.forward_init(ps, fixed)
+            for b in range(B):
+                ref = O.forward_init(ps[b], fixed, K=K)
+                assert rel_err(got[b], ref) <= RTOL
+            if not fixed:
+                r = N.eval_host(got, nat.WANT_DEFECTS)
+                nstate = sum(int(np.sum(st[k]["shooting_indices"] <= O.nx)) for k in list(st)[1:])
+                if not spec["quadrature_indices"]:
+                    assert np.max(np.abs(r["defects_kind"][:, :nstate])) <= 1e-12
+    # the reference-API entry point (one candidate) goes through the same kernel
+    lay = P.product_layer(P.lotka_spec(), cb.Tsit5(8), initialization=cb.forward_initialization)
+    ps_f = lay.initialparameters(None)
+    assert np.all(np.isfinite(cb.to_vec(ps_f)))
+
+
+def test_oed_criteria_batched():
+    """the six criteria of criteria.jl:33-63 per candidate on the device vs NumPy on the same FIM"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(23)
+    spec = P.lotka_oed_spec(shooting_points=[0.0, 3.0, 6.0, 9.0], fishing=rng.uniform(0, 1, 48))
+    lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2))
+    B = 65
+    ps = cb.to_vec(ps_t)[None, :] + 0.02 * rng.standard_normal((B, N.nvars))
+    Finit = np.array([[0.5, 0.1], [0.1, 0.4]])
+    crit, F = cb.batched_criteria(N, ps, fim_init=Finit)
+    host = [c() for c in (cb.ACriterion, cb.DCriterion, cb.ECriterion, cb.FisherACriterion, cb.FisherDCriterion,
+                          cb.FisherECriterion)]
+    for b in range(B):
+        ref = np.array([c(F[b]) for c in host])
+        assert np.allclose(crit[b], ref, rtol=1e-10, atol=0), (b, crit[b], ref)
