@@ -565,6 +565,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     }
     (void)sio;
     L.nvars = vo;
+    L.max_M = *std::max_element(h->h_M.begin(), h->h_M.end());
     h->n_sens = seo;
     h->n_samples = so + 1;
 
@@ -690,6 +691,9 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
                  o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos),
                  o_jc = push(blob, h->jac_const);
+    std::vector<double> mdata;
+    if (d->model_data && d->model_data_len > 0) mdata.assign(d->model_data, d->model_data + d->model_data_len);
+    const size_t o_md = push(blob, mdata);
     const size_t o_gr = (blob.size() + 15) & ~size_t(15);
     h->grad_cap = std::max(1, L.nvars);
     blob.resize(o_gr + sizeof(GradEntry) * (size_t)h->grad_cap);
@@ -752,6 +756,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.oth = (const MatchEntry *)(base + o_ot);
     L.jpos = (const int *)(base + o_jp);
     h->d_jac_const = (JacConst *)(base + o_jc);
+    L.model_data = mdata.empty() ? nullptr : (const double *)(base + o_md);
     h->d_defects = (DefectEntry *)(base + o_de);
     h->d_quad = (int *)(base + o_q);
     h->d_grad = (GradEntry *)(base + o_gr);

@@ -14,6 +14,7 @@ struct DevLayer {
     int nx, np_all, nact, ntp, I, K;
     int R;            // direction groups per unit = max_i ceil(ns_i / G); 1 when G == 0
     int nvars;
+    int max_M;               // largest number of pieces of an interval
     int flat;                // launch mapping: 1 = flat thread index (tiny batches), 0 = grid (b-tiles, i, r)
     int uniform_h;           // every piece of the layer has the same step size h = (t1 - t0)/K
     double hA[21];           // uniform_h: h * a_ij (Tsit5, slots as tsit5_coeffs) or the 4 RK4 factors
@@ -35,6 +36,7 @@ struct DevLayer {
     const double *ic_fix0;   // [I*nx] the same with fixval = problem.u0 on every interval (forward sweep)
     const long long *sens_off;  // [I] first row of the interval's block in `sens`
     const int *samp_off;     // [I] first merged-trajectory sample of the interval
+    const double *model_data;  // model constants in HBM (DENSE20: W row-major 20x20, then b[20]) or nullptr
     const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
     const unsigned *act_mask;     // [sum M][R] bit g: direction r*G+g is forced during the piece (G = handle's group size)
     // shooting defects of the boundary between interval i and i+1 (src/multiple_shooting.jl:150-163)

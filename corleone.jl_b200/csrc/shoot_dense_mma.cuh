@@ -1,0 +1,440 @@
+// K2-dense: shooting units of a dense 20-state model  x' = W x + phi(x) + b u  with the FULL sensitivity
+// Jacobian, on the FP64 tensor path (mma.sync.m8n8k4.f64).
+//
+// Here the sensitivity right-hand side is a real dense contraction:  d/dt [x S] = W [x S] + (elementwise terms),
+// the same 20x20 matrix W applied to all 1 + ns columns of every unit at every stage (north_star: "tensor cores
+// only if the Jacobian-matrix products become a real dense contraction at large state dimension").  On B200 DMMA
+// and DFMA share one FP64 datapath (tools/dmma_micro.cu), but DMMA reaches the nominal 64 FMA/clk/SM with 1/8 of
+// the issue slots and keeps W in 15 fragment registers per lane instead of constant-bank operands.
+//
+// Mapping.  A block owns CPB = 5 consecutive candidates of one interval: 125 columns [x | S_1..S_24] x 5 in
+// 16 warps (register files are allotted in units of 4 warps, so 16 is the size that wastes none):
+//   warp 0      (x tile): columns g = 0..4 = the states x of candidates b0 + g (columns 5..7 idle)
+//   warp w >= 1 (S tile): column c = 8(w-1) + g of the 120 sensitivity columns = direction c / 5 of candidate b0 + c % 5
+// A tile is the A operand (rows = columns of Y, k = state) of  D[col][i] = sum_j Y[j][col] W[i][j]; W^T is the B
+// operand.  Lane (g = lane/4, t = lane%4) owns the five states 5t..5t+4 of column g in every vector of the
+// integrator: as A fragment it supplies state 5t+kt in k-tile kt, and the state order of the three n-tiles is
+// permuted (n-slot 2t+e of tile nt <-> state 5t+2nt+e, the sixth slot is zero padding) so that the D fragments it
+// receives are exactly its own five states.  No shuffle, no shared-memory transpose: the stage derivative lands
+// in the registers of the lane that needs it.  The only exchange is x -> S tiles (the -3 x^2 S term): the x tile
+// publishes its stage input in shared memory (100 doubles, double-buffered), one __syncthreads per stage.  Loads and
+// stores of a warp touch 5 consecutive candidates per row.
+//
+// Reference semantics as in shoot.cuh (pieces, FSAL restart per piece, accumulator-form Tsit5, fused K3/K5 epilogue).
+#pragma once
+#include "common.cuh"
+#include "tableau.cuh"
+#include <algorithm>
+#include <cstdlib>
+
+namespace cb200 {
+
+constexpr int DM_NX = 20;        // states
+constexpr int DM_CPB = 5;        // candidates per block
+constexpr int DM_SW = 15;        // S-tile warps: 15 * 8 = 24 * 5 columns per round
+constexpr int DM_DPR = 24;       // directions per round
+constexpr int DM_WARPS = DM_SW + 1;
+constexpr int DM_THREADS = DM_WARPS * 32;
+
+__device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};\n"
+                 : "+d"(c0), "+d"(c1)
+                 : "d"(a), "d"(b));
+}
+
+struct DenseTile {
+    double Wf[15];   // B fragments of W^T: [kt*3 + nt]
+    bool is_x;       // x tile (warp 0)
+    bool on;         // tile has at least one live column
+    bool col_on;     // this lane's column is live
+    int cand;        // candidate slot 0..CPB-1 of this lane's column
+    int t;           // lane % 4
+};
+
+// k = W y + elementwise(y; x) for the lane's five states.  sx: [2][CPB][20] stage inputs of the x columns.
+// Every warp of the block calls this the same number of times (one __syncthreads inside).
+// The x tile publishes c = -3 x^2 (what the S tiles need) into `slot` ([CPB][20]).  PIPE = false: x and S tiles of the same unit
+// run in lockstep, one __syncthreads per call.  PIPE = true: the x tile ran ahead, `slot` already holds its value.
+template <bool PIPE, bool IS_X>
+__device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, const double *binit, double *k, double *slot)
+{
+    double q[5];
+    if constexpr (IS_X) {
+#pragma unroll
+        for (int s = 0; s < 5; s++) q[s] = y[s] * y[s];
+        if (T.col_on) {
+#pragma unroll
+            for (int s = 0; s < 5; s++) slot[T.cand * DM_NX + 5 * T.t + s] = -3.0 * q[s];
+        }
+    }
+    // the accumulators start from the b-term of the piece: b u for the states, b for the running piece's control
+    // direction, 0 otherwise -- it costs no instruction
+    double d[6] = {binit[0], binit[1], binit[2], binit[3], binit[4], 0.0};
+    if (T.on) {
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++) {
+            dmma884(d[0], d[1], y[kt], T.Wf[kt * 3 + 0]);
+            dmma884(d[2], d[3], y[kt], T.Wf[kt * 3 + 1]);
+            dmma884(d[4], d[5], y[kt], T.Wf[kt * 3 + 2]);
+        }
+    }
+    if constexpr (!PIPE) __syncthreads();
+    if (T.on) {
+        if constexpr (IS_X) {  // f(x) = W x - x^3 + b u
+#pragma unroll
+            for (int s = 0; s < 5; s++) k[s] = fma(-q[s], y[s], d[s]);
+        } else {               // f_x v + f_u = W v - 3 x^2 v (+ b)
+#pragma unroll
+            for (int s = 0; s < 5; s++) k[s] = fma(slot[T.cand * DM_NX + 5 * T.t + s], y[s], d[s]);
+        }
+    }
+}
+
+// slot of the next right-hand-side call: two alternating slots (lockstep) or one slot per call of the item (pipelined)
+#define DM_RHS(y)                                                                 \
+    do {                                                                          \
+        dense_rhs<PIPE, IS_X>(T, y, binit, k, xc + slot_idx * (DM_CPB * DM_NX)); \
+        slot_idx = PIPE ? slot_idx + 1 : (slot_idx ^ 1);                          \
+    } while (0)
+
+// One unit group (CPB candidates of interval i, direction round `round`) for the calling warp's tile.
+// xc: stage-exchange slots in shared memory.
+template <int METHOD, bool UNI, bool PIPE, bool IS_X>
+__device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__restrict__ ps, long long ldb, long long B,
+                                           const ShootOut &o, int i, int round, long long b0, double *xc)
+{
+    constexpr int NX = DM_NX, NCF = METHOD == 0 ? 21 : 4;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+
+    const int nu0 = __ldg(L.n_u0 + i), nc = __ldg(L.n_c + i);
+    const int ns = nu0 + L.ntp + nc;
+    if (round > 0 && round * DM_DPR >= ns) return;   // uniform over the block
+
+    DenseTile T;
+    T.is_x = IS_X;
+    T.t = t;
+    const int col = 8 * (warp - 1) + g;                                      // S tiles: column among the 120 of this round
+    T.cand = IS_X ? (g < DM_CPB ? g : 0) : col % DM_CPB;
+    const int dir = round * DM_DPR + col / DM_CPB;                     // S tiles: direction of this lane's column
+    long long b = b0 + T.cand;
+    const bool cand_live = b < B;
+    if (!cand_live) b = B - 1;
+    T.col_on = IS_X ? (g < DM_CPB) : (dir < ns);
+    T.on = IS_X ? true : (round * DM_DPR + (8 * (warp - 1)) / DM_CPB < ns);   // warp-uniform: the tile's first column is live
+    const bool store = T.col_on && cand_live;
+
+    // W^T fragments in the permuted state order (see header) and the lane's slice of b
+    {
+        const double *W = L.model_data;   // row-major 20x20, then b[20]
+#pragma unroll
+        for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+            for (int nt = 0; nt < 3; nt++) {
+                // B[k = t][n = g]: k-state 5t + kt; n-slot g = 2 tau + e -> state 5 tau + 2 nt + e (nt = 2, e = 1: padding)
+                const int tau = g >> 1, e = g & 1;
+                const int sn = 5 * tau + 2 * nt + e;
+                T.Wf[kt * 3 + nt] = (nt == 2 && e == 1) ? 0.0 : __ldg(W + sn * NX + (5 * t + kt));
+            }
+    }
+
+    const int voff = __ldg(L.var_off + i);
+    const double *__restrict__ v = ps + (long long)voff * ldb + b;
+    // ---- initial values of the lane's five entries
+    double yd[5];
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int k = 5 * t + s;
+        const int src = __ldg(L.ic_src + i * NX + k);
+        if (IS_X)
+            yd[s] = (src >= 0) ? v[(long long)src * ldb] : __ldg(L.ic_fix + i * NX + k);
+        else
+            yd[s] = (T.col_on && src >= 0 && src == dir) ? 1.0 : 0.0;
+    }
+    if (!T.col_on) {
+#pragma unroll
+        for (int s = 0; s < 5; s++) yd[s] = 0.0;
+    }
+    const int cdir = dir - nu0 - L.ntp;   // local control index this column differentiates with respect to (< 0: a u0 direction)
+    const int M = __ldg(L.M + i), po = __ldg(L.piece_off + i), so = __ldg(L.samp_off + i);
+    const int nrow = NX + L.nact;
+    const bool last_interval = (i == L.I - 1);
+    const double *__restrict__ vc = v + (long long)(nu0 + L.ntp) * ldb;
+    int slot_idx = 0;
+
+    int ci_nx = __ldg(L.cidx + (long long)po * L.nact);
+    double u_nx = vc[(long long)ci_nx * ldb];
+    for (int j = 0; j < M; j++) {
+        const int ci = ci_nx;
+        const double u = u_nx;
+        if (j + 1 < M) {
+            ci_nx = __ldg(L.cidx + (long long)(po + j + 1) * L.nact);
+            u_nx = vc[(long long)ci_nx * ldb];
+        }
+        double binit[5];   // b-term of this piece for the lane's states
+        {
+            const double w = IS_X ? u : ((T.col_on && cdir == ci) ? 1.0 : 0.0);
+#pragma unroll
+            for (int s = 0; s < 5; s++) binit[s] = w * __ldg(L.model_data + NX * NX + 5 * t + s);
+        }
+        if (o.traj && IS_X && store && round == 0 && j == 0) {  // save_start = (j == 1)
+            double *tr = o.traj + ((long long)so * nrow) * o.ldo + b;
+#pragma unroll
+            for (int s = 0; s < 5; s++) tr[(long long)(5 * t + s) * o.ldo] = yd[s];
+            if (t == 0) tr[(long long)NX * o.ldo] = u;
+        }
+        double cf[NCF];
+        if constexpr (UNI) {
+#pragma unroll
+            for (int c = 0; c < NCF; c++) cf[c] = L.hA[c];
+        } else {
+            const double h = __ldg(L.ph + po + j);
+            if constexpr (METHOD == 0)
+                tsit5_coeffs(h, cf);
+            else
+                rk4_coeffs(h, cf);
+        }
+        double k[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        if constexpr (METHOD == 0) {   // accumulator-form Tsit5 (shoot.cuh), five components per lane
+            double s2[5], s3[5], s4[5], s5[5], s6[5];
+            DM_RHS(yd);
+            for (int st = 0; st < L.K; st++) {
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    s2[c] = fma(cf[0], k[c], yd[c]);
+                    s3[c] = fma(cf[1], k[c], yd[c]);
+                    s4[c] = fma(cf[3], k[c], yd[c]);
+                    s5[c] = fma(cf[6], k[c], yd[c]);
+                    s6[c] = fma(cf[10], k[c], yd[c]);
+                    yd[c] = fma(cf[15], k[c], yd[c]);
+                }
+                DM_RHS(s2);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    s3[c] = fma(cf[2], k[c], s3[c]);
+                    s4[c] = fma(cf[4], k[c], s4[c]);
+                    s5[c] = fma(cf[7], k[c], s5[c]);
+                    s6[c] = fma(cf[11], k[c], s6[c]);
+                    yd[c] = fma(cf[16], k[c], yd[c]);
+                }
+                DM_RHS(s3);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    s4[c] = fma(cf[5], k[c], s4[c]);
+                    s5[c] = fma(cf[8], k[c], s5[c]);
+                    s6[c] = fma(cf[12], k[c], s6[c]);
+                    yd[c] = fma(cf[17], k[c], yd[c]);
+                }
+                DM_RHS(s4);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    s5[c] = fma(cf[9], k[c], s5[c]);
+                    s6[c] = fma(cf[13], k[c], s6[c]);
+                    yd[c] = fma(cf[18], k[c], yd[c]);
+                }
+                DM_RHS(s5);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    s6[c] = fma(cf[14], k[c], s6[c]);
+                    yd[c] = fma(cf[19], k[c], yd[c]);
+                }
+                DM_RHS(s6);
+#pragma unroll
+                for (int c = 0; c < 5; c++) yd[c] = fma(cf[20], k[c], yd[c]);
+                if (st + 1 < L.K) DM_RHS(yd);   // FSAL
+            }
+        } else {   // classical RK4
+            double acc[5], td[5];
+            for (int st = 0; st < L.K; st++) {
+                DM_RHS(yd);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    acc[c] = fma(cf[2], k[c], yd[c]);
+                    td[c] = fma(cf[0], k[c], yd[c]);
+                }
+                DM_RHS(td);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    acc[c] = fma(cf[3], k[c], acc[c]);
+                    td[c] = fma(cf[0], k[c], yd[c]);
+                }
+                DM_RHS(td);
+#pragma unroll
+                for (int c = 0; c < 5; c++) {
+                    acc[c] = fma(cf[3], k[c], acc[c]);
+                    td[c] = fma(cf[1], k[c], yd[c]);
+                }
+                DM_RHS(td);
+#pragma unroll
+                for (int c = 0; c < 5; c++) yd[c] = fma(cf[2], k[c], acc[c]);
+            }
+        }
+        // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
+        if (o.traj && IS_X && store && round == 0 && (j + 1 < M || last_interval)) {
+            double *tr = o.traj + ((long long)(so + j + 1) * nrow) * o.ldo + b;
+#pragma unroll
+            for (int s = 0; s < 5; s++) tr[(long long)(5 * t + s) * o.ldo] = yd[s];
+            if (t == 0) tr[(long long)NX * o.ldo] = u;
+        }
+    }
+
+    // ---- results (fused K3 / K5 epilogue, as in shoot.cuh)
+    if (!store) return;
+    if constexpr (IS_X) {
+        if (round != 0) return;
+#pragma unroll
+        for (int s = 0; s < 5; s++) {
+            const int k = 5 * t + s;
+            if (o.xend) o.xend[((long long)i * NX + k) * o.ldo + b] = yd[s];
+            if (o.objq && k == o.obj_state) o.objq[(long long)i * o.ldo + b] = yd[s];
+        }
+        if ((o.dk || o.dst) && i + 1 < L.I) {
+            const int vn = __ldg(L.var_off + i + 1);
+#pragma unroll
+            for (int s = 0; s < 5; s++) {
+                const int k = 5 * t + s;
+                const int pk = __ldg(L.dpos_kind + i * NX + k);
+                if (pk >= 0) {
+                    const int src = __ldg(L.ic_src + (i + 1) * NX + k);
+                    const double nxt = (src >= 0) ? ps[(long long)(vn + src) * ldb + b] : __ldg(L.ic_fix + (i + 1) * NX + k);
+                    const double dd = yd[s] - nxt;
+                    if (o.dk) o.dk[(long long)pk * o.ldo + b] = dd;
+                    if (o.dst) o.dst[(long long)__ldg(L.dpos_stage + i * NX + k) * o.ldo + b] = dd;
+                }
+            }
+            if (t == 0) {  // parameter and control matchings: one lane per candidate
+                const int e1 = __ldg(L.oth_off + i + 1);
+                for (int e = __ldg(L.oth_off + i); e < e1; e++) {
+                    const MatchEntry m = L.oth[e];
+                    const double dd = ps[(long long)m.a * ldb + b] - ps[(long long)m.b * ldb + b];
+                    if (o.dk) o.dk[(long long)m.pos_kind * o.ldo + b] = dd;
+                    if (o.dst) o.dst[(long long)m.pos_stage * o.ldo + b] = dd;
+                }
+            }
+        }
+        return;
+    }
+    const long long s0 = __ldg(L.sens_off + i);
+    const bool inc = o.obj_all || i == L.I - 1;
+#pragma unroll
+    for (int s = 0; s < 5; s++) {
+        const int k = 5 * t + s;
+        if (o.sens) o.sens[(s0 + (long long)dir * NX + k) * o.ldo + b] = yd[s];
+        if (o.jac && i + 1 < L.I) {
+            const int jp = __ldg(L.jpos + i * NX + k);
+            if (jp >= 0) o.jac[(long long)(jp + dir) * o.ldo + b] = yd[s];
+        }
+        if (k == o.obj_state) {
+            const double val = inc ? yd[s] : 0.0;
+            if (o.grad) o.grad[(long long)(voff + dir) * o.ldo + b] = val;
+            if (o.grad_sum) atomicAdd(o.grad_sum + voff + dir, val);
+        }
+    }
+}
+
+#undef DM_RHS
+
+// Lockstep kernel: one block per unit group, x and S tiles exchange through two alternating slots.
+template <int METHOD, bool UNI>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
+                       const ShootOut o)
+{
+    __shared__ double sx[2 * DM_CPB * DM_NX];
+    if ((threadIdx.x >> 5) == 0)   // both branches meet at the same barrier (id 0), once per right-hand-side call
+        dense_unit<METHOD, UNI, false, true>(L, ps, ldb, B, o, blockIdx.y, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
+    else
+        dense_unit<METHOD, UNI, false, false>(L, ps, ldb, B, o, blockIdx.y, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
+}
+
+__device__ __forceinline__ void dm_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
+__device__ __forceinline__ void dm_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
+
+// Pipelined persistent kernel: one block per SM walks the unit groups; the x tile (warp 0) integrates the states
+// of group n+1 -- they do not depend on the sensitivities -- and leaves -3 x^2 of every stage in one of two
+// shared-memory item buffers while the 15 S tiles integrate group n from the other buffer WITHOUT any barrier
+// between stages: the S warps drift apart and the DMMA phases of some overlap the DFMA phases of others.
+// Hand-over per item: named barriers FULL[buf] (x arrives, S wait) and EMPTY[buf] (S arrive, x waits).
+template <int METHOD, bool UNI>
+__global__ void __launch_bounds__(DM_THREADS, 1)
+shoot_dense_mma_pipe_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
+                            const ShootOut o, long long n_items, int n_groups_lo, int rounds, int nst)
+{
+    extern __shared__ double xcbuf[];   // [2][nst][CPB][20]
+    const bool is_x = (threadIdx.x >> 5) == 0;   // the oldest warp: schedulers that favour older warps keep it ahead
+    const long long per = (long long)nst * DM_CPB * DM_NX;
+    long long kcount = 0;
+    for (long long n = blockIdx.x; n < n_items; n += gridDim.x, kcount++) {
+        const int buf = (int)(kcount & 1);
+        // item -> (group, interval, round); intervals fastest so that a block's consecutive items share nothing but W
+        const int i = (int)(n % L.I);
+        const long long rest = n / L.I;
+        const int round = (int)(rest % rounds);
+        const long long grp = rest / rounds;
+        double *xc = xcbuf + buf * per;
+        if (is_x) {
+            if (kcount >= 2) dm_bar_sync(1 + 2 + buf);    // EMPTY[buf]: the S tiles are done with item kcount - 2
+            dense_unit<METHOD, UNI, true, true>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc);
+            __threadfence_block();
+            dm_bar_arrive(1 + buf);                        // FULL[buf]
+        } else {
+            dm_bar_sync(1 + buf);                          // FULL[buf]
+            dense_unit<METHOD, UNI, true, false>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc);
+            dm_bar_arrive(1 + 2 + buf);                    // EMPTY[buf]
+        }
+    }
+    if (is_x) {   // consume the EMPTY signals of the last two items so that no barrier is left half-arrived
+        for (long long kk = kcount >= 2 ? kcount - 2 : 0; kk < kcount; kk++) dm_bar_sync(1 + 2 + (int)(kk & 1));
+    }
+    (void)n_groups_lo;
+}
+
+// returns cudaError_t as int; -1000 if the layer does not fit this kernel (the caller falls back to shoot_kernel)
+inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, long long ldb, long long B, const ShootOut &o,
+                            int max_ns, int max_pieces, cudaStream_t s)
+{
+    if (L.nact != 1 || L.ntp != 0 || L.nx != DM_NX || !L.model_data) return -1000;
+    if (B <= 0) return 0;
+    const long long gx = (B + DM_CPB - 1) / DM_CPB;
+    int rounds = (max_ns + DM_DPR - 1) / DM_DPR;
+    if (rounds < 1) rounds = 1;
+    // right-hand-side calls per interval: Tsit5 6K per piece (FSAL after the last step skipped), RK4 4K
+    const int nst = max_pieces * (method == 0 ? 6 : 4) * L.K;
+    const size_t smem = sizeof(double) * 2 * (size_t)nst * DM_CPB * DM_NX;
+    static const bool lockstep = getenv("CB200_DENSE20_LOCKSTEP") != nullptr;
+    if (!lockstep && smem <= 200 * 1024) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const long long n_items = gx * L.I * rounds;
+        const unsigned grid = (unsigned)std::min<long long>(n_items, sms);
+        auto go = [&](auto kern) {
+            cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            kern<<<grid, DM_THREADS, smem, s>>>(L, ps, ldb, B, o, n_items, 0, rounds, nst);
+        };
+        if (method == 0) {
+            if (L.uniform_h) go(shoot_dense_mma_pipe_kernel<0, true>);
+            else go(shoot_dense_mma_pipe_kernel<0, false>);
+        } else {
+            if (L.uniform_h) go(shoot_dense_mma_pipe_kernel<1, true>);
+            else go(shoot_dense_mma_pipe_kernel<1, false>);
+        }
+        return (int)cudaGetLastError();
+    }
+    if (gx > 2147483647LL || L.I > 65535 || rounds > 65535) return -1000;
+    dim3 grid((unsigned)gx, (unsigned)L.I, (unsigned)rounds);
+    if (method == 0) {
+        if (L.uniform_h)
+            shoot_dense_mma_kernel<0, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+        else
+            shoot_dense_mma_kernel<0, false><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+    } else {
+        if (L.uniform_h)
+            shoot_dense_mma_kernel<1, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+        else
+            shoot_dense_mma_kernel<1, false><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+    }
+    return (int)cudaGetLastError();
+}
+
+}  // namespace cb200

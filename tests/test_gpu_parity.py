@@ -258,3 +258,46 @@ def test_oed_criteria_batched():
     for b in range(B):
         ref = np.array([c(F[b]) for c in host])
         assert np.allclose(crit[b], ref, rtol=1e-10, atol=0), (b, crit[b], ref)
+
+
+@pytest.mark.parametrize("method", ["tsit5", "rk4"])
+def test_dense20_tensor_path_many_groups(method):
+    """dense 20-state model on the FP64 tensor-path kernel with more unit groups than SMs (several items per
+    persistent block, both shared-memory item buffers reused) and a batch that is not a multiple of the group size"""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(20261019 + 44)
+    spec = P.dense20_spec(8, rng)
+    alg = cb.Tsit5(2) if method == "tsit5" else cb.RK4(2)
+    O = po.OracleLayer(spec)
+    lay = P.product_layer(spec, alg)
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    B = 203
+    ps = batch_ps(O, B, rng, 0.1)
+    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_JAC | nat.WANT_TRAJ
+    r = N.eval_host(ps, want, objective_row=1, with_sums=True)
+    assert rel_err(r["grad_sum"], r["grad"].sum(axis=0)) <= 1e-12
+    rows, cols, src = N.jac_structure()
+    blocks = O.block_structure()
+    nx, I = O.nx, O.I
+    for b in (0, 4, 5, 101, 199, 202):
+        o = O.eval(ps[b], method=method, K=2)
+        assert rel_err(r["xend"][b].reshape(I, nx).T, o["xend"]) <= RTOL
+        assert rel_err(r["defects_kind"][b], o["defk"]) <= RTOL
+        assert rel_err(r["defects_stage"][b], o["defs"]) <= RTOL
+        assert rel_err(r["traj"][b].reshape(O.nsamples, O.nrow).T, o["u"]) <= RTOL
+        assert rel_err(r["objective"][b], o["last"][0]) <= RTOL
+    for b in (5, 202):
+        Jx, Jd, Jl = O.jacobians(ps[b], method=method, K=2)
+        off = 0
+        for i in range(I):
+            ns = blocks[i + 1] - blocks[i]
+            S = r["sens"][b][off:off + nx * ns].reshape(ns, nx).T
+            assert rel_err(S, Jx[nx * i:nx * (i + 1), blocks[i]:blocks[i + 1]]) <= RTOL
+            off += nx * ns
+        assert rel_err(r["grad"][b], Jl[0]) <= RTOL
+        J = np.zeros((O.ndef, O.nvars))
+        np.add.at(J, (rows - 1, cols - 1), r["jac_vals"][b])
+        assert rel_err(J, Jd) <= RTOL
