@@ -7,8 +7,9 @@
 Workload (N=1): BASELINE.json configs[1] = `lqr_ms100_b4096`: linear-quadratic regulator, 100 shooting
 intervals x 4096 candidates, Tsit5 with 2 fixed steps per control piece (M = 4 pieces per interval), full
 forward sensitivities (ns = 8 directions per interval).  One unit = one (interval, candidate) system.
-A step = one pass of the hot path over the batch: integration + sensitivities of every unit, shooting
-defects (both orderings), objective and objective gradient.  Weak scaling: every rank owns B candidates;
+A step = one pass of the hot path over the batch: integration + sensitivities of every unit, delivered as what
+the reference's NLP callbacks consume (src/dynprob.jl:68-73,105-131,143-164): objective f, gradient grad f,
+shooting constraints c (kind-major, the order dynprob uses) and the nonzeros of the constraint Jacobian cons_j.  Weak scaling: every rank owns B candidates;
 only the cross-candidate sums (objective, gradient) are all-reduced (DESIGN.md "multi-GPU").
 """
 import argparse
@@ -34,7 +35,7 @@ OBJECTIVE_ROW = 2   # x2 = accumulated cost (examples/linear_quadratic/main.jl:4
 E_EVALS = M_PIECES * (6 * K_STEPS_PER_PIECE + 1)
 NZ = NX * (1 + NS_DIRS)
 FLOPS_PER_UNIT = E_EVALS * (10 + 36) + M_PIECES * K_STEPS_PER_PIECE * 42 * NZ      # 8440
-#   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic
+#   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic (BASELINE.md formula)
 BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                                # 240
 
 
@@ -234,7 +235,7 @@ def main():
 
     # ---- device-resident arm: rotate over buffer sets whose total footprint exceeds L2 (126 MB)
     sz = N.out_sizes()
-    fields = ("sens", "defects_kind", "defects_stage", "objective", "grad")
+    fields = ("jac_vals", "defects_kind", "objective", "grad")   # cons_j, c, f, grad f
     set_bytes = 8 * B * (nvars + sum(sz[f] for f in fields))
     nsets = max(2, int(np.ceil(3 * 126e6 / set_bytes)))
     d_ps, d_out, d_sums = [], [], []
@@ -242,7 +243,7 @@ def main():
         d_ps.append(torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev))   # [nvars, B] SoA
         d_out.append({f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields})
         d_sums.append(torch.zeros(nvars + 1, dtype=torch.float64, device=dev))
-    want = nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
     flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
 
     def step(s, comm=True):
@@ -319,12 +320,17 @@ def main():
     pin_out = {f: torch.empty((B, sz[f]), dtype=torch.float64).pin_memory() for f in fields}
     pinned = {f: v.numpy() for f, v in pin_out.items()}
     ps_np = pin_ps.numpy()
+    host_ptrs = {f: pinned[f].ctypes.data for f in fields}
+
+    def host_eval():   # cb200_eval on host pointers: returns when the results are in the caller's buffers
+        N.eval_raw(ps_np.ctypes.data, B, nvars, want, 0, host_ptrs, OBJECTIVE_ROW)
+
     for _ in range(3):
-        N.eval_host(ps_np, want, OBJECTIVE_ROW, pinned_out=pinned)
+        host_eval()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        N.eval_host(ps_np, want, OBJECTIVE_ROW, pinned_out=pinned)
+        host_eval()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)

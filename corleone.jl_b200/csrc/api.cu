@@ -48,11 +48,6 @@ struct DefectEntry {
     int pos_stage;  // position in stage_ordered_shooting_constraints
 };
 
-struct JacConst {   // jac[slot] = value (the matching conditions' constant +-1 entries)
-    int slot;
-    double value;
-};
-
 struct GradEntry {   // grad[var] = sens[src] (src >= 0) or 1.0 (src == -1)
     int var;
     long long src;
@@ -106,14 +101,6 @@ __global__ void grad_kernel(const GradEntry *__restrict__ tab, int n, const doub
             if ((threadIdx.x & 31) == 0) atomicAdd(grad_sum + t.var, v);
         }
     }
-}
-
-// K5: the constant +-1 entries of cons_j (state / parameter / control matchings w.r.t. the next interval's variables)
-__global__ void jac_const_kernel(const JacConst *__restrict__ tab, int n, long long B, double *__restrict__ jac, long long ldo)
-{
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    if (b >= B) return;
-    for (int e = blockIdx.y; e < n; e += gridDim.y) jac[(long long)tab[e].slot * ldo + b] = tab[e].value;
 }
 
 // quadrature accumulation on the merged trajectory (src/multiple_shooting.jl:171-177)
@@ -308,8 +295,7 @@ struct cb200_handle {
     std::vector<int> h_cidx, h_ic_src;
     std::vector<DefectEntry> defects;
     std::vector<int> dpos_kind, dpos_stage, oth_off, jpos;
-    std::vector<JacConst> jac_const;   // the +-1 entries of cons_j
-    JacConst *d_jac_const = nullptr;
+    long long jac_nnz_var = 0;         // leading entries of the triplet list whose values come from sens
     std::vector<MatchEntry> oth;
     std::vector<long long> jac_rows, jac_cols, jac_src;
     long long n_sens = 0;
@@ -679,8 +665,27 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         for (int i = std::max(I, 1); i <= I; i++) h->oth_off[i] = (int)h->oth.size();
     }
 
-    for (size_t k = 0; k < h->jac_src.size(); k++)
-        if (h->jac_src[k] < 0) h->jac_const.push_back(JacConst{(int)k, h->jac_src[k] == -1 ? 1.0 : -1.0});
+    // triplet order: the sensitivity-valued entries first (their values are what cb200_eval delivers as jac_vals,
+    // the kernel writes them straight to their slot), then the constant +-1 entries of the matching conditions
+    {
+        const size_t nnz = h->jac_src.size();
+        std::vector<long long> newpos(nnz), r2, c2, s2;
+        size_t nv = 0;
+        for (size_t k = 0; k < nnz; k++)
+            if (h->jac_src[k] >= 0) newpos[k] = (long long)nv++;
+        h->jac_nnz_var = (long long)nv;
+        for (size_t k = 0; k < nnz; k++)
+            if (h->jac_src[k] < 0) newpos[k] = (long long)nv++;
+        r2.resize(nnz); c2.resize(nnz); s2.resize(nnz);
+        for (size_t k = 0; k < nnz; k++) {
+            r2[newpos[k]] = h->jac_rows[k];
+            c2[newpos[k]] = h->jac_cols[k];
+            s2[newpos[k]] = h->jac_src[k];
+        }
+        for (int &jp : h->jpos)
+            if (jp >= 0) jp = (int)newpos[jp];   // a state's ns entries stay contiguous: only constants moved out
+        h->jac_rows.swap(r2); h->jac_cols.swap(c2); h->jac_src.swap(s2);
+    }
     // upload
     std::vector<char> blob;
     const size_t o_M = push(blob, h->h_M), o_po = push(blob, h->h_piece_off), o_t0 = push(blob, pt0),
@@ -689,8 +694,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
                  o_de = push(blob, h->defects), o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol),
                  o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
-                 o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos),
-                 o_jc = push(blob, h->jac_const);
+                 o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos);
     std::vector<double> mdata;
     if (d->model_data && d->model_data_len > 0) mdata.assign(d->model_data, d->model_data + d->model_data_len);
     const size_t o_md = push(blob, mdata);
@@ -755,7 +759,6 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.oth_off = (const int *)(base + o_oo);
     L.oth = (const MatchEntry *)(base + o_ot);
     L.jpos = (const int *)(base + o_jp);
-    h->d_jac_const = (JacConst *)(base + o_jc);
     L.model_data = mdata.empty() ? nullptr : (const double *)(base + o_md);
     h->d_defects = (DefectEntry *)(base + o_de);
     h->d_quad = (int *)(base + o_q);
@@ -826,6 +829,7 @@ extern "C" int cb200_get_sizes(const cb200_handle *h, cb200_sizes *s)
     s->n_sens = h->n_sens;
     s->n_units = h->L.I;
     s->jac_nnz = (int64_t)h->jac_rows.size();
+    s->jac_nnz_var = (int64_t)h->jac_nnz_var;
     return CB200_OK;
 }
 
@@ -966,11 +970,6 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
         grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
         h->launches++;
     }
-    if (pl.jac && !h->jac_const.empty()) {
-        const int nc = (int)h->jac_const.size();
-        jac_const_kernel<<<dim3(nblk(B, 128), (unsigned)std::min(nc, 4096)), 128, 0, st>>>(h->d_jac_const, nc, B, d.jac, B);
-        h->launches++;
-    }
     if (pl.traj && h->nquad > 0 && I > 1) {
         traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, d.xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
                                                      h->d_quad, h->nquad);
@@ -1052,7 +1051,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         {pl.grad, nvars, &h->ws_grad, out->grad, &DevSet::grad},
         {pl.fim, n2, &h->ws_fim, out->fim, &DevSet::fim},
         {need_objq, I, &h->ws_objq, nullptr, &DevSet::objq},
-        {pl.jac, (long long)h->jac_rows.size(), &h->ws_jac, out->jac_vals, &DevSet::jac},
+        {pl.jac, h->jac_nnz_var, &h->ws_jac, out->jac_vals, &DevSet::jac},
         {pl.crit, 6, &h->ws_crit, out->criteria, &DevSet::crit},
     };
 

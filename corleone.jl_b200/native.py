@@ -55,7 +55,7 @@ class Out(C.Structure):
 
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
-                ("nvars", "n_defects", "n_samples", "n_row", "n_sens", "n_units", "jac_nnz")]
+                ("nvars", "n_defects", "n_samples", "n_row", "n_sens", "n_units", "jac_nnz", "jac_nnz_var")]
 
 
 class NativeError(RuntimeError):
@@ -152,7 +152,7 @@ class NativeLayer:
         self.sizes = s
         self.nx, self.I, self.nvars = nx, len(intervals), int(s.nvars)
         self.n_defects, self.n_samples, self.n_row = int(s.n_defects), int(s.n_samples), int(s.n_row)
-        self.n_sens, self.jac_nnz = int(s.n_sens), int(s.jac_nnz)
+        self.n_sens, self.jac_nnz, self.jac_nnz_var = int(s.n_sens), int(s.jac_nnz), int(s.jac_nnz_var)
         self.fim_n = fim_n
         self.device = device
 
@@ -208,7 +208,7 @@ class NativeLayer:
     def out_sizes(self):
         return dict(xend=self.nx * self.I, sens=self.n_sens, traj=self.n_row * self.n_samples,
                     defects_kind=self.n_defects, defects_stage=self.n_defects, objective=1, grad=self.nvars,
-                    fim=self.fim_n * self.fim_n, jac_vals=self.jac_nnz, criteria=6)
+                    fim=self.fim_n * self.fim_n, jac_vals=self.jac_nnz_var, criteria=6)
 
     def eval_raw(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1):
         """Raw pointer call (host or device pointers as `flags` says). ptrs: field name -> int address."""

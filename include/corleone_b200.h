@@ -130,7 +130,8 @@ typedef struct {
  *   grad           n = nvars
  *   fim            n = fim_n*fim_n     column-major symmetric matrix
  *   criteria       n = 6               A, D, E, FisherA, FisherD, FisherE of F = F_init + F(t_end)
- *   jac_vals       n = jac_nnz         nonzeros of the constraint Jacobian, triplet order of cb200_jac_structure
+ *   jac_vals       n = jac_nnz_var     sensitivity-valued nonzeros of the constraint Jacobian = the leading
+ *                                       triplets of cb200_jac_structure (the constant +-1 entries follow them)
  *   fim_sum        fim_n*fim_n doubles total: sum over the B candidates of `fim`
  *   objective_sum  1 double total: sum over the B candidates of `objective`   (expectation-type objectives;
  *   grad_sum       nvars doubles total: sum over the B candidates of `grad`    the per-rank partial sums that
@@ -163,6 +164,7 @@ typedef struct {
     int64_t n_sens;         /* sum_i nx * ns_i */
     int64_t n_units;        /* I: (interval) units per candidate */
     int64_t jac_nnz;        /* nonzeros of d(shooting_constraints)/d(ps) */
+    int64_t jac_nnz_var;    /* the leading jac_nnz_var triplets carry sensitivity values (jac_vals); the rest are +-1 */
 } cb200_sizes;
 
 typedef struct cb200_handle cb200_handle;
@@ -194,7 +196,8 @@ int cb200_forward_init(cb200_handle *h, double *ps, int64_t B, int64_t ldb, uint
                        const int32_t *fixed_indices, int32_t n_fixed);
 
 /* Sparsity of d(shooting_constraints kind-major)/d(ps): nnz triplets (1-based row, col) and, per entry,
- * src >= 0: 0-based row into `sens`;  src == -1: constant +1;  src == -2: constant -1. */
+ * src >= 0: 0-based row into `sens`;  src == -1: constant +1;  src == -2: constant -1.  The jac_nnz_var entries
+ * with src >= 0 come first, in the order of `jac_vals`. */
 int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int64_t *src);
 
 /* Device time of the last cb200_eval's integration kernel(s) in milliseconds (CUDA events on the

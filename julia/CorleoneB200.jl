@@ -82,6 +82,7 @@ struct Sizes                     # cb200_sizes
     n_sens::Int64
     n_units::Int64
     jac_nnz::Int64
+    jac_nnz_var::Int64
 end
 
 const WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS = 0x001, 0x002, 0x004, 0x008
@@ -116,7 +117,7 @@ end
 function EnsembleB200(; model::Symbol, steps_per_piece = 1, method = :tsit5, device = 0,
         model_data = Float64[], fim = (0, 0))
     e = EnsembleB200(model, steps_per_piece, method, device, collect(Float64, model_data), fim, C_NULL,
-        Sizes(0, 0, 0, 0, 0, 0, 0), 0)
+        Sizes(0, 0, 0, 0, 0, 0, 0, 0), 0)
     finalizer(e) do x
         x.handle == C_NULL || ccall((:cb200_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle)
     end
@@ -168,7 +169,7 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
         check(ccall((:cb200_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h), "cb200_create")
     end
     e.handle = h[]
-    s = Ref(Sizes(0, 0, 0, 0, 0, 0, 0))
+    s = Ref(Sizes(0, 0, 0, 0, 0, 0, 0, 0))
     check(ccall((:cb200_get_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{Sizes}), e.handle, s), "cb200_get_sizes")
     e.sizes = s[]
     e.nx = nx
@@ -198,7 +199,7 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     grad = alloc(WANT_GRAD, s.nvars)
     nf = e.fim[2]
     fim = alloc(WANT_FIM, nf * nf)
-    jac = alloc(WANT_JAC, s.jac_nnz)
+    jac = alloc(WANT_JAC, s.jac_nnz_var)
     crit = alloc(WANT_CRIT, 6)
     fsum = zeros(nf, nf)
     ptr(a) = isempty(a) ? Ptr{Float64}(C_NULL) : pointer(a)
@@ -264,12 +265,16 @@ function jac_structure(e::EnsembleB200)
 end
 
 function b200_cons_j(e::EnsembleB200)
-    rows, cols, _ = jac_structure(e)
+    rows, cols, src = jac_structure(e)
+    nv = Int(e.sizes.jac_nnz_var)                        # the leading triplets carry sensitivity values
     return function (J, x, st)                          # rows of the shooting block follow the point constraints
         vals = vec(evaluate(e, reshape(collect(x), :, 1); want = WANT_JAC).jac_vals)
         fill!(J, 0)
-        for k in eachindex(rows)
-            J[rows[k], cols[k]] += vals[k]               # already assembled on the device (K5), triplet order
+        for k in 1:nv
+            J[rows[k], cols[k]] += vals[k]               # assembled on the device (K5), triplet order
+        end
+        for k in (nv + 1):length(rows)
+            J[rows[k], cols[k]] += src[k] == -1 ? 1.0 : -1.0   # matching conditions w.r.t. the next interval's variables
         end
         return J
     end

@@ -69,7 +69,8 @@ def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
             np.add.at(J, (rows - 1, cols - 1), vals)
             errs["jac"] = max(errs.get("jac", 0.0), rel_err(J, Jd))
             # the same values assembled on the device (K5, WANT_JAC): bit-identical to the gather from sens
-            assert np.array_equal(r["jac_vals"][b], vals), "device cons_j values differ from sens gather"
+            assert np.all(src[:N.jac_nnz_var] >= 0) and np.all(src[N.jac_nnz_var:] < 0)
+            assert np.array_equal(r["jac_vals"][b], vals[:N.jac_nnz_var]), "device cons_j values differ from sens gather"
     return errs
 
 
@@ -299,5 +300,5 @@ def test_dense20_tensor_path_many_groups(method):
             off += nx * ns
         assert rel_err(r["grad"][b], Jl[0]) <= RTOL
         J = np.zeros((O.ndef, O.nvars))
-        np.add.at(J, (rows - 1, cols - 1), r["jac_vals"][b])
+        np.add.at(J, (rows - 1, cols - 1), np.concatenate([r["jac_vals"][b], np.where(src[N.jac_nnz_var:] == -1, 1.0, -1.0)]))
         assert rel_err(J, Jd) <= RTOL
