@@ -6,7 +6,7 @@ int launch_lotka2_oed(int G, int method, const DevLayer &L, const double *ps, lo
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lotka2Oed, 0, 1)
+        CB200_DISPATCH_G(Lotka2Oed, 0, 5)  // 96 registers: 20 warps/SM; G x MINB sweep in profiles/
     default:
         return -1000;
     }
