@@ -3,6 +3,7 @@ against the oracle on a random sample of candidates (the oracle cannot do the wh
 
     config 2  lqr_ms100_b4096      100 intervals x 4096 candidates, 8 sensitivity directions
     config 3  lotka_oed_64x16k     64 intervals x 16384 parameter samples, Fisher information accumulation
+    config 4  dense20_256x65k      256 intervals, full 20 x 24 sensitivity Jacobian (a 1280-candidate chunk of the 65k)
 """
 import numpy as np
 import pytest
@@ -107,3 +108,53 @@ def test_config3_lotka_oed_full_size():
         assert rel(r["defects_kind"][b], o["defk"]) <= RTOL
         assert rel(r["xend"][b].reshape(O.I, O.nx).T, o["xend"]) <= RTOL
     assert nd == 63 * (9 + 2)
+
+
+def test_config4_dense20_full_intervals():
+    """256 intervals x 1280 candidates (327 680 units, 0.16 G sensitivity values) through the tensor-path kernel:
+    oracle on a sample, semigroup property of the sensitivities, reproducibility."""
+    torch = pytest.importorskip("torch")
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(20261019 + 4)
+    spec = P.config4_dense20(256, rng)
+    lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2))
+    O = po.OracleLayer(spec)
+    B, nvars, I, nx = 1280, N.nvars, 256, 20
+    ps0 = cb.to_vec(ps_t)
+    ps = np.tile(ps0, (B, 1)) + 0.1 * rng.standard_normal((B, nvars))
+    ps = N.forward_init(ps)                      # continuous trajectories: nodes from the device forward sweep
+    dev = torch.device("cuda:0")
+    d_ps = torch.from_numpy(np.ascontiguousarray(ps.T)).to(dev)
+    sz = N.out_sizes()
+    outs = {f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in ("xend", "sens", "defects_kind")}
+    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
+    N.set_stream(torch.cuda.current_stream().cuda_stream)
+    N.eval_raw(d_ps.data_ptr(), B, B, want, flags, {k: v.data_ptr() for k, v in outs.items()}, 1)
+    torch.cuda.synchronize()
+    first = {k: v.clone() for k, v in outs.items()}
+    N.eval_raw(d_ps.data_ptr(), B, B, want, flags, {k: v.data_ptr() for k, v in outs.items()}, 1)
+    torch.cuda.synchronize()
+    for k in outs:
+        assert torch.equal(first[k], outs[k]), f"{k} is not reproducible"
+    xend = outs["xend"].cpu().numpy().T.reshape(B, I, nx)
+    defk = outs["defects_kind"].cpu().numpy().T
+    assert np.all(np.isfinite(xend))
+    # forward-initialised candidates: every state matching vanishes (test/core/multiple_shooting.jl:131-152)
+    assert np.max(np.abs(defk)) <= 1e-11
+    blocks = N.block_structure()
+    for b in rng.choice(B, 3, replace=False):
+        o = O.eval(ps[b], K=2)
+        assert rel(xend[b].T, o["xend"]) <= RTOL
+        assert rel(defk[b], o["defk"]) <= 1e-9      # defects ~ 0: absolute scale
+    # sensitivities of one candidate against the oracle's dense Jacobian (intervals 0, 1, 128, 255)
+    b = int(rng.integers(B))
+    sens_b = outs["sens"][:, b].cpu().numpy()
+    Jx, _, _ = O.jacobians(ps[b], K=2)
+    off = np.concatenate([[0], np.cumsum([nx * (blocks[i + 1] - blocks[i]) for i in range(I)])])
+    for i in (0, 1, 128, 255):
+        ns = blocks[i + 1] - blocks[i]
+        S = sens_b[off[i]:off[i + 1]].reshape(ns, nx).T
+        assert rel(S, Jx[nx * i:nx * (i + 1), blocks[i]:blocks[i + 1]]) <= RTOL
