@@ -318,7 +318,7 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status;
 };
 
 static int default_G(int model)
@@ -799,7 +799,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed})
+                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status})
         b->release();
     if (h->tables) cudaFree(h->tables);
     for (int k = 0; k < cb200_handle::EV_RING; k++) {
@@ -915,6 +915,7 @@ struct EvalPlan {
 struct DevSet {
     double *xend = nullptr, *sens = nullptr, *traj = nullptr, *dk = nullptr, *ds = nullptr, *obj = nullptr,
            *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr;
+    int *status = nullptr;      // [B] of the batch / chunk
     double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // shared by all chunks (atomic accumulation)
     const double *finit = nullptr;
 };
@@ -946,6 +947,7 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     so.grad = pl.fused_grad ? d.grad : nullptr;
     so.grad_sum = pl.fused_grad ? d.gsum : nullptr;
     so.jac = d.jac;
+    so.status = d.status;
     so.obj_state = pl.obj_state;
     so.obj_all = pl.obj_quad;
     const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
@@ -1103,6 +1105,10 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
                 d.*(it.slot) = (double *)it.ws->p;
             }
         }
+        if (out->status) {   // int32 per candidate, the caller's device buffer
+            d.status = out->status;
+            CUDA_TRY(cudaMemsetAsync(d.status, 0, sizeof(int) * (size_t)B, h->stream));
+        }
         int rc = eval_core(h, h->stream, d_ps, d_ldb, B, pl, d);
         if (rc) return rc;
         if (!direct) {
@@ -1146,6 +1152,10 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     if (stage_per_cand && h->ws_out.reserve(sizeof(double) * stage_per_cand * (size_t)B))
         return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
 
+    if (out->status) {
+        if (h->ws_status.reserve(sizeof(int) * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
+        CUDA_TRY(cudaMemsetAsync(h->ws_status.p, 0, sizeof(int) * (size_t)B, h->stream));
+    }
     cudaStream_t streams[cb200_handle::NAUX + 1];
     int ns_used = 1;
     streams[0] = h->stream;
@@ -1179,8 +1189,11 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         DevSet d = shared;
         for (const Item &it : items)
             if (it.on) d.*(it.slot) = (double *)it.ws->p + (size_t)b0 * (size_t)it.n;
+        if (out->status) d.status = (int *)h->ws_status.p + b0;
         int rc = eval_core(h, st, d_ps, bn, bn, pl, d);
         if (rc) return rc;
+        if (out->status)
+            CUDA_TRY(cudaMemcpyAsync(out->status + b0, d.status, sizeof(int) * (size_t)bn, cudaMemcpyDeviceToHost, st));
         size_t stage_off = (size_t)b0 * stage_per_cand;
         for (const Item &it : items) {
             if (!it.on || !it.user) continue;

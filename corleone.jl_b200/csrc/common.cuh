@@ -64,6 +64,7 @@ struct ShootOut {
     double *grad;      // [var * ldo + b]
     double *grad_sum;  // [var] sum over the candidates of this launch (atomicAdd of warp partial sums)
     double *jac;       // [slot * ldo + b] values of d(shooting_constraints)/d(ps) in cb200_jac_structure order
+    int *status;       // [b] failure flags (atomicOr): bit 0 = a non-finite end state on some interval
     int obj_state;     // 0-based state row of the objective, -1: none
     int obj_all;       // 1: every interval contributes to the objective (quadrature state), 0: last interval only
 };

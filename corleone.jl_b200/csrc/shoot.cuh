@@ -312,6 +312,12 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
 #define CB200_XS(k) ((k) < NXD ? yd[(k) < NXD ? (k) : 0] : yq[(k) >= NXD ? (k)-NXD : 0])
 #define CB200_SS(g, k) ((k) < NXD ? yd[NXD * (1 + (g)) + ((k) < NXD ? (k) : 0)] : yq[NQ * (1 + (g)) + ((k) >= NXD ? (k)-NXD : 0)])
     if (r == 0 && live) {
+        if (o.status) {  // failure detection: the reference never inspects the solver's return code
+            bool ok = true;
+#pragma unroll
+            for (int k = 0; k < NX; k++) ok = ok && isfinite(CB200_XS(k));
+            if (!ok) atomicOr(o.status + b, 1);
+        }
         if (o.xend) {
 #pragma unroll
             for (int k = 0; k < NX; k++) o.xend[((long long)i * NX + k) * o.ldo + b] = CB200_XS(k);

@@ -282,6 +282,12 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
     if (!store) return;
     if constexpr (IS_X) {
         if (round != 0) return;
+        if (o.status) {
+            bool ok = true;
+#pragma unroll
+            for (int s = 0; s < 5; s++) ok = ok && isfinite(yd[s]);
+            if (!ok) atomicOr(o.status + b, 1);
+        }
 #pragma unroll
         for (int s = 0; s < 5; s++) {
             const int k = 5 * t + s;

@@ -49,7 +49,7 @@ class Out(C.Structure):
         ("defects_stage", C.c_void_p), ("objective", C.c_void_p), ("grad", C.c_void_p), ("fim", C.c_void_p),
         ("fim_sum", C.c_void_p), ("objective_sum", C.c_void_p), ("grad_sum", C.c_void_p),
         ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
-        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p),
+        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p), ("status", C.c_void_p),
     ]
 
 
@@ -250,6 +250,8 @@ class NativeLayer:
         if (want & (WANT_FIM | WANT_CRIT)) and fim_init is not None:
             fi = np.asfortranarray(fim_init, dtype=np.float64)   # kept alive until the call returns
             ptrs["fim_init"] = fi.ctypes.data
+        res["status"] = np.zeros(B, dtype=np.int32)   # failure flags per candidate (bit 0: non-finite state)
+        ptrs["status"] = res["status"].ctypes.data
         if with_sums:   # cross-candidate sums accumulated on the device (the per-rank partials of a sharded run)
             if want & WANT_OBJ:
                 res["objective_sum"] = np.zeros(1, dtype=np.float64)

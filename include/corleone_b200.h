@@ -154,6 +154,8 @@ typedef struct {
     int32_t reserved;
     double *jac_vals;
     double *criteria;
+    int32_t *status;            /* [B] failure flags per candidate (always filled when non-NULL): bit 0 = a non-finite
+                                   end state on some interval.  The reference never inspects the solver's retcode. */
 } cb200_out;
 
 typedef struct {

@@ -72,6 +72,7 @@ struct Out                       # cb200_out
     reserved::Int32
     jac_vals::Ptr{Float64}
     criteria::Ptr{Float64}
+    status::Ptr{Int32}
 end
 
 struct Sizes                     # cb200_sizes
@@ -201,17 +202,18 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     fim = alloc(WANT_FIM, nf * nf)
     jac = alloc(WANT_JAC, s.jac_nnz_var)
     crit = alloc(WANT_CRIT, 6)
+    status = zeros(Int32, B)
     fsum = zeros(nf, nf)
     ptr(a) = isempty(a) ? Ptr{Float64}(C_NULL) : pointer(a)
-    GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init jac crit begin
+    GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init jac crit status begin
         o = Out(ptr(xend), ptr(sens), ptr(traj), ptr(dk), ptr(ds), ptr(obj), ptr(grad), ptr(fim),
             (want & WANT_FIM) != 0 ? pointer(fsum) : Ptr{Float64}(C_NULL), C_NULL, C_NULL,
-            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit))
+            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), pointer(status))
         check(ccall((:cb200_eval, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, UInt32, UInt32, Ref{Out}),
                 e.handle, P, B, size(P, 1), want, 0, o), "cb200_eval")
     end
-    return (; xend, sens, traj, defects_kind = dk, defects_stage = ds, objective = obj, grad, fim, fim_sum = fsum, jac_vals = jac, criteria = crit)
+    return (; xend, sens, traj, defects_kind = dk, defects_stage = ds, objective = obj, grad, fim, fim_sum = fsum, jac_vals = jac, criteria = crit, status)
 end
 
 # ---------------------------------------------------------------- drop-in: layer(nothing, ps, st) on the GPU

@@ -182,6 +182,13 @@ def test_empty_batch_and_errors():
         N.eval_host(np.zeros((1, N.nvars)), nat.WANT_OBJ, objective_row=99)
     with pytest.raises(nat.NativeError):
         N.eval_host(np.zeros((1, N.nvars)), nat.WANT_FIM)
+    # failure flags: a candidate whose node is NaN is reported, its neighbours are not
+    ps = np.tile(cb.to_vec(ps_t), (5, 1))
+    ps[3, 40] = np.nan
+    ps[1, 2] = 1e308          # overflows during integration
+    r = N.eval_host(ps, nat.WANT_XEND | nat.WANT_DEFECTS)
+    assert list(r["status"]) == [0, 1, 0, 1, 0]
+    assert np.all(np.isfinite(r["xend"][[0, 2, 4]]))
 
 
 def test_device_resident_soa_path():
