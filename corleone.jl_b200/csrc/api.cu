@@ -318,7 +318,9 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small;
+    static constexpr size_t PIN_BYTES = 1 << 20;   // pinned host mirror of small evaluations
+    void *pin = nullptr;
 };
 
 static int default_G(int model)
@@ -799,9 +801,10 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status})
+                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small})
         b->release();
     if (h->tables) cudaFree(h->tables);
+    if (h->pin) cudaFreeHost(h->pin);
     for (int k = 0; k < cb200_handle::EV_RING; k++) {
         if (h->ev0[k]) cudaEventDestroy(h->ev0[k]);
         if (h->ev1[k]) cudaEventDestroy(h->ev1[k]);
@@ -996,8 +999,12 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     CUDA_TRY(cudaSetDevice(h->device));
     const DevLayer &L0 = h->L;
     const int nx = L0.nx, I = L0.I, nvars = L0.nvars;
-    const bool dev = flags & CB200_MEM_DEVICE, ps_soa = flags & CB200_PS_SOA, out_soa = flags & CB200_OUT_SOA;
+    bool dev = flags & CB200_MEM_DEVICE, ps_soa = flags & CB200_PS_SOA, out_soa = flags & CB200_OUT_SOA;
     if (ps_soa ? (ldb < B) : (ldb < nvars)) return fail(CB200_ERR_ARG, "ldb too small");
+    if (B == 1) {   // one candidate (the reference's own use): both layouts coincide, no conversion kernels
+        ps_soa = out_soa = true;
+        ldb = 1;
+    }
     const long long nrow = nx + L0.nact;
     const long long ndef = (long long)h->defects.size();
     const int n2 = h->fim_n * h->fim_n;
@@ -1121,6 +1128,67 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         return CB200_OK;   // enqueued on the handle's stream
     }
 
+    // =================================================================== host pointers, small evaluation
+    // (one candidate = the reference's own use, or a small variable-major batch): pageable caller arrays would make
+    // every cudaMemcpyAsync a synchronous staged copy, so the inputs go through a pinned mirror with ONE H2D copy,
+    // every result lands in ONE device buffer that comes back with ONE D2H copy, and the CPU scatters it.
+    {
+        size_t out_doubles = 0;
+        for (const Item &it : items)
+            if (it.on && it.user) out_doubles += (size_t)it.n * (size_t)B;
+        const size_t sums_doubles = (size_t)(pl.osum ? 1 : 0) + (pl.gsum ? (size_t)nvars : 0) + (pl.fsum ? (size_t)n2 : 0);
+        const size_t in_doubles = (size_t)nvars * (size_t)B;
+        const size_t tot = sizeof(double) * (out_doubles + sums_doubles + in_doubles) + sizeof(int) * (size_t)B;
+        if (ps_soa && out_soa && ldb == B && tot <= cb200_handle::PIN_BYTES) {
+            if (!h->pin) CUDA_TRY(cudaHostAlloc(&h->pin, cb200_handle::PIN_BYTES, cudaHostAllocDefault));
+            if (h->ws_small.reserve(tot)) return fail(CB200_ERR_NOMEM, "device out of memory");
+            double *hp = (double *)h->pin, *dp = (double *)h->ws_small.p;
+            // layout (doubles): [inputs | results ... | sums] then the status ints
+            if (in_doubles) {
+                memcpy(hp, ps, sizeof(double) * in_doubles);
+                CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * in_doubles, cudaMemcpyHostToDevice, h->stream));
+            }
+            DevSet d = shared;
+            size_t off = in_doubles;
+            for (const Item &it : items) {
+                if (!it.on) continue;
+                if (it.user) {
+                    d.*(it.slot) = dp + off;
+                    off += (size_t)it.n * (size_t)B;
+                } else {
+                    if (it.ws->reserve(sizeof(double) * (size_t)it.n * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
+                    d.*(it.slot) = (double *)it.ws->p;
+                }
+            }
+            const size_t sums_off = off;
+            if (pl.osum) { d.osum = dp + off; off += 1; }
+            if (pl.gsum) { d.gsum = dp + off; off += (size_t)nvars; }
+            if (pl.fsum) { d.fsum = dp + off; off += (size_t)n2; }
+            if (sums_doubles) CUDA_TRY(cudaMemsetAsync(dp + sums_off, 0, sizeof(double) * sums_doubles, h->stream));
+            int *d_status = (int *)(dp + off);
+            if (out->status) {
+                d.status = d_status;
+                CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)B, h->stream));
+            }
+            int rc = eval_core(h, h->stream, in_doubles ? dp : nullptr, B, B, pl, d);
+            if (rc) return rc;
+            const size_t back = sizeof(double) * (off - in_doubles) + (out->status ? sizeof(int) * (size_t)B : 0);
+            if (back) CUDA_TRY(cudaMemcpyAsync(hp + in_doubles, dp + in_doubles, back, cudaMemcpyDeviceToHost, h->stream));
+            CUDA_TRY(cudaStreamSynchronize(h->stream));
+            size_t o2 = in_doubles;
+            for (const Item &it : items) {
+                if (!it.on || !it.user) continue;
+                memcpy(it.user, hp + o2, sizeof(double) * (size_t)it.n * (size_t)B);
+                o2 += (size_t)it.n * (size_t)B;
+            }
+            if (pl.osum) { *out->objective_sum = hp[o2]; o2 += 1; }
+            if (pl.gsum) { memcpy(out->grad_sum, hp + o2, sizeof(double) * (size_t)nvars); o2 += (size_t)nvars; }
+            if (pl.fsum) { memcpy(out->fim_sum, hp + o2, sizeof(double) * (size_t)n2); o2 += (size_t)n2; }
+            if (out->status) memcpy(out->status, hp + o2, sizeof(int) * (size_t)B);
+            return CB200_OK;
+        }
+    }
+
     // =================================================================== host pointers: chunked, pipelined
     // The batch is cut into chunks of candidates; chunk c runs on stream c % NS: host->device copy, layout
     // conversion, the kernels, conversion back and device->host copies.  With pinned caller buffers the copy
@@ -1171,8 +1239,11 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (nvars > 0) {
             double *soa = (double *)h->ws_ps.p + (size_t)b0 * nvars;   // chunk SoA block [nvars][bn]
             if (ps_soa) {  // host, variable-major (single chunk)
-                CUDA_TRY(cudaMemcpy2DAsync(soa, sizeof(double) * bn, ps + b0, sizeof(double) * ldb, sizeof(double) * bn,
-                                           nvars, cudaMemcpyHostToDevice, st));
+                if (ldb == bn)
+                    CUDA_TRY(cudaMemcpyAsync(soa, ps, sizeof(double) * (size_t)nvars * (size_t)bn, cudaMemcpyHostToDevice, st));
+                else
+                    CUDA_TRY(cudaMemcpy2DAsync(soa, sizeof(double) * bn, ps + b0, sizeof(double) * ldb, sizeof(double) * bn,
+                                               nvars, cudaMemcpyHostToDevice, st));
             } else {       // host, candidate-major (Julia nvars x B matrix)
                 double *stg = (double *)h->ws_in.p + (size_t)b0 * nvars;
                 if (ldb == nvars)
