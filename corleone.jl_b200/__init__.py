@@ -22,7 +22,7 @@ from .single_shooting import InitialConditionRemaker, SingleShootingLayer, from_
 from .trajectory import Trajectory, is_shooting_solution, shooting_violations
 from . import native
 from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion, FisherECriterion,
-                       batched_criteria)
+                       batched_criteria, criteria_gradient)
 
 
 def setup(rng, layer):

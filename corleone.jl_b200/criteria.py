@@ -52,3 +52,40 @@ def batched_criteria(nat: "native.NativeLayer", ps_batch, fim_init=None):
     """(B, 6) array, columns in `ORDER`, of F = F_init + F(t_end) for every candidate; also returns the FIMs."""
     r = nat.eval_host(ps_batch, native.WANT_FIM | native.WANT_CRIT, fim_init=fim_init)
     return r["criteria"], r["fim"].reshape(-1, nat.fim_n, nat.fim_n)
+
+
+def criteria_gradient(nat: "native.NativeLayer", ps_batch, fim_init=None):
+    """Gradients of the six criteria w.r.t. the flat variable vector, per candidate: (B, 6, nvars).
+
+    One cb200_eval delivers F and the second-order sensitivities d F(t_end) / d(variables of the last interval)
+    (rows of `sens` that belong to the F_triu states); the chain rule through the small n x n matrix functions is
+    host arithmetic.  With multiple shooting F is a shooting state, so only the last interval's block is non-zero
+    (the other blocks enter through the matching constraints, as in the reference's NLP)."""
+    r = nat.eval_host(ps_batch, native.WANT_FIM | native.WANT_SENS, fim_init=fim_init)
+    B, n, nx, I = r["fim"].shape[0], nat.fim_n, nat.nx, nat.I
+    blocks = nat.block_structure()
+    ns_last = int(blocks[I] - blocks[I - 1])
+    sens_off = sum(nx * int(blocks[i + 1] - blocks[i]) for i in range(I - 1))
+    f_off = nat.fim_offset - 1
+    out = np.zeros((B, 6, nat.nvars))
+    iu = [(a, b) for b in range(n) for a in range(b + 1)]          # column-major upper triangle (augmentation.jl:211)
+    for c in range(B):
+        F = r["fim"][c].reshape(n, n)
+        S = r["sens"][c][sens_off:sens_off + nx * ns_last].reshape(ns_last, nx)    # [direction, state]
+        lam, V = np.linalg.eigh(F)
+        Finv = np.linalg.inv(F)
+        det = np.linalg.det(F)
+        vmin = V[:, 0]
+        for d in range(ns_last):
+            dF = np.zeros((n, n))
+            for q, (a, b) in enumerate(iu):
+                dF[a, b] = dF[b, a] = S[d, f_off + q]
+            g = out[c, :, blocks[I - 1] + d]
+            t = np.trace(Finv @ dF)
+            g[0] = -np.trace(Finv @ dF @ Finv)
+            g[1] = -t / det
+            g[2] = -(vmin @ dF @ vmin) / lam[0] ** 2
+            g[3] = -np.trace(dF)
+            g[4] = -det * t
+            g[5] = -(vmin @ dF @ vmin)
+    return out

@@ -332,6 +332,8 @@ static int default_G(int model)
     case CB200_MODEL_LIN1D: return 4;
     case CB200_MODEL_EGERSTEDT: return 2;
     case CB200_MODEL_DENSE20: return 1;
+    case CB200_MODEL_LOTKA2_OED: return 1;   // second-order sensitivities of [x; G; F]: 12 dynamic + 6 quadrature per thread (G = 2 spills)
+    case CB200_MODEL_LIN1D_OED: return 2;
     default: return 0;
     }
 }

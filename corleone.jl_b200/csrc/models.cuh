@@ -87,6 +87,17 @@ struct Lotka2 {
         dv[0] = fma(c.j00, v[0], fma(c.j01, v[1], fma(F.c00, x[0], F.c01 * c.x12)));
         dv[1] = fma(c.j10, v[0], fma(c.j11, v[1], fma(F.c10, x[1], F.c11 * c.x12)));
     }
+    // second-order term of the sensitivity equations: out = d/d eps [ f_x g + f_p[:, fpcol] ] along the tangent
+    // (dx, e_pcol) -- i.e. (f_xx[dx] + f_xp[e_pcol]) g + (f_px[dx] + f_pp[e_pcol])[:, fpcol]; pcol / fpcol = -1: none
+    CB_DEV void d2(const double *x, const double *p, const double *dx, int pcol, const double *g, int fpcol, double *out)
+    {
+        const double dp0 = pcol == 0 ? 1.0 : 0.0, dp1 = pcol == 1 ? 1.0 : 0.0, dp2 = pcol == 2 ? 1.0 : 0.0;
+        const double dj00 = -p[1] * dx[1] - dp1 * x[1] - 0.4 * dp0, dj01 = -p[1] * dx[0] - dp1 * x[0];
+        const double dj10 = p[2] * dx[1] + dp2 * x[1], dj11 = p[2] * dx[0] + dp2 * x[0] - 0.2 * dp0;
+        const double dx12 = fma(dx[0], x[1], x[0] * dx[1]);
+        out[0] = fma(dj00, g[0], dj01 * g[1]) + (fpcol == 0 ? -0.4 * dx[0] : (fpcol == 1 ? -dx12 : 0.0));
+        out[1] = fma(dj10, g[0], dj11 * g[1]) + (fpcol == 0 ? -0.2 * dx[1] : (fpcol == 2 ? dx12 : 0.0));
+    }
 };
 
 // ---- linear-quadratic regulator (examples/linear_quadratic/main.jl:45-50), p = (a, b, u)
@@ -136,6 +147,11 @@ struct Lin1d {
     CB_DEV void jvp(const double *x, const double *p, const Ctx &, const double *v, const Force &F, double *dv)
     {
         dv[0] = fma(p[0], v[0], F.w * x[0]);
+    }
+    // f = p x: f_x = p, f_p = x  ->  d(f_x g + f_p[:, fpcol]) = dp g + (fpcol == 0 ? dx : 0)
+    CB_DEV void d2(const double *, const double *, const double *dx, int pcol, const double *g, int fpcol, double *out)
+    {
+        out[0] = (pcol == 0 ? g[0] : 0.0) + (fpcol == 0 ? dx[0] : 0.0);
     }
 };
 
@@ -212,16 +228,19 @@ struct OedAug {
     static_assert(Base::NQ == 0, "OED base model must not carry quadrature states");
     static constexpr int BX = Base::NX, NF = Traits::NF, NOBS = Traits::NOBS;
     static constexpr int NXD = BX + BX * NF, NQ = NF * (NF + 1) / 2, NX = NXD + NQ, NP = Base::NP + NOBS;
-    static constexpr bool HAS_JVP = false;
-    struct Ctx {};
-    struct Force {};
-    CB_DEV void f(const double *y, const double *p, double *dy, Ctx &)
+    static constexpr bool HAS_JVP = true;
+    struct Ctx {
+        typename Base::Ctx base;
+    };
+    struct Force {
+        int pcol;   // tangent p column of the augmented problem: < Base::NP a model parameter, >= a weight w_i; -1 none
+    };
+    CB_DEV void f(const double *y, const double *p, double *dy, Ctx &c)
     {
-        typename Base::Ctx c;
-        Base::f(y, p, dy, c);
+        Base::f(y, p, dy, c.base);
 #pragma unroll
         for (int k = 0; k < NF; k++)
-            Base::jvp(y, p, c, y + BX + BX * k, Base::make_force(Traits::pcol(k), p), dy + BX + BX * k);
+            Base::jvp(y, p, c.base, y + BX + BX * k, Base::make_force(Traits::pcol(k), p), dy + BX + BX * k);
         const double *G = y + BX;
         const double *w = p + Base::NP;
         double *dF = dy + NXD;
@@ -236,8 +255,41 @@ struct OedAug {
                 dF[q++] = acc;
             }
     }
-    CB_DEV Force make_force(int, const double *) { return Force{}; }
-    CB_DEV void jvp(const double *, const double *, const Ctx &, const double *, const Force &, double *) {}
+    CB_DEV Force make_force(int pcol, const double *) { return Force{pcol}; }
+    // tangent of the augmented right-hand side (what ForwardDiff through the OED layer propagates):
+    //   dx'  = f_x dx + f_p e_pcol
+    //   dG'  = f_x dG + (f_xx[dx] + f_xp[e_pcol]) G + d(f_p columns)
+    //   dF'  = sum_i dw_i (h_i G)'(h_i G) + w_i [ (h_i dG)'(h_i G) + (h_i G)'(h_i dG) ]
+    CB_DEV void jvp(const double *y, const double *p, const Ctx &c, const double *v, const Force &F, double *dv)
+    {
+        const int bp = F.pcol < Base::NP ? F.pcol : -1;   // model-parameter part of the direction
+        Base::jvp(y, p, c.base, v, Base::make_force(bp, p), dv);
+#pragma unroll
+        for (int k = 0; k < NF; k++) {
+            double lin[BX], sec[BX];
+            Base::jvp(y, p, c.base, v + BX + BX * k, Base::make_force(-1, p), lin);
+            Base::d2(y, p, v, bp, y + BX + BX * k, Traits::pcol(k), sec);
+#pragma unroll
+            for (int r = 0; r < BX; r++) dv[BX + BX * k + r] = lin[r] + sec[r];
+        }
+        const double *G = y + BX, *dG = v + BX;
+        const double *w = p + Base::NP;
+        double *dF = dv + NXD;
+        int q = 0;
+#pragma unroll
+        for (int b = 0; b < NF; b++)
+#pragma unroll
+            for (int a = 0; a <= b; a++) {
+                double acc = 0.0;
+#pragma unroll
+                for (int i = 0; i < NOBS; i++) {
+                    const double gg = G[i + BX * a] * G[i + BX * b];
+                    const double dgg = fma(dG[i + BX * a], G[i + BX * b], G[i + BX * a] * dG[i + BX * b]);
+                    acc += (F.pcol == Base::NP + i ? gg : 0.0) + w[i] * dgg;
+                }
+                dF[q++] = acc;
+            }
+    }
 };
 struct LotkaOedTraits {
     static constexpr int NF = 2, NOBS = 2;

@@ -132,7 +132,8 @@ class NativeLayer:
         put("quadrature_indices", quadrature_indices, np.int64, _i64p)
         put("n_pieces", [len(iv["tspans"]) for iv in intervals], np.int32, _i32p)
         put("tspans", [x for iv in intervals for ts in iv["tspans"] for x in ts], np.float64, _dp)
-        ig = [np.asarray(iv["index_grid"], dtype=np.int64).reshape(nact, -1).ravel(order="F") for iv in intervals]
+        ig = [np.asarray(iv["index_grid"], dtype=np.int64).reshape(nact, -1).ravel(order="F") if nact
+              else np.zeros(0, dtype=np.int64) for iv in intervals]   # no controls: empty index grid
         put("index_grid", np.concatenate(ig) if ig else [], np.int64, _i64p)
         put("n_u0", [iv["n_u0"] for iv in intervals], np.int32, _i32p)
         put("n_local_controls", [iv["n_c"] for iv in intervals], np.int32, _i32p)
@@ -154,6 +155,7 @@ class NativeLayer:
         self.n_defects, self.n_samples, self.n_row = int(s.n_defects), int(s.n_samples), int(s.n_row)
         self.n_sens, self.jac_nnz, self.jac_nnz_var = int(s.n_sens), int(s.jac_nnz), int(s.jac_nnz_var)
         self.fim_n = fim_n
+        self.fim_offset = fim_offset
         self.device = device
 
     def close(self):

@@ -309,3 +309,58 @@ def test_dense20_tensor_path_many_groups(method):
         J = np.zeros((O.ndef, O.nvars))
         np.add.at(J, (rows - 1, cols - 1), np.concatenate([r["jac_vals"][b], np.where(src[N.jac_nnz_var:] == -1, 1.0, -1.0)]))
         assert rel_err(J, Jd) <= RTOL
+
+
+def test_offgrid_nodes_control_matchings_and_tunable_ic():
+    """shooting nodes that are not control grid points give control matchings (src/single_shooting.jl:333-340,
+    src/multiple_shooting.jl:150-163) and non-uniform piece lengths (per-piece step sizes); tunable initial
+    conditions on the first interval (test/core/multiple_shooting.jl style)"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(31)
+    spec = P.lotka_spec(shooting_points=[0.0, 2.95, 6.0, 8.17], controls=rng.uniform(0, 1, 120), tunable_ic=[2, 1])
+    assert_ok(full_compare(spec, cb.Tsit5(2), 4, rng, objective_row=3))
+    spec = P.lotka_spec(shooting_points=[0.0, 2.95, 6.0, 8.17], controls=rng.uniform(0, 1, 120), quadrature=True)
+    assert_ok(full_compare(spec, cb.RK4(2), 35, rng, objective_row=3))
+
+
+def test_layer_without_controls():
+    """no ControlParameter at all: index_grid = control_indices = [], one piece = the problem's tspan
+    (src/single_shooting.jl:329-332); every parameter is tunable"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(37)
+    spec = P.lotka_spec(shooting_points=None, tunable_ic=[1, 2])
+    spec["controls"] = []
+    assert_ok(full_compare(spec, cb.Tsit5(40), 3, rng, objective_row=3))
+
+
+def test_oed_second_order_sensitivities():
+    """sensitivities of the augmented OED system [x; G; F_triu] w.r.t. nodes, parameters, the control and the
+    measurement weights (what ForwardDiff through the OED layer yields, lib/CorleoneOED/src/augmentation.jl:131-253):
+    d F(t_end) / d(everything) is what a design optimiser differentiates the criteria with."""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(41)
+    for sp in (None, [0.0, 3.0, 6.0, 9.0]):
+        spec = P.lotka_oed_spec(shooting_points=sp, fishing=rng.uniform(0, 1, 48), w=0.7)
+        assert_ok(full_compare(spec, cb.Tsit5(2), 3, rng, objective_row=7, check_traj=False))   # objective = F11
+    spec = P.config3_lotka_oed(6, rng)
+    assert_ok(full_compare(spec, cb.RK4(2), 34, rng, objective_row=9, check_traj=False))          # F22
+    assert_ok(full_compare(P.lin1d_oed_spec(), cb.Tsit5(1), 3, rng, objective_row=3, check_traj=False))
+
+
+def test_oed_criteria_gradient_vs_finite_differences():
+    import corleone_b200 as cb
+    rng = np.random.default_rng(43)
+    spec = P.lotka_oed_spec(shooting_points=None, fishing=rng.uniform(0, 1, 48), w=0.8)
+    lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2))
+    ps = cb.to_vec(ps_t)[None, :] + 0.02 * rng.standard_normal((2, N.nvars))
+    Finit = 0.3 * np.eye(2)
+    g = cb.criteria_gradient(N, ps, fim_init=Finit)
+    h = 1e-6
+    for v in rng.choice(N.nvars, 12, replace=False):
+        pp, pm = ps.copy(), ps.copy()
+        pp[:, v] += h
+        pm[:, v] -= h
+        cp, _ = cb.batched_criteria(N, pp, fim_init=Finit)
+        cm, _ = cb.batched_criteria(N, pm, fim_init=Finit)
+        fd = (cp - cm) / (2 * h)
+        assert np.allclose(g[:, :, v], fd, rtol=2e-6, atol=1e-7), (v, g[:, :, v], fd)
