@@ -22,7 +22,7 @@ from .single_shooting import InitialConditionRemaker, SingleShootingLayer, from_
 from .trajectory import Trajectory, is_shooting_solution, shooting_violations
 from . import native
 from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion, FisherECriterion,
-                       batched_criteria, criteria_gradient)
+                       batched_criteria, criteria_gradient, global_information_gain, local_information_gain)
 
 
 def setup(rng, layer):

@@ -89,3 +89,27 @@ def criteria_gradient(nat: "native.NativeLayer", ps_batch, fim_init=None):
             g[4] = -det * t
             g[5] = -(vmin @ dF @ vmin)
     return out
+
+
+def _hxG(traj_samples, bx: int, nf: int, nobs: int):
+    """h_x G at every trajectory sample for observed = the leading nobs states (unit rows of h_x):
+    traj_samples (..., n_samples, n_row) -> (..., n_samples, nobs, nf)."""
+    G = np.asarray(traj_samples)[..., bx:bx + bx * nf]
+    G = G.reshape(G.shape[:-1] + (nf, bx))            # vec(G) is column-major: [column c][state r]
+    return np.swapaxes(G, -1, -2)[..., :nobs, :]
+
+
+def local_information_gain(traj_samples, bx: int, nf: int, nobs: int):
+    """local_information_gain (lib/CorleoneOED/src/oed.jl:500-510): for every sample t_k and observed function i
+    the rank-one matrix (h_i G(t_k))'(h_i G(t_k)); result (..., n_samples, nobs, nf, nf).  `traj_samples` are the
+    merged trajectory samples of the augmented layer as cb200_eval(WANT_TRAJ) returns them (batched or not)."""
+    x = _hxG(traj_samples, bx, nf, nobs)
+    return x[..., :, None] * x[..., None, :]
+
+
+def global_information_gain(traj_samples, F_tf, bx: int, nf: int, nobs: int):
+    """global_information_gain (oed.jl:520-534): the same with rows scaled by C = inv(F(t_f))."""
+    C = np.linalg.inv(np.asarray(F_tf))
+    x = _hxG(traj_samples, bx, nf, nobs)
+    x = np.einsum("...koc,...cd->...kod", x, C) if C.ndim > 2 else x @ C
+    return x[..., :, None] * x[..., None, :]
