@@ -441,7 +441,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     h->G_sens = default_G(d->model);
     if (const char *env = getenv("CB200_DIRS_PER_THREAD")) {
         int g = atoi(env);
-        if (g > 0 && g <= 32) h->G_sens = g;
+        if (g > 0 && g <= 24) h->G_sens = g;
     }
 
     // scatter maps A, B (src/single_shooting.jl:306-318): column ids in ascending p index
@@ -577,11 +577,23 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
             else if (dd >= nu0 + ntp && crow[dd - nu0 - ntp] >= 0)
                 pc = L.row_to_p[crow[dd - nu0 - ntp]];
             dir_pcol[(size_t)vof + dd] = (signed char)pc;
-            if (Gs <= 0 || pc < 0) continue;
-            for (int j = 0; j < M; j++) {
+            if (Gs <= 0) continue;
+            // first piece in which the direction is non-zero: u0 seeds and parameters from the start, a control
+            // value from the first piece that uses it (never: a local control no piece refers to)
+            int first = (dd < nu0 + ntp) ? 0 : M;
+            for (int j = 0; j < M && pc >= 0; j++) {
                 const bool on = (dd < nu0 + ntp) ||
                                 h->h_cidx[(size_t)(pof + j) * nact + crow[dd - nu0 - ntp]] == dd - nu0 - ntp;
-                if (on) act_mask[(size_t)(pof + j) * Rmask + dd / Gs] |= 1u << (dd % Gs);
+                if (on) {
+                    act_mask[(size_t)(pof + j) * Rmask + dd / Gs] |= 1u << (dd % Gs);
+                    first = std::min(first, j);
+                }
+            }
+            // bits 24..31 of the word: live prefix length of the group during the piece
+            for (int j = first; j < M; j++) {
+                unsigned &w = act_mask[(size_t)(pof + j) * Rmask + dd / Gs];
+                const unsigned na = (unsigned)(dd % Gs) + 1u;
+                if ((w >> 24) < na) w = (w & 0xffffffu) | (na << 24);
             }
         }
     }

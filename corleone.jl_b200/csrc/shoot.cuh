@@ -165,6 +165,25 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
     }
 }
 
+// Structural zeros of the sensitivities: the derivative with respect to a control value is identically zero until
+// the first piece that uses it, so a piece only integrates the leading `na` directions of the thread's group (the
+// host table gives na = 1 + index of the last direction that is already switched on; the variable order (u0, p,
+// controls in time order) makes the live directions a prefix).  One instantiation per prefix length, selected by
+// a warp-uniform branch.
+template <class Mdl, int G, int METHOD, int GA = G>
+__device__ __forceinline__ void integrate_active(int na, double *yd, double *yq, const double *p,
+                                                 const typename Mdl::Force *F, const double *cf, int K)
+{
+    if constexpr (GA == 0) {
+        integrate_piece<Mdl, 0, METHOD>(yd, yq, p, F, cf, K);
+    } else {
+        if (na >= GA)
+            integrate_piece<Mdl, GA, METHOD>(yd, yq, p, F, cf, K);
+        else
+            integrate_active<Mdl, G, METHOD, (GA > 4 ? GA - 2 : GA - 1)>(na, yd, yq, p, F, cf, K);
+    }
+}
+
 // one merged-trajectory sample: [x(t); controls of the piece in layer row order] (src/single_shooting.jl:456)
 template <class Mdl>
 __device__ __forceinline__ void save_sample(const DevLayer &L, const ShootOut &o, long long sample, int nrow, long long b,
@@ -278,7 +297,8 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
 #pragma unroll
         for (int q = 0; q < NP; q++)
             if (L.pmap_kind[q] == 1) p[q] = pv_nx[q];
-        const unsigned mask = mask_nx;
+        const unsigned mask = mask_nx & 0xffffffu;
+        const int na = (int)(mask_nx >> 24);   // live prefix of the direction group during this piece
         if (j + 1 < M) {
 #pragma unroll
             for (int q = 0; q < NP; q++)
@@ -294,7 +314,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         if (o.traj && live && r == 0 && j == 0)  // save_start = (j == 1)
             save_sample<Mdl>(L, o, (long long)so, nrow, b, yd, yq, p);
         if constexpr (UNI) {
-            integrate_piece<Mdl, G, METHOD>(yd, yq, p, F, L.hA, L.K);
+            integrate_active<Mdl, G, METHOD>(na, yd, yq, p, F, L.hA, L.K);
         } else {
             double cf[NCF];
             const double h = __ldg(L.ph + po + j);
@@ -302,7 +322,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
                 tsit5_coeffs(h, cf);
             else
                 rk4_coeffs(h, cf);
-            integrate_piece<Mdl, G, METHOD>(yd, yq, p, F, cf, L.K);
+            integrate_active<Mdl, G, METHOD>(na, yd, yq, p, F, cf, L.K);
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
