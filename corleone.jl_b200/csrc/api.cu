@@ -338,19 +338,22 @@ static int default_G(int model)
     }
 }
 
-static int model_dims(int model, int *nx, int *np)
+static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
 {
+    int d = 0;   // dynamic states: the leading states that feed a right-hand side (the rest are quadrature-like)
     switch (model) {
-    case CB200_MODEL_LOTKA3: *nx = 3; *np = 3; return 0;
-    case CB200_MODEL_LQR: *nx = 2; *np = 3; return 0;
-    case CB200_MODEL_LOTKA2: *nx = 2; *np = 3; return 0;
-    case CB200_MODEL_LOTKA2_OED: *nx = 9; *np = 5; return 0;
-    case CB200_MODEL_LIN1D: *nx = 1; *np = 1; return 0;
-    case CB200_MODEL_LIN1D_OED: *nx = 3; *np = 2; return 0;
-    case CB200_MODEL_DENSE20: *nx = 20; *np = 1; return 0;
-    case CB200_MODEL_EGERSTEDT: *nx = 3; *np = 3; return 0;
+    case CB200_MODEL_LOTKA3: *nx = 3; *np = 3; d = 2; break;
+    case CB200_MODEL_LQR: *nx = 2; *np = 3; d = 1; break;
+    case CB200_MODEL_LOTKA2: *nx = 2; *np = 3; d = 2; break;
+    case CB200_MODEL_LOTKA2_OED: *nx = 9; *np = 5; d = 6; break;
+    case CB200_MODEL_LIN1D: *nx = 1; *np = 1; d = 1; break;
+    case CB200_MODEL_LIN1D_OED: *nx = 3; *np = 2; d = 2; break;
+    case CB200_MODEL_DENSE20: *nx = 20; *np = 1; d = 20; break;
+    case CB200_MODEL_EGERSTEDT: *nx = 3; *np = 3; d = 2; break;
     default: return -1;
     }
+    if (nxd) *nxd = d;
+    return 0;
 }
 
 static int launch_model(int model, int G, int method, const DevLayer &L, const double *ps, long long ldb,
@@ -403,8 +406,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     *out = nullptr;
     if (d->struct_size != (int32_t)sizeof(cb200_desc))
         return fail(CB200_ERR_ARG, "cb200_desc.struct_size %d != %d", d->struct_size, (int)sizeof(cb200_desc));
-    int mnx = 0, mnp = 0;
-    if (model_dims(d->model, &mnx, &mnp)) return fail(CB200_ERR_UNSUPPORTED, "unknown model id %d", d->model);
+    int mnx = 0, mnp = 0, mnxd = 0;
+    if (model_dims(d->model, &mnx, &mnp, &mnxd)) return fail(CB200_ERR_UNSUPPORTED, "unknown model id %d", d->model);
     if (d->nx != mnx || d->np_all != mnp)
         return fail(CB200_ERR_ARG, "model %d expects nx=%d, np=%d; got nx=%d, np=%d", d->model, mnx, mnp, d->nx,
                     d->np_all);
@@ -562,38 +565,52 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     // direction tables of the sensitivity kernel: the p column every local variable perturbs and, per piece
     // and direction group, the mask of directions whose forcing term f_p / f_u is switched on
     std::vector<signed char> dir_pcol((size_t)std::max(1, L.nvars), (signed char)-1);
+    std::vector<short> dir_perm((size_t)std::max(1, L.nvars), (short)-1);
     const int Gs = h->G_sens;
     const int Rmask = Gs > 0 ? std::max(1, (h->max_ns + Gs - 1) / Gs) : 1;
     std::vector<unsigned> act_mask((size_t)po * Rmask, 0u);
     for (int i = 0; i < I; i++) {
         const int nu0 = h->h_n_u0[i], nc = h->h_n_c[i], M = h->h_M[i], pof = h->h_piece_off[i], vof = h->h_var_off[i];
+        const int nsi = h->ns[i];
         std::vector<int> crow((size_t)std::max(1, nc), -1);
         for (int j = 0; j < M; j++)
             for (int r = 0; r < nact; r++) crow[h->h_cidx[(size_t)(pof + j) * nact + r]] = r;
-        for (int dd = 0; dd < h->ns[i]; dd++) {
+        // first piece in which a direction is non-zero: u0 seeds on dynamic states and parameters from the start,
+        // a control value from the first piece that uses it, never (= M) for seeds on quadrature-like states (their
+        // sensitivity is the constant seed) and for local controls no piece refers to
+        std::vector<int> first((size_t)std::max(1, nsi), M);
+        for (int dd = 0; dd < nsi; dd++) {
             int pc = -1;
-            if (dd >= nu0 && dd < nu0 + ntp)
+            if (dd < nu0) {
+                for (int k = 0; k < nx; k++)
+                    if (h->h_ic_src[(size_t)i * nx + k] == dd && k < mnxd) first[dd] = 0;
+            } else if (dd < nu0 + ntp) {
                 pc = L.tunable_p0[dd - nu0];
-            else if (dd >= nu0 + ntp && crow[dd - nu0 - ntp] >= 0)
+                first[dd] = 0;
+            } else if (crow[dd - nu0 - ntp] >= 0) {
                 pc = L.row_to_p[crow[dd - nu0 - ntp]];
-            dir_pcol[(size_t)vof + dd] = (signed char)pc;
-            if (Gs <= 0) continue;
-            // first piece in which the direction is non-zero: u0 seeds and parameters from the start, a control
-            // value from the first piece that uses it (never: a local control no piece refers to)
-            int first = (dd < nu0 + ntp) ? 0 : M;
-            for (int j = 0; j < M && pc >= 0; j++) {
-                const bool on = (dd < nu0 + ntp) ||
-                                h->h_cidx[(size_t)(pof + j) * nact + crow[dd - nu0 - ntp]] == dd - nu0 - ntp;
-                if (on) {
-                    act_mask[(size_t)(pof + j) * Rmask + dd / Gs] |= 1u << (dd % Gs);
-                    first = std::min(first, j);
-                }
+                for (int j = M - 1; j >= 0; j--)
+                    if (h->h_cidx[(size_t)(pof + j) * nact + crow[dd - nu0 - ntp]] == dd - nu0 - ntp) first[dd] = j;
             }
-            // bits 24..31 of the word: live prefix length of the group during the piece
-            for (int j = first; j < M; j++) {
-                unsigned &w = act_mask[(size_t)(pof + j) * Rmask + dd / Gs];
-                const unsigned na = (unsigned)(dd % Gs) + 1u;
-                if ((w >> 24) < na) w = (w & 0xffffffu) | (na << 24);
+            dir_pcol[(size_t)vof + dd] = (signed char)pc;
+        }
+        std::vector<int> order((size_t)nsi);
+        for (int dd = 0; dd < nsi; dd++) order[dd] = dd;
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return first[a] < first[b]; });
+        for (int sl = 0; sl < nsi; sl++) {
+            const int dd = order[sl];
+            dir_perm[(size_t)vof + sl] = (short)dd;
+            if (Gs <= 0) continue;
+            const int pc = dir_pcol[(size_t)vof + dd];
+            for (int j = 0; j < M; j++) {
+                unsigned &w = act_mask[(size_t)(pof + j) * Rmask + sl / Gs];
+                const bool forced = pc >= 0 && ((dd < nu0 + ntp) ||
+                                    h->h_cidx[(size_t)(pof + j) * nact + crow[dd - nu0 - ntp]] == dd - nu0 - ntp);
+                if (forced) w |= 1u << (sl % Gs);
+                if (j >= first[dd]) {   // bits 24..31: live prefix length of the group during the piece
+                    const unsigned na = (unsigned)(sl % Gs) + 1u;
+                    if ((w >> 24) < na) w = (w & 0xffffffu) | (na << 24);
+                }
             }
         }
     }
@@ -708,7 +725,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
                  o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
-                 o_de = push(blob, h->defects), o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol),
+                 o_de = push(blob, h->defects), o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol), o_dperm = push(blob, dir_perm),
                  o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
                  o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos);
     std::vector<double> mdata;
@@ -769,6 +786,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.sens_off = (const long long *)(base + o_se);
     L.samp_off = (const int *)(base + o_so);
     L.dir_pcol = (const signed char *)(base + o_dp);
+    L.dir_perm = (const short *)(base + o_dperm);
     L.act_mask = (const unsigned *)(base + o_am);
     L.dpos_kind = (const int *)(base + o_dk);
     L.dpos_stage = (const int *)(base + o_dst);

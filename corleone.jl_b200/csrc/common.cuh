@@ -38,7 +38,9 @@ struct DevLayer {
     const int *samp_off;     // [I] first merged-trajectory sample of the interval
     const double *model_data;  // model constants in HBM (DENSE20: W row-major 20x20, then b[20]) or nullptr
     const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
-    const unsigned *act_mask;     // [sum M][R] bit g: direction r*G+g is forced during the piece (G = handle's group size)
+    const short *dir_perm;        // [nvars] direction held by slot s of the interval (activation order, see shoot.cuh)
+    const unsigned *act_mask;     // [sum M][R] bits 0..23: slot r*G+g is forced during the piece (G = handle's group size);
+                                  //            bits 24..31: live prefix length of the group
     // shooting defects of the boundary between interval i and i+1 (src/multiple_shooting.jl:150-163)
     const int *dpos_kind;    // [I*nx] position of the state matching of state k in shooting_constraints, -1: none
     const int *dpos_stage;   // [I*nx] same, in stage_ordered_shooting_constraints

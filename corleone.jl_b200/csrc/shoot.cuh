@@ -241,6 +241,18 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
 
     // ---- initial state: InitialConditionRemaker (src/single_shooting.jl:260-266), fixval per :359;
     //      sensitivity seeds: e_k for the u0 direction that feeds state k
+    // slot g of this thread holds direction dmap[g] of the interval: the host orders the directions by the piece
+    // in which they become non-zero (u0 seeds on dynamic states and parameters first, controls in time order,
+    // directions that never change -- seeds on quadrature-like states, unused controls -- last), so that the live
+    // directions of every piece are a prefix of the group; -1: padding
+    int dmap[G1];
+#pragma unroll
+    for (int g = 0; g < G1; g++) dmap[g] = -1;
+    if constexpr (G > 0) {
+#pragma unroll
+        for (int g = 0; g < G; g++)
+            if (d0 + g < ns) dmap[g] = (int)L.dir_perm[voff + d0 + g];
+    }
     double yd[ND], yq[NQA];
 #pragma unroll
     for (int k = 0; k < NX; k++) {
@@ -253,7 +265,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         if constexpr (G > 0) {
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                const double seed = (src >= 0 && src == d0 + g) ? 1.0 : 0.0;
+                const double seed = (src >= 0 && src == dmap[g]) ? 1.0 : 0.0;
                 if (k < NXD)
                     yd[NXD * (1 + g) + k] = seed;
                 else
@@ -268,7 +280,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
     if constexpr (G > 0) {
 #pragma unroll
         for (int g = 0; g < G; g++)
-            if (d0 + g < ns) pcol[g] = (int)L.dir_pcol[voff + d0 + g];
+            if (dmap[g] >= 0) pcol[g] = (int)L.dir_pcol[voff + dmap[g]];
     }
     // ---- parameters: p_full = A*p + B*controls_j (src/single_shooting.jl:319-323)
     double p[NP];
@@ -377,8 +389,8 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
             const long long s0 = __ldg(L.sens_off + i);
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                const int d = d0 + g;
-                if (d < ns) {
+                const int d = dmap[g];
+                if (d >= 0) {
 #pragma unroll
                     for (int k = 0; k < NX; k++) o.sens[(s0 + (long long)d * NX + k) * o.ldo + b] = CB200_SS(g, k);
                 }
@@ -393,7 +405,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
                 if (jp >= 0) {
 #pragma unroll
                     for (int g = 0; g < G; g++)
-                        if (d0 + g < ns) o.jac[(long long)(jp + d0 + g) * o.ldo + b] = CB200_SS(g, k);
+                        if (dmap[g] >= 0) o.jac[(long long)(jp + dmap[g]) * o.ldo + b] = CB200_SS(g, k);
                 }
             }
         }
@@ -403,8 +415,8 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
             const bool inc = o.obj_all || i == L.I - 1;
 #pragma unroll
             for (int g = 0; g < G; g++) {
-                const int d = d0 + g;
-                if (d < ns) {
+                const int d = dmap[g];
+                if (d >= 0) {
                     double val = 0.0;
 #pragma unroll
                     for (int k = 0; k < NX; k++) val = (inc && k == o.obj_state) ? CB200_SS(g, k) : val;
