@@ -37,7 +37,7 @@ NZ = NX * (1 + NS_DIRS)
 FLOPS_PER_UNIT = E_EVALS * (10 + 36) + M_PIECES * K_STEPS_PER_PIECE * 42 * NZ      # 8440
 #   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic (BASELINE.md formula)
 BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                                # 240
-NCU_DRAM_BYTES_PER_LAUNCH = 30308608 + 40457984   # profiles/r1_shoot_lqr_G4_fused.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 30290432 + 40308224   # profiles/r1_shoot_lqr_G4_fused.txt
 
 
 def host_threads():
@@ -388,7 +388,7 @@ def main():
                          # the 94 MB of results is still in the 126 MB L2 when the kernel ends
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
                          "algorithmic_bytes_per_launch": BYTES_PER_UNIT * I_INTERVALS * B,
-                         "kernel": "shoot_kernel<Lqr,G=4,Tsit5,uniform,4 blocks/SM> incl. fused defect/gradient epilogue",
+                         "kernel": "shoot_kernel<Lqr,G=4,Tsit5,uniform,4 blocks/SM> incl. fused defect/gradient/cons_j epilogue",
                          "kernel_ms": kern_ms,
                          "flops_per_unit": FLOPS_PER_UNIT, "bytes_per_unit": BYTES_PER_UNIT,
                          "peak_source": "FP64 probes measured in this run, max of DFMA chains "
