@@ -101,6 +101,33 @@ def egerstedt_spec():
                 tunable_ic=[], quadrature_indices=[], shooting_points=None)
 
 
+def vdp_spec(n_intervals=5, rng=None):
+    """Van der Pol with Lagrange state (lib/OptimalControlBenchmarks/src/problems/van_der_pol.jl), 40 control values"""
+    rng = np.random.default_rng(SEED0 + 8) if rng is None else rng
+    t = np.arange(40) / 4.0
+    return dict(model="vdp3", u0=[0.0, 1.0, 0.0], p0=[0.0], tspan=(0.0, 10.0),
+                controls=[(1, t, rng.uniform(-1, 1, 40))], tunable_ic=[], quadrature_indices=[3],
+                shooting_points=[10.0 * k / n_intervals for k in range(n_intervals)])
+
+
+def cartpole_spec(n_intervals=4, rng=None):
+    """cart pendulum with Lagrange state (.../cart_pendulum.jl), 32 control values on (0, 4)"""
+    rng = np.random.default_rng(SEED0 + 9) if rng is None else rng
+    t = np.arange(32) / 8.0
+    return dict(model="cartpole5", u0=[0.0, 0.0, 0.0, 0.0, 0.0], p0=[0.0], tspan=(0.0, 4.0),
+                controls=[(1, t, rng.uniform(-3, 3, 32))], tunable_ic=[], quadrature_indices=[],
+                shooting_points=[4.0 * k / n_intervals for k in range(n_intervals)])
+
+
+def rocket_spec(n_intervals=4, rng=None):
+    """Goddard rocket with free final time T as tunable parameter (.../goddarts_rocket.jl), normalised time (0, 1)"""
+    rng = np.random.default_rng(SEED0 + 10) if rng is None else rng
+    t = np.arange(20) / 20.0
+    return dict(model="rocket3", u0=[1.0, 0.0, 1.0], p0=[0.2, 0.5], tspan=(0.0, 1.0),
+                controls=[(2, t, rng.uniform(0.2, 0.8, 20))], tunable_ic=[], quadrature_indices=[],
+                shooting_points=[k / n_intervals for k in range(n_intervals)])
+
+
 def layer_from_spec(spec, alg, **kw):
     """Build the SingleShootingLayer / MultipleShootingLayer a spec describes."""
     prob = ODEProblem(spec["model"], spec["u0"], spec["tspan"], spec["p0"], model_data=spec.get("model_data"))

@@ -331,6 +331,9 @@ static int default_G(int model)
     case CB200_MODEL_LOTKA2: return 2;
     case CB200_MODEL_LIN1D: return 4;
     case CB200_MODEL_EGERSTEDT: return 2;
+    case CB200_MODEL_VDP3: return 2;
+    case CB200_MODEL_CARTPOLE5: return 1;
+    case CB200_MODEL_ROCKET3: return 2;
     case CB200_MODEL_DENSE20: return 1;
     case CB200_MODEL_LOTKA2_OED: return 1;   // second-order sensitivities of [x; G; F]: 12 dynamic + 6 quadrature per thread (G = 2 spills)
     case CB200_MODEL_LIN1D_OED: return 2;
@@ -350,6 +353,9 @@ static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
     case CB200_MODEL_LIN1D_OED: *nx = 3; *np = 2; d = 2; break;
     case CB200_MODEL_DENSE20: *nx = 20; *np = 1; d = 20; break;
     case CB200_MODEL_EGERSTEDT: *nx = 3; *np = 3; d = 2; break;
+    case CB200_MODEL_VDP3: *nx = 3; *np = 1; d = 2; break;
+    case CB200_MODEL_CARTPOLE5: *nx = 5; *np = 1; d = 4; break;
+    case CB200_MODEL_ROCKET3: *nx = 3; *np = 2; d = 3; break;
     default: return -1;
     }
     if (nxd) *nxd = d;
@@ -368,6 +374,9 @@ static int launch_model(int model, int G, int method, const DevLayer &L, const d
     case CB200_MODEL_LIN1D_OED: return launch_lin1d_oed(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_DENSE20: return launch_dense20(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_EGERSTEDT: return launch_egerstedt(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_VDP3: return launch_vdp3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_CARTPOLE5: return launch_cartpole5(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_ROCKET3: return launch_rocket3(G, method, L, ps, ldb, B, o, s);
     default: return -1000;
     }
 }
@@ -384,6 +393,9 @@ static int forward_model(int model, int method, const DevLayer &L, double *ps, l
     case CB200_MODEL_LIN1D_OED: return forward_lin1d_oed(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_DENSE20: return forward_dense20(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_EGERSTEDT: return forward_egerstedt(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_VDP3: return forward_vdp3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_CARTPOLE5: return forward_cartpole5(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_ROCKET3: return forward_rocket3(method, L, ps, ldb, B, fixed, s);
     default: return -1000;
     }
 }

@@ -105,6 +105,18 @@ int forward_lin1d_oed(int method, const DevLayer &L, double *ps, long long ldb, 
         cudaStream_t s);
 int forward_dense20(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s);
+int launch_vdp3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_vdp3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_cartpole5(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_cartpole5(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_rocket3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_rocket3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
 
 }  // namespace cb200

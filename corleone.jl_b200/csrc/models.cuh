@@ -302,4 +302,117 @@ struct Lin1dOedTraits {
 using Lotka2Oed = OedAug<Lotka2, LotkaOedTraits>;
 using Lin1dOed = OedAug<Lin1d, Lin1dOedTraits>;
 
+
+// ---- Models written once on a generic scalar: the directional derivative is taken by forward-mode AD on the
+//      device (a (value, tangent) pair through the same expression) -- what ForwardDiff does to the user's Julia
+//      closure in the reference (src/dynprob.jl:150,161).  Adding a model of lib/OptimalControlBenchmarks is one
+//      struct with a templated rhs.
+struct Dual {
+    double v, d;
+};
+CB_DEV Dual operator+(Dual a, Dual b) { return {a.v + b.v, a.d + b.d}; }
+CB_DEV Dual operator-(Dual a, Dual b) { return {a.v - b.v, a.d - b.d}; }
+CB_DEV Dual operator-(Dual a) { return {-a.v, -a.d}; }
+CB_DEV Dual operator*(Dual a, Dual b) { return {a.v * b.v, fma(a.d, b.v, a.v * b.d)}; }
+CB_DEV Dual operator/(Dual a, Dual b)
+{
+    const double q = a.v / b.v;
+    return {q, (a.d - q * b.d) / b.v};
+}
+CB_DEV Dual operator+(Dual a, double c) { return {a.v + c, a.d}; }
+CB_DEV Dual operator+(double c, Dual a) { return {a.v + c, a.d}; }
+CB_DEV Dual operator-(Dual a, double c) { return {a.v - c, a.d}; }
+CB_DEV Dual operator-(double c, Dual a) { return {c - a.v, -a.d}; }
+CB_DEV Dual operator*(Dual a, double c) { return {a.v * c, a.d * c}; }
+CB_DEV Dual operator*(double c, Dual a) { return {a.v * c, a.d * c}; }
+CB_DEV Dual operator/(Dual a, double c) { return {a.v / c, a.d / c}; }
+CB_DEV Dual operator/(double c, Dual b)
+{
+    const double q = c / b.v;
+    return {q, -q * b.d / b.v};
+}
+CB_DEV double sin(double a) { return ::sin(a); }   // the Dual overloads below would hide the global ones
+CB_DEV double cos(double a) { return ::cos(a); }
+CB_DEV double exp(double a) { return ::exp(a); }
+CB_DEV Dual sin(Dual a) { return {::sin(a.v), ::cos(a.v) * a.d}; }
+CB_DEV Dual cos(Dual a) { return {::cos(a.v), -::sin(a.v) * a.d}; }
+CB_DEV Dual exp(Dual a)
+{
+    const double e = ::exp(a.v);
+    return {e, e * a.d};
+}
+
+template <class M>
+struct AutoJvp {
+    static constexpr int NX = M::NX, NXD = M::NXD, NQ = M::NQ, NP = M::NP;
+    static constexpr bool HAS_JVP = true;
+    struct Ctx {};
+    struct Force {
+        int pcol;
+    };
+    CB_DEV void f(const double *x, const double *p, double *dx, Ctx &) { M::template rhs<double>(x, p, dx); }
+    CB_DEV Force make_force(int pcol, const double *) { return Force{pcol}; }
+    CB_DEV void jvp(const double *x, const double *p, const Ctx &, const double *v, const Force &F, double *dv)
+    {
+        Dual xd[NXD], pd[NP], out[NX];
+#pragma unroll
+        for (int k = 0; k < NXD; k++) xd[k] = Dual{x[k], v[k]};
+#pragma unroll
+        for (int q = 0; q < NP; q++) pd[q] = Dual{p[q], q == F.pcol ? 1.0 : 0.0};
+        M::template rhs<Dual>(xd, pd, out);
+#pragma unroll
+        for (int k = 0; k < NX; k++) dv[k] = out[k].d;
+    }
+};
+
+// Van der Pol oscillator with its Lagrange term (lib/OptimalControlBenchmarks/src/problems/van_der_pol.jl:16-33)
+struct VdpRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = (1.0 - x[1] * x[1]) * x[0] - x[1] + p[0];
+        dx[1] = x[0];
+        dx[2] = x[0] * x[0] + x[1] * x[1] + p[0] * p[0];
+    }
+};
+using Vdp3 = AutoJvp<VdpRhs>;
+
+// Cart pendulum with its Lagrange term (lib/OptimalControlBenchmarks/src/problems/cart_pendulum.jl:17-48);
+// states (x, theta, dx, dtheta, cost), p = (w).  The two denominators differ in the reference and are kept so.
+struct CartPoleRhs {
+    static constexpr int NX = 5, NXD = 4, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double al = 10.0, be = 50.0, ga = 0.5, M = 1.0, m = 0.1, g = 9.81, pi = 3.141592653589793;
+        const T s = sin(x[1]), c = cos(x[1]);
+        const T num = p[0] + (m * g) * s * c + m * (x[3] * x[3]) * s;
+        const T omc = 1.0 - c;
+        dx[0] = x[2];
+        dx[1] = x[3];
+        dx[2] = num / (M + m * (omc * omc));
+        dx[3] = -g * s - (num / (M + m * (1.0 - c * c))) * c;
+        const T dth = x[1] - pi;
+        dx[4] = 1.0e-3 * (al * (x[0] * x[0]) + be * (dth * dth) + ga * (p[0] * p[0]));
+    }
+};
+using CartPole5 = AutoJvp<CartPoleRhs>;
+
+// Goddard rocket with free final time (lib/OptimalControlBenchmarks/src/problems/goddarts_rocket.jl:16-40);
+// states (r, v, m), p = (T, u)
+struct RocketRhs {
+    static constexpr int NX = 3, NXD = 3, NQ = 0, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double b = 7.0, Tmax = 3.5, A = 310.0, k = 500.0, r0 = 1.0;
+        const T drag = A * (x[1] * x[1]) * exp(-k * (x[0] - r0));
+        dx[0] = p[0] * x[1];
+        dx[1] = p[0] * (-1.0 / (x[0] * x[0]) + (1.0 / x[2]) * (Tmax * p[1] - drag));
+        dx[2] = p[0] * (-b * p[1]);
+    }
+};
+using Rocket3 = AutoJvp<RocketRhs>;
+
 }  // namespace cb200

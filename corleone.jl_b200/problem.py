@@ -21,6 +21,9 @@ MODEL_REGISTRY = {
     "lin1d_oed": (5, 3, 2),
     "dense20": (6, 20, 1),
     "egerstedt": (7, 3, 3),
+    "vdp3": (8, 3, 1),
+    "cartpole5": (9, 5, 1),
+    "rocket3": (10, 3, 2),
 }
 
 # base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)

@@ -56,7 +56,11 @@ typedef enum {
     CB200_MODEL_LIN1D = 4,      /* lib/CorleoneOED/test/core/1d_oed.jl:11-13 */
     CB200_MODEL_LIN1D_OED = 5,
     CB200_MODEL_DENSE20 = 6,    /* synthetic BASELINE config 4: x' = W x - x^3 + b u */
-    CB200_MODEL_EGERSTEDT = 7   /* test/core/local_controls.jl:46-52 */
+    CB200_MODEL_EGERSTEDT = 7,  /* test/core/local_controls.jl:46-52 */
+    /* lib/OptimalControlBenchmarks/src/problems: right-hand sides with their Lagrange term as last state */
+    CB200_MODEL_VDP3 = 8,       /* van_der_pol.jl:16-33 */
+    CB200_MODEL_CARTPOLE5 = 9,  /* cart_pendulum.jl:17-48 */
+    CB200_MODEL_ROCKET3 = 10    /* goddarts_rocket.jl:16-40, p = (T, u) */
 } cb200_model;
 
 typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;

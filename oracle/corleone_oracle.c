@@ -74,6 +74,36 @@ static inline dual daddc(dual a, double c)
     return a;
 }
 static inline dual dneg(dual a) { return dscale(a, -1.0); }
+static inline dual ddiv(dual a, dual b)
+{
+    dual r;
+    r.v = a.v / b.v;
+    for (int k = 0; k < g_nd; k++) r.d[k] = (a.d[k] - r.v * b.d[k]) / b.v;
+    return r;
+}
+static inline dual dsin(dual a)
+{
+    dual r;
+    const double c = cos(a.v);
+    r.v = sin(a.v);
+    for (int k = 0; k < g_nd; k++) r.d[k] = c * a.d[k];
+    return r;
+}
+static inline dual dcos(dual a)
+{
+    dual r;
+    const double s = sin(a.v);
+    r.v = cos(a.v);
+    for (int k = 0; k < g_nd; k++) r.d[k] = -s * a.d[k];
+    return r;
+}
+static inline dual dexp(dual a)
+{
+    dual r;
+    r.v = exp(a.v);
+    for (int k = 0; k < g_nd; k++) r.d[k] = r.v * a.d[k];
+    return r;
+}
 /* r += c * a */
 static inline void daxpy(dual *r, double c, const dual *a)
 {
@@ -161,6 +191,41 @@ static void rhs_dense20(const dual *x, const dual *p, dual *du, const double *da
  *   F'     = sum_i w_i (h_x[i,:] G)' (h_x[i,:] G), upper triangle                  (:222-233)
  * observed = leading nobs states (u[1:2] for Lotka, [u[1]] for the 1-D problem), so h_x rows are unit rows.
  */
+/* lib/OptimalControlBenchmarks/src/problems/van_der_pol.jl:16-33, Lagrange term as third state; p = (u) */
+static void rhs_vdp3(const dual *x, const dual *p, dual *du)
+{
+    dual one_m = dsub(dconst(1.0), dmul(x[1], x[1]));
+    du[0] = dadd(dsub(dmul(one_m, x[0]), x[1]), p[0]);
+    du[1] = x[0];
+    du[2] = dadd(dadd(dmul(x[0], x[0]), dmul(x[1], x[1])), dmul(p[0], p[0]));
+}
+/* cart_pendulum.jl:17-48: states (x, theta, dx, dtheta, cost), p = (w); the two denominators differ in the reference */
+static void rhs_cartpole5(const dual *x, const dual *p, dual *du)
+{
+    const double al = 10.0, be = 50.0, ga = 0.5, M = 1.0, m = 0.1, g = 9.81, pi = 3.141592653589793;
+    dual s = dsin(x[1]), c = dcos(x[1]);
+    dual num = dadd(dadd(p[0], dscale(dmul(s, c), m * g)), dscale(dmul(dmul(x[3], x[3]), s), m));
+    dual omc = dsub(dconst(1.0), c);
+    du[0] = x[2];
+    du[1] = x[3];
+    du[2] = ddiv(num, daddc(dscale(dmul(omc, omc), m), M));
+    dual den2 = daddc(dscale(dsub(dconst(1.0), dmul(c, c)), m), M);
+    du[3] = dsub(dscale(s, -g), dmul(ddiv(num, den2), c));
+    dual dth = daddc(x[1], -pi);
+    du[4] = dscale(dadd(dadd(dscale(dmul(x[0], x[0]), al), dscale(dmul(dth, dth), be)), dscale(dmul(p[0], p[0]), ga)), 1.0e-3);
+}
+/* goddarts_rocket.jl:16-40: states (r, v, m), p = (T, u) */
+static void rhs_rocket3(const dual *x, const dual *p, dual *du)
+{
+    const double b = 7.0, Tmax = 3.5, A = 310.0, k = 500.0, r0 = 1.0;
+    dual drag = dmul(dscale(dmul(x[1], x[1]), A), dexp(dscale(daddc(x[0], -r0), -k)));
+    du[0] = dmul(p[0], x[1]);
+    dual grav = ddiv(dconst(-1.0), dmul(x[0], x[0]));
+    dual thrust = dmul(ddiv(dconst(1.0), x[2]), dsub(dscale(p[1], Tmax), drag));
+    du[1] = dmul(p[0], dadd(grav, thrust));
+    du[2] = dmul(p[0], dscale(p[1], -b));
+}
+
 typedef void (*rhs_fn)(const dual *, const dual *, dual *);
 typedef void (*jac_fn)(const dual *, const dual *, dual *, dual *);
 static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, const dual *u, const dual *p,
@@ -199,6 +264,9 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_LIN1D_OED: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, u, p, du); break;
     case CO_DENSE20: rhs_dense20(u, p, du, m->data); break;
     case CO_EGERSTEDT: rhs_egerstedt(u, p, du); break;
+    case CO_VDP3: rhs_vdp3(u, p, du); break;
+    case CO_CARTPOLE5: rhs_cartpole5(u, p, du); break;
+    case CO_ROCKET3: rhs_rocket3(u, p, du); break;
     default: break;
     }
 }

@@ -40,7 +40,10 @@ enum co_model {
     CO_LIN1D = 4,       /* lib/CorleoneOED/test/core/1d_oed.jl:11-13 */
     CO_LIN1D_OED = 5,   /* augmentation of CO_LIN1D, params=[1], observed=[u[1]] */
     CO_DENSE20 = 6,     /* synthetic BASELINE config 4: x' = W x - x^3 + b u */
-    CO_EGERSTEDT = 7    /* test/core/local_controls.jl:46-52 */
+    CO_EGERSTEDT = 7,   /* test/core/local_controls.jl:46-52 */
+    CO_VDP3 = 8,        /* lib/OptimalControlBenchmarks/src/problems/van_der_pol.jl:16-33 (+ Lagrange state) */
+    CO_CARTPOLE5 = 9,   /* .../cart_pendulum.jl:17-48 (+ Lagrange state) */
+    CO_ROCKET3 = 10     /* .../goddarts_rocket.jl:16-40, p = (T, u) */
 };
 
 enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };

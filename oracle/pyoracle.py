@@ -23,6 +23,9 @@ MODELS = {
     "lin1d_oed": 5,
     "dense20": 6,
     "egerstedt": 7,
+    "vdp3": 8,
+    "cartpole5": 9,
+    "rocket3": 10,
 }
 METHODS = {"tsit5": 0, "rk4": 1}
 CO_ND = 16

@@ -14,9 +14,15 @@ RTOL = 1e-10
 
 
 def rel_err(a, b):
+    """max |a - b| / max(1, max |b|); non-finite entries must coincide (inf where they do not: never swallowed)"""
     a, b = np.asarray(a, float), np.asarray(b, float)
-    scale = max(1.0, float(np.max(np.abs(b))) if b.size else 1.0)
-    return float(np.max(np.abs(a - b))) / scale if a.size else 0.0
+    if not a.size:
+        return 0.0
+    fa, fb = np.isfinite(a), np.isfinite(b)
+    if not np.array_equal(fa, fb) or not fa.all():
+        return float("inf")
+    scale = max(1.0, float(np.max(np.abs(b))))
+    return float(np.max(np.abs(a - b))) / scale
 
 
 def batch_ps(layer_o, B, rng, scale=0.05):
@@ -364,3 +370,18 @@ def test_oed_criteria_gradient_vs_finite_differences():
         cm, _ = cb.batched_criteria(N, pm, fim_init=Finit)
         fd = (cp - cm) / (2 * h)
         assert np.allclose(g[:, :, v], fd, rtol=2e-6, atol=1e-7), (v, g[:, :, v], fd)
+
+
+@pytest.mark.parametrize("name", ["vdp", "cartpole", "rocket"])
+def test_benchmark_suite_models_forward_mode_ad(name):
+    """right-hand sides of lib/OptimalControlBenchmarks written once on a generic scalar; the kernels take the
+    directional derivatives by forward-mode AD on the device (sin, cos, exp, division covered)"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(47)
+    spec, row, scale = {"vdp": (P.vdp_spec(5, rng), 3, 0.05), "cartpole": (P.cartpole_spec(4, rng), 5, 0.05),
+                        "rocket": (P.rocket_spec(4, rng), 3, 0.001)}[name]
+    from oracle import pyoracle as po
+    O = po.OracleLayer(spec)
+    ps = O.default_ps()[None, :] + scale * rng.standard_normal((33, O.nvars))
+    assert_ok(full_compare(spec, cb.Tsit5(3), 33, rng, objective_row=row, ps=ps))
+    assert_ok(full_compare(spec, cb.RK4(4), 3, rng, objective_row=row, ps=ps[:3]))
