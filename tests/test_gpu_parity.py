@@ -384,3 +384,47 @@ def test_benchmark_suite_models_forward_mode_ad(name):
     ps = O.default_ps()[None, :] + scale * rng.standard_normal((33, O.nvars))
     assert_ok(full_compare(spec, cb.Tsit5(3), 33, rng, objective_row=row, ps=ps))
     assert_ok(full_compare(spec, cb.RK4(4), 3, rng, objective_row=row, ps=ps[:3]))
+
+
+def test_every_memory_layout_of_cb200_eval_agrees():
+    """host candidate-major (chunked, multi-stream; last chunk partial), host variable-major, device candidate-major
+    and device variable-major calls give bit-identical results"""
+    torch = pytest.importorskip("torch")
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    rng = np.random.default_rng(53)
+    spec = P.lqr_spec(12, rng)
+    lay = P.product_layer(spec, cb.Tsit5(2))
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    B, nvars = 1500, N.nvars
+    ps = cb.to_vec(ps_t)[None, :] + 0.1 * rng.standard_normal((B, nvars))
+    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_JAC
+    fields = ("xend", "sens", "defects_kind", "defects_stage", "objective", "grad", "jac_vals")
+    ref = N.eval_host(ps, want, objective_row=2)                                   # host, candidate-major, 6 chunks
+    sz = N.out_sizes()
+    # host, variable-major in and out
+    ps_soa = np.ascontiguousarray(ps.T)
+    out = {f: np.empty((sz[f], B)) for f in fields}
+    N.eval_raw(ps_soa.ctypes.data, B, B, want, nat.PS_SOA | nat.OUT_SOA, {f: out[f].ctypes.data for f in fields}, 2)
+    for f in fields:
+        assert np.array_equal(out[f].T, ref[f]), ("host soa", f)
+    dev = torch.device("cuda:0")
+    N.set_stream(torch.cuda.current_stream().cuda_stream)
+    # device, candidate-major in and out (Julia CuArray-style nvars x B matrices)
+    d_ps = torch.from_numpy(ps).to(dev)
+    d_out = {f: torch.empty((B, sz[f]), dtype=torch.float64, device=dev) for f in fields}
+    N.eval_raw(d_ps.data_ptr(), B, nvars, want, nat.MEM_DEVICE, {f: d_out[f].data_ptr() for f in fields}, 2)
+    torch.cuda.synchronize()
+    for f in fields:
+        assert np.array_equal(d_out[f].cpu().numpy(), ref[f]), ("device candidate-major", f)
+    # device, variable-major with a padded leading dimension
+    ldb = B + 12
+    d_pad = torch.zeros((nvars, ldb), dtype=torch.float64, device=dev)
+    d_pad[:, :B] = torch.from_numpy(ps_soa).to(dev)
+    d_o2 = {f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields}
+    N.eval_raw(d_pad.data_ptr(), B, ldb, want, nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA,
+               {f: d_o2[f].data_ptr() for f in fields}, 2)
+    torch.cuda.synchronize()
+    for f in fields:
+        assert np.array_equal(d_o2[f].cpu().numpy().T, ref[f]), ("device soa", f)
