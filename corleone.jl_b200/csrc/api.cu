@@ -1122,8 +1122,12 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             shared.gsum = pl.gsum ? base + 1 : nullptr;
             shared.fsum = pl.fsum ? base + 1 + nvars : nullptr;
         }
-        if (shared.osum) CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double), h->stream));
-        if (shared.gsum) CUDA_TRY(cudaMemsetAsync(shared.gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
+        if (shared.osum && shared.gsum == shared.osum + 1) {   // one accumulator block [objective | gradient]: one memset
+            CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double) * (size_t)(nvars + 1), h->stream));
+        } else {
+            if (shared.osum) CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double), h->stream));
+            if (shared.gsum) CUDA_TRY(cudaMemsetAsync(shared.gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
+        }
         if (shared.fsum) CUDA_TRY(cudaMemsetAsync(shared.fsum, 0, sizeof(double) * n2, h->stream));
         if (out->fim_init && (pl.fim || pl.fsum || pl.crit)) {
             if (h->ws_finit.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
