@@ -70,3 +70,30 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.lower() or f == "configs.py", f"{f} mentions the oracle"
+
+
+def _build_c_client(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "cabi_lin1d")
+    libdir = os.path.join(ROOT, "corleone.jl_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-O2", "-I", os.path.join(ROOT, "include"),
+                           os.path.join(ROOT, "tests", "c", "cabi_lin1d.c"), "-o", exe, "-L", libdir,
+                           "-lcorleone_b200", "-lm", f"-Wl,-rpath,{libdir}"])
+    return subprocess.run([exe], capture_output=True, text=True, timeout=120)
+
+
+def test_plain_c_client_compiles_and_fails_loudly_without_gpu(tmp_path):
+    """the header is plain C99; tests/c/cabi_lin1d.c links against the library alone.  Without a device the
+    program must stop at cb200_create with the no-fallback message (exit code 2), never compute on the CPU."""
+    res = _build_c_client(tmp_path)
+    assert res.returncode in (0, 2), res.stdout + res.stderr
+    if res.returncode == 2:
+        assert "no CPU fallback" in res.stderr
+
+
+@pytest.mark.gpu
+def test_plain_c_client(tmp_path):
+    """tests/c/cabi_lin1d.c: a C program with nothing but the header and the shared library (what a ccall sees)"""
+    res = _build_c_client(tmp_path)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "cabi_lin1d ok" in res.stdout
