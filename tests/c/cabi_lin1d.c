@@ -2,7 +2,7 @@
  * Plain-C client of libcorleone_b200.so: no Python, no torch -- the boundary as a Julia `ccall` (or any FFI) sees it.
  *
  * Problem: lib/CorleoneOED/test/core/1d_oed.jl:11-13  x' = p x, x(0) = 1, p tunable (default -2), tspan (0, 1),
- * single shooting without controls, RK4 with 64 steps.  Closed form: x(1) = exp(p), dx(1)/dp = exp(p).
+ * single shooting without controls, Tsit5 with 64 fixed steps.  Closed form: x(1) = exp(p), dx(1)/dp = exp(p).
  * The descriptor is filled by hand exactly as LuxCore.initialstates would produce it (Int64, 1-based).
  *
  *   gcc -O2 -I include tests/c/cabi_lin1d.c -o /tmp/cabi_lin1d -L corleone.jl_b200 -lcorleone_b200 -lm
@@ -19,7 +19,7 @@ int main(void)
     memset(&d, 0, sizeof d);
     d.struct_size = (int32_t)sizeof d;
     d.model = CB200_MODEL_LIN1D;
-    d.method = CB200_RK4;
+    d.method = CB200_TSIT5;
     d.steps_per_piece = 64;
     d.nx = 1;
     d.np_all = 1;
@@ -97,6 +97,6 @@ int main(void)
     out.objective_row = 7;
     if (cb200_eval(h, ps, B, 1, CB200_WANT_OBJ, 0, &out) != CB200_ERR_ARG || strlen(cb200_last_error()) == 0) return 6;
     cb200_destroy(h);
-    printf("cabi_lin1d ok: version %d, max relative error vs exp(p) %.3e (RK4, 64 steps)\n", cb200_version(), worst);
+    printf("cabi_lin1d ok: version %d, max relative error vs exp(p) %.3e (Tsit5, 64 steps)\n", cb200_version(), worst);
     return worst < 1e-9 ? 0 : 1;
 }

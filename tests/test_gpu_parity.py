@@ -428,3 +428,41 @@ def test_every_memory_layout_of_cb200_eval_agrees():
     torch.cuda.synchronize()
     for f in fields:
         assert np.array_equal(d_o2[f].cpu().numpy().T, ref[f]), ("device soa", f)
+
+
+def test_reference_goldens_through_the_device_path():
+    """the reference's own golden values (adaptive Tsit5) reproduced by the CUDA path at converged fixed steps:
+    G4 hybrid/forward node (test/core/multiple_shooting.jl:202-222, atol 1e-10), G3 single-shooting objective
+    (test/examples/lotka_oc.jl:80), G7 A-criterion single / multiple shooting (lib/CorleoneOED/test/core/lotka_oed.jl:124),
+    G9 analytic 1-D OED (lib/CorleoneOED/test/core/1d_oed.jl:11-31)"""
+    import json
+    import os
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    g = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_goldens.json")))
+    # G4: custom node on interval 2, forward sweep with fixed_indices = [2, 4]
+    lay = P.product_layer(P.lotka_spec(), cb.Tsit5(8))
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    blocks = N.block_structure()
+    ps = cb.to_vec(ps_t)
+    ps[blocks[1]:blocks[1] + 3] = [0.5, 3.0, -5.0]
+    out = N.forward_init(ps[None, :], fixed_indices=(2, 4))[0]
+    assert np.allclose(out[blocks[2]:blocks[2] + 3], g["G4_hybrid_forward_node"]["values"], atol=1e-10, rtol=0)
+    assert np.array_equal(out[blocks[3]:blocks[3] + 3], [0.5, 0.7, 0.0])
+    # G3: single-shooting objective at the initial point
+    lay = P.product_layer(P.lotka_spec(shooting_points=None), cb.Tsit5(4))
+    ps_t, st = cb.setup(None, lay)
+    r = lay._native(st, ps_t).eval_host(cb.to_vec(ps_t)[None, :], nat.WANT_OBJ, objective_row=3)
+    assert abs(r["objective"][0, 0] - g["G3_lotka_ss_objective"]["value"]) < 1e-9
+    # G7: A-criterion at the initial point
+    for sp, key, tol in ((None, "single_shooting", 1.5e-8), ([0.0, 3.0, 6.0, 9.0], "multiple_shooting", 2e-7)):
+        lay, ps_t, st, N = P.native_from_spec(P.lotka_oed_spec(shooting_points=sp), cb.Tsit5(8))
+        crit, F = cb.batched_criteria(N, cb.to_vec(ps_t)[None, :])
+        assert abs(crit[0, 0] / g["G7_oed_A_criterion"][key] - 1) < tol
+    # G9: x' = p x, p = -2: F = int_0^1 t^2 e^{2 p t} dt
+    lay, ps_t, st, N = P.native_from_spec(P.lin1d_oed_spec(), cb.Tsit5(4))
+    r = N.eval_host(cb.to_vec(ps_t)[None, :], nat.WANT_FIM | nat.WANT_XEND)
+    p = -2.0
+    F_exact = (np.exp(2 * p) * (2 * p * p - 2 * p + 1) - 1) / (4 * p ** 3)
+    assert abs(r["fim"][0, 0] - F_exact) < 1e-10 and abs(r["xend"][0, 0] - np.exp(p)) < 1e-12
