@@ -163,3 +163,43 @@ def test_tsit5_order_conditions_and_convergence():
         e1 = np.abs(L.eval(ps, method=method, K=1)["last"][:3] - ref[:3]).max()
         e2 = np.abs(L.eval(ps, method=method, K=2)["last"][:3] - ref[:3]).max()
         assert order - 0.8 < math.log2(e1 / e2) < order + 1.5, (method, e1, e2)
+
+
+def test_fp64_oracle_vs_extended_precision_restatement():
+    """An independent restatement of the same fixed-step Tsit5 piece loop in 40-digit arithmetic (mpmath): the FP64
+    oracle agrees to rounding (<= 1e-13 relative), so differences at the 1e-10 parity tolerance are never rounding."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    A = [[], ["0.161"], ["-0.008480655492356989", "0.335480655492357"],
+         ["2.8971530571054935", "-6.359448489975075", "4.3622954328695815"],
+         ["5.325864828439257", "-11.748883564062828", "7.4955393428898365", "-0.09249506636175525"],
+         ["5.86145544294642", "-12.92096931784711", "8.159367898576159", "-0.071584973281401", "-0.028269050394068383"],
+         ["0.09646076681806523", "0.01", "0.4798896504144996", "1.379008574103742", "-3.290069515436081", "2.324710524099774"]]
+    A = [[mp.mpf(float(x)) for x in row] for row in A]   # the tableau as the FP64 constants both codes use
+
+    rng = np.random.default_rng(5)
+    ctrl = rng.uniform(0, 1, 120)
+    spec = P.lotka_spec(controls=ctrl)
+    L = po.OracleLayer(spec)
+    K = 3
+    r = L.eval(L.default_ps(), K=K)
+    # interval 1: (0, 3), 30 pieces of 0.1 with controls ctrl[0:30], from u0 = [0.5, 0.7, 0]
+    x = [mp.mpf("0.5"), mp.mpf("0.7"), mp.mpf(0)]
+    grid = [mp.mpf(float(k / 10.0)) for k in range(31)]
+    for j in range(30):
+        h = (grid[j + 1] - grid[j]) / K
+        u = mp.mpf(float(ctrl[j]))
+        # 0.4 and 0.2 enter the FP64 code as FP64 constants
+        def ff(y, u=u):
+            x12 = y[0] * y[1]
+            return [y[0] - x12 - mp.mpf(0.4) * u * y[0], -y[1] + x12 - mp.mpf(0.2) * u * y[1],
+                    (y[0] - 1) ** 2 + (y[1] - 1) ** 2]
+        for _ in range(K):
+            ks = [ff(x)]
+            for s in range(1, 6):
+                y = [x[c] + h * sum(A[s][m] * ks[m][c] for m in range(s)) for c in range(3)]
+                ks.append(ff(y))
+            x = [x[c] + h * sum(A[6][m] * ks[m][c] for m in range(6)) for c in range(3)]
+    ref = np.array([float(v) for v in x])
+    got = r["xend"][:, 0]
+    assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-13
