@@ -40,13 +40,36 @@ BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                           
 NCU_DRAM_BYTES_PER_LAUNCH = 30290432 + 40308224   # profiles/r1_shoot_lqr_G4_fused.txt
 
 
+try:
+    ORIG_AFFINITY = os.sched_getaffinity(0)      # before bind_to_gpu_numa_node narrows it
+except AttributeError:
+    ORIG_AFFINITY = None
+
+
 def host_threads():
     """Threads for the CPU arms: every core this process may run on (torchrun exports OMP_NUM_THREADS=1, which
     would otherwise make the reference arm single-threaded)."""
+    if ORIG_AFFINITY is not None:
+        return max(1, len(ORIG_AFFINITY))
+    return max(1, os.cpu_count() or 1)
+
+
+def bind_to_gpu_numa_node(index):
+    """Run this rank on the CPU cores next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is
+    allocated: the e2e arm moves 117 MB per step over PCIe, and first-touch places the buffers on the local node."""
     try:
-        return max(1, len(os.sched_getaffinity(0)))
-    except AttributeError:
-        return max(1, os.cpu_count() or 1)
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        cpus = (cpus & allowed) or allowed
+        os.sched_setaffinity(0, cpus)
+        return len(cpus)
+    except Exception:
+        return 0
 
 
 def load_peaks():
@@ -135,6 +158,8 @@ def cpu_baseline(spec, ps, seconds_target=12.0, nthreads=0):
     """The oracle port timed on the host cores on a bounded sample of the same workload (~seconds_target of
     CPU work: whole passes over the batch, repeated)."""
     from oracle import pyoracle as po
+    if ORIG_AFFINITY is not None:
+        os.sched_setaffinity(0, ORIG_AFFINITY)   # the CPU arm gets every core again, not only the GPU's NUMA node
     O = po.OracleLayer(spec)
     nthreads = nthreads or host_threads()
     O.bench_units(ps[:64], K=K_STEPS_PER_PIECE, with_sens=True, nthreads=nthreads)          # warm-up (threads, caches)
@@ -218,6 +243,7 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
