@@ -304,7 +304,6 @@ struct cb200_handle {
     int fim_off = -1, fim_n = 0;
     int G_sens = 2;                   // sensitivity directions per thread
     void *tables = nullptr;           // one device allocation holding every table
-    DefectEntry *d_defects = nullptr;
     int *d_quad = nullptr;
     GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row
     int grad_cap = 0;
@@ -318,7 +317,7 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_fsum, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small;
     static constexpr size_t PIN_BYTES = 1 << 20;   // pinned host mirror of small evaluations
     void *pin = nullptr;
 };
@@ -737,7 +736,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
                  o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
-                 o_de = push(blob, h->defects), o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol), o_dperm = push(blob, dir_perm),
+                 o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol), o_dperm = push(blob, dir_perm),
                  o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
                  o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos);
     std::vector<double> mdata;
@@ -806,7 +805,6 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.oth = (const MatchEntry *)(base + o_ot);
     L.jpos = (const int *)(base + o_jp);
     L.model_data = mdata.empty() ? nullptr : (const double *)(base + o_md);
-    h->d_defects = (DefectEntry *)(base + o_de);
     h->d_quad = (int *)(base + o_q);
     h->d_grad = (GradEntry *)(base + o_gr);
 
@@ -845,7 +843,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_fsum, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small})
+                      &h->ws_grad, &h->ws_fim, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small})
         b->release();
     if (h->tables) cudaFree(h->tables);
     if (h->pin) cudaFreeHost(h->pin);
