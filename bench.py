@@ -9,7 +9,8 @@ intervals x 4096 candidates, Tsit5 with 2 fixed steps per control piece (M = 4 p
 forward sensitivities (ns = 8 directions per interval).  One unit = one (interval, candidate) system.
 A step = one pass of the hot path over the batch: integration + sensitivities of every unit, delivered as what
 the reference's NLP callbacks consume (src/dynprob.jl:68-73,105-131,143-164): objective f, gradient grad f,
-shooting constraints c (kind-major, the order dynprob uses) and the nonzeros of the constraint Jacobian cons_j.  Weak scaling: every rank owns B candidates;
+shooting constraints c (kind-major, the order dynprob uses) and the nonzeros of the constraint Jacobian cons_j
+(grad f without its structural zeros: the objective state of the last interval depends on that interval's block only).  Weak scaling: every rank owns B candidates;
 only the cross-candidate sums (objective, gradient) are all-reduced (DESIGN.md "multi-GPU").
 """
 import argparse
@@ -262,7 +263,8 @@ def main():
 
     # ---- device-resident arm: rotate over buffer sets whose total footprint exceeds L2 (126 MB)
     sz = N.out_sizes()
-    fields = ("jac_vals", "defects_kind", "objective", "grad")   # cons_j, c, f, grad f
+    fields = ("jac_vals", "defects_kind", "objective", "grad_compact")   # cons_j, c, f, grad f (structural zeros omitted)
+    sz["grad_compact"] = N.grad_structure(OBJECTIVE_ROW)[1]
     set_bytes = 8 * B * (nvars + sum(sz[f] for f in fields))
     nsets = max(2, int(np.ceil(3 * 126e6 / set_bytes)))
     d_ps, d_out, d_sums = [], [], []
@@ -270,7 +272,8 @@ def main():
         d_ps.append(torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev))   # [nvars, B] SoA
         d_out.append({f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields})
         d_sums.append(torch.zeros(nvars + 1, dtype=torch.float64, device=dev))
-    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    # WANT_GRAD stays set for the cross-candidate gradient sum (grad_sum); the per-candidate gradient is delivered compact
+    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_GRAD_COMPACT
     flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
 
     def step(s, comm=True):

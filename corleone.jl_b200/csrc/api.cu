@@ -317,7 +317,7 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small, ws_gradc;
     static constexpr size_t PIN_BYTES = 1 << 20;   // pinned host mirror of small evaluations
     void *pin = nullptr;
 };
@@ -843,7 +843,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small})
+                      &h->ws_grad, &h->ws_fim, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small, &h->ws_gradc})
         b->release();
     if (h->tables) cudaFree(h->tables);
     if (h->pin) cudaFreeHost(h->pin);
@@ -910,6 +910,21 @@ extern "C" int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t
     return CB200_OK;
 }
 
+// Variables the objective row depends on: the contiguous range [first, first + n) of the flat ps vector (1-based
+// `first` as Julia indexes): every variable for a quadrature row (it sums over the intervals), the last interval's
+// block for any other state row.  Returns n, or a negative status.
+extern "C" int64_t cb200_grad_structure(const cb200_handle *h, int32_t objective_row, int64_t *first)
+{
+    if (!h) return fail(CB200_ERR_ARG, "null handle");
+    const int nx = h->L.nx, I = h->L.I;
+    if (objective_row < 1 || objective_row > nx) return fail(CB200_ERR_ARG, "objective_row is not a state row");
+    bool quad = false;
+    for (int q : h->quad0) quad |= (q == objective_row - 1);
+    const int f0 = quad ? 0 : h->h_var_off[I - 1];
+    if (first) *first = f0 + 1;
+    return h->L.nvars - f0;
+}
+
 extern "C" float cb200_last_kernel_ms(const cb200_handle *h)
 {
     float ms = -1.0f;
@@ -951,7 +966,8 @@ static int transpose(cb200_handle *h, cudaStream_t st, const double *in, long lo
 
 // what one evaluation produces, resolved from (want, out)
 struct EvalPlan {
-    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum, jac, crit;
+    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum, jac, crit, gradc;
+    int gradc_first, gradc_n;   // compact gradient: variables [gradc_first, gradc_first + gradc_n)
     bool fused_grad, need_sens, need_xend;
     int obj_state, obj_ctrl_var, obj_quad, objective_row;
 };
@@ -959,7 +975,7 @@ struct EvalPlan {
 // device SoA buffers of one batch (or one chunk of it), leading dimension = its candidate count
 struct DevSet {
     double *xend = nullptr, *sens = nullptr, *traj = nullptr, *dk = nullptr, *ds = nullptr, *obj = nullptr,
-           *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr;
+           *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr, *gradc = nullptr;
     int *status = nullptr;      // [B] of the batch / chunk
     double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // shared by all chunks (atomic accumulation)
     const double *finit = nullptr;
@@ -990,6 +1006,8 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     so.dst = ndef > 0 ? d.ds : nullptr;
     so.objq = d.objq;
     so.grad = pl.fused_grad ? d.grad : nullptr;
+    so.gradc = d.gradc;
+    so.gradc_first = pl.gradc_first;
     so.grad_sum = pl.fused_grad ? d.gsum : nullptr;
     so.jac = d.jac;
     so.status = d.status;
@@ -1065,11 +1083,12 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     pl.gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
     pl.jac = (want & CB200_WANT_JAC) && out->jac_vals;
     pl.crit = (want & CB200_WANT_CRIT) && out->criteria;
+    pl.gradc = (want & CB200_WANT_GRAD_COMPACT) && out->grad_compact;
     if ((pl.fim || pl.fsum || pl.crit) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
     if (pl.crit && h->fim_n > CB200_MAX_FIM) return fail(CB200_ERR_UNSUPPORTED, "criteria need fim_n <= %d", CB200_MAX_FIM);
     pl.obj_state = pl.obj_ctrl_var = -1;
     pl.objective_row = out->objective_row;
-    if (pl.obj || pl.grad || pl.osum || pl.gsum) {
+    if (pl.obj || pl.grad || pl.osum || pl.gsum || pl.gradc) {
         const int row = out->objective_row;
         if (row < 1 || row > nrow) return fail(CB200_ERR_ARG, "objective_row out of range");
         if (row <= nx) {
@@ -1082,7 +1101,12 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         }
     }
     pl.fused_grad = (pl.grad || pl.gsum) && pl.obj_state >= 0;   // gradient written by the shooting kernel
-    pl.need_sens = pl.sens || pl.fused_grad || pl.jac;           // sensitivity directions are integrated
+    if (pl.gradc) {
+        if (pl.obj_state < 0) return fail(CB200_ERR_UNSUPPORTED, "grad_compact needs a state row as objective (a control row's gradient is a unit vector)");
+        pl.gradc_first = pl.obj_quad ? 0 : h->h_var_off[I - 1];   // a quadrature row sums over all intervals
+        pl.gradc_n = nvars - pl.gradc_first;
+    }
+    pl.need_sens = pl.sens || pl.fused_grad || pl.jac || pl.gradc;   // sensitivity directions are integrated
     pl.need_xend = pl.xend || pl.fim || pl.fsum || pl.crit || (pl.traj && h->nquad > 0);
     const bool need_objq = (pl.obj || pl.osum) && pl.obj_state >= 0;
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {
@@ -1104,6 +1128,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         {need_objq, I, &h->ws_objq, nullptr, &DevSet::objq},
         {pl.jac, h->jac_nnz_var, &h->ws_jac, out->jac_vals, &DevSet::jac},
         {pl.crit, 6, &h->ws_crit, out->criteria, &DevSet::crit},
+        {pl.gradc, pl.gradc_n, &h->ws_gradc, out->grad_compact, &DevSet::gradc},
     };
 
     // ---- cross-candidate sums (expectation-type objective / gradient, FIM): accumulated on the device

@@ -64,6 +64,8 @@ struct ShootOut {
     double *dst;       // [pos_stage * ldo + b]
     double *objq;      // [i * ldo + b] end value of state obj_state on interval i
     double *grad;      // [var * ldo + b]
+    double *gradc;     // [(var - gradc_first) * ldo + b] compact gradient: only the variables the objective depends on
+    int gradc_first;   // first variable of that range (the range ends at nvars)
     double *grad_sum;  // [var] sum over the candidates of this launch (atomicAdd of warp partial sums)
     double *jac;       // [slot * ldo + b] values of d(shooting_constraints)/d(ps) in cb200_jac_structure order
     int *status;       // [b] failure flags (atomicOr): bit 0 = a non-finite end state on some interval

@@ -411,7 +411,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         }
         // objective gradient: variable voff + d is direction d of this interval, so every thread owns the
         // gradient entries of its directions (zero when the interval does not reach the objective)
-        if (o.grad || o.grad_sum) {
+        if (o.grad || o.grad_sum || o.gradc) {
             const bool inc = o.obj_all || i == L.I - 1;
 #pragma unroll
             for (int g = 0; g < G; g++) {
@@ -421,6 +421,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
 #pragma unroll
                     for (int k = 0; k < NX; k++) val = (inc && k == o.obj_state) ? CB200_SS(g, k) : val;
                     if (o.grad && live) o.grad[(long long)(voff + d) * o.ldo + b] = val;
+                    if (o.gradc && live && voff + d >= o.gradc_first) o.gradc[(long long)(voff + d - o.gradc_first) * o.ldo + b] = val;
                     if (o.grad_sum) {
                         if (!live) val = 0.0;
                         if (!L.flat) {  // whole warp shares (i, r): shuffle tree, one atomic per warp

@@ -333,6 +333,7 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
         if (k == o.obj_state) {
             const double val = inc ? yd[s] : 0.0;
             if (o.grad) o.grad[(long long)(voff + dir) * o.ldo + b] = val;
+            if (o.gradc && voff + dir >= o.gradc_first) o.gradc[(long long)(voff + dir - o.gradc_first) * o.ldo + b] = val;
             if (o.grad_sum) atomicAdd(o.grad_sum + voff + dir, val);
         }
     }

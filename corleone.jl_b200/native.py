@@ -14,14 +14,14 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CORLEONE_B200_LIB") or os.path.join(_HERE, "libcorleone_b200.so")
 _lib = None
 
-WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT = 1, 2, 4, 8, 16, 32, 64, 128, 256
+WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT, WANT_GRAD_COMPACT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
 MEM_DEVICE, PS_SOA, OUT_SOA = 1, 2, 4
 
 EXPORTS = (
     "cb200_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_sizes",
     "cb200_block_structure", "cb200_set_stream", "cb200_eval", "cb200_jac_structure",
     "cb200_last_kernel_ms", "cb200_kernel_ms_history", "cb200_launch_count", "cb200_probe_fp64_tflops",
-    "cb200_probe_fp64_mma_tflops", "cb200_forward_init",
+    "cb200_probe_fp64_mma_tflops", "cb200_forward_init", "cb200_grad_structure",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -49,7 +49,7 @@ class Out(C.Structure):
         ("defects_stage", C.c_void_p), ("objective", C.c_void_p), ("grad", C.c_void_p), ("fim", C.c_void_p),
         ("fim_sum", C.c_void_p), ("objective_sum", C.c_void_p), ("grad_sum", C.c_void_p),
         ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
-        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p), ("status", C.c_void_p),
+        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p), ("grad_compact", C.c_void_p), ("status", C.c_void_p),
     ]
 
 
@@ -80,6 +80,8 @@ def lib():
         L.cb200_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
                                  C.POINTER(Out)]
         L.cb200_forward_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, _i32p, C.c_int32]
+        L.cb200_grad_structure.argtypes = [C.c_void_p, C.c_int32, _i64p]
+        L.cb200_grad_structure.restype = C.c_int64
         L.cb200_jac_structure.argtypes = [C.c_void_p, _i64p, _i64p, _i64p]
         L.cb200_last_kernel_ms.argtypes = [C.c_void_p]
         L.cb200_last_kernel_ms.restype = C.c_float
@@ -182,6 +184,14 @@ class NativeLayer:
         n = self.jac_nnz
         return r[:n], c[:n], s[:n]
 
+    def grad_structure(self, objective_row: int):
+        """(first variable (0-based), count) of the contiguous variable range the objective row depends on"""
+        first = C.c_int64()
+        n = lib().cb200_grad_structure(self._h, objective_row, C.byref(first))
+        if n < 0:
+            raise NativeError(f"cb200_grad_structure failed ({n}): {lib().cb200_last_error().decode()}")
+        return int(first.value) - 1, int(n)
+
     def set_stream(self, cuda_stream: int):
         _check(lib().cb200_set_stream(self._h, C.c_void_p(cuda_stream)), "cb200_set_stream")
 
@@ -239,6 +249,9 @@ class NativeLayer:
         if want & WANT_FIM: fields.append("fim")
         if want & WANT_JAC: fields.append("jac_vals")
         if want & WANT_CRIT: fields.append("criteria")
+        if want & WANT_GRAD_COMPACT:
+            fields.append("grad_compact")
+            sz["grad_compact"] = self.grad_structure(objective_row)[1]
         res = {}
         for f in fields:
             if pinned_out is not None and f in pinned_out:

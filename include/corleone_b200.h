@@ -113,6 +113,7 @@ typedef struct {
 #define CB200_WANT_GRAD 0x020u      /* d objective / d ps */
 #define CB200_WANT_FIM 0x040u       /* F_init + symmetric F(t_end) per candidate, and its sum over candidates */
 #define CB200_WANT_CRIT 0x100u      /* the six OED criteria of Symmetric(F) per candidate (criteria.jl:33-63) */
+#define CB200_WANT_GRAD_COMPACT 0x200u /* d objective / d ps without the structural zeros (cb200_grad_structure) */
 #define CB200_WANT_JAC 0x080u       /* values of d(shooting_constraints)/d(ps), cb200_jac_structure order (cons_j) */
 
 /* memory / layout flags */
@@ -132,6 +133,7 @@ typedef struct {
  *   defects_stage  n = n_defects       stage_ordered_shooting_constraints order (:229,249-252)
  *   objective      n = 1
  *   grad           n = nvars
+ *   grad_compact   n = cb200_grad_structure(...)   the gradient entries of the variables the objective depends on
  *   fim            n = fim_n*fim_n     column-major symmetric matrix
  *   criteria       n = 6               A, D, E, FisherA, FisherD, FisherE of F = F_init + F(t_end)
  *   jac_vals       n = jac_nnz_var     sensitivity-valued nonzeros of the constraint Jacobian = the leading
@@ -158,6 +160,7 @@ typedef struct {
     int32_t reserved;
     double *jac_vals;
     double *criteria;
+    double *grad_compact;
     int32_t *status;            /* [B] failure flags per candidate (always filled when non-NULL): bit 0 = a non-finite
                                    end state on some interval.  The reference never inspects the solver's retcode. */
 } cb200_out;
@@ -193,6 +196,11 @@ int cb200_set_stream(cb200_handle *h, void *cuda_stream);
  * enqueued on the handle's stream (device pointers). */
 int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t ldb, uint32_t want, uint32_t flags,
                const cb200_out *out);
+
+/* Variables the objective row depends on: the contiguous range [*first, *first + n) (1-based) of the flat variable
+ * vector -- everything for a quadrature row, the last interval's block for another state row; returns n (< 0: error).
+ * `grad_compact` holds exactly these entries: a dense gradient of a 100-interval layer is 99 % structural zeros. */
+int64_t cb200_grad_structure(const cb200_handle *h, int32_t objective_row, int64_t *first);
 
 /* forward_initialization(rng, shooting; ps, fixed_indices) (src/node_initialization.jl:152-170) for B candidates at
  * once: walks the intervals in order and overwrites each interval's node values ps.interval_i.u0 in place with the

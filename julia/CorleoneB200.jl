@@ -72,6 +72,7 @@ struct Out                       # cb200_out
     reserved::Int32
     jac_vals::Ptr{Float64}
     criteria::Ptr{Float64}
+    grad_compact::Ptr{Float64}
     status::Ptr{Int32}
 end
 
@@ -208,7 +209,7 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init jac crit status begin
         o = Out(ptr(xend), ptr(sens), ptr(traj), ptr(dk), ptr(ds), ptr(obj), ptr(grad), ptr(fim),
             (want & WANT_FIM) != 0 ? pointer(fsum) : Ptr{Float64}(C_NULL), C_NULL, C_NULL,
-            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), pointer(status))
+            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), Ptr{Float64}(C_NULL), pointer(status))
         check(ccall((:cb200_eval, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, UInt32, UInt32, Ref{Out}),
                 e.handle, P, B, size(P, 1), want, 0, o), "cb200_eval")

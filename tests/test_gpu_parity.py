@@ -43,7 +43,8 @@ def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
     assert N.nvars == O.nvars and N.n_defects == O.ndef and N.n_samples == O.nsamples and N.n_row == O.nrow
     assert np.array_equal(N.block_structure(), O.block_structure())
     ps = batch_ps(O, B, rng) if ps is None else ps
-    want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_JAC
+    want = (nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_JAC
+            | nat.WANT_GRAD_COMPACT)
     if check_traj:
         want |= nat.WANT_TRAJ
     r = N.eval_host(ps, want, objective_row=objective_row)
@@ -51,6 +52,9 @@ def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
     nx, I = O.nx, O.I
     errs = dict(xend=0.0, defk=0.0, defs=0.0, obj=0.0, traj=0.0, sens=0.0, grad=0.0)
     rows, cols, src = N.jac_structure()
+    g0, gn = N.grad_structure(objective_row)
+    assert g0 + gn == N.nvars and np.array_equal(r["grad_compact"], r["grad"][:, g0:])
+    assert not np.any(r["grad"][:, :g0])          # what the compact form leaves out is structurally zero
     for b in range(B):
         o = O.eval(ps[b], method=method, K=K)
         errs["xend"] = max(errs["xend"], rel_err(r["xend"][b].reshape(I, nx).T, o["xend"]))
