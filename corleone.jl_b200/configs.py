@@ -128,6 +128,36 @@ def rocket_spec(n_intervals=4, rng=None):
                 shooting_points=[k / n_intervals for k in range(n_intervals)])
 
 
+def quadrotor_spec(n_intervals=3, rng=None):
+    """quadrotor with Lagrange state (.../quadrotor.jl): four controls (w1, w2, w3, u) on different grids"""
+    rng = np.random.default_rng(SEED0 + 11) if rng is None else rng
+    tw, tu = np.arange(15) / 2.0, np.arange(30) / 4.0
+    return dict(model="quadrotor7", u0=[0.0, 0.0, 1.0, 0.0, 0.0, 0.0, 0.0], p0=[1 / 3, 1 / 3, 1 / 3, 0.0],
+                tspan=(0.0, 7.5),
+                controls=[(1, tw, rng.uniform(0, 1, 15)), (2, tw, rng.uniform(0, 1, 15)), (3, tw, rng.uniform(0, 1, 15)),
+                          (4, tu, rng.uniform(0, 1, 30))],
+                tunable_ic=[], quadrature_indices=[7], shooting_points=[7.5 * k / n_intervals for k in range(n_intervals)])
+
+
+def threetank_spec(n_intervals=4, rng=None):
+    """three-tank system with Lagrange state (.../three_tank.jl): sqrt right-hand side, three controls"""
+    rng = np.random.default_rng(SEED0 + 12) if rng is None else rng
+    t = np.arange(24) / 4.0
+    return dict(model="threetank4", u0=[2.0, 2.0, 2.0, 0.0], p0=[1 / 3, 1 / 3, 1 / 3], tspan=(0.0, 6.0),
+                controls=[(1, t, rng.uniform(0.4, 0.7, 24)), (2, t, rng.uniform(0.4, 0.7, 24)),
+                          (3, t, rng.uniform(0.1, 0.3, 24))],
+                tunable_ic=[], quadrature_indices=[], shooting_points=[6.0 * k / n_intervals for k in range(n_intervals)])
+
+
+def batchreactor_spec(n_intervals=4, rng=None):
+    """batch reactor (.../batch_reactor.jl): Arrhenius terms exp(-c / u), temperature control in [298, 398]"""
+    rng = np.random.default_rng(SEED0 + 13) if rng is None else rng
+    t = np.arange(20) / 20.0
+    return dict(model="batchreactor2", u0=[1.0, 0.0], p0=[298.0], tspan=(0.0, 1.0),
+                controls=[(1, t, rng.uniform(298, 398, 20))], tunable_ic=[], quadrature_indices=[],
+                shooting_points=[k / n_intervals for k in range(n_intervals)])
+
+
 def layer_from_spec(spec, alg, **kw):
     """Build the SingleShootingLayer / MultipleShootingLayer a spec describes."""
     prob = ODEProblem(spec["model"], spec["u0"], spec["tspan"], spec["p0"], model_data=spec.get("model_data"))

@@ -119,6 +119,18 @@ int launch_rocket3(int G, int method, const DevLayer &L, const double *ps, long 
         const ShootOut &o, cudaStream_t s);
 int forward_rocket3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s);
+int launch_quadrotor7(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_quadrotor7(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_threetank4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_threetank4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_batchreactor2(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_batchreactor2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
 
 }  // namespace cb200

@@ -336,6 +336,12 @@ CB_DEV double cos(double a) { return ::cos(a); }
 CB_DEV double exp(double a) { return ::exp(a); }
 CB_DEV Dual sin(Dual a) { return {::sin(a.v), ::cos(a.v) * a.d}; }
 CB_DEV Dual cos(Dual a) { return {::cos(a.v), -::sin(a.v) * a.d}; }
+CB_DEV double sqrt(double a) { return ::sqrt(a); }
+CB_DEV Dual sqrt(Dual a)
+{
+    const double r = ::sqrt(a.v);
+    return {r, 0.5 * a.d / r};
+}
 CB_DEV Dual exp(Dual a)
 {
     const double e = ::exp(a.v);
@@ -414,5 +420,57 @@ struct RocketRhs {
     }
 };
 using Rocket3 = AutoJvp<RocketRhs>;
+
+
+// Quadrotor with its Lagrange term (lib/OptimalControlBenchmarks/src/problems/quadrotor.jl:9-52): states (x1..x6, cost),
+// p = (w1, w2, w3, u) -- four controls
+struct QuadrotorRhs {
+    static constexpr int NX = 7, NXD = 6, NQ = 1, NP = 4;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double g = 9.81, M = 1.3, L = 0.305, I = 0.0605;
+        const T s5 = sin(x[4]), c5 = cos(x[4]);
+        dx[0] = x[1];
+        dx[1] = g * s5 + p[0] * p[3] * s5 / M;
+        dx[2] = x[3];
+        dx[3] = g * c5 - g + p[0] * p[3] * c5 / M;
+        dx[4] = x[5];
+        dx[5] = (p[2] - p[1]) * (L / I) * p[3];
+        dx[6] = 5.0 * (p[3] * p[3]);
+    }
+};
+using Quadrotor7 = AutoJvp<QuadrotorRhs>;
+
+// Three-tank system with its Lagrange term (.../three_tank.jl:9-53): states (x1, x2, x3, cost), p = (w1, w2, w3)
+struct ThreeTankRhs {
+    static constexpr int NX = 4, NXD = 3, NQ = 1, NP = 3;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double c1 = 1.0, c2 = 2.0, c3 = 0.8, k1 = 2.0, k2 = 3.0, k3 = 1.0, k4 = 3.0;
+        const T r1 = sqrt(x[0]), r2 = sqrt(x[1]), r3 = sqrt(x[2]), q = p[2] * sqrt(c3 * x[0]);
+        dx[0] = c1 * p[0] + c2 * p[1] - r2 - q;
+        dx[1] = r1 - r2;
+        dx[2] = r2 - r3 + q;
+        const T e2 = x[1] - k2, e3 = x[2] - k4;
+        dx[3] = k1 * (e2 * e2) + k3 * (e3 * e3);
+    }
+};
+using ThreeTank4 = AutoJvp<ThreeTankRhs>;
+
+// Batch reactor (.../batch_reactor.jl:9-17): states (x1, x2), p = (u) -- Arrhenius terms exp(-c / u)
+struct BatchReactorRhs {
+    static constexpr int NX = 2, NXD = 2, NQ = 0, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const T r1 = 4.0e3 * exp(-2500.0 / p[0]) * (x[0] * x[0]);
+        const T r2 = 62.0e4 * exp(-5000.0 / p[0]) * (x[1] * x[1]);
+        dx[0] = -r1;
+        dx[1] = r1 - r2;
+    }
+};
+using BatchReactor2 = AutoJvp<BatchReactorRhs>;
 
 }  // namespace cb200

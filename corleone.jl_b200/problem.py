@@ -24,6 +24,9 @@ MODEL_REGISTRY = {
     "vdp3": (8, 3, 1),
     "cartpole5": (9, 5, 1),
     "rocket3": (10, 3, 2),
+    "quadrotor7": (11, 7, 4),
+    "threetank4": (12, 4, 3),
+    "batchreactor2": (13, 2, 1),
 }
 
 # base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)

@@ -60,7 +60,10 @@ typedef enum {
     /* lib/OptimalControlBenchmarks/src/problems: right-hand sides with their Lagrange term as last state */
     CB200_MODEL_VDP3 = 8,       /* van_der_pol.jl:16-33 */
     CB200_MODEL_CARTPOLE5 = 9,  /* cart_pendulum.jl:17-48 */
-    CB200_MODEL_ROCKET3 = 10    /* goddarts_rocket.jl:16-40, p = (T, u) */
+    CB200_MODEL_ROCKET3 = 10,   /* goddarts_rocket.jl:16-40, p = (T, u) */
+    CB200_MODEL_QUADROTOR7 = 11,    /* quadrotor.jl:9-52, p = (w1, w2, w3, u) */
+    CB200_MODEL_THREETANK4 = 12,    /* three_tank.jl:9-53, p = (w1, w2, w3) */
+    CB200_MODEL_BATCHREACTOR2 = 13  /* batch_reactor.jl:9-17, p = (u) */
 } cb200_model;
 
 typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;

@@ -97,6 +97,13 @@ static inline dual dcos(dual a)
     for (int k = 0; k < g_nd; k++) r.d[k] = -s * a.d[k];
     return r;
 }
+static inline dual dsqrt(dual a)
+{
+    dual r;
+    r.v = sqrt(a.v);
+    for (int k = 0; k < g_nd; k++) r.d[k] = 0.5 * a.d[k] / r.v;
+    return r;
+}
 static inline dual dexp(dual a)
 {
     dual r;
@@ -226,6 +233,41 @@ static void rhs_rocket3(const dual *x, const dual *p, dual *du)
     du[2] = dmul(p[0], dscale(p[1], -b));
 }
 
+/* quadrotor.jl:9-52: states (x1..x6, cost), p = (w1, w2, w3, u) */
+static void rhs_quadrotor7(const dual *x, const dual *p, dual *du)
+{
+    const double g = 9.81, M = 1.3, L = 0.305, I = 0.0605;
+    dual s5 = dsin(x[4]), c5 = dcos(x[4]);
+    dual wu = dmul(p[0], p[3]);
+    du[0] = x[1];
+    du[1] = dadd(dscale(s5, g), dscale(dmul(wu, s5), 1.0 / M));
+    du[2] = x[3];
+    du[3] = dadd(daddc(dscale(c5, g), -g), dscale(dmul(wu, c5), 1.0 / M));
+    du[4] = x[5];
+    du[5] = dmul(dscale(dsub(p[2], p[1]), L / I), p[3]);
+    du[6] = dscale(dmul(p[3], p[3]), 5.0);
+}
+/* three_tank.jl:9-53: states (x1, x2, x3, cost), p = (w1, w2, w3) */
+static void rhs_threetank4(const dual *x, const dual *p, dual *du)
+{
+    const double c1 = 1.0, c2 = 2.0, c3 = 0.8, k1 = 2.0, k2 = 3.0, k3 = 1.0, k4 = 3.0;
+    dual r1 = dsqrt(x[0]), r2 = dsqrt(x[1]), r3 = dsqrt(x[2]);
+    dual q = dmul(p[2], dsqrt(dscale(x[0], c3)));
+    du[0] = dsub(dsub(dadd(dscale(p[0], c1), dscale(p[1], c2)), r2), q);
+    du[1] = dsub(r1, r2);
+    du[2] = dadd(dsub(r2, r3), q);
+    dual e2 = daddc(x[1], -k2), e3 = daddc(x[2], -k4);
+    du[3] = dadd(dscale(dmul(e2, e2), k1), dscale(dmul(e3, e3), k3));
+}
+/* batch_reactor.jl:9-17: states (x1, x2), p = (u) */
+static void rhs_batchreactor2(const dual *x, const dual *p, dual *du)
+{
+    dual r1 = dscale(dmul(dexp(ddiv(dconst(-2500.0), p[0])), dmul(x[0], x[0])), 4.0e3);
+    dual r2 = dscale(dmul(dexp(ddiv(dconst(-5000.0), p[0])), dmul(x[1], x[1])), 62.0e4);
+    du[0] = dneg(r1);
+    du[1] = dsub(r1, r2);
+}
+
 typedef void (*rhs_fn)(const dual *, const dual *, dual *);
 typedef void (*jac_fn)(const dual *, const dual *, dual *, dual *);
 static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, const dual *u, const dual *p,
@@ -267,6 +309,9 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_VDP3: rhs_vdp3(u, p, du); break;
     case CO_CARTPOLE5: rhs_cartpole5(u, p, du); break;
     case CO_ROCKET3: rhs_rocket3(u, p, du); break;
+    case CO_QUADROTOR7: rhs_quadrotor7(u, p, du); break;
+    case CO_THREETANK4: rhs_threetank4(u, p, du); break;
+    case CO_BATCHREACTOR2: rhs_batchreactor2(u, p, du); break;
     default: break;
     }
 }

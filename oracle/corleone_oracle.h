@@ -43,7 +43,10 @@ enum co_model {
     CO_EGERSTEDT = 7,   /* test/core/local_controls.jl:46-52 */
     CO_VDP3 = 8,        /* lib/OptimalControlBenchmarks/src/problems/van_der_pol.jl:16-33 (+ Lagrange state) */
     CO_CARTPOLE5 = 9,   /* .../cart_pendulum.jl:17-48 (+ Lagrange state) */
-    CO_ROCKET3 = 10     /* .../goddarts_rocket.jl:16-40, p = (T, u) */
+    CO_ROCKET3 = 10,    /* .../goddarts_rocket.jl:16-40, p = (T, u) */
+    CO_QUADROTOR7 = 11, /* .../quadrotor.jl:9-52 (+ Lagrange state), p = (w1, w2, w3, u) */
+    CO_THREETANK4 = 12, /* .../three_tank.jl:9-53 (+ Lagrange state), p = (w1, w2, w3) */
+    CO_BATCHREACTOR2 = 13 /* .../batch_reactor.jl:9-17, p = (u) */
 };
 
 enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };

@@ -26,6 +26,9 @@ MODELS = {
     "vdp3": 8,
     "cartpole5": 9,
     "rocket3": 10,
+    "quadrotor7": 11,
+    "threetank4": 12,
+    "batchreactor2": 13,
 }
 METHODS = {"tsit5": 0, "rk4": 1}
 CO_ND = 16
