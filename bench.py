@@ -38,7 +38,7 @@ NZ = NX * (1 + NS_DIRS)
 FLOPS_PER_UNIT = E_EVALS * (10 + 36) + M_PIECES * K_STEPS_PER_PIECE * 42 * NZ      # 8440
 #   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic (BASELINE.md formula)
 BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                                # 240
-NCU_DRAM_BYTES_PER_LAUNCH = 30290432 + 40308224   # profiles/r1_shoot_lqr_G4_fused.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 26837760 + 15322368   # profiles/r1_shoot_lqr_G4_fused.txt
 
 
 try:
@@ -413,8 +413,8 @@ def main():
             "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                          "frac": ach_tflops / fp64_peak if fp64_peak > 0 else None,
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                         # command (profiles/r1_shoot_lqr_G4_fused.txt): 30.3 MB read + 40.5 MB written; the rest of
-                         # the 94 MB of results is still in the 126 MB L2 when the kernel ends
+                         # command (profiles/r1_shoot_lqr_G4_fused.txt): 26.8 MB read + 15.3 MB written; the rest of
+                         # the 65 MB of results is still in the 126 MB write-back L2 when the kernel ends
                          "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
                          "algorithmic_bytes_per_launch": BYTES_PER_UNIT * I_INTERVALS * B,
                          "kernel": "shoot_kernel<Lqr,G=4,Tsit5,uniform,4 blocks/SM> incl. fused defect/gradient/cons_j epilogue",
