@@ -13,7 +13,7 @@ from .multiple_shooting import (MultipleShootingLayer, control_matchings, defaul
                                 get_number_of_shooting_constraints, get_number_of_state_matchings,
                                 parameter_matchings, shooting_constraints, shooting_constraints_,
                                 stage_ordered_shooting_constraints, stage_ordered_shooting_constraints_,
-                                state_matchings)
+                                state_matchings, trajectory_jacobian)
 from .node_initialization import (constant_initialization, custom_initialization, forward_initialization,
                                   forward_initialization_batch,
                                   hybrid_initialization, linear_initialization, random_initialization)

@@ -291,7 +291,8 @@ struct cb200_handle {
     std::vector<int> quad0;           // 0-based quadrature states
     std::vector<int> ns;              // directions per interval
     std::vector<int> h_M, h_var_off, h_n_u0, h_n_c, h_samp_off, h_piece_off;
-    std::vector<long long> h_sens_off;
+    std::vector<long long> h_sens_off, h_tsens_off;
+    long long n_tsens = 0;
     std::vector<int> h_cidx, h_ic_src;
     std::vector<DefectEntry> defects;
     std::vector<int> dpos_kind, dpos_stage, oth_off, jpos;
@@ -317,7 +318,7 @@ struct cb200_handle {
     cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
     long long n_timed = 0;
     long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small, ws_gradc;
+    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small, ws_gradc, ws_tsens;
     static constexpr size_t PIN_BYTES = 1 << 20;   // pinned host mirror of small evaluations
     void *pin = nullptr;
 };
@@ -527,6 +528,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         h->h_n_c.push_back(d->n_local_controls[i]);
         h->h_samp_off.push_back(so);
         h->h_sens_off.push_back(seo);
+        h->h_tsens_off.push_back(h->n_tsens);
+        h->n_tsens += (long long)(M + (i == I - 1 ? 1 : 0)) * (d->n_u0[i] + ntp + d->n_local_controls[i]) * nx;
         const int nsi = d->n_u0[i] + ntp + d->n_local_controls[i];
         h->ns.push_back(nsi);
         h->max_ns = std::max(h->max_ns, nsi);
@@ -747,7 +750,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     const size_t o_M = push(blob, h->h_M), o_po = push(blob, h->h_piece_off), o_t0 = push(blob, pt0),
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
-                 o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_so = push(blob, h->h_samp_off),
+                 o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_tse = push(blob, h->h_tsens_off), o_so = push(blob, h->h_samp_off),
                  o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol), o_dperm = push(blob, dir_perm),
                  o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
                  o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos);
@@ -807,6 +810,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.ic_fix = (const double *)(base + o_if);
     L.ic_fix0 = (const double *)(base + o_if0);
     L.sens_off = (const long long *)(base + o_se);
+    L.tsens_off = (const long long *)(base + o_tse);
     L.samp_off = (const int *)(base + o_so);
     L.dir_pcol = (const signed char *)(base + o_dp);
     L.dir_perm = (const short *)(base + o_dperm);
@@ -855,7 +859,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
-                      &h->ws_grad, &h->ws_fim, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small, &h->ws_gradc})
+                      &h->ws_grad, &h->ws_fim, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small, &h->ws_gradc, &h->ws_tsens})
         b->release();
     if (h->tables) cudaFree(h->tables);
     if (h->pin) cudaFreeHost(h->pin);
@@ -887,6 +891,7 @@ extern "C" int cb200_get_sizes(const cb200_handle *h, cb200_sizes *s)
     s->n_units = h->L.I;
     s->jac_nnz = (int64_t)h->jac_rows.size();
     s->jac_nnz_var = (int64_t)h->jac_nnz_var;
+    s->n_traj_sens = (int64_t)h->n_tsens;
     return CB200_OK;
 }
 
@@ -978,7 +983,7 @@ static int transpose(cb200_handle *h, cudaStream_t st, const double *in, long lo
 
 // what one evaluation produces, resolved from (want, out)
 struct EvalPlan {
-    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum, jac, crit, gradc;
+    bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum, jac, crit, gradc, tsens;
     int gradc_first, gradc_n;   // compact gradient: variables [gradc_first, gradc_first + gradc_n)
     bool fused_grad, need_sens, need_xend;
     int obj_state, obj_ctrl_var, obj_quad, objective_row;
@@ -987,7 +992,7 @@ struct EvalPlan {
 // device SoA buffers of one batch (or one chunk of it), leading dimension = its candidate count
 struct DevSet {
     double *xend = nullptr, *sens = nullptr, *traj = nullptr, *dk = nullptr, *ds = nullptr, *obj = nullptr,
-           *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr, *gradc = nullptr;
+           *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr, *gradc = nullptr, *tsens = nullptr;
     int *status = nullptr;      // [B] of the batch / chunk
     double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // shared by all chunks (atomic accumulation)
     const double *finit = nullptr;
@@ -1013,6 +1018,7 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     so.xend = d.xend;
     so.sens = d.sens;
     so.traj = d.traj;
+    so.tsens = d.tsens;
     so.ldo = B;
     so.dk = ndef > 0 ? d.dk : nullptr;
     so.dst = ndef > 0 ? d.ds : nullptr;
@@ -1096,6 +1102,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     pl.jac = (want & CB200_WANT_JAC) && out->jac_vals;
     pl.crit = (want & CB200_WANT_CRIT) && out->criteria;
     pl.gradc = (want & CB200_WANT_GRAD_COMPACT) && out->grad_compact;
+    pl.tsens = (want & CB200_WANT_TRAJ_SENS) && out->traj_sens;
     if ((pl.fim || pl.fsum || pl.crit) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
     if (pl.crit && h->fim_n > CB200_MAX_FIM) return fail(CB200_ERR_UNSUPPORTED, "criteria need fim_n <= %d", CB200_MAX_FIM);
     pl.obj_state = pl.obj_ctrl_var = -1;
@@ -1118,7 +1125,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         pl.gradc_first = pl.obj_quad ? 0 : h->h_var_off[I - 1];   // a quadrature row sums over all intervals
         pl.gradc_n = nvars - pl.gradc_first;
     }
-    pl.need_sens = pl.sens || pl.fused_grad || pl.jac || pl.gradc;   // sensitivity directions are integrated
+    pl.need_sens = pl.sens || pl.fused_grad || pl.jac || pl.gradc || pl.tsens;   // sensitivity directions are integrated
     pl.need_xend = pl.xend || pl.fim || pl.fsum || pl.crit || (pl.traj && h->nquad > 0);
     const bool need_objq = (pl.obj || pl.osum) && pl.obj_state >= 0;
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {
@@ -1141,6 +1148,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         {pl.jac, h->jac_nnz_var, &h->ws_jac, out->jac_vals, &DevSet::jac},
         {pl.crit, 6, &h->ws_crit, out->criteria, &DevSet::crit},
         {pl.gradc, pl.gradc_n, &h->ws_gradc, out->grad_compact, &DevSet::gradc},
+        {pl.tsens, h->n_tsens, &h->ws_tsens, out->traj_sens, &DevSet::tsens},
     };
 
     // ---- cross-candidate sums (expectation-type objective / gradient, FIM): accumulated on the device

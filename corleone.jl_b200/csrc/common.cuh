@@ -36,6 +36,7 @@ struct DevLayer {
     const double *ic_fix0;   // [I*nx] the same with fixval = problem.u0 on every interval (forward sweep)
     const long long *sens_off;  // [I] first row of the interval's block in `sens`
     const int *samp_off;     // [I] first merged-trajectory sample of the interval
+    const long long *tsens_off;  // [I] first row of the interval's block in `traj_sens`
     const double *model_data;  // model constants in HBM (DENSE20: W row-major 20x20, then b[20]) or nullptr
     const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
     const short *dir_perm;        // [nvars] direction held by slot s of the interval (activation order, see shoot.cuh)
@@ -58,6 +59,7 @@ struct ShootOut {
     double *xend;  // [(i*nx + k) * ldo + b]
     double *sens;  // [(sens_off[i] + d*nx + k) * ldo + b]
     double *traj;  // [((samp_off[i] + j) * nrow + r) * ldo + b]
+    double *tsens; // [(tsens_off[i] + (j * ns_i + d) * nx + k) * ldo + b]: sensitivities at the interval's j-th sample
     long long ldo;
     // fused epilogue (K3): defects in both orderings, the objective state of every interval, objective gradient
     double *dk;        // [pos_kind * ldo + b]

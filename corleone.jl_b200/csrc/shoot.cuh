@@ -200,6 +200,24 @@ __device__ __forceinline__ void save_sample(const DevLayer &L, const ShootOut &o
         if (L.pmap_kind[q] == 1) t[(long long)(NX + L.pmap_idx[q]) * o.ldo] = p[q];
 }
 
+// sensitivities of the thread's directions at one trajectory sample (WANT_TRAJ_SENS): what the point constraints of
+// src/dynprob.jl:30-58 differentiate.  row0 = tsens_off[i] + j * ns * NX.
+template <class Mdl, int G>
+__device__ __forceinline__ void save_sens_sample(const ShootOut &o, long long row0, long long b, const int *dmap,
+                                                 const double *yd, const double *yq)
+{
+    constexpr int NX = Mdl::NX, NXD = Mdl::NXD, NQ = Mdl::NQ;
+#pragma unroll
+    for (int g = 0; g < G; g++) {
+        if (dmap[g] >= 0) {
+#pragma unroll
+            for (int k = 0; k < NX; k++)
+                o.tsens[(row0 + (long long)dmap[g] * NX + k) * o.ldo + b] =
+                    (k < NXD) ? yd[NXD * (1 + g) + (k < NXD ? k : 0)] : yq[NQ * (1 + g) + (k >= NXD ? k - NXD : 0)];
+        }
+    }
+}
+
 // MINB: resident blocks of 128 threads per SM the register allocation must allow (__launch_bounds__); chosen
 // per (model, G) in the model's dispatch table from ptxas -v (largest value without spills in the step loop).
 template <class Mdl, int G, int METHOD, bool UNI, int MINB>
@@ -325,6 +343,9 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         }
         if (o.traj && live && r == 0 && j == 0)  // save_start = (j == 1)
             save_sample<Mdl>(L, o, (long long)so, nrow, b, yd, yq, p);
+        if constexpr (G > 0) {
+            if (o.tsens && live && j == 0) save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i), b, dmap, yd, yq);
+        }
         if constexpr (UNI) {
             integrate_active<Mdl, G, METHOD>(na, yd, yq, p, F, L.hA, L.K);
         } else {
@@ -339,6 +360,10 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
             save_sample<Mdl>(L, o, (long long)(so + j + 1), nrow, b, yd, yq, p);
+        if constexpr (G > 0) {
+            if (o.tsens && live && (j + 1 < M || last_interval))
+                save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i) + (long long)(j + 1) * ns * NX, b, dmap, yd, yq);
+        }
     }
     // ---- results.  xs(k): end state component k (compile-time k)
 #define CB200_XS(k) ((k) < NXD ? yd[(k) < NXD ? (k) : 0] : yq[(k) >= NXD ? (k)-NXD : 0])

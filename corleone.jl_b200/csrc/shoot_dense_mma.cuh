@@ -177,6 +177,11 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
 #pragma unroll
             for (int s = 0; s < 5; s++) binit[s] = w * __ldg(L.model_data + NX * NX + 5 * t + s);
         }
+        if (!IS_X && o.tsens && store && j == 0) {   // sensitivities at the interval's start sample
+            const long long row0 = __ldg(L.tsens_off + i) + (long long)dir * NX + 5 * t;
+#pragma unroll
+            for (int s = 0; s < 5; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
+        }
         if (o.traj && IS_X && store && round == 0 && j == 0) {  // save_start = (j == 1)
             double *tr = o.traj + ((long long)so * nrow) * o.ldo + b;
 #pragma unroll
@@ -270,6 +275,11 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
             }
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
+        if (!IS_X && o.tsens && store && (j + 1 < M || last_interval)) {
+            const long long row0 = __ldg(L.tsens_off + i) + ((long long)(j + 1) * ns + dir) * NX + 5 * t;
+#pragma unroll
+            for (int s = 0; s < 5; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
+        }
         if (o.traj && IS_X && store && round == 0 && (j + 1 < M || last_interval)) {
             double *tr = o.traj + ((long long)(so + j + 1) * nrow) * o.ldo + b;
 #pragma unroll

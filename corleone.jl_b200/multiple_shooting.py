@@ -111,6 +111,51 @@ class MultipleShootingLayer:
         return nat.eval_host(ps_batch, want, objective_row, fim_init)
 
 
+def trajectory_jacobian(shooting, st, ps_like, result, b: int = 0) -> np.ndarray:
+    """Dense d(merged trajectory samples)/d(flat variables) of candidate `b`, shape (n_row, n_samples, nvars) --
+    what ForwardDiff through `traj` yields and the point constraints of src/dynprob.jl:30-58,89-103 differentiate.
+
+    Assembled from one cb200_eval with WANT_TRAJ_SENS | WANT_SENS: `traj_sens` holds the per-interval blocks at
+    every saved sample; quadrature rows additionally carry the running sums of the earlier intervals
+    (src/multiple_shooting.jl:171-177), whose derivatives are the end-of-interval blocks of `sens`; a control row
+    is the control value of the piece that ends at the sample (src/single_shooting.jl:456)."""
+    single = isinstance(shooting, SingleShootingLayer)
+    layer = shooting if single else shooting.layer
+    sts = [st] if single else list(st.values())
+    pss = [ps_like] if single else list(ps_like.values())
+    nat = shooting._native(st, ps_like)
+    nx, nrow, I = nat.nx, nat.n_row, nat.I
+    blocks = nat.block_structure()
+    quad = [q - 1 for q in layer.quadrature_indices]
+    ts, se = result["traj_sens"][b], result["sens"][b]
+    J = np.zeros((nrow, nat.n_samples, nat.nvars))
+    so = toff = soff = 0
+    qacc = np.zeros((len(quad), nat.nvars))          # d(running quadrature sum)/d(variables of earlier intervals)
+    for i in range(I):
+        ns = int(blocks[i + 1] - blocks[i])
+        grid = np.asarray(_flatten_chunks(sts[i]["index_grid"]), dtype=np.int64)
+        nact = len(sts[i]["_control_indices"])
+        grid = grid.reshape(nact, -1) if nact else np.zeros((0, len(_flatten_chunks(sts[i]["tspans"]))), dtype=np.int64)
+        M = grid.shape[1] if nact else len(_flatten_chunks(sts[i]["tspans"]))
+        nsmp = M + (1 if i == I - 1 else 0)
+        c0 = blocks[i] + len(pss[i]["u0"]) + len(pss[i]["p"])
+        blk = ts[toff:toff + nsmp * ns * nx].reshape(nsmp, ns, nx)
+        for j in range(nsmp):
+            J[:nx, so + j, blocks[i]:blocks[i + 1]] = blk[j].T
+            for qi, q in enumerate(quad):
+                J[q, so + j, :] += qacc[qi]
+            piece = max(j - 1, 0)
+            for r in range(nact):
+                J[nx + r, so + j, c0 + grid[r, piece] - 1] = 1.0
+        send = se[soff:soff + nx * ns].reshape(ns, nx)
+        for qi, q in enumerate(quad):
+            qacc[qi, blocks[i]:blocks[i + 1]] += send[:, q]
+        so += M
+        toff += nsmp * ns * nx
+        soff += nx * ns
+    return J
+
+
 # ---- constraint counts (:184-218)
 def get_number_of_state_matchings(shooting, ps=None, st=None, rng=None):
     st = shooting.initialstates(rng) if st is None else st

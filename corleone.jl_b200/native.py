@@ -14,7 +14,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("CORLEONE_B200_LIB") or os.path.join(_HERE, "libcorleone_b200.so")
 _lib = None
 
-WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT, WANT_GRAD_COMPACT = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512
+WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT, WANT_GRAD_COMPACT, WANT_TRAJ_SENS = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
 MEM_DEVICE, PS_SOA, OUT_SOA = 1, 2, 4
 
 EXPORTS = (
@@ -49,13 +49,13 @@ class Out(C.Structure):
         ("defects_stage", C.c_void_p), ("objective", C.c_void_p), ("grad", C.c_void_p), ("fim", C.c_void_p),
         ("fim_sum", C.c_void_p), ("objective_sum", C.c_void_p), ("grad_sum", C.c_void_p),
         ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
-        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p), ("grad_compact", C.c_void_p), ("status", C.c_void_p),
+        ("jac_vals", C.c_void_p), ("criteria", C.c_void_p), ("grad_compact", C.c_void_p), ("traj_sens", C.c_void_p), ("status", C.c_void_p),
     ]
 
 
 class Sizes(C.Structure):
     _fields_ = [(n, C.c_int64) for n in
-                ("nvars", "n_defects", "n_samples", "n_row", "n_sens", "n_units", "jac_nnz", "jac_nnz_var")]
+                ("nvars", "n_defects", "n_samples", "n_row", "n_sens", "n_units", "jac_nnz", "jac_nnz_var", "n_traj_sens")]
 
 
 class NativeError(RuntimeError):
@@ -156,6 +156,7 @@ class NativeLayer:
         self.nx, self.I, self.nvars = nx, len(intervals), int(s.nvars)
         self.n_defects, self.n_samples, self.n_row = int(s.n_defects), int(s.n_samples), int(s.n_row)
         self.n_sens, self.jac_nnz, self.jac_nnz_var = int(s.n_sens), int(s.jac_nnz), int(s.jac_nnz_var)
+        self.n_traj_sens = int(s.n_traj_sens)
         self.fim_n = fim_n
         self.fim_offset = fim_offset
         self.device = device
@@ -220,7 +221,7 @@ class NativeLayer:
     def out_sizes(self):
         return dict(xend=self.nx * self.I, sens=self.n_sens, traj=self.n_row * self.n_samples,
                     defects_kind=self.n_defects, defects_stage=self.n_defects, objective=1, grad=self.nvars,
-                    fim=self.fim_n * self.fim_n, jac_vals=self.jac_nnz_var, criteria=6)
+                    fim=self.fim_n * self.fim_n, jac_vals=self.jac_nnz_var, criteria=6, traj_sens=self.n_traj_sens)
 
     def eval_raw(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1):
         """Raw pointer call (host or device pointers as `flags` says). ptrs: field name -> int address."""
@@ -249,6 +250,7 @@ class NativeLayer:
         if want & WANT_FIM: fields.append("fim")
         if want & WANT_JAC: fields.append("jac_vals")
         if want & WANT_CRIT: fields.append("criteria")
+        if want & WANT_TRAJ_SENS: fields.append("traj_sens")
         if want & WANT_GRAD_COMPACT:
             fields.append("grad_compact")
             sz["grad_compact"] = self.grad_structure(objective_row)[1]

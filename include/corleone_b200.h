@@ -117,6 +117,7 @@ typedef struct {
 #define CB200_WANT_FIM 0x040u       /* F_init + symmetric F(t_end) per candidate, and its sum over candidates */
 #define CB200_WANT_CRIT 0x100u      /* the six OED criteria of Symmetric(F) per candidate (criteria.jl:33-63) */
 #define CB200_WANT_GRAD_COMPACT 0x200u /* d objective / d ps without the structural zeros (cb200_grad_structure) */
+#define CB200_WANT_TRAJ_SENS 0x400u /* sensitivities at every saved sample (point constraints, src/dynprob.jl:30-58) */
 #define CB200_WANT_JAC 0x080u       /* values of d(shooting_constraints)/d(ps), cb200_jac_structure order (cons_j) */
 
 /* memory / layout flags */
@@ -139,6 +140,10 @@ typedef struct {
  *   grad_compact   n = cb200_grad_structure(...)   the gradient entries of the variables the objective depends on
  *   fim            n = fim_n*fim_n     column-major symmetric matrix
  *   criteria       n = 6               A, D, E, FisherA, FisherD, FisherE of F = F_init + F(t_end)
+ *   traj_sens      n = n_traj_sens     d (state k at the interval's j-th sample) / d (variable d of the SAME interval):
+ *                                       rows ordered interval, sample j (0 = the interval's start; the end sample of a
+ *                                       non-final interval is dropped as in `traj`), direction d, state k.  Raw
+ *                                       per-interval values: the running sums of quadrature rows are not added
  *   jac_vals       n = jac_nnz_var     sensitivity-valued nonzeros of the constraint Jacobian = the leading
  *                                       triplets of cb200_jac_structure (the constant +-1 entries follow them)
  *   fim_sum        fim_n*fim_n doubles total: sum over the B candidates of `fim`
@@ -164,6 +169,7 @@ typedef struct {
     double *jac_vals;
     double *criteria;
     double *grad_compact;
+    double *traj_sens;
     int32_t *status;            /* [B] failure flags per candidate (always filled when non-NULL): bit 0 = a non-finite
                                    end state on some interval.  The reference never inspects the solver's retcode. */
 } cb200_out;
@@ -177,6 +183,7 @@ typedef struct {
     int64_t n_units;        /* I: (interval) units per candidate */
     int64_t jac_nnz;        /* nonzeros of d(shooting_constraints)/d(ps) */
     int64_t jac_nnz_var;    /* the leading jac_nnz_var triplets carry sensitivity values (jac_vals); the rest are +-1 */
+    int64_t n_traj_sens;    /* sum_i samples_i * ns_i * nx */
 } cb200_sizes;
 
 typedef struct cb200_handle cb200_handle;

@@ -73,6 +73,7 @@ struct Out                       # cb200_out
     jac_vals::Ptr{Float64}
     criteria::Ptr{Float64}
     grad_compact::Ptr{Float64}
+    traj_sens::Ptr{Float64}
     status::Ptr{Int32}
 end
 
@@ -85,6 +86,7 @@ struct Sizes                     # cb200_sizes
     n_units::Int64
     jac_nnz::Int64
     jac_nnz_var::Int64
+    n_traj_sens::Int64
 end
 
 const WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS = 0x001, 0x002, 0x004, 0x008
@@ -120,7 +122,7 @@ end
 function EnsembleB200(; model::Symbol, steps_per_piece = 1, method = :tsit5, device = 0,
         model_data = Float64[], fim = (0, 0))
     e = EnsembleB200(model, steps_per_piece, method, device, collect(Float64, model_data), fim, C_NULL,
-        Sizes(0, 0, 0, 0, 0, 0, 0, 0), 0)
+        Sizes(0, 0, 0, 0, 0, 0, 0, 0, 0), 0)
     finalizer(e) do x
         x.handle == C_NULL || ccall((:cb200_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle)
     end
@@ -172,7 +174,7 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
         check(ccall((:cb200_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h), "cb200_create")
     end
     e.handle = h[]
-    s = Ref(Sizes(0, 0, 0, 0, 0, 0, 0, 0))
+    s = Ref(Sizes(0, 0, 0, 0, 0, 0, 0, 0, 0))
     check(ccall((:cb200_get_sizes, LIB), Cint, (Ptr{Cvoid}, Ref{Sizes}), e.handle, s), "cb200_get_sizes")
     e.sizes = s[]
     e.nx = nx
@@ -210,7 +212,7 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init jac crit status begin
         o = Out(ptr(xend), ptr(sens), ptr(traj), ptr(dk), ptr(ds), ptr(obj), ptr(grad), ptr(fim),
             (want & WANT_FIM) != 0 ? pointer(fsum) : Ptr{Float64}(C_NULL), C_NULL, C_NULL,
-            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), Ptr{Float64}(C_NULL), pointer(status))
+            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), pointer(status))
         check(ccall((:cb200_eval, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, UInt32, UInt32, Ref{Out}),
                 e.handle, P, B, size(P, 1), want, 0, o), "cb200_eval")

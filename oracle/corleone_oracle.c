@@ -887,6 +887,63 @@ int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int 
     return 0;
 }
 
+/* Tangents of the merged trajectory samples (what ForwardDiff through `traj` yields; the point constraints of
+ * src/dynprob.jl:30-58,89-103 differentiate these): du_out[r + nrow*(sample + nsamples*d)], quadrature rows carry
+ * the accumulated sums of multiple_shooting.jl:171-177 and therefore depend on earlier intervals' variables too. */
+int co_eval_traj(const co_layer *L, const double *ps, const double *dps, int nd, int method, int K, double *u_out,
+                 double *du_out)
+{
+    if (nd > CO_ND) return -1;
+    g_nd = nd;
+    const int nx = L->nx, nrow = nx + L->nact, I = L->I;
+    int maxM = 0, maxv = 0, nsamples = 1;
+    for (int i = 0; i < I; i++) {
+        if (L->iv[i].M > maxM) maxM = L->iv[i].M;
+        int nv = L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
+        if (nv > maxv) maxv = nv;
+        nsamples += L->iv[i].M;
+    }
+    dual **S = (dual **)malloc(sizeof(dual *) * (size_t)I);
+    double *ts = (double *)malloc(sizeof(double) * (size_t)(maxM + 1));
+    dual *vars = (dual *)malloc(sizeof(dual) * (size_t)(maxv > 0 ? maxv : 1));
+    for (int i = 0; i < I; i++) {
+        const interval *it = &L->iv[i];
+        int nv = it->n_u0 + L->ntp + it->n_c;
+        for (int k = 0; k < nv; k++) {
+            vars[k].v = ps[it->var_off + k];
+            for (int d = 0; d < nd; d++) vars[k].d[d] = dps[(size_t)d * L->nvars + it->var_off + k];
+        }
+        S[i] = (dual *)malloc(sizeof(dual) * (size_t)((it->M + 1) * nrow));
+        solve_interval(L, i, vars, method, K, S[i], ts, it->shooting);
+    }
+    for (int i = 1; i < I; i++) {
+        const interval *prev = &L->iv[i - 1], *it = &L->iv[i];
+        for (int q = 0; q < L->nquad; q++) {
+            int r = L->quad[q] - 1;
+            dual qp = S[i - 1][(size_t)prev->M * nrow + r];
+            for (int j = 0; j <= it->M; j++) S[i][(size_t)j * nrow + r] = dadd(S[i][(size_t)j * nrow + r], qp);
+        }
+    }
+    int so = 0;
+    for (int i = 0; i < I; i++) {
+        const interval *it = &L->iv[i];
+        for (int j = 0; j < it->M + (i == I - 1); j++)
+            for (int r = 0; r < nrow; r++) {
+                if (u_out) u_out[r + (size_t)nrow * (so + j)] = S[i][(size_t)j * nrow + r].v;
+                if (du_out)
+                    for (int d = 0; d < nd; d++)
+                        du_out[r + (size_t)nrow * ((so + j) + (size_t)nsamples * d)] = S[i][(size_t)j * nrow + r].d[d];
+            }
+        so += it->M;
+    }
+    for (int i = 0; i < I; i++) free(S[i]);
+    free(S);
+    free(ts);
+    free(vars);
+    g_nd = 0;
+    return 0;
+}
+
 int co_forward_init(const co_layer *L, double *ps, const int *fixed, int nfixed, int method, int K)
 {
     g_nd = 0;

@@ -113,6 +113,10 @@ int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int 
             double *t_out, double *u_out, double *xend, double *dxend, double *defk, double *ddefk,
             double *defs, double *ddefs, double *last, double *dlast);
 
+/* tangents of the merged trajectory samples: du_out[r + nrow*(sample + nsamples*d)] (column-major, nd trailing) */
+int co_eval_traj(const co_layer *L, const double *ps, const double *dps, int nd, int method, int K, double *u_out,
+                 double *du_out);
+
 /* forward_initialization (src/node_initialization.jl:152-170): overwrites the u0 entries of ps in place */
 int co_forward_init(const co_layer *L, double *ps, const int *fixed_indices, int nfixed, int method, int K);
 

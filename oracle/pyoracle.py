@@ -85,6 +85,8 @@ def lib():
         L.co_default_ps.argtypes = [C.c_void_p, dp]
         L.co_eval.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int] + [dp] * 10
         L.co_eval.restype = C.c_int
+        L.co_eval_traj.argtypes = [C.c_void_p, dp, dp, C.c_int, C.c_int, C.c_int, dp, dp]
+        L.co_eval_traj.restype = C.c_int
         L.co_forward_init.argtypes = [C.c_void_p, dp, ip, C.c_int, C.c_int, C.c_int]
         L.co_forward_init.restype = C.c_int
         L.co_bench_units.argtypes = [C.c_void_p, dp, C.c_int64, C.c_int64, C.c_int64, C.c_int, C.c_int,
@@ -269,6 +271,23 @@ class OracleLayer:
             Jd[:, c0:c0 + nd] = r["ddefk"]
             Jl[:, c0:c0 + nd] = r["dlast"]
         return Jx, Jd, Jl
+
+    def traj_jacobian(self, ps, method="tsit5", K=1):
+        """Dense d(merged trajectory samples)/d(ps): (nrow, nsamples, nvars), quadrature rows accumulated as in
+        multiple_shooting.jl:171-177 (what the point constraints of dynprob.jl differentiate)."""
+        ps = np.ascontiguousarray(ps, dtype=np.float64)
+        n = self.nvars
+        J = np.zeros((self.nrow, self.nsamples, n))
+        u = np.zeros((self.nrow, self.nsamples), order="F")
+        for c0 in range(0, n, CO_ND):
+            nd = min(CO_ND, n - c0)
+            seeds = np.zeros((n, nd), order="F")
+            seeds[c0 + np.arange(nd), np.arange(nd)] = 1.0
+            du = np.zeros((self.nrow, self.nsamples, nd), order="F")
+            rc = lib().co_eval_traj(self.h, _dp(ps), _dp(seeds), nd, METHODS[method], K, _dp(u), _dp(du))
+            assert rc == 0
+            J[:, :, c0:c0 + nd] = du
+        return u, J
 
     def bench_units(self, ps_batch, method="tsit5", K=1, with_sens=True, nthreads=0, b_range=None):
         """ps_batch: (B, nvars) C-contiguous == nvars x B column-major. Returns (seconds, units, checksum)."""

@@ -32,8 +32,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8
-    assert ctypes.sizeof(native.Out) == 12 * 8 + 8 + 8 + 8 + 8 + 8
-    assert ctypes.sizeof(native.Sizes) == 8 * 8
+    assert ctypes.sizeof(native.Out) == 12 * 8 + 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(native.Sizes) == 9 * 8
 
 
 def test_bad_descriptor_is_rejected_before_any_device_work():

@@ -472,3 +472,31 @@ def test_reference_goldens_through_the_device_path():
     p = -2.0
     F_exact = (np.exp(2 * p) * (2 * p * p - 2 * p + 1) - 1) / (4 * p ** 3)
     assert abs(r["fim"][0, 0] - F_exact) < 1e-10 and abs(r["xend"][0, 0] - np.exp(p)) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["lotka_quad", "lqr", "dense20", "lotka_ss"])
+def test_trajectory_sensitivities_for_point_constraints(name):
+    """d(every saved trajectory sample)/d(ps): WANT_TRAJ_SENS + host assembly == the oracle's tangents through the
+    merged trajectory (what the point constraints of src/dynprob.jl:30-58 differentiate)"""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    from oracle import pyoracle as po
+    rng = np.random.default_rng(59)
+    spec, alg = {"lotka_quad": (P.lotka_spec(controls=rng.uniform(0, 1, 120), quadrature=True), cb.Tsit5(2)),
+                 "lqr": (P.lqr_spec(7, rng), cb.RK4(2)),
+                 "dense20": (P.dense20_spec(3, rng), cb.Tsit5(2)),
+                 "lotka_ss": (P.lotka_spec(shooting_points=None, controls=rng.uniform(0, 1, 120), tunable_ic=[1, 2]),
+                              cb.Tsit5(1))}[name]
+    O = po.OracleLayer(spec)
+    lay = P.product_layer(spec, alg)
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    B = 4
+    ps = batch_ps(O, B, rng)
+    r = N.eval_host(ps, nat.WANT_TRAJ | nat.WANT_TRAJ_SENS | nat.WANT_SENS)
+    method = "tsit5" if alg.method_id == 0 else "rk4"
+    for b in (0, B - 1):
+        u, Jref = O.traj_jacobian(ps[b], method=method, K=alg.steps_per_piece)
+        assert rel_err(r["traj"][b].reshape(O.nsamples, O.nrow).T, u) <= RTOL
+        J = cb.trajectory_jacobian(lay, st, ps_t, r, b)
+        assert rel_err(J, Jref) <= RTOL
