@@ -220,7 +220,9 @@ __device__ __forceinline__ void save_sens_sample(const ShootOut &o, long long ro
 
 // MINB: resident blocks of 128 threads per SM the register allocation must allow (__launch_bounds__); chosen
 // per (model, G) in the model's dispatch table from ptxas -v (largest value without spills in the step loop).
-template <class Mdl, int G, int METHOD, bool UNI, int MINB>
+// TS: also store the sensitivities at every saved sample (WANT_TRAJ_SENS) -- a separate instantiation, so that the
+// common case keeps its register allocation and instruction schedule.
+template <class Mdl, int G, int METHOD, bool UNI, int MINB, bool TS>
 __global__ void __launch_bounds__(128, MINB)
 shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B, const ShootOut o)
 {
@@ -343,7 +345,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         }
         if (o.traj && live && r == 0 && j == 0)  // save_start = (j == 1)
             save_sample<Mdl>(L, o, (long long)so, nrow, b, yd, yq, p);
-        if constexpr (G > 0) {
+        if constexpr (G > 0 && TS) {
             if (o.tsens && live && j == 0) save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i), b, dmap, yd, yq);
         }
         if constexpr (UNI) {
@@ -360,7 +362,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
             save_sample<Mdl>(L, o, (long long)(so + j + 1), nrow, b, yd, yq, p);
-        if constexpr (G > 0) {
+        if constexpr (G > 0 && TS) {
             if (o.tsens && live && (j + 1 < M || last_interval))
                 save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i) + (long long)(j + 1) * ns * NX, b, dmap, yd, yq);
         }
@@ -575,10 +577,19 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
         grid = dim3((unsigned)((nthreads + bs - 1) / bs), 1, 1);
     else
         grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.I, (unsigned)L.R);
+    if constexpr (G > 0) {
+        if (o.tsens) {
+            if (L.uniform_h)
+                shoot_kernel<Mdl, G, METHOD, true, 1, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            else
+                shoot_kernel<Mdl, G, METHOD, false, 1, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            return (int)cudaGetLastError();
+        }
+    }
     if (L.uniform_h)
-        shoot_kernel<Mdl, G, METHOD, true, MINB><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+        shoot_kernel<Mdl, G, METHOD, true, MINB, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
     else
-        shoot_kernel<Mdl, G, METHOD, false, MINB><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+        shoot_kernel<Mdl, G, METHOD, false, MINB, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
     return (int)cudaGetLastError();
 }
 
