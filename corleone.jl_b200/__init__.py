@@ -21,6 +21,7 @@ from .problem import MODEL_REGISTRY, ODEProblem, RK4, Tsit5
 from .single_shooting import InitialConditionRemaker, SingleShootingLayer, from_vec, to_vec
 from .trajectory import Trajectory, is_shooting_solution, shooting_violations
 from . import native
+from .dynprob import CorleoneDynamicOptProblem, solve_slsqp
 from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion, FisherECriterion,
                        batched_criteria, criteria_gradient, global_information_gain, local_information_gain)
 

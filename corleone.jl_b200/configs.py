@@ -162,8 +162,10 @@ def layer_from_spec(spec, alg, **kw):
     """Build the SingleShootingLayer / MultipleShootingLayer a spec describes."""
     prob = ODEProblem(spec["model"], spec["u0"], spec["tspan"], spec["p0"], model_data=spec.get("model_data"))
     names = spec.get("control_names") or [f"u{k + 1}" for k in range(len(spec["controls"]))]
-    ctr = [(ci, ControlParameter(t, name=n, controls=(np.zeros(len(t)) if u is None else u)))
-           for (ci, t, u), n in zip(spec["controls"], names)]
+    cb = spec.get("control_bounds") or [None] * len(spec["controls"])
+    ctr = [(ci, ControlParameter(t, name=n, controls=(np.zeros(len(t)) if u is None else u),
+                                 **({} if b is None else {"bounds": b})))
+           for (ci, t, u), n, b in zip(spec["controls"], names, cb)]
     args = dict(controls=ctr, tunable_ic=spec.get("tunable_ic", []),
                 quadrature_indices=spec.get("quadrature_indices", []))
     args.update(kw)

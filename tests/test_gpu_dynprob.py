@@ -1,0 +1,86 @@
+"""The NLP assembly of src/dynprob.jl on top of the device path: the reference's example tests
+(test/examples/lotka_oc.jl, test/examples/lotka_ms.jl) with SciPy's SLSQP standing in for Ipopt."""
+import numpy as np
+import pytest
+
+import problems as P
+
+pytestmark = pytest.mark.gpu
+
+
+def _lotka_layer(cb, shooting_points, K, **kw):
+    spec = P.lotka_spec(shooting_points=shooting_points)
+    spec["control_names"] = ["fishing"]
+    spec["control_bounds"] = [(0.0, 1.0)]
+    return P.product_layer(spec, cb.Tsit5(K), bounds_p=([1.0, 1.0], [1.0, 1.0]), **kw)
+
+
+def test_lotka_ms_callbacks_reference_goldens():
+    """test/examples/lotka_ms.jl:45-48: objective and constraint vector at the initial point"""
+    import corleone_b200 as cb
+    lay = _lotka_layer(cb, [0.0, 3.0, 6.0, 9.0], 8, bounds_ic=([0.1, 0.1, 0.0], [100.0, 100.0, 100.0]))
+    prob = cb.CorleoneDynamicOptProblem(lay, "x₃")
+    assert len(prob.u0) == lay.parameterlength() == 137
+    assert abs(prob.objective(prob.u0) - 1.2417260108009376) < 1e-9          # reference atol 1e-4
+    gold = np.array([1.3757549609694821, 0.2235735751355118, 1.24172601080094, 1.375754960969481, 0.22357357513551102,
+                     1.2417260108009385, 1.3757549609694824, 0.2235735751355129, 1.2417260108009414] + [0.0] * 6)
+    c = prob.constraints(prob.u0)
+    assert c.shape == (15,) and np.allclose(c, gold, atol=1e-10, rtol=0)
+    assert np.array_equal(prob.lcons, np.zeros(15)) and np.array_equal(prob.ucons, np.zeros(15))
+    # bounds as the reference test checks them
+    assert np.all(prob.lb[-30:] == 0.0) and np.all(prob.ub[-30:] == 1.0)
+
+
+def test_lotka_single_shooting_optimum():
+    """test/examples/lotka_oc.jl:80-94: f(u0) = 6.062277454291031, optimum 1.344336 (atol 1e-4)"""
+    import corleone_b200 as cb
+    lay = _lotka_layer(cb, None, 2)
+    prob = cb.CorleoneDynamicOptProblem(lay, "x₃")
+    assert abs(prob.objective(prob.u0) - 6.062277454291031) < 1e-6
+    res = cb.solve_slsqp(prob, maxiter=400, ftol=1e-12)
+    assert res.success, res.message
+    assert abs(res.fun - 1.344336) < 1e-4
+    assert np.all(res.x[:2] == 1.0)                                           # p_opt.p == p0[2:end]
+    assert np.all((res.x[2:] >= -1e-12) & (res.x[2:] <= 1 + 1e-12))
+
+
+def test_lotka_multiple_shooting_optimum():
+    """test/examples/lotka_ms.jl:50-56: the same optimum through 15 matching constraints"""
+    import corleone_b200 as cb
+    lay = _lotka_layer(cb, [0.0, 3.0, 6.0, 9.0], 2, bounds_ic=([0.1, 0.1, 0.0], [100.0, 100.0, 100.0]))
+    prob = cb.CorleoneDynamicOptProblem(lay, "x₃")
+    res = cb.solve_slsqp(prob, maxiter=600, ftol=1e-12)
+    # the parameter matchings p_i - p_{i+1} = 0 are redundant with lb.p == ub.p: SLSQP may stop at the optimum with
+    # "positive directional derivative" (status 8) on that degenerate set instead of status 0
+    assert res.status in (0, 8), res.message
+    assert abs(res.fun - 1.344336) < 1e-4
+    assert np.max(np.abs(prob.constraints(res.x))) < 1e-5       # the reference solves with Ipopt tol = 1e-3
+
+
+def test_point_constraints_and_their_jacobian():
+    """point constraints (src/dynprob.jl:89-103) stacked before the shooting constraints; Jacobian vs central differences"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(61)
+    spec = P.lotka_spec(shooting_points=[0.0, 3.0, 6.0, 9.0], controls=rng.uniform(0, 1, 120), quadrature=True)
+    spec["control_names"] = ["fishing"]
+    lay = P.product_layer(spec, cb.Tsit5(2))
+    tcon = [1.0, 3.0, 4.5, 6.0, 11.9]
+    prob = cb.CorleoneDynamicOptProblem(lay, "x₃", ("x₁", dict(t=tcon, bounds=(0.4, np.inf))),
+                                        ("x₃", dict(t=[9.0, 12.0], bounds=(0.0, 5.0))))
+    x = prob.u0 + 0.05 * rng.standard_normal(len(prob.u0))
+    f, g, c, J = prob.value_and_derivatives(x)
+    assert prob.n_point == len(c) - prob.n_shoot and J.shape == (len(c), len(x))
+    assert np.all(prob.lcons[:5] == 0.4) and np.all(np.isinf(prob.ucons[:5]))
+    h = 1e-6
+    for v in rng.choice(len(x), 10, replace=False):
+        xp, xm = x.copy(), x.copy()
+        xp[v] += h
+        xm[v] -= h
+        fd_c = (prob.constraints(xp) - prob.constraints(xm)) / (2 * h)
+        fd_f = (prob.objective(xp) - prob.objective(xm)) / (2 * h)
+        assert np.allclose(J[:, v], fd_c, rtol=1e-6, atol=2e-7), v
+        assert abs(g[v] - fd_f) < 2e-7 * max(1.0, abs(fd_f))
+    # batch axis: the same numbers for several candidates at once
+    X = x[None, :] + 0.01 * rng.standard_normal((5, len(x)))
+    fo, co, go = prob.evaluate_batch(X)
+    assert abs(fo[2] - prob.objective(X[2])) < 1e-13 and np.allclose(co[4], prob.constraints(X[4]), rtol=0, atol=1e-13)
