@@ -23,7 +23,8 @@ from .trajectory import Trajectory, is_shooting_solution, shooting_violations
 from . import native
 from .dynprob import CorleoneDynamicOptProblem, solve_slsqp
 from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion, FisherECriterion,
-                       batched_criteria, criteria_gradient, global_information_gain, local_information_gain)
+                       batched_criteria, criteria_gradient, global_information_gain, local_information_gain,
+                       sampling_sum_matrix, solve_oed_slsqp)
 
 
 def setup(rng, layer):

@@ -113,3 +113,54 @@ def global_information_gain(traj_samples, F_tf, bx: int, nf: int, nobs: int):
     x = _hxG(traj_samples, bx, nf, nobs)
     x = np.einsum("...koc,...cd->...kod", x, C) if C.ndim > 2 else x @ C
     return x[..., :, None] * x[..., None, :]
+
+
+def sampling_sum_matrix(layer, st, ps_like, rows):
+    """Linear map of the sampling sums (lib/CorleoneOED/src/oed.jl:610-618): for every measurement control (row of the
+    index grid, 0-based in `rows`) the integral of its piecewise-constant weight, sum_j controls[index_grid[row, j]]
+    * dt_j, as a matrix acting on the flat variable vector; a multiple-shooting layer sums over the intervals (:566-570)."""
+    from .multiple_shooting import get_block_structure
+    from .single_shooting import SingleShootingLayer, _flatten_chunks
+    single = isinstance(layer, SingleShootingLayer)
+    sts = [st] if single else list(st.values())
+    pss = [ps_like] if single else list(ps_like.values())
+    blocks = get_block_structure(layer)
+    A = np.zeros((len(rows), int(blocks[-1])))
+    for i, (s, p) in enumerate(zip(sts, pss)):
+        grid = np.asarray(_flatten_chunks(s["index_grid"]), dtype=np.int64)
+        tsp = _flatten_chunks(s["tspans"])
+        dts = np.array([b - a for a, b in tsp])
+        c0 = int(blocks[i]) + len(p["u0"]) + len(p["p"])
+        for k, row in enumerate(rows):
+            np.add.at(A[k], c0 + grid[row] - 1, dts)
+    return A
+
+
+def solve_oed_slsqp(layer, st, ps_like, nat, criterion: int = 0, M=None, measurement_rows=(), fim_init=None, x0=None,
+                    maxiter=300, ftol=1e-12):
+    """Minimise one criterion (index into ORDER) of F = F_init + F(t_end) over the flat variables within their bounds,
+    subject to sampling sums <= M (lib/CorleoneOED/ext/CorleoneOEDOptimizationExtension.jl), with SciPy's SLSQP standing
+    in for Ipopt.  Value, FIM and second-order sensitivities come from one cb200_eval per iterate; single shooting."""
+    from scipy.optimize import Bounds, LinearConstraint, minimize
+    from .multiple_shooting import get_bounds
+    from .single_shooting import to_vec
+    x0 = to_vec(ps_like) if x0 is None else np.asarray(x0, dtype=np.float64)
+    lo, hi = get_bounds(layer)
+    cache = {}
+
+    def ev(x):
+        key = x.tobytes()
+        if cache.get("key") != key:
+            crit, F = batched_criteria(nat, x[None, :], fim_init=fim_init)
+            g = criteria_gradient(nat, x[None, :], fim_init=fim_init)
+            cache.update(key=key, val=(float(crit[0, criterion]), g[0, criterion].copy(), F[0]))
+        return cache["val"]
+
+    cons = []
+    if M is not None and len(measurement_rows):
+        cons.append(LinearConstraint(sampling_sum_matrix(layer, st, ps_like, list(measurement_rows)), -np.inf,
+                                     np.asarray(M, dtype=np.float64)))
+    res = minimize(lambda x: ev(x)[0], x0, jac=lambda x: ev(x)[1], bounds=Bounds(to_vec(lo), to_vec(hi)),
+                   constraints=cons, method="SLSQP", options=dict(maxiter=maxiter, ftol=ftol))
+    res.fim = ev(res.x)[2]
+    return res

@@ -84,3 +84,26 @@ def test_point_constraints_and_their_jacobian():
     X = x[None, :] + 0.01 * rng.standard_normal((5, len(x)))
     fo, co, go = prob.evaluate_batch(X)
     assert abs(fo[2] - prob.objective(X[2])) < 1e-13 and np.allclose(co[4], prob.constraints(X[4]), rtol=0, atol=1e-13)
+
+
+def test_lotka_oed_design_optimum():
+    """lib/CorleoneOED/test/core/lotka_oed.jl:105-145 (single shooting): sampling sums [12, 12] at the start, A-criterion
+    0.05352869250783344; optimum under sampling sums <= 4: A = 0.03707508955468313 and the golden Fisher matrix"""
+    import corleone_b200 as cb
+    spec = P.lotka_oed_spec()
+    spec["control_bounds"] = [(0.0, 1.0)] * 3
+    lay = P.product_layer(spec, cb.Tsit5(4), bounds_p=([1.0, 1.0], [1.0, 1.0]))
+    ps_t, st = cb.setup(None, lay)
+    st["_fim"] = (7, 2)
+    N = lay._native(st, ps_t)
+    x0 = cb.to_vec(ps_t)
+    A = cb.sampling_sum_matrix(lay, st, ps_t, [1, 2])
+    assert np.allclose(A @ x0, [12.0, 12.0], atol=1e-12)                       # lotka_oed.jl:61-64
+    lo, hi = cb.get_bounds(lay)
+    assert np.array_equal(cb.to_vec(lo), np.r_[np.ones(2), np.zeros(48 + 24 + 79)])     # :58-59
+    assert np.array_equal(cb.to_vec(hi), np.ones(2 + 48 + 24 + 79))
+    res = cb.solve_oed_slsqp(lay, st, ps_t, N, criterion=0, M=[4.0, 4.0], measurement_rows=(1, 2), maxiter=600)
+    assert res.success and abs(res.fun / 0.03707508955468313 - 1) < 1e-5, (res.fun, res.message)   # measured: -1.3e-7
+    Fgold = np.array([[38.58695777364362, 5.304118558316029], [5.304118558316029, 92.03122059902915]])
+    assert np.allclose(res.fim, Fgold, rtol=1e-5), res.fim                                        # measured: 1e-7
+    assert np.all(A @ res.x <= 4.0 + 1e-8)
