@@ -158,6 +158,33 @@ def batchreactor_spec(n_intervals=4, rng=None):
                 shooting_points=[k / n_intervals for k in range(n_intervals)])
 
 
+def lotkacomp_spec(n_intervals=4, rng=None):
+    """competitive Lotka-Volterra with Lagrange state (.../lotka_competitive.jl)"""
+    rng = np.random.default_rng(SEED0 + 14) if rng is None else rng
+    t = np.arange(40) / 4.0
+    return dict(model="lotkacomp3", u0=[0.5, 1.5, 0.0], p0=[0.5], tspan=(0.0, 10.0),
+                controls=[(1, t, rng.uniform(0, 1, 40))], tunable_ic=[], quadrature_indices=[3],
+                shooting_points=[10.0 * k / n_intervals for k in range(n_intervals)])
+
+
+def f8_spec(n_intervals=4, rng=None):
+    """F-8 aircraft, time-optimal: final time T tunable, control u (.../f8.jl), normalised time (0, 1)"""
+    rng = np.random.default_rng(SEED0 + 15) if rng is None else rng
+    t = np.arange(24) / 24.0
+    return dict(model="f8aircraft4", u0=[0.4655, 0.0, 0.0, 0.0], p0=[0.5, 0.5], tspan=(0.0, 1.0),
+                controls=[(2, t, rng.uniform(0, 1, 24))], tunable_ic=[], quadrature_indices=[],
+                shooting_points=[k / n_intervals for k in range(n_intervals)])
+
+
+def doubleosc_spec(n_intervals=3, rng=None):
+    """double oscillator (.../double_oscillator.jl); explicit time dependence carried by the state tau' = 1"""
+    rng = np.random.default_rng(SEED0 + 16) if rng is None else rng
+    t = np.arange(30) / 5.0
+    return dict(model="doubleosc6", u0=[0.0, 0.0, 0.0, 0.0, 0.0, 0.0], p0=[1.0], tspan=(0.0, 6.0),
+                controls=[(1, t, rng.uniform(-1, 1, 30))], tunable_ic=[3, 4], quadrature_indices=[6],
+                shooting_points=[6.0 * k / n_intervals for k in range(n_intervals)])
+
+
 def layer_from_spec(spec, alg, **kw):
     """Build the SingleShootingLayer / MultipleShootingLayer a spec describes."""
     prob = ODEProblem(spec["model"], spec["u0"], spec["tspan"], spec["p0"], model_data=spec.get("model_data"))

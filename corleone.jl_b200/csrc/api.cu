@@ -337,6 +337,9 @@ static int default_G(int model)
     case CB200_MODEL_QUADROTOR7: return 1;
     case CB200_MODEL_THREETANK4: return 2;
     case CB200_MODEL_BATCHREACTOR2: return 2;
+    case CB200_MODEL_LOTKACOMP3: return 2;
+    case CB200_MODEL_F8AIRCRAFT4: return 2;
+    case CB200_MODEL_DOUBLEOSC6: return 1;
     case CB200_MODEL_DENSE20: return 1;
     case CB200_MODEL_LOTKA2_OED: return 1;   // second-order sensitivities of [x; G; F]: 12 dynamic + 6 quadrature per thread (G = 2 spills)
     case CB200_MODEL_LIN1D_OED: return 2;
@@ -362,6 +365,9 @@ static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
     case CB200_MODEL_QUADROTOR7: *nx = 7; *np = 4; d = 6; break;
     case CB200_MODEL_THREETANK4: *nx = 4; *np = 3; d = 3; break;
     case CB200_MODEL_BATCHREACTOR2: *nx = 2; *np = 1; d = 2; break;
+    case CB200_MODEL_LOTKACOMP3: *nx = 3; *np = 1; d = 2; break;
+    case CB200_MODEL_F8AIRCRAFT4: *nx = 4; *np = 2; d = 3; break;
+    case CB200_MODEL_DOUBLEOSC6: *nx = 6; *np = 1; d = 5; break;
     default: return -1;
     }
     if (nxd) *nxd = d;
@@ -386,6 +392,9 @@ static int launch_model(int model, int G, int method, const DevLayer &L, const d
     case CB200_MODEL_QUADROTOR7: return launch_quadrotor7(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_THREETANK4: return launch_threetank4(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_BATCHREACTOR2: return launch_batchreactor2(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKACOMP3: return launch_lotkacomp3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_F8AIRCRAFT4: return launch_f8aircraft4(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DOUBLEOSC6: return launch_doubleosc6(G, method, L, ps, ldb, B, o, s);
     default: return -1000;
     }
 }
@@ -408,6 +417,9 @@ static int forward_model(int model, int method, const DevLayer &L, double *ps, l
     case CB200_MODEL_QUADROTOR7: return forward_quadrotor7(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_THREETANK4: return forward_threetank4(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_BATCHREACTOR2: return forward_batchreactor2(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKACOMP3: return forward_lotkacomp3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_F8AIRCRAFT4: return forward_f8aircraft4(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DOUBLEOSC6: return forward_doubleosc6(method, L, ps, ldb, B, fixed, s);
     default: return -1000;
     }
 }

@@ -133,6 +133,18 @@ int launch_batchreactor2(int G, int method, const DevLayer &L, const double *ps,
         const ShootOut &o, cudaStream_t s);
 int forward_batchreactor2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s);
+int launch_lotkacomp3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lotkacomp3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_f8aircraft4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_f8aircraft4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_doubleosc6(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_doubleosc6(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
 
 }  // namespace cb200

@@ -473,4 +473,62 @@ struct BatchReactorRhs {
 };
 using BatchReactor2 = AutoJvp<BatchReactorRhs>;
 
+
+// Competitive Lotka-Volterra with its Lagrange term (.../lotka_competitive.jl:9-31): states (x0, x1, cost), p = (u)
+struct LotkaCompRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double c1 = 0.1, c2 = 0.4, al = 1.2, K = 1.8;
+        dx[0] = x[0] * (1.0 - (x[0] + al * x[1]) / K) - c1 * x[0] * p[0];
+        dx[1] = x[1] * (1.0 - (x[0] + x[1]) / K) - c2 * x[1] * p[0];
+        const T e0 = x[0] - 1.0, e1 = x[1] - 1.0;
+        dx[2] = e0 * e0 + e1 * e1;
+    }
+};
+using LotkaComp3 = AutoJvp<LotkaCompRhs>;
+
+// F-8 aircraft, time-optimal (.../f8.jl:9-41): states (x0, x1, x2, obj), p = (T, u); obj' = T is quadrature-like
+struct F8Rhs {
+    static constexpr int NX = 4, NXD = 3, NQ = 1, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double xi = 0.05236;
+        const T x0sq = x[0] * x[0], x0cu = x0sq * x[0];
+        T d1 = -0.877 * x[0] + x[2] - 0.088 * x[0] * x[2] + 0.47 * x0sq - 0.019 * (x[1] * x[1]);
+        d1 = d1 - x0sq * x[2] + 3.846 * x0cu;
+        d1 = d1 + (0.215 * xi - 0.63 * xi * xi * xi) - (0.28 * xi) * x0sq + (0.47 * xi * xi) * x[0];
+        d1 = d1 - ((0.215 * xi - 0.63 * xi * xi * xi) - (0.28 * xi) * x0sq) * (2.0 * p[1]);
+        T d3 = -4.208 * x[0] - 0.396 * x[2] - 0.47 * x0sq - 3.564 * x0cu;
+        d3 = d3 + (20.967 * xi - 61.4 * xi * xi * xi) - (6.265 * xi) * x0sq + (46.0 * xi * xi) * x[0];
+        d3 = d3 - ((20.967 * xi - 61.4 * xi * xi * xi) - (6.265 * xi) * x0sq) * (2.0 * p[1]);
+        dx[0] = p[0] * d1;
+        dx[1] = p[0] * x[2];
+        dx[2] = p[0] * d3;
+        dx[3] = p[0];
+    }
+};
+using F8Aircraft4 = AutoJvp<F8Rhs>;
+
+// Double oscillator with its Lagrange term (.../double_oscillator.jl:9-38).  The right-hand side depends on time
+// (sin(2 pi t / T)); the kernels integrate autonomous systems, so time rides along as a state with tau' = 1:
+// states (x0, x1, x2, x3, tau, cost), p = (u)
+struct DoubleOscRhs {
+    static constexpr int NX = 6, NXD = 5, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double m1 = 200.0, m2 = 2.0, k1 = 100.0, k2 = 3.0, c = 0.5;   // T = 2 pi: sin(2 pi / T * t) = sin(t)
+        dx[0] = x[2];
+        dx[1] = x[3];
+        dx[2] = (-(k1 + k2) / m1) * x[0] + (k2 / m1) * x[1] + (1.0 / m1) * sin(x[4]);
+        dx[3] = (k2 / m2) * x[0] - (k2 / m2) * x[1] - (c / m2) * (1.0 - p[0]) * x[3];
+        dx[4] = 1.0 + 0.0 * x[4];
+        dx[5] = 0.5 * (x[0] * x[0] + x[1] * x[1] + p[0] * p[0]);
+    }
+};
+using DoubleOsc6 = AutoJvp<DoubleOscRhs>;
+
 }  // namespace cb200

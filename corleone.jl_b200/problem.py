@@ -27,6 +27,9 @@ MODEL_REGISTRY = {
     "quadrotor7": (11, 7, 4),
     "threetank4": (12, 4, 3),
     "batchreactor2": (13, 2, 1),
+    "lotkacomp3": (14, 3, 1),
+    "f8aircraft4": (15, 4, 2),
+    "doubleosc6": (16, 6, 1),
 }
 
 # base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)

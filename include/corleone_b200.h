@@ -63,7 +63,10 @@ typedef enum {
     CB200_MODEL_ROCKET3 = 10,   /* goddarts_rocket.jl:16-40, p = (T, u) */
     CB200_MODEL_QUADROTOR7 = 11,    /* quadrotor.jl:9-52, p = (w1, w2, w3, u) */
     CB200_MODEL_THREETANK4 = 12,    /* three_tank.jl:9-53, p = (w1, w2, w3) */
-    CB200_MODEL_BATCHREACTOR2 = 13  /* batch_reactor.jl:9-17, p = (u) */
+    CB200_MODEL_BATCHREACTOR2 = 13, /* batch_reactor.jl:9-17, p = (u) */
+    CB200_MODEL_LOTKACOMP3 = 14,    /* lotka_competitive.jl:9-31 */
+    CB200_MODEL_F8AIRCRAFT4 = 15,   /* f8.jl:9-41, p = (T, u) */
+    CB200_MODEL_DOUBLEOSC6 = 16     /* double_oscillator.jl:9-38; time rides along as a state (tau' = 1) */
 } cb200_model;
 
 typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;

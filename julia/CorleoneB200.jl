@@ -94,7 +94,7 @@ const WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT = 0x010, 0x020, 0x040, 
 
 const MODELS = Dict(:lotka3 => 0, :lqr => 1, :lotka2 => 2, :lotka2_oed => 3, :lin1d => 4, :lin1d_oed => 5,
                     :dense20 => 6, :egerstedt => 7, :vdp3 => 8, :cartpole5 => 9, :rocket3 => 10, :quadrotor7 => 11, :threetank4 => 12,
-                    :batchreactor2 => 13)
+                    :batchreactor2 => 13, :lotkacomp3 => 14, :f8aircraft4 => 15, :doubleosc6 => 16)
 
 lasterror() = unsafe_string(ccall((:cb200_last_error, LIB), Cstring, ()))
 check(rc, what) = rc == 0 || error("$what failed ($rc): $(lasterror())")

@@ -268,6 +268,53 @@ static void rhs_batchreactor2(const dual *x, const dual *p, dual *du)
     du[1] = dsub(r1, r2);
 }
 
+/* lotka_competitive.jl:9-31: states (x0, x1, cost), p = (u) */
+static void rhs_lotkacomp3(const dual *x, const dual *p, dual *du)
+{
+    const double c1 = 0.1, c2 = 0.4, al = 1.2, K = 1.8;
+    dual a = dsub(dconst(1.0), dscale(dadd(x[0], dscale(x[1], al)), 1.0 / K));
+    dual b = dsub(dconst(1.0), dscale(dadd(x[0], x[1]), 1.0 / K));
+    du[0] = dsub(dmul(x[0], a), dscale(dmul(x[0], p[0]), c1));
+    du[1] = dsub(dmul(x[1], b), dscale(dmul(x[1], p[0]), c2));
+    dual e0 = daddc(x[0], -1.0), e1 = daddc(x[1], -1.0);
+    du[2] = dadd(dmul(e0, e0), dmul(e1, e1));
+}
+/* f8.jl:9-41: states (x0, x1, x2, obj), p = (T, u) */
+static void rhs_f8aircraft4(const dual *x, const dual *p, dual *du)
+{
+    const double xi = 0.05236;
+    dual x0sq = dmul(x[0], x[0]), x0cu = dmul(x0sq, x[0]);
+    dual d1 = dadd(dscale(x[0], -0.877), x[2]);
+    d1 = dsub(d1, dscale(dmul(x[0], x[2]), 0.088));
+    d1 = dadd(d1, dscale(x0sq, 0.47));
+    d1 = dsub(d1, dscale(dmul(x[1], x[1]), 0.019));
+    d1 = dsub(d1, dmul(x0sq, x[2]));
+    d1 = dadd(d1, dscale(x0cu, 3.846));
+    dual q1 = dsub(dconst(0.215 * xi - 0.63 * xi * xi * xi), dscale(x0sq, 0.28 * xi));
+    d1 = dadd(dadd(d1, q1), dscale(x[0], 0.47 * xi * xi));
+    d1 = dsub(d1, dmul(q1, dscale(p[1], 2.0)));
+    dual d3 = dsub(dsub(dsub(dscale(x[0], -4.208), dscale(x[2], 0.396)), dscale(x0sq, 0.47)), dscale(x0cu, 3.564));
+    dual q3 = dsub(dconst(20.967 * xi - 61.4 * xi * xi * xi), dscale(x0sq, 6.265 * xi));
+    d3 = dadd(dadd(d3, q3), dscale(x[0], 46.0 * xi * xi));
+    d3 = dsub(d3, dmul(q3, dscale(p[1], 2.0)));
+    du[0] = dmul(p[0], d1);
+    du[1] = dmul(p[0], x[2]);
+    du[2] = dmul(p[0], d3);
+    du[3] = p[0];
+}
+/* double_oscillator.jl:9-38 with time as a state: (x0, x1, x2, x3, tau, cost), p = (u) */
+static void rhs_doubleosc6(const dual *x, const dual *p, dual *du)
+{
+    const double m1 = 200.0, m2 = 2.0, k1 = 100.0, k2 = 3.0, c = 0.5;
+    du[0] = x[2];
+    du[1] = x[3];
+    du[2] = dadd(dadd(dscale(x[0], -(k1 + k2) / m1), dscale(x[1], k2 / m1)), dscale(dsin(x[4]), 1.0 / m1));
+    du[3] = dsub(dsub(dscale(x[0], k2 / m2), dscale(x[1], k2 / m2)),
+                 dscale(dmul(dsub(dconst(1.0), p[0]), x[3]), c / m2));
+    du[4] = dconst(1.0);
+    du[5] = dscale(dadd(dadd(dmul(x[0], x[0]), dmul(x[1], x[1])), dmul(p[0], p[0])), 0.5);
+}
+
 typedef void (*rhs_fn)(const dual *, const dual *, dual *);
 typedef void (*jac_fn)(const dual *, const dual *, dual *, dual *);
 static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, const dual *u, const dual *p,
@@ -312,6 +359,9 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_QUADROTOR7: rhs_quadrotor7(u, p, du); break;
     case CO_THREETANK4: rhs_threetank4(u, p, du); break;
     case CO_BATCHREACTOR2: rhs_batchreactor2(u, p, du); break;
+    case CO_LOTKACOMP3: rhs_lotkacomp3(u, p, du); break;
+    case CO_F8AIRCRAFT4: rhs_f8aircraft4(u, p, du); break;
+    case CO_DOUBLEOSC6: rhs_doubleosc6(u, p, du); break;
     default: break;
     }
 }

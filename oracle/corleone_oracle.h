@@ -46,7 +46,10 @@ enum co_model {
     CO_ROCKET3 = 10,    /* .../goddarts_rocket.jl:16-40, p = (T, u) */
     CO_QUADROTOR7 = 11, /* .../quadrotor.jl:9-52 (+ Lagrange state), p = (w1, w2, w3, u) */
     CO_THREETANK4 = 12, /* .../three_tank.jl:9-53 (+ Lagrange state), p = (w1, w2, w3) */
-    CO_BATCHREACTOR2 = 13 /* .../batch_reactor.jl:9-17, p = (u) */
+    CO_BATCHREACTOR2 = 13, /* .../batch_reactor.jl:9-17, p = (u) */
+    CO_LOTKACOMP3 = 14,  /* .../lotka_competitive.jl:9-31 (+ Lagrange state) */
+    CO_F8AIRCRAFT4 = 15, /* .../f8.jl:9-41, p = (T, u) */
+    CO_DOUBLEOSC6 = 16   /* .../double_oscillator.jl:9-38 (+ time and Lagrange states) */
 };
 
 enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };

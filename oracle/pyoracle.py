@@ -29,6 +29,9 @@ MODELS = {
     "quadrotor7": 11,
     "threetank4": 12,
     "batchreactor2": 13,
+    "lotkacomp3": 14,
+    "f8aircraft4": 15,
+    "doubleosc6": 16,
 }
 METHODS = {"tsit5": 0, "rk4": 1}
 CO_ND = 16

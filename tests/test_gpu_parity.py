@@ -375,7 +375,8 @@ def test_oed_criteria_gradient_vs_finite_differences():
         assert np.allclose(g[:, :, v], fd, rtol=2e-6, atol=1e-7), (v, g[:, :, v], fd)
 
 
-@pytest.mark.parametrize("name", ["vdp", "cartpole", "rocket", "quadrotor", "threetank", "batchreactor"])
+@pytest.mark.parametrize("name", ["vdp", "cartpole", "rocket", "quadrotor", "threetank", "batchreactor", "lotkacomp", "f8",
+                                  "doubleosc"])
 def test_benchmark_suite_models_forward_mode_ad(name):
     """right-hand sides of lib/OptimalControlBenchmarks written once on a generic scalar; the kernels take the
     directional derivatives by forward-mode AD on the device (sin, cos, exp, division covered)"""
@@ -384,7 +385,9 @@ def test_benchmark_suite_models_forward_mode_ad(name):
     spec, row, scale = {"vdp": (P.vdp_spec(5, rng), 3, 0.05), "cartpole": (P.cartpole_spec(4, rng), 5, 0.05),
                         "rocket": (P.rocket_spec(4, rng), 3, 0.001), "quadrotor": (P.quadrotor_spec(3, rng), 7, 0.05),
                         "threetank": (P.threetank_spec(4, rng), 4, 0.02),
-                        "batchreactor": (P.batchreactor_spec(4, rng), 2, 0.01)}[name]
+                        "batchreactor": (P.batchreactor_spec(4, rng), 2, 0.01),
+                        "lotkacomp": (P.lotkacomp_spec(4, rng), 3, 0.05), "f8": (P.f8_spec(4, rng), 4, 0.02),
+                        "doubleosc": (P.doubleosc_spec(3, rng), 6, 0.05)}[name]
     from oracle import pyoracle as po
     O = po.OracleLayer(spec)
     ps = O.default_ps()[None, :] + scale * rng.standard_normal((33, O.nvars))
