@@ -67,12 +67,15 @@ def combine_sums(parts: dict, device=None, group=None) -> dict:
     return out
 
 
-def gather_candidates(local, n_candidates: int, group=None):
+def gather_candidates(local, n_candidates: int, group=None, device=None):
     """All-gather per-candidate rows: local is (B_local, n) on this rank -> (n_candidates, n) on every
-    rank, candidates in global order (ranks hold contiguous shards, possibly of unequal size)."""
+    rank, candidates in global order (ranks hold contiguous shards, possibly of unequal size).  `device`: where the
+    collective runs (the rank's GPU for NCCL; None = where `local` lives, e.g. the CPU for gloo)."""
     import torch
     dist = _dist()
     local = torch.as_tensor(local)
+    if device is not None:
+        local = local.to(device)
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return local
     world = dist.get_world_size(group)
@@ -115,6 +118,6 @@ class ShardedEvaluator:
         if parts:
             res.update({k: v.cpu().numpy() for k, v in combine_sums(parts, self.device, self.group).items()})
         for k in gather:
-            res[k] = gather_candidates(res[k], ps_all.shape[0], self.group).cpu().numpy()
+            res[k] = gather_candidates(res[k], ps_all.shape[0], self.group, self.device).cpu().numpy()
         res["_shard"] = sh
         return res
