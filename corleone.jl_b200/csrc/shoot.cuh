@@ -57,12 +57,13 @@ __device__ __forceinline__ void rhs_all(const double *td, const double *p, const
     }
 }
 
-template <class Mdl, int G, int METHOD>
+template <class Mdl, int G, int METHOD, bool SQ = true>
 __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const double *p, const typename Mdl::Force *F,
                                                 const double *cf, int K)
 {
     constexpr int ND = Mdl::NXD * (1 + G), NQ = (Mdl::NQ * (1 + G) > 0) ? Mdl::NQ * (1 + G) : 1;
     constexpr int NQR = Mdl::NQ * (1 + G);
+    constexpr int Q0 = SQ ? 0 : Mdl::NQ;   // direction groups other than the first do not need the state's quadratures
     double kq[NQ];
     if constexpr (METHOD == 0) {
         // Accumulator form of the 7-stage scheme: as soon as a stage derivative k_j is known it is folded into
@@ -73,7 +74,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
         rhs_all<Mdl, G>(yd, p, F, k, kq);
         for (int s = 0; s < K; s++) {
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[15], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[15], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 s2[c] = fma(cf[0], k[c], yd[c]);
@@ -85,7 +86,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(s2, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[16], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[16], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 s3[c] = fma(cf[2], k[c], s3[c]);
@@ -96,7 +97,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(s3, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[17], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[17], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 s4[c] = fma(cf[5], k[c], s4[c]);
@@ -106,7 +107,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(s4, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[18], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[18], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 s5[c] = fma(cf[9], k[c], s5[c]);
@@ -115,7 +116,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(s5, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[19], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[19], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 s6[c] = fma(cf[14], k[c], s6[c]);
@@ -123,7 +124,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(s6, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[20], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[20], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) yd[c] = fma(cf[20], k[c], yd[c]);
             if (s + 1 < K)  // FSAL: k7 of this step is k1 of the next; after the last step it is never used
@@ -134,7 +135,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
         for (int s = 0; s < K; s++) {
             rhs_all<Mdl, G>(yd, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[2], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[2], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 acc[c] = fma(cf[2], k[c], yd[c]);
@@ -142,7 +143,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(td, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[3], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[3], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 acc[c] = fma(cf[3], k[c], acc[c]);
@@ -150,7 +151,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(td, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[3], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[3], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) {
                 acc[c] = fma(cf[3], k[c], acc[c]);
@@ -158,7 +159,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
             }
             rhs_all<Mdl, G>(td, p, F, k, kq);
 #pragma unroll
-            for (int c = 0; c < NQR; c++) yq[c] = fma(cf[2], kq[c], yq[c]);
+            for (int c = Q0; c < NQR; c++) yq[c] = fma(cf[2], kq[c], yq[c]);
 #pragma unroll
             for (int c = 0; c < ND; c++) yd[c] = fma(cf[2], k[c], acc[c]);
         }
@@ -170,17 +171,17 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
 // host table gives na = 1 + index of the last direction that is already switched on; the variable order (u0, p,
 // controls in time order) makes the live directions a prefix).  One instantiation per prefix length, selected by
 // a warp-uniform branch.
-template <class Mdl, int G, int METHOD, int GA = G>
+template <class Mdl, int G, int METHOD, bool SQ, int GA = G>
 __device__ __forceinline__ void integrate_active(int na, double *yd, double *yq, const double *p,
                                                  const typename Mdl::Force *F, const double *cf, int K)
 {
     if constexpr (GA == 0) {
-        integrate_piece<Mdl, 0, METHOD>(yd, yq, p, F, cf, K);
+        integrate_piece<Mdl, 0, METHOD, SQ>(yd, yq, p, F, cf, K);
     } else {
         if (na >= GA)
-            integrate_piece<Mdl, GA, METHOD>(yd, yq, p, F, cf, K);
+            integrate_piece<Mdl, GA, METHOD, SQ>(yd, yq, p, F, cf, K);
         else
-            integrate_active<Mdl, G, METHOD, (GA > 4 ? GA - 2 : GA - 1)>(na, yd, yq, p, F, cf, K);
+            integrate_active<Mdl, G, METHOD, SQ, (GA > 4 ? GA - 2 : GA - 1)>(na, yd, yq, p, F, cf, K);
     }
 }
 
@@ -349,7 +350,10 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
             if (o.tsens && live && j == 0) save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i), b, dmap, yd, yq);
         }
         if constexpr (UNI) {
-            integrate_active<Mdl, G, METHOD>(na, yd, yq, p, F, L.hA, L.K);
+            if (r == 0)   // block-uniform: only the first direction group reports the state (and its quadratures)
+                integrate_active<Mdl, G, METHOD, true>(na, yd, yq, p, F, L.hA, L.K);
+            else
+                integrate_active<Mdl, G, METHOD, false>(na, yd, yq, p, F, L.hA, L.K);
         } else {
             double cf[NCF];
             const double h = __ldg(L.ph + po + j);
@@ -357,7 +361,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
                 tsit5_coeffs(h, cf);
             else
                 rk4_coeffs(h, cf);
-            integrate_active<Mdl, G, METHOD>(na, yd, yq, p, F, cf, L.K);
+            integrate_active<Mdl, G, METHOD, true>(na, yd, yq, p, F, cf, L.K);
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
