@@ -25,6 +25,8 @@ from .dynprob import CorleoneDynamicOptProblem, solve_slsqp
 from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, FisherDCriterion, FisherECriterion,
                        batched_criteria, criteria_gradient, global_information_gain, local_information_gain,
                        sampling_sum_matrix, solve_oed_slsqp)
+from . import oed
+from .oed import OEDLayer
 
 
 def setup(rng, layer):

@@ -128,23 +128,15 @@ __global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const
 // Symmetric(F) (rows of crit: A = tr(inv F), D = 1/det F, E = max eig(inv F), FisherA = -tr F, FisherD = -det F,
 // FisherE = -min eig F) from the eigenvalues of F (cyclic Jacobi, n <= CB200_MAX_FIM).
 constexpr int CB200_MAX_FIM = 8;
-__global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long long B, int nx, int I, int f_off,
-                           int n, const double *__restrict__ finit, double *__restrict__ fim, long long ldo,
-                           double *__restrict__ fsum, double *__restrict__ crit)
+// common tail of the read-out kernels: A = the full symmetric matrix of this thread's candidate
+__device__ __forceinline__ void fim_emit(double (&A)[CB200_MAX_FIM][CB200_MAX_FIM], int n, bool live, long long b,
+                                         double *__restrict__ fim, long long ldo, double *__restrict__ fsum,
+                                         double *__restrict__ crit)
 {
-    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-    const bool live = b < B;
-    double A[CB200_MAX_FIM][CB200_MAX_FIM];
     for (int c = 0; c < n; c++)
         for (int r = 0; r < n; r++) {
-            const int a = r < c ? r : c, bb = r < c ? c : r;  // upper-triangle entry (a, bb), a <= bb
-            const int q = bb * (bb + 1) / 2 + a;             // column-major triu position
-            double v = 0.0;
-            if (live) {
-                v = xend[((long long)(I - 1) * nx + f_off + q) * ldx + b] + (finit ? finit[r + n * c] : 0.0);
-                if (fim) fim[(long long)(r + n * c) * ldo + b] = v;
-            }
-            if (crit) A[r][c] = v;
+            double v = live ? A[r][c] : 0.0;
+            if (live && fim) fim[(long long)(r + n * c) * ldo + b] = v;
             if (fsum) {
                 for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
                 if ((threadIdx.x & 31) == 0) atomicAdd(fsum + r + n * c, v);
@@ -197,6 +189,83 @@ __global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long 
     crit[4 * ldo + b] = -det;
     crit[5 * ldo + b] = -lmin;
 }
+
+__global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long long B, int nx, int I, int f_off,
+                           int n, const double *__restrict__ finit, double *__restrict__ fim, long long ldo,
+                           double *__restrict__ fsum, double *__restrict__ crit)
+{
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = b < B;
+    double A[CB200_MAX_FIM][CB200_MAX_FIM];
+    for (int c = 0; c < n; c++)
+        for (int r = 0; r < n; r++) {
+            const int a = r < c ? r : c, bb = r < c ? c : r;  // upper-triangle entry (a, bb), a <= bb
+            const int q = bb * (bb + 1) / 2 + a;             // column-major triu position
+            A[r][c] = live ? xend[((long long)(I - 1) * nx + f_off + q) * ldx + b] + (finit ? finit[r + n * c] : 0.0) : 0.0;
+        }
+    fim_emit(A, n, live, b, fim, ldo, fsum, crit);
+}
+
+// K4 read-out of the sample-based variants (lib/CorleoneOED/src/oed.jl): the information is collected from the saved
+// samples of the merged trajectory instead of one end state.  g_k(s)[a] = G[k + bx*a] at sample s (observed = the
+// leading n_obs states).  rows: one per (interval, observation-grid row); row_sample = its sample, row_var[row*n_obs+k]
+// = flat ps index of the weight of observed function k there, -1 = not measured (WeightedObservation, oed.jl:2-16).
+//   mode 1  Discrete, no measurements (:446-461): F = sum over ALL samples of s s', s = sum_k g_k (augmentation.jl:182-186)
+//   mode 2  DiscreteSampled (:409-432): F = sum_rows sum_k (w_k g_k)'(w_k g_k)   -- the weight enters squared (:8-10)
+//   mode 3  ContinuousSampled, fixed (:352-362): F = sum_rows sum_k w_k (F_k(sample+1) - F_k(sample))
+__global__ void fim_samples_kernel(const double *__restrict__ traj, long long ldt, long long B, int nrow, int n_samples,
+                                   const double *__restrict__ ps, long long ldb, int mode, int bx, int n, int n_obs,
+                                   int f_off, int n_rows, const int *__restrict__ row_sample,
+                                   const int *__restrict__ row_var, const double *__restrict__ finit,
+                                   double *__restrict__ fim, long long ldo, double *__restrict__ fsum,
+                                   double *__restrict__ crit)
+{
+    const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+    const bool live = b < B;
+    double A[CB200_MAX_FIM][CB200_MAX_FIM];
+    for (int c = 0; c < n; c++)
+        for (int r = 0; r < n; r++) A[r][c] = (live && finit) ? finit[r + n * c] : 0.0;
+    if (live) {
+        const int ntri = n * (n + 1) / 2;
+        const int count = mode == 1 ? n_samples : n_rows;
+        for (int row = 0; row < count; row++) {
+            const int smp = mode == 1 ? row : row_sample[row];
+            const double *u = traj + (long long)nrow * smp * ldt + b;   // state r of the sample: u[r * ldt]
+            if (mode == 1) {
+                double sg[CB200_MAX_FIM];
+                for (int a = 0; a < n; a++) {
+                    double acc = 0.0;
+                    for (int k = 0; k < n_obs; k++) acc += u[(long long)(bx + k + bx * a) * ldt];
+                    sg[a] = acc;
+                }
+                for (int c = 0; c < n; c++)
+                    for (int r = 0; r < n; r++) A[r][c] += sg[r] * sg[c];
+                continue;
+            }
+            for (int k = 0; k < n_obs; k++) {
+                const int var = row_var[row * n_obs + k];
+                if (var < 0) continue;
+                const double w = ps[(long long)var * ldb + b];
+                if (mode == 2) {
+                    double g[CB200_MAX_FIM];
+                    for (int a = 0; a < n; a++) g[a] = w * u[(long long)(bx + k + bx * a) * ldt];
+                    for (int c = 0; c < n; c++)
+                        for (int r = 0; r < n; r++) A[r][c] += g[r] * g[c];
+                } else {
+                    const double *un = u + (long long)nrow * ldt;   // the next sample
+                    for (int c = 0; c < n; c++)
+                        for (int r = 0; r < n; r++) {
+                            const int lo = r < c ? r : c, hi = r < c ? c : r;
+                            const long long q = f_off + k * ntri + hi * (hi + 1) / 2 + lo;
+                            A[r][c] += w * (un[q * ldt] - u[q * ldt]);
+                        }
+                }
+            }
+        }
+    }
+    fim_emit(A, n, live, b, fim, ldo, fsum, crit);
+}
+
 
 // tiled transpose: in[r*ld_in + c] (nr x nc) -> out[c*ld_out + r]
 __global__ void transpose_kernel(const double *__restrict__ in, long long ld_in, double *__restrict__ out,
@@ -303,6 +372,8 @@ struct cb200_handle {
     int n_samples = 0;
     int max_ns = 0;
     int fim_off = -1, fim_n = 0;
+    int fim_mode = 0, fim_bx = 0, n_obs = 0, n_obs_rows = 0;   // sample-based read-outs
+    int *d_obs_sample = nullptr, *d_obs_var = nullptr;
     int G_sens = 2;                   // sensitivity directions per thread
     void *tables = nullptr;           // one device allocation holding every table
     int *d_quad = nullptr;
@@ -343,6 +414,12 @@ static int default_G(int model)
     case CB200_MODEL_DENSE20: return 1;
     case CB200_MODEL_LOTKA2_OED: return 1;   // second-order sensitivities of [x; G; F]: 12 dynamic + 6 quadrature per thread (G = 2 spills)
     case CB200_MODEL_LIN1D_OED: return 2;
+    case CB200_MODEL_LOTKA2_OED_CU: return 1;
+    case CB200_MODEL_LOTKA2_OED_CF: return 1;
+    case CB200_MODEL_LOTKA2_OED_DS: return 1;
+    case CB200_MODEL_LOTKA2_OED_DU: return 1;
+    case CB200_MODEL_LIN1D_OED_CF: return 2;
+    case CB200_MODEL_LIN1D_OED_DS: return 2;
     default: return 0;
     }
 }
@@ -368,6 +445,12 @@ static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
     case CB200_MODEL_LOTKACOMP3: *nx = 3; *np = 1; d = 2; break;
     case CB200_MODEL_F8AIRCRAFT4: *nx = 4; *np = 2; d = 3; break;
     case CB200_MODEL_DOUBLEOSC6: *nx = 6; *np = 1; d = 5; break;
+    case CB200_MODEL_LOTKA2_OED_CU: *nx = 9; *np = 3; d = 6; break;
+    case CB200_MODEL_LOTKA2_OED_CF: *nx = 12; *np = 5; d = 6; break;
+    case CB200_MODEL_LOTKA2_OED_DS: *nx = 6; *np = 5; d = 6; break;
+    case CB200_MODEL_LOTKA2_OED_DU: *nx = 6; *np = 3; d = 6; break;
+    case CB200_MODEL_LIN1D_OED_CF: *nx = 3; *np = 2; d = 2; break;
+    case CB200_MODEL_LIN1D_OED_DS: *nx = 2; *np = 2; d = 2; break;
     default: return -1;
     }
     if (nxd) *nxd = d;
@@ -395,6 +478,12 @@ static int launch_model(int model, int G, int method, const DevLayer &L, const d
     case CB200_MODEL_LOTKACOMP3: return launch_lotkacomp3(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_F8AIRCRAFT4: return launch_f8aircraft4(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_DOUBLEOSC6: return launch_doubleosc6(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKA2_OED_CU: return launch_lotka2_oed_cu(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKA2_OED_CF: return launch_lotka2_oed_cf(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKA2_OED_DS: return launch_lotka2_oed_ds(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKA2_OED_DU: return launch_lotka2_oed_du(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LIN1D_OED_CF: return launch_lin1d_oed_cf(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LIN1D_OED_DS: return launch_lin1d_oed_ds(G, method, L, ps, ldb, B, o, s);
     default: return -1000;
     }
 }
@@ -420,6 +509,12 @@ static int forward_model(int model, int method, const DevLayer &L, double *ps, l
     case CB200_MODEL_LOTKACOMP3: return forward_lotkacomp3(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_F8AIRCRAFT4: return forward_f8aircraft4(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_DOUBLEOSC6: return forward_doubleosc6(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKA2_OED_CU: return forward_lotka2_oed_cu(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKA2_OED_CF: return forward_lotka2_oed_cf(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKA2_OED_DS: return forward_lotka2_oed_ds(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKA2_OED_DU: return forward_lotka2_oed_du(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LIN1D_OED_CF: return forward_lin1d_oed_cf(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LIN1D_OED_DS: return forward_lin1d_oed_ds(method, L, ps, ldb, B, fixed, s);
     default: return -1000;
     }
 }
@@ -512,12 +607,42 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     }
     h->nquad = d->n_quadrature;
     for (int k = 0; k < d->n_quadrature; k++) h->quad0.push_back((int)d->quadrature_indices[k] - 1);
-    if (d->fim_offset > 0) {
-        h->fim_off = d->fim_offset - 1;
-        h->fim_n = d->fim_n;
-        if (h->fim_off + h->fim_n * (h->fim_n + 1) / 2 > nx) {
+    h->fim_mode = d->fim_mode;
+    if (d->fim_mode < 0 || d->fim_mode > CB200_FIM_FIXED_CONTINUOUS) {
+        delete h;
+        return fail(CB200_ERR_ARG, "unknown fim_mode %d", d->fim_mode);
+    }
+    if (d->fim_mode == CB200_FIM_END || d->fim_mode == CB200_FIM_FIXED_CONTINUOUS) {
+        if (d->fim_offset > 0) {
+            h->fim_off = d->fim_offset - 1;
+            h->fim_n = d->fim_n;
+            const int blocks = d->fim_mode == CB200_FIM_FIXED_CONTINUOUS ? d->n_observed : 1;
+            if (h->fim_off + blocks * h->fim_n * (h->fim_n + 1) / 2 > nx) {
+                delete h;
+                return fail(CB200_ERR_ARG, "Fisher block exceeds the state vector");
+            }
+        } else if (d->fim_mode == CB200_FIM_FIXED_CONTINUOUS) {
             delete h;
-            return fail(CB200_ERR_ARG, "Fisher block exceeds the state vector");
+            return fail(CB200_ERR_ARG, "fim_mode FIXED_CONTINUOUS needs fim_offset");
+        }
+    }
+    if (d->fim_mode != CB200_FIM_END) {
+        h->fim_n = d->fim_n;
+        h->fim_bx = d->fim_base_nx;
+        h->n_obs = d->n_observed;
+        if (h->fim_off < 0) h->fim_off = 0;   // "has a Fisher read-out"
+        if (h->fim_n < 1 || h->fim_n > CB200_MAX_FIM || h->fim_bx < 1 || h->n_obs < 1 || h->n_obs > h->fim_bx ||
+            h->fim_bx * (1 + h->fim_n) > nx) {
+            delete h;
+            return fail(CB200_ERR_ARG, "sample-based Fisher read-out: need 1 <= fim_n <= %d, 1 <= n_observed <= fim_base_nx and [x; G] within the state", CB200_MAX_FIM);
+        }
+        if (d->fim_mode != CB200_FIM_DISCRETE && (!d->n_observation_rows || !d->observation_grid)) {
+            delete h;
+            return fail(CB200_ERR_ARG, "fim_mode %d needs observation_grid", d->fim_mode);
+        }
+        if (d->fim_mode == CB200_FIM_FIXED_CONTINUOUS && I != 1) {
+            delete h;
+            return fail(CB200_ERR_UNSUPPORTED, "the fixed continuous read-out is defined for single shooting only (oed.jl:352-362)");
         }
     }
 
@@ -757,8 +882,34 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
             if (jp >= 0) jp = (int)newpos[jp];   // a state's ns entries stay contiguous: only constants moved out
         h->jac_rows.swap(r2); h->jac_cols.swap(c2); h->jac_src.swap(s2);
     }
+    // observation rows of the sample-based Fisher read-outs
+    std::vector<int> obs_sample, obs_var;
+    if (h->fim_mode == CB200_FIM_DISCRETE_SAMPLED || h->fim_mode == CB200_FIM_FIXED_CONTINUOUS) {
+        long long go = 0;
+        for (int i = 0; i < I; i++) {
+            const int rows = d->n_observation_rows[i];
+            const int max_rows = h->h_M[i] + ((i == I - 1 && h->fim_mode == CB200_FIM_DISCRETE_SAMPLED) ? 1 : 0);
+            if (rows < 0 || rows > max_rows) {
+                delete h;
+                return fail(CB200_ERR_ARG, "interval %d: %d observation rows, at most %d samples", i + 1, rows, max_rows);
+            }
+            for (int j = 0; j < rows; j++) {
+                obs_sample.push_back(h->h_samp_off[i] + j);
+                for (int k = 0; k < h->n_obs; k++) {
+                    const long long idx = d->observation_grid[go++];
+                    if (idx < 0 || idx > h->h_n_c[i]) {
+                        delete h;
+                        return fail(CB200_ERR_ARG, "interval %d: observation_grid entry %lld outside 0..%d", i + 1, idx, h->h_n_c[i]);
+                    }
+                    obs_var.push_back(idx == 0 ? -1 : h->h_var_off[i] + h->h_n_u0[i] + ntp + (int)idx - 1);
+                }
+            }
+        }
+        h->n_obs_rows = (int)obs_sample.size();
+    }
     // upload
     std::vector<char> blob;
+    const size_t o_obs_s = push(blob, obs_sample), o_obs_v = push(blob, obs_var);
     const size_t o_M = push(blob, h->h_M), o_po = push(blob, h->h_piece_off), o_t0 = push(blob, pt0),
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
@@ -782,6 +933,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     e = cudaMemcpy(h->tables, blob.data(), blob.size(), cudaMemcpyHostToDevice);
     if (e != cudaSuccess) return bail("cudaMemcpy(tables)", e);
     char *base = (char *)h->tables;
+    h->d_obs_sample = (int *)(base + o_obs_s);
+    h->d_obs_var = (int *)(base + o_obs_v);
     L.M = (const int *)(base + o_M);
     L.piece_off = (const int *)(base + o_po);
     L.pt0 = (const double *)(base + o_t0);
@@ -997,7 +1150,7 @@ static int transpose(cb200_handle *h, cudaStream_t st, const double *in, long lo
 struct EvalPlan {
     bool xend, sens, traj, dk, ds, obj, grad, fim, osum, gsum, fsum, jac, crit, gradc, tsens;
     int gradc_first, gradc_n;   // compact gradient: variables [gradc_first, gradc_first + gradc_n)
-    bool fused_grad, need_sens, need_xend;
+    bool fused_grad, need_sens, need_xend, need_traj;
     int obj_state, obj_ctrl_var, obj_quad, objective_row;
 };
 
@@ -1065,13 +1218,18 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
         grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
         h->launches++;
     }
-    if (pl.traj && h->nquad > 0 && I > 1) {
+    if (pl.need_traj && h->nquad > 0 && I > 1) {
         traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, d.xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
                                                      h->d_quad, h->nquad);
         h->launches++;
     }
     if (pl.fim || pl.fsum || pl.crit) {
-        fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, B, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, B, d.fsum, d.crit);
+        if (h->fim_mode == CB200_FIM_END)
+            fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, B, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, B, d.fsum, d.crit);
+        else
+            fim_samples_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, B, (int)nrow, h->n_samples, d_ps, d_ldb, h->fim_mode,
+                                                           h->fim_bx, h->fim_n, h->n_obs, h->fim_off, h->n_obs_rows,
+                                                           h->d_obs_sample, h->d_obs_var, d.finit, d.fim, B, d.fsum, d.crit);
         h->launches++;
     }
     CUDA_TRY(cudaGetLastError());
@@ -1138,7 +1296,9 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         pl.gradc_n = nvars - pl.gradc_first;
     }
     pl.need_sens = pl.sens || pl.fused_grad || pl.jac || pl.gradc || pl.tsens;   // sensitivity directions are integrated
-    pl.need_xend = pl.xend || pl.fim || pl.fsum || pl.crit || (pl.traj && h->nquad > 0);
+    const bool any_fim = pl.fim || pl.fsum || pl.crit;
+    pl.need_traj = pl.traj || (any_fim && h->fim_mode != CB200_FIM_END);   // sample-based read-outs consume the samples
+    pl.need_xend = pl.xend || (any_fim && h->fim_mode == CB200_FIM_END) || (pl.need_traj && h->nquad > 0);
     const bool need_objq = (pl.obj || pl.osum) && pl.obj_state >= 0;
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {
         h->h_grad.assign(1, GradEntry{pl.obj_ctrl_var, -1});
@@ -1150,7 +1310,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     const Item items[] = {
         {pl.need_xend, (long long)nx * I, &h->ws_xend, pl.xend ? out->xend : nullptr, &DevSet::xend},
         {pl.sens, h->n_sens, &h->ws_sens, out->sens, &DevSet::sens},
-        {pl.traj, nrow * h->n_samples, &h->ws_traj, out->traj, &DevSet::traj},
+        {pl.need_traj, nrow * h->n_samples, &h->ws_traj, pl.traj ? out->traj : nullptr, &DevSet::traj},
         {pl.dk, ndef, &h->ws_dk, out->defects_kind, &DevSet::dk},
         {pl.ds, ndef, &h->ws_ds, out->defects_stage, &DevSet::ds},
         {pl.obj, 1, &h->ws_obj, out->objective, &DevSet::obj},

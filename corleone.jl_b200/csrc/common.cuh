@@ -145,6 +145,30 @@ int launch_doubleosc6(int G, int method, const DevLayer &L, const double *ps, lo
         const ShootOut &o, cudaStream_t s);
 int forward_doubleosc6(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s);
+int launch_lotka2_oed_cu(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lotka2_oed_cu(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_lotka2_oed_cf(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lotka2_oed_cf(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_lotka2_oed_ds(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lotka2_oed_ds(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_lotka2_oed_du(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lotka2_oed_du(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_lin1d_oed_cf(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lin1d_oed_cf(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_lin1d_oed_ds(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lin1d_oed_ds(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
 
 }  // namespace cb200

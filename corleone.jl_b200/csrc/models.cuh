@@ -217,17 +217,28 @@ struct Dense20 {
 };
 #endif
 
-// ---- OED augmentation (lib/CorleoneOED/src/augmentation.jl), ContinuousSampled non-fixed variant:
-//   state  [x; vec(G) column-major nx x NF; F[triu] column-major]     (:239, selector :211)
-//   params [base p; w_1..w_NOBS]                                       (:228-230)
-//   G' = f_x G + f_p[:, params]  (:147-154),  F' = sum_i w_i (h_x[i,:] G)'(h_x[i,:] G)  (:222-233)
-// observed = the leading NOBS states, so h_x rows are unit rows.  Traits::pcol(c) is the 0-based p column
-// of Fisher parameter c.  x and G are dynamic states; the F entries are quadratures.
+// ---- OED augmentation (lib/CorleoneOED/src/augmentation.jl).  State [x; vec(G) column-major nx x NF; F ...],
+//      G' = f_x G + f_p[:, params] (:147-154); observed = the leading NOBS states, so h_x rows are unit rows and
+//      g_i = (h_x[i,:] G) = row i of G.  Traits::pcol(c) is the 0-based p column of Fisher parameter c.
+//      x and G are dynamic states; the F entries are quadratures.  Traits::MODE picks the variant:
+//   OED_CS  ContinuousSampled, non-fixed (:206-253 with measurements): params [base p; w_1..w_NOBS] (:228-230),
+//           F[triu] column-major (:239, selector :211), F' = sum_i w_i g_i' g_i (:222-227)
+//   OED_CU  Continuous without measurements (:217-220): no weights, F' = s's with s = sum_i g_i (rows summed FIRST)
+//   OED_CF  ContinuousSampled, fixed (:255-292): one F_k[triu] block per observed function, F_k' = g_k' g_k; the
+//           weights are appended as controls (:275-278) but do not enter the right-hand side -- they weight the
+//           increments of F_k in the read-out (oed.jl:352-362)
+//   OED_DS / OED_DU  Discrete with / without measurements (:171-203): no F states at all; the information is summed
+//           over the saved samples (oed.jl:401-428).  DS appends the weights as controls, DU does not.
+enum { OED_CS = 0, OED_CU = 1, OED_CF = 2, OED_DS = 3, OED_DU = 4 };
 template <class Base, class Traits>
 struct OedAug {
     static_assert(Base::NQ == 0, "OED base model must not carry quadrature states");
-    static constexpr int BX = Base::NX, NF = Traits::NF, NOBS = Traits::NOBS;
-    static constexpr int NXD = BX + BX * NF, NQ = NF * (NF + 1) / 2, NX = NXD + NQ, NP = Base::NP + NOBS;
+    static constexpr int BX = Base::NX, NF = Traits::NF, NOBS = Traits::NOBS, MODE = Traits::MODE;
+    static constexpr int NTRI = NF * (NF + 1) / 2;
+    static constexpr int NW = (MODE == OED_CU || MODE == OED_DU) ? 0 : NOBS;   // weights appended to p
+    static constexpr int NXD = BX + BX * NF;
+    static constexpr int NQ = (MODE == OED_DS || MODE == OED_DU) ? 0 : (MODE == OED_CF ? NOBS * NTRI : NTRI);
+    static constexpr int NX = NXD + NQ, NP = Base::NP + NW;
     static constexpr bool HAS_JVP = true;
     struct Ctx {
         typename Base::Ctx base;
@@ -235,31 +246,70 @@ struct OedAug {
     struct Force {
         int pcol;   // tangent p column of the augmented problem: < Base::NP a model parameter, >= a weight w_i; -1 none
     };
+    // F-part of the right-hand side (dG = nullptr) or of its tangent (dG = tangent of G, wcol = weight index or -1)
+    template <bool dG_ON>
+    static __device__ __forceinline__ void fisher_rhs(const double *G, const double *dG, const double *w, int wcol, double *dF)
+    {
+        if constexpr (NQ == 0) return;
+        if constexpr (MODE == OED_CU) {
+            double s[NF], ds[NF];
+#pragma unroll
+            for (int a = 0; a < NF; a++) {
+                s[a] = 0.0, ds[a] = 0.0;
+#pragma unroll
+                for (int i = 0; i < NOBS; i++) {
+                    s[a] += G[i + BX * a];
+                    if constexpr (dG_ON) ds[a] += dG[i + BX * a];
+                }
+            }
+            int q = 0;
+#pragma unroll
+            for (int b = 0; b < NF; b++)
+#pragma unroll
+                for (int a = 0; a <= b; a++) dF[q++] = dG_ON ? fma(ds[a], s[b], s[a] * ds[b]) : s[a] * s[b];
+        } else if constexpr (MODE == OED_CF) {
+            int q = 0;
+#pragma unroll
+            for (int i = 0; i < NOBS; i++)
+#pragma unroll
+                for (int b = 0; b < NF; b++)
+#pragma unroll
+                    for (int a = 0; a <= b; a++)
+                        dF[q++] = dG_ON ? fma(dG[i + BX * a], G[i + BX * b], G[i + BX * a] * dG[i + BX * b])
+                                     : G[i + BX * a] * G[i + BX * b];
+        } else {
+            int q = 0;
+#pragma unroll
+            for (int b = 0; b < NF; b++)
+#pragma unroll
+                for (int a = 0; a <= b; a++) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < NOBS; i++) {
+                        const double gg = G[i + BX * a] * G[i + BX * b];
+                        if constexpr (dG_ON) {
+                            const double dgg = fma(dG[i + BX * a], G[i + BX * b], G[i + BX * a] * dG[i + BX * b]);
+                            acc += (wcol == i ? gg : 0.0) + w[i] * dgg;
+                        } else
+                            acc += w[i] * gg;
+                    }
+                    dF[q++] = acc;
+                }
+        }
+    }
     CB_DEV void f(const double *y, const double *p, double *dy, Ctx &c)
     {
         Base::f(y, p, dy, c.base);
 #pragma unroll
         for (int k = 0; k < NF; k++)
             Base::jvp(y, p, c.base, y + BX + BX * k, Base::make_force(Traits::pcol(k), p), dy + BX + BX * k);
-        const double *G = y + BX;
-        const double *w = p + Base::NP;
-        double *dF = dy + NXD;
-        int q = 0;
-#pragma unroll
-        for (int b = 0; b < NF; b++)
-#pragma unroll
-            for (int a = 0; a <= b; a++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int i = 0; i < NOBS; i++) acc += w[i] * (G[i + BX * a] * G[i + BX * b]);
-                dF[q++] = acc;
-            }
+        fisher_rhs<false>(y + BX, y + BX, p + Base::NP, -1, dy + NXD);
     }
     CB_DEV Force make_force(int pcol, const double *) { return Force{pcol}; }
     // tangent of the augmented right-hand side (what ForwardDiff through the OED layer propagates):
     //   dx'  = f_x dx + f_p e_pcol
     //   dG'  = f_x dG + (f_xx[dx] + f_xp[e_pcol]) G + d(f_p columns)
-    //   dF'  = sum_i dw_i (h_i G)'(h_i G) + w_i [ (h_i dG)'(h_i G) + (h_i G)'(h_i dG) ]
+    //   dF'  = sum_i dw_i (h_i G)'(h_i G) + w_i [ (h_i dG)'(h_i G) + (h_i G)'(h_i dG) ]     (OED_CS)
     CB_DEV void jvp(const double *y, const double *p, const Ctx &c, const double *v, const Force &F, double *dv)
     {
         const int bp = F.pcol < Base::NP ? F.pcol : -1;   // model-parameter part of the direction
@@ -272,35 +322,27 @@ struct OedAug {
 #pragma unroll
             for (int r = 0; r < BX; r++) dv[BX + BX * k + r] = lin[r] + sec[r];
         }
-        const double *G = y + BX, *dG = v + BX;
-        const double *w = p + Base::NP;
-        double *dF = dv + NXD;
-        int q = 0;
-#pragma unroll
-        for (int b = 0; b < NF; b++)
-#pragma unroll
-            for (int a = 0; a <= b; a++) {
-                double acc = 0.0;
-#pragma unroll
-                for (int i = 0; i < NOBS; i++) {
-                    const double gg = G[i + BX * a] * G[i + BX * b];
-                    const double dgg = fma(dG[i + BX * a], G[i + BX * b], G[i + BX * a] * dG[i + BX * b]);
-                    acc += (F.pcol == Base::NP + i ? gg : 0.0) + w[i] * dgg;
-                }
-                dF[q++] = acc;
-            }
+        fisher_rhs<true>(y + BX, v + BX, p + Base::NP, F.pcol - Base::NP, dv + NXD);
     }
 };
-struct LotkaOedTraits {
-    static constexpr int NF = 2, NOBS = 2;
+template <int M>
+struct LotkaOedTraitsT {
+    static constexpr int NF = 2, NOBS = 2, MODE = M;
     static __device__ __forceinline__ constexpr int pcol(int c) { return c + 1; }  // params = [2, 3]
 };
-struct Lin1dOedTraits {
-    static constexpr int NF = 1, NOBS = 1;
+template <int M>
+struct Lin1dOedTraitsT {
+    static constexpr int NF = 1, NOBS = 1, MODE = M;
     static __device__ __forceinline__ constexpr int pcol(int) { return 0; }  // params = [1]
 };
-using Lotka2Oed = OedAug<Lotka2, LotkaOedTraits>;
-using Lin1dOed = OedAug<Lin1d, Lin1dOedTraits>;
+using Lotka2Oed = OedAug<Lotka2, LotkaOedTraitsT<OED_CS>>;
+using Lin1dOed = OedAug<Lin1d, Lin1dOedTraitsT<OED_CS>>;
+using Lotka2OedCu = OedAug<Lotka2, LotkaOedTraitsT<OED_CU>>;
+using Lotka2OedCf = OedAug<Lotka2, LotkaOedTraitsT<OED_CF>>;
+using Lotka2OedDs = OedAug<Lotka2, LotkaOedTraitsT<OED_DS>>;
+using Lotka2OedDu = OedAug<Lotka2, LotkaOedTraitsT<OED_DU>>;
+using Lin1dOedCf = OedAug<Lin1d, Lin1dOedTraitsT<OED_CF>>;
+using Lin1dOedDs = OedAug<Lin1d, Lin1dOedTraitsT<OED_DS>>;
 
 
 // ---- Models written once on a generic scalar: the directional derivative is taken by forward-mode AD on the

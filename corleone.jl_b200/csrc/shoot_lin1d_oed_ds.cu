@@ -1,0 +1,21 @@
+// Instantiations of the shooting kernel for model Lin1dOedDs (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_lin1d_oed_ds(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Lin1dOedDs, 0, 1)
+        CB200_DISPATCH_G(Lin1dOedDs, 1, 1)
+        CB200_DISPATCH_G(Lin1dOedDs, 2, 1)
+    default:
+        return -1000;
+    }
+}
+int forward_lin1d_oed_ds(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lin1dOedDs>(method, L, ps, ldb, B, fixed, s);
+}
+}  // namespace cb200

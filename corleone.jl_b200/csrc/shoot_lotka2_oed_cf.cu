@@ -1,0 +1,21 @@
+// Instantiations of the shooting kernel for model Lotka2OedCf (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_lotka2_oed_cf(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(Lotka2OedCf, 0, 1)
+        CB200_DISPATCH_G(Lotka2OedCf, 1, 1)
+        CB200_DISPATCH_G(Lotka2OedCf, 2, 1)
+    default:
+        return -1000;
+    }
+}
+int forward_lotka2_oed_cf(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<Lotka2OedCf>(method, L, ps, ldb, B, fixed, s);
+}
+}  // namespace cb200

@@ -34,12 +34,14 @@ class Desc(C.Structure):
         ("struct_size", C.c_int32), ("model", C.c_int32), ("method", C.c_int32), ("steps_per_piece", C.c_int32),
         ("nx", C.c_int32), ("np_all", C.c_int32), ("n_controls", C.c_int32), ("n_tunable_p", C.c_int32),
         ("n_intervals", C.c_int32), ("n_quadrature", C.c_int32), ("device", C.c_int32),
-        ("fim_offset", C.c_int32), ("fim_n", C.c_int32), ("reserved", C.c_int32),
+        ("fim_offset", C.c_int32), ("fim_n", C.c_int32), ("fim_mode", C.c_int32),
         ("u0", _dp), ("tunable_p", _i64p), ("control_indices", _i64p), ("quadrature_indices", _i64p),
         ("n_pieces", _i32p), ("tspans", _dp), ("index_grid", _i64p), ("n_u0", _i32p),
         ("n_local_controls", _i32p), ("is_shooting", _i32p), ("ic_sorting", _i64p),
         ("ic_n_constants", _i32p), ("ic_constants", _i64p), ("n_shooting_indices", _i32p),
         ("shooting_indices", _i64p), ("model_data", _dp), ("model_data_len", C.c_int64),
+        ("fim_base_nx", C.c_int32), ("n_observed", C.c_int32), ("n_observation_rows", _i32p),
+        ("observation_grid", _i64p),
     ]
 
 
@@ -110,9 +112,11 @@ class NativeLayer:
     """Owns one cb200_handle built from a layer's static tables (the reference's `st`)."""
 
     def __init__(self, *, model_id, method, steps_per_piece, nx, np_all, u0, tunable_p, control_indices,
-                 quadrature_indices, intervals, device=0, fim_offset=0, fim_n=0, model_data=None):
+                 quadrature_indices, intervals, device=0, fim_offset=0, fim_n=0, model_data=None, fim_mode=0,
+                 fim_base_nx=0, n_observed=0, observation_rows=None):
         """intervals: list of dicts with tspans [(t0,t1)...], index_grid (n_controls x M int64 1-based),
-        n_u0, n_c, is_shooting, sorting, constants, shooting_indices (all 1-based as the reference)."""
+        n_u0, n_c, is_shooting, sorting, constants, shooting_indices (all 1-based as the reference).
+        observation_rows: per interval an (rows x n_observed) int array = WeightedObservation.grid (fim_mode 2, 3)."""
         L = lib()
         nact = len(control_indices)
         keep = {}
@@ -121,7 +125,8 @@ class NativeLayer:
         d.model, d.method, d.steps_per_piece = model_id, method, steps_per_piece
         d.nx, d.np_all, d.n_controls, d.n_tunable_p = nx, np_all, nact, len(tunable_p)
         d.n_intervals, d.n_quadrature, d.device = len(intervals), len(quadrature_indices), device
-        d.fim_offset, d.fim_n = fim_offset, fim_n
+        d.fim_offset, d.fim_n, d.fim_mode = fim_offset, fim_n, fim_mode
+        d.fim_base_nx, d.n_observed = fim_base_nx, n_observed
 
         def put(name, values, dtype, ptr):
             a = _arr(values if len(values) else [0], dtype)
@@ -148,6 +153,10 @@ class NativeLayer:
         if model_data is not None:
             put("model_data", model_data, np.float64, _dp)
             d.model_data_len = len(model_data)
+        if observation_rows is not None:
+            rows = [np.asarray(r, dtype=np.int64).reshape(-1, n_observed) for r in observation_rows]
+            put("n_observation_rows", [len(r) for r in rows], np.int32, _i32p)
+            put("observation_grid", np.concatenate([r.ravel() for r in rows]) if rows else [], np.int64, _i64p)
         self._h = C.c_void_p()
         _check(L.cb200_create(C.byref(d), C.byref(self._h)), "cb200_create")
         s = Sizes()
@@ -159,6 +168,7 @@ class NativeLayer:
         self.n_traj_sens = int(s.n_traj_sens)
         self.fim_n = fim_n
         self.fim_offset = fim_offset
+        self.fim_mode = fim_mode
         self.device = device
 
     def close(self):

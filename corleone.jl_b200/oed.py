@@ -1,0 +1,209 @@
+"""OEDLayer -- host-side mirror of lib/CorleoneOED/src/oed.jl (:30-180 constructors, :286-372 initial states,
+:381-470 Fisher read-outs) for the compiled-in base models.
+
+The reference derives the augmented right-hand side symbolically (augmentation.jl); here each (base model, variant)
+pair is a compiled-in model of libcorleone_b200.so (csrc/models.cuh `OedAug`):
+
+    OEDLayer{false}, measurements          -> "<base>_oed"      [x; G; F_triu],            p = [base p; w]
+    OEDLayer{false}, no measurements       -> "<base>_oed_cu"   [x; G; F_triu],            p = base p
+    OEDLayer{false}, measurements, FIXED   -> "<base>_oed_cf"   [x; G; F_1 triu; F_2 ...], p = [base p; w]
+    OEDLayer{true},  measurements          -> "<base>_oed_ds"   [x; G],                    p = [base p; w]  (*)
+    OEDLayer{true},  no measurements       -> "<base>_oed_du"   [x; G],                    p = base p
+
+(*) Deviation, on purpose.  In the reference the discrete variants do not append the weights to the problem's
+parameters (augmentation.jl:171-203), so the measurement controls are filtered out of the index grid
+(src/single_shooting.jl:301-304) and the samples at the measurement times come from `saveat` (oed.jl:106-113) --
+interpolated inside a solver step.  A fixed-step kernel has no business interpolating: here the weights ARE (inert)
+parameters of the `_ds` model, so the measurement grids cut the pieces and every measurement time is a step end.
+The flat parameter vector is the same (ps.controls holds the weights in both); the saved samples carry the weights as
+additional trailing control rows.
+
+Every evaluation goes through cb200_eval (`CB200_WANT_FIM` / `CB200_WANT_CRIT`); this module only builds tables.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from . import native
+from .controls import ControlParameter, build_index_grid, get_timegrid
+from .multiple_shooting import MultipleShootingLayer
+from .problem import MODEL_REGISTRY
+from .single_shooting import SingleShootingLayer, _flatten_chunks, to_vec
+
+# base model -> (Fisher parameter indices (1-based), number of observed functions = leading states)
+OED_BASE = {"lotka2": ((2, 3), 2), "lin1d": ((1,), 1)}
+FIM_END, FIM_DISCRETE, FIM_DISCRETE_SAMPLED, FIM_FIXED_CONTINUOUS = 0, 1, 2, 3
+
+
+def _variant(discrete: bool, sampled: bool, fixed: bool) -> str:
+    if discrete:
+        return "_oed_ds" if sampled else "_oed_du"
+    if not sampled:
+        return "_oed_cu"
+    return "_oed_cf" if fixed else "_oed"
+
+
+class OEDLayer:
+    """OEDLayer{DISCRETE}(layer; params, measurements, observed) (oed.jl:77-180).  `layer` is a Single- or
+    MultipleShootingLayer over a base model of OED_BASE; `params` / `observed` are fixed by the compiled-in
+    augmentation (the reference's test problems: params = [2, 3], observed = u[1:2] for Lotka)."""
+
+    def __init__(self, layer, discrete: bool = False, measurements=()):
+        single = isinstance(layer, SingleShootingLayer)
+        base = layer if single else layer.layer
+        prob = base.problem
+        if prob.model not in OED_BASE:
+            raise KeyError(f"no compiled-in OED augmentation of model {prob.model!r}; available: {sorted(OED_BASE)}")
+        params, nobs = OED_BASE[prob.model]
+        measurements = list(measurements)
+        self.DISCRETE = bool(discrete)
+        self.SAMPLED = len(measurements) > 0
+        self.FIXED = len(base.control_indices) == 0 and len(base.tunable_ic) == 0          # (:87,128)
+        if self.SAMPLED and len(measurements) != nobs:
+            raise ValueError(f"{nobs} observed functions need {nobs} measurement controls")
+        model = prob.model + _variant(self.DISCRETE, self.SAMPLED, self.FIXED)
+        if model not in MODEL_REGISTRY:
+            raise KeyError(f"OED variant {model!r} is not compiled in")
+        _, nx_aug, np_aug = MODEL_REGISTRY[model]
+        bx, p_length = len(prob.u0), len(prob.p)
+        nf = len(params)
+        self.base_nx, self.n_fisher, self.n_obs = bx, nf, nobs
+        samplings = list(range(1, len(measurements) + 1))
+        ctrls = list(zip(base.control_indices, base.controls)) + [(p_length + k, m) for k, m in zip(samplings, measurements)]
+        self.sampling_indices = [k + len(base.controls) for k in samplings]                # (:93,135)
+        newprob = prob.remake(model=model, u0=np.concatenate([prob.u0, np.zeros(nx_aug - bx)]),
+                              p=np.concatenate([prob.p, np.ones(np_aug - p_length)]))
+        if single:
+            lb, ub = (np.concatenate([b, np.zeros(nx_aug - bx)]) for b in base.bounds_ic)  # (:117-122)
+            self.layer = SingleShootingLayer(newprob, base.algorithm, controls=ctrls, tunable_ic=list(base.tunable_ic),
+                                             bounds_ic=(lb, ub), state_initialization=base.state_initialization,
+                                             bounds_p=base.bounds_p, parameter_initialization=base.parameter_initialization,
+                                             quadrature_indices=[], device=base.device)
+        else:
+            pts = [t[0] for t in layer.shooting_intervals]
+            self.layer = MultipleShootingLayer(newprob, base.algorithm, *pts, controls=ctrls,
+                                               tunable_ic=list(base.tunable_ic),
+                                               state_initialization=base.state_initialization, bounds_p=base.bounds_p,
+                                               parameter_initialization=base.parameter_initialization,
+                                               quadrature_indices=[], device=base.device)
+        self.single = single
+        self.model = model
+        if self.DISCRETE:
+            self.fim_mode = FIM_DISCRETE_SAMPLED if self.SAMPLED else FIM_DISCRETE
+        else:
+            self.fim_mode = FIM_FIXED_CONTINUOUS if (self.SAMPLED and self.FIXED) else FIM_END
+        if self.fim_mode == FIM_FIXED_CONTINUOUS and not single:
+            raise NotImplementedError("OEDLayer{false, true, true} reads ps.controls of ONE layer (oed.jl:352-362): single shooting only")
+
+    def __repr__(self):
+        return (f"{'Fixed ' if self.FIXED else ''}OEDLayer {'with' if self.SAMPLED else 'without'} "
+                f"{'discrete' if self.DISCRETE else 'continuous'} measurement model and {len(self.sampling_indices)} observed functions.")
+
+    def n_observed(self):
+        return len(self.sampling_indices)
+
+    def _base_layer(self):
+        return self.layer if self.single else self.layer.layer
+
+    # ---- LuxCore triple
+    def initialparameters(self, rng):
+        return self.layer.initialparameters(rng)
+
+    def _weighting_grid(self, tspan, restrict: bool):
+        """oed.jl:291-311 (single shooting: restrict = False) / :341-357 (per interval of a multiple-shooting layer)"""
+        controls = self._base_layer().controls
+        grids = [get_timegrid(c) for c in controls]
+        overall = np.unique(np.concatenate(grids + [np.asarray(tspan, dtype=np.float64)]))
+        if restrict:
+            overall = overall[(overall >= tspan[0]) & (overall < tspan[1])]
+        sidx = [s - 1 for s in self.sampling_indices]
+        observed_grid = [np.nonzero(np.isin(overall, np.unique(grids[s])))[0] for s in sidx]
+        mi = _flatten_chunks(build_index_grid(*controls, tspan=tspan))
+        mi = np.atleast_2d(mi)
+        uniq = lambda row: row[np.sort(np.unique(row, return_index=True)[1])]   # Julia's unique keeps first-seen order
+        measurement_indices = [uniq(mi[s]) for s in sidx]
+        rows = np.zeros((len(overall), len(sidx)), dtype=np.int64)
+        for j, og in enumerate(observed_grid):
+            rows[og, j] = measurement_indices[j][: len(og)]
+        return rows, [uniq(r) for r in mi]
+
+    def initialstates(self, rng):
+        st = self.layer.initialstates(rng)
+        nf, nobs = self.n_fisher, self.n_obs
+        first = st if self.single else next(iter(st.values()))
+        first["F_init"] = np.zeros((nf, nf))
+        fim = dict(offset=0, n=nf, mode=self.fim_mode, base_nx=self.base_nx, n_observed=nobs, rows=None)
+        if self.fim_mode in (FIM_END, FIM_FIXED_CONTINUOUS):
+            fim["offset"] = self.base_nx * (1 + nf) + 1
+        if self.fim_mode == FIM_DISCRETE_SAMPLED:
+            if self.single:
+                grid, act = self._weighting_grid(self._base_layer().problem.tspan, False)
+                st["observation_grid"], st["active_controls"] = grid, act
+                fim["rows"] = [grid]
+            else:
+                fim["rows"] = []
+                for sti in st.values():
+                    tsp = _flatten_chunks(sti["tspans"])
+                    grid, act = self._weighting_grid((tsp[0][0], tsp[-1][1]), True)
+                    sti["observation_grid"], sti["active_controls"] = grid, act
+                    fim["rows"].append(grid)
+        elif self.fim_mode == FIM_FIXED_CONTINUOUS:
+            # active_controls = unique index-grid values of each measurement control (:304,312-318); the read-out
+            # zips row j of hcat(controls[active]...) with the j-th increment of F (:357-362)
+            controls = self._base_layer().controls
+            mi = np.atleast_2d(_flatten_chunks(build_index_grid(*controls, tspan=self._base_layer().problem.tspan)))
+            uniq = lambda row: row[np.sort(np.unique(row, return_index=True)[1])]
+            act = [uniq(mi[s - 1]) for s in self.sampling_indices]
+            if len({len(a) for a in act}) != 1:
+                raise ValueError("reduce(hcat, ...) of measurement controls with different lengths (oed.jl:357)")
+            st["active_controls"] = act
+            n_pieces = len(_flatten_chunks(st["tspans"]))
+            fim["rows"] = [np.stack(act, axis=1)[: n_pieces]]
+        first["_fim"] = fim
+        return st
+
+    def setup(self, rng):
+        return self.initialparameters(rng), self.initialstates(rng)
+
+    def native(self, ps, st) -> native.NativeLayer:
+        return self.layer._native(st, ps)
+
+    # ---- Fisher information for a batch of candidates (oed.jl:381-461), one cb200_eval
+    def fisher_information(self, X, ps_like, st, add_initial: bool = True, criteria: bool = False):
+        """X: (B, nvars) flat candidates.  Returns F (B, n, n) [, criteria (B, 6)]."""
+        nat = self.native(ps_like, st)
+        first = st if self.single else next(iter(st.values()))
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        want = native.WANT_FIM | (native.WANT_CRIT if criteria else 0)
+        r = nat.eval_host(X, want, fim_init=first["F_init"] if add_initial else None)
+        F = r["fim"].reshape(X.shape[0], self.n_fisher, self.n_fisher)
+        return (F, r["criteria"]) if criteria else F
+
+    def get_sampling_sums(self, ps, st):
+        """get_sampling_sums (oed.jl:536-640): one number per measurement control -- the number of (weighted)
+        measurements for the discrete variants (:573-580), the measured time sum_j w_j dt_j for the continuous ones
+        (:582-589,610-618); a multiple-shooting layer sums over its intervals (:559-563)."""
+        if not self.SAMPLED:
+            return np.zeros(0)
+        pairs = [(ps, st)] if self.single else [(ps[k], st[k]) for k in st]
+        out = np.zeros(self.n_obs)
+        for psi, sti in pairs:
+            c = np.asarray(psi["controls"], dtype=np.float64)
+            if self.DISCRETE:
+                for k, s in enumerate(self.sampling_indices):
+                    out[k] += c[np.asarray(sti["active_controls"][s - 1]) - 1].sum()
+                continue
+            tsp = _flatten_chunks(sti["tspans"])
+            dts = np.array([b - a for a, b in tsp])
+            if self.FIXED:
+                for k, sub in enumerate(sti["active_controls"]):
+                    out[k] += (c[np.asarray(sub) - 1] * dts).sum()
+            else:
+                grid = np.atleast_2d(np.asarray(_flatten_chunks(sti["index_grid"]), dtype=np.int64))
+                for k, s in enumerate(self.sampling_indices):
+                    out[k] += (c[grid[s - 1] - 1] * dts).sum()
+        return out
+
+
+def flat(ps) -> np.ndarray:
+    return to_vec(ps)

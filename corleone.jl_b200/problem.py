@@ -30,6 +30,12 @@ MODEL_REGISTRY = {
     "lotkacomp3": (14, 3, 1),
     "f8aircraft4": (15, 4, 2),
     "doubleosc6": (16, 6, 1),
+    "lotka2_oed_cu": (17, 9, 3),
+    "lotka2_oed_cf": (18, 12, 5),
+    "lotka2_oed_ds": (19, 6, 5),
+    "lotka2_oed_du": (20, 6, 3),
+    "lin1d_oed_cf": (21, 3, 2),
+    "lin1d_oed_ds": (22, 2, 2),
 }
 
 # base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)

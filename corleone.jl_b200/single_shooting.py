@@ -213,7 +213,10 @@ class SingleShootingLayer:
             nx=nx, np_all=npar, u0=prob.u0, tunable_p=[i for i in range(1, npar + 1) if i not in cidx],
             control_indices=cidx, quadrature_indices=self.quadrature_indices,
             intervals=[self._interval_desc(s, l, is_shooting) for s, l in zip(interval_sts, interval_lengths)],
-            device=self.device, fim_offset=fim[0], fim_n=fim[1], model_data=prob.model_data)
+            device=self.device, model_data=prob.model_data,
+            **(dict(fim_offset=fim["offset"], fim_n=fim["n"], fim_mode=fim["mode"], fim_base_nx=fim["base_nx"],
+                    n_observed=fim["n_observed"], observation_rows=fim["rows"]) if isinstance(fim, dict)
+               else dict(fim_offset=fim[0], fim_n=fim[1])))
 
     def _native(self, st, ps, shooting_layer: bool = False):
         # fixval is problem.u0 unless the caller passes shooting_layer = true (:359); one handle per flag

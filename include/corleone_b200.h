@@ -66,7 +66,15 @@ typedef enum {
     CB200_MODEL_BATCHREACTOR2 = 13, /* batch_reactor.jl:9-17, p = (u) */
     CB200_MODEL_LOTKACOMP3 = 14,    /* lotka_competitive.jl:9-31 */
     CB200_MODEL_F8AIRCRAFT4 = 15,   /* f8.jl:9-41, p = (T, u) */
-    CB200_MODEL_DOUBLEOSC6 = 16     /* double_oscillator.jl:9-38; time rides along as a state (tau' = 1) */
+    CB200_MODEL_DOUBLEOSC6 = 16,    /* double_oscillator.jl:9-38; time rides along as a state (tau' = 1) */
+    /* the other variants of the OED augmentation (lib/CorleoneOED/src/augmentation.jl), Lotka: params=[2,3],
+       observed=u[1:2]; 1-D: params=[1], observed=[u[1]] */
+    CB200_MODEL_LOTKA2_OED_CU = 17, /* Continuous, no measurements (:217-220): [x; G; F_triu], F' = (sum_i h_i G)'(sum_i h_i G) */
+    CB200_MODEL_LOTKA2_OED_CF = 18, /* ContinuousSampled, fixed (:255-292): [x; G; F_1 triu; F_2 triu], p = (base p; w) */
+    CB200_MODEL_LOTKA2_OED_DS = 19, /* DiscreteSampled (:171-203): [x; G], p = (base p; w); information summed over samples */
+    CB200_MODEL_LOTKA2_OED_DU = 20, /* Discrete, no measurements (:171-203): [x; G], p = base p */
+    CB200_MODEL_LIN1D_OED_CF = 21,
+    CB200_MODEL_LIN1D_OED_DS = 22
 } cb200_model;
 
 typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;
@@ -89,7 +97,7 @@ typedef struct {
     int32_t device;             /* CUDA ordinal */
     int32_t fim_offset;         /* 1-based state index of the first F_triu state, 0 = no Fisher block */
     int32_t fim_n;              /* n: F is n x n, stored as n(n+1)/2 column-major upper-triangle states */
-    int32_t reserved;
+    int32_t fim_mode;           /* cb200_fim_mode: how the Fisher information is read out (0 = from the end state) */
     const double *u0;                   /* [nx] problem.u0 (fixval of the first interval, single_shooting.jl:359) */
     const int64_t *tunable_p;           /* [n_tunable_p] 1-based indices into problem.p (single_shooting.jl:109) */
     const int64_t *control_indices;     /* [n_controls] 1-based p index per control, user order (layer.control_indices) */
@@ -108,7 +116,27 @@ typedef struct {
     const int64_t *shooting_indices;    /* [sum] st.shooting_indices, 1-based over [states; controls] */
     const double *model_data;           /* model constants (DENSE20: W row-major 20x20, then b[20]) or NULL */
     int64_t model_data_len;
+    /* sample-based Fisher read-outs (fim_mode != 0); G = the nx_base x fim_n block behind the base states, the
+       observed functions are the leading n_observed base states */
+    int32_t fim_base_nx;                /* states of the un-augmented problem */
+    int32_t n_observed;                 /* n_observed(oed) = number of observed functions (oed.jl:283) */
+    const int32_t *n_observation_rows;  /* [I] length(st.observation_grid.grid) of each interval (oed.jl:307-323,
+                                           350-366); NULL when fim_mode == CB200_FIM_DISCRETE */
+    const int64_t *observation_grid;    /* [sum rows][n_observed] WeightedObservation.grid, row-major as Julia's
+                                           Vector{Vector{Int64}}: 1-based index into the interval's ps.controls of
+                                           the weight applied at the row's sample, 0 = not measured (oed.jl:2-16).
+                                           Row j of interval i belongs to the interval's j-th saved sample.  For
+                                           CB200_FIM_FIXED_CONTINUOUS row j holds the j-th entries of
+                                           st.active_controls (oed.jl:352-362) and weights F(sample j+1) - F(sample j) */
 } cb200_desc;
+
+/* Fisher read-out (lib/CorleoneOED/src/oed.jl:381-461) */
+typedef enum {
+    CB200_FIM_END = 0,              /* continuous: F_init + Symmetric(F_triu(t_end))                       (:388-398) */
+    CB200_FIM_DISCRETE = 1,         /* OEDLayer{true,false}: sum over all saved samples of (sum_i h_i G)'(sum_i h_i G) (:446-461) */
+    CB200_FIM_DISCRETE_SAMPLED = 2, /* OEDLayer{true,true}: sum_s sum_i (w_i h_i G)'(w_i h_i G)            (:401-432) */
+    CB200_FIM_FIXED_CONTINUOUS = 3  /* OEDLayer{false,true,true}: sum_j sum_i w_i[j] (F_i(t_j+1) - F_i(t_j)) (:352-362,464-470) */
+} cb200_fim_mode;
 
 /* what cb200_eval should produce (bit mask) */
 #define CB200_WANT_XEND 0x001u      /* raw end state of every interval */
@@ -117,7 +145,7 @@ typedef struct {
 #define CB200_WANT_DEFECTS 0x008u   /* shooting constraints, both orderings */
 #define CB200_WANT_OBJ 0x010u       /* last(traj)[objective_row] per candidate */
 #define CB200_WANT_GRAD 0x020u      /* d objective / d ps */
-#define CB200_WANT_FIM 0x040u       /* F_init + symmetric F(t_end) per candidate, and its sum over candidates */
+#define CB200_WANT_FIM 0x040u       /* F_init + the layer's Fisher read-out (cb200_fim_mode) per candidate, and its sum over candidates */
 #define CB200_WANT_CRIT 0x100u      /* the six OED criteria of Symmetric(F) per candidate (criteria.jl:33-63) */
 #define CB200_WANT_GRAD_COMPACT 0x200u /* d objective / d ps without the structural zeros (cb200_grad_structure) */
 #define CB200_WANT_TRAJ_SENS 0x400u /* sensitivities at every saved sample (point constraints, src/dynprob.jl:30-58) */

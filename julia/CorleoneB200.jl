@@ -35,7 +35,7 @@ struct Desc                      # cb200_desc
     device::Int32
     fim_offset::Int32
     fim_n::Int32
-    reserved::Int32
+    fim_mode::Int32                  # cb200_fim_mode
     u0::Ptr{Float64}
     tunable_p::Ptr{Int64}
     control_indices::Ptr{Int64}
@@ -53,6 +53,10 @@ struct Desc                      # cb200_desc
     shooting_indices::Ptr{Int64}
     model_data::Ptr{Float64}
     model_data_len::Int64
+    fim_base_nx::Int32
+    n_observed::Int32
+    n_observation_rows::Ptr{Int32}
+    observation_grid::Ptr{Int64}
 end
 
 struct Out                       # cb200_out
@@ -94,7 +98,9 @@ const WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT = 0x010, 0x020, 0x040, 
 
 const MODELS = Dict(:lotka3 => 0, :lqr => 1, :lotka2 => 2, :lotka2_oed => 3, :lin1d => 4, :lin1d_oed => 5,
                     :dense20 => 6, :egerstedt => 7, :vdp3 => 8, :cartpole5 => 9, :rocket3 => 10, :quadrotor7 => 11, :threetank4 => 12,
-                    :batchreactor2 => 13, :lotkacomp3 => 14, :f8aircraft4 => 15, :doubleosc6 => 16)
+                    :batchreactor2 => 13, :lotkacomp3 => 14, :f8aircraft4 => 15, :doubleosc6 => 16,
+                    :lotka2_oed_cu => 17, :lotka2_oed_cf => 18, :lotka2_oed_ds => 19, :lotka2_oed_du => 20,
+                    :lin1d_oed_cf => 21, :lin1d_oed_ds => 22)
 
 lasterror() = unsafe_string(ccall((:cb200_last_error, LIB), Cstring, ()))
 check(rc, what) = rc == 0 || error("$what failed ($rc): $(lasterror())")
@@ -115,13 +121,17 @@ mutable struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     device::Int
     model_data::Vector{Float64}
     fim::Tuple{Int, Int}                 # (1-based offset of the first F_triu state, n) or (0, 0)
+    fim_mode::Int                        # 0 end state, 1 Discrete, 2 DiscreteSampled, 3 fixed ContinuousSampled
+    fim_base_nx::Int                     # states of the un-augmented problem (sample-based read-outs)
+    n_observed::Int
     handle::Ptr{Cvoid}
     sizes::Sizes
     nx::Int
 end
 function EnsembleB200(; model::Symbol, steps_per_piece = 1, method = :tsit5, device = 0,
-        model_data = Float64[], fim = (0, 0))
-    e = EnsembleB200(model, steps_per_piece, method, device, collect(Float64, model_data), fim, C_NULL,
+        model_data = Float64[], fim = (0, 0), fim_mode = 0, fim_base_nx = 0, n_observed = 0)
+    e = EnsembleB200(model, steps_per_piece, method, device, collect(Float64, model_data), fim, fim_mode,
+        fim_base_nx, n_observed, C_NULL,
         Sizes(0, 0, 0, 0, 0, 0, 0, 0, 0), 0)
     finalizer(e) do x
         x.handle == C_NULL || ccall((:cb200_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle)
@@ -163,14 +173,24 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
     end
     u0 = collect(Float64, prob.u0)
     md = e.model_data
+    # WeightedObservation.grid of every interval (lib/CorleoneOED/src/oed.jl:2-16,307-323,350-366), rows flattened
+    n_obs_rows = Int32[]; obs_grid = Int64[]
+    for f in fields
+        sti = getproperty(st, f)
+        haskey(sti, :observation_grid) || continue
+        push!(n_obs_rows, length(sti.observation_grid.grid))
+        foreach(row -> append!(obs_grid, row), sti.observation_grid.grid)
+    end
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve u0 tunable_p cidx quad n_pieces tsp grid n_u0 n_c is_sh sorting ncon cons nsi sidx md begin
+    GC.@preserve u0 tunable_p cidx quad n_pieces tsp grid n_u0 n_c is_sh sorting ncon cons nsi sidx md n_obs_rows obs_grid begin
         d = Desc(sizeof(Desc), MODELS[e.model], e.method === :tsit5 ? 0 : 1, e.steps_per_piece, nx, np_all,
-            length(cidx), length(tunable_p), I, length(quad), e.device, e.fim[1], e.fim[2], 0,
+            length(cidx), length(tunable_p), I, length(quad), e.device, e.fim[1], e.fim[2], e.fim_mode,
             pointer(u0), pointer(tunable_p), pointer(cidx), pointer(quad), pointer(n_pieces), pointer(tsp),
             pointer(grid), pointer(n_u0), pointer(n_c), pointer(is_sh), pointer(sorting), pointer(ncon),
             pointer(cons), pointer(nsi), pointer(sidx), isempty(md) ? Ptr{Float64}(C_NULL) : pointer(md),
-            length(md))
+            length(md), e.fim_base_nx, e.n_observed,
+            isempty(n_obs_rows) ? Ptr{Int32}(C_NULL) : pointer(n_obs_rows),
+            isempty(obs_grid) ? Ptr{Int64}(C_NULL) : pointer(obs_grid))
         check(ccall((:cb200_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h), "cb200_create")
     end
     e.handle = h[]

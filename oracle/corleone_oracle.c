@@ -317,8 +317,13 @@ static void rhs_doubleosc6(const dual *x, const dual *p, dual *du)
 
 typedef void (*rhs_fn)(const dual *, const dual *, dual *);
 typedef void (*jac_fn)(const dual *, const dual *, dual *, dual *);
-static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, const dual *u, const dual *p,
-                    dual *du)
+/* variants of the augmentation (augmentation.jl): which F states exist and what they integrate */
+enum { AUG_CS = 0, /* ContinuousSampled, non-fixed :206-253: F' = sum_i w_i g_i'g_i, p = [base; w]         */
+       AUG_CU = 1, /* Continuous, no measurements :217-220: F' = (sum_i g_i)'(sum_i g_i), p = base        */
+       AUG_CF = 2, /* ContinuousSampled, fixed :255-292: F_k' = g_k'g_k per observed k, p = [base; w]      */
+       AUG_D = 3   /* Discrete / DiscreteSampled :171-203: no F states                                     */ };
+static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, int variant, const dual *u,
+                    const dual *p, dual *du)
 {
     dual Jx[CO_MAX_NX], Jp[CO_MAX_NX];
     f(u, p, du);
@@ -334,12 +339,26 @@ static void rhs_oed(rhs_fn f, jac_fn jac, int nx, int npb, int nF, int nobs, con
     dual *dF = du + nx + nx * nF;
     const dual *w = p + npb;
     int q = 0;
-    for (int b = 0; b < nF; b++)
-        for (int a = 0; a <= b; a++) {
-            dual acc = dconst(0.0);
-            for (int i = 0; i < nobs; i++) acc = dadd(acc, dmul(w[i], dmul(G[i + nx * a], G[i + nx * b])));
-            dF[q++] = acc;
+    if (variant == AUG_CS) {
+        for (int b = 0; b < nF; b++)
+            for (int a = 0; a <= b; a++) {
+                dual acc = dconst(0.0);
+                for (int i = 0; i < nobs; i++) acc = dadd(acc, dmul(w[i], dmul(G[i + nx * a], G[i + nx * b])));
+                dF[q++] = acc;
+            }
+    } else if (variant == AUG_CU) { /* rows of h_x G are summed first, then the outer product (:217-220) */
+        dual sg[CO_MAX_NX];
+        for (int a = 0; a < nF; a++) {
+            sg[a] = dconst(0.0);
+            for (int i = 0; i < nobs; i++) sg[a] = dadd(sg[a], G[i + nx * a]);
         }
+        for (int b = 0; b < nF; b++)
+            for (int a = 0; a <= b; a++) dF[q++] = dmul(sg[a], sg[b]);
+    } else if (variant == AUG_CF) { /* _F = vcat over k of F[k,:,:][selector] (:271) */
+        for (int i = 0; i < nobs; i++)
+            for (int b = 0; b < nF; b++)
+                for (int a = 0; a <= b; a++) dF[q++] = dmul(G[i + nx * a], G[i + nx * b]);
+    }
 }
 
 static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du)
@@ -348,9 +367,9 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_LOTKA3: rhs_lotka3(u, p, du); break;
     case CO_LQR: rhs_lqr(u, p, du); break;
     case CO_LOTKA2: rhs_lotka2(u, p, du); break;
-    case CO_LOTKA2_OED: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, u, p, du); break;
+    case CO_LOTKA2_OED: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, AUG_CS, u, p, du); break;
     case CO_LIN1D: rhs_lin1d(u, p, du); break;
-    case CO_LIN1D_OED: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, u, p, du); break;
+    case CO_LIN1D_OED: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, AUG_CS, u, p, du); break;
     case CO_DENSE20: rhs_dense20(u, p, du, m->data); break;
     case CO_EGERSTEDT: rhs_egerstedt(u, p, du); break;
     case CO_VDP3: rhs_vdp3(u, p, du); break;
@@ -362,6 +381,12 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_LOTKACOMP3: rhs_lotkacomp3(u, p, du); break;
     case CO_F8AIRCRAFT4: rhs_f8aircraft4(u, p, du); break;
     case CO_DOUBLEOSC6: rhs_doubleosc6(u, p, du); break;
+    case CO_LOTKA2_OED_CU: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, AUG_CU, u, p, du); break;
+    case CO_LOTKA2_OED_CF: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, AUG_CF, u, p, du); break;
+    case CO_LOTKA2_OED_DS:
+    case CO_LOTKA2_OED_DU: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, AUG_D, u, p, du); break;
+    case CO_LIN1D_OED_CF: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, AUG_CF, u, p, du); break;
+    case CO_LIN1D_OED_DS: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, AUG_D, u, p, du); break;
     default: break;
     }
 }

@@ -49,7 +49,14 @@ enum co_model {
     CO_BATCHREACTOR2 = 13, /* .../batch_reactor.jl:9-17, p = (u) */
     CO_LOTKACOMP3 = 14,  /* .../lotka_competitive.jl:9-31 (+ Lagrange state) */
     CO_F8AIRCRAFT4 = 15, /* .../f8.jl:9-41, p = (T, u) */
-    CO_DOUBLEOSC6 = 16   /* .../double_oscillator.jl:9-38 (+ time and Lagrange states) */
+    CO_DOUBLEOSC6 = 16,  /* .../double_oscillator.jl:9-38 (+ time and Lagrange states) */
+    /* the other variants of lib/CorleoneOED/src/augmentation.jl for the Lotka / 1-D problems */
+    CO_LOTKA2_OED_CU = 17, /* Continuous, no measurements (:217-220) */
+    CO_LOTKA2_OED_CF = 18, /* ContinuousSampled, fixed (:255-292) */
+    CO_LOTKA2_OED_DS = 19, /* DiscreteSampled (:171-203) */
+    CO_LOTKA2_OED_DU = 20, /* Discrete (:171-203) */
+    CO_LIN1D_OED_CF = 21,
+    CO_LIN1D_OED_DS = 22
 };
 
 enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };

@@ -32,6 +32,12 @@ MODELS = {
     "lotkacomp3": 14,
     "f8aircraft4": 15,
     "doubleosc6": 16,
+    "lotka2_oed_cu": 17,
+    "lotka2_oed_cf": 18,
+    "lotka2_oed_ds": 19,
+    "lotka2_oed_du": 20,
+    "lin1d_oed_cf": 21,
+    "lin1d_oed_ds": 22,
 }
 METHODS = {"tsit5": 0, "rk4": 1}
 CO_ND = 16
@@ -305,3 +311,89 @@ class OracleLayer:
 
 def max_threads():
     return lib().co_max_threads()
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# Fisher read-outs of lib/CorleoneOED/src/oed.jl, restated literally (plain loops, 1-based tables as Julia holds them).
+# `u` is the (nrow, nsamples) sample matrix of OracleLayer.eval; observed = the leading n_obs states, so
+# h_x[k, :] G = row k of the bx x nf block G that follows the base states (augmentation.jl:131-159).
+def _hxG(u, s, bx, nf, n_obs):
+    """[h_1 G; h_2 G; ...] at sample s: (n_obs, nf)"""
+    return np.array([[u[bx + k + bx * a, s] for a in range(nf)] for k in range(n_obs)])
+
+
+def weighting_grid(control_grids, sampling_positions, index_grid, tspan, restrict):
+    """WeightedObservation.grid (oed.jl:291-311 for a single-shooting layer, :341-357 per interval of a multiple-shooting
+    layer with restrict = True).  control_grids: the full time grid of EVERY control of the layer; sampling_positions:
+    1-based positions of the measurement controls among them; index_grid: build_index_grid(controls...; tspan) as an
+    (n_controls, M) 1-based matrix.  Returns a list (one entry per point of the overall grid) of lists (one entry per
+    measurement control) of 1-based indices into ps.controls, 0 = no measurement there."""
+    overall = sorted(set(float(t) for g in control_grids for t in g) | {float(tspan[0]), float(tspan[1])})
+    if restrict:
+        overall = [t for t in overall if tspan[0] <= t < tspan[1]]
+    observed_grid = []
+    for s in sampling_positions:
+        grid = sorted(set(float(t) for t in control_grids[s - 1]))
+        observed_grid.append([i + 1 for i, t in enumerate(overall) if t in grid])          # findall(in(grid), overall)
+    measurement_indices = []
+    for s in sampling_positions:
+        seen = []
+        for v in index_grid[s - 1]:
+            if int(v) not in seen:
+                seen.append(int(v))                                                        # unique(mi)
+        measurement_indices.append(seen)
+    out = []
+    for i in range(1, len(overall) + 1):
+        row = []
+        for j in range(len(observed_grid)):
+            idn = observed_grid[j].index(i) + 1 if i in observed_grid[j] else None         # findfirst(i .== observed_grid[j])
+            row.append(0 if idn is None else measurement_indices[j][idn - 1])
+        out.append(row)
+    return out
+
+
+def fisher_discrete_sampled(controls, grid, u, sample0, bx, nf, n_obs):
+    """WeightedObservation call (oed.jl:2-16): sum_i (psub .* G_i)'(psub .* G_i) over the rows of `grid`; row i
+    belongs to sample sample0 + i of `u`.  controls: the (interval's) ps.controls vector."""
+    F = np.zeros((nf, nf))
+    for i, row in enumerate(grid):
+        psub = np.array([0.0 if j == 0 else controls[j - 1] for j in row])
+        G = psub[:, None] * _hxG(u, sample0 + i, bx, nf, n_obs)
+        F += G.T @ G
+    return F
+
+
+def fisher_discrete(u, bx, nf, n_obs):
+    """OEDLayer{true, false} (oed.jl:446-461) with the output expression of augmentation.jl:182-186: the rows of
+    h_x G are summed first, then G'G, summed over ALL saved samples."""
+    F = np.zeros((nf, nf))
+    for s in range(u.shape[1]):
+        g = _hxG(u, s, bx, nf, n_obs).sum(axis=0)[None, :]
+        F += g.T @ g
+    return F
+
+
+def fisher_fixed_continuous(controls, active_controls, u, bx, nf, n_obs):
+    """OEDLayer{false, true, true} (oed.jl:352-362): fim[s] is the (nf, nf, n_obs) array of the per-observation
+    Fisher states at sample s (augmentation.jl:262-271), w = eachrow(hcat(controls[active]...)), and
+    F = sum over zip(w, diff(fim)) of F[:, :, k] * w[k]."""
+    f_off = bx * (1 + nf)
+    ntri = nf * (nf + 1) // 2
+
+    def fim_at(s):
+        out = np.zeros((nf, nf, n_obs))
+        for k in range(n_obs):
+            for i in range(nf):
+                for j in range(nf):
+                    lo, hi = min(i, j), max(i, j)
+                    out[i, j, k] = u[f_off + k * ntri + hi * (hi + 1) // 2 + lo, s]
+        return out
+
+    fim = [fim_at(s) for s in range(u.shape[1])]
+    w = np.stack([np.asarray(controls)[np.asarray(a) - 1] for a in active_controls], axis=1)   # rows = eachrow(hcat)
+    diffF = [b - a for a, b in zip(fim[:-1], fim[1:])]
+    F = np.zeros((nf, nf))
+    for wi, dF in zip(w, diffF):
+        for k in range(n_obs):
+            F += dF[:, :, k] * wi[k]
+    return F
