@@ -72,23 +72,23 @@ def criteria_gradient(nat: "native.NativeLayer", ps_batch, fim_init=None):
     for c in range(B):
         F = r["fim"][c].reshape(n, n)
         S = r["sens"][c][sens_off:sens_off + nx * ns_last].reshape(ns_last, nx)    # [direction, state]
-        lam, V = np.linalg.eigh(F)
-        Finv = np.linalg.inv(F)
-        det = np.linalg.det(F)
-        vmin = V[:, 0]
-        for d in range(ns_last):
-            dF = np.zeros((n, n))
-            for q, (a, b) in enumerate(iu):
-                dF[a, b] = dF[b, a] = S[d, f_off + q]
-            g = out[c, :, blocks[I - 1] + d]
-            t = np.trace(Finv @ dF)
-            g[0] = -np.trace(Finv @ dF @ Finv)
-            g[1] = -t / det
-            g[2] = -(vmin @ dF @ vmin) / lam[0] ** 2
-            g[3] = -np.trace(dF)
-            g[4] = -det * t
-            g[5] = -(vmin @ dF @ vmin)
+        dF = np.zeros((n, n, ns_last))
+        for q, (a, b) in enumerate(iu):
+            dF[a, b] = dF[b, a] = S[:, f_off + q]
+        out[c, :, blocks[I - 1]:blocks[I]] = criteria_chain(F, dF)
     return out
+
+
+def criteria_chain(F, dF):
+    """d(criteria)/dv from F (n, n) and dF/dv (n, n, nv): (6, nv), rows in `ORDER` (criteria.jl:33-63 differentiated)."""
+    lam, V = np.linalg.eigh(F)
+    Finv = np.linalg.inv(F)
+    det = np.linalg.det(F)
+    vmin = V[:, 0]
+    t = np.einsum("ab,bav->v", Finv, dF)                 # tr(F^-1 dF)
+    q = np.einsum("a,abv,b->v", vmin, dF, vmin)          # v_min' dF v_min
+    return np.stack([-np.einsum("ab,bcv,ca->v", Finv, dF, Finv), -t / det, -q / lam[0] ** 2,
+                     -np.einsum("aav->v", dF), -det * t, -q])
 
 
 def _hxG(traj_samples, bx: int, nf: int, nobs: int):

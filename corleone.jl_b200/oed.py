@@ -179,6 +179,68 @@ class OEDLayer:
         F = r["fim"].reshape(X.shape[0], self.n_fisher, self.n_fisher)
         return (F, r["criteria"]) if criteria else F
 
+    def fisher_gradient(self, X, ps_like, st, add_initial: bool = True):
+        """F (B, n, n) and dF/d(flat variables) (B, n, n, nvars) -- what ForwardDiff through `fisher_information` yields.
+        One cb200_eval per call: the samples and their sensitivities (CB200_WANT_TRAJ_SENS) come from the device, the
+        product rule of the read-out (oed.jl:2-16,352-362,446-461) is host arithmetic.  The end-state read-out goes
+        through criteria.criteria_gradient instead."""
+        from .multiple_shooting import trajectory_jacobian
+        if self.fim_mode == FIM_END:
+            raise ValueError("end-state read-out: use criteria.criteria_gradient")
+        nat = self.native(ps_like, st)
+        first = st if self.single else next(iter(st.values()))
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        r = nat.eval_host(X, native.WANT_FIM | native.WANT_TRAJ | native.WANT_TRAJ_SENS | native.WANT_SENS,
+                          fim_init=first["F_init"] if add_initial else None)
+        B, n, bx, nobs = X.shape[0], self.n_fisher, self.base_nx, self.n_obs
+        F = r["fim"].reshape(B, n, n)
+        dF = np.zeros((B, n, n, nat.nvars))
+        blocks = nat.block_structure()
+        rows = []                                           # (sample, observed k, flat variable of the weight)
+        if self.fim_mode != FIM_DISCRETE:
+            sts = [st] if self.single else list(st.values())
+            pss = [ps_like] if self.single else list(ps_like.values())
+            s0 = 0
+            for i, (sti, psi, grid) in enumerate(zip(sts, pss, first["_fim"]["rows"])):
+                c0 = int(blocks[i]) + len(psi["u0"]) + len(psi["p"])
+                rows += [(s0 + j, k, c0 + int(v) - 1) for j, row in enumerate(grid) for k, v in enumerate(row) if v > 0]
+                s0 += len(_flatten_chunks(sti["tspans"]))
+        gi = bx + bx * np.arange(n)                         # state rows of g_k: gi + k
+        ntri = n * (n + 1) // 2
+        tri = np.array([[max(a, b) * (max(a, b) + 1) // 2 + min(a, b) for b in range(n)] for a in range(n)])
+        f_off = bx * (1 + n)
+        for b in range(B):
+            u = r["traj"][b].reshape(nat.n_samples, nat.n_row).T
+            J = trajectory_jacobian(self.layer, st, ps_like, r, b)             # (n_row, n_samples, nvars)
+            if self.fim_mode == FIM_DISCRETE:
+                s = sum(u[gi + k] for k in range(nobs))                         # (n, n_samples)
+                ds = sum(J[gi + k] for k in range(nobs))                        # (n, n_samples, nvars)
+                dF[b] = np.einsum("asv,bs->abv", ds, s) + np.einsum("as,bsv->abv", s, ds)
+                continue
+            for smp, k, var in rows:
+                w = X[b, var]
+                if self.fim_mode == FIM_DISCRETE_SAMPLED:
+                    g, dg = u[gi + k, smp], J[gi + k, smp]
+                    dF[b] += w * w * (dg[:, None, :] * g[None, :, None] + g[:, None, None] * dg[None, :, :])
+                    dF[b, :, :, var] += 2.0 * w * np.outer(g, g)
+                else:
+                    q = f_off + k * ntri + tri
+                    dF[b] += w * (J[q, smp + 1] - J[q, smp])
+                    dF[b, :, :, var] += u[q, smp + 1] - u[q, smp]
+        return F, dF
+
+    def criteria_gradient(self, X, ps_like, st, add_initial: bool = True):
+        """the six criteria (B, 6) and their gradients (B, 6, nvars) for any variant"""
+        from .criteria import batched_criteria, criteria_chain, criteria_gradient
+        first = st if self.single else next(iter(st.values()))
+        if self.fim_mode == FIM_END:
+            nat = self.native(ps_like, st)
+            fi = first["F_init"] if add_initial else None
+            return batched_criteria(nat, X, fim_init=fi)[0], criteria_gradient(nat, X, fim_init=fi)
+        F, dF = self.fisher_gradient(X, ps_like, st, add_initial)
+        crit = self.fisher_information(X, ps_like, st, add_initial, criteria=True)[1]
+        return crit, np.stack([criteria_chain(F[b], dF[b]) for b in range(len(F))])
+
     def get_sampling_sums(self, ps, st):
         """get_sampling_sums (oed.jl:536-640): one number per measurement control -- the number of (weighted)
         measurements for the discrete variants (:573-580), the measured time sum_j w_j dt_j for the continuous ones
@@ -203,6 +265,42 @@ class OEDLayer:
                 for k, s in enumerate(self.sampling_indices):
                     out[k] += (c[grid[s - 1] - 1] * dts).sum()
         return out
+
+
+def sampling_sum_matrix(oed: OEDLayer, ps_like, st) -> np.ndarray:
+    """get_sampling_sums is linear in the variables for every variant: its matrix (n_observed, nvars)."""
+    from .single_shooting import from_vec
+    x0 = to_vec(ps_like)
+    A = np.zeros((oed.n_obs if oed.SAMPLED else 0, len(x0)))
+    for v in range(len(x0)):
+        e = np.zeros(len(x0))
+        e[v] = 1.0
+        A[:, v] = oed.get_sampling_sums(from_vec(e, ps_like), st)
+    return A
+
+
+def solve_slsqp(oed: OEDLayer, ps_like, st, criterion: int = 0, M=None, x0=None, maxiter=300, ftol=1e-12):
+    """OptimizationProblem(oed, criterion; M) (lib/CorleoneOED/ext/CorleoneOEDOptimizationExtension.jl) with SciPy's
+    SLSQP standing in for Ipopt: minimise one criterion (index into criteria.ORDER) within the variable bounds subject
+    to sampling sums <= M; value and gradient from the device (criteria_gradient).  Single shooting."""
+    from scipy.optimize import Bounds, LinearConstraint, minimize
+    from .multiple_shooting import get_bounds
+    x0 = to_vec(ps_like) if x0 is None else np.asarray(x0, dtype=np.float64)
+    lo, hi = get_bounds(oed.layer)
+    cache = {}
+
+    def ev(x):
+        key = x.tobytes()
+        if cache.get("key") != key:
+            c, g = oed.criteria_gradient(x[None, :], ps_like, st)
+            cache.update(key=key, val=(float(c[0, criterion]), g[0, criterion].copy()))
+        return cache["val"]
+
+    cons = []
+    if M is not None and oed.SAMPLED:
+        cons.append(LinearConstraint(sampling_sum_matrix(oed, ps_like, st), -np.inf, np.asarray(M, dtype=np.float64)))
+    return minimize(lambda x: ev(x)[0], x0, jac=lambda x: ev(x)[1], bounds=Bounds(to_vec(lo), to_vec(hi)),
+                    constraints=cons, method="SLSQP", options=dict(maxiter=maxiter, ftol=ftol))
 
 
 def flat(ps) -> np.ndarray:

@@ -164,3 +164,89 @@ def test_sample_based_readout_rejects_bad_tables():
     st["_fim"]["rows"] = [np.full_like(st["observation_grid"], 10_000)]
     with pytest.raises(nat.NativeError, match="observation_grid"):
         o.native(ps, st)
+
+
+GRAD_CASES = [("discrete_sampled_ss", True, True, None, False), ("discrete_sampled_ms", True, True, SHOOT, False),
+              ("discrete_unsampled_ms", True, False, SHOOT, False), ("continuous_fixed_ss", False, True, None, True)]
+
+
+@pytest.mark.parametrize("name,discrete,sampled,shooting,fixed", GRAD_CASES, ids=[c[0] for c in GRAD_CASES])
+def test_fisher_gradient_of_the_sample_based_readouts(name, discrete, sampled, shooting, fixed):
+    """dF/d(variables) assembled from the device's sample sensitivities == the same product rule on the oracle's
+    dual-number sample Jacobian (<= 1e-10), and == central differences of the device's own F (<= 1e-6)"""
+    from oracle import pyoracle as po
+    K = 2
+    meas = ()
+    if sampled:
+        meas = measurements(0.7)
+        if fixed:
+            meas = [cb.ControlParameter(T1, controls=np.full(len(T1), 0.7), bounds=(0.0, 1.0)) for _ in range(2)]
+    o = oedm.OEDLayer(lotka_base(shooting, fixed=fixed, K=K), discrete, meas)
+    ps, st = o.setup(None)
+    O = po.OracleLayer(_oracle_spec(o, ps))
+    rng = np.random.default_rng(17)
+    x = cb.to_vec(ps)
+    if shooting is not None:
+        x = O.forward_init(x, K=K)
+    x = x + 0.02 * rng.standard_normal(len(x))
+    F, dF = o.fisher_gradient(x[None, :], ps, st)
+    # (1) central differences of the device's own read-out on a handful of variables of every kind
+    pick = rng.choice(len(x), size=min(12, len(x)), replace=False)
+    h = 1e-6
+    Xp = np.tile(x, (2 * len(pick), 1))
+    for q, v in enumerate(pick):
+        Xp[2 * q, v] += h
+        Xp[2 * q + 1, v] -= h
+    Fp = o.fisher_information(Xp, ps, st)
+    for q, v in enumerate(pick):
+        fd = (Fp[2 * q] - Fp[2 * q + 1]) / (2 * h)
+        assert rel_err(dF[0, :, :, v], fd) <= 1e-6, (name, v)
+    # (2) the oracle's samples and sample Jacobian through the same product rule
+    u, J = O.traj_jacobian(x, K=K)
+    Fo = oracle_fim(o, O, ps, st, x, K)
+    assert rel_err(F[0], Fo) <= RTOL
+    eps = 1e-7
+    for v in pick[:4]:       # directional check of the oracle read-out itself along the dual-number tangent
+        up = u + eps * J[:, :, v]
+        um = u - eps * J[:, :, v]
+        xp, xm = x.copy(), x.copy()
+        xp[v] += eps
+        xm[v] -= eps
+
+        def readout(uu, xx):
+            class _O:   # oracle_fim only needs eval()["u"]
+                def eval(self, _x, K):
+                    return dict(u=uu)
+            return oracle_fim(o, _O(), ps, st, xx, K)
+        lin = (readout(up, xp) - readout(um, xm)) / (2 * eps)
+        assert rel_err(dF[0, :, :, v], lin) <= 1e-7, (name, v)
+    crit, g = o.criteria_gradient(x[None, :], ps, st)
+    Fi = np.linalg.inv(F[0])
+    assert rel_err(g[0, 0], -np.einsum("ab,bcv,ca->v", Fi, dF[0], Fi)) <= 1e-12      # A criterion: -tr(F^-1 dF F^-1)
+
+
+def test_design_optimum_of_the_1d_problem_fixed_continuous_and_discrete():
+    """lib/CorleoneOED/test/core/1d_oed.jl with the measurement budget as a constraint: the information density
+    t^2 e^{2pt} peaks at t = 1/|p| = 0.5, so the optimal design measures on the pieces (samples) around it."""
+    t = np.arange(100) / 100.0
+    prob = cb.ODEProblem("lin1d", [1.0], (0.0, 1.0), [-2.0])
+    base = cb.SingleShootingLayer(prob, cb.Tsit5(4), bounds_p=([-2.0], [-2.0]))
+    prim = lambda s: np.exp(-4.0 * s) * (-(s * s) / 4.0 - s / 8.0 - 1.0 / 32.0)
+    edges = np.r_[t, 1.0]
+    # fixed continuous: F is linear in w; budget sum_j w_j dt <= 0.2 -> w = 1 on the 20 richest pieces
+    o = oedm.OEDLayer(base, False, [cb.ControlParameter(t, controls=np.full(100, 0.2), bounds=(0.0, 1.0))])
+    ps, st = o.setup(None)
+    res = oedm.solve_slsqp(o, ps, st, criterion=0, M=[0.2])
+    c = prim(edges[1:]) - prim(edges[:-1])
+    best = np.sort(np.argsort(c)[-20:])
+    w = res.x[-100:]
+    assert abs(res.fun - 1.0 / c[best].sum()) <= 1e-6 / c[best].sum(), (res.fun, 1.0 / c[best].sum())
+    assert np.all(w[best] > 0.99) and np.sum(w) <= 20.0 + 1e-6
+    # discrete: sum_i w_i <= 20 measurements; F = sum (w_i g_i)^2 -> the 20 samples with the largest g^2
+    o = oedm.OEDLayer(base, True, [cb.ControlParameter(t, controls=np.full(100, 0.2), bounds=(0.0, 1.0))])
+    ps, st = o.setup(None)
+    res = oedm.solve_slsqp(o, ps, st, criterion=0, M=[20.0])
+    g2 = (t * np.exp(-2.0 * t)) ** 2
+    best = np.sort(np.argsort(g2)[-20:])
+    assert res.fun <= 1.0 / g2[best].sum() * (1 + 1e-6) or abs(res.fun - 1.0 / g2[best].sum()) <= 1e-3 / g2[best].sum()
+    assert abs(o.fisher_information(res.x[None, :], ps, st)[0, 0, 0] - 1.0 / res.fun) <= 1e-9 / res.fun
