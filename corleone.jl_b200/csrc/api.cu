@@ -374,6 +374,7 @@ struct cb200_handle {
     int fim_off = -1, fim_n = 0;
     int fim_mode = 0, fim_bx = 0, n_obs = 0, n_obs_rows = 0;   // sample-based read-outs
     int *d_obs_sample = nullptr, *d_obs_var = nullptr;
+    int range_i0 = 0, range_n = -1;   // cb200_set_interval_range: intervals [i0, i0 + n); n < 0 = all
     int G_sens = 2;                   // sensitivity directions per thread
     void *tables = nullptr;           // one device allocation holding every table
     int *d_quad = nullptr;
@@ -570,6 +571,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.nact = nact;
     L.ntp = ntp;
     L.I = I;
+    L.i0 = 0;
+    L.In = I;
     L.K = d->steps_per_piece;
     L.R = 1;
     h->G_sens = default_G(d->model);
@@ -1081,6 +1084,23 @@ extern "C" int cb200_set_stream(cb200_handle *h, void *stream)
     return CB200_OK;
 }
 
+extern "C" int cb200_set_interval_range(cb200_handle *h, int32_t first, int32_t last)
+{
+    if (!h) return fail(CB200_ERR_ARG, "null handle");
+    std::lock_guard<std::mutex> lk(h->mu);
+    const int I = h->L.I;
+    if (first == 1 && last == I) {
+        h->range_i0 = 0;
+        h->range_n = -1;
+        return CB200_OK;
+    }
+    if (first < 1 || last > I || last < first - 1)
+        return fail(CB200_ERR_ARG, "interval range %d:%d outside 1:%d", first, last, I);
+    h->range_i0 = first - 1;
+    h->range_n = last - first + 1;   // first:first-1 is Julia's empty range
+    return CB200_OK;
+}
+
 extern "C" int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int64_t *src)
 {
     if (!h) return fail(CB200_ERR_ARG, "null handle");
@@ -1179,6 +1199,22 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
         L.R = (h->max_ns + G - 1) / G;
         if (L.R < 1) L.R = 1;
     }
+    const bool partial = h->range_n >= 0 && h->range_n < I;
+    if (partial) {
+        // a sub-range of the intervals (interval sharding across devices): everything the other intervals would
+        // have written stays zero, so that the per-device results ASSEMBLE BY SUMMATION (one all-reduce)
+        L.i0 = h->range_i0;
+        L.In = h->range_n;
+        const struct { double *p; long long n; } z[] = {
+            {d.xend, (long long)nx * I}, {d.sens, h->n_sens}, {d.traj, nrow * h->n_samples}, {d.dk, ndef}, {d.ds, ndef},
+            {d.grad, L0.nvars}, {d.objq, I}, {d.jac, h->jac_nnz_var}, {d.gradc, pl.gradc_n}, {d.tsens, h->n_tsens}};
+        for (const auto &e : z)
+            if (e.p && e.n > 0) CUDA_TRY(cudaMemsetAsync(e.p, 0, sizeof(double) * (size_t)e.n * (size_t)B, st));
+        if (L.In == 0) {   // nothing to integrate on this device: the outputs are the zeros
+            if (pl.obj && d.obj) CUDA_TRY(cudaMemsetAsync(d.obj, 0, sizeof(double) * (size_t)B, st));
+            return CB200_OK;
+        }
+    }
     ShootOut so{};
     so.xend = d.xend;
     so.sens = d.sens;
@@ -1208,15 +1244,21 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     h->n_timed++;
 
     // ---- K3 remainder: objective sum over intervals, control-row gradient, trajectory quadratures, FIM
-    if (pl.obj || pl.osum) {
+    // a control-row objective lives on the last interval: under interval sharding only its owner reports it
+    const bool owns_last = !partial || (L.i0 + L.In == I);
+    if ((pl.obj || pl.osum) && pl.obj_state < 0 && !owns_last) {
+        if (d.obj) CUDA_TRY(cudaMemsetAsync(d.obj, 0, sizeof(double) * (size_t)B, st));
+    } else if (pl.obj || pl.osum) {
         objective_kernel<<<nblk(B, 256), 256, 0, st>>>(d.objq, B, d_ps, d_ldb, B, I, pl.obj_state >= 0, pl.obj_quad,
                                                      pl.obj_ctrl_var, d.obj, d.osum);
         h->launches++;
     }
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {  // objective = a control row: the gradient is a unit vector
         if (d.grad) CUDA_TRY(cudaMemsetAsync(d.grad, 0, sizeof(double) * (size_t)L0.nvars * (size_t)B, st));
-        grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
-        h->launches++;
+        if (owns_last) {
+            grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
+            h->launches++;
+        }
     }
     if (pl.need_traj && h->nquad > 0 && I > 1) {
         traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, d.xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
@@ -1275,6 +1317,12 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     pl.tsens = (want & CB200_WANT_TRAJ_SENS) && out->traj_sens;
     if ((pl.fim || pl.fsum || pl.crit) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
     if (pl.crit && h->fim_n > CB200_MAX_FIM) return fail(CB200_ERR_UNSUPPORTED, "criteria need fim_n <= %d", CB200_MAX_FIM);
+    if (h->range_n >= 0 && h->range_n < I) {
+        if (pl.fim || pl.fsum || pl.crit)
+            return fail(CB200_ERR_UNSUPPORTED, "the Fisher read-out needs every interval on one device: reset cb200_set_interval_range");
+        if (pl.traj && h->nquad > 0 && I > 1)
+            return fail(CB200_ERR_UNSUPPORTED, "trajectory samples with quadrature running sums need every interval on one device");
+    }
     pl.obj_state = pl.obj_ctrl_var = -1;
     pl.objective_row = out->objective_row;
     if (pl.obj || pl.grad || pl.osum || pl.gsum || pl.gradc) {

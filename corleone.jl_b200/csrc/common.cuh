@@ -16,6 +16,7 @@ struct DevLayer {
     int nvars;
     int max_M;               // largest number of pieces of an interval
     int flat;                // launch mapping: 1 = flat thread index (tiny batches), 0 = grid (b-tiles, i, r)
+    int i0, In;              // intervals [i0, i0 + In) are integrated by this launch (cb200_set_interval_range); default 0, I
     int uniform_h;           // every piece of the layer has the same step size h = (t1 - t0)/K
     double hA[21];           // uniform_h: h * a_ij (Tsit5, slots as tsit5_coeffs) or the 4 RK4 factors
     int pmap_kind[MAX_NP];   // p_full[q] = kind ? controls_j[idx] : ps.p[idx]   (A, B of single_shooting.jl:306-323)

@@ -238,17 +238,18 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         // no integer divisions, and (i, r) is block-uniform
         // (lanes beyond B redo candidate B-1 without storing, so that warps stay whole for the shuffles)
         b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-        i = blockIdx.y;
+        i = blockIdx.y + L.i0;
         r = blockIdx.z;
     } else {
         // flat launch for tiny batches (B < 32): lanes of a warp span intervals and direction groups
-        const long long nsys = B * L.I;
+        const long long nsys = B * L.In;
         const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
         if (tid >= nsys * L.R) return;
         r = (int)(tid / nsys);
         const long long rem = tid - r * nsys;
-        i = (int)(rem / B);
-        b = rem - (long long)i * B;
+        const int il = (int)(rem / B);
+        i = il + L.i0;
+        b = rem - (long long)il * B;
     }
 
     const bool live = b < B;
@@ -571,16 +572,16 @@ inline int launch_block_size()
 template <class Mdl, int G, int METHOD, int MINB>
 int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, const ShootOut &o, cudaStream_t s)
 {
-    const long long nthreads = B * L.I * (long long)L.R;
+    const long long nthreads = B * L.In * (long long)L.R;
     if (nthreads <= 0) return 0;
     const int bs = launch_block_size();
     DevLayer L2 = L;
     dim3 grid;
-    L2.flat = (B < 32 || L.I > 65535 || L.R > 65535) ? 1 : 0;
+    L2.flat = (B < 32 || L.In > 65535 || L.R > 65535) ? 1 : 0;
     if (L2.flat)
         grid = dim3((unsigned)((nthreads + bs - 1) / bs), 1, 1);
     else
-        grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.I, (unsigned)L.R);
+        grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.In, (unsigned)L.R);
     if constexpr (G > 0) {
         if (o.tsens) {
             if (L.uniform_h)

@@ -359,9 +359,9 @@ shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restr
 {
     __shared__ double sx[2 * DM_CPB * DM_NX];
     if ((threadIdx.x >> 5) == 0)   // both branches meet at the same barrier (id 0), once per right-hand-side call
-        dense_unit<METHOD, UNI, false, true>(L, ps, ldb, B, o, blockIdx.y, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
+        dense_unit<METHOD, UNI, false, true>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
     else
-        dense_unit<METHOD, UNI, false, false>(L, ps, ldb, B, o, blockIdx.y, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
+        dense_unit<METHOD, UNI, false, false>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
 }
 
 __device__ __forceinline__ void dm_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
@@ -384,8 +384,8 @@ shoot_dense_mma_pipe_kernel(const __grid_constant__ DevLayer L, const double *__
     for (long long n = blockIdx.x; n < n_items; n += gridDim.x, kcount++) {
         const int buf = (int)(kcount & 1);
         // item -> (group, interval, round); intervals fastest so that a block's consecutive items share nothing but W
-        const int i = (int)(n % L.I);
-        const long long rest = n / L.I;
+        const int i = (int)(n % L.In) + L.i0;
+        const long long rest = n / L.In;
         const int round = (int)(rest % rounds);
         const long long grp = rest / rounds;
         double *xc = xcbuf + buf * per;
@@ -423,7 +423,7 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const long long n_items = gx * L.I * rounds;
+        const long long n_items = gx * L.In * rounds;
         const unsigned grid = (unsigned)std::min<long long>(n_items, sms);
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -438,8 +438,8 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
         }
         return (int)cudaGetLastError();
     }
-    if (gx > 2147483647LL || L.I > 65535 || rounds > 65535) return -1000;
-    dim3 grid((unsigned)gx, (unsigned)L.I, (unsigned)rounds);
+    if (gx > 2147483647LL || L.In > 65535 || rounds > 65535) return -1000;
+    dim3 grid((unsigned)gx, (unsigned)L.In, (unsigned)rounds);
     if (method == 0) {
         if (L.uniform_h)
             shoot_dense_mma_kernel<0, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);

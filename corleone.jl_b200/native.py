@@ -21,7 +21,7 @@ EXPORTS = (
     "cb200_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_sizes",
     "cb200_block_structure", "cb200_set_stream", "cb200_eval", "cb200_jac_structure",
     "cb200_last_kernel_ms", "cb200_kernel_ms_history", "cb200_launch_count", "cb200_probe_fp64_tflops",
-    "cb200_probe_fp64_mma_tflops", "cb200_forward_init", "cb200_grad_structure",
+    "cb200_probe_fp64_mma_tflops", "cb200_forward_init", "cb200_grad_structure", "cb200_set_interval_range",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -79,6 +79,7 @@ def lib():
         L.cb200_get_sizes.argtypes = [C.c_void_p, C.POINTER(Sizes)]
         L.cb200_block_structure.argtypes = [C.c_void_p, _i64p]
         L.cb200_set_stream.argtypes = [C.c_void_p, C.c_void_p]
+        L.cb200_set_interval_range.argtypes = [C.c_void_p, C.c_int32, C.c_int32]
         L.cb200_eval.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, C.c_uint32,
                                  C.POINTER(Out)]
         L.cb200_forward_init.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_uint32, _i32p, C.c_int32]
@@ -181,6 +182,10 @@ class NativeLayer:
             self.close()
         except Exception:
             pass
+
+    def set_interval_range(self, first: int, last: int):
+        """restrict the following evaluations to intervals first:last (1-based, inclusive; 1:I = all)"""
+        _check(lib().cb200_set_interval_range(self._h, int(first), int(last)), "cb200_set_interval_range")
 
     # ---- queries
     def block_structure(self) -> np.ndarray:

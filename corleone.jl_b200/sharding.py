@@ -10,6 +10,15 @@ cross-candidate partial sums crosses NVLink:
     allreduce(SUM)   objective_sum (1), grad_sum (nvars), fim_sum (n*n)   -- one flat buffer, one call
     allgather        per-candidate rows (defects, objectives) only when a caller wants them assembled
 
+When there are fewer candidates than GPUs (B < world size: the reference's own B = 1 use on a long horizon), the
+*interval* axis is partitioned instead (`IntervalShardedEvaluator`): rank r integrates the contiguous interval range
+`partition(I, world, r)` of every candidate (cb200_set_interval_range).  A matching defect belongs to the interval that
+ends at the node and needs only that interval's end state and the next interval's variables, which every rank holds,
+so nothing is exchanged before the epilogue; the per-rank outputs are full-size and zero outside the rank's range and
+assemble with
+
+    allreduce(SUM)   [defects | objective | gradient | constraint-Jacobian values | end states ...] -- one flat buffer
+
 Works on any torch.distributed backend: NCCL on the GPUs, gloo in the CPU tests.
 """
 from __future__ import annotations
@@ -119,5 +128,38 @@ class ShardedEvaluator:
             res.update({k: v.cpu().numpy() for k, v in combine_sums(parts, self.device, self.group).items()})
         for k in gather:
             res[k] = gather_candidates(res[k], ps_all.shape[0], self.group, self.device).cpu().numpy()
+        res["_shard"] = sh
+        return res
+
+
+class IntervalShardedEvaluator:
+    """Interval-sharded evaluation of one layer for B < world size.
+
+    `evaluate_range(ps_all, first, last) -> dict` is the rank-local hot path restricted to the intervals first:last
+    (1-based, inclusive; NativeLayer.set_interval_range + eval_host): every array has its full shape and is zero where
+    other intervals would have written.  All arrays are assembled by ONE all-reduce(SUM) of their concatenation
+    (`status` flags are summed too: non-zero = some interval of the candidate failed)."""
+
+    def __init__(self, evaluate_range, n_intervals: int, group=None, device=None):
+        self.evaluate_range = evaluate_range
+        self.n_intervals = int(n_intervals)
+        self.group = group
+        self.device = device
+
+    def rank_world(self):
+        dist = _dist()
+        if dist.is_available() and dist.is_initialized():
+            return dist.get_rank(self.group), dist.get_world_size(self.group)
+        return 0, 1
+
+    def __call__(self, ps_all: np.ndarray):
+        rank, world = self.rank_world()
+        sh = partition(self.n_intervals, world, rank)
+        res = dict(self.evaluate_range(ps_all, sh.start + 1, sh.stop))     # an empty shard is first:first-1
+        keys = [k for k in sorted(res) if isinstance(res[k], np.ndarray)]
+        parts = {k: res[k].astype(np.float64).ravel() for k in keys}
+        summed = combine_sums(parts, self.device, self.group)
+        for k in keys:
+            res[k] = summed[k].cpu().numpy().reshape(res[k].shape).astype(res[k].dtype)
         res["_shard"] = sh
         return res

@@ -17,7 +17,7 @@
  *                     289-295), the ForwardDiff derivatives of both (src/dynprob.jl:143-164), and the
  *                     continuous Fisher information (lib/CorleoneOED/src/oed.jl:381-398).
  *   cb200_jac_structure <- sparsity of cons_j in get_block_structure order (src/multiple_shooting.jl:320-328).
- *   cb200_destroy, cb200_last_error, cb200_version, cb200_set_stream: lifetime / plumbing (new).
+ *   cb200_destroy, cb200_last_error, cb200_version, cb200_set_stream, cb200_set_interval_range: lifetime / plumbing (new).
  *
  * Conventions
  *   - plain C, no exceptions cross the boundary; every call returns 0 or a negative cb200_status;
@@ -231,6 +231,15 @@ int cb200_block_structure(const cb200_handle *h, int64_t *blocks);
 
 /* optional: run on a caller-provided cudaStream_t (default: a private non-blocking stream). */
 int cb200_set_stream(cb200_handle *h, void *cuda_stream);
+
+/* Interval sharding ("B < #GPUs"): restrict the following cb200_eval calls to the shooting
+ * intervals first:last (1-based, inclusive, as a Julia range; first:first-1 = none, 1:I = all = the default) -- the
+ * slice of `mythreadmap` over intervals (src/Corleone.jl:22-24, src/multiple_shooting.jl:118-130) one device takes.
+ * Every per-candidate output keeps its full size and order; what the other intervals would have written is ZERO
+ * (matching defects belong to the interval that ends at the node), so the results of devices holding disjoint
+ * ranges assemble by summation: one all-reduce(SUM).  Not available with a partial range: the Fisher read-outs and
+ * trajectory samples with quadrature running sums (both need every interval's end state). */
+int cb200_set_interval_range(cb200_handle *h, int32_t first, int32_t last);
 
 /* Evaluate B candidates.  ldb: leading dimension of ps (>= nvars candidate-major, >= B variable-major).
  * Returns after the results are in the caller's buffers (host pointers) or after the work has been
