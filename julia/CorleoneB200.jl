@@ -139,6 +139,11 @@ function EnsembleB200(; model::Symbol, steps_per_piece = 1, method = :tsit5, dev
     return e
 end
 
+"Restrict the following evaluations to the shooting intervals `r` (interval sharding across devices, B < #GPUs)."
+set_interval_range!(e::EnsembleB200, r::UnitRange{Int}) =
+    check(ccall((:cb200_set_interval_range, LIB), Cint, (Ptr{Cvoid}, Int32, Int32), e.handle, first(r), last(r)),
+        "cb200_set_interval_range")
+
 flat_tspans(ts::Tuple{Vararg{Tuple{<:Real, <:Real}}}) = collect(ts)
 flat_tspans(ts::Tuple) = reduce(vcat, map(flat_tspans, ts))               # <=100-piece chunks (local_controls.jl:190-193)
 flat_grid(g::AbstractMatrix) = g
