@@ -209,3 +209,43 @@ def native_from_spec(spec, alg, device=0):
     if spec.get("fim"):
         first["_fim"] = tuple(spec["fim"])
     return lay, ps, st, lay._native(st, ps)
+
+
+# ---- the rest of lib/OptimalControlBenchmarks/src/problems: (model, u0, p0, tspan, [(p index, lo, hi) per control],
+#      number of control values, quadrature_indices, objective row (1-based), perturbation scale of the parity tests)
+#      initial values and horizons as in the problem files; control values are drawn uniformly inside (a part of) the
+#      bounds the files state
+BENCH_TABLE = {
+    "brysondenham": ("brysondenham3", [0.0, 1.0, 0.0], [0.0], (0.0, 1.0), [(1, -2.0, 2.0)], 20, [3], 3, 0.05),
+    "catalystmixing": ("catalystmixing2", [1.0, 0.0], [0.0], (0.0, 1.0), [(1, 0.0, 1.0)], 20, [], 1, 0.05),
+    "cushioned": ("cushioned3", [2.0, 5.0, 0.0], [1.0, 0.0], (0.0, 10.0), [(2, -5.0, 5.0)], 20, [3], 3, 0.05),
+    "denbigh": ("denbigh3", [1.0, 0.0, 0.0], [300.0], (0.0, 1000.0), [(1, 300.0, 330.0)], 100, [], 3, 0.005),   # fixed steps: rates <= 0.25
+    "dielectrophoretic": ("dielectrophoretic3", [1.0, 0.0, 0.0], [1.0, 1.0], (0.0, 5.0), [(2, -1.0, 1.0)], 20, [3], 1, 0.05),
+    "electriccar": ("electriccar4", [0.0, 0.0, 0.0, 0.0], [0.0], (0.0, 10.0), [(1, 0.0, 0.1)], 20, [4], 4, 0.01),
+    "fuller": ("fuller3", [0.01, 0.0, 0.0], [0.5], (0.0, 1.0), [(1, 0.0, 1.0)], 20, [3], 3, 0.05),
+    "jackson": ("jackson3", [1.0, 0.0, 0.0], [0.5], (0.0, 1.0), [(1, 0.0, 1.0)], 20, [], 3, 0.05),
+    "mountaincar": ("mountaincar3", [-0.5, 0.0, 0.0], [1.0, 0.5], (0.0, 100.0), [(2, -1.0, 1.0)], 20, [3], 1, 0.02),
+    "particlesteering": ("particlesteering5", [0.0, 0.0, 0.0, 0.0, 0.0], [3.0e-2, 0.0], (0.0, 10.0),
+                         [(2, -1.5, 1.5)], 20, [5], 1, 0.02),
+    "raomease": ("raomease2", [1.0, 0.0], [0.0], (0.0, 10.0), [(1, -1.0, 1.0)], 20, [2], 2, 0.05),
+    "robbins": ("robbins4", [1.0, -2.0, 0.0, 0.0], [0.0], (0.0, 10.0), [(1, -1.0, 1.0)], 20, [4], 4, 0.05),
+    "moonlanding": ("moonlanding3", [1.0, -0.783, 1.0], [1.0, 0.5], (0.0, 1.0), [(2, 0.0, 1.227)], 20, [], 3, 0.02),
+    "lotkashared": ("lotkashared4", [1.5, 1.0, 0.5, 0.0], [0.5], (0.0, 40.0), [(1, 0.0, 1.0)], 40, [4], 4, 0.02),
+    "hangingchain": ("hangingchain3", [1.0, 0.0, 0.0], [0.5], (0.0, 1.0), [(1, -1.0, 2.0)], 20, [], 2, 0.05),
+    "tubularreactor": ("tubularreactor2", [1.0, 0.0], [0.0], (0.0, 1.0), [(1, 0.0, 5.0)], 20, [], 2, 0.05),
+    "ocean": ("ocean4", [2.0e3, 1.0e4, 0.0, 0.0], [7.0, 7.0], (0.0, 400.0), [(1, 0.0, 40.0), (2, 0.0, 40.0)], 20, [4], 4, 0.02),
+    "ductedfan": ("ductedfan7", [0.0] * 7, [0.5, 0.0, 8.5], (0.0, 10.0), [(2, -1.0, 1.0), (3, 0.0, 10.0)], 20, [7], 7, 0.02),
+    "hangglider": ("hangglider4", [0.0, 1.0e3, 13.23, -1.288], [0.5, 0.5], (0.0, 100.0), [(2, 0.2, 1.2)], 20, [], 1, 0.01),
+}
+
+
+def bench_spec(name, n_intervals=4, rng=None):
+    """(spec, objective row, perturbation scale) of one of the BENCH_TABLE problems on `n_intervals` shooting intervals"""
+    model, u0, p0, tspan, ctr, n, quad, row, scale = BENCH_TABLE[name]
+    rng = np.random.default_rng(SEED0 + 100 + sorted(BENCH_TABLE).index(name)) if rng is None else rng
+    t = tspan[0] + (tspan[1] - tspan[0]) * np.arange(n) / n
+    spec = dict(model=model, u0=list(u0), p0=list(p0), tspan=tspan,
+                controls=[(ci, t, rng.uniform(lo, hi, n)) for ci, lo, hi in ctr],
+                control_bounds=[(lo, hi) for _, lo, hi in ctr], tunable_ic=[], quadrature_indices=list(quad),
+                shooting_points=[tspan[0] + (tspan[1] - tspan[0]) * k / n_intervals for k in range(n_intervals)])
+    return spec, row, scale

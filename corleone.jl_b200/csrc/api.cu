@@ -421,6 +421,25 @@ static int default_G(int model)
     case CB200_MODEL_LOTKA2_OED_DU: return 1;
     case CB200_MODEL_LIN1D_OED_CF: return 2;
     case CB200_MODEL_LIN1D_OED_DS: return 2;
+    case CB200_MODEL_BRYSONDENHAM3: return 2;
+    case CB200_MODEL_CATALYSTMIXING2: return 2;
+    case CB200_MODEL_CUSHIONED3: return 2;
+    case CB200_MODEL_DENBIGH3: return 2;
+    case CB200_MODEL_DIELECTROPHORETIC3: return 2;
+    case CB200_MODEL_ELECTRICCAR4: return 2;
+    case CB200_MODEL_FULLER3: return 2;
+    case CB200_MODEL_JACKSON3: return 2;
+    case CB200_MODEL_MOUNTAINCAR3: return 2;
+    case CB200_MODEL_PARTICLESTEERING5: return 1;
+    case CB200_MODEL_RAOMEASE2: return 2;
+    case CB200_MODEL_ROBBINS4: return 2;
+    case CB200_MODEL_MOONLANDING3: return 2;
+    case CB200_MODEL_LOTKASHARED4: return 2;
+    case CB200_MODEL_HANGINGCHAIN3: return 2;
+    case CB200_MODEL_TUBULARREACTOR2: return 2;
+    case CB200_MODEL_OCEAN4: return 2;
+    case CB200_MODEL_DUCTEDFAN7: return 1;
+    case CB200_MODEL_HANGGLIDER4: return 2;
     default: return 0;
     }
 }
@@ -452,6 +471,25 @@ static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
     case CB200_MODEL_LOTKA2_OED_DU: *nx = 6; *np = 3; d = 6; break;
     case CB200_MODEL_LIN1D_OED_CF: *nx = 3; *np = 2; d = 2; break;
     case CB200_MODEL_LIN1D_OED_DS: *nx = 2; *np = 2; d = 2; break;
+    case CB200_MODEL_BRYSONDENHAM3: *nx = 3; *np = 1; d = 2; break;
+    case CB200_MODEL_CATALYSTMIXING2: *nx = 2; *np = 1; d = 2; break;
+    case CB200_MODEL_CUSHIONED3: *nx = 3; *np = 2; d = 2; break;
+    case CB200_MODEL_DENBIGH3: *nx = 3; *np = 1; d = 2; break;
+    case CB200_MODEL_DIELECTROPHORETIC3: *nx = 3; *np = 2; d = 2; break;
+    case CB200_MODEL_ELECTRICCAR4: *nx = 4; *np = 1; d = 2; break;
+    case CB200_MODEL_FULLER3: *nx = 3; *np = 1; d = 2; break;
+    case CB200_MODEL_JACKSON3: *nx = 3; *np = 1; d = 2; break;
+    case CB200_MODEL_MOUNTAINCAR3: *nx = 3; *np = 2; d = 2; break;
+    case CB200_MODEL_PARTICLESTEERING5: *nx = 5; *np = 2; d = 4; break;
+    case CB200_MODEL_RAOMEASE2: *nx = 2; *np = 1; d = 1; break;
+    case CB200_MODEL_ROBBINS4: *nx = 4; *np = 1; d = 3; break;
+    case CB200_MODEL_MOONLANDING3: *nx = 3; *np = 2; d = 3; break;
+    case CB200_MODEL_LOTKASHARED4: *nx = 4; *np = 1; d = 3; break;
+    case CB200_MODEL_HANGINGCHAIN3: *nx = 3; *np = 1; d = 1; break;
+    case CB200_MODEL_TUBULARREACTOR2: *nx = 2; *np = 1; d = 1; break;
+    case CB200_MODEL_OCEAN4: *nx = 4; *np = 2; d = 3; break;
+    case CB200_MODEL_DUCTEDFAN7: *nx = 7; *np = 3; d = 6; break;
+    case CB200_MODEL_HANGGLIDER4: *nx = 4; *np = 2; d = 4; break;
     default: return -1;
     }
     if (nxd) *nxd = d;
@@ -485,6 +523,25 @@ static int launch_model(int model, int G, int method, const DevLayer &L, const d
     case CB200_MODEL_LOTKA2_OED_DU: return launch_lotka2_oed_du(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_LIN1D_OED_CF: return launch_lin1d_oed_cf(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_LIN1D_OED_DS: return launch_lin1d_oed_ds(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_BRYSONDENHAM3: return launch_brysondenham3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_CATALYSTMIXING2: return launch_catalystmixing2(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_CUSHIONED3: return launch_cushioned3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DENBIGH3: return launch_denbigh3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DIELECTROPHORETIC3: return launch_dielectrophoretic3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_ELECTRICCAR4: return launch_electriccar4(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_FULLER3: return launch_fuller3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_JACKSON3: return launch_jackson3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_MOUNTAINCAR3: return launch_mountaincar3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_PARTICLESTEERING5: return launch_particlesteering5(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_RAOMEASE2: return launch_raomease2(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_ROBBINS4: return launch_robbins4(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_MOONLANDING3: return launch_moonlanding3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_LOTKASHARED4: return launch_lotkashared4(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_HANGINGCHAIN3: return launch_hangingchain3(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_TUBULARREACTOR2: return launch_tubularreactor2(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_OCEAN4: return launch_ocean4(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DUCTEDFAN7: return launch_ductedfan7(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_HANGGLIDER4: return launch_hangglider4(G, method, L, ps, ldb, B, o, s);
     default: return -1000;
     }
 }
@@ -516,6 +573,25 @@ static int forward_model(int model, int method, const DevLayer &L, double *ps, l
     case CB200_MODEL_LOTKA2_OED_DU: return forward_lotka2_oed_du(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_LIN1D_OED_CF: return forward_lin1d_oed_cf(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_LIN1D_OED_DS: return forward_lin1d_oed_ds(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_BRYSONDENHAM3: return forward_brysondenham3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_CATALYSTMIXING2: return forward_catalystmixing2(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_CUSHIONED3: return forward_cushioned3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DENBIGH3: return forward_denbigh3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DIELECTROPHORETIC3: return forward_dielectrophoretic3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_ELECTRICCAR4: return forward_electriccar4(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_FULLER3: return forward_fuller3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_JACKSON3: return forward_jackson3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_MOUNTAINCAR3: return forward_mountaincar3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_PARTICLESTEERING5: return forward_particlesteering5(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_RAOMEASE2: return forward_raomease2(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_ROBBINS4: return forward_robbins4(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_MOONLANDING3: return forward_moonlanding3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_LOTKASHARED4: return forward_lotkashared4(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_HANGINGCHAIN3: return forward_hangingchain3(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_TUBULARREACTOR2: return forward_tubularreactor2(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_OCEAN4: return forward_ocean4(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DUCTEDFAN7: return forward_ductedfan7(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_HANGGLIDER4: return forward_hangglider4(method, L, ps, ldb, B, fixed, s);
     default: return -1000;
     }
 }

@@ -170,6 +170,82 @@ int launch_lin1d_oed_ds(int G, int method, const DevLayer &L, const double *ps, 
         const ShootOut &o, cudaStream_t s);
 int forward_lin1d_oed_ds(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s);
+int launch_brysondenham3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_brysondenham3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_catalystmixing2(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_catalystmixing2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_cushioned3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_cushioned3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_denbigh3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_denbigh3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_dielectrophoretic3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_dielectrophoretic3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_electriccar4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_electriccar4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_fuller3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_fuller3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_jackson3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_jackson3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_mountaincar3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_mountaincar3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_particlesteering5(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_particlesteering5(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_raomease2(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_raomease2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_robbins4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_robbins4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_moonlanding3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_moonlanding3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_lotkashared4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_lotkashared4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_hangingchain3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_hangingchain3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_tubularreactor2(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_tubularreactor2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_ocean4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_ocean4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_ductedfan7(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_ductedfan7(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
+int launch_hangglider4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s);
+int forward_hangglider4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
 
 }  // namespace cb200

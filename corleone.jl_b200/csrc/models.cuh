@@ -573,4 +573,282 @@ struct DoubleOscRhs {
 };
 using DoubleOsc6 = AutoJvp<DoubleOscRhs>;
 
+// lib/OptimalControlBenchmarks/src/problems/bryson_denham.jl:9-36; states (x, v, cost), p = (w)
+struct BrysonDenhamRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = x[1];
+        dx[1] = p[0];
+        dx[2] = p[0] * p[0];
+    }
+};
+using BrysonDenham3 = AutoJvp<BrysonDenhamRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/catalyst_mixing.jl:9-22; states (x1, x2), p = (w)
+struct CatalystMixingRhs {
+    static constexpr int NX = 2, NXD = 2, NQ = 0, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const T a = 10.0 * x[1] - x[0];
+        dx[0] = p[0] * a;
+        dx[1] = p[0] * (x[0] - 10.0 * x[1]) - (1.0 - p[0]) * x[1];
+    }
+};
+using CatalystMixing2 = AutoJvp<CatalystMixingRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/cushioned_oscillation.jl:9-37; states (x, v, obj), p = (t_s, u)
+struct CushionedRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double m = 5.0, c = 10.0;
+        dx[0] = p[0] * x[1];
+        dx[1] = p[0] * ((1.0 / m) * (p[1] - c * x[0]));
+        dx[2] = p[0];
+    }
+};
+using Cushioned3 = AutoJvp<CushionedRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/denbigh.jl:9-37; states (x1, x2, x3), p = (T); the second equation is `k1 x1 - k3 + k4 x2` as the reference writes it
+struct DenbighRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const T e1 = exp(-3.0e3 / p[0]), e2 = exp(-6.0e3 / p[0]);
+        const T k1 = 1.0e3 * e1, k2 = 1.0e7 * e2, k3 = 1.0e1 * e1;
+        dx[0] = -(k1 * x[0]) - k2 * x[0];
+        dx[1] = k1 * x[0] - k3 + 1.0e-3 * x[1];
+        dx[2] = k3 * x[1];
+    }
+};
+using Denbigh3 = AutoJvp<DenbighRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/dielectrophoretic_particle.jl:9-34; states (x0, x1, obj), p = (t_s, u)
+struct DielectrophoreticRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = p[0] * (x[1] * p[1] + (-0.75) * (p[1] * p[1]));
+        dx[1] = p[0] * (p[1] - x[1]);
+        dx[2] = p[0];
+    }
+};
+using Dielectrophoretic3 = AutoJvp<DielectrophoreticRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/electric_car.jl:9-62; states (x1, x2, x3, cost), p = (u)
+struct ElectricCarRhs {
+    static constexpr int NX = 4, NXD = 2, NQ = 2, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double Kr = 10.0, rho = 1.293, Cx = 0.4, S = 2.0, r = 0.33, Kf = 0.03, Km = 0.27, Rm = 0.03, Lm = 0.05,
+                     M = 250.0, g = 9.81, V = 150.0, Rb = 0.05;
+        dx[0] = (V * p[0] - Rm * x[0] - Km * x[1]) / Lm;
+        dx[1] = (Km * x[0] - (r / Kr) * (M * g * Kf + (0.5 * rho * S * Cx * r * r / (Kr * Kr)) * (x[1] * x[1]))) * (Kr * Kr / (M * r * r));
+        dx[2] = (r / Kr) * x[1];
+        dx[3] = V * p[0] * x[0] + Rb * (x[0] * x[0]);
+    }
+};
+using ElectricCar4 = AutoJvp<ElectricCarRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/fuller.jl:9-32; states (x0, x1, cost), p = (u)
+struct FullerRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = x[1];
+        dx[1] = 1.0 - 2.0 * p[0];
+        dx[2] = x[0] * x[0];
+    }
+};
+using Fuller3 = AutoJvp<FullerRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/jackson.jl:9-50; states (x1, x2, x3), p = (u)
+struct JacksonRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const T a = 1.0 * x[0] - 10.0 * x[1];
+        const T b = (1.0 - p[0]) * (1.0 * x[1]);
+        dx[0] = -(p[0] * a);
+        dx[1] = p[0] * a - b;
+        dx[2] = b;
+    }
+};
+using Jackson3 = AutoJvp<JacksonRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/mountain_car.jl:9-31; states (x, v, obj), p = (t_s, u)
+struct MountainCarRhs {
+    static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = p[0] * x[1];
+        dx[1] = p[0] * (1.0e-3 * p[1] - 2.5e-3 * cos(3.0 * x[0]));
+        dx[2] = p[0];
+    }
+};
+using MountainCar3 = AutoJvp<MountainCarRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/particle_steering.jl:9-42; states (x1, x2, dx1, dx2, obj), p = (t_s, u)
+struct ParticleSteeringRhs {
+    static constexpr int NX = 5, NXD = 4, NQ = 1, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = p[0] * x[2];
+        dx[1] = p[0] * x[3];
+        dx[2] = p[0] * (100.0 * cos(p[1]));
+        dx[3] = p[0] * (100.0 * sin(p[1]));
+        dx[4] = p[0];
+    }
+};
+using ParticleSteering5 = AutoJvp<ParticleSteeringRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/rao_mease.jl:9-26; states (x, cost), p = (u)
+struct RaoMeaseRhs {
+    static constexpr int NX = 2, NXD = 1, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = -(x[0] * x[0] * x[0]) + p[0];
+        dx[1] = x[0] * x[0] + p[0] * p[0];
+    }
+};
+using RaoMease2 = AutoJvp<RaoMeaseRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/robbins.jl:9-44; states (x1, x2, x3, cost), p = (u); alpha = 3, beta = 0, gamma = 0.5
+struct RobbinsRhs {
+    static constexpr int NX = 4, NXD = 3, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = x[1];
+        dx[1] = x[2];
+        dx[2] = p[0];
+        dx[3] = 3.0 * x[0] + 0.0 * (x[0] * x[0]) + 0.5 * (p[0] * p[0]);
+    }
+};
+using Robbins4 = AutoJvp<RobbinsRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/moon_landing.jl:9-31; states (h, v, m), p = (t_s, T)
+struct MoonLandingRhs {
+    static constexpr int NX = 3, NXD = 3, NQ = 0, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = p[0] * x[1];
+        dx[1] = p[0] * (-1.0 + p[1] / x[2]);
+        dx[2] = p[0] * (-(p[1] / 2.349));
+    }
+};
+using MoonLanding3 = AutoJvp<MoonLandingRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/lotka_shared.jl:9-32; states (x0, x1, x2, cost), p = (u)
+struct LotkaSharedRhs {
+    static constexpr int NX = 4, NXD = 3, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = x[0] - x[0] * x[1] - x[0] * x[2];
+        dx[1] = -x[1] + x[0] * x[1] - 0.1 * x[1] * p[0];
+        dx[2] = -x[2] + 1.2 * x[0] * x[2] - 0.4 * x[2] * p[0];
+        dx[3] = (x[0] - 1.5) * (x[0] - 1.5) + (x[1] - 1.0) * (x[1] - 1.0) + (x[2] - 1.0) * (x[2] - 1.0);
+    }
+};
+using LotkaShared4 = AutoJvp<LotkaSharedRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/hanging_chain.jl:9-48; states (x1, x2, x3), p = (u)
+struct HangingChainRhs {
+    static constexpr int NX = 3, NXD = 1, NQ = 2, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const T s = sqrt(1.0 + p[0] * p[0]);
+        dx[0] = p[0];
+        dx[1] = x[0] * s;
+        dx[2] = s;
+    }
+};
+using HangingChain3 = AutoJvp<HangingChainRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/tubular_reactor.jl:9-22; states (x1, x2), p = (u)
+struct TubularReactorRhs {
+    static constexpr int NX = 2, NXD = 1, NQ = 1, NP = 1;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        dx[0] = -((p[0] + 0.5 * (p[0] * p[0])) * x[0]);
+        dx[1] = p[0] * x[0];
+    }
+};
+using TubularReactor2 = AutoJvp<TubularReactorRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/ocean.jl:9-64; states (S, R, tau, cost), p = (u1, u2); time rides along as a state (tau' = 1) for the discount factor
+struct OceanRhs {
+    static constexpr int NX = 4, NXD = 3, NQ = 1, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const T Dl = 3.5e4 - x[1] - x[0];
+        dx[0] = -p[0];
+        dx[1] = p[0] - p[1] - 1.0e-3 * (x[0] - 0.1 * Dl);
+        dx[2] = 1.0 + 0.0 * x[2];
+        const T U = 50.0 * p[0] - 0.5 * (p[0] * p[0]), A = 2.0 * p[1] + 2.0 * (p[1] * p[1]), C = 50.0 - 4.0e-3 * x[1];
+        const T q = 0.3 * x[0] - 6.0e2;
+        dx[3] = -(exp(-3.0e-2 * x[2]) * (U - A - p[0] * C - q * q));
+    }
+};
+using Ocean4 = AutoJvp<OceanRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/ducted_fan.jl:9-61; states (x1, v1, x2, v2, alpha, valpha, cost), p = (t_s, u1, u2)
+struct DuctedFanRhs {
+    static constexpr int NX = 7, NXD = 6, NQ = 1, NP = 3;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double m = 2.2, J = 0.05, r = 0.2, mg = 4.0, mu = 1.0;
+        const T s = sin(x[4]), c = cos(x[4]);
+        dx[0] = p[0] * x[1];
+        dx[1] = p[0] * ((1.0 / m) * (p[1] * c - p[2] * s));
+        dx[2] = p[0] * x[3];
+        dx[3] = p[0] * ((1.0 / m) * (-mg + p[1] * s + p[2] * c));
+        dx[4] = p[0] * x[5];
+        dx[5] = p[0] * ((r / J) * p[1]);
+        dx[6] = (2.0 * (p[1] * p[1]) + p[2] * p[2]) + mu * p[0];
+    }
+};
+using DuctedFan7 = AutoJvp<DuctedFanRhs>;
+
+// lib/OptimalControlBenchmarks/src/problems/hang_glider.jl:9-66; states (x, y, vx, vy), p = (T, cL)
+struct HangGliderRhs {
+    static constexpr int NX = 4, NXD = 4, NQ = 0, NP = 2;
+    template <class T>
+    CB_DEV void rhs(const T *x, const T *p, T *dx)
+    {
+        const double uc = 2.5, rc = 100.0, c0 = 0.034, c1 = 0.069662, S = 14.0, rho = 1.13, m = 100.0, g = 9.81;
+        const T rr = x[0] / rc - 2.5;
+        const T r = rr * rr;
+        const T Uup = uc * (1.0 - r) * exp(-r);
+        const T w = x[3] - Uup;
+        const T v2 = x[2] * x[2] + w * w;
+        const T v = sqrt(v2);
+        const T Dr = (0.5 * rho * S) * (c0 + c1 * (p[1] * p[1])) * v2;
+        const T L = (0.5 * rho * S) * p[1] * v2;
+        dx[0] = p[0] * x[2];
+        dx[1] = p[0] * x[3];
+        dx[2] = (p[0] * (-1.0)) * (L * w + Dr * x[2]) / (m * v);
+        dx[3] = p[0] * ((L * x[2] - Dr * w) / (m * v) - g);
+    }
+};
+using HangGlider4 = AutoJvp<HangGliderRhs>;
+
 }  // namespace cb200

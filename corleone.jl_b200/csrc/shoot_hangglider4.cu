@@ -1,0 +1,20 @@
+// Instantiations of the shooting kernel for model HangGlider4 (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_hangglider4(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(HangGlider4, 0, 1)
+        CB200_DISPATCH_G(HangGlider4, 2, 1)
+    default:
+        return -1000;
+    }
+}
+int forward_hangglider4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<HangGlider4>(method, L, ps, ldb, B, fixed, s);
+}
+}  // namespace cb200

@@ -1,0 +1,20 @@
+// Instantiations of the shooting kernel for model MoonLanding3 (see shoot.cuh).
+#include "models.cuh"
+#include "shoot.cuh"
+namespace cb200 {
+int launch_moonlanding3(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
+        const ShootOut &o, cudaStream_t s)
+{
+    switch (G) {
+        CB200_DISPATCH_G(MoonLanding3, 0, 1)
+        CB200_DISPATCH_G(MoonLanding3, 2, 1)
+    default:
+        return -1000;
+    }
+}
+int forward_moonlanding3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
+        cudaStream_t s)
+{
+    return launch_forward<MoonLanding3>(method, L, ps, ldb, B, fixed, s);
+}
+}  // namespace cb200

@@ -36,6 +36,25 @@ MODEL_REGISTRY = {
     "lotka2_oed_du": (20, 6, 3),
     "lin1d_oed_cf": (21, 3, 2),
     "lin1d_oed_ds": (22, 2, 2),
+    "brysondenham3": (23, 3, 1),
+    "catalystmixing2": (24, 2, 1),
+    "cushioned3": (25, 3, 2),
+    "denbigh3": (26, 3, 1),
+    "dielectrophoretic3": (27, 3, 2),
+    "electriccar4": (28, 4, 1),
+    "fuller3": (29, 3, 1),
+    "jackson3": (30, 3, 1),
+    "mountaincar3": (31, 3, 2),
+    "particlesteering5": (32, 5, 2),
+    "raomease2": (33, 2, 1),
+    "robbins4": (34, 4, 1),
+    "moonlanding3": (35, 3, 2),
+    "lotkashared4": (36, 4, 1),
+    "hangingchain3": (37, 3, 1),
+    "tubularreactor2": (38, 2, 1),
+    "ocean4": (39, 4, 2),
+    "ductedfan7": (40, 7, 3),
+    "hangglider4": (41, 4, 2),
 }
 
 # base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)

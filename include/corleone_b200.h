@@ -74,7 +74,27 @@ typedef enum {
     CB200_MODEL_LOTKA2_OED_DS = 19, /* DiscreteSampled (:171-203): [x; G], p = (base p; w); information summed over samples */
     CB200_MODEL_LOTKA2_OED_DU = 20, /* Discrete, no measurements (:171-203): [x; G], p = base p */
     CB200_MODEL_LIN1D_OED_CF = 21,
-    CB200_MODEL_LIN1D_OED_DS = 22
+    CB200_MODEL_LIN1D_OED_DS = 22,
+    /* the rest of lib/OptimalControlBenchmarks/src/problems (Lagrange terms and free-time clocks as last states) */
+    CB200_MODEL_BRYSONDENHAM3 = 23,   /* bryson_denham.jl:9-36; states (x, v, cost), p = (w) */
+    CB200_MODEL_CATALYSTMIXING2 = 24,   /* catalyst_mixing.jl:9-22; states (x1, x2), p = (w) */
+    CB200_MODEL_CUSHIONED3 = 25,   /* cushioned_oscillation.jl:9-37; states (x, v, obj), p = (t_s, u) */
+    CB200_MODEL_DENBIGH3 = 26,   /* denbigh.jl:9-37; states (x1, x2, x3), p = (T) */
+    CB200_MODEL_DIELECTROPHORETIC3 = 27,   /* dielectrophoretic_particle.jl:9-34; states (x0, x1, obj), p = (t_s, u) */
+    CB200_MODEL_ELECTRICCAR4 = 28,   /* electric_car.jl:9-62; states (x1, x2, x3, cost), p = (u) */
+    CB200_MODEL_FULLER3 = 29,   /* fuller.jl:9-32; states (x0, x1, cost), p = (u) */
+    CB200_MODEL_JACKSON3 = 30,   /* jackson.jl:9-50; states (x1, x2, x3), p = (u) */
+    CB200_MODEL_MOUNTAINCAR3 = 31,   /* mountain_car.jl:9-31; states (x, v, obj), p = (t_s, u) */
+    CB200_MODEL_PARTICLESTEERING5 = 32,   /* particle_steering.jl:9-42; states (x1, x2, dx1, dx2, obj), p = (t_s, u) */
+    CB200_MODEL_RAOMEASE2 = 33,   /* rao_mease.jl:9-26; states (x, cost), p = (u) */
+    CB200_MODEL_ROBBINS4 = 34,   /* robbins.jl:9-44; states (x1, x2, x3, cost), p = (u) */
+    CB200_MODEL_MOONLANDING3 = 35,   /* moon_landing.jl:9-31; states (h, v, m), p = (t_s, T) */
+    CB200_MODEL_LOTKASHARED4 = 36,   /* lotka_shared.jl:9-32; states (x0, x1, x2, cost), p = (u) */
+    CB200_MODEL_HANGINGCHAIN3 = 37,   /* hanging_chain.jl:9-48; states (x1, x2, x3), p = (u) */
+    CB200_MODEL_TUBULARREACTOR2 = 38,   /* tubular_reactor.jl:9-22; states (x1, x2), p = (u) */
+    CB200_MODEL_OCEAN4 = 39,   /* ocean.jl:9-64; states (S, R, tau, cost), p = (u1, u2) */
+    CB200_MODEL_DUCTEDFAN7 = 40,   /* ducted_fan.jl:9-61; states (x1, v1, x2, v2, alpha, valpha, cost), p = (t_s, u1, u2) */
+    CB200_MODEL_HANGGLIDER4 = 41   /* hang_glider.jl:9-66; states (x, y, vx, vy), p = (T, cL) */
 } cb200_model;
 
 typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;

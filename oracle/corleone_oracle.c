@@ -315,6 +315,176 @@ static void rhs_doubleosc6(const dual *x, const dual *p, dual *du)
     du[5] = dscale(dadd(dadd(dmul(x[0], x[0]), dmul(x[1], x[1])), dmul(p[0], p[0])), 0.5);
 }
 
+/* lib/OptimalControlBenchmarks/src/problems/bryson_denham.jl:9-36; states (x, v, cost), p = (w) */
+static void rhs_brysondenham3(const dual *x, const dual *p, dual *du)
+{
+    du[0] = x[1];
+    du[1] = p[0];
+    du[2] = dmul(p[0], p[0]);
+}
+/* lib/OptimalControlBenchmarks/src/problems/catalyst_mixing.jl:9-22; states (x1, x2), p = (w) */
+static void rhs_catalystmixing2(const dual *x, const dual *p, dual *du)
+{
+    dual a = dsub(dscale(x[1], 10.0), x[0]);
+    du[0] = dmul(p[0], a);
+    du[1] = dsub(dmul(p[0], dsub(x[0], dscale(x[1], 10.0))), dmul(dsub(dconst(1.0), p[0]), x[1]));
+}
+/* lib/OptimalControlBenchmarks/src/problems/cushioned_oscillation.jl:9-37; states (x, v, obj), p = (t_s, u) */
+static void rhs_cushioned3(const dual *x, const dual *p, dual *du)
+{
+    const double m = 5.0, c = 10.0;
+    du[0] = dmul(p[0], x[1]);
+    du[1] = dmul(p[0], dscale(dsub(p[1], dscale(x[0], c)), 1.0 / m));
+    du[2] = p[0];
+}
+/* lib/OptimalControlBenchmarks/src/problems/denbigh.jl:9-37; states (x1, x2, x3), p = (T); the second equation is `k1 x1 - k3 + k4 x2` as the reference writes it */
+static void rhs_denbigh3(const dual *x, const dual *p, dual *du)
+{
+    dual e1 = dexp(ddiv(dconst(-3.0e3), p[0])), e2 = dexp(ddiv(dconst(-6.0e3), p[0]));
+    dual k1 = dscale(e1, 1.0e3), k2 = dscale(e2, 1.0e7), k3 = dscale(e1, 1.0e1);
+    du[0] = dsub(dneg(dmul(k1, x[0])), dmul(k2, x[0]));
+    du[1] = dadd(dsub(dmul(k1, x[0]), k3), dscale(x[1], 1.0e-3));
+    du[2] = dmul(k3, x[1]);
+}
+/* lib/OptimalControlBenchmarks/src/problems/dielectrophoretic_particle.jl:9-34; states (x0, x1, obj), p = (t_s, u) */
+static void rhs_dielectrophoretic3(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dmul(p[0], dadd(dmul(x[1], p[1]), dscale(dmul(p[1], p[1]), -0.75)));
+    du[1] = dmul(p[0], dsub(p[1], x[1]));
+    du[2] = p[0];
+}
+/* lib/OptimalControlBenchmarks/src/problems/electric_car.jl:9-62; states (x1, x2, x3, cost), p = (u) */
+static void rhs_electriccar4(const dual *x, const dual *p, dual *du)
+{
+    const double Kr = 10.0, rho = 1.293, Cx = 0.4, S = 2.0, r = 0.33, Kf = 0.03, Km = 0.27, Rm = 0.03, Lm = 0.05,
+                 M = 250.0, g = 9.81, V = 150.0, Rb = 0.05;
+    du[0] = dscale(dsub(dsub(dscale(p[0], V), dscale(x[0], Rm)), dscale(x[1], Km)), 1.0 / Lm);
+    dual drag = daddc(dscale(dmul(x[1], x[1]), 0.5 * rho * S * Cx * r * r / (Kr * Kr)), M * g * Kf);
+    du[1] = dscale(dsub(dscale(x[0], Km), dscale(drag, r / Kr)), Kr * Kr / (M * r * r));
+    du[2] = dscale(x[1], r / Kr);
+    du[3] = dadd(dmul(dscale(p[0], V), x[0]), dscale(dmul(x[0], x[0]), Rb));
+}
+/* lib/OptimalControlBenchmarks/src/problems/fuller.jl:9-32; states (x0, x1, cost), p = (u) */
+static void rhs_fuller3(const dual *x, const dual *p, dual *du)
+{
+    du[0] = x[1];
+    du[1] = dsub(dconst(1.0), dscale(p[0], 2.0));
+    du[2] = dmul(x[0], x[0]);
+}
+/* lib/OptimalControlBenchmarks/src/problems/jackson.jl:9-50; states (x1, x2, x3), p = (u) */
+static void rhs_jackson3(const dual *x, const dual *p, dual *du)
+{
+    dual a = dsub(x[0], dscale(x[1], 10.0));
+    dual b = dmul(dsub(dconst(1.0), p[0]), x[1]);
+    du[0] = dneg(dmul(p[0], a));
+    du[1] = dsub(dmul(p[0], a), b);
+    du[2] = b;
+}
+/* lib/OptimalControlBenchmarks/src/problems/mountain_car.jl:9-31; states (x, v, obj), p = (t_s, u) */
+static void rhs_mountaincar3(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dmul(p[0], x[1]);
+    du[1] = dmul(p[0], dsub(dscale(p[1], 1.0e-3), dscale(dcos(dscale(x[0], 3.0)), 2.5e-3)));
+    du[2] = p[0];
+}
+/* lib/OptimalControlBenchmarks/src/problems/particle_steering.jl:9-42; states (x1, x2, dx1, dx2, obj), p = (t_s, u) */
+static void rhs_particlesteering5(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dmul(p[0], x[2]);
+    du[1] = dmul(p[0], x[3]);
+    du[2] = dmul(p[0], dscale(dcos(p[1]), 100.0));
+    du[3] = dmul(p[0], dscale(dsin(p[1]), 100.0));
+    du[4] = p[0];
+}
+/* lib/OptimalControlBenchmarks/src/problems/rao_mease.jl:9-26; states (x, cost), p = (u) */
+static void rhs_raomease2(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dadd(dneg(dmul(dmul(x[0], x[0]), x[0])), p[0]);
+    du[1] = dadd(dmul(x[0], x[0]), dmul(p[0], p[0]));
+}
+/* lib/OptimalControlBenchmarks/src/problems/robbins.jl:9-44; states (x1, x2, x3, cost), p = (u); alpha = 3, beta = 0, gamma = 0.5 */
+static void rhs_robbins4(const dual *x, const dual *p, dual *du)
+{
+    du[0] = x[1];
+    du[1] = x[2];
+    du[2] = p[0];
+    du[3] = dadd(dadd(dscale(x[0], 3.0), dscale(dmul(x[0], x[0]), 0.0)), dscale(dmul(p[0], p[0]), 0.5));
+}
+/* lib/OptimalControlBenchmarks/src/problems/moon_landing.jl:9-31; states (h, v, m), p = (t_s, T) */
+static void rhs_moonlanding3(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dmul(p[0], x[1]);
+    du[1] = dmul(p[0], daddc(ddiv(p[1], x[2]), -1.0));
+    du[2] = dmul(p[0], dneg(dscale(p[1], 1.0 / 2.349)));
+}
+/* lib/OptimalControlBenchmarks/src/problems/lotka_shared.jl:9-32; states (x0, x1, x2, cost), p = (u) */
+static void rhs_lotkashared4(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dsub(dsub(x[0], dmul(x[0], x[1])), dmul(x[0], x[2]));
+    du[1] = dsub(dadd(dneg(x[1]), dmul(x[0], x[1])), dmul(dscale(x[1], 0.1), p[0]));
+    du[2] = dsub(dadd(dneg(x[2]), dmul(dscale(x[0], 1.2), x[2])), dmul(dscale(x[2], 0.4), p[0]));
+    dual a = daddc(x[0], -1.5), b = daddc(x[1], -1.0), c = daddc(x[2], -1.0);
+    du[3] = dadd(dadd(dmul(a, a), dmul(b, b)), dmul(c, c));
+}
+/* lib/OptimalControlBenchmarks/src/problems/hanging_chain.jl:9-48; states (x1, x2, x3), p = (u) */
+static void rhs_hangingchain3(const dual *x, const dual *p, dual *du)
+{
+    dual s = dsqrt(daddc(dmul(p[0], p[0]), 1.0));
+    du[0] = p[0];
+    du[1] = dmul(x[0], s);
+    du[2] = s;
+}
+/* lib/OptimalControlBenchmarks/src/problems/tubular_reactor.jl:9-22; states (x1, x2), p = (u) */
+static void rhs_tubularreactor2(const dual *x, const dual *p, dual *du)
+{
+    du[0] = dneg(dmul(dadd(p[0], dscale(dmul(p[0], p[0]), 0.5)), x[0]));
+    du[1] = dmul(p[0], x[0]);
+}
+/* lib/OptimalControlBenchmarks/src/problems/ocean.jl:9-64; states (S, R, tau, cost), p = (u1, u2); time rides along as a state (tau' = 1) for the discount factor */
+static void rhs_ocean4(const dual *x, const dual *p, dual *du)
+{
+    dual Dl = dsub(dsub(dconst(3.5e4), x[1]), x[0]);
+    du[0] = dneg(p[0]);
+    du[1] = dsub(dsub(p[0], p[1]), dscale(dsub(x[0], dscale(Dl, 0.1)), 1.0e-3));
+    du[2] = dconst(1.0);
+    dual U = dsub(dscale(p[0], 50.0), dscale(dmul(p[0], p[0]), 0.5));
+    dual A = dadd(dscale(p[1], 2.0), dscale(dmul(p[1], p[1]), 2.0));
+    dual C = dsub(dconst(50.0), dscale(x[1], 4.0e-3));
+    dual q = daddc(dscale(x[0], 0.3), -6.0e2);
+    du[3] = dneg(dmul(dexp(dscale(x[2], -3.0e-2)), dsub(dsub(dsub(U, A), dmul(p[0], C)), dmul(q, q))));
+}
+/* lib/OptimalControlBenchmarks/src/problems/ducted_fan.jl:9-61; states (x1, v1, x2, v2, alpha, valpha, cost), p = (t_s, u1, u2) */
+static void rhs_ductedfan7(const dual *x, const dual *p, dual *du)
+{
+    const double m = 2.2, J = 0.05, r = 0.2, mg = 4.0, mu = 1.0;
+    dual s = dsin(x[4]), c = dcos(x[4]);
+    du[0] = dmul(p[0], x[1]);
+    du[1] = dmul(p[0], dscale(dsub(dmul(p[1], c), dmul(p[2], s)), 1.0 / m));
+    du[2] = dmul(p[0], x[3]);
+    du[3] = dmul(p[0], dscale(dadd(daddc(dmul(p[1], s), -mg), dmul(p[2], c)), 1.0 / m));
+    du[4] = dmul(p[0], x[5]);
+    du[5] = dmul(p[0], dscale(p[1], r / J));
+    du[6] = dadd(dadd(dscale(dmul(p[1], p[1]), 2.0), dmul(p[2], p[2])), dscale(p[0], mu));
+}
+/* lib/OptimalControlBenchmarks/src/problems/hang_glider.jl:9-66; states (x, y, vx, vy), p = (T, cL) */
+static void rhs_hangglider4(const dual *x, const dual *p, dual *du)
+{
+    const double uc = 2.5, rc = 100.0, c0 = 0.034, c1 = 0.069662, S = 14.0, rho = 1.13, m = 100.0, g = 9.81;
+    dual rr = daddc(dscale(x[0], 1.0 / rc), -2.5);
+    dual r = dmul(rr, rr);
+    dual Uup = dmul(dscale(dsub(dconst(1.0), r), uc), dexp(dneg(r)));
+    dual w = dsub(x[3], Uup);
+    dual v2 = dadd(dmul(x[2], x[2]), dmul(w, w));
+    dual v = dsqrt(v2);
+    dual Dr = dmul(dscale(daddc(dscale(dmul(p[1], p[1]), c1), c0), 0.5 * rho * S), v2);
+    dual L = dmul(dscale(p[1], 0.5 * rho * S), v2);
+    dual mv = dscale(v, m);
+    du[0] = dmul(p[0], x[2]);
+    du[1] = dmul(p[0], x[3]);
+    du[2] = ddiv(dmul(dneg(p[0]), dadd(dmul(L, w), dmul(Dr, x[2]))), mv);
+    du[3] = dmul(p[0], daddc(ddiv(dsub(dmul(L, x[2]), dmul(Dr, w)), mv), -g));
+}
+
 typedef void (*rhs_fn)(const dual *, const dual *, dual *);
 typedef void (*jac_fn)(const dual *, const dual *, dual *, dual *);
 /* variants of the augmentation (augmentation.jl): which F states exist and what they integrate */
@@ -387,6 +557,25 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_LOTKA2_OED_DU: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, AUG_D, u, p, du); break;
     case CO_LIN1D_OED_CF: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, AUG_CF, u, p, du); break;
     case CO_LIN1D_OED_DS: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, AUG_D, u, p, du); break;
+    case CO_BRYSONDENHAM3: rhs_brysondenham3(u, p, du); break;
+    case CO_CATALYSTMIXING2: rhs_catalystmixing2(u, p, du); break;
+    case CO_CUSHIONED3: rhs_cushioned3(u, p, du); break;
+    case CO_DENBIGH3: rhs_denbigh3(u, p, du); break;
+    case CO_DIELECTROPHORETIC3: rhs_dielectrophoretic3(u, p, du); break;
+    case CO_ELECTRICCAR4: rhs_electriccar4(u, p, du); break;
+    case CO_FULLER3: rhs_fuller3(u, p, du); break;
+    case CO_JACKSON3: rhs_jackson3(u, p, du); break;
+    case CO_MOUNTAINCAR3: rhs_mountaincar3(u, p, du); break;
+    case CO_PARTICLESTEERING5: rhs_particlesteering5(u, p, du); break;
+    case CO_RAOMEASE2: rhs_raomease2(u, p, du); break;
+    case CO_ROBBINS4: rhs_robbins4(u, p, du); break;
+    case CO_MOONLANDING3: rhs_moonlanding3(u, p, du); break;
+    case CO_LOTKASHARED4: rhs_lotkashared4(u, p, du); break;
+    case CO_HANGINGCHAIN3: rhs_hangingchain3(u, p, du); break;
+    case CO_TUBULARREACTOR2: rhs_tubularreactor2(u, p, du); break;
+    case CO_OCEAN4: rhs_ocean4(u, p, du); break;
+    case CO_DUCTEDFAN7: rhs_ductedfan7(u, p, du); break;
+    case CO_HANGGLIDER4: rhs_hangglider4(u, p, du); break;
     default: break;
     }
 }

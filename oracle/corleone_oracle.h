@@ -56,7 +56,27 @@ enum co_model {
     CO_LOTKA2_OED_DS = 19, /* DiscreteSampled (:171-203) */
     CO_LOTKA2_OED_DU = 20, /* Discrete (:171-203) */
     CO_LIN1D_OED_CF = 21,
-    CO_LIN1D_OED_DS = 22
+    CO_LIN1D_OED_DS = 22,
+    /* the rest of lib/OptimalControlBenchmarks/src/problems */
+    CO_BRYSONDENHAM3 = 23,
+    CO_CATALYSTMIXING2 = 24,
+    CO_CUSHIONED3 = 25,
+    CO_DENBIGH3 = 26,
+    CO_DIELECTROPHORETIC3 = 27,
+    CO_ELECTRICCAR4 = 28,
+    CO_FULLER3 = 29,
+    CO_JACKSON3 = 30,
+    CO_MOUNTAINCAR3 = 31,
+    CO_PARTICLESTEERING5 = 32,
+    CO_RAOMEASE2 = 33,
+    CO_ROBBINS4 = 34,
+    CO_MOONLANDING3 = 35,
+    CO_LOTKASHARED4 = 36,
+    CO_HANGINGCHAIN3 = 37,
+    CO_TUBULARREACTOR2 = 38,
+    CO_OCEAN4 = 39,
+    CO_DUCTEDFAN7 = 40,
+    CO_HANGGLIDER4 = 41
 };
 
 enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };

@@ -38,6 +38,25 @@ MODELS = {
     "lotka2_oed_du": 20,
     "lin1d_oed_cf": 21,
     "lin1d_oed_ds": 22,
+    "brysondenham3": 23,
+    "catalystmixing2": 24,
+    "cushioned3": 25,
+    "denbigh3": 26,
+    "dielectrophoretic3": 27,
+    "electriccar4": 28,
+    "fuller3": 29,
+    "jackson3": 30,
+    "mountaincar3": 31,
+    "particlesteering5": 32,
+    "raomease2": 33,
+    "robbins4": 34,
+    "moonlanding3": 35,
+    "lotkashared4": 36,
+    "hangingchain3": 37,
+    "tubularreactor2": 38,
+    "ocean4": 39,
+    "ductedfan7": 40,
+    "hangglider4": 41,
 }
 METHODS = {"tsit5": 0, "rk4": 1}
 CO_ND = 16

@@ -8,7 +8,7 @@ from corleone_b200.configs import (config1_lotka_ms24, config2_lqr, config3_lotk
                                    dense20_data, egerstedt_spec, layer_from_spec, lin1d_oed_spec,
                                    lotka_oed_spec, lotka_spec, native_from_spec, cartpole_spec, rocket_spec, vdp_spec,
                                    batchreactor_spec, quadrotor_spec, threetank_spec, doubleosc_spec,
-                                   f8_spec, lotkacomp_spec)
+                                   f8_spec, lotkacomp_spec, bench_spec, BENCH_TABLE)
 
 
 def lotka_ms24_spec(rng):

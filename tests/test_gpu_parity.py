@@ -395,6 +395,20 @@ def test_benchmark_suite_models_forward_mode_ad(name):
     assert_ok(full_compare(spec, cb.RK4(4), 3, rng, objective_row=row, ps=ps[:3]))
 
 
+@pytest.mark.parametrize("name", sorted(P.BENCH_TABLE))
+def test_benchmark_suite_remaining_problems(name):
+    """the rest of lib/OptimalControlBenchmarks/src/problems (every problem file has a compiled-in right-hand side):
+    states, defects, objective, sensitivities, gradient and constraint Jacobian against the oracle"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(61)
+    spec, row, scale = P.bench_spec(name, 3 if name == "ductedfan" else 4)
+    from oracle import pyoracle as po
+    O = po.OracleLayer(spec)
+    ps = O.default_ps()[None, :] * (1.0 + scale * rng.standard_normal((9, O.nvars))) + scale * rng.standard_normal((9, O.nvars))
+    assert_ok(full_compare(spec, cb.Tsit5(3), 9, rng, objective_row=row, ps=ps))
+    assert_ok(full_compare(spec, cb.RK4(4), 2, rng, objective_row=row, ps=ps[:2]))
+
+
 def test_every_memory_layout_of_cb200_eval_agrees():
     """host candidate-major (chunked, multi-stream; last chunk partial), host variable-major, device candidate-major
     and device variable-major calls give bit-identical results"""

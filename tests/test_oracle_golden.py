@@ -203,3 +203,25 @@ def test_fp64_oracle_vs_extended_precision_restatement():
     ref = np.array([float(v) for v in x])
     got = r["xend"][:, 0]
     assert np.max(np.abs(got - ref) / np.maximum(1.0, np.abs(ref))) <= 1e-13
+
+
+@pytest.mark.parametrize("name", sorted(__import__("problems").BENCH_TABLE))
+def test_benchmark_problem_derivatives_match_central_differences(name):
+    """every right-hand side of lib/OptimalControlBenchmarks restated in the oracle: the dual-number derivatives of the
+    last sample agree with central differences of the values (pins the hand-written tangent arithmetic)"""
+    import problems as P
+    from oracle import pyoracle as po
+    spec, row, scale = P.bench_spec(name, 3 if name == "ductedfan" else 4)
+    O = po.OracleLayer(spec)
+    rng = np.random.default_rng(1)
+    x = O.default_ps() * (1 + scale * rng.standard_normal(O.nvars)) + scale * rng.standard_normal(O.nvars)
+    r = O.eval(x, K=3)
+    assert np.isfinite(r["xend"]).all() and np.isfinite(r["defk"]).all()
+    _, _, Jl = O.jacobians(x, K=3)
+    for v in rng.choice(O.nvars, 4, replace=False):
+        h = 1e-6 * max(1.0, abs(x[v]))
+        xp, xm = x.copy(), x.copy()
+        xp[v] += h
+        xm[v] -= h
+        fd = (O.eval(xp, K=3)["last"] - O.eval(xm, K=3)["last"]) / (2 * h)
+        assert np.max(np.abs(fd - Jl[:, v])) <= 1e-6 * max(1.0, np.max(np.abs(Jl[:, v]))), (name, v)
