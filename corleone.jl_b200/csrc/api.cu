@@ -619,8 +619,18 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     if (d->nx != mnx || d->np_all != mnp)
         return fail(CB200_ERR_ARG, "model %d expects nx=%d, np=%d; got nx=%d, np=%d", d->model, mnx, mnp, d->nx,
                     d->np_all);
-    if (d->method != CB200_TSIT5 && d->method != CB200_RK4) return fail(CB200_ERR_UNSUPPORTED, "unknown method");
+    if (d->method != CB200_TSIT5 && d->method != CB200_RK4 && d->method != CB200_TSIT5_ADAPTIVE)
+        return fail(CB200_ERR_UNSUPPORTED, "unknown method");
     if (d->steps_per_piece < 1) return fail(CB200_ERR_ARG, "steps_per_piece must be >= 1");
+    if (d->method == CB200_TSIT5_ADAPTIVE) {
+        switch (d->model) {
+        case CB200_MODEL_LOTKA3: case CB200_MODEL_LOTKA2: case CB200_MODEL_LQR: case CB200_MODEL_LIN1D:
+        case CB200_MODEL_LOTKA2_OED: case CB200_MODEL_LIN1D_OED: break;
+        default:
+            return fail(CB200_ERR_UNSUPPORTED, "model %d has no adaptive-step kernel compiled in (CB200_DISPATCH_GA in its shoot_*.cu)", d->model);
+        }
+        if (!(d->abstol > 0.0) || !(d->reltol > 0.0)) return fail(CB200_ERR_ARG, "adaptive Tsit5 needs abstol > 0 and reltol > 0");
+    }
     if (d->n_intervals < 1) return fail(CB200_ERR_ARG, "n_intervals must be >= 1");
     if (d->n_controls < 0 || d->n_controls > MAX_CTRL) return fail(CB200_ERR_ARG, "n_controls out of range");
     if (d->np_all > MAX_NP) return fail(CB200_ERR_ARG, "np_all too large");
@@ -650,6 +660,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.i0 = 0;
     L.In = I;
     L.K = d->steps_per_piece;
+    L.abstol = d->abstol;
+    L.reltol = d->reltol;
     L.R = 1;
     h->G_sens = default_G(d->model);
     if (const char *env = getenv("CB200_DIRS_PER_THREAD")) {
@@ -1041,10 +1053,10 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         h_ref = ph[0];
     }
     for (int k = 0; k < 21; k++) L.hA[k] = 0.0;
-    if (d->method == CB200_TSIT5) {
-        tsit5_coeffs(h_ref, L.hA);
-    } else {
+    if (d->method == CB200_RK4) {
         rk4_coeffs(h_ref, L.hA);
+    } else {
+        tsit5_coeffs(h_ref, L.hA);
     }
     L.cidx = (const int *)(base + o_ci);
     L.var_off = (const int *)(base + o_vo);

@@ -19,6 +19,7 @@ struct DevLayer {
     int i0, In;              // intervals [i0, i0 + In) are integrated by this launch (cb200_set_interval_range); default 0, I
     int uniform_h;           // every piece of the layer has the same step size h = (t1 - t0)/K
     double hA[21];           // uniform_h: h * a_ij (Tsit5, slots as tsit5_coeffs) or the 4 RK4 factors
+    double abstol, reltol;   // method 2 (adaptive Tsit5): the problem's tolerances
     int pmap_kind[MAX_NP];   // p_full[q] = kind ? controls_j[idx] : ps.p[idx]   (A, B of single_shooting.jl:306-323)
     int pmap_idx[MAX_NP];
     int tunable_p0[MAX_NP];  // 0-based p index of tunable parameter m

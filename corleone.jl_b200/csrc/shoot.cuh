@@ -166,6 +166,159 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
     }
 }
 
+// ---- method 2: adaptive Tsit5, the reference's default mode (`solve(problem, Tsit5(); ...)` per control piece with the
+// problem's abstol / reltol, src/single_shooting.jl:443-453).  OrdinaryDiffEq's stepping restated from its published
+// algorithm (DESIGN.md section 3 has the long form and the pin on the reference's golden vectors): Hairer's initial-step
+// heuristic, embedded 4th-order error estimate in the RMS norm, PI controller with the Float32 `fastpow`, steps clipped
+// to the end of the piece; every piece starts over.  The step sequence is decided by the STATE components only; the
+// thread's sensitivity directions ride along on it (all direction groups of a unit therefore take identical steps).
+// Not a throughput path: the k's are kept (registers / local memory) and lanes of a warp may take different step counts.
+__device__ __forceinline__ float cb_fastlog2(float x)
+{
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    const unsigned ux = __float_as_uint(x);
+    const unsigned e = (ux & 0x7F800000u) >> 23;
+    const bool greater = (ux & 0x00400000u) != 0u;   // significand > 1.5
+    const float signif = __fsub_rn(__uint_as_float((ux & 0x007FFFFFu) | (greater ? 0x3f000000u : 0x3f800000u)), 1.0f);
+    const float fexp = __fsub_rn((float)e, greater ? 126.0f : 127.0f);
+    // no FMA contraction: Julia evaluates (a*s + b)*s/(s + c) with separate roundings
+    return __fadd_rn(fexp, __fdiv_rn(__fmul_rn(__fadd_rn(__fmul_rn(a, signif), b), signif), __fadd_rn(signif, c)));
+}
+__device__ __forceinline__ double cb_fastpow(double x, double y)
+{
+    return x == 0.0 ? 0.0 : (double)exp2f(__fmul_rn((float)y, cb_fastlog2((float)x)));
+}
+
+template <class Mdl, int G>
+__device__ __noinline__ void integrate_piece_adaptive(double *yd, double *yq, const double *p, const typename Mdl::Force *F,
+                                                      double t0, double t1, double abstol, double reltol)
+{
+    using namespace ts5;
+    constexpr int NXD = Mdl::NXD, NQS = Mdl::NQ, NX = Mdl::NX;
+    constexpr int ND = NXD * (1 + G), NQR = NQS * (1 + G), NQA = NQR > 0 ? NQR : 1, NQS1 = NQS > 0 ? NQS : 1;
+    constexpr double A[7][6] = {{0, 0, 0, 0, 0, 0},         {a21, 0, 0, 0, 0, 0},       {a31, a32, 0, 0, 0, 0},
+                                {a41, a42, a43, 0, 0, 0},   {a51, a52, a53, a54, 0, 0}, {a61, a62, a63, a64, a65, 0},
+                                {a71, a72, a73, a74, a75, a76}};
+    constexpr double BT[7] = {bt1, bt2, bt3, bt4, bt5, bt6, bt7};
+    double kd[7][ND], kq[7][NQA], td[ND], nd[ND], nq[NQA];
+    const double dtmax = t1 - t0;
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1.0e-4;
+    double t = t0, dt, qold = qoldinit;
+    rhs_all<Mdl, G>(yd, p, F, kd[0], kq[0]);
+    {   // initial step on the state components (dynamic ones in yd[0..NXD), quadrature-like ones in yq[0..NQ))
+        const double smalldt = 1.0e-6;
+        double s0 = 0.0, s1 = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; c++) {
+            const double y = c < NXD ? yd[c < NXD ? c : 0] : yq[c >= NXD ? c - NXD : 0];
+            const double f = c < NXD ? kd[0][c < NXD ? c : 0] : kq[0][c >= NXD ? c - NXD : 0];
+            const double sk = abstol + fabs(y) * reltol;
+            s0 += (y / sk) * (y / sk);
+            s1 += (f / sk) * (f / sk);
+        }
+        const double d0 = sqrt(s0 / NX), d1 = sqrt(s1 / NX);
+        double dt0 = (d0 < 1.0e-5 || d1 < 1.0e-5) ? smalldt : 0.01 * (d0 / d1);
+        dt0 = fmin(dt0, dtmax);
+        if (dt0 < 10.0 * 2.220446049250313e-16) {
+            dt = smalldt;
+        } else {
+            double u1[NXD], f1d[NXD], f1q[NQS1];
+#pragma unroll
+            for (int c = 0; c < NXD; c++) u1[c] = yd[c] + dt0 * kd[0][c];
+            rhs_all<Mdl, 0>(u1, p, F, f1d, f1q);
+            double s2 = 0.0;
+#pragma unroll
+            for (int c = 0; c < NX; c++) {
+                const double y = c < NXD ? yd[c < NXD ? c : 0] : yq[c >= NXD ? c - NXD : 0];
+                const double f0 = c < NXD ? kd[0][c < NXD ? c : 0] : kq[0][c >= NXD ? c - NXD : 0];
+                const double f1 = c < NXD ? f1d[c < NXD ? c : 0] : f1q[c >= NXD ? c - NXD : 0];
+                const double sk = abstol + fabs(y) * reltol;
+                s2 += ((f1 - f0) / sk) * ((f1 - f0) / sk);
+            }
+            const double d2 = sqrt(s2 / NX) / dt0;
+            const double md = fmax(d1, d2);
+            const double dt1 = md <= 1.0e-15 ? fmax(smalldt, dt0 * 1.0e-3) : pow(10.0, -(2.0 + log10(md)) / 5.0);
+            dt = fmin(fmin(100.0 * dt0, dt1), dtmax);
+        }
+    }
+    for (int iter = 0; iter < 1000000 && t < t1; iter++) {
+        dt = fmin(dt, dtmax);
+        dt = fmin(dt, t1 - t);
+#pragma unroll
+        for (int st = 1; st < 6; st++) {
+#pragma unroll
+            for (int c = 0; c < ND; c++) {
+                double acc = A[st][0] * kd[0][c];
+#pragma unroll
+                for (int j = 1; j < st; j++) acc += A[st][j] * kd[j][c];
+                td[c] = yd[c] + dt * acc;
+            }
+            rhs_all<Mdl, G>(td, p, F, kd[st], kq[st]);
+        }
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            double acc = A[6][0] * kd[0][c];
+#pragma unroll
+            for (int j = 1; j < 6; j++) acc += A[6][j] * kd[j][c];
+            nd[c] = yd[c] + dt * acc;
+        }
+#pragma unroll
+        for (int c = 0; c < NQR; c++) {
+            double acc = A[6][0] * kq[0][c];
+#pragma unroll
+            for (int j = 1; j < 6; j++) acc += A[6][j] * kq[j][c];
+            nq[c] = yq[c] + dt * acc;
+        }
+        rhs_all<Mdl, G>(nd, p, F, kd[6], kq[6]);
+        double se = 0.0;
+#pragma unroll
+        for (int c = 0; c < NX; c++) {
+            double ut = 0.0;
+#pragma unroll
+            for (int j = 0; j < 7; j++) ut += BT[j] * (c < NXD ? kd[j][c < NXD ? c : 0] : kq[j][c >= NXD ? c - NXD : 0]);
+            const double y0 = c < NXD ? yd[c < NXD ? c : 0] : yq[c >= NXD ? c - NXD : 0];
+            const double y1 = c < NXD ? nd[c < NXD ? c : 0] : nq[c >= NXD ? c - NXD : 0];
+            const double w = dt * ut / (abstol + fmax(fabs(y0), fabs(y1)) * reltol);
+            se += w * w;
+        }
+        const double EEst = sqrt(se / NX);
+        if (EEst != EEst) {   // non-finite: OrdinaryDiffEq stops with retcode Unstable; the status flag reports it
+#pragma unroll
+            for (int c = 0; c < NXD; c++) yd[c] = EEst;
+            return;
+        }
+        double q, q11 = 0.0;
+        if (EEst == 0.0) {
+            q = 1.0 / qmax;
+        } else {
+            q11 = cb_fastpow(EEst, beta1);
+            q = q11 / cb_fastpow(qold, beta2);
+            q = fmax(1.0 / qmax, fmin(1.0 / qmin, q / gamma));
+        }
+        if (EEst <= 1.0) {
+            qold = fmax(EEst, qoldinit);
+            const double dtnew = dt / q;
+            double tt = t + dt;
+            const double big = fabs(t1);
+            if (fabs(tt - t1) < 100.0 * (__longlong_as_double(__double_as_longlong(big) + 1) - big)) tt = t1;   // 100 eps(t1)
+            t = tt;
+#pragma unroll
+            for (int c = 0; c < ND; c++) {
+                yd[c] = nd[c];
+                kd[0][c] = kd[6][c];
+            }
+#pragma unroll
+            for (int c = 0; c < NQR; c++) {
+                yq[c] = nq[c];
+                kq[0][c] = kq[6][c];
+            }
+            dt = fmin(dtmax, dtnew);
+        } else {
+            dt = dt / fmin(1.0 / qmin, q11 / gamma);
+        }
+    }
+}
+
 // Structural zeros of the sensitivities: the derivative with respect to a control value is identically zero until
 // the first piece that uses it, so a piece only integrates the leading `na` directions of the thread's group (the
 // host table gives na = 1 + index of the last direction that is already switched on; the variable order (u0, p,
@@ -350,7 +503,9 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         if constexpr (G > 0 && TS) {
             if (o.tsens && live && j == 0) save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i), b, dmap, yd, yq);
         }
-        if constexpr (UNI) {
+        if constexpr (METHOD == 2) {
+            integrate_piece_adaptive<Mdl, G>(yd, yq, p, F, __ldg(L.pt0 + po + j), __ldg(L.pt1 + po + j), L.abstol, L.reltol);
+        } else if constexpr (UNI) {
             if (r == 0)   // block-uniform: only the first direction group reports the state (and its quadratures)
                 integrate_active<Mdl, G, METHOD, true>(na, yd, yq, p, F, L.hA, L.K);
             else
@@ -362,7 +517,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
                 tsit5_coeffs(h, cf);
             else
                 rk4_coeffs(h, cf);
-            integrate_active<Mdl, G, METHOD, true>(na, yd, yq, p, F, cf, L.K);
+            integrate_active<Mdl, G, (METHOD == 2 ? 0 : METHOD), true>(na, yd, yq, p, F, cf, L.K);
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
@@ -526,25 +681,30 @@ forward_kernel(const __grid_constant__ DevLayer L, double *__restrict__ ps, long
                 if (L.pmap_kind[q] == 1)
                     p[q] = vc[(long long)__ldg(L.cidx + (long long)(po + j) * L.nact + L.pmap_idx[q]) * ldb];
             double cf[NCF];
-            if (L.uniform_h) {
+            if constexpr (METHOD != 2) {
+                if (L.uniform_h) {
 #pragma unroll
-                for (int c = 0; c < NCF; c++) cf[c] = L.hA[c];
-            } else {
-                const double h = __ldg(L.ph + po + j);
-                if constexpr (METHOD == 0)
-                    tsit5_coeffs(h, cf);
-                else
-                    rk4_coeffs(h, cf);
+                    for (int c = 0; c < NCF; c++) cf[c] = L.hA[c];
+                } else {
+                    const double h = __ldg(L.ph + po + j);
+                    if constexpr (METHOD == 0)
+                        tsit5_coeffs(h, cf);
+                    else
+                        rk4_coeffs(h, cf);
+                }
             }
             typename Mdl::Force F[1];
-            integrate_piece<Mdl, 0, METHOD>(yd, yq, p, F, cf, L.K);
+            if constexpr (METHOD == 2)
+                integrate_piece_adaptive<Mdl, 0>(yd, yq, p, F, __ldg(L.pt0 + po + j), __ldg(L.pt1 + po + j), L.abstol, L.reltol);
+            else
+                integrate_piece<Mdl, 0, METHOD>(yd, yq, p, F, cf, L.K);
         }
 #pragma unroll
         for (int k = 0; k < NX; k++) carry[k] = (k < NXD) ? yd[k < NXD ? k : 0] : yq[k >= NXD ? k - NXD : 0];
     }
 }
 
-template <class Mdl>
+template <class Mdl, bool ADAPTIVE = false>
 int launch_forward(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
                    cudaStream_t s)
 {
@@ -552,8 +712,14 @@ int launch_forward(int method, const DevLayer &L, double *ps, long long ldb, lon
     const unsigned grid = (unsigned)((B + 63) / 64);
     if (method == 0)
         forward_kernel<Mdl, 0><<<grid, 64, 0, s>>>(L, ps, ldb, B, fixed);
-    else
+    else if (method == 1)
         forward_kernel<Mdl, 1><<<grid, 64, 0, s>>>(L, ps, ldb, B, fixed);
+    else {
+        if constexpr (ADAPTIVE)
+            forward_kernel<Mdl, 2><<<grid, 64, 0, s>>>(L, ps, ldb, B, fixed);
+        else
+            return -1000;   // the adaptive instantiation of this model is not compiled in
+    }
     return (int)cudaGetLastError();
 }
 
@@ -584,17 +750,23 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
         grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.In, (unsigned)L.R);
     if constexpr (G > 0) {
         if (o.tsens) {
-            if (L.uniform_h)
-                shoot_kernel<Mdl, G, METHOD, true, 1, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
-            else
-                shoot_kernel<Mdl, G, METHOD, false, 1, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            if constexpr (METHOD != 2) {
+                if (L.uniform_h) {
+                    shoot_kernel<Mdl, G, METHOD, true, 1, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+                    return (int)cudaGetLastError();
+                }
+            }
+            shoot_kernel<Mdl, G, METHOD, false, 1, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
             return (int)cudaGetLastError();
         }
     }
-    if (L.uniform_h)
-        shoot_kernel<Mdl, G, METHOD, true, MINB, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
-    else
-        shoot_kernel<Mdl, G, METHOD, false, MINB, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+    if constexpr (METHOD != 2) {
+        if (L.uniform_h) {
+            shoot_kernel<Mdl, G, METHOD, true, MINB, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            return (int)cudaGetLastError();
+        }
+    }
+    shoot_kernel<Mdl, G, METHOD, false, MINB, false><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
     return (int)cudaGetLastError();
 }
 
@@ -605,7 +777,14 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
 #endif
 #define CB200_DISPATCH_G(Mdl, Gv, MBv)                                                      \
     case Gv:                                                                                \
+        if (method > 1) return -1000;   /* no adaptive instantiation of this model */       \
         return method == 0 ? launch_one<Mdl, Gv, 0, CB200_MB(MBv)>(L, ps, ldb, B, o, s)   \
                            : launch_one<Mdl, Gv, 1, CB200_MB(MBv)>(L, ps, ldb, B, o, s);
+// ... plus method 2, adaptive Tsit5 (one block per SM register budget: it is not a throughput path)
+#define CB200_DISPATCH_GA(Mdl, Gv, MBv)                                                     \
+    case Gv:                                                                                \
+        return method == 0   ? launch_one<Mdl, Gv, 0, CB200_MB(MBv)>(L, ps, ldb, B, o, s) \
+               : method == 1 ? launch_one<Mdl, Gv, 1, CB200_MB(MBv)>(L, ps, ldb, B, o, s) \
+                             : launch_one<Mdl, Gv, 2, 1>(L, ps, ldb, B, o, s);
 
 }  // namespace cb200

@@ -6,10 +6,10 @@ int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long lo
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lin1d, 0, 1)
-        CB200_DISPATCH_G(Lin1d, 1, 1)
-        CB200_DISPATCH_G(Lin1d, 2, 1)
-        CB200_DISPATCH_G(Lin1d, 4, 1)
+        CB200_DISPATCH_GA(Lin1d, 0, 1)
+        CB200_DISPATCH_GA(Lin1d, 1, 1)
+        CB200_DISPATCH_GA(Lin1d, 2, 1)
+        CB200_DISPATCH_GA(Lin1d, 4, 1)
     default:
         return -1000;
     }
@@ -17,6 +17,6 @@ int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long lo
 int forward_lin1d(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lin1d>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lin1d, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

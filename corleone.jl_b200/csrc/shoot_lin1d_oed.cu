@@ -6,9 +6,9 @@ int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lin1dOed, 0, 1)
-        CB200_DISPATCH_G(Lin1dOed, 1, 1)
-        CB200_DISPATCH_G(Lin1dOed, 2, 1)
+        CB200_DISPATCH_GA(Lin1dOed, 0, 1)
+        CB200_DISPATCH_GA(Lin1dOed, 1, 1)
+        CB200_DISPATCH_GA(Lin1dOed, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, lon
 int forward_lin1d_oed(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lin1dOed>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lin1dOed, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,11 +6,11 @@ int launch_lotka2(int G, int method, const DevLayer &L, const double *ps, long l
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lotka2, 0, 1)
-        CB200_DISPATCH_G(Lotka2, 1, 1)
-        CB200_DISPATCH_G(Lotka2, 2, 1)
-        CB200_DISPATCH_G(Lotka2, 3, 1)
-        CB200_DISPATCH_G(Lotka2, 4, 1)
+        CB200_DISPATCH_GA(Lotka2, 0, 1)
+        CB200_DISPATCH_GA(Lotka2, 1, 1)
+        CB200_DISPATCH_GA(Lotka2, 2, 1)
+        CB200_DISPATCH_GA(Lotka2, 3, 1)
+        CB200_DISPATCH_GA(Lotka2, 4, 1)
     default:
         return -1000;
     }
@@ -18,6 +18,6 @@ int launch_lotka2(int G, int method, const DevLayer &L, const double *ps, long l
 int forward_lotka2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lotka2>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lotka2, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,9 +6,9 @@ int launch_lotka2_oed(int G, int method, const DevLayer &L, const double *ps, lo
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lotka2Oed, 0, 5)  // 96 registers: 20 warps/SM; G x MINB sweep in profiles/
-        CB200_DISPATCH_G(Lotka2Oed, 1, 1)
-        CB200_DISPATCH_G(Lotka2Oed, 2, 1)
+        CB200_DISPATCH_GA(Lotka2Oed, 0, 5)  // 96 registers: 20 warps/SM; G x MINB sweep in profiles/
+        CB200_DISPATCH_GA(Lotka2Oed, 1, 1)
+        CB200_DISPATCH_GA(Lotka2Oed, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_lotka2_oed(int G, int method, const DevLayer &L, const double *ps, lo
 int forward_lotka2_oed(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lotka2Oed>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lotka2Oed, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

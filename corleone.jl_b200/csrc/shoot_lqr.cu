@@ -6,11 +6,11 @@ int launch_lqr(int G, int method, const DevLayer &L, const double *ps, long long
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lqr, 0, 1)
-        CB200_DISPATCH_G(Lqr, 1, 1)
-        CB200_DISPATCH_G(Lqr, 2, 1)
-        CB200_DISPATCH_G(Lqr, 4, 4)  // 127 registers, no spills: 16 warps/SM (ptxas -v); best of the G x MINB sweep
-        CB200_DISPATCH_G(Lqr, 8, 1)
+        CB200_DISPATCH_GA(Lqr, 0, 1)
+        CB200_DISPATCH_GA(Lqr, 1, 1)
+        CB200_DISPATCH_GA(Lqr, 2, 1)
+        CB200_DISPATCH_GA(Lqr, 4, 4)  // 127 registers, no spills: 16 warps/SM (ptxas -v); best of the G x MINB sweep
+        CB200_DISPATCH_GA(Lqr, 8, 1)
     default:
         return -1000;
     }
@@ -18,6 +18,6 @@ int launch_lqr(int G, int method, const DevLayer &L, const double *ps, long long
 int forward_lqr(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lqr>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lqr, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

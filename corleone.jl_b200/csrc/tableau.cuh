@@ -14,6 +14,10 @@ constexpr double a61 = 5.86145544294642, a62 = -12.92096931784711, a63 = 8.15936
                  a64 = -0.071584973281401, a65 = -0.028269050394068383;
 constexpr double a71 = 0.09646076681806523, a72 = 0.01, a73 = 0.4798896504144996, a74 = 1.379008574103742,
                  a75 = -3.290069515436081, a76 = 2.324710524099774;
+// embedded error estimator (btilde) of the 5(4) pair -- method 2, adaptive stepping
+constexpr double bt1 = -0.00178001105222577714, bt2 = -0.0008164344596567469, bt3 = 0.007880878010261995,
+                 bt4 = -0.1447110071732629, bt5 = 0.5823571654525552, bt6 = -0.45808210592918697,
+                 bt7 = 0.015151515151515152;
 }  // namespace ts5
 
 // Tsit5 coefficient slots: cf[0]=h a21; [1..2]=h a31,a32; [3..5]=h a4.; [6..9]=h a5.; [10..14]=h a6.; [15..20]=h a7.

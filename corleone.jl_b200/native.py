@@ -41,7 +41,7 @@ class Desc(C.Structure):
         ("ic_n_constants", _i32p), ("ic_constants", _i64p), ("n_shooting_indices", _i32p),
         ("shooting_indices", _i64p), ("model_data", _dp), ("model_data_len", C.c_int64),
         ("fim_base_nx", C.c_int32), ("n_observed", C.c_int32), ("n_observation_rows", _i32p),
-        ("observation_grid", _i64p),
+        ("observation_grid", _i64p), ("abstol", C.c_double), ("reltol", C.c_double),
     ]
 
 
@@ -114,7 +114,7 @@ class NativeLayer:
 
     def __init__(self, *, model_id, method, steps_per_piece, nx, np_all, u0, tunable_p, control_indices,
                  quadrature_indices, intervals, device=0, fim_offset=0, fim_n=0, model_data=None, fim_mode=0,
-                 fim_base_nx=0, n_observed=0, observation_rows=None):
+                 fim_base_nx=0, n_observed=0, observation_rows=None, abstol=1e-6, reltol=1e-3):
         """intervals: list of dicts with tspans [(t0,t1)...], index_grid (n_controls x M int64 1-based),
         n_u0, n_c, is_shooting, sorting, constants, shooting_indices (all 1-based as the reference).
         observation_rows: per interval an (rows x n_observed) int array = WeightedObservation.grid (fim_mode 2, 3)."""
@@ -128,6 +128,7 @@ class NativeLayer:
         d.n_intervals, d.n_quadrature, d.device = len(intervals), len(quadrature_indices), device
         d.fim_offset, d.fim_n, d.fim_mode = fim_offset, fim_n, fim_mode
         d.fim_base_nx, d.n_observed = fim_base_nx, n_observed
+        d.abstol, d.reltol = abstol, reltol
 
         def put(name, values, dtype, ptr):
             a = _arr(values if len(values) else [0], dtype)

@@ -96,9 +96,15 @@ class ODEProblem:
 
 @dataclass(frozen=True)
 class Tsit5:
-    """Tsitouras 5(4), fixed step: `steps_per_piece` steps h = (t1-t0)/K on every control piece."""
+    """Tsitouras 5(4).  Fixed step (default): `steps_per_piece` steps h = (t1-t0)/K on every control piece -- the
+    `adaptive=false, dt=h` mode.  `adaptive=True`: the reference's default mode, OrdinaryDiffEq's step-size control with
+    the problem's `abstol` / `reltol` keyword arguments (ODEProblem(...; abstol, reltol); defaults 1e-6 / 1e-3)."""
     steps_per_piece: int = 1
-    method_id: int = 0
+    adaptive: bool = False
+
+    @property
+    def method_id(self) -> int:
+        return 2 if self.adaptive else 0
 
 
 @dataclass(frozen=True)

@@ -214,6 +214,7 @@ class SingleShootingLayer:
             control_indices=cidx, quadrature_indices=self.quadrature_indices,
             intervals=[self._interval_desc(s, l, is_shooting) for s, l in zip(interval_sts, interval_lengths)],
             device=self.device, model_data=prob.model_data,
+            abstol=float(prob.kwargs.get("abstol", 1e-6)), reltol=float(prob.kwargs.get("reltol", 1e-3)),
             **(dict(fim_offset=fim["offset"], fim_n=fim["n"], fim_mode=fim["mode"], fim_base_nx=fim["base_nx"],
                     n_observed=fim["n_observed"], observation_rows=fim["rows"]) if isinstance(fim, dict)
                else dict(fim_offset=fim[0], fim_n=fim[1])))

@@ -97,7 +97,14 @@ typedef enum {
     CB200_MODEL_HANGGLIDER4 = 41   /* hang_glider.jl:9-66; states (x, y, vx, vy), p = (T, cL) */
 } cb200_model;
 
-typedef enum { CB200_TSIT5 = 0, CB200_RK4 = 1 } cb200_method;
+typedef enum {
+    CB200_TSIT5 = 0,            /* fixed step h = (t1 - t0)/steps_per_piece on every piece (adaptive = false, dt = h) */
+    CB200_RK4 = 1,              /* classical RK4, fixed step */
+    CB200_TSIT5_ADAPTIVE = 2    /* the reference's default: adaptive Tsit5 with the problem's abstol / reltol, every piece a
+                                   fresh `solve` (src/single_shooting.jl:443-453); OrdinaryDiffEq's controller restated --
+                                   reproduces the reference's golden vectors to ~1e-15.  steps_per_piece is ignored.
+                                   Compiled in for LOTKA3, LOTKA2, LQR, LIN1D, LOTKA2_OED, LIN1D_OED */
+} cb200_method;
 
 /*
  * Static description of one layer == the reference's `st` (one entry per shooting interval; a
@@ -148,6 +155,8 @@ typedef struct {
                                            Row j of interval i belongs to the interval's j-th saved sample.  For
                                            CB200_FIM_FIXED_CONTINUOUS row j holds the j-th entries of
                                            st.active_controls (oed.jl:352-362) and weights F(sample j+1) - F(sample j) */
+    double abstol, reltol;              /* CB200_TSIT5_ADAPTIVE: problem.kwargs abstol / reltol (OrdinaryDiffEq defaults
+                                           1e-6 / 1e-3); ignored by the fixed-step methods */
 } cb200_desc;
 
 /* Fisher read-out (lib/CorleoneOED/src/oed.jl:381-461) */

@@ -57,6 +57,8 @@ struct Desc                      # cb200_desc
     n_observed::Int32
     n_observation_rows::Ptr{Int32}
     observation_grid::Ptr{Int64}
+    abstol::Float64
+    reltol::Float64
 end
 
 struct Out                       # cb200_out
@@ -189,14 +191,15 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
     end
     h = Ref{Ptr{Cvoid}}(C_NULL)
     GC.@preserve u0 tunable_p cidx quad n_pieces tsp grid n_u0 n_c is_sh sorting ncon cons nsi sidx md n_obs_rows obs_grid begin
-        d = Desc(sizeof(Desc), MODELS[e.model], e.method === :tsit5 ? 0 : 1, e.steps_per_piece, nx, np_all,
+        d = Desc(sizeof(Desc), MODELS[e.model], e.method === :tsit5 ? 0 : (e.method === :rk4 ? 1 : 2), e.steps_per_piece, nx, np_all,
             length(cidx), length(tunable_p), I, length(quad), e.device, e.fim[1], e.fim[2], e.fim_mode,
             pointer(u0), pointer(tunable_p), pointer(cidx), pointer(quad), pointer(n_pieces), pointer(tsp),
             pointer(grid), pointer(n_u0), pointer(n_c), pointer(is_sh), pointer(sorting), pointer(ncon),
             pointer(cons), pointer(nsi), pointer(sidx), isempty(md) ? Ptr{Float64}(C_NULL) : pointer(md),
             length(md), e.fim_base_nx, e.n_observed,
             isempty(n_obs_rows) ? Ptr{Int32}(C_NULL) : pointer(n_obs_rows),
-            isempty(obs_grid) ? Ptr{Int64}(C_NULL) : pointer(obs_grid))
+            isempty(obs_grid) ? Ptr{Int64}(C_NULL) : pointer(obs_grid),
+            Float64(get(prob.kwargs, :abstol, 1.0e-6)), Float64(get(prob.kwargs, :reltol, 1.0e-3)))
         check(ccall((:cb200_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h), "cb200_create")
     end
     e.handle = h[]

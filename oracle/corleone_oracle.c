@@ -594,9 +594,174 @@ static const double TS_A[7][6] = {
 
 /* one control piece: K steps of h = (t1-t0)/K; k1 is re-evaluated at the piece start because every piece is
  * a fresh `solve` in the reference (src/single_shooting.jl:443-453); FSAL inside the piece. */
+/* ------------------------------------------------------------------ adaptive Tsit5
+ * The reference's DEFAULT mode: `solve(problem, Tsit5(); ...)` per control piece (src/single_shooting.jl:443-453) with
+ * the problem's abstol / reltol (test/core/multiple_shooting.jl:23: 1e-8 / 1e-6; OrdinaryDiffEq defaults 1e-6 / 1e-3).
+ * The stepping itself is OrdinaryDiffEq's (third party, not under /root/reference; compat "1, 2", no Manifest) and is
+ * restated here from its published algorithm:
+ *   - initial step: Hairer-Norsett-Wanner heuristic as OrdinaryDiffEq's `ode_determine_initdt` applies it
+ *     (d0 = |u0/sk|, d1 = |f0/sk|, dt0 = 0.01 d0/d1, one explicit Euler probe, dt1 = 10^(-(2+log10 max(d1,d2))/5),
+ *     dt = min(100 dt0, dt1, dtmax)), norms = RMS, sk = abstol + |u0| reltol, dtmax = the span of the piece;
+ *   - embedded error estimate utilde = dt sum_j btilde_j k_j, EEst = RMS(utilde / (abstol + max(|uprev|,|u|) reltol));
+ *   - PI controller: q11 = EEst^beta1, q = q11 / qold^beta2 (beta1 = 7/50, beta2 = 2/25), q = clamp(q / gamma, 1/qmax,
+ *     1/qmin) with gamma = 0.9, qmin = 0.2, qmax = 10; accept iff EEst <= 1, then qold = max(EEst, 1e-4), dt <- dt/q;
+ *     reject: dt <- dt / min(1/qmin, q11/gamma); the powers are taken with DiffEqBase's `fastpow` (Float32: Goldberg's
+ *     rational approximation of log2, then exp2);
+ *   - every step is clipped to the end of the piece and t snaps to it within 100 eps.
+ * Every piece is a fresh `solve`: initial step and controller memory start over.
+ * PIN: with this restatement the reference's golden vectors G1 / G4 (test/core/multiple_shooting.jl:54-72,220), which
+ * a converged fixed-step integration only reaches to 5e-11, are reproduced to ~1e-15 (tests/test_oracle_golden.py) --
+ * the accepted step sequence is the reference's.
+ * Forward sensitivities ride along on the SAME step sequence (error control on the values only): the derivative of
+ * the computed map with the steps frozen.  (ForwardDiff through `solve` lets the partials take part in the norm, so
+ * the reference's own derivatives depend on the AD chunking; the values do not.) */
+static double g_abstol = 1.0e-6, g_reltol = 1.0e-3;
+void co_set_tolerances(double abstol, double reltol)
+{
+    g_abstol = abstol;
+    g_reltol = reltol;
+}
+static const double TS_BT[7] = {-0.00178001105222577714, -0.0008164344596567469, 0.007880878010261995,
+                                -0.1447110071732629,     0.5823571654525552,     -0.45808210592918697,
+                                0.015151515151515152};
+/* DiffEqBase fastpow(x, y) = exp2(Float32(y) * fastlog2(Float32(x))) */
+static float co_fastlog2(float x)
+{
+    const float a = 0.338953f, b = 2.198599f, c = 1.523692f;
+    unsigned ux, ux2;
+    memcpy(&ux, &x, 4);
+    const unsigned e = (ux & 0x7F800000u) >> 23;
+    volatile float signif, fexp, t1, t2, t3; /* volatile: no FMA contraction, as in Julia without @muladd */
+    float sf;
+    if (ux & 0x00400000u) {
+        ux2 = (ux & 0x007FFFFFu) | 0x3f000000u;
+        fexp = (float)e - 126.0f;
+    } else {
+        ux2 = (ux & 0x007FFFFFu) | 0x3f800000u;
+        fexp = (float)e - 127.0f;
+    }
+    memcpy(&sf, &ux2, 4);
+    signif = sf - 1.0f;
+    t1 = a * signif;
+    t1 = t1 + b;
+    t2 = t1 * signif;
+    t3 = signif + c;
+    t2 = t2 / t3;
+    return fexp + t2;
+}
+static double co_fastpow(double x, double y)
+{
+    if (x == 0.0) return 0.0;
+    volatile float e = (float)y * co_fastlog2((float)x);
+    return (double)exp2f(e);
+}
+static double rms_state(const double *v, int n)
+{
+    double s = 0.0;
+    for (int c = 0; c < n; c++) s += v[c] * v[c];
+    return sqrt(s / (double)n);
+}
+static void integrate_piece_adaptive(const model_ctx *m, int nx, dual *x, const dual *p, double t0, double t1)
+{
+    dual k[7][CO_MAX_NX], tmp[CO_MAX_NX], xn[CO_MAX_NX];
+    double w[CO_MAX_NX], sk[CO_MAX_NX];
+    const double abstol = g_abstol, reltol = g_reltol, dtmax = t1 - t0;
+    const double beta1 = 7.0 / 50.0, beta2 = 2.0 / 25.0, gamma = 0.9, qmin = 0.2, qmax = 10.0, qoldinit = 1.0e-4;
+    double t = t0, dt, qold = qoldinit;
+    model_rhs(m, x, p, k[0]);
+    { /* initial step */
+        const double smalldt = 1.0e-6;
+        for (int c = 0; c < nx; c++) sk[c] = abstol + fabs(x[c].v) * reltol;
+        for (int c = 0; c < nx; c++) w[c] = x[c].v / sk[c];
+        const double d0 = rms_state(w, nx);
+        for (int c = 0; c < nx; c++) w[c] = k[0][c].v / sk[c];
+        const double d1 = rms_state(w, nx);
+        double dt0 = (d0 < 1.0e-5 || d1 < 1.0e-5) ? smalldt : 0.01 * (d0 / d1);
+        if (dt0 > dtmax) dt0 = dtmax;
+        if (dt0 < 10.0 * 2.220446049250313e-16) {
+            dt = smalldt;
+        } else {
+            const int nd = g_nd;
+            g_nd = 0; /* the probe needs values only */
+            for (int c = 0; c < nx; c++) tmp[c] = dconst(x[c].v + dt0 * k[0][c].v);
+            model_rhs(m, tmp, p, xn);
+            g_nd = nd;
+            for (int c = 0; c < nx; c++) w[c] = (xn[c].v - k[0][c].v) / sk[c];
+            const double d2 = rms_state(w, nx) / dt0;
+            const double md = d1 > d2 ? d1 : d2;
+            const double dt1 = md <= 1.0e-15 ? (smalldt > dt0 * 1.0e-3 ? smalldt : dt0 * 1.0e-3)
+                                             : pow(10.0, -(2.0 + log10(md)) / 5.0);
+            dt = 100.0 * dt0;
+            if (dt1 < dt) dt = dt1;
+            if (dtmax < dt) dt = dtmax;
+        }
+    }
+    for (long iter = 0; iter < 1000000L && t < t1; iter++) {
+        if (dt > dtmax) dt = dtmax;
+        if (dt > t1 - t) dt = t1 - t;
+        for (int st = 1; st < 6; st++) {
+            for (int c = 0; c < nx; c++) {
+                dual acc = dscale(k[0][c], TS_A[st][0]);
+                for (int j = 1; j < st; j++) daxpy(&acc, TS_A[st][j], &k[j][c]);
+                tmp[c] = x[c];
+                daxpy(&tmp[c], dt, &acc);
+            }
+            model_rhs(m, tmp, p, k[st]);
+        }
+        for (int c = 0; c < nx; c++) {
+            dual acc = dscale(k[0][c], TS_A[6][0]);
+            for (int j = 1; j < 6; j++) daxpy(&acc, TS_A[6][j], &k[j][c]);
+            xn[c] = x[c];
+            daxpy(&xn[c], dt, &acc);
+        }
+        model_rhs(m, xn, p, k[6]);
+        for (int c = 0; c < nx; c++) {
+            double ut = 0.0;
+            for (int j = 0; j < 7; j++) ut += TS_BT[j] * k[j][c].v;
+            const double a0 = fabs(x[c].v), a1 = fabs(xn[c].v);
+            w[c] = dt * ut / (abstol + (a0 > a1 ? a0 : a1) * reltol);
+        }
+        const double EEst = rms_state(w, nx);
+        if (EEst != EEst) { /* non-finite: the reference would stop with retcode Unstable; poison the state */
+            for (int c = 0; c < nx; c++) x[c] = dconst(NAN);
+            return;
+        }
+        double q, q11 = 0.0;
+        if (EEst == 0.0) {
+            q = 1.0 / qmax;
+        } else {
+            q11 = co_fastpow(EEst, beta1);
+            q = q11 / co_fastpow(qold, beta2);
+            q = q / gamma;
+            if (q > 1.0 / qmin) q = 1.0 / qmin;
+            if (q < 1.0 / qmax) q = 1.0 / qmax;
+        }
+        if (EEst <= 1.0) {
+            qold = EEst > qoldinit ? EEst : qoldinit;
+            const double dtnew = dt / q;
+            double tt = t + dt;
+            const double big = fabs(t1);
+            if (fabs(tt - t1) < 100.0 * (nextafter(big, INFINITY) - big)) tt = t1;
+            t = tt;
+            for (int c = 0; c < nx; c++) {
+                x[c] = xn[c];
+                k[0][c] = k[6][c];
+            }
+            dt = dtnew < dtmax ? dtnew : dtmax;
+        } else {
+            const double r = q11 / gamma;
+            dt = dt / (r < 1.0 / qmin ? r : 1.0 / qmin);
+        }
+    }
+}
+
 static void integrate_piece(const model_ctx *m, int nx, dual *x, const dual *p, double t0, double t1, int K,
                             int method)
 {
+    if (method == CO_TSIT5_ADAPTIVE) {
+        integrate_piece_adaptive(m, nx, x, p, t0, t1);
+        return;
+    }
     dual k[7][CO_MAX_NX], tmp[CO_MAX_NX];
     double h = (t1 - t0) / (double)K;
     if (method == CO_TSIT5) {

@@ -79,7 +79,9 @@ enum co_model {
     CO_HANGGLIDER4 = 41
 };
 
-enum co_method { CO_TSIT5 = 0, CO_RK4 = 1 };
+enum co_method { CO_TSIT5 = 0, CO_RK4 = 1, CO_TSIT5_ADAPTIVE = 2 /* the reference's default mode; K is ignored */ };
+/* abstol / reltol of CO_TSIT5_ADAPTIVE (process-wide; defaults 1e-6 / 1e-3 as OrdinaryDiffEq's) */
+void co_set_tolerances(double abstol, double reltol);
 
 typedef struct {
     int model;

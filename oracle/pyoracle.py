@@ -58,7 +58,7 @@ MODELS = {
     "ductedfan7": 40,
     "hangglider4": 41,
 }
-METHODS = {"tsit5": 0, "rk4": 1}
+METHODS = {"tsit5": 0, "rk4": 1, "tsit5_adaptive": 2}
 CO_ND = 16
 
 
@@ -129,6 +129,11 @@ def lib():
         L.co_subvector_indices.restype = C.c_int
         _LIB = L
     return _LIB
+
+
+def set_tolerances(abstol: float, reltol: float):
+    """abstol / reltol of method "tsit5_adaptive" (the reference passes them through the ODEProblem's kwargs)"""
+    lib().co_set_tolerances(C.c_double(abstol), C.c_double(reltol))
 
 
 def _dp(a):

@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8 + 2 * 4 + 2 * 8
+    assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8 + 2 * 4 + 2 * 8 + 2 * 8
     assert ctypes.sizeof(native.Out) == 12 * 8 + 8 + 8 + 8 + 8 + 8 + 8
     assert ctypes.sizeof(native.Sizes) == 9 * 8
 

@@ -38,7 +38,9 @@ def full_compare(spec, alg, B, rng, objective_row, check_traj=True, ps=None):
     lay = P.product_layer(spec, alg)
     ps_t, st = cb.setup(None, lay)
     N = lay._native(st, ps_t)
-    method = "tsit5" if alg.method_id == 0 else "rk4"
+    method = {0: "tsit5", 1: "rk4", 2: "tsit5_adaptive"}[alg.method_id]
+    if alg.method_id == 2:   # the problem's tolerances (ODEProblem kwargs), OrdinaryDiffEq's defaults otherwise
+        po.set_tolerances(spec.get("kwargs", {}).get("abstol", 1e-6), spec.get("kwargs", {}).get("reltol", 1e-3))
     K = alg.steps_per_piece
     assert N.nvars == O.nvars and N.n_defects == O.ndef and N.n_samples == O.nsamples and N.n_row == O.nrow
     assert np.array_equal(N.block_structure(), O.block_structure())
