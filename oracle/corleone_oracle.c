@@ -11,8 +11,10 @@
  *   OED augmentation [x; G; F_triu]                  lib/CorleoneOED/src/augmentation.jl:131-159,206-253
  * Third-party arithmetic the reference calls but does not contain:
  *   OrdinaryDiffEqTsit5 (Project.toml:44, compat "1, 2", unpinned -- no Manifest): explicit 7-stage FSAL
- *   Tsitouras 5(4) scheme, published tableau (Tsitouras 2011); run with adaptive=false, so only the
- *   propagation weights are used.  ForwardDiff (dual numbers through `solve`): restated as `dual` below.
+ *   Tsitouras 5(4) scheme, published tableau (Tsitouras 2011).  CO_TSIT5 / CO_RK4 run it with adaptive=false (only the
+ *   propagation weights); CO_TSIT5_ADAPTIVE restates OrdinaryDiffEq's step-size control as well (see
+ *   integrate_piece_adaptive) and reproduces the reference's golden vectors to ~1e-15.
+ *   ForwardDiff (dual numbers through `solve`): restated as `dual` below.
  */
 #include "corleone_oracle.h"
 
