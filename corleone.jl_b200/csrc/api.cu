@@ -623,12 +623,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         return fail(CB200_ERR_UNSUPPORTED, "unknown method");
     if (d->steps_per_piece < 1) return fail(CB200_ERR_ARG, "steps_per_piece must be >= 1");
     if (d->method == CB200_TSIT5_ADAPTIVE) {
-        switch (d->model) {
-        case CB200_MODEL_LOTKA3: case CB200_MODEL_LOTKA2: case CB200_MODEL_LQR: case CB200_MODEL_LIN1D:
-        case CB200_MODEL_LOTKA2_OED: case CB200_MODEL_LIN1D_OED: break;
-        default:
-            return fail(CB200_ERR_UNSUPPORTED, "model %d has no adaptive-step kernel compiled in (CB200_DISPATCH_GA in its shoot_*.cu)", d->model);
-        }
+        if (d->model == CB200_MODEL_DENSE20)
+            return fail(CB200_ERR_UNSUPPORTED, "model %d has no adaptive-step kernel (the tensor-path kernel is fixed-step)", d->model);
         if (!(d->abstol > 0.0) || !(d->reltol > 0.0)) return fail(CB200_ERR_ARG, "adaptive Tsit5 needs abstol > 0 and reltol > 0");
     }
     if (d->n_intervals < 1) return fail(CB200_ERR_ARG, "n_intervals must be >= 1");

@@ -241,9 +241,14 @@ __device__ __noinline__ void integrate_piece_adaptive(double *yd, double *yq, co
             dt = fmin(fmin(100.0 * dt0, dt1), dtmax);
         }
     }
-    for (int iter = 0; iter < 1000000 && t < t1; iter++) {
+    for (int iter = 0; t < t1; iter++) {
         dt = fmin(dt, dtmax);
         dt = fmin(dt, t1 - t);
+        if (iter >= 100000 || !(dt > 0.0)) {   // OrdinaryDiffEq: retcode MaxIters (maxiters = 1e5) / DtLessThanMin
+#pragma unroll
+            for (int c = 0; c < NXD; c++) yd[c] = nan("");
+            return;
+        }
 #pragma unroll
         for (int st = 1; st < 6; st++) {
 #pragma unroll

@@ -6,9 +6,9 @@ int launch_cartpole5(int G, int method, const DevLayer &L, const double *ps, lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(CartPole5, 0, 1)
-        CB200_DISPATCH_G(CartPole5, 1, 1)
-        CB200_DISPATCH_G(CartPole5, 2, 1)
+        CB200_DISPATCH_GA(CartPole5, 0, 1)
+        CB200_DISPATCH_GA(CartPole5, 1, 1)
+        CB200_DISPATCH_GA(CartPole5, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_cartpole5(int G, int method, const DevLayer &L, const double *ps, lon
 int forward_cartpole5(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<CartPole5>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<CartPole5, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,8 +6,8 @@ int launch_catalystmixing2(int G, int method, const DevLayer &L, const double *p
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(CatalystMixing2, 0, 1)
-        CB200_DISPATCH_G(CatalystMixing2, 2, 1)
+        CB200_DISPATCH_GA(CatalystMixing2, 0, 1)
+        CB200_DISPATCH_GA(CatalystMixing2, 2, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_catalystmixing2(int G, int method, const DevLayer &L, const double *p
 int forward_catalystmixing2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<CatalystMixing2>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<CatalystMixing2, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

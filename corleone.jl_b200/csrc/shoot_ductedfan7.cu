@@ -6,8 +6,8 @@ int launch_ductedfan7(int G, int method, const DevLayer &L, const double *ps, lo
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(DuctedFan7, 0, 1)
-        CB200_DISPATCH_G(DuctedFan7, 1, 1)
+        CB200_DISPATCH_GA(DuctedFan7, 0, 1)
+        CB200_DISPATCH_GA(DuctedFan7, 1, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_ductedfan7(int G, int method, const DevLayer &L, const double *ps, lo
 int forward_ductedfan7(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<DuctedFan7>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<DuctedFan7, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,10 +6,10 @@ int launch_egerstedt(int G, int method, const DevLayer &L, const double *ps, lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Egerstedt, 0, 1)
-        CB200_DISPATCH_G(Egerstedt, 1, 1)
-        CB200_DISPATCH_G(Egerstedt, 2, 1)
-        CB200_DISPATCH_G(Egerstedt, 3, 1)
+        CB200_DISPATCH_GA(Egerstedt, 0, 1)
+        CB200_DISPATCH_GA(Egerstedt, 1, 1)
+        CB200_DISPATCH_GA(Egerstedt, 2, 1)
+        CB200_DISPATCH_GA(Egerstedt, 3, 1)
     default:
         return -1000;
     }
@@ -17,6 +17,6 @@ int launch_egerstedt(int G, int method, const DevLayer &L, const double *ps, lon
 int forward_egerstedt(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Egerstedt>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Egerstedt, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

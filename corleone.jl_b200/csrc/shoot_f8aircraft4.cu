@@ -6,9 +6,9 @@ int launch_f8aircraft4(int G, int method, const DevLayer &L, const double *ps, l
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(F8Aircraft4, 0, 1)
-        CB200_DISPATCH_G(F8Aircraft4, 1, 1)
-        CB200_DISPATCH_G(F8Aircraft4, 2, 1)
+        CB200_DISPATCH_GA(F8Aircraft4, 0, 1)
+        CB200_DISPATCH_GA(F8Aircraft4, 1, 1)
+        CB200_DISPATCH_GA(F8Aircraft4, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_f8aircraft4(int G, int method, const DevLayer &L, const double *ps, l
 int forward_f8aircraft4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<F8Aircraft4>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<F8Aircraft4, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,8 +6,8 @@ int launch_jackson3(int G, int method, const DevLayer &L, const double *ps, long
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Jackson3, 0, 1)
-        CB200_DISPATCH_G(Jackson3, 2, 1)
+        CB200_DISPATCH_GA(Jackson3, 0, 1)
+        CB200_DISPATCH_GA(Jackson3, 2, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_jackson3(int G, int method, const DevLayer &L, const double *ps, long
 int forward_jackson3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Jackson3>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Jackson3, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,9 +6,9 @@ int launch_lin1d_oed_ds(int G, int method, const DevLayer &L, const double *ps, 
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lin1dOedDs, 0, 1)
-        CB200_DISPATCH_G(Lin1dOedDs, 1, 1)
-        CB200_DISPATCH_G(Lin1dOedDs, 2, 1)
+        CB200_DISPATCH_GA(Lin1dOedDs, 0, 1)
+        CB200_DISPATCH_GA(Lin1dOedDs, 1, 1)
+        CB200_DISPATCH_GA(Lin1dOedDs, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_lin1d_oed_ds(int G, int method, const DevLayer &L, const double *ps, 
 int forward_lin1d_oed_ds(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lin1dOedDs>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lin1dOedDs, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

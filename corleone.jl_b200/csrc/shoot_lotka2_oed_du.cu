@@ -6,9 +6,9 @@ int launch_lotka2_oed_du(int G, int method, const DevLayer &L, const double *ps,
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Lotka2OedDu, 0, 1)
-        CB200_DISPATCH_G(Lotka2OedDu, 1, 1)
-        CB200_DISPATCH_G(Lotka2OedDu, 2, 1)
+        CB200_DISPATCH_GA(Lotka2OedDu, 0, 1)
+        CB200_DISPATCH_GA(Lotka2OedDu, 1, 1)
+        CB200_DISPATCH_GA(Lotka2OedDu, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_lotka2_oed_du(int G, int method, const DevLayer &L, const double *ps,
 int forward_lotka2_oed_du(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Lotka2OedDu>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Lotka2OedDu, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

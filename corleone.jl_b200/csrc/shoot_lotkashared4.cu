@@ -6,8 +6,8 @@ int launch_lotkashared4(int G, int method, const DevLayer &L, const double *ps, 
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(LotkaShared4, 0, 1)
-        CB200_DISPATCH_G(LotkaShared4, 2, 1)
+        CB200_DISPATCH_GA(LotkaShared4, 0, 1)
+        CB200_DISPATCH_GA(LotkaShared4, 2, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_lotkashared4(int G, int method, const DevLayer &L, const double *ps, 
 int forward_lotkashared4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<LotkaShared4>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<LotkaShared4, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

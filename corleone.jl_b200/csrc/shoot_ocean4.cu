@@ -6,8 +6,8 @@ int launch_ocean4(int G, int method, const DevLayer &L, const double *ps, long l
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Ocean4, 0, 1)
-        CB200_DISPATCH_G(Ocean4, 2, 1)
+        CB200_DISPATCH_GA(Ocean4, 0, 1)
+        CB200_DISPATCH_GA(Ocean4, 2, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_ocean4(int G, int method, const DevLayer &L, const double *ps, long l
 int forward_ocean4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Ocean4>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Ocean4, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,8 +6,8 @@ int launch_particlesteering5(int G, int method, const DevLayer &L, const double 
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(ParticleSteering5, 0, 1)
-        CB200_DISPATCH_G(ParticleSteering5, 1, 1)
+        CB200_DISPATCH_GA(ParticleSteering5, 0, 1)
+        CB200_DISPATCH_GA(ParticleSteering5, 1, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_particlesteering5(int G, int method, const DevLayer &L, const double 
 int forward_particlesteering5(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<ParticleSteering5>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<ParticleSteering5, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,9 +6,9 @@ int launch_quadrotor7(int G, int method, const DevLayer &L, const double *ps, lo
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Quadrotor7, 0, 1)
-        CB200_DISPATCH_G(Quadrotor7, 1, 1)
-        CB200_DISPATCH_G(Quadrotor7, 2, 1)
+        CB200_DISPATCH_GA(Quadrotor7, 0, 1)
+        CB200_DISPATCH_GA(Quadrotor7, 1, 1)
+        CB200_DISPATCH_GA(Quadrotor7, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_quadrotor7(int G, int method, const DevLayer &L, const double *ps, lo
 int forward_quadrotor7(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Quadrotor7>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Quadrotor7, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -6,8 +6,8 @@ int launch_raomease2(int G, int method, const DevLayer &L, const double *ps, lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(RaoMease2, 0, 1)
-        CB200_DISPATCH_G(RaoMease2, 2, 1)
+        CB200_DISPATCH_GA(RaoMease2, 0, 1)
+        CB200_DISPATCH_GA(RaoMease2, 2, 1)
     default:
         return -1000;
     }
@@ -15,6 +15,6 @@ int launch_raomease2(int G, int method, const DevLayer &L, const double *ps, lon
 int forward_raomease2(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<RaoMease2>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<RaoMease2, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

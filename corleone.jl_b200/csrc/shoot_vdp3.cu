@@ -6,9 +6,9 @@ int launch_vdp3(int G, int method, const DevLayer &L, const double *ps, long lon
         const ShootOut &o, cudaStream_t s)
 {
     switch (G) {
-        CB200_DISPATCH_G(Vdp3, 0, 1)
-        CB200_DISPATCH_G(Vdp3, 1, 1)
-        CB200_DISPATCH_G(Vdp3, 2, 1)
+        CB200_DISPATCH_GA(Vdp3, 0, 1)
+        CB200_DISPATCH_GA(Vdp3, 1, 1)
+        CB200_DISPATCH_GA(Vdp3, 2, 1)
     default:
         return -1000;
     }
@@ -16,6 +16,6 @@ int launch_vdp3(int G, int method, const DevLayer &L, const double *ps, long lon
 int forward_vdp3(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<Vdp3>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<Vdp3, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

@@ -103,7 +103,7 @@ typedef enum {
     CB200_TSIT5_ADAPTIVE = 2    /* the reference's default: adaptive Tsit5 with the problem's abstol / reltol, every piece a
                                    fresh `solve` (src/single_shooting.jl:443-453); OrdinaryDiffEq's controller restated --
                                    reproduces the reference's golden vectors to ~1e-15.  steps_per_piece is ignored.
-                                   Compiled in for LOTKA3, LOTKA2, LQR, LIN1D, LOTKA2_OED, LIN1D_OED */
+                                   Every model but DENSE20 */
 } cb200_method;
 
 /*

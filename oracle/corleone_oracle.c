@@ -698,9 +698,13 @@ static void integrate_piece_adaptive(const model_ctx *m, int nx, dual *x, const 
             if (dtmax < dt) dt = dtmax;
         }
     }
-    for (long iter = 0; iter < 1000000L && t < t1; iter++) {
+    for (long iter = 0; t < t1; iter++) {
         if (dt > dtmax) dt = dtmax;
         if (dt > t1 - t) dt = t1 - t;
+        if (iter >= 100000L || !(dt > 0.0)) { /* OrdinaryDiffEq: retcode MaxIters (maxiters = 1e5) / DtLessThanMin */
+            for (int c = 0; c < nx; c++) x[c] = dconst(NAN);
+            return;
+        }
         for (int st = 1; st < 6; st++) {
             for (int c = 0; c < nx; c++) {
                 dual acc = dscale(k[0][c], TS_A[st][0]);

@@ -116,8 +116,43 @@ def test_adaptive_oed_fisher_information_parity(shooting):
 def test_models_without_an_adaptive_kernel_say_so():
     import corleone_b200 as cb
     from corleone_b200 import native as nat
-    spec, _, _ = P.bench_spec("fuller")
-    lay = P.product_layer(spec, cb.Tsit5(adaptive=True))
+    lay = P.product_layer(P.dense20_spec(4), cb.Tsit5(adaptive=True))
     ps, st = cb.setup(None, lay)
     with pytest.raises(nat.NativeError, match="adaptive-step kernel"):
         lay._native(st, ps)
+
+
+@pytest.mark.parametrize("name", ["vdp", "fuller", "hangglider", "ductedfan", "discrete_oed"])
+def test_adaptive_parity_other_models(name):
+    """forward-mode-AD models and an OED variant in adaptive mode"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(79)
+    if name == "vdp":
+        spec, row, scale = P.vdp_spec(5, rng), 3, 0.05
+    elif name == "discrete_oed":
+        spec = dict(P.lotka_oed_spec(shooting_points=[0.0, 3.0, 6.0, 9.0], fishing=rng.uniform(0, 1, 48)))
+        spec.update(model="lotka2_oed_ds", u0=[0.5, 0.7] + [0.0] * 4)
+        spec.pop("fim", None)
+        row, scale = 1, 0.02
+    else:
+        spec, row, scale = P.bench_spec(name, 3 if name == "ductedfan" else 4)
+    spec = dict(spec, kwargs=dict(abstol=1e-8, reltol=1e-6))
+    from oracle import pyoracle as po
+    O = po.OracleLayer(spec)
+    ps = O.default_ps()[None, :] * (1.0 + scale * rng.standard_normal((5, O.nvars))) + scale * rng.standard_normal((5, O.nvars))
+    assert_ok(full_compare(spec, cb.Tsit5(adaptive=True), 5, rng, objective_row=row, ps=ps))
+
+
+def test_adaptive_failures_are_flagged_and_terminate():
+    """a candidate whose integration cannot proceed (non-finite input; an explosive right-hand side that drives the
+    step below resolution) ends with the status flag set instead of spinning; its neighbours are unaffected"""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    lay, ps_t, st = _layer(dict(P.lotka_spec(), kwargs=CORE))
+    N = lay._native(st, ps_t)
+    X = np.tile(cb.to_vec(ps_t), (4, 1))
+    X[1, 5] = np.nan
+    X[2, N.block_structure()[1]] = 1e200          # node value: x' ~ -x y overflows at once
+    r = N.eval_host(X, nat.WANT_XEND | nat.WANT_DEFECTS)
+    assert list(r["status"] != 0) == [False, True, True, False]
+    assert np.array_equal(r["xend"][0], r["xend"][3]) and np.isfinite(r["xend"][0]).all()
