@@ -186,7 +186,8 @@ __device__ __forceinline__ float cb_fastlog2(float x)
 }
 __device__ __forceinline__ double cb_fastpow(double x, double y)
 {
-    return x == 0.0 ? 0.0 : (double)exp2f(__fmul_rn((float)y, cb_fastlog2((float)x)));
+    // exp2 of the Float32 product, rounded to Float32 (through double: correctly rounded, as Julia's exp2(::Float32) is to < 1 ulp)
+    return x == 0.0 ? 0.0 : (double)(float)exp2((double)__fmul_rn((float)y, cb_fastlog2((float)x)));
 }
 
 template <class Mdl, int G>

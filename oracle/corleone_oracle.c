@@ -655,7 +655,7 @@ static double co_fastpow(double x, double y)
 {
     if (x == 0.0) return 0.0;
     volatile float e = (float)y * co_fastlog2((float)x);
-    return (double)exp2f(e);
+    return (double)(float)exp2((double)e); /* Float32 result, correctly rounded */
 }
 static double rms_state(const double *v, int n)
 {

@@ -98,6 +98,9 @@ def test_adaptive_oed_fisher_information_parity(shooting):
     X = np.tile(x0, (B, 1))
     X[:, -(24 + 79):] = rng.uniform(0, 1, (B, 24 + 79))            # the measurement weights of the last block(s)
     r = N.eval_host(X, nat.WANT_FIM | nat.WANT_XEND | nat.WANT_SENS)
+    # at reltol = 1e-3 the controller's Float32 powers quantise the step size (a last-bit difference in the error
+    # estimate moves a step by 6e-8 relative): two implementations agree to ~1e-5 reltol, not to 1e-10
+    RTOL = 1e-8
     for b in range(B):
         o = O.eval(X[b], method="tsit5_adaptive")
         assert rel_err(r["xend"][b].reshape(O.I, O.nx).T, o["xend"]) <= RTOL

@@ -1,0 +1,117 @@
+#!/usr/bin/env python
+"""Randomised parity sweep on a GPU: random layers (model, number of shooting intervals, non-uniform and mutually
+different control grids, tunable initial conditions, quadrature indices), random method (Tsit5 / RK4 fixed step, adaptive
+Tsit5), random batch sizes -- every output of cb200_eval against the CPU checker.
+
+    python tools/fuzz_parity.py [--cases 60] [--seed 0]
+
+Prints one line per case and a summary; exit code 1 if any case exceeds 1e-10 (test infrastructure: uses oracle/)."""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def random_spec(rng):
+    import problems as P
+    kind = rng.choice(["lotka3", "lqr", "lotka2", "bench", "bench", "oed"])
+    if kind == "bench":
+        name = str(rng.choice(sorted(P.BENCH_TABLE)))
+        spec, row, scale = P.bench_spec(name, int(rng.integers(1, 5)), rng)
+        if spec["shooting_points"] is not None and len(spec["shooting_points"]) == 1:
+            spec["shooting_points"] = None
+        return name, spec, row, scale
+    if kind == "oed":
+        n = int(rng.integers(2, 6))
+        sp = None if n == 2 else [12.0 * k / n for k in range(n)]
+        spec = P.lotka_oed_spec(shooting_points=sp, fishing=rng.uniform(0, 1, 48), w=float(rng.uniform(0.2, 1.0)))
+        spec.pop("fim", None)
+        return "lotka2_oed", spec, int(rng.integers(1, 10)), 0.02
+    # hand-written models on random non-uniform grids
+    T = 12.0 if kind != "lqr" else 3.0
+    n = int(rng.integers(3, 40))
+    # random points on top of a coarse regular grid: no piece longer than 0.5, so that the fixed-step methods stay
+    # inside their stability region (an overflowing trajectory compares NaN with NaN and says nothing)
+    grid = np.unique(np.r_[np.arange(0.0, T, 0.5), np.round(np.sort(rng.uniform(0, T, n)), 3)])
+    grid = grid[grid < T]
+    nshoot = int(rng.integers(1, 6))
+    sp = None if nshoot == 1 else list(np.unique(np.r_[0.0, np.round(np.sort(rng.uniform(0.2, T - 0.2, nshoot - 1)), 2)]))
+    if sp is not None:
+        # a control needs a value on every interval (the reference indexes ps.controls[1] of an empty vector otherwise,
+        # the library rejects such a layer in cb200_create): one grid point inside each interval, not at its start
+        edges = np.r_[sp, T]
+        extra = [a + (b - a) * float(rng.uniform(0.1, 0.9)) for a, b in zip(edges[:-1], edges[1:])]
+        grid = np.unique(np.r_[grid, np.round(extra, 4)])
+    if kind == "lotka3":
+        quad = bool(rng.integers(0, 2))
+        tic = [] if rng.integers(0, 2) else [int(k) for k in np.sort(rng.choice([1, 2], int(rng.integers(1, 3)), replace=False))]
+        spec = dict(model="lotka3", u0=[0.5, 0.7, 0.0], p0=[0.0, 1.0, 1.0], tspan=(0.0, T),
+                    controls=[(1, grid, rng.uniform(0, 1, len(grid)))], tunable_ic=tic,
+                    quadrature_indices=[3] if quad else [], shooting_points=sp)
+        return "lotka3", spec, 3, 0.05
+    if kind == "lqr":
+        spec = dict(model="lqr", u0=[1.0, 0.0], p0=[-1.0, 1.0, 0.0], tspan=(0.0, T),
+                    controls=[(3, grid, rng.standard_normal(len(grid)))], tunable_ic=[],
+                    quadrature_indices=[2] if rng.integers(0, 2) else [], shooting_points=sp)
+        return "lqr", spec, 2, 0.05
+    spec = dict(model="lotka2", u0=[0.5, 0.7], p0=[0.0, 1.0, 1.0], tspan=(0.0, T),
+                controls=[(1, grid, rng.uniform(0, 1, len(grid)))], tunable_ic=[1, 2] if rng.integers(0, 2) else [],
+                quadrature_indices=[], shooting_points=sp)
+    return "lotka2", spec, int(rng.integers(1, 3)), 0.05
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cases", type=int, default=60)
+    ap.add_argument("--seed", type=int, default=0)
+    a = ap.parse_args()
+    import corleone_b200 as cb
+    import test_gpu_parity as T
+    rng = np.random.default_rng(a.seed)
+    worst, bad, t0 = 0.0, [], time.time()
+    for c in range(a.cases):
+        name, spec, row, scale = random_spec(rng)
+        m = int(rng.integers(0, 3))
+        alg = [cb.Tsit5(int(rng.integers(1, 5))), cb.RK4(int(rng.integers(2, 6))), cb.Tsit5(adaptive=True)][m]
+        if m == 2:
+            tol = float(10.0 ** rng.uniform(-9, -4))
+            spec = dict(spec, kwargs=dict(abstol=tol * 1e-2, reltol=tol))
+        B = int(rng.choice([1, 2, 3, 31, 33, 64, 70]))
+        from oracle import pyoracle as po
+        O = po.OracleLayer(spec)
+        ps = O.default_ps()[None, :] * (1.0 + scale * rng.standard_normal((B, O.nvars))) + scale * rng.standard_normal((B, O.nvars))
+        meth = ["tsit5", "rk4", "tsit5_adaptive"][m]
+        if m == 2:
+            po.set_tolerances(spec["kwargs"]["abstol"], spec["kwargs"]["reltol"])
+        if not all(np.isfinite(O.eval(p, method=meth, K=alg.steps_per_piece)["xend"]).all() for p in ps):
+            print(f"case {c:3d} {name:18s} skipped: the drawn step size is outside the method's stability region", flush=True)
+            continue
+        try:
+            errs = T.full_compare(spec, alg, B, rng, objective_row=row, ps=ps)
+            e = max(errs.values())
+        except Exception as ex:      # noqa: BLE001 -- report and go on
+            import traceback
+            e, errs = float("inf"), {"exception": repr(ex)[:200], "trace": traceback.format_exc()[-600:]}
+        # adaptive stepping: the controller takes its powers in Float32, so a last-bit difference in the error estimate
+        # can move a step by 6e-8 relative; with a local error of the order of reltol that bounds the agreement of two
+        # implementations at ~1e-5 reltol (the tight-tolerance goldens are still met to 1e-14)
+        bound = 1e-10 if m != 2 else max(1e-10, 1e-5 * spec["kwargs"]["reltol"])
+        worst = max(worst, e / bound * 1e-10)
+        if not e <= bound:
+            bad.append((c, name, errs))
+        tag = ['tsit5', 'rk4', 'adaptive'][m] + (f"({spec['kwargs']['reltol']:.0e})" if m == 2 else "")
+        print(f"case {c:3d} {name:18s} I={O.I} nvars={O.nvars:4d} B={B:3d} method={tag:15s} max err {e:.2e}", flush=True)
+    print(f"fuzz_parity: {a.cases} cases, worst {worst:.2e} (scaled to the 1e-10 bound), {len(bad)} above their bound, {time.time() - t0:.0f} s")
+    for b in bad:
+        print("  BAD", b)
+    sys.exit(1 if bad else 0)
+
+
+if __name__ == "__main__":
+    main()
