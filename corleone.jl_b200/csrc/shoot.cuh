@@ -168,7 +168,7 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
 
 // ---- method 2: adaptive Tsit5, the reference's default mode (`solve(problem, Tsit5(); ...)` per control piece with the
 // problem's abstol / reltol, src/single_shooting.jl:443-453).  OrdinaryDiffEq's stepping restated from its published
-// algorithm (DESIGN.md section 3 has the long form and the pin on the reference's golden vectors): Hairer's initial-step
+// algorithm (has the long form and the pin on the reference's golden vectors): Hairer's initial-step
 // heuristic, embedded 4th-order error estimate in the RMS norm, PI controller with the Float32 `fastpow`, steps clipped
 // to the end of the piece; every piece starts over.  The step sequence is decided by the STATE components only; the
 // thread's sensitivity directions ride along on it (all direction groups of a unit therefore take identical steps).

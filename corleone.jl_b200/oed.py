@@ -179,6 +179,44 @@ class OEDLayer:
         F = r["fim"].reshape(X.shape[0], self.n_fisher, self.n_fisher)
         return (F, r["criteria"]) if criteria else F
 
+    # ---- read-outs of the saved samples (oed.jl:464-534), batched: X (B, nvars)
+    def _samples(self, X, ps_like, st):
+        nat = self.native(ps_like, st)
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        r = nat.eval_host(X, native.WANT_TRAJ)
+        return r["traj"].reshape(X.shape[0], nat.n_samples, nat.n_row)
+
+    def sensitivities(self, X, ps_like, st):
+        """sensitivities(oed, traj) (oed.jl:464-470): G(t_k) = dx/dp at every saved sample, (B, n_samples, nx_base, n_fisher)"""
+        tr = self._samples(X, ps_like, st)
+        bx, nf = self.base_nx, self.n_fisher
+        G = tr[..., bx:bx + bx * nf].reshape(tr.shape[:-1] + (nf, bx))       # vec(G) is column-major
+        return np.swapaxes(G, -1, -2)
+
+    def observed_equations(self, X, ps_like, st):
+        """observed_equations(oed, traj) (oed.jl:481-488): the observed functions = the leading states, (B, n_samples, n_obs)"""
+        return self._samples(X, ps_like, st)[..., :max(self.n_obs, OED_BASE[self.model.split("_oed")[0]][1])]
+
+    def local_information_gain(self, X, ps_like, st):
+        """local_information_gain (oed.jl:500-510): (h_i G(t_k))'(h_i G(t_k)) per sample and observed function"""
+        from .criteria import local_information_gain
+        nobs = OED_BASE[self.model.split("_oed")[0]][1]
+        return local_information_gain(self._samples(X, ps_like, st), self.base_nx, self.n_fisher, nobs)
+
+    def global_information_gain(self, X, ps_like, st):
+        """global_information_gain (oed.jl:520-534): the same with rows scaled by inv(F(t_f)), F from the layer's read-out"""
+        from .criteria import global_information_gain
+        nobs = OED_BASE[self.model.split("_oed")[0]][1]
+        F = self.fisher_information(X, ps_like, st)
+        return global_information_gain(self._samples(X, ps_like, st), F, self.base_nx, self.n_fisher, nobs)
+
+    def update_fim(self, experiments, st):
+        """update_fim (oed.jl:166-186): fold finished experiments (flat candidates, rows of `experiments`) into F_init"""
+        first = st if self.single else next(iter(st.values()))
+        F = self.fisher_information(experiments["X"], experiments["ps"], experiments["st"], add_initial=False)
+        first["F_init"] = first["F_init"] + F.sum(axis=0)
+        return st
+
     def fisher_gradient(self, X, ps_like, st, add_initial: bool = True):
         """F (B, n, n) and dF/d(flat variables) (B, n, n, nvars) -- what ForwardDiff through `fisher_information` yields.
         One cb200_eval per call: the samples and their sensitivities (CB200_WANT_TRAJ_SENS) come from the device, the

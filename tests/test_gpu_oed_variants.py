@@ -250,3 +250,37 @@ def test_design_optimum_of_the_1d_problem_fixed_continuous_and_discrete():
     best = np.sort(np.argsort(g2)[-20:])
     assert res.fun <= 1.0 / g2[best].sum() * (1 + 1e-6) or abs(res.fun - 1.0 / g2[best].sum()) <= 1e-3 / g2[best].sum()
     assert abs(o.fisher_information(res.x[None, :], ps, st)[0, 0, 0] - 1.0 / res.fun) <= 1e-9 / res.fun
+
+
+def test_sample_readouts_sensitivities_observed_and_information_gains():
+    """sensitivities / observed_equations / local and global information gain (oed.jl:464-534) for a batch, against the
+    oracle's samples; summing the local gains with the design weights gives the discrete layer's Fisher information"""
+    from oracle import pyoracle as po
+    o = oedm.OEDLayer(lotka_base(None, K=2), True, measurements(0.6))
+    ps, st = o.setup(None)
+    O = po.OracleLayer(_oracle_spec(o, ps))
+    rng = np.random.default_rng(23)
+    X = cb.to_vec(ps)[None, :] + 0.02 * rng.standard_normal((3, len(cb.to_vec(ps))))
+    G = o.sensitivities(X, ps, st)
+    obs = o.observed_equations(X, ps, st)
+    L = o.local_information_gain(X, ps, st)
+    Gl = o.global_information_gain(X, ps, st)
+    F = o.fisher_information(X, ps, st)
+    for b in range(3):
+        u = O.eval(X[b], K=2)["u"]
+        assert rel_err(obs[b].T, u[:2]) <= RTOL
+        for s in (0, 7, u.shape[1] - 1):
+            Gs = u[2:6, s].reshape(2, 2).T
+            assert rel_err(G[b, s], Gs) <= RTOL
+            for i in range(2):
+                assert rel_err(L[b, s, i], np.outer(Gs[i], Gs[i])) <= RTOL
+                x = Gs[i] @ np.linalg.inv(F[b])
+                assert rel_err(Gl[b, s, i], np.outer(x, x)) <= 1e-9
+        # discrete layer: F = sum_s sum_i w_is^2 (local gain)
+        pd = cb.from_vec(X[b], ps)
+        W = np.where(st["observation_grid"] > 0, pd["controls"][np.maximum(st["observation_grid"], 1) - 1], 0.0)
+        assert rel_err(np.einsum("si,siab->ab", W ** 2, L[b]), F[b]) <= 1e-12
+    # update_fim folds finished experiments into F_init
+    F0 = o.fisher_information(X[:1], ps, st)[0]
+    o.update_fim(dict(X=X[1:], ps=ps, st=st), st)
+    assert rel_err(o.fisher_information(X[:1], ps, st)[0], F0 + F[1] + F[2]) <= 1e-13
