@@ -12,8 +12,17 @@
 #include <string>
 #include <vector>
 
+#include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges around every C-ABI call (no cost without a profiler attached)
+
 #include "common.cuh"
 #include "tableau.cuh"
+
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
+}  // namespace
 
 using namespace cb200;
 
@@ -610,6 +619,7 @@ static size_t push(std::vector<char> &blob, const std::vector<T> &v)
 
 extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
 {
+    NvtxRange nvtx_range("cb200_create");
     if (!d || !out) return fail(CB200_ERR_ARG, "null argument");
     *out = nullptr;
     if (d->struct_size != (int32_t)sizeof(cb200_desc))
@@ -1107,6 +1117,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
 
 extern "C" int cb200_destroy(cb200_handle *h)
 {
+    NvtxRange nvtx_range("cb200_destroy");
     if (!h) return CB200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
@@ -1365,6 +1376,7 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
 extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t ldb, uint32_t want, uint32_t flags,
                           const cb200_out *out)
 {
+    NvtxRange nvtx_range("cb200_eval");
     if (!h || !out) return fail(CB200_ERR_ARG, "null argument");
     if (B < 0) return fail(CB200_ERR_ARG, "negative batch");
     if (B == 0) return CB200_OK;
@@ -1692,6 +1704,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
 extern "C" int cb200_forward_init(cb200_handle *h, double *ps, int64_t B, int64_t ldb, uint32_t flags,
                                   const int32_t *fixed_indices, int32_t n_fixed)
 {
+    NvtxRange nvtx_range("cb200_forward_init");
     if (!h || (!ps && h->L.nvars > 0)) return fail(CB200_ERR_ARG, "null argument");
     if (B < 0 || n_fixed < 0 || (n_fixed > 0 && !fixed_indices)) return fail(CB200_ERR_ARG, "bad argument");
     if (B == 0 || h->L.nvars == 0) return CB200_OK;
