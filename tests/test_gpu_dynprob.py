@@ -107,3 +107,32 @@ def test_lotka_oed_design_optimum():
     Fgold = np.array([[38.58695777364362, 5.304118558316029], [5.304118558316029, 92.03122059902915]])
     assert np.allclose(res.fim, Fgold, rtol=1e-5), res.fim                                        # measured: 1e-7
     assert np.all(A @ res.x <= 4.0 + 1e-8)
+
+
+def test_reference_example_callbacks_in_the_default_adaptive_mode():
+    """test/examples/lotka_ms.jl:45-48,76-79 and lotka_oc.jl:80 with the integration mode the reference runs them in
+    (adaptive Tsit5, abstol 1e-8 / reltol 1e-6): optprob.f and optprob.f.cons at the initial point to all printed digits,
+    and the optimum of the single-shooting example"""
+    import corleone_b200 as cb
+
+    def layer(shooting_points, **kw):
+        spec = dict(P.lotka_spec(shooting_points=shooting_points), kwargs=dict(abstol=1.0e-8, reltol=1.0e-6))
+        spec["control_names"] = ["fishing"]
+        spec["control_bounds"] = [(0.0, 1.0)]
+        return P.product_layer(spec, cb.Tsit5(adaptive=True), bounds_p=([1.0, 1.0], [1.0, 1.0]), **kw)
+
+    bic = ([0.1, 0.1, 0.0], [100.0, 100.0, 100.0])
+    prob = cb.CorleoneDynamicOptProblem(layer([0.0, 3.0, 6.0, 9.0], bounds_ic=bic), "x₃")
+    assert abs(prob.objective(prob.u0) - 1.2417260108009376) <= 2e-14
+    gold = np.array([1.3757549609694821, 0.2235735751355118, 1.24172601080094, 1.375754960969481, 0.22357357513551102,
+                     1.2417260108009385, 1.3757549609694824, 0.2235735751355129, 1.2417260108009414] + [0.0] * 6)
+    assert np.max(np.abs(prob.constraints(prob.u0) - gold)) <= 2e-14
+    probq = cb.CorleoneDynamicOptProblem(layer([0.0, 3.0, 6.0, 9.0], bounds_ic=bic, quadrature_indices=[3]), "x₃")
+    assert abs(probq.objective(probq.u0) - 4 * 1.2417260108009376) <= 5e-14
+    goldq = np.array([1.3757549609694821, 0.2235735751355118, 1.375754960969481, 0.22357357513551102,
+                      1.3757549609694824, 0.2235735751355129] + [0.0] * 6)
+    assert np.max(np.abs(probq.constraints(probq.u0) - goldq)) <= 2e-14
+    ss = cb.CorleoneDynamicOptProblem(layer(None), "x₃")
+    assert abs(ss.objective(ss.u0) - 6.062277454291031) <= 5e-14
+    res = cb.solve_slsqp(ss, maxiter=400, ftol=1e-12)
+    assert res.success and abs(res.fun - 1.344336) < 1e-4
