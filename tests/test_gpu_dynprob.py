@@ -136,3 +136,25 @@ def test_reference_example_callbacks_in_the_default_adaptive_mode():
     assert abs(ss.objective(ss.u0) - 6.062277454291031) <= 5e-14
     res = cb.solve_slsqp(ss, maxiter=400, ftol=1e-12)
     assert res.success and abs(res.fun - 1.344336) < 1e-4
+
+
+def test_lotka_oed_design_optimum_in_the_default_adaptive_mode():
+    """the same design problem integrated as the reference integrates it (adaptive Tsit5 at the default tolerances):
+    the initial A-criterion to 1e-13 and the optimum `_uopt.objective ≈ 0.03707508955468313` (lotka_oed.jl:124,140-145)"""
+    import corleone_b200 as cb
+    spec = P.lotka_oed_spec()
+    spec["control_bounds"] = [(0.0, 1.0)] * 3
+    lay = P.product_layer(spec, cb.Tsit5(adaptive=True), bounds_p=([1.0, 1.0], [1.0, 1.0]))
+    ps_t, st = cb.setup(None, lay)
+    st["_fim"] = (7, 2)
+    N = lay._native(st, ps_t)
+    crit, _ = cb.batched_criteria(N, cb.to_vec(ps_t)[None, :])
+    assert abs(crit[0, 0] / 0.05352869250783344 - 1) <= 1e-13
+    A = cb.sampling_sum_matrix(lay, st, ps_t, [1, 2])
+    res = cb.solve_oed_slsqp(lay, st, ps_t, N, criterion=0, M=[4.0, 4.0], measurement_rows=(1, 2), maxiter=600)
+    dev = res.fun / 0.03707508955468313 - 1
+    print("adaptive design optimum: relative deviation from the reference's", dev)
+    assert abs(dev) < 1e-6, (res.fun, res.message)
+    Fgold = np.array([[38.58695777364362, 5.304118558316029], [5.304118558316029, 92.03122059902915]])
+    assert np.allclose(res.fim, Fgold, rtol=1e-5), res.fim
+    assert np.all(A @ res.x <= 4.0 + 1e-8)
