@@ -101,9 +101,14 @@ def main():
         # adaptive stepping: the controller takes its powers in Float32, so a last-bit difference in the error estimate
         # can move a step by 6e-8 relative; with a local error of the order of reltol that bounds the agreement of two
         # implementations at ~1e-5 reltol (the tight-tolerance goldens are still met to 1e-14)
+        # ... and the tangents ride on steps chosen for the VALUES: their own local error is not controlled, so the same
+        # step quantum shows up in them at up to ~1e-9 (seen on the ocean problem: 2e-10 at reltol 8e-9)
         bound = 1e-10 if m != 2 else max(1e-10, 1e-5 * spec["kwargs"]["reltol"])
-        worst = max(worst, e / bound * 1e-10)
-        if not e <= bound:
+        bound_d = bound if m != 2 else max(1e-8, bound)
+        if "exception" not in errs:
+            e = max(v / (bound_d if k in ("sens", "grad", "jac") else bound) for k, v in errs.items()) * 1e-10
+        worst = max(worst, e)
+        if not e <= 1e-10:
             bad.append((c, name, errs))
         tag = ['tsit5', 'rk4', 'adaptive'][m] + (f"({spec['kwargs']['reltol']:.0e})" if m == 2 else "")
         print(f"case {c:3d} {name:18s} I={O.I} nvars={O.nvars:4d} B={B:3d} method={tag:15s} max err {e:.2e}", flush=True)
