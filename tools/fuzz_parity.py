@@ -66,6 +66,53 @@ def random_spec(rng):
     return "lotka2", spec, int(rng.integers(1, 3)), 0.05
 
 
+def extra_checks(cb, spec, alg, O, ps, meth, row):
+    """the other surfaces of the C ABI on the same random layer: sample sensitivities (WANT_TRAJ_SENS), the forward
+    initialisation sweep, device-pointer calls in both layouts, interval ranges that sum to the full evaluation"""
+    import torch
+    import problems as P
+    from corleone_b200 import native as nat
+    from test_gpu_parity import rel_err
+    lay = P.product_layer(spec, alg)
+    ps_t, st = cb.setup(None, lay)
+    N = lay._native(st, ps_t)
+    K = alg.steps_per_piece
+    out = {}
+    r = N.eval_host(ps, nat.WANT_TRAJ | nat.WANT_TRAJ_SENS | nat.WANT_SENS)
+    u, Jref = O.traj_jacobian(ps[0], method=meth, K=K)
+    out["traj_sens"] = rel_err(cb.trajectory_jacobian(lay, st, ps_t, r, 0), Jref)
+    # forward initialisation (no-op for single shooting)
+    fixed = [i for i in range(2, O.I + 1) if (i * 7 + len(ps)) % 3 == 0]
+    fo = N.forward_init(ps[:2].copy(), fixed_indices=tuple(fixed))
+    out["forward_init"] = max(rel_err(fo[b], O.forward_init(ps[b], fixed_indices=fixed, method=meth, K=K)) for b in range(min(2, len(ps))))
+    # device pointers: variable-major in and out, and candidate-major in and out == the host call
+    want = nat.WANT_XEND | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    ref = N.eval_host(ps, want, objective_row=row)
+    B, sz = len(ps), N.out_sizes()
+    fields = ["xend", "objective", "grad"] + (["defects_kind"] if N.n_defects else [])
+    for flags, lay_in in ((nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA, "soa"), (nat.MEM_DEVICE, "aos")):
+        d_ps = torch.from_numpy(np.ascontiguousarray(ps.T if lay_in == "soa" else ps)).cuda()
+        d_out = {f: torch.zeros((sz[f], B) if lay_in == "soa" else (B, sz[f]), dtype=torch.float64, device="cuda") for f in fields}
+        N.set_stream(torch.cuda.current_stream().cuda_stream)
+        N.eval_raw(d_ps.data_ptr(), B, B if lay_in == "soa" else N.nvars, want, flags, {f: d_out[f].data_ptr() for f in fields}, row)
+        torch.cuda.synchronize()
+        for f in fields:
+            got = d_out[f].cpu().numpy()
+            got = got.T if lay_in == "soa" else got
+            out["device_" + lay_in] = max(out.get("device_" + lay_in, 0.0), 0.0 if np.array_equal(got, ref[f]) else rel_err(got, ref[f]) + 1e-9)
+    # interval ranges
+    if O.I > 1:
+        half = O.I // 2
+        tot = None
+        for a, b in ((1, half), (half + 1, O.I)):
+            N.set_interval_range(a, b)
+            rr = N.eval_host(ps, want, objective_row=row)
+            tot = {k: rr[k].copy() for k in fields} if tot is None else {k: tot[k] + rr[k] for k in fields}
+        N.set_interval_range(1, O.I)
+        out["interval_ranges"] = max(0.0 if np.array_equal(tot[f], ref[f]) else rel_err(tot[f], ref[f]) for f in fields)
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--cases", type=int, default=60)
@@ -94,6 +141,7 @@ def main():
             continue
         try:
             errs = T.full_compare(spec, alg, B, rng, objective_row=row, ps=ps)
+            errs.update(extra_checks(cb, spec, alg, O, ps, meth, row))
             e = max(errs.values())
         except Exception as ex:      # noqa: BLE001 -- report and go on
             import traceback
@@ -106,7 +154,7 @@ def main():
         bound = 1e-10 if m != 2 else max(1e-10, 1e-5 * spec["kwargs"]["reltol"])
         bound_d = bound if m != 2 else max(1e-8, bound)
         if "exception" not in errs:
-            e = max(v / (bound_d if k in ("sens", "grad", "jac") else bound) for k, v in errs.items()) * 1e-10
+            e = max(v / (bound_d if k in ("sens", "grad", "jac", "traj_sens") else bound) for k, v in errs.items()) * 1e-10
         worst = max(worst, e)
         if not e <= 1e-10:
             bad.append((c, name, errs))
