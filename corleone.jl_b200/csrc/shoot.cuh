@@ -786,11 +786,11 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
         if (method > 1) return -1000;   /* no adaptive instantiation of this model */       \
         return method == 0 ? launch_one<Mdl, Gv, 0, CB200_MB(MBv)>(L, ps, ldb, B, o, s)   \
                            : launch_one<Mdl, Gv, 1, CB200_MB(MBv)>(L, ps, ldb, B, o, s);
-// ... plus method 2, adaptive Tsit5 (one block per SM register budget: it is not a throughput path)
+// ... plus method 2, adaptive Tsit5 (128-register budget: 0.537 vs 0.556 ms at 255 registers, profiles/README.md)
 #define CB200_DISPATCH_GA(Mdl, Gv, MBv)                                                     \
     case Gv:                                                                                \
         return method == 0   ? launch_one<Mdl, Gv, 0, CB200_MB(MBv)>(L, ps, ldb, B, o, s) \
                : method == 1 ? launch_one<Mdl, Gv, 1, CB200_MB(MBv)>(L, ps, ldb, B, o, s) \
-                             : launch_one<Mdl, Gv, 2, 1>(L, ps, ldb, B, o, s);
+                             : launch_one<Mdl, Gv, 2, 4>(L, ps, ldb, B, o, s);
 
 }  // namespace cb200
