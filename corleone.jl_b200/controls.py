@@ -48,10 +48,25 @@ class ControlParameter:
         return f"ControlParameter({self.name!r}, {len(self.t)} points)"
 
 
+_SORTED = {}   # id(array) -> (array, is it non-decreasing?): a layer asks for the same grid once per shooting interval
+
+
+def _is_sorted(t: np.ndarray) -> bool:
+    hit = _SORTED.get(id(t))
+    if hit is None or hit[0] is not t:
+        if len(_SORTED) > 256:
+            _SORTED.clear()
+        hit = _SORTED[id(t)] = (t, bool(np.all(t[1:] >= t[:-1])) and not np.isnan(t).any())
+    return hit[1]
+
+
 def _restrict(t: np.ndarray, tspan) -> np.ndarray:
-    """findall(tspan[1] .<= t .< tspan[2])  (0-based positions; local_controls.jl:55)"""
+    """findall(tspan[1] .<= t .< tspan[2])  (0-based positions; local_controls.jl:55).  On a sorted grid the positions
+    are one contiguous run found by bisection -- a layer with I intervals would otherwise scan the grid I times."""
     if tspan is None:
         return np.arange(len(t))
+    if len(t) > 64 and _is_sorted(t):
+        return np.arange(np.searchsorted(t, tspan[0], side="left"), np.searchsorted(t, tspan[1], side="left"))
     return np.nonzero((tspan[0] <= t) & (t < tspan[1]))[0]
 
 

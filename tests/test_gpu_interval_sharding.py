@@ -93,3 +93,33 @@ def test_control_row_objective_and_rejections():
         N.set_interval_range(3, 5)
     N.set_interval_range(1, N.I)
     assert N.eval_host(X, nat.WANT_TRAJ)["traj"].shape == (1, N.n_samples * N.n_row)
+
+
+def test_more_than_65535_intervals_flat_launch_equals_ranged_grid_launches():
+    """a long horizon: 66 000 shooting intervals exceed gridDim.y, so the kernel runs with a flat thread index; two
+    interval ranges of 33 000 each run with the regular (candidate tiles, interval, direction group) grid -- their
+    sum is bit-identical to the flat evaluation"""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    rng = np.random.default_rng(10)
+    lay, ps_t, st, N = _setup(P.lqr_spec(66000, rng), cb.Tsit5(2))
+    assert N.I == 66000 and N.nvars == 527998
+    B = 40
+    X = np.tile(cb.to_vec(ps_t), (B, 1))
+    X += 0.05 * rng.standard_normal(X.shape)
+    want = nat.WANT_XEND | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    full = N.eval_host(X, want, objective_row=2)
+    assert np.isfinite(full["xend"]).all() and not full["status"].any()
+    tot = _assemble(N, X, want, 2, [(1, 33000), (33001, 66000)])
+    for k in ("xend", "defects_kind", "defects_stage", "grad"):
+        assert np.array_equal(tot[k], full[k]), k
+    assert np.allclose(tot["objective"], full["objective"], rtol=1e-12, atol=0)
+    # the closed form of the LQR state over one interval pins the values themselves: x' = a x + b u, piecewise constant u
+    ps = cb.from_vec(X[0], ps_t)
+    i = 41234
+    blk = ps[f"interval_{i + 1}"]
+    a, b = blk["p"]
+    x = blk["u0"][0]
+    for u in blk["controls"]:
+        x = np.exp(a * 0.03) * x + b * u * (np.exp(a * 0.03) - 1.0) / a
+    assert abs(full["xend"][0].reshape(N.I, 2)[i, 0] - x) <= 1e-9 * max(1.0, abs(x))
