@@ -1022,7 +1022,7 @@ co_layer *co_layer_create(const co_problem *P)
     (void)allc;
 
     /* shooting intervals: sort!(unique!(vcat(tpoints, tspan))) -> consecutive pairs (multiple_shooting.jl:86-90) */
-    double pts[4096];
+    double *pts = (double *)malloc(sizeof(double) * (size_t)(P->n_shoot + 2));
     int np = 0;
     for (int k = 0; k < P->n_shoot; k++) pts[np++] = P->shoot_pts[k];
     pts[np++] = P->tspan[0];
@@ -1047,6 +1047,10 @@ co_layer *co_layer_create(const co_problem *P)
             it->grid = (double *)malloc(sizeof(double) * (size_t)(cap + 1));
             it->idx = (int64_t *)malloc(sizeof(int64_t) * (size_t)(L->nact * cap));
             it->M = co_build_index_grid(L->nact, act_t, act_nt, it->t0, it->t1, it->idx, it->grid, cap);
+            if (it->M > 0) { /* keep what the interval uses, not room for every grid point of every control */
+                it->grid = (double *)realloc(it->grid, sizeof(double) * (size_t)(it->M + 1));
+                it->idx = (int64_t *)realloc(it->idx, sizeof(int64_t) * (size_t)(L->nact * it->M));
+            }
         } else {
             /* no controls: tspans = (problem.tspan,) -- the *problem's* span, also on sub-intervals
              * (single_shooting.jl:329-332; reference quirk kept) */
@@ -1102,6 +1106,7 @@ co_layer *co_layer_create(const co_problem *P)
         L->nsamples += L->iv[i].M;
         if (i > 0) L->ndef += L->iv[i].n_sidx + L->ntp;
     }
+    free(pts);
     return L;
 }
 
