@@ -825,7 +825,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     // direction tables of the sensitivity kernel: the p column every local variable perturbs and, per piece
     // and direction group, the mask of directions whose forcing term f_p / f_u is switched on
     std::vector<signed char> dir_pcol((size_t)std::max(1, L.nvars), (signed char)-1);
-    std::vector<short> dir_perm((size_t)std::max(1, L.nvars), (short)-1);
+    std::vector<int> dir_perm((size_t)std::max(1, L.nvars), -1);
     const int Gs = h->G_sens;
     const int Rmask = Gs > 0 ? std::max(1, (h->max_ns + Gs - 1) / Gs) : 1;
     std::vector<unsigned> act_mask((size_t)po * Rmask, 0u);
@@ -859,7 +859,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return first[a] < first[b]; });
         for (int sl = 0; sl < nsi; sl++) {
             const int dd = order[sl];
-            dir_perm[(size_t)vof + sl] = (short)dd;
+            dir_perm[(size_t)vof + sl] = dd;
             if (Gs <= 0) continue;
             const int pc = dir_pcol[(size_t)vof + dd];
             for (int j = 0; j < M; j++) {
@@ -1075,7 +1075,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.tsens_off = (const long long *)(base + o_tse);
     L.samp_off = (const int *)(base + o_so);
     L.dir_pcol = (const signed char *)(base + o_dp);
-    L.dir_perm = (const short *)(base + o_dperm);
+    L.dir_perm = (const int *)(base + o_dperm);
     L.act_mask = (const unsigned *)(base + o_am);
     L.dpos_kind = (const int *)(base + o_dk);
     L.dpos_stage = (const int *)(base + o_dst);

@@ -41,7 +41,7 @@ struct DevLayer {
     const long long *tsens_off;  // [I] first row of the interval's block in `traj_sens`
     const double *model_data;  // model constants in HBM (DENSE20: W row-major 20x20, then b[20]) or nullptr
     const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
-    const short *dir_perm;        // [nvars] direction held by slot s of the interval (activation order, see shoot.cuh)
+    const int *dir_perm;          // [nvars] direction held by slot s of the interval (activation order, see shoot.cuh)
     const unsigned *act_mask;     // [sum M][R] bits 0..23: slot r*G+g is forced during the piece (G = handle's group size);
                                   //            bits 24..31: live prefix length of the group
     // shooting defects of the boundary between interval i and i+1 (src/multiple_shooting.jl:150-163)
