@@ -22,6 +22,12 @@ struct NvtxRange {
     explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
     ~NvtxRange() { nvtxRangePop(); }
 };
+struct D20Slot {
+    int refs = 0;
+    double data[420];
+};
+std::mutex g_d20_mu;
+D20Slot g_d20[64];   // per device ordinal
 }  // namespace
 
 using namespace cb200;
@@ -384,6 +390,7 @@ struct cb200_handle {
     int fim_mode = 0, fim_bx = 0, n_obs = 0, n_obs_rows = 0;   // sample-based read-outs
     int *d_obs_sample = nullptr, *d_obs_var = nullptr;
     int range_i0 = 0, range_n = -1;   // cb200_set_interval_range: intervals [i0, i0 + n); n < 0 = all
+    bool d20_ref = false;             // holds a reference on the device's DENSE20 constant block
     int G_sens = 2;                   // sensitivity directions per thread
     void *tables = nullptr;           // one device allocation holding every table
     int *d_quad = nullptr;
@@ -1091,6 +1098,18 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
             cb200_destroy(h);
             return fail(CB200_ERR_ARG, "DENSE20 needs model_data of 420 doubles (W row-major, then b)");
         }
+        {   // the thread-per-direction kernels read W, b from ONE __constant__ block per device: live DENSE20 handles on
+            // a device must share their data (the tensor-path kernel reads the handle's own table and has no such limit)
+            std::lock_guard<std::mutex> lk(g_d20_mu);
+            D20Slot &slot = g_d20[d->device & 63];
+            if (slot.refs > 0 && memcmp(slot.data, d->model_data, sizeof slot.data) != 0) {
+                cb200_destroy(h);
+                return fail(CB200_ERR_UNSUPPORTED, "another DENSE20 layer with different model_data is alive on device %d", d->device);
+            }
+            memcpy(slot.data, d->model_data, sizeof slot.data);
+            slot.refs++;
+            h->d20_ref = true;
+        }
         int rc = dense20_set_data(d->model_data, d->model_data_len);
         if (rc != 0) return bail("cudaMemcpyToSymbol(dense20)", (cudaError_t)rc);
     }
@@ -1121,6 +1140,11 @@ extern "C" int cb200_destroy(cb200_handle *h)
     if (!h) return CB200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->d20_ref) {
+        std::lock_guard<std::mutex> lk(g_d20_mu);
+        g_d20[h->device & 63].refs--;
+        h->d20_ref = false;
+    }
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,
                       &h->ws_grad, &h->ws_fim, &h->ws_finit, &h->ws_out, &h->ws_sums, &h->ws_objq, &h->ws_jac, &h->ws_crit, &h->ws_fixed, &h->ws_status, &h->ws_small, &h->ws_gradc, &h->ws_tsens})
         b->release();

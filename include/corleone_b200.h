@@ -141,7 +141,8 @@ typedef struct {
     const int64_t *ic_constants;        /* [sum ic_n_constants] InitialConditionRemaker.constants, 1-based */
     const int32_t *n_shooting_indices;  /* [I] */
     const int64_t *shooting_indices;    /* [sum] st.shooting_indices, 1-based over [states; controls] */
-    const double *model_data;           /* model constants (DENSE20: W row-major 20x20, then b[20]) or NULL */
+    const double *model_data;           /* model constants (DENSE20: W row-major 20x20, then b[20]) or NULL.  Live DENSE20
+                                           handles on one device must carry the same data (one __constant__ block) */
     int64_t model_data_len;
     /* sample-based Fisher read-outs (fim_mode != 0); G = the nx_base x fim_n block behind the base states, the
        observed functions are the leading n_observed base states */

@@ -519,3 +519,29 @@ def test_trajectory_sensitivities_for_point_constraints(name):
         assert rel_err(r["traj"][b].reshape(O.nsamples, O.nrow).T, u) <= RTOL
         J = cb.trajectory_jacobian(lay, st, ps_t, r, b)
         assert rel_err(J, Jref) <= RTOL
+
+
+def test_dense20_layers_on_one_device_share_their_constant_block():
+    """the thread-per-direction dense kernels read W, b from one __constant__ block per device: a second live layer with
+    DIFFERENT data is refused (it would silently change the first one's values-only evaluations), identical data and
+    sequential use are fine"""
+    import gc
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    gc.collect()
+    spec = P.dense20_spec(2)
+    lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2))
+    lay2, ps2, st2, N2 = P.native_from_spec(P.dense20_spec(3), cb.Tsit5(2))        # same data: accepted
+    other = dict(spec, model_data=np.asarray(spec["model_data"]) * 1.5)
+    with pytest.raises(nat.NativeError, match="different model_data"):
+        P.native_from_spec(other, cb.Tsit5(2))
+    x = cb.to_vec(ps_t)[None, :]
+    ref = N.eval_host(x, nat.WANT_XEND)["xend"].copy()
+    N.close(); N2.close()
+    for s in (st, st2):
+        for v in (s.values() if "tspans" not in s else [s]):
+            v.pop("_native", None)
+    gc.collect()
+    lay3, ps3, st3, N3 = P.native_from_spec(other, cb.Tsit5(2))                     # alone on the device: accepted
+    assert not np.array_equal(N3.eval_host(x, nat.WANT_XEND)["xend"], ref)
+    N3.close()
