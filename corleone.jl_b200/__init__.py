@@ -26,7 +26,7 @@ from .criteria import (ACriterion, DCriterion, ECriterion, FisherACriterion, Fis
                        batched_criteria, criteria_gradient, global_information_gain, local_information_gain,
                        sampling_sum_matrix, solve_oed_slsqp)
 from . import oed
-from .oed import OEDLayer
+from .oed import MultiExperimentLayer, OEDLayer
 
 
 def setup(rng, layer):

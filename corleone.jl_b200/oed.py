@@ -305,6 +305,81 @@ class OEDLayer:
         return out
 
 
+class MultiExperimentLayer:
+    """MultiExperimentLayer{DISCRETE}(prob, alg, nexp; ...) (lib/CorleoneOED/src/multiexperiments.jl:9-16,66-74,88-91): `n_exp`
+    experiments of ONE OED layer, jointly designed; parameters and states are grouped by experiment (`experiment_i`), the
+    Fisher information is the sum over the experiments plus F_init of the first (:279-303).
+
+    On the device the experiment axis is just more of the batch axis: a batch of B joint designs is evaluated as
+    B * n_exp candidates of the underlying layer in ONE cb200_eval and summed per design.  The variant that splits the
+    parameter set among the experiments (:76-86,94-107) needs one augmentation per parameter subset and is not compiled
+    in."""
+
+    def __init__(self, oed: OEDLayer, n_exp: int):
+        if n_exp < 1:
+            raise ValueError("n_exp must be >= 1")
+        self.layers, self.n_exp = oed, int(n_exp)
+        self.names = [f"experiment_{i + 1}" for i in range(self.n_exp)]
+
+    def __repr__(self):
+        o = self.layers
+        return (f"{'Fixed ' if o.FIXED else ''}MultiExperimentLayer with {'discrete' if o.DISCRETE else 'continuous'} "
+                f"measurement model and {self.n_exp} experiments.")
+
+    def n_observed(self):
+        return self.n_exp * self.layers.n_observed()                                         # (:189)
+
+    def initialparameters(self, rng):
+        return {k: self.layers.initialparameters(rng) for k in self.names}                   # (:120-124)
+
+    def initialstates(self, rng):
+        return {k: self.layers.initialstates(rng) for k in self.names}                       # (:166-170)
+
+    def setup(self, rng):
+        return self.initialparameters(rng), self.initialstates(rng)
+
+    def get_bounds(self):
+        from .multiple_shooting import get_bounds
+        lo, hi = get_bounds(self.layers.layer)
+        return {k: lo for k in self.names}, {k: hi for k in self.names}                      # (:318-324)
+
+    def get_block_structure(self):
+        from .multiple_shooting import get_block_structure
+        b = np.asarray(get_block_structure(self.layers.layer), dtype=np.int64)               # (:339-351)
+        return np.concatenate([b if i == 0 else b[1:] + i * b[-1] for i in range(self.n_exp)])
+
+    def get_number_of_shooting_constraints(self, ps, st):
+        if self.layers.single:
+            return 0
+        from .multiple_shooting import get_number_of_shooting_constraints
+        k = self.names[0]
+        return self.n_exp * get_number_of_shooting_constraints(self.layers.layer, ps[k], st[k])   # (:190)
+
+    def get_sampling_sums(self, ps, st):
+        return np.concatenate([self.layers.get_sampling_sums(ps[k], st[k]) for k in self.names])   # (:249-255)
+
+    def fisher_information(self, X, ps_like, st, add_initial: bool = True):
+        """X: (B, n_exp * nvars) joint designs, experiments in order.  Returns F (B, n, n) = F_init + sum_e F_e (:279-289)."""
+        k0 = self.names[0]
+        X = np.atleast_2d(np.asarray(X, dtype=np.float64))
+        nv = len(to_vec(ps_like[k0]))
+        assert X.shape[1] == self.n_exp * nv, (X.shape, self.n_exp, nv)
+        F = self.layers.fisher_information(X.reshape(X.shape[0] * self.n_exp, nv), ps_like[k0], st[k0], add_initial=False)
+        F = F.reshape(X.shape[0], self.n_exp, *F.shape[1:]).sum(axis=1)
+        if add_initial:
+            first = st[k0] if self.layers.single else next(iter(st[k0].values()))
+            F = F + first["F_init"]
+        return F
+
+    def update_fim(self, experiments, st):
+        """update_fim (:195-221): fold finished joint designs (rows of experiments["X"]) into F_init of the first experiment"""
+        k0 = self.names[0]
+        first = st[k0] if self.layers.single else next(iter(st[k0].values()))
+        F = self.fisher_information(experiments["X"], experiments["ps"], experiments["st"], add_initial=False)
+        first["F_init"] = first["F_init"] + F.sum(axis=0)
+        return st
+
+
 def sampling_sum_matrix(oed: OEDLayer, ps_like, st) -> np.ndarray:
     """get_sampling_sums is linear in the variables for every variant: its matrix (n_observed, nvars)."""
     from .single_shooting import from_vec

@@ -284,3 +284,27 @@ def test_sample_readouts_sensitivities_observed_and_information_gains():
     F0 = o.fisher_information(X[:1], ps, st)[0]
     o.update_fim(dict(X=X[1:], ps=ps, st=st), st)
     assert rel_err(o.fisher_information(X[:1], ps, st)[0], F0 + F[1] + F[2]) <= 1e-13
+
+
+@pytest.mark.parametrize("discrete", [False, True])
+def test_multi_experiment_fisher_information_is_the_sum_over_experiments(discrete):
+    """MultiExperimentLayer (multiexperiments.jl:279-289): F = F_init + sum_e F_e, a batch of joint designs evaluated as
+    B * n_exp candidates in one call; update_fim folds finished designs into F_init (:195-221)"""
+    o = oedm.OEDLayer(lotka_base(None, K=2), discrete, measurements(0.8))
+    m = cb.MultiExperimentLayer(o, 3)
+    ps, st = m.setup(None)
+    rng = np.random.default_rng(29)
+    nv = len(cb.to_vec(ps["experiment_1"]))
+    X = np.tile(cb.to_vec(ps), (4, 1))
+    X[:, :] += 0.0
+    for e in range(3):      # different fishing controls and weights per experiment
+        X[:, e * nv + 2:(e + 1) * nv] = rng.uniform(0, 1, (4, nv - 2))
+    F_init = np.array([[0.2, 0.05], [0.05, 0.1]])
+    st["experiment_1"]["F_init"] = F_init
+    F = m.fisher_information(X, ps, st)
+    for b in range(4):
+        parts = [o.fisher_information(X[b, e * nv:(e + 1) * nv][None, :], ps["experiment_1"], st["experiment_1"],
+                                      add_initial=False)[0] for e in range(3)]
+        assert rel_err(F[b], F_init + sum(parts)) <= 1e-13
+    m.update_fim(dict(X=X[2:], ps=ps, st=st), st)
+    assert rel_err(st["experiment_1"]["F_init"], F_init + (F[2] - F_init) + (F[3] - F_init)) <= 1e-13

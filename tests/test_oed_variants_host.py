@@ -146,3 +146,24 @@ def test_cut_pieces_equal_uncut_pieces_with_proportionally_more_steps():
     b = pyoracle.OracleLayer(_oracle_spec(uncut, ps_u)).eval(cb.to_vec(ps_u), K=8)
     assert a["u"].shape[1] == 49 and b["u"].shape[1] == 13
     assert np.array_equal(a["u"][:6, ::4], b["u"][:6, :])
+
+
+def test_multi_experiment_layer_structure():
+    """lib/CorleoneOED/test/core/lotka_oed.jl:154-247 (the variant with one parameter set for all experiments): grouping
+    by experiment, block structure, bounds, sampling sums per experiment"""
+    for shooting in (None, (0.0, 3.0, 6.0, 9.0)):
+        for discrete in (False, True):
+            m = cb.MultiExperimentLayer(oedm.OEDLayer(lotka_base(shooting), discrete, measurements()), 2)
+            ps, st = m.setup(None)
+            assert list(ps) == list(st) == ["experiment_1", "experiment_2"]
+            nv = len(cb.to_vec(ps["experiment_1"]))
+            assert len(cb.to_vec(ps)) == 2 * nv
+            b1 = cb.get_block_structure(m.layers.layer)
+            assert np.array_equal(m.get_block_structure(), np.r_[b1, b1[1:] + b1[-1]])
+            lo, hi = m.get_bounds()
+            assert np.array_equal(cb.to_vec(lo), np.tile(cb.to_vec(cb.get_bounds(m.layers.layer)[0]), 2))
+            sums = m.get_sampling_sums(ps, st)
+            assert np.allclose(sums, [24.0, 79.0, 24.0, 79.0] if discrete else [12.0] * 4, rtol=0, atol=1e-12)   # :230
+            assert m.n_observed() == 4
+            # per experiment: 3 nodes x (states + 2 tunable parameters), states = 9 ([x; G; F]) or 6 ([x; G])
+            assert m.get_number_of_shooting_constraints(ps, st) == (0 if shooting is None else 2 * 3 * ((6 if discrete else 9) + 2))
