@@ -645,6 +645,10 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         if (!(d->abstol > 0.0) || !(d->reltol > 0.0)) return fail(CB200_ERR_ARG, "adaptive Tsit5 needs abstol > 0 and reltol > 0");
     }
     if (d->n_intervals < 1) return fail(CB200_ERR_ARG, "n_intervals must be >= 1");
+    if (!d->u0 || !d->n_pieces || !d->tspans || !d->n_u0 || !d->n_local_controls || !d->is_shooting || !d->ic_sorting ||
+        !d->ic_n_constants || !d->n_shooting_indices || (d->n_controls > 0 && (!d->index_grid || !d->control_indices)) ||
+        (d->n_tunable_p > 0 && !d->tunable_p) || (d->n_quadrature > 0 && !d->quadrature_indices))
+        return fail(CB200_ERR_ARG, "a required table pointer of cb200_desc is NULL");
     if (d->n_controls < 0 || d->n_controls > MAX_CTRL) return fail(CB200_ERR_ARG, "n_controls out of range");
     if (d->np_all > MAX_NP) return fail(CB200_ERR_ARG, "np_all too large");
     if (d->n_tunable_p + d->n_controls != d->np_all)

@@ -46,6 +46,15 @@ def test_bad_descriptor_is_rejected_before_any_device_work():
     d.struct_size = ctypes.sizeof(native.Desc)
     d.model = 99
     assert L.cb200_create(ctypes.byref(d), ctypes.byref(h)) == -3
+    # consistent sizes but no tables: refused with a message, not a segfault
+    d.model, d.nx, d.np_all, d.n_tunable_p, d.n_controls, d.n_intervals, d.steps_per_piece = 4, 1, 1, 1, 0, 1, 1
+    assert L.cb200_create(ctypes.byref(d), ctypes.byref(h)) == -1
+    assert b"NULL" in L.cb200_last_error()
+    # adaptive mode needs positive tolerances; unknown method ids are refused
+    d.method, d.abstol, d.reltol = 2, 0.0, 1e-3
+    assert L.cb200_create(ctypes.byref(d), ctypes.byref(h)) == -1 and b"abstol" in L.cb200_last_error()
+    d.method = 7
+    assert L.cb200_create(ctypes.byref(d), ctypes.byref(h)) == -3
 
 
 def test_no_cpu_fallback():
