@@ -94,17 +94,38 @@ class ODEProblem:
         return ODEProblem(**d)
 
 
-@dataclass(frozen=True)
 class Tsit5:
-    """Tsitouras 5(4).  Fixed step (default): `steps_per_piece` steps h = (t1-t0)/K on every control piece -- the
-    `adaptive=false, dt=h` mode.  `adaptive=True`: the reference's default mode, OrdinaryDiffEq's step-size control with
-    the problem's `abstol` / `reltol` keyword arguments (ODEProblem(...; abstol, reltol); defaults 1e-6 / 1e-3)."""
-    steps_per_piece: int = 1
-    adaptive: bool = False
+    """Tsitouras 5(4).
+
+    Tsit5()                    the reference's own call: adaptive, OrdinaryDiffEq's step-size control with the problem's
+                               `abstol` / `reltol` keyword arguments (ODEProblem(...; abstol, reltol); defaults 1e-6 / 1e-3)
+    Tsit5(K) / Tsit5(steps_per_piece=K)
+                               fixed step: K steps h = (t1-t0)/K on every control piece -- `adaptive=false, dt=h`, the mode
+                               BASELINE.json benchmarks
+    Tsit5(adaptive=True)       adaptive, explicitly"""
+
+    def __init__(self, steps_per_piece: int | None = None, adaptive: bool | None = None):
+        if adaptive is None:
+            adaptive = steps_per_piece is None
+        if adaptive and steps_per_piece not in (None, 1):
+            raise ValueError("steps_per_piece has no meaning for the adaptive mode")
+        self.steps_per_piece = 1 if steps_per_piece is None else int(steps_per_piece)
+        self.adaptive = bool(adaptive)
+        if self.steps_per_piece < 1:
+            raise ValueError("steps_per_piece must be >= 1")
 
     @property
     def method_id(self) -> int:
         return 2 if self.adaptive else 0
+
+    def __repr__(self):
+        return "Tsit5()" if self.adaptive else f"Tsit5(steps_per_piece={self.steps_per_piece})"
+
+    def __eq__(self, other):
+        return isinstance(other, Tsit5) and (self.steps_per_piece, self.adaptive) == (other.steps_per_piece, other.adaptive)
+
+    def __hash__(self):
+        return hash(("Tsit5", self.steps_per_piece, self.adaptive))
 
 
 @dataclass(frozen=True)
