@@ -3,7 +3,7 @@
 different control grids, tunable initial conditions, quadrature indices), random method (Tsit5 / RK4 fixed step, adaptive
 Tsit5), random batch sizes -- every output of cb200_eval against the CPU checker.
 
-    python tools/fuzz_parity.py [--cases 60] [--seed 0]
+    python tests/fuzz_parity.py [--cases 60] [--seed 0]
 
 Prints one line per case and a summary; exit code 1 if any case exceeds 1e-10 (test infrastructure: uses oracle/)."""
 import argparse
@@ -15,7 +15,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))   # lives with the tests: it uses the CPU checker under oracle/
 
 
 def random_spec(rng):
