@@ -79,6 +79,11 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f)).read()
                 assert "oracle" not in txt.lower() or f == "configs.py", f"{f} mentions the oracle"
+    # measurement helpers are not tests either: nothing under tools/ may import the checker
+    for f in os.listdir(os.path.join(ROOT, "tools")):
+        if f.endswith((".py", ".sh")):
+            txt = open(os.path.join(ROOT, "tools", f)).read()
+            assert "pyoracle" not in txt and "from oracle" not in txt and "import oracle" not in txt, f"tools/{f} uses the oracle"
 
 
 def _build_c_client(tmp_path):
