@@ -38,7 +38,7 @@ NZ = NX * (1 + NS_DIRS)
 FLOPS_PER_UNIT = E_EVALS * (10 + 36) + M_PIECES * K_STEPS_PER_PIECE * 42 * NZ      # 8440
 #   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic (BASELINE.md formula)
 BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                                # 240
-NCU_DRAM_BYTES_PER_LAUNCH = 27219712 + 16570368   # profiles/r1_shoot_lqr_G4_fused.txt
+NCU_DRAM_BYTES_PER_LAUNCH = 26944000 + 17881344   # profiles/r1_shoot_lqr_G4_fused.txt
 
 
 try:
