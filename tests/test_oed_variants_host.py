@@ -167,3 +167,24 @@ def test_multi_experiment_layer_structure():
             assert m.n_observed() == 4
             # per experiment: 3 nodes x (states + 2 tunable parameters), states = 9 ([x; G; F]) or 6 ([x; G])
             assert m.get_number_of_shooting_constraints(ps, st) == (0 if shooting is None else 2 * 3 * ((6 if discrete else 9) + 2))
+
+
+@pytest.mark.parametrize("discrete", [False, True])
+@pytest.mark.parametrize("fixed", [False, True])
+def test_multiexperiments_case_1_of_the_reference_test(discrete, fixed):
+    """lib/CorleoneOED/test/core/lotka_oed.jl:154-247, the branch `split = false, shooting = false`: two experiments over
+    the same parameter set; sampling sums, bounds and block structure exactly as the reference asserts them (:228-240)"""
+    num_exp = 2
+    g = 0.25 * np.arange(48)
+    meas = [cb.ControlParameter(g, controls=np.ones(48), bounds=(0.0, 1.0)) for _ in range(2)]
+    multi = cb.MultiExperimentLayer(oedm.OEDLayer(lotka_base(None, fixed=fixed), discrete, meas), num_exp)
+    ps, st = multi.setup(None)
+    res = multi.get_sampling_sums(ps, st)
+    assert np.array_equal(res, [48.0] * 4) if discrete else np.allclose(res, [12.0] * 4, rtol=0, atol=1e-12)
+    lb, ub = multi.get_bounds()
+    head = [0.0] if fixed else []
+    assert np.array_equal(cb.to_vec(lb), np.tile(np.r_[head, np.ones(2), np.zeros(2 * 48 if fixed else 3 * 48)], num_exp))
+    assert np.array_equal(cb.to_vec(ub), np.tile(np.r_[head, np.ones(2), np.ones(2 * 48 if fixed else 3 * 48)], num_exp))
+    blocks = multi.get_block_structure()
+    per = 3 + 48 * 2 if fixed else 2 + 48 * 3
+    assert np.array_equal(blocks, np.r_[0, np.cumsum([per] * num_exp)])
