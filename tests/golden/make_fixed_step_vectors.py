@@ -1,5 +1,5 @@
 #!/usr/bin/env python
-"""Generate tests/golden/fixed_step_vectors.json: fixed-step input/output vectors of the hot path computed by the
+"""Generate tests/golden/fixed_step_vectors.json: fixed-step (and one adaptive) input/output vectors of the hot path computed by the
 CPU oracle (oracle/corleone_oracle.c) on seeded inputs.  The reference itself is Julia and cannot run in the
 build container, so these are ORACLE outputs (the oracle is pinned on the reference's own goldens in
 tests/test_oracle_golden.py); committing them guards against the oracle and the CUDA path drifting together.
@@ -27,6 +27,9 @@ def case(name, spec_fn, method, K, B, seed, objective_row, scale=0.05):
     ps = O.default_ps()[None, :] + scale * rng.standard_normal((B, O.nvars))
     out = dict(name=name, method=method, K=K, seed=seed, objective_row=objective_row, scale=scale, B=B,
                nvars=O.nvars, ps=ps.tolist(), xend=[], defk=[], defs=[], objective=[], grad=[], sens_blocks=[])
+    if method == "tsit5_adaptive":   # the reference's default mode at the tolerances of its core tests
+        out.update(abstol=1.0e-8, reltol=1.0e-6)
+        po.set_tolerances(out["abstol"], out["reltol"])
     blocks = O.block_structure()
     for b in range(B):
         o = O.eval(ps[b], method=method, K=K)
@@ -50,6 +53,7 @@ CASES = [
     ("lqr_ms10_tsit5", lambda r: P.lqr_spec(10, r), "tsit5", 2, 2, 103, 2),
     ("egerstedt_ss_tsit5", lambda r: P.egerstedt_spec(), "tsit5", 2, 2, 104, 3),
     ("dense20_ms3_tsit5", lambda r: P.dense20_spec(3, r), "tsit5", 2, 2, 105, 1),
+    ("lotka_ms4_adaptive", lambda r: P.lotka_spec(controls=r.uniform(0, 1, 120)), "tsit5_adaptive", 1, 2, 106, 3),
 ]
 
 if __name__ == "__main__":
