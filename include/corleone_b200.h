@@ -232,7 +232,9 @@ typedef struct {
     double *grad_compact;
     double *traj_sens;
     int32_t *status;            /* [B] failure flags per candidate (always filled when non-NULL): bit 0 = a non-finite
-                                   end state on some interval.  The reference never inspects the solver's retcode. */
+                                   end state on some interval (in the adaptive mode also: more than 1e5 steps in a piece or a
+                                   step below resolution -- OrdinaryDiffEq's MaxIters / DtLessThanMin / Unstable).  The reference
+                                   never inspects the solver's retcode. */
 } cb200_out;
 
 typedef struct {
