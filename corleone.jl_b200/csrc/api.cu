@@ -1573,18 +1573,19 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             if (it.on && it.user) out_doubles += (size_t)it.n * (size_t)B;
         const size_t sums_doubles = (size_t)(pl.osum ? 1 : 0) + (pl.gsum ? (size_t)nvars : 0) + (pl.fsum ? (size_t)n2 : 0);
         const size_t in_doubles = (size_t)nvars * (size_t)B;
-        const size_t tot = sizeof(double) * (out_doubles + sums_doubles + in_doubles) + sizeof(int) * (size_t)B;
+        const size_t status_doubles = out->status ? ((size_t)B * sizeof(int) + sizeof(double) - 1) / sizeof(double) : 0;
+        const size_t tot = sizeof(double) * (out_doubles + sums_doubles + in_doubles + status_doubles);
         if (ps_soa && out_soa && ldb == B && tot <= cb200_handle::PIN_BYTES) {
             if (!h->pin) CUDA_TRY(cudaHostAlloc(&h->pin, cb200_handle::PIN_BYTES, cudaHostAllocDefault));
             if (h->ws_small.reserve(tot)) return fail(CB200_ERR_NOMEM, "device out of memory");
             double *hp = (double *)h->pin, *dp = (double *)h->ws_small.p;
-            // layout (doubles): [inputs | results ... | sums] then the status ints
-            if (in_doubles) {
-                memcpy(hp, ps, sizeof(double) * in_doubles);
-                CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * in_doubles, cudaMemcpyHostToDevice, h->stream));
-            }
+            // layout (doubles): [inputs | status ints (zeroed on the host: they travel with the inputs) | results ... | sums]
+            if (in_doubles) memcpy(hp, ps, sizeof(double) * in_doubles);
+            if (status_doubles) memset(hp + in_doubles, 0, sizeof(double) * status_doubles);
+            if (in_doubles + status_doubles)
+                CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * (in_doubles + status_doubles), cudaMemcpyHostToDevice, h->stream));
             DevSet d = shared;
-            size_t off = in_doubles;
+            size_t off = in_doubles + status_doubles;
             for (const Item &it : items) {
                 if (!it.on) continue;
                 if (it.user) {
@@ -1600,17 +1601,14 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             if (pl.gsum) { d.gsum = dp + off; off += (size_t)nvars; }
             if (pl.fsum) { d.fsum = dp + off; off += (size_t)n2; }
             if (sums_doubles) CUDA_TRY(cudaMemsetAsync(dp + sums_off, 0, sizeof(double) * sums_doubles, h->stream));
-            int *d_status = (int *)(dp + off);
-            if (out->status) {
-                d.status = d_status;
-                CUDA_TRY(cudaMemsetAsync(d_status, 0, sizeof(int) * (size_t)B, h->stream));
-            }
+            if (out->status) d.status = (int *)(dp + in_doubles);
             int rc = eval_core(h, h->stream, in_doubles ? dp : nullptr, B, B, pl, d);
             if (rc) return rc;
-            const size_t back = sizeof(double) * (off - in_doubles) + (out->status ? sizeof(int) * (size_t)B : 0);
+            const size_t back = sizeof(double) * (off - in_doubles);
             if (back) CUDA_TRY(cudaMemcpyAsync(hp + in_doubles, dp + in_doubles, back, cudaMemcpyDeviceToHost, h->stream));
             CUDA_TRY(cudaStreamSynchronize(h->stream));
-            size_t o2 = in_doubles;
+            if (out->status) memcpy(out->status, hp + in_doubles, sizeof(int) * (size_t)B);
+            size_t o2 = in_doubles + status_doubles;
             for (const Item &it : items) {
                 if (!it.on || !it.user) continue;
                 memcpy(it.user, hp + o2, sizeof(double) * (size_t)it.n * (size_t)B);
@@ -1619,7 +1617,6 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             if (pl.osum) { *out->objective_sum = hp[o2]; o2 += 1; }
             if (pl.gsum) { memcpy(out->grad_sum, hp + o2, sizeof(double) * (size_t)nvars); o2 += (size_t)nvars; }
             if (pl.fsum) { memcpy(out->fim_sum, hp + o2, sizeof(double) * (size_t)n2); o2 += (size_t)n2; }
-            if (out->status) memcpy(out->status, hp + o2, sizeof(int) * (size_t)B);
             return CB200_OK;
         }
     }
