@@ -156,8 +156,12 @@ def build_index_grid(*controls: ControlParameter, offset: bool = True, tspan=(-n
 
 
 def find_shooting_indices(tspan, control: ControlParameter) -> bool:
-    """local_controls.jl:180"""
-    return bool(np.any(tspan[0] == control.t))
+    """local_controls.jl:180: any(tspan[1] .== control.t) -- by bisection on a sorted grid"""
+    t = control.t
+    if len(t) > 64 and _is_sorted(t):
+        k = int(np.searchsorted(t, tspan[0], side="left"))
+        return bool(k < len(t) and t[k] == tspan[0])
+    return bool(np.any(tspan[0] == t))
 
 
 def collect_tspans(*controls: ControlParameter, tspan=(-np.inf, np.inf), subdivide: int = INT64_MAX):
