@@ -4,14 +4,19 @@
     python bench.py --gpus N --steps K --warmup W            our arm (one process per GPU under torchrun)
     python bench.py --impl reference --gpus N --steps K ...   the restated reference CPU path on the host cores
 
-Workload (N=1): BASELINE.json configs[1] = `lqr_ms100_b4096`: linear-quadratic regulator, 100 shooting
-intervals x 4096 candidates, Tsit5 with 2 fixed steps per control piece (M = 4 pieces per interval), full
-forward sensitivities (ns = 8 directions per interval).  One unit = one (interval, candidate) system.
-A step = one pass of the hot path over the batch: integration + sensitivities of every unit, delivered as what
-the reference's NLP callbacks consume (src/dynprob.jl:68-73,105-131,143-164): objective f, gradient grad f,
-shooting constraints c (kind-major, the order dynprob uses) and the nonzeros of the constraint Jacobian cons_j
-(grad f without its structural zeros: the objective state of the last interval depends on that interval's block only).  Weak scaling: every rank owns B candidates;
-only the cross-candidate sums (objective, gradient) are all-reduced (DESIGN.md "multi-GPU").
+One unit = one (interval, candidate) system: integrate [x; S] across the interval's control pieces and emit the end
+state, the sensitivities and the shooting defect.  One step = one pass of the hot path over the whole batch.
+
+N = 1   headline = BASELINE.json configs[3] `dense20_256x65k`, the largest single-GPU configuration (BASELINE.json
+        quotes the metric on no particular config): synthetic 20-state problem x' = W x - x^3 + b u, 256 shooting
+        intervals x 65 536 candidates, Tsit5 with K = 2 fixed steps on each of the M = 4 control pieces, the FULL
+        sensitivity Jacobian (ns = 24 directions, nz = 500) -- 16.8 M units, 64 GB of sensitivities resident in HBM.
+        `all_configs` carries configs 1 (latency), 2, 3 and 4, each with kernel time, roofline and e2e.
+N > 1   BASELINE.json configs[4] `scale_1M`: 256 intervals x 4096 candidates of the same model = 2^20 units, STRONG
+        scaling: the candidate axis is sharded over the ranks; inside the timed region every step ends with
+        allreduce(objective_sum, grad_sum) and allgather(defects) over NVLink -- fused into the evaluation's own
+        kernels through the library's communicator (cb200_comm_*, P2P windows), not NCCL calls from the host.
+        `secondary` keeps the config-2 weak-scaling number of round 1.
 """
 import argparse
 import json
@@ -26,20 +31,21 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-WORKLOAD = "lqr_ms100_b4096"
-I_INTERVALS, B_PER_GPU, K_STEPS_PER_PIECE, M_PIECES, NS_DIRS, NX = 100, 4096, 2, 4, 8, 2
-OBJECTIVE_ROW = 2   # x2 = accumulated cost (examples/linear_quadratic/main.jl:49, loss = :x2)
+METRIC = "shooting-interval solves+sensitivities/sec (FP64)"
 
-# Algorithmic work per unit (DESIGN.md "roofline"):
+# ---- algorithmic work per unit (DESIGN.md "roofline"):
 #   E = M (6K + 1) RHS evaluations (Tsit5, FSAL re-seeded at every piece start)
-#   W = E (C_f + C_JS) + M K 42 nz,  nz = nx (1 + ns);   LQR: C_f = 10, C_JS = 2 nnz(J) ns + nnz(f_p,f_u) = 36
-E_EVALS = M_PIECES * (6 * K_STEPS_PER_PIECE + 1)
-NZ = NX * (1 + NS_DIRS)
-FLOPS_PER_UNIT = E_EVALS * (10 + 36) + M_PIECES * K_STEPS_PER_PIECE * 42 * NZ      # 8440
-#   Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes of compulsory HBM traffic (BASELINE.md formula)
-BYTES_PER_UNIT = 8 * (NX + 2 + M_PIECES + NZ + 4 + 0)                                # 240
-NCU_DRAM_BYTES_PER_LAUNCH = 26944000 + 17881344   # profiles/r1_shoot_lqr_G4_fused.txt
-
+#   W = E (C_f + C_JS + C_F) + M K 42 nz flop;  Q = 8 (nz_in + np + nc_i + nz_out + n_defect + n_obj) bytes
+WORK = {
+    # config 4/5: M = 4, K = 2: E = 52; C_f = 2*400 + 80; C_JS = 2*400*24 + 3*20*24; nz = 20 * 25
+    "dense20": dict(flops=52 * (880 + 20640) + 4 * 2 * 42 * 500, bytes=8 * (20 + 4 + 500 + 20)),
+    # config 2: M = 4, K = 2: E = 52; C_f = 10, C_JS = 36; nz = 2 * 9
+    "lqr": dict(flops=52 * (10 + 36) + 4 * 2 * 42 * 18, bytes=8 * (2 + 2 + 4 + 18 + 4)),
+    # config 3: M = 2, K = 2: E = 26; C_f + C_JS + C_F = 51; nz = 9 (SURVEY.md 8d worked example)
+    "lotka_oed": dict(flops=26 * 51 + 2 * 2 * 42 * 9, bytes=8 * (9 + 3 + 6 + 9 + 9)),
+    # config 1: M = 5, K = 4: E = 125; Lotka3: C_f = 20, C_JS = 2*6*10 + 6; nz = 3 * 11
+    "lotka_ms24": dict(flops=125 * (20 + 126) + 5 * 4 * 42 * 33, bytes=8 * (3 + 2 + 5 + 33 + 3 + 1)),
+}
 
 try:
     ORIG_AFFINITY = os.sched_getaffinity(0)      # before bind_to_gpu_numa_node narrows it
@@ -57,7 +63,7 @@ def host_threads():
 
 def bind_to_gpu_numa_node(index):
     """Run this rank on the CPU cores next to its GPU (NVML's ideal affinity) BEFORE any pinned host buffer is
-    allocated: the e2e arm moves 117 MB per step over PCIe, and first-touch places the buffers on the local node."""
+    allocated: first touch places the buffers on the local node."""
     try:
         import pynvml
         pynvml.nvmlInit()
@@ -78,8 +84,19 @@ def load_peaks():
     if os.path.exists(p):
         with open(p) as f:
             d = json.load(f)
-        return d.get("hbm_gbs", 6650.0), "measured"
-    return 6650.0, "fallback"
+        return d.get("hbm_gbs", 6650.0), "MEASURED_PEAKS.json (measured)"
+    return 6650.0, "B200_PROFILING.md fallback (MEASURED_PEAKS.json absent)"
+
+
+def ncu_traffic(kernel_key):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the config's dominant kernel, from the committed
+    ncu --set full capture (profiles/r2_traffic.json: value, workload of the capture, file, date) -- or None."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel_key)
+    except Exception:
+        return None
 
 
 class ClockSampler:
@@ -139,12 +156,23 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_inputs(nvars, ps0, B, rng):
+# ================================================================================================== workloads
+def dense20_inputs_soa(torch, dev, ps0, B, seed):
+    """[nvars, B] on the device: every node and control value of the template perturbed by 0.1 N(0,1)
+    (x0 ~ U[-1,1], u ~ U[-1,1] in the template)"""
+    g = torch.Generator(device=dev)
+    g.manual_seed(seed)
+    base = torch.from_numpy(np.asarray(ps0)).to(dev)
+    x = torch.randn((len(ps0), B), dtype=torch.float64, device=dev, generator=g)
+    x.mul_(0.1).add_(base[:, None])
+    return x
+
+
+def lqr_inputs(nvars, ps0, B, rng, n_intervals=100):
     """candidate matrix (B, nvars): nodes x ~ U[0,4], cost node 0, controls N(0,1)"""
     ps = np.tile(ps0, (B, 1))
-    # layout per interval (u0 (0 or 2), p (2), controls (4)); interval 1 has no u0
     off = 0
-    for i in range(I_INTERVALS):
+    for i in range(n_intervals):
         nu0 = 0 if i == 0 else 2
         if nu0:
             ps[:, off] = rng.uniform(0, 4, B)
@@ -155,50 +183,332 @@ def make_inputs(nvars, ps0, B, rng):
     return ps
 
 
-def cpu_baseline(spec, ps, seconds_target=12.0, nthreads=0):
-    """The oracle port timed on the host cores on a bounded sample of the same workload (~seconds_target of
-    CPU work: whole passes over the batch, repeated)."""
+def oed_inputs(N, ps0, B, rng, n_intervals=64):
+    ps = np.tile(ps0, (B, 1))
+    blocks = N.block_structure()
+    pp = rng.uniform(0.8, 1.2, (B, 2))
+    for i in range(n_intervals):
+        nu0 = 0 if i == 0 else 9
+        ps[:, blocks[i] + nu0: blocks[i] + nu0 + 2] = pp
+    return ps
+
+
+def fp64_peak(nat, dev_index):
+    """FP64 roof measured in this run: DFMA and DMMA share one datapath on B200 (tools/dmma_micro.cu), the higher probe is
+    the peak.  MEASURED_PEAKS.json (driver-written) carries HBM and bf16 figures only."""
+    a = nat.probe_fp64_tflops(dev_index, 40000)
+    b = nat.probe_fp64_mma_tflops(dev_index, 20000)
+    return max(a, b), (f"FP64 probes measured in this run, max of DFMA chains ({a:.2f}) and mma.sync.m8n8k4.f64 ({b:.2f}) "
+                       "TFLOP/s (nominal 148 SM x 64 FMA/clk x 2 x 1.965 GHz = 37.2); MEASURED_PEAKS.json has no FP64 figure")
+
+
+def roofline_entry(work, units, kern_ms, peak, peak_src, hbm_peak, hbm_src, kernel, traffic_key):
+    ach = work["flops"] * units / (kern_ms * 1e-3) / 1e12
+    gbs = work["bytes"] * units / (kern_ms * 1e-3) / 1e9
+    tr = ncu_traffic(traffic_key)
+    return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
+            "traffic": tr["bytes_per_launch"] if tr else None,
+            "traffic_source": (f"{tr['file']} ({tr['date']}; ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one "
+                               f"launch on {tr['workload']})") if tr else None,
+            "algorithmic_bytes_per_launch": work["bytes"] * units, "kernel": kernel, "kernel_ms": kern_ms,
+            "flops_per_unit": work["flops"], "bytes_per_unit": work["bytes"], "peak_source": peak_src,
+            "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}
+
+
+def timed_steps(torch, stream, step, steps, warmup, barrier=None, N=None):
+    """W untimed steps, then K steps between CUDA events on the launching stream, a synchronize on both sides.
+    Returns (milliseconds of the K steps, kernels the handle N launched inside the timed region)"""
+    for s in range(warmup):
+        step(s)
+    (barrier or torch.cuda.synchronize)()
+    l0 = N.launch_count() if N is not None else 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for s in range(steps):
+        step(s)
+    e1.record(stream)
+    (barrier or torch.cuda.synchronize)()
+    return e0.elapsed_time(e1), (N.launch_count() - l0 if N is not None else 0)
+
+
+# -------------------------------------------------------------------------------------------------- config 4 (headline)
+def run_config4(args, torch, dev, local_rank, clk, n_candidates=65536, e2e=True):
+    from corleone_b200 import Tsit5, configs, native as nat, to_vec
+    I = 256
+    spec = configs.config4_dense20(I)
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(2), device=local_rank)
+    B, nvars = n_candidates, N.nvars
+    stream = torch.cuda.current_stream()
+    N.set_stream(stream.cuda_stream)
+    sz = N.out_sizes()
+    d_ps = dense20_inputs_soa(torch, dev, to_vec(ps_t), B, configs.SEED0 + 4)          # [nvars, B], 3.2 GB: larger than L2
+    fields = ("defects_kind", "xend")
+    d_out = {f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields}
+    # the sensitivity Jacobian (n_sens x B doubles = 64 GB) stays resident in handle-owned HBM (cb200_out.resident)
+    want = nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_XEND
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
+    ptrs = {f: d_out[f].data_ptr() for f in fields}
+
+    def step(s):
+        N.eval_raw(d_ps.data_ptr(), B, B, want, flags, ptrs, 1, resident=nat.WANT_SENS)
+
+    step(0)
+    torch.cuda.synchronize()
+    clk.mark()   # the GPU is under this workload's load from here on (a step takes most of a second)
+    ms_total, launches = timed_steps(torch, stream, step, args.steps, max(3, args.warmup), N=N)
+    kern_ms = float(np.mean(N.kernel_ms_history(min(256, args.steps))))
+    units = I * B
+    res = {"workload": "dense20_256x65k" if B == 65536 else f"dense20_256x{B}", "units_per_step": units,
+           "value": units * args.steps / (ms_total * 1e-3), "unit": "units/s", "ms_per_step": ms_total / args.steps,
+           "kernel_ms": kern_ms, "steps": args.steps,
+           "outputs": f"sens ({8 * sz['sens'] * B / 1e9:.1f} GB, resident in HBM), defects_kind, xend",
+           "chunking": "none on the device-resident arm: one persistent launch over all units of the step"}
+    res["_launches_timed"] = launches
+    res["_N"] = N
+    e2e_res = None
+    if e2e:
+        # ---- end to end through cb200_eval with HOST buffers: candidate-major (Julia nvars x B) pinned input, the
+        # defects and end states come back to pinned host memory, the 64 GB Jacobian stays on the device (resident)
+        e2e_steps = max(1, min(args.steps, args.e2e_steps or 3))
+        pin_ps = torch.empty((B, nvars), dtype=torch.float64, pin_memory=True)
+        pin_ps.copy_(d_ps.t())          # the same candidates, candidate-major
+        del d_ps
+        for f in fields:
+            del d_out[f]
+        torch.cuda.empty_cache()
+        pin_out = {f: torch.empty((B, sz[f]), dtype=torch.float64, pin_memory=True) for f in fields}
+        hp = {f: pin_out[f].data_ptr() for f in fields}
+
+        def host_eval():
+            N.eval_raw(pin_ps.data_ptr(), B, nvars, want, 0, hp, 1, resident=nat.WANT_SENS)
+
+        host_eval()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            host_eval()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        e2e_res = {"value": units * e2e_steps / dt, "unit": "units/s", "h2d_bytes_per_step": 8 * B * nvars,
+                   "d2h_bytes_per_step": 8 * B * sum(sz[f] for f in fields), "steps": e2e_steps,
+                   "ms_per_step": 1e3 * dt / e2e_steps,
+                   "api": "cb200_eval with pinned host buffers, candidate-major (Julia layout), 8 candidate chunks on 3 streams; "
+                          "defects_kind and xend return to the host, the sensitivity Jacobian stays device-resident "
+                          "(cb200_out.resident = CB200_WANT_SENS, cb200_resident)"}
+        del pin_ps, pin_out
+    res["e2e"] = e2e_res
+    return res
+
+
+# -------------------------------------------------------------------------------------------------- config 2
+def run_config2(args, torch, dev, local_rank, steps, rank=0):
+    from corleone_b200 import Tsit5, configs, native as nat, to_vec
+    I, B, K = 100, 4096, 2
+    spec = configs.config2_lqr()
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(K), device=local_rank)
+    nvars = N.nvars
+    rng = np.random.default_rng(configs.SEED0 + 2 + 1000 * rank)
+    ps_host = lqr_inputs(nvars, to_vec(ps_t), B, rng)
+    stream = torch.cuda.current_stream()
+    N.set_stream(stream.cuda_stream)
+    sz = N.out_sizes()
+    fields = ("jac_vals", "defects_kind", "objective", "grad_compact")   # cons_j, c, f, grad f (structural zeros omitted)
+    sz["grad_compact"] = N.grad_structure(2)[1]
+    set_bytes = 8 * B * (nvars + sum(sz[f] for f in fields))
+    nsets = max(2, int(np.ceil(3 * 126e6 / set_bytes)))
+    d_ps, d_out, d_sums = [], [], []
+    for s in range(nsets):
+        d_ps.append(torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev))
+        d_out.append({f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields})
+        d_sums.append(torch.zeros(nvars + 1, dtype=torch.float64, device=dev))
+    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_GRAD_COMPACT
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
+
+    def step(s):
+        k = s % nsets
+        ptrs = {f: d_out[k][f].data_ptr() for f in fields}
+        ptrs["objective_sum"] = d_sums[k].data_ptr()
+        ptrs["grad_sum"] = d_sums[k].data_ptr() + 8
+        N.eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, 2)
+
+    ms_total, launches = timed_steps(torch, stream, step, steps, 3, N=N)
+    kern_ms = float(np.mean(N.kernel_ms_history(min(256, steps))))
+    units = I * B
+    # e2e: pinned host buffers, the NLP consumer's outputs (f, c, cons_j, compact grad f)
+    e2e_steps = min(steps, 10)
+    pin_ps = torch.from_numpy(ps_host).pin_memory()
+    pin_out = {f: torch.empty((B, sz[f]), dtype=torch.float64, pin_memory=True) for f in fields}
+    hp = {f: pin_out[f].data_ptr() for f in fields}
+
+    def host_eval(res_bits=0, flds=fields):
+        N.eval_raw(pin_ps.data_ptr(), B, nvars, want, 0, {f: hp[f] for f in flds}, 2, resident=res_bits)
+
+    def time_host(fn):
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / e2e_steps
+
+    dt_full = time_host(host_eval)
+    # the consumer that factorises cons_j on the device: only f, c and the compact gradient cross PCIe
+    slim = ("defects_kind", "objective", "grad_compact")
+    dt_slim = time_host(lambda: host_eval(nat.WANT_JAC, slim))
+    out = {"workload": "lqr_ms100_b4096", "units_per_step": units, "value": units * steps / (ms_total * 1e-3), "unit": "units/s",
+           "ms_per_step": ms_total / steps, "kernel_ms": kern_ms, "steps": steps,
+           "l2": f"inputs larger than L2: {nsets} rotating buffer sets of {set_bytes / 1e6:.0f} MB",
+           "e2e": {"value": units / dt_full, "unit": "units/s", "h2d_bytes_per_step": 8 * B * nvars,
+                   "d2h_bytes_per_step": 8 * B * sum(sz[f] for f in fields), "steps": e2e_steps, "ms_per_step": 1e3 * dt_full,
+                   "api": "cb200_eval, pinned host buffers, candidate-major; f, c, cons_j nonzeros, compact gradient to the host"},
+           "e2e_jac_resident": {"value": units / dt_slim, "unit": "units/s", "h2d_bytes_per_step": 8 * B * nvars,
+                                "d2h_bytes_per_step": 8 * B * sum(sz[f] for f in slim), "steps": e2e_steps,
+                                "ms_per_step": 1e3 * dt_slim,
+                                "api": "the same with cons_j kept on the device (cb200_out.resident = CB200_WANT_JAC)"},
+           "gpu_launches": launches, "_N": N, "_spec": spec, "_ps_host": ps_host}
+    return out
+
+
+# -------------------------------------------------------------------------------------------------- config 3
+def run_config3(args, torch, dev, local_rank, steps):
+    from corleone_b200 import Tsit5, configs, native as nat, to_vec
+    I, B = 64, 16384
+    spec = configs.config3_lotka_oed(I)
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(2), device=local_rank)
+    nvars = N.nvars
+    rng = np.random.default_rng(configs.SEED0 + 3)
+    ps = oed_inputs(N, to_vec(ps_t), B, rng, I)
+    sz = N.out_sizes()
+    fields = ("fim", "criteria", "defects_kind")
+    nsets = 3   # 3 x (ps 0.1 GB + results 0.15 GB) > L2
+    d_ps = [torch.from_numpy(np.ascontiguousarray(np.roll(ps, s, axis=0).T)).to(dev) for s in range(nsets)]
+    outs = [{f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields} for _ in range(nsets)]
+    fsum = torch.zeros(4, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream()
+    N.set_stream(stream.cuda_stream)
+    want = nat.WANT_FIM | nat.WANT_CRIT | nat.WANT_DEFECTS
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
+
+    def step(s):
+        k = s % nsets
+        ptrs = {f: outs[k][f].data_ptr() for f in fields}
+        ptrs["fim_sum"] = fsum.data_ptr()
+        N.eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, 1)
+
+    ms_total, launches = timed_steps(torch, stream, step, steps, 3, N=N)
+    kern_ms = float(np.mean(N.kernel_ms_history(min(256, steps))))
+    units = I * B
+    e2e_steps = min(steps, 10)
+    pin_ps = torch.from_numpy(ps).pin_memory()
+    pin_out = {f: torch.empty((B, sz[f]), dtype=torch.float64, pin_memory=True) for f in fields}
+    hsum = np.zeros(4)
+    hp = {f: pin_out[f].data_ptr() for f in fields}
+    hp["fim_sum"] = hsum.ctypes.data
+
+    def host_eval():
+        N.eval_raw(pin_ps.data_ptr(), B, nvars, want, 0, hp, 1)
+
+    for _ in range(2):
+        host_eval()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_eval()
+    dt = (time.perf_counter() - t0) / e2e_steps
+    return {"workload": "lotka_oed_64x16k", "units_per_step": units, "value": units * steps / (ms_total * 1e-3), "unit": "units/s",
+            "ms_per_step": ms_total / steps, "kernel_ms": kern_ms, "steps": steps, "gpu_launches": launches,
+            "outputs": "Fisher information per sample, its sum over the samples, six criteria, shooting defects",
+            "e2e": {"value": units / dt, "unit": "units/s", "h2d_bytes_per_step": 8 * B * nvars,
+                    "d2h_bytes_per_step": 8 * B * sum(sz[f] for f in fields) + 32, "steps": e2e_steps, "ms_per_step": 1e3 * dt,
+                    "api": "cb200_eval, pinned host buffers, candidate-major"}, "_N": N}
+
+
+# -------------------------------------------------------------------------------------------------- config 1
+def run_config1(args, torch, dev, local_rank):
+    """single-candidate latency of cb200_eval through host pointers (f, grad f, c, cons_j), the reference's own use"""
+    from corleone_b200 import Tsit5, configs, native as nat, to_vec
+    spec = configs.config1_lotka_ms24()
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(4), device=local_rank)
+    ps = to_vec(ps_t)[None, :].copy()
+    sz = N.out_sizes()
+    fields = ("jac_vals", "defects_kind", "objective", "grad")
+    out = {f: np.empty((1, sz[f])) for f in fields}
+    ptrs = {f: out[f].ctypes.data for f in fields}
+    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
+    for _ in range(50):
+        N.eval_raw(ps.ctypes.data, 1, N.nvars, want, 0, ptrs, 3)
+    n = 2000
+    t0 = time.perf_counter()
+    for _ in range(n):
+        N.eval_raw(ps.ctypes.data, 1, N.nvars, want, 0, ptrs, 3)
+    us = (time.perf_counter() - t0) / n * 1e6
+    # kernel time alone: the same request with device pointers (no graph), CUDA events around the integration kernel
+    d_ps = torch.from_numpy(ps.T.copy()).to(dev)
+    d_out = {f: torch.empty((sz[f], 1), dtype=torch.float64, device=dev) for f in fields}
+    N.set_stream(torch.cuda.current_stream().cuda_stream)
+    for _ in range(20):
+        N.eval_raw(d_ps.data_ptr(), 1, 1, want, nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA, {f: d_out[f].data_ptr() for f in fields}, 3)
+    torch.cuda.synchronize()
+    kern_us = 1e3 * float(np.mean(N.kernel_ms_history(16)))
+    units = 24
+    return {"workload": "lotka_ms24 (B = 1)", "units_per_step": units, "value": units / (us * 1e-6), "unit": "units/s",
+            "latency_us_per_call": us, "ms_per_step": us * 1e-3, "kernel_ms": kern_us * 1e-3,
+            "api": "cb200_eval with host pointers, one candidate: f, grad f, c, cons_j; the whole call (H2D, kernels, D2H) is one "
+                   "captured CUDA graph",
+            "e2e": {"value": units / (us * 1e-6), "unit": "units/s", "h2d_bytes_per_step": 8 * N.nvars,
+                    "d2h_bytes_per_step": 8 * sum(sz[f] for f in fields), "ms_per_step": us * 1e-3}, "_N": N, "_spec": spec, "_ps": ps}
+
+
+# ================================================================================================== CPU arms
+def cpu_baseline(spec, ps, K, seconds_target=12.0, nthreads=0, n_intervals=None):
+    """The oracle port timed on the host cores on a bounded sample of the same workload (~seconds_target of CPU work)."""
     from oracle import pyoracle as po
     if ORIG_AFFINITY is not None:
         os.sched_setaffinity(0, ORIG_AFFINITY)   # the CPU arm gets every core again, not only the GPU's NUMA node
     O = po.OracleLayer(spec)
     nthreads = nthreads or host_threads()
-    O.bench_units(ps[:64], K=K_STEPS_PER_PIECE, with_sens=True, nthreads=nthreads)          # warm-up (threads, caches)
+    O.bench_units(ps[: max(1, min(len(ps), nthreads))], K=K, with_sens=True, nthreads=nthreads)   # warm-up (threads, caches)
     tot_t, tot_u, passes = 0.0, 0, 0
     while tot_t < seconds_target and passes < 1000:
-        t, u, _ = O.bench_units(ps, K=K_STEPS_PER_PIECE, with_sens=True, nthreads=nthreads)
+        t, u, _ = O.bench_units(ps, K=K, with_sens=True, nthreads=nthreads)
         tot_t += t
         tot_u += u
         passes += 1
     return (tot_u / tot_t, nthreads,
-            f"{passes} passes over {ps.shape[0]} candidates x {I_INTERVALS} intervals ({tot_u} units), {tot_t:.1f} s")
+            f"{passes} passes over {ps.shape[0]} candidates x {O.I} intervals ({tot_u} units), {tot_t:.1f} s")
+
+
+def dense20_sample(n, seed):
+    """host sample of the config-4/5 inputs for the CPU arms: (n, nvars) candidate-major"""
+    from corleone_b200 import configs
+    from oracle import pyoracle as po
+    spec = configs.config4_dense20(256)
+    O = po.OracleLayer(spec)
+    rng = np.random.default_rng(seed)
+    return spec, O, O.default_ps()[None, :] + 0.1 * rng.standard_normal((n, O.nvars))
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU implementation of the path on the host cores.  The real
-    reference is Julia (absent here), so this is the oracle port with all host threads (kind = "port")."""
+    """--impl reference: the reference's CPU implementation of the path on the host cores.  The real reference is
+    Julia (absent here), so this is the oracle port with all host threads (kind = "port")."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from corleone_b200 import configs
-    from oracle import pyoracle as po
-    spec = configs.config2_lqr()
-    O = po.OracleLayer(spec)
-    rng = np.random.default_rng(configs.SEED0 + 2)
-    B = B_PER_GPU * args.gpus
     nthreads = host_threads()
-    # each step = a bounded sample of the workload (whole passes over one rank's batch), sized so that the run
-    # ends within a few minutes
-    ps = make_inputs(O.nvars, O.default_ps(), B_PER_GPU, rng)
-    t, u, _ = O.bench_units(ps, K=K_STEPS_PER_PIECE, nthreads=nthreads)
+    n_gpu_candidates = 65536 if args.gpus == 1 else 4096
+    workload = "dense20_256x65k" if args.gpus == 1 else "scale_1M"
+    nb = max(nthreads, 16)
+    spec, O, ps = dense20_sample(nb, configs.SEED0 + 4)
+    t, u, _ = O.bench_units(ps, K=2, nthreads=nthreads)
     budget = min(10.0, 120.0 / max(1, args.steps + args.warmup))
     passes = max(1, int(budget / max(t, 1e-6)))
-    nb = B_PER_GPU
 
     def one_step():
         tt, uu = 0.0, 0
         for _ in range(passes):
-            t1, u1, _ = O.bench_units(ps, K=K_STEPS_PER_PIECE, nthreads=nthreads)
+            t1, u1, _ = O.bench_units(ps, K=2, nthreads=nthreads)
             tt += t1
             uu += u1
         return tt, uu
@@ -211,35 +521,220 @@ def run_reference(args):
         tot_t += t
         tot_u += u
     value = tot_u / tot_t
-    sample = f"{passes} passes over {nb} candidates x {I_INTERVALS} intervals per step (of {B} in the {args.gpus}-GPU job)"
+    sample = (f"{passes} passes over {nb} candidates x 256 intervals per step (of {n_gpu_candidates} candidates in the "
+              f"{args.gpus}-GPU job)")
     print(json.dumps({
-        "impl": "reference", "metric": "shooting-interval solves+sensitivities/sec (FP64)", "value": value,
-        "unit": "units/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "intervals": I_INTERVALS, "candidates_per_gpu": B_PER_GPU,
-                   "method": "tsit5", "steps_per_piece": K_STEPS_PER_PIECE, "pieces_per_interval": M_PIECES,
-                   "sens_directions": NS_DIRS, "sample": sample},
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "units/s", "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": dense20_config(workload, n_gpu_candidates, args.gpus, sample=sample),
         "cpu_baseline": {"value": value, "unit": "units/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
 
 
+def dense20_config(workload, candidates, world, **extra):
+    c = {"workload": workload, "model": "dense20: x' = W x - x^3 + b u (synthetic, BASELINE.md section 5)", "intervals": 256,
+         "candidates": candidates, "method": "tsit5", "steps_per_piece": 2, "pieces_per_interval": 4,
+         "sens_directions": 24, "units_per_step": 256 * candidates,
+         "l2": "inputs larger than L2 (candidate matrix 3.2 GB at 65 536 candidates, 200 MB at 4096); results stream to HBM",
+         "parallelism": ("single GPU" if world == 1 else
+                         f"candidate axis sharded x{world} (strong scaling), per step allreduce(objective_sum, grad_sum) + "
+                         "allgather(defects) inside the timed region")}
+    c.update(extra)
+    return c
+
+
+# ================================================================================================== N > 1: config 5
+def run_scale(args, torch, dist, dev, world, rank, local_rank):
+    from corleone_b200 import Tsit5, configs, native as nat, to_vec
+    I, B_total = 256, 4096
+    assert B_total % world == 0
+    B = B_total // world
+    b0 = rank * B
+    spec = configs.config4_dense20(I)
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(2), device=local_rank)
+    nvars = N.nvars
+    stream = torch.cuda.current_stream()
+    N.set_stream(stream.cuda_stream)
+    # communicator: rank 0 makes the NCCL id, the host (torch.distributed here, Distributed.jl / MPI for a Julia host)
+    # hands it round; from then on the library runs its own data plane
+    ident = [nat.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    N.comm_init(world, rank, ident[0], max_B_total=B_total)
+    info = N.comm_info()
+    sz = N.out_sizes()
+    # all ranks draw the whole batch from one seed and keep their slice: identical to the 1-GPU job
+    full = dense20_inputs_soa(torch, dev, to_vec(ps_t), B_total, configs.SEED0 + 5)
+    d_ps = full[:, b0:b0 + B].contiguous()
+    del full
+    d_obj = torch.empty((1, B), dtype=torch.float64, device=dev)
+    d_xend = torch.empty((sz["xend"], B), dtype=torch.float64, device=dev)
+    d_sums = torch.zeros(1 + nvars, dtype=torch.float64, device=dev)
+    want = nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_XEND | nat.WANT_OBJ | nat.WANT_GRAD
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA | nat.COMM_REDUCE | nat.COMM_GATHER
+    ptrs = {"objective": d_obj.data_ptr(), "xend": d_xend.data_ptr(), "objective_sum": d_sums.data_ptr(),
+            "grad_sum": d_sums.data_ptr() + 8}
+
+    def step(s):
+        N.eval_raw(d_ps.data_ptr(), B, B, want, flags, ptrs, 1, resident=nat.WANT_SENS, comm_B_total=B_total, comm_b0=b0)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    with ClockSampler(local_rank) as clk:
+        clk.wait_first()
+        step(0)
+        barrier()
+        clk.mark()
+        ms_total, launches = timed_steps(torch, stream, step, args.steps, max(3, args.warmup), barrier, N=N)
+        kern_ms = float(np.mean(N.kernel_ms_history(min(256, args.steps))))
+        t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total = float(t.item())
+        clocks = clk.summary()
+    units = I * B_total
+    value = units * args.steps / (ms_total * 1e-3)
+    # check of the collectives on the timed workload: the gathered defects and the reduced sums are the same on every rank
+    gp, gld = N.comm_gathered()
+    chk = torch.tensor([float(d_sums[0].item())], dtype=torch.float64, device=dev)
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    sums_identical = bool(lo.item() == hi.item())
+
+    # ---- e2e: every rank feeds its shard from pinned host memory; its own defects, end states and the all-reduced sums
+    # come back to the host; the all-gathered defect vector and the Jacobian stay on the device
+    e2e_steps = max(1, min(args.steps, args.e2e_steps or 5))
+    pin_ps = torch.empty((B, nvars), dtype=torch.float64, pin_memory=True)
+    pin_ps.copy_(d_ps.t())
+    pin_dk = torch.empty((B, sz["defects_kind"]), dtype=torch.float64, pin_memory=True)
+    pin_x = torch.empty((B, sz["xend"]), dtype=torch.float64, pin_memory=True)
+    pin_obj = torch.empty((B, 1), dtype=torch.float64, pin_memory=True)
+    h_sums = np.zeros(1 + nvars)
+    hp = {"defects_kind": pin_dk.data_ptr(), "xend": pin_x.data_ptr(), "objective": pin_obj.data_ptr(),
+          "objective_sum": h_sums.ctypes.data, "grad_sum": h_sums.ctypes.data + 8}
+    hflags = nat.COMM_REDUCE | nat.COMM_GATHER
+
+    def host_eval():
+        N.eval_raw(pin_ps.data_ptr(), B, nvars, want, hflags, hp, 1, resident=nat.WANT_SENS, comm_B_total=B_total, comm_b0=b0)
+
+    host_eval()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_eval()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    e2e = {"value": units * e2e_steps / dt, "unit": "units/s", "h2d_bytes_per_step": 8 * B * nvars * world,
+           "d2h_bytes_per_step": 8 * (B * (sz["defects_kind"] + sz["xend"] + 1) + 1 + nvars) * world, "steps": e2e_steps,
+           "ms_per_step": 1e3 * dt / e2e_steps,
+           "api": "cb200_eval with pinned host buffers per rank + CB200_COMM_REDUCE | CB200_COMM_GATHER; every rank's own "
+                  "defects / end states / objectives and the all-reduced sums return to the host, the all-gathered defect "
+                  "vector and the Jacobian stay on the device (bytes are whole-job totals)"}
+    barrier()
+    N.comm_destroy()
+    secondary = None
+    if not args.no_secondary:
+        # round 1's workload for comparison: config 2, weak scaling, 4096 candidates per rank, sums all-reduced
+        secondary = run_config2_weak(args, torch, dist, dev, world, rank, local_rank)
+    if rank == 0:
+        peak, peak_src = fp64_peak(nat, local_rank)
+        hbm_peak, hbm_src = load_peaks()
+        tmap = {0: "none", 1: "nccl (ncclAllReduce + ncclAllGather after the kernels)",
+                2: "p2p (defects stored into every rank's window by the shooting kernel, one-shot all-reduce in the tail of the "
+                   "objective kernel; no NCCL call per step)"}
+        line = {
+            "metric": METRIC, "value": value, "unit": "units/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": dense20_config("scale_1M", B_total, world, candidates_per_gpu=B, transport=tmap[info["transport"]],
+                                     collectives_checked={"reduced_sums_identical_on_all_ranks": sums_identical,
+                                                          "gather_leading_dimension": gld}),
+            "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": roofline_entry(WORK["dense20"], I * B, kern_ms, peak, peak_src, hbm_peak, hbm_src,
+                                       "shoot_dense_mma_pipe_kernel<Tsit5,uniform> (FP64 tensor path) incl. fused defect all-gather "
+                                       "stores, per rank", "dense20"),
+            "secondary": secondary,
+        }
+        print(json.dumps(line))
+
+
+def run_config2_weak(args, torch, dist, dev, world, rank, local_rank):
+    from corleone_b200 import Tsit5, configs, native as nat, to_vec
+    I, B, K = 100, 4096, 2
+    spec = configs.config2_lqr()
+    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(K), device=local_rank)
+    nvars = N.nvars
+    rng = np.random.default_rng(configs.SEED0 + 2 + 1000 * rank)
+    ps_host = lqr_inputs(nvars, to_vec(ps_t), B, rng)
+    stream = torch.cuda.current_stream()
+    N.set_stream(stream.cuda_stream)
+    ident = [nat.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(ident, src=0)
+    N.comm_init(world, rank, ident[0], max_B_total=0)
+    sz = N.out_sizes()
+    fields = ("jac_vals", "defects_kind", "objective", "grad_compact")
+    sz["grad_compact"] = N.grad_structure(2)[1]
+    nsets = 5
+    d_ps = [torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev) for s in range(nsets)]
+    d_out = [{f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields} for _ in range(nsets)]
+    d_sums = [torch.zeros(nvars + 1, dtype=torch.float64, device=dev) for _ in range(nsets)]
+    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_GRAD_COMPACT
+    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA | nat.COMM_REDUCE
+
+    def step(s):
+        k = s % nsets
+        ptrs = {f: d_out[k][f].data_ptr() for f in fields}
+        ptrs["objective_sum"] = d_sums[k].data_ptr()
+        ptrs["grad_sum"] = d_sums[k].data_ptr() + 8
+        N.eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, 2)
+
+    def barrier():
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+
+    steps = max(20, args.steps)
+    ms_total, _ = timed_steps(torch, stream, step, steps, 5, barrier)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    barrier()
+    N.comm_destroy()
+    return {"workload": "lqr_ms100_b4096 per GPU (weak scaling, round 1's bench)", "value": I * B * world * steps / (ms_total * 1e-3),
+            "unit": "units/s", "ms_per_step": ms_total / steps, "steps": steps,
+            "collective": "all-reduce of (objective_sum, grad_sum) fused into the tail of the objective kernel"}
+
+
+# ================================================================================================== main
+def strip(d):
+    return {k: v for k, v in d.items() if not k.startswith("_")}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0, help="default: min(steps, 20)")
+    ap.add_argument("--no-secondary", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--only", default="", help="N = 1: comma list of configs to run (1,2,3,4); default all")
+    ap.add_argument("--candidates", type=int, default=65536, help="N = 1: candidates of the config-4 run (tuning; 65536 = the config)")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
 
     import torch
     import torch.distributed as dist
-    from corleone_b200 import Tsit5, configs, native as nat
+    from corleone_b200 import native as nat
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -247,192 +742,83 @@ def main():
     bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    assert world == args.gpus or world == 1, f"--gpus {args.gpus} but WORLD_SIZE={world}"
-
-    spec = configs.config2_lqr()
-    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(K_STEPS_PER_PIECE), device=local_rank)
-    from corleone_b200 import to_vec
-    B = B_PER_GPU
-    nvars = N.nvars
-    rng = np.random.default_rng(configs.SEED0 + 2 + 1000 * rank)
-    ps_host = make_inputs(nvars, to_vec(ps_t), B, rng)                      # (B, nvars) candidate-major
-    stream = torch.cuda.current_stream()
-    N.set_stream(stream.cuda_stream)
-
-    # ---- device-resident arm: rotate over buffer sets whose total footprint exceeds L2 (126 MB)
-    sz = N.out_sizes()
-    fields = ("jac_vals", "defects_kind", "objective", "grad_compact")   # cons_j, c, f, grad f (structural zeros omitted)
-    sz["grad_compact"] = N.grad_structure(OBJECTIVE_ROW)[1]
-    set_bytes = 8 * B * (nvars + sum(sz[f] for f in fields))
-    nsets = max(2, int(np.ceil(3 * 126e6 / set_bytes)))
-    d_ps, d_out, d_sums = [], [], []
-    for s in range(nsets):
-        d_ps.append(torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev))   # [nvars, B] SoA
-        d_out.append({f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields})
-        d_sums.append(torch.zeros(nvars + 1, dtype=torch.float64, device=dev))
-    # WANT_GRAD stays set for the cross-candidate gradient sum (grad_sum); the per-candidate gradient is delivered compact
-    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_GRAD_COMPACT
-    flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
-
-    def step(s, comm=True):
-        k = s % nsets
-        ptrs = {f: d_out[k][f].data_ptr() for f in fields}
-        ptrs["objective_sum"] = d_sums[k].data_ptr()
-        ptrs["grad_sum"] = d_sums[k].data_ptr() + 8
-        if world > 1 and sum_done[k] is not None:
-            stream.wait_event(sum_done[k])        # buffer set k: its previous all-reduce must have finished
-        N.eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, OBJECTIVE_ROW)
-        if world > 1 and comm:
-            # the path's only exchange: cross-candidate partial sums (1 + nvars doubles), all-reduced on a side
-            # stream so that the next evaluation (another buffer set) overlaps the NCCL latency
-            ev = torch.cuda.Event()
-            ev.record(stream)
-            comm_stream.wait_event(ev)
-            with torch.cuda.stream(comm_stream):
-                dist.all_reduce(d_sums[k])
-                sum_done[k] = torch.cuda.Event()
-                sum_done[k].record(comm_stream)
-
-    comm_stream = torch.cuda.Stream() if world > 1 else None
-    sum_done = [None] * nsets
-
-    def barrier():
-        torch.cuda.synchronize()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for s in range(max(3, args.warmup)):
-        step(s)
-    barrier()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local_rank) as clk:
-        clk.wait_first()
-        # put the GPU under the same load for ~0.7 s before the timed region so that the sampler (100 ms
-        # period) sees the clocks this workload actually runs at; these steps are extra warm-up
-        t_end, s2 = time.time() + 0.7, 0
-        clk.mark()
-        while time.time() < t_end:   # wall-clock bounded, so no collective here: ranks run different counts
-            step(s2, comm=False)
-            s2 += 1
-            if s2 % 64 == 0:
-                torch.cuda.synchronize()
-        barrier()
-        launches0 = N.launch_count()
-        ev0.record(stream)
-        for s in range(args.steps):
-            step(s)
-        if world > 1:
-            stream.wait_stream(comm_stream)   # the timed region ends when the last all-reduce has finished
-        ev1.record(stream)
-        barrier()
-        ms_total = ev0.elapsed_time(ev1)
-        launches_timed = N.launch_count() - launches0
-        # kernel durations of the timed steps (event pairs the library records around the integration kernel)
-        hist = N.kernel_ms_history(min(256, args.steps))
-        kern_ms = float(np.mean(hist)) if len(hist) else float("nan")
-        t_end = time.time() + 0.3
-        while time.time() < t_end:
-            step(0, comm=False)
-        torch.cuda.synchronize()
-    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
-    units_per_step = I_INTERVALS * B * world
-    value = units_per_step * args.steps / (ms_total * 1e-3)
-
-    # ---- end-to-end arm: the public host API (Julia-style candidate-major matrices in pinned host memory)
-    e2e_steps = args.e2e_steps or min(args.steps, 20)
-    pin_ps = torch.from_numpy(ps_host).pin_memory()
-    pin_out = {f: torch.empty((B, sz[f]), dtype=torch.float64).pin_memory() for f in fields}
-    pinned = {f: v.numpy() for f, v in pin_out.items()}
-    ps_np = pin_ps.numpy()
-    host_ptrs = {f: pinned[f].ctypes.data for f in fields}
-
-    def host_eval():   # cb200_eval on host pointers: returns when the results are in the caller's buffers
-        N.eval_raw(ps_np.ctypes.data, B, nvars, want, 0, host_ptrs, OBJECTIVE_ROW)
-
-    for _ in range(3):
-        host_eval()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        host_eval()
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = units_per_step * e2e_steps / float(t.item())
-    # context for e2e: the same bytes as plain pinned copies, both directions concurrently on two streams
-    d_in = torch.empty(B * nvars, dtype=torch.float64, device=dev)
-    d_res = torch.empty(B * sum(sz[f] for f in fields), dtype=torch.float64, device=dev)
-    h_res = torch.empty(d_res.shape, dtype=torch.float64).pin_memory()
-    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
-    torch.cuda.synchronize()
-    t0 = time.perf_counter()
-    for _ in range(5):
-        with torch.cuda.stream(s_in):
-            d_in.copy_(pin_ps.view(-1), non_blocking=True)
-        with torch.cuda.stream(s_out):
-            h_res.copy_(d_res, non_blocking=True)
-    torch.cuda.synchronize()
-    copy_ms = (time.perf_counter() - t0) / 5 * 1e3
-    del d_in, d_res, h_res
-    h2d = 8 * B * nvars
-    d2h = 8 * B * sum(sz[f] for f in fields)
-
-    if rank == 0:
-        hbm_peak, hbm_src = load_peaks()
-        # FP64 roof: DFMA and DMMA share one datapath on B200 (tools/dmma_micro.cu); the higher probe is the peak
-        peak_dfma = nat.probe_fp64_tflops(local_rank, 40000)
-        peak_dmma = nat.probe_fp64_mma_tflops(local_rank, 20000)
-        fp64_peak = max(peak_dfma, peak_dmma)
-        ach_tflops = FLOPS_PER_UNIT * I_INTERVALS * B / (kern_ms * 1e-3) / 1e12
-        ach_gbs = BYTES_PER_UNIT * I_INTERVALS * B / (kern_ms * 1e-3) / 1e9
-        line = {
-            "metric": "shooting-interval solves+sensitivities/sec (FP64)", "value": value, "unit": "units/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "intervals": I_INTERVALS, "candidates_per_gpu": B,
-                       "method": "tsit5", "steps_per_piece": K_STEPS_PER_PIECE, "pieces_per_interval": M_PIECES,
-                       "sens_directions": NS_DIRS, "units_per_step": units_per_step,
-                       "l2": f"inputs larger than L2: {nsets} rotating buffer sets of {set_bytes / 1e6:.0f} MB",
-                       "parallelism": (f"batch-sharded x{world}, NCCL allreduce(objective_sum, grad_sum) per step on a side stream"
-                                       if world > 1 else "single GPU")},
-            "e2e": {"value": e2e_value, "unit": "units/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "steps": e2e_steps, "ms_per_step": 1e3 * units_per_step / e2e_value,
-                    "pcie_copy_only_ms": copy_ms,
-                    "api": "cb200_eval with pinned host buffers, candidate-major (Julia layout), 8 chunks on 3 streams"},
-            "gpu_launches": int(launches_timed),
-            "clocks": clk.summary(),
-            "roofline": {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
-                         "frac": ach_tflops / fp64_peak if fp64_peak > 0 else None,
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, ncu --set full capture of this
-                         # command (profiles/r1_shoot_lqr_G4_fused.txt): 26.8 MB read + 15.3 MB written; the rest of
-                         # the 65 MB of results is still in the 126 MB write-back L2 when the kernel ends
-                         "traffic": NCU_DRAM_BYTES_PER_LAUNCH, "traffic_unit": "bytes per launch",
-                         "algorithmic_bytes_per_launch": BYTES_PER_UNIT * I_INTERVALS * B,
-                         "kernel": "shoot_kernel<Lqr,G=4,Tsit5,uniform,4 blocks/SM> incl. fused defect/gradient/cons_j epilogue",
-                         "kernel_ms": kern_ms,
-                         "flops_per_unit": FLOPS_PER_UNIT, "bytes_per_unit": BYTES_PER_UNIT,
-                         "peak_source": "FP64 probes measured in this run, max of DFMA chains "
-                                        f"({peak_dfma:.2f}) and mma.sync.m8n8k4.f64 ({peak_dmma:.2f}) TFLOP/s; "
-                                        "MEASURED_PEAKS.json has no FP64 figure",
-                         "hbm": {"achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                                 "peak_source": f"MEASURED_PEAKS.json ({hbm_src})"}},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            v, cores, sample = cpu_baseline(spec, ps_host)
-            line["cpu_baseline"] = {"value": v, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample}
-        print(json.dumps(line))
-    if world > 1:
+        run_scale(args, torch, dist, dev, world, rank, local_rank)
         dist.barrier()
         dist.destroy_process_group()
+        return
+
+    only = set(args.only.split(",")) if args.only else {"1", "2", "3", "4"}
+    peak, peak_src = fp64_peak(nat, local_rank)
+    hbm_peak, hbm_src = load_peaks()
+    all_configs = []
+    line = {}
+    with ClockSampler(local_rank) as clk:
+        clk.wait_first()
+        if "4" in only:
+            c4 = run_config4(args, torch, dev, local_rank, clk, args.candidates)
+            clocks = clk.summary()
+            units = c4["units_per_step"]
+            c4["roofline"] = roofline_entry(WORK["dense20"], units, c4["kernel_ms"], peak, peak_src, hbm_peak, hbm_src,
+                                            "shoot_dense_mma_pipe_kernel<Tsit5,uniform> (FP64 tensor path, mma.sync.m8n8k4.f64) "
+                                            "incl. fused defect epilogue", "dense20")
+            line = {"metric": METRIC, "value": c4["value"], "unit": "units/s", "n_gpus": 1, "steps": args.steps,
+                    "warmup": max(3, args.warmup), "ms_per_step": c4["ms_per_step"], "higher_is_better": True,
+                    "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                    "config": dense20_config(c4["workload"], args.candidates, 1, chunking=c4["chunking"], outputs=c4["outputs"]),
+                    "e2e": c4["e2e"], "gpu_launches": int(c4["_launches_timed"]),
+                    "clocks": clocks, "roofline": c4["roofline"]}
+            if not args.no_cpu_baseline:
+                from corleone_b200 import configs
+                spec, O, ps = dense20_sample(max(host_threads(), 16), configs.SEED0 + 4)
+                v, cores, sample = cpu_baseline(spec, ps, 2)
+                line["cpu_baseline"] = {"value": v, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample}
+            c4["_N"].close()
+            all_configs.append(strip(c4))
+            torch.cuda.empty_cache()
+        sub_steps = max(20, args.steps)
+        if "2" in only:
+            c2 = run_config2(args, torch, dev, local_rank, sub_steps)
+            c2["roofline"] = roofline_entry(WORK["lqr"], c2["units_per_step"], c2["kernel_ms"], peak, peak_src, hbm_peak, hbm_src,
+                                            "shoot_kernel<Lqr,G=4,Tsit5,uniform,4 blocks/SM> incl. fused defect/gradient/cons_j epilogue",
+                                            "lqr")
+            if not args.no_cpu_baseline:
+                v, cores, sample = cpu_baseline(c2["_spec"], c2["_ps_host"][:1024], 2, seconds_target=4.0)
+                c2["cpu_baseline"] = {"value": v, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample}
+            c2["_N"].close()
+            all_configs.append(strip(c2))
+        if "3" in only:
+            c3 = run_config3(args, torch, dev, local_rank, sub_steps)
+            c3["roofline"] = roofline_entry(WORK["lotka_oed"], c3["units_per_step"], c3["kernel_ms"], peak, peak_src, hbm_peak,
+                                            hbm_src, "shoot_kernel<OedAug<Lotka2>,G=0,Tsit5,uniform> incl. fused Fisher read-out, "
+                                            "criteria and defect epilogue", "lotka_oed")
+            c3["_N"].close()
+            all_configs.append(strip(c3))
+        if "1" in only:
+            c1 = run_config1(args, torch, dev, local_rank)
+            c1["roofline"] = roofline_entry(WORK["lotka_ms24"], c1["units_per_step"], c1["kernel_ms"], peak, peak_src, hbm_peak,
+                                            hbm_src, "shoot_kernel<Lotka3,G=2,Tsit5,uniform>, flat launch (latency-bound: 120 threads)",
+                                            "lotka_ms24")
+            if not args.no_cpu_baseline:
+                from oracle import pyoracle as po
+                O = po.OracleLayer(c1["_spec"])
+                t0 = time.perf_counter()
+                for _ in range(200):
+                    O.bench_units(c1["_ps"], K=4, with_sens=True, nthreads=1)
+                c1["cpu_baseline"] = {"value": 24 / ((time.perf_counter() - t0) / 200), "unit": "units/s", "cores": 1, "kind": "port",
+                                      "sample": "200 single-candidate evaluations, 1 thread (the reference default is serial)"}
+            c1["_N"].close()
+            all_configs.append(strip(c1))
+    if not line:   # tuning runs without config 4: the first config that ran is the line
+        first = all_configs[0]
+        line = {"metric": METRIC, "value": first["value"], "unit": "units/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": first["ms_per_step"], "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": {"workload": first["workload"]},
+                "e2e": first.get("e2e"), "roofline": first.get("roofline"), "gpu_launches": None}
+    line["all_configs"] = all_configs
+    print(json.dumps(line))
 
 
 if __name__ == "__main__":

@@ -16,9 +16,11 @@ OBJ = os.path.join(HERE, os.environ.get("CB200_OBJ_DIR", "build"))
 LIB = os.path.join(HERE, os.environ.get("CB200_LIB_NAME", "libcorleone_b200.so"))
 EXTRA = os.environ.get("CB200_NVCC_EXTRA", "").split()   # tuning builds, e.g. -DCB200_MINB=4 (with CB200_OBJ_DIR)
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+# -Xfatbin -compress-all: the device code is stored compressed (the driver inflates it at module load): 3x smaller
+# objects -- with the per-model instantiation lists trimmed to G in {0, default} the library is ~35 MB instead of 198 MB
 FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++",
+    "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-Xfatbin", "-compress-all",
 ]
 
 

@@ -14,8 +14,10 @@
 
 #include <nvtx3/nvToolsExt.h>   // header-only NVTX 3: ranges around every C-ABI call (no cost without a profiler attached)
 
-#include "common.cuh"
+#include "handle.cuh"
 #include "tableau.cuh"
+#include "tail.cuh"
+#include "fim.cuh"
 
 namespace {
 struct NvtxRange {
@@ -34,7 +36,7 @@ using namespace cb200;
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
-static int fail(int code, const char *fmt, ...)
+int cb200_fail(int code, const char *fmt, ...)
 {
     char buf[512];
     va_list ap;
@@ -44,29 +46,6 @@ static int fail(int code, const char *fmt, ...)
     g_err = buf;
     return code;
 }
-#define CUDA_TRY(expr)                                                                                   \
-    do {                                                                                                 \
-        cudaError_t e_ = (expr);                                                                         \
-        if (e_ != cudaSuccess)                                                                           \
-            return fail(CB200_ERR_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, \
-                        __LINE__);                                                                       \
-    } while (0)
-
-// ------------------------------------------------------------------ epilogue tables
-struct DefectEntry {
-    int a_kind;   // 0: xend row, 1: ps variable
-    int a_idx;
-    int b_kind;   // 1: ps variable, 2: constant
-    int b_idx;
-    double b_const;
-    int pos_kind;   // position in shooting_constraints (kind-major)
-    int pos_stage;  // position in stage_ordered_shooting_constraints
-};
-
-struct GradEntry {   // grad[var] = sens[src] (src >= 0) or 1.0 (src == -1)
-    int var;
-    long long src;
-};
 
 // ------------------------------------------------------------------ kernels
 // objective = last(getsym(traj))  (src/dynprob.jl:70-71): one row of the last merged sample.  col[i*ldc + b] is
@@ -74,7 +53,7 @@ struct GradEntry {   // grad[var] = sens[src] (src >= 0) or 1.0 (src == -1)
 // running sum over intervals in interval order (src/multiple_shooting.jl:171-177).
 __global__ void objective_kernel(const double *__restrict__ col, long long ldc, const double *__restrict__ ps,
                                  long long ldb, long long B, int I, int has_state, int is_quad, int ctrl_var,
-                                 double *__restrict__ obj, double *__restrict__ obj_sum)
+                                 double *__restrict__ obj, double *__restrict__ obj_sum, const TailArgs tail)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     double v = 0.0;
@@ -95,6 +74,7 @@ __global__ void objective_kernel(const double *__restrict__ col, long long ldc, 
         for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
         if ((threadIdx.x & 31) == 0) atomicAdd(obj_sum, v);
     }
+    tail_maybe(tail);   // the last block hands the cross-candidate sums on (all-reduced over the ranks) and closes the epoch
 }
 
 __global__ void grad_kernel(const GradEntry *__restrict__ tab, int n, const double *__restrict__ sens,
@@ -142,72 +122,10 @@ __global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const
 // With `crit` the six optimality criteria of lib/CorleoneOED/src/criteria.jl:33-63 are evaluated per candidate on
 // Symmetric(F) (rows of crit: A = tr(inv F), D = 1/det F, E = max eig(inv F), FisherA = -tr F, FisherD = -det F,
 // FisherE = -min eig F) from the eigenvalues of F (cyclic Jacobi, n <= CB200_MAX_FIM).
-constexpr int CB200_MAX_FIM = 8;
-// common tail of the read-out kernels: A = the full symmetric matrix of this thread's candidate
-__device__ __forceinline__ void fim_emit(double (&A)[CB200_MAX_FIM][CB200_MAX_FIM], int n, bool live, long long b,
-                                         double *__restrict__ fim, long long ldo, double *__restrict__ fsum,
-                                         double *__restrict__ crit)
-{
-    for (int c = 0; c < n; c++)
-        for (int r = 0; r < n; r++) {
-            double v = live ? A[r][c] : 0.0;
-            if (live && fim) fim[(long long)(r + n * c) * ldo + b] = v;
-            if (fsum) {
-                for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
-                if ((threadIdx.x & 31) == 0) atomicAdd(fsum + r + n * c, v);
-            }
-        }
-    if (!crit || !live) return;
-    double tr = 0.0;
-    for (int k = 0; k < n; k++) tr += A[k][k];
-    for (int sweep = 0; sweep < 40; sweep++) {   // cyclic Jacobi on the symmetric matrix; eigenvalues end on the diagonal
-        double off = 0.0, dia = 0.0;
-        for (int p = 0; p < n; p++) {
-            dia += A[p][p] * A[p][p];
-            for (int q = p + 1; q < n; q++) off += A[p][q] * A[p][q];
-        }
-        if (off <= 1e-32 * dia || off == 0.0) break;
-        for (int p = 0; p < n; p++)
-            for (int q = p + 1; q < n; q++) {
-                const double apq = A[p][q];
-                if (apq == 0.0) continue;
-                const double theta = (A[q][q] - A[p][p]) / (2.0 * apq);
-                const double t = (theta >= 0.0 ? 1.0 : -1.0) / (fabs(theta) + sqrt(theta * theta + 1.0));
-                const double c = 1.0 / sqrt(t * t + 1.0), sn = t * c;
-                for (int k = 0; k < n; k++) {   // A <- A J
-                    const double akp = A[k][p], akq = A[k][q];
-                    A[k][p] = c * akp - sn * akq;
-                    A[k][q] = sn * akp + c * akq;
-                }
-                for (int k = 0; k < n; k++) {   // A <- J' A
-                    const double apk = A[p][k], aqk = A[q][k];
-                    A[p][k] = c * apk - sn * aqk;
-                    A[q][k] = sn * apk + c * aqk;
-                }
-            }
-    }
-    double det = 1.0, trinv = 0.0, lmin = A[0][0];
-    for (int k = 0; k < n; k++) {
-        const double l = A[k][k];
-        det *= l;
-        trinv += 1.0 / l;
-        lmin = fmin(lmin, l);
-    }
-    // max eig(inv F) = 1 / (smallest eigenvalue of F) for positive definite F; for an indefinite F the largest
-    // reciprocal is taken, as eigvals(inv(F)) would give
-    double einv = 1.0 / A[0][0];
-    for (int k = 1; k < n; k++) einv = fmax(einv, 1.0 / A[k][k]);
-    crit[0 * ldo + b] = trinv;
-    crit[1 * ldo + b] = 1.0 / det;
-    crit[2 * ldo + b] = einv;
-    crit[3 * ldo + b] = -tr;
-    crit[4 * ldo + b] = -det;
-    crit[5 * ldo + b] = -lmin;
-}
-
+// fim_emit: fim.cuh
 __global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long long B, int nx, int I, int f_off,
                            int n, const double *__restrict__ finit, double *__restrict__ fim, long long ldo,
-                           double *__restrict__ fsum, double *__restrict__ crit)
+                           double *__restrict__ fsum, double *__restrict__ crit, const TailArgs tail)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const bool live = b < B;
@@ -219,6 +137,7 @@ __global__ void fim_kernel(const double *__restrict__ xend, long long ldx, long 
             A[r][c] = live ? xend[((long long)(I - 1) * nx + f_off + q) * ldx + b] + (finit ? finit[r + n * c] : 0.0) : 0.0;
         }
     fim_emit(A, n, live, b, fim, ldo, fsum, crit);
+    tail_maybe(tail);
 }
 
 // K4 read-out of the sample-based variants (lib/CorleoneOED/src/oed.jl): the information is collected from the saved
@@ -233,7 +152,7 @@ __global__ void fim_samples_kernel(const double *__restrict__ traj, long long ld
                                    int f_off, int n_rows, const int *__restrict__ row_sample,
                                    const int *__restrict__ row_var, const double *__restrict__ finit,
                                    double *__restrict__ fim, long long ldo, double *__restrict__ fsum,
-                                   double *__restrict__ crit)
+                                   double *__restrict__ crit, const TailArgs tail)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     const bool live = b < B;
@@ -279,6 +198,7 @@ __global__ void fim_samples_kernel(const double *__restrict__ traj, long long ld
         }
     }
     fim_emit(A, n, live, b, fim, ldo, fsum, crit);
+    tail_maybe(tail);
 }
 
 
@@ -337,79 +257,6 @@ __global__ void dmma_probe_kernel(double *out, int iters, double seed)
     for (int i = 0; i < 8; i++) s += c[i];
     out[blockIdx.x * (long long)blockDim.x + threadIdx.x] = s;
 }
-
-// ------------------------------------------------------------------ handle
-struct DevBuf {
-    void *p = nullptr;
-    size_t cap = 0;
-    int reserve(size_t bytes)
-    {
-        if (bytes <= cap) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        size_t want = bytes + bytes / 8;
-        cudaError_t e = cudaMalloc(&p, want);
-        if (e != cudaSuccess) {
-            e = cudaMalloc(&p, bytes);
-            want = bytes;
-        }
-        if (e != cudaSuccess) return (int)e;
-        cap = want;
-        return 0;
-    }
-    void release()
-    {
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-    }
-};
-
-struct cb200_handle {
-    std::mutex mu;
-    int device = 0;
-    int model = 0, method = 0;
-    DevLayer L{};
-    int nquad = 0;
-    std::vector<int> quad0;           // 0-based quadrature states
-    std::vector<int> ns;              // directions per interval
-    std::vector<int> h_M, h_var_off, h_n_u0, h_n_c, h_samp_off, h_piece_off;
-    std::vector<long long> h_sens_off, h_tsens_off;
-    long long n_tsens = 0;
-    std::vector<int> h_cidx, h_ic_src;
-    std::vector<DefectEntry> defects;
-    std::vector<int> dpos_kind, dpos_stage, oth_off, jpos;
-    long long jac_nnz_var = 0;         // leading entries of the triplet list whose values come from sens
-    std::vector<MatchEntry> oth;
-    std::vector<long long> jac_rows, jac_cols, jac_src;
-    long long n_sens = 0;
-    int n_samples = 0;
-    int max_ns = 0;
-    int fim_off = -1, fim_n = 0;
-    int fim_mode = 0, fim_bx = 0, n_obs = 0, n_obs_rows = 0;   // sample-based read-outs
-    int *d_obs_sample = nullptr, *d_obs_var = nullptr;
-    int range_i0 = 0, range_n = -1;   // cb200_set_interval_range: intervals [i0, i0 + n); n < 0 = all
-    bool d20_ref = false;             // holds a reference on the device's DENSE20 constant block
-    int G_sens = 2;                   // sensitivity directions per thread
-    void *tables = nullptr;           // one device allocation holding every table
-    int *d_quad = nullptr;
-    GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row
-    int grad_cap = 0;
-    std::vector<GradEntry> h_grad;
-    cudaStream_t stream = nullptr;
-    bool own_stream = false;
-    static constexpr int NAUX = 2;        // extra streams of the chunked host path (copy/compute overlap)
-    cudaStream_t aux[NAUX] = {};
-    cudaEvent_t ev_fork = nullptr, ev_join[NAUX] = {};
-    static constexpr int EV_RING = 256;   // event pairs around the integration kernel of the last 256 evals
-    cudaEvent_t ev0[EV_RING] = {}, ev1[EV_RING] = {};
-    long long n_timed = 0;
-    long long launches = 0;
-    DevBuf ws_ps, ws_in, ws_xend, ws_sens, ws_traj, ws_dk, ws_ds, ws_obj, ws_grad, ws_fim, ws_finit, ws_out, ws_sums, ws_objq, ws_jac, ws_crit, ws_fixed, ws_status, ws_small, ws_gradc, ws_tsens;
-    static constexpr size_t PIN_BYTES = 1 << 20;   // pinned host mirror of small evaluations
-    void *pin = nullptr;
-};
 
 static int default_G(int model)
 {
@@ -649,6 +496,27 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         !d->ic_n_constants || !d->n_shooting_indices || (d->n_controls > 0 && (!d->index_grid || !d->control_indices)) ||
         (d->n_tunable_p > 0 && !d->tunable_p) || (d->n_quadrature > 0 && !d->quadrature_indices))
         return fail(CB200_ERR_ARG, "a required table pointer of cb200_desc is NULL");
+    {   // counts a C-ABI caller can get wrong: everything that is dereferenced or used as an index below
+        long long n_si = 0, n_ic = 0;
+        for (int i = 0; i < d->n_intervals; i++) {
+            if (d->n_u0[i] < 0 || d->n_u0[i] > d->nx) return fail(CB200_ERR_ARG, "interval %d: n_u0 outside 0..nx", i + 1);
+            if (d->n_local_controls[i] < 0) return fail(CB200_ERR_ARG, "interval %d: negative n_local_controls", i + 1);
+            if (d->n_shooting_indices[i] < 0 || d->ic_n_constants[i] < 0)
+                return fail(CB200_ERR_ARG, "interval %d: negative table length", i + 1);
+            n_si += d->n_shooting_indices[i];
+            n_ic += d->ic_n_constants[i];
+        }
+        if ((n_si > 0 && !d->shooting_indices) || (n_ic > 0 && !d->ic_constants))
+            return fail(CB200_ERR_ARG, "shooting_indices / ic_constants is NULL although its per-interval counts are not zero");
+        for (long long q = 0; q < n_si; q++)
+            if (d->shooting_indices[q] < 1 || d->shooting_indices[q] > d->nx + d->n_controls)
+                return fail(CB200_ERR_ARG, "shooting_indices[%lld] = %lld outside 1..nx + n_controls", q, (long long)d->shooting_indices[q]);
+        for (long long q = 0; q < n_ic; q++)
+            if (d->ic_constants[q] < 1 || d->ic_constants[q] > d->nx)
+                return fail(CB200_ERR_ARG, "ic_constants[%lld] outside 1..nx", q);
+        if (d->fim_offset > 0 && (d->fim_n < 1 || d->fim_n > 8))   // 8 = CB200_MAX_FIM of the read-out kernels
+            return fail(CB200_ERR_ARG, "fim_n = %d with a Fisher block (fim_offset > 0): need 1 <= fim_n <= 8", d->fim_n);
+    }
     if (d->n_controls < 0 || d->n_controls > MAX_CTRL) return fail(CB200_ERR_ARG, "n_controls out of range");
     if (d->np_all > MAX_NP) return fail(CB200_ERR_ARG, "np_all too large");
     if (d->n_tunable_p + d->n_controls != d->np_all)
@@ -1117,6 +985,15 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         int rc = dense20_set_data(d->model_data, d->model_data_len);
         if (rc != 0) return bail("cudaMemcpyToSymbol(dense20)", (cudaError_t)rc);
     }
+    {   // accumulators of the cross-candidate sums, zero at rest (handle.cuh)
+        const size_t n_acc = (size_t)(1 + L.nvars + h->fim_n * h->fim_n);
+        e = cudaMalloc((void **)&h->acc, sizeof(double) * n_acc + 16);
+        if (e != cudaSuccess) return bail("cudaMalloc(acc)", e);
+        e = cudaMemset(h->acc, 0, sizeof(double) * n_acc + 16);
+        if (e != cudaSuccess) return bail("cudaMemset(acc)", e);
+        h->tail_counter = (unsigned *)(h->acc + n_acc);
+        h->graphs_enabled = getenv("CB200_NO_GRAPH") == nullptr;
+    }
     e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
     if (e != cudaSuccess) return bail("cudaStreamCreate", e);
     h->own_stream = true;
@@ -1144,6 +1021,11 @@ extern "C" int cb200_destroy(cb200_handle *h)
     if (!h) return CB200_OK;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    comm_release(h);
+    for (SmallGraph &g : h->graphs)
+        if (g.exec) cudaGraphExecDestroy(g.exec);
+    h->graphs.clear();
+    if (h->acc) cudaFree(h->acc);
     if (h->d20_ref) {
         std::lock_guard<std::mutex> lk(g_d20_mu);
         g_d20[h->device & 63].refs--;
@@ -1295,20 +1177,47 @@ struct EvalPlan {
     int gradc_first, gradc_n;   // compact gradient: variables [gradc_first, gradc_first + gradc_n)
     bool fused_grad, need_sens, need_xend, need_traj;
     int obj_state, obj_ctrl_var, obj_quad, objective_row;
+    bool fused_fim;             // the shooting kernel does the Fisher read-out itself (OED models, FIM_END)
+    bool reduce, gather;        // CB200_COMM_REDUCE / CB200_COMM_GATHER
+    long long B_total, b0;      // all-gather: candidates of all ranks, this rank's first
 };
 
-// device SoA buffers of one batch (or one chunk of it), leading dimension = its candidate count
+// where the kind-major defects of one batch (or chunk) go: the compact block of the evaluation, or this rank's columns
+// of the all-gather window together with every peer's window (P2P transport)
+struct GatherPlan {
+    double *dk = nullptr;       // local destination, [pos * ldk + b]
+    long long ldk = 0;
+    double *const *peers = nullptr;
+    long long peer_off = 0;
+    int n_peers = 0, self = 0;
+};
+
+// device SoA buffers of one batch (or one chunk of it): [q * ldo + b]
 struct DevSet {
     double *xend = nullptr, *sens = nullptr, *traj = nullptr, *dk = nullptr, *ds = nullptr, *obj = nullptr,
            *grad = nullptr, *fim = nullptr, *objq = nullptr, *jac = nullptr, *crit = nullptr, *gradc = nullptr, *tsens = nullptr;
     int *status = nullptr;      // [B] of the batch / chunk
-    double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // shared by all chunks (atomic accumulation)
+    double *osum = nullptr, *gsum = nullptr, *fsum = nullptr;   // the handle's accumulators (shared by all chunks)
     const double *finit = nullptr;
+    GatherPlan gp;
 };
 
+// OED models whose end-state Fisher read-out the shooting kernel can do in its epilogue (models.cuh: FIM_N, FIM_OFF)
+static bool model_fuses_fim(int model, int *n, int *off)
+{
+    switch (model) {
+    case CB200_MODEL_LOTKA2_OED:
+    case CB200_MODEL_LOTKA2_OED_CU: *n = 2; *off = 6; return true;
+    case CB200_MODEL_LIN1D_OED: *n = 1; *off = 2; return true;
+    default: return false;
+    }
+}
+
 // The device pipeline of one batch on one stream: K1/K2 with the fused K3 epilogue, then the small kernels.
-static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long long d_ldb, long long B, const EvalPlan &pl,
-                     const DevSet &d)
+// ldo: leading dimension of every result (>= B: a chunk writes its columns of the whole batch's buffers).
+// tail: carried by the last kernel of the pipeline (nullptr: the caller runs the tail itself, after joining its chunks).
+static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long long d_ldb, long long B, long long ldo,
+                     const EvalPlan &pl, const DevSet &d, const TailArgs *tail)
 {
     const DevLayer &L0 = h->L;
     const int nx = L0.nx, I = L0.I;
@@ -1329,12 +1238,19 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
         L.i0 = h->range_i0;
         L.In = h->range_n;
         const struct { double *p; long long n; } z[] = {
-            {d.xend, (long long)nx * I}, {d.sens, h->n_sens}, {d.traj, nrow * h->n_samples}, {d.dk, ndef}, {d.ds, ndef},
+            {d.xend, (long long)nx * I}, {d.sens, h->n_sens}, {d.traj, nrow * h->n_samples}, {d.gp.dk, ndef}, {d.ds, ndef},
             {d.grad, L0.nvars}, {d.objq, I}, {d.jac, h->jac_nnz_var}, {d.gradc, pl.gradc_n}, {d.tsens, h->n_tsens}};
         for (const auto &e : z)
-            if (e.p && e.n > 0) CUDA_TRY(cudaMemsetAsync(e.p, 0, sizeof(double) * (size_t)e.n * (size_t)B, st));
+            if (e.p && e.n > 0) {
+                const long long ld = (e.p == d.gp.dk) ? d.gp.ldk : ldo;
+                CUDA_TRY(cudaMemset2DAsync(e.p, sizeof(double) * (size_t)ld, 0, sizeof(double) * (size_t)B, (size_t)e.n, st));
+            }
         if (L.In == 0) {   // nothing to integrate on this device: the outputs are the zeros
             if (pl.obj && d.obj) CUDA_TRY(cudaMemsetAsync(d.obj, 0, sizeof(double) * (size_t)B, st));
+            if (tail && (tail->nseg > 0 || tail->barrier)) {
+                tail_kernel<<<1, 256, 0, st>>>(*tail);
+                h->launches++;
+            }
             return CB200_OK;
         }
     }
@@ -1343,8 +1259,13 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     so.sens = d.sens;
     so.traj = d.traj;
     so.tsens = d.tsens;
-    so.ldo = B;
-    so.dk = ndef > 0 ? d.dk : nullptr;
+    so.ldo = ldo;
+    so.dk = ndef > 0 ? d.gp.dk : nullptr;
+    so.ldk = d.gp.ldk > 0 ? d.gp.ldk : ldo;
+    so.dk_peers = d.gp.peers;
+    so.dk_peer_off = d.gp.peer_off;
+    so.n_dk_peers = (ndef > 0 && d.gp.dk) ? d.gp.n_peers : 0;
+    so.dk_self = d.gp.self;
     so.dst = ndef > 0 ? d.ds : nullptr;
     so.objq = d.objq;
     so.grad = pl.fused_grad ? d.grad : nullptr;
@@ -1355,6 +1276,13 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     so.status = d.status;
     so.obj_state = pl.obj_state;
     so.obj_all = pl.obj_quad;
+    if (pl.fused_fim) {
+        so.fim_fused = 1;
+        so.fim = d.fim;
+        so.fsum = d.fsum;
+        so.crit = d.crit;
+        so.finit = d.finit;
+    }
     const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
     CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], st));
     int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, st);
@@ -1366,38 +1294,71 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     CUDA_TRY(cudaEventRecord(h->ev1[ev_slot], st));
     h->n_timed++;
 
-    // ---- K3 remainder: objective sum over intervals, control-row gradient, trajectory quadratures, FIM
+    // ---- K3 remainder: control-row gradient, trajectory quadratures, FIM, objective sum over intervals (last: it
+    //      carries the tail)
     // a control-row objective lives on the last interval: under interval sharding only its owner reports it
     const bool owns_last = !partial || (L.i0 + L.In == I);
-    if ((pl.obj || pl.osum) && pl.obj_state < 0 && !owns_last) {
-        if (d.obj) CUDA_TRY(cudaMemsetAsync(d.obj, 0, sizeof(double) * (size_t)B, st));
-    } else if (pl.obj || pl.osum) {
-        objective_kernel<<<nblk(B, 256), 256, 0, st>>>(d.objq, B, d_ps, d_ldb, B, I, pl.obj_state >= 0, pl.obj_quad,
-                                                     pl.obj_ctrl_var, d.obj, d.osum);
-        h->launches++;
-    }
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {  // objective = a control row: the gradient is a unit vector
-        if (d.grad) CUDA_TRY(cudaMemsetAsync(d.grad, 0, sizeof(double) * (size_t)L0.nvars * (size_t)B, st));
+        if (d.grad) CUDA_TRY(cudaMemset2DAsync(d.grad, sizeof(double) * (size_t)ldo, 0, sizeof(double) * (size_t)B, (size_t)L0.nvars, st));
         if (owns_last) {
-            grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, B, d.gsum);
+            grad_kernel<<<dim3(nblk(B, 128), 1), 128, 0, st>>>(h->d_grad, 1, nullptr, B, B, d.grad, ldo, d.gsum);
             h->launches++;
         }
     }
     if (pl.need_traj && h->nquad > 0 && I > 1) {
-        traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, d.xend, B, B, nx, (int)nrow, I, L.samp_off, L.M,
+        traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, ldo, d.xend, ldo, B, nx, (int)nrow, I, L.samp_off, L.M,
                                                      h->d_quad, h->nquad);
         h->launches++;
     }
-    if (pl.fim || pl.fsum || pl.crit) {
+    const bool want_tail = tail && tail->counter && (tail->nseg > 0 || tail->barrier);
+    TailArgs none{};
+    const bool run_obj = (pl.obj || pl.osum) && !(pl.obj_state < 0 && !owns_last);
+    const bool run_fim = (pl.fim || pl.fsum || pl.crit) && !pl.fused_fim;
+    bool tail_done = false;
+    if (run_fim) {
+        const TailArgs &ta = (want_tail && !run_obj) ? *tail : none;
+        tail_done = want_tail && !run_obj;
         if (h->fim_mode == CB200_FIM_END)
-            fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, B, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, B, d.fsum, d.crit);
+            fim_kernel<<<nblk(B, 128), 128, 0, st>>>(d.xend, ldo, B, nx, I, h->fim_off, h->fim_n, d.finit, d.fim, ldo, d.fsum, d.crit, ta);
         else
-            fim_samples_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, B, B, (int)nrow, h->n_samples, d_ps, d_ldb, h->fim_mode,
+            fim_samples_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, ldo, B, (int)nrow, h->n_samples, d_ps, d_ldb, h->fim_mode,
                                                            h->fim_bx, h->fim_n, h->n_obs, h->fim_off, h->n_obs_rows,
-                                                           h->d_obs_sample, h->d_obs_var, d.finit, d.fim, B, d.fsum, d.crit);
+                                                           h->d_obs_sample, h->d_obs_var, d.finit, d.fim, ldo, d.fsum, d.crit, ta);
+        h->launches++;
+    }
+    if ((pl.obj || pl.osum) && !run_obj) {
+        if (d.obj) CUDA_TRY(cudaMemsetAsync(d.obj, 0, sizeof(double) * (size_t)B, st));
+    } else if (run_obj) {
+        objective_kernel<<<nblk(B, 256), 256, 0, st>>>(d.objq, ldo, d_ps, d_ldb, B, I, pl.obj_state >= 0, pl.obj_quad,
+                                                     pl.obj_ctrl_var, d.obj, d.osum, want_tail ? *tail : none);
+        tail_done = want_tail;
+        h->launches++;
+    }
+    if (want_tail && !tail_done) {
+        tail_kernel<<<1, 256, 0, st>>>(*tail);
         h->launches++;
     }
     CUDA_TRY(cudaGetLastError());
+    return CB200_OK;
+}
+
+// copy / transpose a quantity-major device block [n][ld_in] (B live columns) to its destination
+static int deliver(cb200_handle *h, cudaStream_t st, const double *src, long long ld_in, long long n, long long B, double *dst,
+                   bool dst_soa, bool dst_host)
+{
+    if (n <= 0 || B <= 0) return CB200_OK;
+    const cudaMemcpyKind kind = dst_host ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    if (dst_soa) {
+        if (ld_in == B)
+            CUDA_TRY(cudaMemcpyAsync(dst, src, sizeof(double) * (size_t)n * (size_t)B, kind, st));
+        else
+            CUDA_TRY(cudaMemcpy2DAsync(dst, sizeof(double) * (size_t)B, src, sizeof(double) * (size_t)ld_in, sizeof(double) * (size_t)B,
+                                       (size_t)n, kind, st));
+        return CB200_OK;
+    }
+    if (dst_host) return fail(CB200_ERR_ARG, "internal: candidate-major host delivery goes through a staging buffer");
+    const int rc = transpose(h, st, src, ld_in, dst, n, n, B);
+    if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
     return CB200_OK;
 }
 
@@ -1407,7 +1368,9 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     NvtxRange nvtx_range("cb200_eval");
     if (!h || !out) return fail(CB200_ERR_ARG, "null argument");
     if (B < 0) return fail(CB200_ERR_ARG, "negative batch");
-    if (B == 0) return CB200_OK;
+    const bool collective = (flags & (CB200_COMM_REDUCE | CB200_COMM_GATHER)) != 0;
+    if (B == 0 && !collective) return CB200_OK;
+    if (B == 0) return fail(CB200_ERR_UNSUPPORTED, "a collective evaluation needs at least one candidate on every rank");
     if (!ps && h->L.nvars > 0) return fail(CB200_ERR_ARG, "null ps");
     std::lock_guard<std::mutex> lk(h->mu);
     CUDA_TRY(cudaSetDevice(h->device));
@@ -1416,32 +1379,44 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     bool dev = flags & CB200_MEM_DEVICE, ps_soa = flags & CB200_PS_SOA, out_soa = flags & CB200_OUT_SOA;
     if (ps_soa ? (ldb < B) : (ldb < nvars)) return fail(CB200_ERR_ARG, "ldb too small");
     if (B == 1) {   // one candidate (the reference's own use): both layouts coincide, no conversion kernels
-        ps_soa = out_soa = true;
+        ps_soa = true;
         ldb = 1;
+        if (!(flags & CB200_COMM_GATHER)) out_soa = true;
     }
     const long long nrow = nx + L0.nact;
     const long long ndef = (long long)h->defects.size();
     const int n2 = h->fim_n * h->fim_n;
+    const uint32_t res = out->resident;
+    auto on = [&](uint32_t bit, const void *p) { return (want & bit) && (p || (res & bit)); };
 
     EvalPlan pl{};
-    pl.sens = (want & CB200_WANT_SENS) && out->sens;
-    pl.grad = (want & CB200_WANT_GRAD) && out->grad;
-    pl.traj = (want & CB200_WANT_TRAJ) && out->traj;
-    pl.xend = (want & CB200_WANT_XEND) && out->xend;
-    pl.dk = (want & CB200_WANT_DEFECTS) && out->defects_kind;
+    pl.sens = on(CB200_WANT_SENS, out->sens);
+    pl.grad = on(CB200_WANT_GRAD, out->grad);
+    pl.traj = on(CB200_WANT_TRAJ, out->traj);
+    pl.xend = on(CB200_WANT_XEND, out->xend);
+    pl.dk = on(CB200_WANT_DEFECTS, out->defects_kind);
     pl.ds = (want & CB200_WANT_DEFECTS) && out->defects_stage;
-    pl.obj = (want & CB200_WANT_OBJ) && out->objective;
-    pl.fim = (want & CB200_WANT_FIM) && out->fim;
+    pl.obj = on(CB200_WANT_OBJ, out->objective);
+    pl.fim = on(CB200_WANT_FIM, out->fim);
     pl.fsum = (want & CB200_WANT_FIM) && out->fim_sum;
     pl.osum = (want & CB200_WANT_OBJ) && out->objective_sum;
     pl.gsum = (want & CB200_WANT_GRAD) && out->grad_sum;
-    pl.jac = (want & CB200_WANT_JAC) && out->jac_vals;
-    pl.crit = (want & CB200_WANT_CRIT) && out->criteria;
-    pl.gradc = (want & CB200_WANT_GRAD_COMPACT) && out->grad_compact;
-    pl.tsens = (want & CB200_WANT_TRAJ_SENS) && out->traj_sens;
+    pl.jac = on(CB200_WANT_JAC, out->jac_vals);
+    pl.crit = on(CB200_WANT_CRIT, out->criteria);
+    pl.gradc = on(CB200_WANT_GRAD_COMPACT, out->grad_compact);
+    pl.tsens = on(CB200_WANT_TRAJ_SENS, out->traj_sens);
+    pl.reduce = (flags & CB200_COMM_REDUCE) != 0;
+    pl.gather = (flags & CB200_COMM_GATHER) != 0;
+    if (collective && !h->comm) return fail(CB200_ERR_ARG, "CB200_COMM_REDUCE / CB200_COMM_GATHER need a communicator (cb200_comm_init)");
+    if (pl.gather) {
+        if (!(want & CB200_WANT_DEFECTS) || ndef == 0) return fail(CB200_ERR_ARG, "CB200_COMM_GATHER needs CB200_WANT_DEFECTS on a layer with shooting constraints");
+        pl.B_total = out->comm_B_total;
+        pl.b0 = out->comm_b0;
+    }
     if ((pl.fim || pl.fsum || pl.crit) && h->fim_off < 0) return fail(CB200_ERR_ARG, "layer has no Fisher block (fim_offset == 0)");
     if (pl.crit && h->fim_n > CB200_MAX_FIM) return fail(CB200_ERR_UNSUPPORTED, "criteria need fim_n <= %d", CB200_MAX_FIM);
-    if (h->range_n >= 0 && h->range_n < I) {
+    const bool partial = h->range_n >= 0 && h->range_n < I;
+    if (partial) {
         if (pl.fim || pl.fsum || pl.crit)
             return fail(CB200_ERR_UNSUPPORTED, "the Fisher read-out needs every interval on one device: reset cb200_set_interval_range");
         if (pl.traj && h->nquad > 0 && I > 1)
@@ -1469,60 +1444,136 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     }
     pl.need_sens = pl.sens || pl.fused_grad || pl.jac || pl.gradc || pl.tsens;   // sensitivity directions are integrated
     const bool any_fim = pl.fim || pl.fsum || pl.crit;
+    {
+        int fn = 0, fo = 0;
+        pl.fused_fim = any_fim && h->fim_mode == CB200_FIM_END && !partial && model_fuses_fim(h->model, &fn, &fo) &&
+                       fn == h->fim_n && fo == h->fim_off && !getenv("CB200_NO_FUSED_FIM");
+    }
     pl.need_traj = pl.traj || (any_fim && h->fim_mode != CB200_FIM_END);   // sample-based read-outs consume the samples
-    pl.need_xend = pl.xend || (any_fim && h->fim_mode == CB200_FIM_END) || (pl.need_traj && h->nquad > 0);
+    pl.need_xend = pl.xend || (any_fim && h->fim_mode == CB200_FIM_END && !pl.fused_fim) || (pl.need_traj && h->nquad > 0);
     const bool need_objq = (pl.obj || pl.osum) && pl.obj_state >= 0;
     if ((pl.grad || pl.gsum) && !pl.fused_grad) {
         h->h_grad.assign(1, GradEntry{pl.obj_ctrl_var, -1});
         CUDA_TRY(cudaMemcpyAsync(h->d_grad, h->h_grad.data(), sizeof(GradEntry), cudaMemcpyHostToDevice, h->stream));
     }
+    int rc = comm_check(h);
+    if (rc) return rc;
 
-    // per-candidate sizes (doubles) of every SoA result
-    struct Item { bool on; long long n; DevBuf *ws; double *user; double *DevSet::*slot; };
+    // per-candidate sizes (doubles) of every SoA result; user == nullptr: the result stays in the workspace
+    struct Item { bool on; long long n; DevBuf *ws; double *user; double *DevSet::*slot; uint32_t bit; };
+    auto usr = [&](uint32_t bit, double *p) { return (res & bit) ? nullptr : p; };
     const Item items[] = {
-        {pl.need_xend, (long long)nx * I, &h->ws_xend, pl.xend ? out->xend : nullptr, &DevSet::xend},
-        {pl.sens, h->n_sens, &h->ws_sens, out->sens, &DevSet::sens},
-        {pl.need_traj, nrow * h->n_samples, &h->ws_traj, pl.traj ? out->traj : nullptr, &DevSet::traj},
-        {pl.dk, ndef, &h->ws_dk, out->defects_kind, &DevSet::dk},
-        {pl.ds, ndef, &h->ws_ds, out->defects_stage, &DevSet::ds},
-        {pl.obj, 1, &h->ws_obj, out->objective, &DevSet::obj},
-        {pl.grad, nvars, &h->ws_grad, out->grad, &DevSet::grad},
-        {pl.fim, n2, &h->ws_fim, out->fim, &DevSet::fim},
-        {need_objq, I, &h->ws_objq, nullptr, &DevSet::objq},
-        {pl.jac, h->jac_nnz_var, &h->ws_jac, out->jac_vals, &DevSet::jac},
-        {pl.crit, 6, &h->ws_crit, out->criteria, &DevSet::crit},
-        {pl.gradc, pl.gradc_n, &h->ws_gradc, out->grad_compact, &DevSet::gradc},
-        {pl.tsens, h->n_tsens, &h->ws_tsens, out->traj_sens, &DevSet::tsens},
+        {pl.need_xend, (long long)nx * I, &h->ws_xend, pl.xend ? usr(CB200_WANT_XEND, out->xend) : nullptr, &DevSet::xend, CB200_WANT_XEND},
+        {pl.sens, h->n_sens, &h->ws_sens, usr(CB200_WANT_SENS, out->sens), &DevSet::sens, CB200_WANT_SENS},
+        {pl.need_traj, nrow * h->n_samples, &h->ws_traj, pl.traj ? usr(CB200_WANT_TRAJ, out->traj) : nullptr, &DevSet::traj, CB200_WANT_TRAJ},
+        {pl.dk && !pl.gather, ndef, &h->ws_dk, usr(CB200_WANT_DEFECTS, out->defects_kind), &DevSet::dk, CB200_WANT_DEFECTS},
+        {pl.ds, ndef, &h->ws_ds, out->defects_stage, &DevSet::ds, 0u},
+        {pl.obj, 1, &h->ws_obj, usr(CB200_WANT_OBJ, out->objective), &DevSet::obj, CB200_WANT_OBJ},
+        {pl.grad, nvars, &h->ws_grad, usr(CB200_WANT_GRAD, out->grad), &DevSet::grad, CB200_WANT_GRAD},
+        {pl.fim, n2, &h->ws_fim, usr(CB200_WANT_FIM, out->fim), &DevSet::fim, CB200_WANT_FIM},
+        {need_objq, I, &h->ws_objq, nullptr, &DevSet::objq, 0u},
+        {pl.jac, h->jac_nnz_var, &h->ws_jac, usr(CB200_WANT_JAC, out->jac_vals), &DevSet::jac, CB200_WANT_JAC},
+        {pl.crit, 6, &h->ws_crit, usr(CB200_WANT_CRIT, out->criteria), &DevSet::crit, CB200_WANT_CRIT},
+        {pl.gradc, pl.gradc_n, &h->ws_gradc, usr(CB200_WANT_GRAD_COMPACT, out->grad_compact), &DevSet::gradc, CB200_WANT_GRAD_COMPACT},
+        {pl.tsens, h->n_tsens, &h->ws_tsens, usr(CB200_WANT_TRAJ_SENS, out->traj_sens), &DevSet::tsens, CB200_WANT_TRAJ_SENS},
     };
+    h->resident_valid = 0;
+    h->last_B = B;
+    h->gradc_n_last = pl.gradc_n;
 
-    // ---- cross-candidate sums (expectation-type objective / gradient, FIM): accumulated on the device
-    DevSet shared{};
-    {
-        if (dev) {
-            shared.osum = pl.osum ? out->objective_sum : nullptr;
-            shared.gsum = pl.gsum ? out->grad_sum : nullptr;
-            shared.fsum = pl.fsum ? out->fim_sum : nullptr;
-        } else if (pl.osum || pl.gsum || pl.fsum) {
-            if (h->ws_sums.reserve(sizeof(double) * (size_t)(nvars + 1 + n2))) return fail(CB200_ERR_NOMEM, "device out of memory");
-            double *base = (double *)h->ws_sums.p;
-            shared.osum = pl.osum ? base : nullptr;
-            shared.gsum = pl.gsum ? base + 1 : nullptr;
-            shared.fsum = pl.fsum ? base + 1 + nvars : nullptr;
-        }
-        if (shared.osum && shared.gsum == shared.osum + 1) {   // one accumulator block [objective | gradient]: one memset
-            CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double) * (size_t)(nvars + 1), h->stream));
-        } else {
-            if (shared.osum) CUDA_TRY(cudaMemsetAsync(shared.osum, 0, sizeof(double), h->stream));
-            if (shared.gsum) CUDA_TRY(cudaMemsetAsync(shared.gsum, 0, sizeof(double) * (size_t)nvars, h->stream));
-        }
-        if (shared.fsum) CUDA_TRY(cudaMemsetAsync(shared.fsum, 0, sizeof(double) * n2, h->stream));
-        if (out->fim_init && (pl.fim || pl.fsum || pl.crit)) {
-            if (h->ws_finit.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
-            CUDA_TRY(cudaMemcpyAsync(h->ws_finit.p, out->fim_init, sizeof(double) * n2,
-                                     dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
-            shared.finit = (const double *)h->ws_finit.p;
-        }
+    // ---- cross-candidate sums (expectation-type objective / gradient, FIM): the kernels accumulate into the handle's
+    //      block (zero at rest); the tail of the evaluation's last kernel hands them on and clears the block
+    if (h->acc_dirty) {
+        CUDA_TRY(cudaMemsetAsync(h->acc, 0, sizeof(double) * (size_t)(1 + nvars + n2), h->stream));
+        CUDA_TRY(cudaMemsetAsync(h->tail_counter, 0, sizeof(unsigned), h->stream));
+        h->acc_dirty = false;
     }
+    DevSet shared{};
+    shared.osum = pl.osum ? h->acc : nullptr;
+    shared.gsum = pl.gsum ? h->acc + 1 : nullptr;
+    shared.fsum = pl.fsum ? h->acc + 1 + nvars : nullptr;
+    TailArgs tail{};
+    tail.counter = h->tail_counter;
+    tail.acc = h->acc;
+    auto add_seg = [&](bool want_it, int off, int len, double *dst) {
+        if (want_it) tail.seg[tail.nseg++] = TailSeg{off, len, dst};
+    };
+    if (out->fim_init && any_fim) {
+        if (h->ws_finit.reserve(sizeof(double) * n2)) return fail(CB200_ERR_NOMEM, "device out of memory");
+        CUDA_TRY(cudaMemcpyAsync(h->ws_finit.p, out->fim_init, sizeof(double) * n2,
+                                 dev ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+        shared.finit = (const double *)h->ws_finit.p;
+    }
+    // ---- communicator: open the epoch; all-gathered defects go straight into the windows on the P2P transport
+    ShootOut comm_so{};
+    double *gather_local = nullptr;   // this rank's columns inside its own window (P2P), [pos * B_total + b]
+    if (collective) {
+        rc = comm_begin(h, pl.reduce, pl.gather, B, pl.B_total, pl.b0, &tail, &comm_so, &gather_local);
+        if (rc) return rc;
+    }
+    const bool nccl_path = collective && !comm_is_p2p(h);
+    TailSeg real_seg[3];
+    int n_real = 0;
+    double *red_stage = nullptr;
+    long long n_stage = 0;
+    // set up the tail's destinations: dst_* are device pointers
+    auto plan_tail = [&](double *dst_o, double *dst_g, double *dst_f) -> int {
+        tail.nseg = 0;
+        add_seg(pl.osum, 0, 1, dst_o);
+        add_seg(pl.gsum, 1, nvars, dst_g);
+        add_seg(pl.fsum, 1 + nvars, n2, dst_f);
+        if (nccl_path && pl.reduce && tail.nseg > 0) {   // NCCL transport: the local sums are staged, all-reduced, then delivered
+            n_stage = 0;
+            for (int s = 0; s < tail.nseg; s++) n_stage += tail.seg[s].len;
+            red_stage = comm_red_stage(h, n_stage);
+            if (!red_stage) return fail(CB200_ERR_NOMEM, "device out of memory");
+            long long pos = 0;
+            n_real = tail.nseg;
+            for (int s = 0; s < tail.nseg; s++) {
+                real_seg[s] = tail.seg[s];
+                tail.seg[s].dst = red_stage + pos;
+                pos += tail.seg[s].len;
+            }
+        }
+        return CB200_OK;
+    };
+    // the gather plan of a batch whose first candidate is column c0 of the evaluation
+    auto gather_plan = [&](double *compact, long long ld_compact, long long c0) {
+        GatherPlan g;
+        if (pl.gather && gather_local) {
+            g.dk = gather_local + c0;
+            g.ldk = pl.B_total;
+            g.peers = comm_so.dk_peers;
+            g.peer_off = comm_so.dk_peer_off + c0;
+            g.n_peers = comm_so.n_dk_peers;
+            g.self = comm_so.dk_self;
+        } else {
+            g.dk = compact ? compact + c0 : nullptr;
+            g.ldk = ld_compact;
+        }
+        return g;
+    };
+    // after the pipeline: NCCL collectives, then the all-gathered defects to the caller
+    auto finish_comm = [&](cudaStream_t st, const double *dk_compact, bool to_host) -> int {
+        if (nccl_path) {
+            const int r2 = comm_finish_nccl(h, st, red_stage, n_stage, real_seg, n_real, pl.gather ? dk_compact : nullptr, ndef, B);
+            if (r2) return r2;
+        }
+        if (pl.gather && out->defects_gathered) {
+            const double *g = comm_gather_ptr(h);
+            if (out_soa || !to_host) return deliver(h, st, g, pl.B_total, ndef, pl.B_total, out->defects_gathered, out_soa, to_host);
+            // candidate-major host matrix: transpose on the device, one contiguous copy back
+            if (h->ws_out.reserve(sizeof(double) * (size_t)ndef * (size_t)pl.B_total)) return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+            const int r3 = transpose(h, st, g, pl.B_total, (double *)h->ws_out.p, ndef, ndef, pl.B_total);
+            if (r3) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)r3));
+            CUDA_TRY(cudaMemcpyAsync(out->defects_gathered, h->ws_out.p, sizeof(double) * (size_t)ndef * (size_t)pl.B_total,
+                                     cudaMemcpyDeviceToHost, st));
+        }
+        return CB200_OK;
+    };
+    // compact local defect block: needed without an all-gather, and as the NCCL all-gather's send buffer
+    const bool need_dk_compact = pl.gather && (nccl_path || !gather_local);
+    h->acc_dirty = pl.osum || pl.gsum || pl.fsum;
 
     // =================================================================== device pointers: one pass
     if (dev) {
@@ -1531,7 +1582,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         long long d_ldb = ldb;
         if (nvars > 0 && !ps_soa) {
             if (h->ws_ps.reserve(sizeof(double) * (size_t)nvars * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory (ps)");
-            int rc = transpose(h, h->stream, ps, ldb, (double *)h->ws_ps.p, B, B, nvars);
+            rc = transpose(h, h->stream, ps, ldb, (double *)h->ws_ps.p, B, B, nvars);
             if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             d_ps = (const double *)h->ws_ps.p;
             d_ldb = B;
@@ -1545,20 +1596,37 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
                 if (it.ws->reserve(sizeof(double) * (size_t)it.n * (size_t)B))
                     return fail(CB200_ERR_NOMEM, "device out of memory for result buffers (B=%lld)", (long long)B);
                 d.*(it.slot) = (double *)it.ws->p;
+                if (!it.user) h->resident_valid |= it.bit;
             }
         }
+        if (need_dk_compact) {
+            if (h->ws_dk.reserve(sizeof(double) * (size_t)ndef * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
+            d.dk = (double *)h->ws_dk.p;
+        }
+        d.gp = gather_plan(d.dk, B, 0);
         if (out->status) {   // int32 per candidate, the caller's device buffer
             d.status = out->status;
             CUDA_TRY(cudaMemsetAsync(d.status, 0, sizeof(int) * (size_t)B, h->stream));
         }
-        int rc = eval_core(h, h->stream, d_ps, d_ldb, B, pl, d);
+        rc = plan_tail(out->objective_sum, out->grad_sum, out->fim_sum);
         if (rc) return rc;
+        rc = eval_core(h, h->stream, d_ps, d_ldb, B, B, pl, d, &tail);
+        if (rc) return rc;
+        h->acc_dirty = false;
         if (!direct) {
             for (const Item &it : items) {
                 if (!it.on || !it.user) continue;
                 rc = transpose(h, h->stream, d.*(it.slot), B, it.user, it.n, it.n, B);
                 if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             }
+        }
+        if (pl.gather && gather_local && pl.dk && out->defects_kind && !(res & CB200_WANT_DEFECTS)) {   // the local view as well
+            rc = deliver(h, h->stream, gather_local, pl.B_total, ndef, B, out->defects_kind, direct, false);
+            if (rc) return rc;
+        }
+        if (collective) {
+            rc = finish_comm(h->stream, d.dk, false);
+            if (rc) return rc;
         }
         return CB200_OK;   // enqueued on the handle's stream
     }
@@ -1567,7 +1635,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     // (one candidate = the reference's own use, or a small variable-major batch): pageable caller arrays would make
     // every cudaMemcpyAsync a synchronous staged copy, so the inputs go through a pinned mirror with ONE H2D copy,
     // every result lands in ONE device buffer that comes back with ONE D2H copy, and the CPU scatters it.
-    {
+    if (!pl.gather) {
         size_t out_doubles = 0;
         for (const Item &it : items)
             if (it.on && it.user) out_doubles += (size_t)it.n * (size_t)B;
@@ -1582,8 +1650,6 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             // layout (doubles): [inputs | status ints (zeroed on the host: they travel with the inputs) | results ... | sums]
             if (in_doubles) memcpy(hp, ps, sizeof(double) * in_doubles);
             if (status_doubles) memset(hp + in_doubles, 0, sizeof(double) * status_doubles);
-            if (in_doubles + status_doubles)
-                CUDA_TRY(cudaMemcpyAsync(dp, hp, sizeof(double) * (in_doubles + status_doubles), cudaMemcpyHostToDevice, h->stream));
             DevSet d = shared;
             size_t off = in_doubles + status_doubles;
             for (const Item &it : items) {
@@ -1594,19 +1660,87 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
                 } else {
                     if (it.ws->reserve(sizeof(double) * (size_t)it.n * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
                     d.*(it.slot) = (double *)it.ws->p;
+                    h->resident_valid |= it.bit;
                 }
             }
-            const size_t sums_off = off;
-            if (pl.osum) { d.osum = dp + off; off += 1; }
-            if (pl.gsum) { d.gsum = dp + off; off += (size_t)nvars; }
-            if (pl.fsum) { d.fsum = dp + off; off += (size_t)n2; }
-            if (sums_doubles) CUDA_TRY(cudaMemsetAsync(dp + sums_off, 0, sizeof(double) * sums_doubles, h->stream));
+            d.gp = gather_plan(d.dk, B, 0);
+            double *dst_o = nullptr, *dst_g = nullptr, *dst_f = nullptr;
+            if (pl.osum) { dst_o = dp + off; off += 1; }
+            if (pl.gsum) { dst_g = dp + off; off += (size_t)nvars; }
+            if (pl.fsum) { dst_f = dp + off; off += (size_t)n2; }
             if (out->status) d.status = (int *)(dp + in_doubles);
-            int rc = eval_core(h, h->stream, in_doubles ? dp : nullptr, B, B, pl, d);
+            rc = plan_tail(dst_o, dst_g, dst_f);
             if (rc) return rc;
             const size_t back = sizeof(double) * (off - in_doubles);
-            if (back) CUDA_TRY(cudaMemcpyAsync(hp + in_doubles, dp + in_doubles, back, cudaMemcpyDeviceToHost, h->stream));
+            // the whole evaluation as one CUDA graph (captured once per shape of the request): a single launch instead
+            // of two copies and two to four kernels -- the call is latency-bound (BASELINE config 1)
+            SmallGraph *sg = nullptr;
+            const unsigned gkey = flags | (pl.fused_fim ? 0x80000000u : 0u);
+            const bool graphable = h->graphs_enabled && !collective && !partial && !(out->fim_init && any_fim) && !h->comm;
+            if (graphable) {
+                if (!h->graphs.empty() && h->graphs.front().gen != devbuf_generation()) {   // a workspace moved: the graphs hold stale pointers
+                    for (SmallGraph &g : h->graphs)
+                        if (g.exec) cudaGraphExecDestroy(g.exec);
+                    h->graphs.clear();
+                }
+                for (SmallGraph &g : h->graphs)
+                    if (g.want == want && g.objective_row == out->objective_row && g.B == B && g.has_status == (out->status != nullptr) &&
+                        g.tot == tot && g.dp == (void *)dp && g.res == res && g.flags == gkey)
+                        sg = &g;
+            }
+            if (sg) {
+                CUDA_TRY(cudaGraphLaunch(sg->exec, h->stream));
+                h->launches += sg->launches;
+            } else {
+                const bool capture = graphable && h->graphs.size() < 16;
+                const long long launches0 = h->launches, timed0 = h->n_timed;
+                if (capture) CUDA_TRY(cudaStreamBeginCapture(h->stream, cudaStreamCaptureModeThreadLocal));
+                cudaError_t ce = cudaSuccess;
+                if (in_doubles + status_doubles)
+                    ce = cudaMemcpyAsync(dp, hp, sizeof(double) * (in_doubles + status_doubles), cudaMemcpyHostToDevice, h->stream);
+                if (ce == cudaSuccess) {
+                    rc = eval_core(h, h->stream, in_doubles ? dp : nullptr, B, B, B, pl, d, &tail);
+                    if (rc == CB200_OK && back)
+                        ce = cudaMemcpyAsync(hp + in_doubles, dp + in_doubles, back, cudaMemcpyDeviceToHost, h->stream);
+                }
+                if (capture) {
+                    cudaGraph_t graph = nullptr;
+                    const cudaError_t ee = cudaStreamEndCapture(h->stream, &graph);
+                    h->n_timed = timed0;   // event records inside a capture carry no timing
+                    if (rc == CB200_OK && ce == cudaSuccess && ee == cudaSuccess && graph) {
+                        SmallGraph g;
+                        g.want = want; g.objective_row = out->objective_row; g.B = B; g.has_status = out->status != nullptr;
+                        g.tot = tot; g.dp = dp; g.res = res; g.flags = gkey; g.launches = h->launches - launches0;
+                        g.gen = devbuf_generation();
+                        if (cudaGraphInstantiate(&g.exec, graph, 0) == cudaSuccess) {
+                            h->graphs.push_back(g);
+                            ce = cudaGraphLaunch(g.exec, h->stream);
+                        } else {
+                            ce = cudaErrorUnknown;
+                        }
+                    } else if (ee != cudaSuccess && ce == cudaSuccess) {
+                        ce = ee;
+                    }
+                    if (graph) cudaGraphDestroy(graph);
+                    if (ce != cudaSuccess || rc != CB200_OK) {   // capture not possible here: never try again on this handle
+                        cudaGetLastError();
+                        h->graphs_enabled = false;
+                        if (rc == CB200_OK) return fail(CB200_ERR_CUDA, "graph capture of the small evaluation failed: %s", cudaGetErrorString(ce));
+                    }
+                }
+                if (rc) return rc;
+                if (ce != cudaSuccess) return fail(CB200_ERR_CUDA, "small evaluation failed: %s", cudaGetErrorString(ce));
+            }
+            if (collective) {
+                rc = finish_comm(h->stream, d.dk, true);
+                if (rc) return rc;
+                if (nccl_path && n_real) {   // the reduced sums were delivered to dp after the D2H copy above: fetch them
+                    const size_t so_off = off - sums_doubles;
+                    CUDA_TRY(cudaMemcpyAsync(hp + so_off, dp + so_off, sizeof(double) * sums_doubles, cudaMemcpyDeviceToHost, h->stream));
+                }
+            }
             CUDA_TRY(cudaStreamSynchronize(h->stream));
+            h->acc_dirty = false;
             if (out->status) memcpy(out->status, hp + in_doubles, sizeof(int) * (size_t)B);
             size_t o2 = in_doubles + status_doubles;
             for (const Item &it : items) {
@@ -1617,7 +1751,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             if (pl.osum) { *out->objective_sum = hp[o2]; o2 += 1; }
             if (pl.gsum) { memcpy(out->grad_sum, hp + o2, sizeof(double) * (size_t)nvars); o2 += (size_t)nvars; }
             if (pl.fsum) { memcpy(out->fim_sum, hp + o2, sizeof(double) * (size_t)n2); o2 += (size_t)n2; }
-            return CB200_OK;
+            return comm_check(h);
         }
     }
 
@@ -1625,7 +1759,8 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     // The batch is cut into chunks of candidates; chunk c runs on stream c % NS: host->device copy, layout
     // conversion, the kernels, conversion back and device->host copies.  With pinned caller buffers the copy
     // engines (one per direction) and the SMs overlap across chunks; the caller's buffers are chunk-contiguous
-    // in the candidate-major (Julia) layout, so every copy is one contiguous cudaMemcpyAsync.
+    // in the candidate-major (Julia) layout, so every copy is one contiguous cudaMemcpyAsync.  On the device every
+    // buffer holds the whole batch quantity-major, [q * B + b]; a chunk works on its columns.
     long long Bc = B;
     if (!ps_soa && !out_soa && B >= 1024) {
         Bc = ((B + 7) / 8 + 31) / 32 * 32;   // ~8 chunks, multiples of a warp
@@ -1636,7 +1771,6 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (v > 0 && !ps_soa && !out_soa) Bc = std::min<long long>(B, (v + 31) / 32 * 32);
     }
     const int nchunks = (int)((B + Bc - 1) / Bc);
-    // workspaces for the whole batch; chunk c owns the slice starting at b0 * n
     if (nvars > 0) {
         const size_t bytes = sizeof(double) * (size_t)nvars * (size_t)B;
         if (h->ws_ps.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (ps, %zu bytes)", bytes);
@@ -1648,9 +1782,27 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         if (it.ws->reserve(sizeof(double) * (size_t)it.n * (size_t)B))
             return fail(CB200_ERR_NOMEM, "device out of memory for result buffers (B=%lld)", (long long)B);
         if (it.user && !out_soa) stage_per_cand += (size_t)it.n;
+        if (!it.user) h->resident_valid |= it.bit;
     }
-    if (stage_per_cand && h->ws_out.reserve(sizeof(double) * stage_per_cand * (size_t)B))
-        return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+    const bool local_dk_from_window = pl.gather && gather_local && pl.dk && out->defects_kind && !(res & CB200_WANT_DEFECTS);
+    if (local_dk_from_window && !out_soa) stage_per_cand += (size_t)ndef;
+    if (need_dk_compact && h->ws_dk.reserve(sizeof(double) * (size_t)ndef * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
+    {   // staging for the candidate-major results of the chunks and, after them, of the all-gathered defects
+        size_t stage = stage_per_cand * (size_t)B;
+        if (pl.gather && out->defects_gathered && !out_soa) stage = std::max(stage, (size_t)ndef * (size_t)pl.B_total);
+        if (stage && h->ws_out.reserve(sizeof(double) * stage)) return fail(CB200_ERR_NOMEM, "device out of memory (staging)");
+    }
+    const size_t sums_doubles = (size_t)(pl.osum ? 1 : 0) + (pl.gsum ? (size_t)nvars : 0) + (pl.fsum ? (size_t)n2 : 0);
+    double *dst_o = nullptr, *dst_g = nullptr, *dst_f = nullptr;
+    if (sums_doubles) {
+        if (h->ws_sums.reserve(sizeof(double) * (size_t)(nvars + 1 + n2))) return fail(CB200_ERR_NOMEM, "device out of memory");
+        double *base = (double *)h->ws_sums.p;
+        dst_o = pl.osum ? base : nullptr;
+        dst_g = pl.gsum ? base + 1 : nullptr;
+        dst_f = pl.fsum ? base + 1 + nvars : nullptr;
+    }
+    rc = plan_tail(dst_o, dst_g, dst_f);
+    if (rc) return rc;
 
     if (out->status) {
         if (h->ws_status.reserve(sizeof(int) * (size_t)B)) return fail(CB200_ERR_NOMEM, "device out of memory");
@@ -1664,18 +1816,16 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));   // memsets / tables above are ordered before the chunks
         for (int k = 1; k < ns_used; k++) CUDA_TRY(cudaStreamWaitEvent(streams[k], h->ev_fork, 0));
     }
+    double *dk_compact = need_dk_compact ? (double *)h->ws_dk.p : nullptr;
     for (int c = 0; c < nchunks; c++) {
         const long long b0 = (long long)c * Bc, bn = std::min(Bc, B - b0);
         cudaStream_t st = streams[c % ns_used];
         const double *d_ps = nullptr;
         if (nvars > 0) {
-            double *soa = (double *)h->ws_ps.p + (size_t)b0 * nvars;   // chunk SoA block [nvars][bn]
+            double *soa = (double *)h->ws_ps.p + b0;   // the chunk's columns of [nvars][B]
             if (ps_soa) {  // host, variable-major (single chunk)
-                if (ldb == bn)
-                    CUDA_TRY(cudaMemcpyAsync(soa, ps, sizeof(double) * (size_t)nvars * (size_t)bn, cudaMemcpyHostToDevice, st));
-                else
-                    CUDA_TRY(cudaMemcpy2DAsync(soa, sizeof(double) * bn, ps + b0, sizeof(double) * ldb, sizeof(double) * bn,
-                                               nvars, cudaMemcpyHostToDevice, st));
+                CUDA_TRY(cudaMemcpy2DAsync(soa, sizeof(double) * (size_t)B, ps + b0, sizeof(double) * (size_t)ldb, sizeof(double) * (size_t)bn,
+                                           nvars, cudaMemcpyHostToDevice, st));
             } else {       // host, candidate-major (Julia nvars x B matrix)
                 double *stg = (double *)h->ws_in.p + (size_t)b0 * nvars;
                 if (ldb == nvars)
@@ -1684,44 +1834,116 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
                 else
                     CUDA_TRY(cudaMemcpy2DAsync(stg, sizeof(double) * nvars, ps + (size_t)b0 * ldb, sizeof(double) * ldb,
                                                sizeof(double) * nvars, bn, cudaMemcpyHostToDevice, st));
-                int rc = transpose(h, st, stg, nvars, soa, bn, bn, nvars);
+                rc = transpose(h, st, stg, nvars, soa, B, bn, nvars);
                 if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
             }
             d_ps = soa;
         }
         DevSet d = shared;
         for (const Item &it : items)
-            if (it.on) d.*(it.slot) = (double *)it.ws->p + (size_t)b0 * (size_t)it.n;
+            if (it.on) d.*(it.slot) = (double *)it.ws->p + b0;
+        if (dk_compact) d.dk = dk_compact + b0;
+        d.gp = gather_plan(d.dk ? d.dk - b0 : nullptr, B, b0);
         if (out->status) d.status = (int *)h->ws_status.p + b0;
-        int rc = eval_core(h, st, d_ps, bn, bn, pl, d);
+        rc = eval_core(h, st, d_ps, B, bn, B, pl, d, nchunks == 1 ? &tail : nullptr);
         if (rc) return rc;
         if (out->status)
             CUDA_TRY(cudaMemcpyAsync(out->status + b0, d.status, sizeof(int) * (size_t)bn, cudaMemcpyDeviceToHost, st));
         size_t stage_off = (size_t)b0 * stage_per_cand;
-        for (const Item &it : items) {
-            if (!it.on || !it.user) continue;
-            const size_t bytes = sizeof(double) * (size_t)it.n * (size_t)bn;
-            if (out_soa) {  // quantity-major host output (single chunk): rows are contiguous
-                CUDA_TRY(cudaMemcpyAsync(it.user, d.*(it.slot), bytes, cudaMemcpyDeviceToHost, st));
+        auto send_back = [&](const double *src, long long ld_in, long long n, double *user) -> int {
+            if (out_soa) {  // quantity-major host output (single chunk)
+                CUDA_TRY(cudaMemcpy2DAsync(user + b0, sizeof(double) * (size_t)B, src, sizeof(double) * (size_t)ld_in,
+                                           sizeof(double) * (size_t)bn, (size_t)n, cudaMemcpyDeviceToHost, st));
             } else {
                 double *stg = (double *)h->ws_out.p + stage_off;
-                stage_off += (size_t)it.n * (size_t)bn;
-                rc = transpose(h, st, d.*(it.slot), bn, stg, it.n, it.n, bn);
-                if (rc) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)rc));
-                CUDA_TRY(cudaMemcpyAsync(it.user + (size_t)b0 * (size_t)it.n, stg, bytes, cudaMemcpyDeviceToHost, st));
+                stage_off += (size_t)n * (size_t)bn;
+                const int r2 = transpose(h, st, src, ld_in, stg, n, n, bn);
+                if (r2) return fail(CB200_ERR_CUDA, "transpose launch failed: %s", cudaGetErrorString((cudaError_t)r2));
+                CUDA_TRY(cudaMemcpyAsync(user + (size_t)b0 * (size_t)n, stg, sizeof(double) * (size_t)n * (size_t)bn, cudaMemcpyDeviceToHost, st));
             }
+            return CB200_OK;
+        };
+        for (const Item &it : items) {
+            if (!it.on || !it.user) continue;
+            rc = send_back(d.*(it.slot), B, it.n, it.user);
+            if (rc) return rc;
+        }
+        if (local_dk_from_window) {
+            rc = send_back(gather_local + b0, pl.B_total, ndef, out->defects_kind);
+            if (rc) return rc;
         }
     }
     for (int k = 1; k < ns_used; k++) {   // join
         CUDA_TRY(cudaEventRecord(h->ev_join[k - 1], streams[k]));
         CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join[k - 1], 0));
     }
-    if (pl.osum) CUDA_TRY(cudaMemcpyAsync(out->objective_sum, shared.osum, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (nchunks > 1 && (tail.nseg > 0 || tail.barrier)) {
+        tail_kernel<<<1, 256, 0, h->stream>>>(tail);
+        h->launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (collective) {
+        rc = finish_comm(h->stream, dk_compact, true);
+        if (rc) return rc;
+    }
+    if (pl.osum) CUDA_TRY(cudaMemcpyAsync(out->objective_sum, dst_o, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     if (pl.gsum)
-        CUDA_TRY(cudaMemcpyAsync(out->grad_sum, shared.gsum, sizeof(double) * (size_t)nvars, cudaMemcpyDeviceToHost, h->stream));
-    if (pl.fsum) CUDA_TRY(cudaMemcpyAsync(out->fim_sum, shared.fsum, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
+        CUDA_TRY(cudaMemcpyAsync(out->grad_sum, dst_g, sizeof(double) * (size_t)nvars, cudaMemcpyDeviceToHost, h->stream));
+    if (pl.fsum) CUDA_TRY(cudaMemcpyAsync(out->fim_sum, dst_f, sizeof(double) * n2, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(cudaStreamSynchronize(h->stream));
+    h->acc_dirty = false;
+    return comm_check(h);
+}
+
+extern "C" int cb200_resident(const cb200_handle *h, uint32_t want_bit, double **ptr, int64_t *ld)
+{
+    if (!h || !ptr) return fail(CB200_ERR_ARG, "null argument");
+    if (!(h->resident_valid & want_bit)) return fail(CB200_ERR_ARG, "no device-resident result for want bit 0x%x from the last evaluation", want_bit);
+    const DevBuf *b = nullptr;
+    switch (want_bit) {
+    case CB200_WANT_XEND: b = &h->ws_xend; break;
+    case CB200_WANT_SENS: b = &h->ws_sens; break;
+    case CB200_WANT_TRAJ: b = &h->ws_traj; break;
+    case CB200_WANT_DEFECTS: b = &h->ws_dk; break;
+    case CB200_WANT_OBJ: b = &h->ws_obj; break;
+    case CB200_WANT_GRAD: b = &h->ws_grad; break;
+    case CB200_WANT_FIM: b = &h->ws_fim; break;
+    case CB200_WANT_JAC: b = &h->ws_jac; break;
+    case CB200_WANT_CRIT: b = &h->ws_crit; break;
+    case CB200_WANT_GRAD_COMPACT: b = &h->ws_gradc; break;
+    case CB200_WANT_TRAJ_SENS: b = &h->ws_tsens; break;
+    default: return fail(CB200_ERR_ARG, "want_bit must be exactly one CB200_WANT_* bit");
+    }
+    *ptr = (double *)b->p;
+    if (ld) *ld = h->last_B;
     return CB200_OK;
+}
+
+extern "C" int cb200_abi_layout(int32_t which, int64_t *vals, int32_t n)
+{
+    if (!vals || n <= 0) return 0;
+    std::vector<int64_t> v;
+    switch (which) {
+    case 0:
+        v = {(int64_t)sizeof(cb200_desc), (int64_t)offsetof(cb200_desc, u0), (int64_t)offsetof(cb200_desc, model_data_len),
+             (int64_t)offsetof(cb200_desc, observation_grid), (int64_t)offsetof(cb200_desc, reltol)};
+        break;
+    case 1:
+        v = {(int64_t)sizeof(cb200_out), (int64_t)offsetof(cb200_out, objective_row), (int64_t)offsetof(cb200_out, jac_vals),
+             (int64_t)offsetof(cb200_out, status), (int64_t)offsetof(cb200_out, defects_gathered), (int64_t)offsetof(cb200_out, comm_b0),
+             (int64_t)offsetof(cb200_out, resident)};
+        break;
+    case 2:
+        v = {(int64_t)sizeof(cb200_sizes), (int64_t)offsetof(cb200_sizes, n_traj_sens)};
+        break;
+    case 3:
+        v = {(int64_t)sizeof(cb200_comm_info), (int64_t)offsetof(cb200_comm_info, epoch), (int64_t)offsetof(cb200_comm_info, error)};
+        break;
+    default: return 0;
+    }
+    const int m = std::min<int>(n, (int)v.size());
+    for (int k = 0; k < m; k++) vals[k] = v[(size_t)k];
+    return m;
 }
 
 // forward_initialization(rng, shooting; ps, fixed_indices) (src/node_initialization.jl:152-170) for B candidates:

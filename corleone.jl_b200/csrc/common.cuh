@@ -57,6 +57,39 @@ struct MatchEntry {  // defect = ps[a] - ps[b]  (parameter and control matchings
     int a, b, pos_kind, pos_stage;
 };
 
+// ---- multi-GPU data plane (comm.cu): peer-mapped windows of the ranks of one box, one rank per GPU.
+constexpr int MAX_RANKS = 16;
+constexpr int FLAG_STRIDE = 16;   // one 128-byte line per flag
+// Device-resident table of one handle's communicator.  Rank p's window is mapped into this process at slots[p] /
+// flags[p] / gather[p] (CUDA IPC between processes, plain peer access between the threads of one process).
+struct CommPeers {
+    int nranks, rank;
+    int s_cap;                                    // doubles per sums slot
+    double *slots[MAX_RANKS];                     // [2][nranks][s_cap]: slot (parity, q) of rank p's window is written by rank q
+    unsigned long long *flags[MAX_RANKS];         // [2][nranks][FLAG_STRIDE]: flag (parity, q) of rank p is set by rank q
+    double *gather[MAX_RANKS];                    // [2][gather_cap]: all-gathered defects, [row][B_total] per parity
+    long long gather_cap;                         // doubles per parity buffer
+    unsigned long long *err;                      // host-mapped error word of THIS rank (0 = fine)
+    long long timeout_ns;                         // a peer that does not show up within this time is reported, not waited for
+};
+struct TailSeg {
+    int off, len;      // segment of the accumulator block
+    double *dst;       // where the finished sums go (device pointer)
+};
+// Tail of the LAST kernel of an evaluation (tail.cuh): the last block to finish hands the cross-candidate sums to their
+// destination -- all-reduced over the ranks by a one-shot exchange through the peer windows -- clears the accumulators
+// and closes the epoch (signal to / wait for every peer: their all-gathered defects have landed).
+struct TailArgs {
+    unsigned *counter;           // nullptr: this kernel carries no tail
+    double *acc;
+    TailSeg seg[3];
+    int nseg;
+    const CommPeers *peers;      // nullptr: single rank
+    unsigned long long epoch;    // >= 1, the same on every rank
+    int exchange;                // all-reduce the segments across the ranks
+    int barrier;                 // signal + wait even without segments (all-gather completion)
+};
+
 struct ShootOut {
     double *xend;  // [(i*nx + k) * ldo + b]
     double *sens;  // [(sens_off[i] + d*nx + k) * ldo + b]
@@ -75,6 +108,18 @@ struct ShootOut {
     int *status;       // [b] failure flags (atomicOr): bit 0 = a non-finite end state on some interval
     int obj_state;     // 0-based state row of the objective, -1: none
     int obj_all;       // 1: every interval contributes to the objective (quadrature state), 0: last interval only
+    long long ldk;     // leading dimension of dk (= ldo, or the candidates of ALL ranks when the defects are all-gathered)
+    // fused all-gather of the kind-major defects: the same value also goes to rank p's window dk_peers[p] + dk_peer_off
+    // (P2P stores over NVLink), p != dk_self; n_dk_peers == 0: none
+    double *const *dk_peers;
+    long long dk_peer_off;
+    int n_dk_peers, dk_self;
+    // fused Fisher read-out of the OED models (FIM_END): threads of the last interval emit F = F_init + Symmetric(F_triu)
+    double *fim;       // [(r + n c) * ldo + b] or nullptr
+    double *fsum;      // [n*n] accumulators (warp shuffle + atomicAdd) or nullptr
+    double *crit;      // [6][ldo] or nullptr
+    const double *finit;
+    int fim_fused;     // 1: the kernel does the read-out
 };
 
 // launchers, one per model translation unit; return cudaError_t as int, or -1000 if (G, method) is not

@@ -21,6 +21,17 @@ namespace cb200 {
 
 #define CB_DEV static __device__ __forceinline__
 
+// FimTraits<M>::N > 0: model M carries an n x n Fisher block F_triu at state offset OFF whose end value the shooting
+// kernel reads out itself (OedAug below); 0 for every other model
+template <class M, class = void>
+struct FimTraits {
+    static constexpr int N = 0, OFF = 0;
+};
+template <class M>
+struct FimTraits<M, decltype((void)M::FIM_N, void())> {
+    static constexpr int N = M::FIM_N, OFF = M::FIM_OFF;
+};
+
 #ifdef CB200_NEED_DENSE20_DATA
 // model constants for DENSE20 (W row-major 20x20, then b[20]); constant-bank operands of the FMAs
 __constant__ double c_dense20[420];
@@ -240,6 +251,8 @@ struct OedAug {
     static constexpr int NQ = (MODE == OED_DS || MODE == OED_DU) ? 0 : (MODE == OED_CF ? NOBS * NTRI : NTRI);
     static constexpr int NX = NXD + NQ, NP = Base::NP + NW;
     static constexpr bool HAS_JVP = true;
+    // end-state Fisher read-out the shooting kernel can fuse into its epilogue (one F_triu block: CS and CU)
+    static constexpr int FIM_N = (MODE == OED_CS || MODE == OED_CU) ? NF : 0, FIM_OFF = NXD;
     struct Ctx {
         typename Base::Ctx base;
     };

@@ -27,9 +27,20 @@
 #pragma once
 #include "common.cuh"
 #include "tableau.cuh"
+#include "fim.cuh"
 #include <cstdlib>
 
 namespace cb200 {
+
+// kind-major defect `pos` of candidate column b: to the local block and -- fused all-gather -- to every peer's window
+// (P2P stores over NVLink; tail.cuh has the completion protocol)
+__device__ __forceinline__ void store_defect(const ShootOut &o, long long pos, long long b, double dd)
+{
+    const long long q = pos * o.ldk + b;
+    o.dk[q] = dd;
+    for (int p = 0; p < o.n_dk_peers; p++)
+        if (p != o.dk_self) (o.dk_peers[p] + o.dk_peer_off)[q] = dd;
+}
 
 // rhs of [x; S_1..S_G] at dynamic stage values td -> dynamic derivatives kd, quadrature derivatives kq
 template <class Mdl, int G>
@@ -337,10 +348,13 @@ __device__ __forceinline__ void integrate_active(int na, double *yd, double *yq,
     if constexpr (GA == 0) {
         integrate_piece<Mdl, 0, METHOD, SQ>(yd, yq, p, F, cf, K);
     } else {
-        if (na >= GA)
+        // instantiated prefix lengths: G, then every second one down to 4, then 3, 2, 1, 0.  The piece runs the
+        // SMALLEST instantiated length >= na (a shorter one would drop live directions)
+        constexpr int NEXT = GA > 4 ? GA - 2 : GA - 1;
+        if (na > NEXT)
             integrate_piece<Mdl, GA, METHOD, SQ>(yd, yq, p, F, cf, K);
         else
-            integrate_active<Mdl, G, METHOD, SQ, (GA > 4 ? GA - 2 : GA - 1)>(na, yd, yq, p, F, cf, K);
+            integrate_active<Mdl, G, METHOD, SQ, NEXT>(na, yd, yq, p, F, cf, K);
     }
 }
 
@@ -564,7 +578,7 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
                     const int src = __ldg(L.ic_src + (i + 1) * NX + k);
                     const double nxt = (src >= 0) ? ps[(long long)(vn + src) * ldb + b] : __ldg(L.ic_fix + (i + 1) * NX + k);
                     const double dd = CB200_XS(k) - nxt;
-                    if (o.dk) o.dk[(long long)pk * o.ldo + b] = dd;
+                    if (o.dk) store_defect(o, pk, b, dd);
                     if (o.dst) o.dst[(long long)__ldg(L.dpos_stage + i * NX + k) * o.ldo + b] = dd;
                 }
             }
@@ -572,9 +586,26 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
             for (int e = __ldg(L.oth_off + i); e < e1; e++) {  // parameter and control matchings
                 const MatchEntry t = L.oth[e];
                 const double dd = ps[(long long)t.a * ldb + b] - ps[(long long)t.b * ldb + b];
-                if (o.dk) o.dk[(long long)t.pos_kind * o.ldo + b] = dd;
+                if (o.dk) store_defect(o, t.pos_kind, b, dd);
                 if (o.dst) o.dst[(long long)t.pos_stage * o.ldo + b] = dd;
             }
+        }
+    }
+    // K4 fused: F = F_init + Symmetric(F_triu(t_end)) of the LAST interval (lib/CorleoneOED/src/oed.jl:388-398), its sum
+    // over the candidates and the criteria, straight from the end state in registers (no second pass over xend)
+    if constexpr (FimTraits<Mdl>::N > 0) {
+        if (o.fim_fused && r == 0 && i == L.I - 1) {
+            constexpr int FN = FimTraits<Mdl>::N, FO = FimTraits<Mdl>::OFF;
+            double A[FN][FN];
+#pragma unroll
+            for (int c = 0; c < FN; c++)
+#pragma unroll
+                for (int rr = 0; rr < FN; rr++) {
+                    const int lo = rr < c ? rr : c, hi = rr < c ? c : rr;
+                    const int q = hi * (hi + 1) / 2 + lo;   // column-major triu position (augmentation.jl:239)
+                    A[rr][c] = CB200_XS(FO + q) + (o.finit ? __ldg(o.finit + rr + FN * c) : 0.0);
+                }
+            fim_emit<FN>(A, FN, live, b, o.fim, o.ldo, o.fsum, o.crit, !L.flat);
         }
     }
     if constexpr (G > 0) {

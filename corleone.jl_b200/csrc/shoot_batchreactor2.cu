@@ -7,7 +7,6 @@ int launch_batchreactor2(int G, int method, const DevLayer &L, const double *ps,
 {
     switch (G) {
         CB200_DISPATCH_GA(BatchReactor2, 0, 1)
-        CB200_DISPATCH_GA(BatchReactor2, 1, 1)
         CB200_DISPATCH_GA(BatchReactor2, 2, 1)
     default:
         return -1000;

@@ -8,7 +8,6 @@ int launch_cartpole5(int G, int method, const DevLayer &L, const double *ps, lon
     switch (G) {
         CB200_DISPATCH_GA(CartPole5, 0, 1)
         CB200_DISPATCH_GA(CartPole5, 1, 1)
-        CB200_DISPATCH_GA(CartPole5, 2, 1)
     default:
         return -1000;
     }

@@ -45,17 +45,33 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
 
 struct DenseTile {
     double Wf[15];   // B fragments of W^T: [kt*3 + nt]
-    bool is_x;       // x tile (warp 0)
-    bool on;         // tile has at least one live column
     bool col_on;     // this lane's column is live
-    int cand;        // candidate slot 0..CPB-1 of this lane's column
     int t;           // lane % 4
 };
 
-// k = W y + elementwise(y; x) for the lane's five states.  sx: [2][CPB][20] stage inputs of the x columns.
-// Every warp of the block calls this the same number of times (one __syncthreads inside).
-// The x tile publishes c = -3 x^2 (what the S tiles need) into `slot` ([CPB][20]).  PIPE = false: x and S tiles of the same unit
-// run in lockstep, one __syncthreads per call.  PIPE = true: the x tile ran ahead, `slot` already holds its value.
+// the lane's W^T fragments in the permuted state order (see header); loaded once per kernel
+__device__ __forceinline__ void dense_load_w(const DevLayer &L, DenseTile &T)
+{
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const double *W = L.model_data;   // row-major 20x20, then b[20]
+    T.t = t;
+#pragma unroll
+    for (int kt = 0; kt < 5; kt++)
+#pragma unroll
+        for (int nt = 0; nt < 3; nt++) {
+            // B[k = t][n = g]: k-state 5t + kt; n-slot g = 2 tau + e -> state 5 tau + 2 nt + e (nt = 2, e = 1: padding)
+            const int tau = g >> 1, e = g & 1;
+            const int sn = 5 * tau + 2 * nt + e;
+            T.Wf[kt * 3 + nt] = (nt == 2 && e == 1) ? 0.0 : __ldg(W + sn * DM_NX + (5 * t + kt));
+        }
+}
+
+// k = W y + elementwise(y; x) for the lane's five states.  `slot` = this lane's five entries of the exchange slot of this
+// right-hand-side call ([CPB][20] per call, already offset by candidate and state group).
+// The x tile publishes c = -3 x^2 (what the S tiles need).  PIPE = false: x and S tiles of the same unit run in lockstep, one
+// __syncthreads per call (every warp of the block calls this the same number of times).  PIPE = true: the x tile ran
+// ahead, `slot` already holds its value.  No predicate on idle tiles: a tile without live columns integrates zeros
+// (lockstep) or never gets here (pipelined), so the stage body is straight-line.
 template <bool PIPE, bool IS_X>
 __device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, const double *binit, double *k, double *slot)
 {
@@ -65,44 +81,47 @@ __device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, c
         for (int s = 0; s < 5; s++) q[s] = y[s] * y[s];
         if (T.col_on) {
 #pragma unroll
-            for (int s = 0; s < 5; s++) slot[T.cand * DM_NX + 5 * T.t + s] = -3.0 * q[s];
+            for (int s = 0; s < 5; s++) slot[s] = -3.0 * q[s];
         }
     }
     // the accumulators start from the b-term of the piece: b u for the states, b for the running piece's control
-    // direction, 0 otherwise -- it costs no instruction
+    // direction, 0 otherwise (the C operand of the first DMMA of each chain)
     double d[6] = {binit[0], binit[1], binit[2], binit[3], binit[4], 0.0};
-    if (T.on) {
 #pragma unroll
-        for (int kt = 0; kt < 5; kt++) {
-            dmma884(d[0], d[1], y[kt], T.Wf[kt * 3 + 0]);
-            dmma884(d[2], d[3], y[kt], T.Wf[kt * 3 + 1]);
-            dmma884(d[4], d[5], y[kt], T.Wf[kt * 3 + 2]);
-        }
+    for (int kt = 0; kt < 5; kt++) {
+        dmma884(d[0], d[1], y[kt], T.Wf[kt * 3 + 0]);
+        dmma884(d[2], d[3], y[kt], T.Wf[kt * 3 + 1]);
+        dmma884(d[4], d[5], y[kt], T.Wf[kt * 3 + 2]);
     }
     if constexpr (!PIPE) __syncthreads();
-    if (T.on) {
-        if constexpr (IS_X) {  // f(x) = W x - x^3 + b u
+    if constexpr (IS_X) {  // f(x) = W x - x^3 + b u
 #pragma unroll
-            for (int s = 0; s < 5; s++) k[s] = fma(-q[s], y[s], d[s]);
-        } else {               // f_x v + f_u = W v - 3 x^2 v (+ b)
+        for (int s = 0; s < 5; s++) k[s] = fma(-q[s], y[s], d[s]);
+    } else {               // f_x v + f_u = W v - 3 x^2 v (+ b)
 #pragma unroll
-            for (int s = 0; s < 5; s++) k[s] = fma(slot[T.cand * DM_NX + 5 * T.t + s], y[s], d[s]);
-        }
+        for (int s = 0; s < 5; s++) k[s] = fma(slot[s], y[s], d[s]);
     }
 }
 
-// slot of the next right-hand-side call: two alternating slots (lockstep) or one slot per call of the item (pipelined)
-#define DM_RHS(y)                                                                 \
-    do {                                                                          \
-        dense_rhs<PIPE, IS_X>(T, y, binit, k, xc + slot_idx * (DM_CPB * DM_NX)); \
-        slot_idx = PIPE ? slot_idx + 1 : (slot_idx ^ 1);                          \
+// slot of the next right-hand-side call: two alternating slots (lockstep) or one slot per call of the item (pipelined);
+// sp walks the lane's entries of the slots, sp_alt is the lockstep partner
+#define DM_RHS(y)                                      \
+    do {                                               \
+        dense_rhs<PIPE, IS_X>(T, y, binit, k, sp);     \
+        if constexpr (PIPE) {                          \
+            sp += DM_CPB * DM_NX;                      \
+        } else {                                       \
+            double *tmp_ = sp;                         \
+            sp = sp_alt;                               \
+            sp_alt = tmp_;                             \
+        }                                              \
     } while (0)
 
 // One unit group (CPB candidates of interval i, direction round `round`) for the calling warp's tile.
 // xc: stage-exchange slots in shared memory.
 template <int METHOD, bool UNI, bool PIPE, bool IS_X>
 __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__restrict__ ps, long long ldb, long long B,
-                                           const ShootOut &o, int i, int round, long long b0, double *xc)
+                                           const ShootOut &o, int i, int round, long long b0, double *xc, DenseTile &T)
 {
     constexpr int NX = DM_NX, NCF = METHOD == 0 ? 21 : 4;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
@@ -110,33 +129,22 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
     const int nu0 = __ldg(L.n_u0 + i), nc = __ldg(L.n_c + i);
     const int ns = nu0 + L.ntp + nc;
     if (round > 0 && round * DM_DPR >= ns) return;   // uniform over the block
+    // pipelined: an S tile without a live column (the first interval has only the control directions) has nothing to
+    // integrate or to store -- the hand-over barriers live in the caller
+    if (PIPE && !IS_X && round * DM_DPR + (8 * (warp - 1)) / DM_CPB >= ns) return;   // warp-uniform
 
-    DenseTile T;
-    T.is_x = IS_X;
-    T.t = t;
-    const int col = 8 * (warp - 1) + g;                                      // S tiles: column among the 120 of this round
-    T.cand = IS_X ? (g < DM_CPB ? g : 0) : col % DM_CPB;
+    const int col = 8 * (warp - 1) + g;                                // S tiles: column among the 120 of this round
+    const int cand = IS_X ? (g < DM_CPB ? g : 0) : col % DM_CPB;
     const int dir = round * DM_DPR + col / DM_CPB;                     // S tiles: direction of this lane's column
-    long long b = b0 + T.cand;
+    long long b = b0 + cand;
     const bool cand_live = b < B;
     if (!cand_live) b = B - 1;
     T.col_on = IS_X ? (g < DM_CPB) : (dir < ns);
-    T.on = IS_X ? true : (round * DM_DPR + (8 * (warp - 1)) / DM_CPB < ns);   // warp-uniform: the tile's first column is live
     const bool store = T.col_on && cand_live;
-
-    // W^T fragments in the permuted state order (see header) and the lane's slice of b
-    {
-        const double *W = L.model_data;   // row-major 20x20, then b[20]
-#pragma unroll
-        for (int kt = 0; kt < 5; kt++)
-#pragma unroll
-            for (int nt = 0; nt < 3; nt++) {
-                // B[k = t][n = g]: k-state 5t + kt; n-slot g = 2 tau + e -> state 5 tau + 2 nt + e (nt = 2, e = 1: padding)
-                const int tau = g >> 1, e = g & 1;
-                const int sn = 5 * tau + 2 * nt + e;
-                T.Wf[kt * 3 + nt] = (nt == 2 && e == 1) ? 0.0 : __ldg(W + sn * NX + (5 * t + kt));
-            }
-    }
+    // the lane's five entries of the exchange slots
+    double *sp = xc + cand * DM_NX + 5 * t;
+    double *sp_alt = sp + DM_CPB * DM_NX;
+    (void)sp_alt;
 
     const int voff = __ldg(L.var_off + i);
     const double *__restrict__ v = ps + (long long)voff * ldb + b;
@@ -160,7 +168,6 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
     const int nrow = NX + L.nact;
     const bool last_interval = (i == L.I - 1);
     const double *__restrict__ vc = v + (long long)(nu0 + L.ntp) * ldb;
-    int slot_idx = 0;
 
     int ci_nx = __ldg(L.cidx + (long long)po * L.nact);
     double u_nx = vc[(long long)ci_nx * ldb];
@@ -314,7 +321,7 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
                     const int src = __ldg(L.ic_src + (i + 1) * NX + k);
                     const double nxt = (src >= 0) ? ps[(long long)(vn + src) * ldb + b] : __ldg(L.ic_fix + (i + 1) * NX + k);
                     const double dd = yd[s] - nxt;
-                    if (o.dk) o.dk[(long long)pk * o.ldo + b] = dd;
+                    if (o.dk) store_defect(o, pk, b, dd);
                     if (o.dst) o.dst[(long long)__ldg(L.dpos_stage + i * NX + k) * o.ldo + b] = dd;
                 }
             }
@@ -323,7 +330,7 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
                 for (int e = __ldg(L.oth_off + i); e < e1; e++) {
                     const MatchEntry m = L.oth[e];
                     const double dd = ps[(long long)m.a * ldb + b] - ps[(long long)m.b * ldb + b];
-                    if (o.dk) o.dk[(long long)m.pos_kind * o.ldo + b] = dd;
+                    if (o.dk) store_defect(o, m.pos_kind, b, dd);
                     if (o.dst) o.dst[(long long)m.pos_stage * o.ldo + b] = dd;
                 }
             }
@@ -358,31 +365,36 @@ shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restr
                        const ShootOut o)
 {
     __shared__ double sx[2 * DM_CPB * DM_NX];
+    DenseTile T;
+    dense_load_w(L, T);
     if ((threadIdx.x >> 5) == 0)   // both branches meet at the same barrier (id 0), once per right-hand-side call
-        dense_unit<METHOD, UNI, false, true>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
+        dense_unit<METHOD, UNI, false, true>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx, T);
     else
-        dense_unit<METHOD, UNI, false, false>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx);
+        dense_unit<METHOD, UNI, false, false>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx, T);
 }
 
 __device__ __forceinline__ void dm_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
 __device__ __forceinline__ void dm_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
 
 // Pipelined persistent kernel: one block per SM walks the unit groups; the x tile (warp 0) integrates the states
-// of group n+1 -- they do not depend on the sensitivities -- and leaves -3 x^2 of every stage in one of two
-// shared-memory item buffers while the 15 S tiles integrate group n from the other buffer WITHOUT any barrier
+// of later groups -- they do not depend on the sensitivities -- and leaves -3 x^2 of every stage in one of NBUF
+// shared-memory item buffers while the 15 S tiles integrate an earlier group from another buffer WITHOUT any barrier
 // between stages: the S warps drift apart and the DMMA phases of some overlap the DFMA phases of others.
-// Hand-over per item: named barriers FULL[buf] (x arrives, S wait) and EMPTY[buf] (S arrive, x waits).
-template <int METHOD, bool UNI>
+// Hand-over per item: named barriers FULL[buf] (x arrives, S wait) and EMPTY[buf] (S arrive, x waits); with NBUF
+// buffers the x tile may be up to NBUF - 1 items ahead.  The W fragments are loaded once per kernel.
+template <int METHOD, bool UNI, int NBUF>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 shoot_dense_mma_pipe_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
-                            const ShootOut o, long long n_items, int n_groups_lo, int rounds, int nst)
+                            const ShootOut o, long long n_items, int rounds, int nst)
 {
-    extern __shared__ double xcbuf[];   // [2][nst][CPB][20]
+    extern __shared__ double xcbuf[];   // [NBUF][nst][CPB][20]
     const bool is_x = (threadIdx.x >> 5) == 0;   // the oldest warp: schedulers that favour older warps keep it ahead
-    const long long per = (long long)nst * DM_CPB * DM_NX;
+    const int per = nst * DM_CPB * DM_NX;
+    DenseTile T;
+    dense_load_w(L, T);
     long long kcount = 0;
+    int buf = 0;
     for (long long n = blockIdx.x; n < n_items; n += gridDim.x, kcount++) {
-        const int buf = (int)(kcount & 1);
         // item -> (group, interval, round); intervals fastest so that a block's consecutive items share nothing but W
         const int i = (int)(n % L.In) + L.i0;
         const long long rest = n / L.In;
@@ -390,23 +402,24 @@ shoot_dense_mma_pipe_kernel(const __grid_constant__ DevLayer L, const double *__
         const long long grp = rest / rounds;
         double *xc = xcbuf + buf * per;
         if (is_x) {
-            if (kcount >= 2) dm_bar_sync(1 + 2 + buf);    // EMPTY[buf]: the S tiles are done with item kcount - 2
-            dense_unit<METHOD, UNI, true, true>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc);
+            if (kcount >= NBUF) dm_bar_sync(1 + NBUF + buf);    // EMPTY[buf]: the S tiles are done with item kcount - NBUF
+            dense_unit<METHOD, UNI, true, true>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc, T);
             __threadfence_block();
-            dm_bar_arrive(1 + buf);                        // FULL[buf]
+            dm_bar_arrive(1 + buf);                               // FULL[buf]
         } else {
-            dm_bar_sync(1 + buf);                          // FULL[buf]
-            dense_unit<METHOD, UNI, true, false>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc);
-            dm_bar_arrive(1 + 2 + buf);                    // EMPTY[buf]
+            dm_bar_sync(1 + buf);                                 // FULL[buf]
+            dense_unit<METHOD, UNI, true, false>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc, T);
+            dm_bar_arrive(1 + NBUF + buf);                        // EMPTY[buf]
         }
+        buf = (buf + 1 == NBUF) ? 0 : buf + 1;
     }
-    if (is_x) {   // consume the EMPTY signals of the last two items so that no barrier is left half-arrived
-        for (long long kk = kcount >= 2 ? kcount - 2 : 0; kk < kcount; kk++) dm_bar_sync(1 + 2 + (int)(kk & 1));
+    if (is_x) {   // consume the EMPTY signals of the last items so that no barrier is left half-arrived
+        const long long first = kcount >= NBUF ? kcount - NBUF : 0;
+        for (long long kk = first; kk < kcount; kk++) dm_bar_sync(1 + NBUF + (int)(kk % NBUF));
     }
-    (void)n_groups_lo;
 }
 
-// returns cudaError_t as int; -1000 if the layer does not fit this kernel (the caller falls back to shoot_kernel)
+// returns cudaError_t as int; -1000 if the layer does not fit this kernel
 inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, long long ldb, long long B, const ShootOut &o,
                             int max_ns, int max_pieces, cudaStream_t s)
 {
@@ -417,24 +430,31 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
     if (rounds < 1) rounds = 1;
     // right-hand-side calls per interval: Tsit5 6K per piece (FSAL after the last step skipped), RK4 4K
     const int nst = max_pieces * (method == 0 ? 6 : 4) * L.K;
-    const size_t smem = sizeof(double) * 2 * (size_t)nst * DM_CPB * DM_NX;
+    const size_t per = sizeof(double) * (size_t)nst * DM_CPB * DM_NX;
     static const bool lockstep = getenv("CB200_DENSE20_LOCKSTEP") != nullptr;
-    if (!lockstep && smem <= 200 * 1024) {
+    static const int nbuf_env = getenv("CB200_DENSE20_NBUF") ? atoi(getenv("CB200_DENSE20_NBUF")) : 0;
+    // three item buffers when they fit (the x tile may run two items ahead), else two
+    int nbuf = (nbuf_env == 2 || nbuf_env == 3) ? nbuf_env : 3;
+    if (nbuf == 3 && 3 * per > 200 * 1024) nbuf = 2;
+    if (!lockstep && nbuf * per <= 200 * 1024) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long n_items = gx * L.In * rounds;
         const unsigned grid = (unsigned)std::min<long long>(n_items, sms);
+        const size_t smem = nbuf * per;
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<grid, DM_THREADS, smem, s>>>(L, ps, ldb, B, o, n_items, 0, rounds, nst);
+            kern<<<grid, DM_THREADS, smem, s>>>(L, ps, ldb, B, o, n_items, rounds, nst);
         };
         if (method == 0) {
-            if (L.uniform_h) go(shoot_dense_mma_pipe_kernel<0, true>);
-            else go(shoot_dense_mma_pipe_kernel<0, false>);
+            if (L.uniform_h) {
+                if (nbuf == 3) go(shoot_dense_mma_pipe_kernel<0, true, 3>);
+                else go(shoot_dense_mma_pipe_kernel<0, true, 2>);
+            } else go(shoot_dense_mma_pipe_kernel<0, false, 2>);
         } else {
-            if (L.uniform_h) go(shoot_dense_mma_pipe_kernel<1, true>);
-            else go(shoot_dense_mma_pipe_kernel<1, false>);
+            if (L.uniform_h) go(shoot_dense_mma_pipe_kernel<1, true, 2>);
+            else go(shoot_dense_mma_pipe_kernel<1, false, 2>);
         }
         return (int)cudaGetLastError();
     }

@@ -8,7 +8,6 @@ int launch_doubleosc6(int G, int method, const DevLayer &L, const double *ps, lo
     switch (G) {
         CB200_DISPATCH_GA(DoubleOsc6, 0, 1)
         CB200_DISPATCH_GA(DoubleOsc6, 1, 1)
-        CB200_DISPATCH_GA(DoubleOsc6, 2, 1)
     default:
         return -1000;
     }

@@ -7,9 +7,7 @@ int launch_egerstedt(int G, int method, const DevLayer &L, const double *ps, lon
 {
     switch (G) {
         CB200_DISPATCH_GA(Egerstedt, 0, 1)
-        CB200_DISPATCH_GA(Egerstedt, 1, 1)
         CB200_DISPATCH_GA(Egerstedt, 2, 1)
-        CB200_DISPATCH_GA(Egerstedt, 3, 1)
     default:
         return -1000;
     }

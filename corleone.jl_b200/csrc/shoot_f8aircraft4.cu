@@ -7,7 +7,6 @@ int launch_f8aircraft4(int G, int method, const DevLayer &L, const double *ps, l
 {
     switch (G) {
         CB200_DISPATCH_GA(F8Aircraft4, 0, 1)
-        CB200_DISPATCH_GA(F8Aircraft4, 1, 1)
         CB200_DISPATCH_GA(F8Aircraft4, 2, 1)
     default:
         return -1000;

@@ -7,8 +7,6 @@ int launch_lin1d(int G, int method, const DevLayer &L, const double *ps, long lo
 {
     switch (G) {
         CB200_DISPATCH_GA(Lin1d, 0, 1)
-        CB200_DISPATCH_GA(Lin1d, 1, 1)
-        CB200_DISPATCH_GA(Lin1d, 2, 1)
         CB200_DISPATCH_GA(Lin1d, 4, 1)
     default:
         return -1000;

@@ -7,7 +7,6 @@ int launch_lin1d_oed(int G, int method, const DevLayer &L, const double *ps, lon
 {
     switch (G) {
         CB200_DISPATCH_GA(Lin1dOed, 0, 1)
-        CB200_DISPATCH_GA(Lin1dOed, 1, 1)
         CB200_DISPATCH_GA(Lin1dOed, 2, 1)
     default:
         return -1000;

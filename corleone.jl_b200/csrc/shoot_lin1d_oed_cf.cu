@@ -7,7 +7,6 @@ int launch_lin1d_oed_cf(int G, int method, const DevLayer &L, const double *ps, 
 {
     switch (G) {
         CB200_DISPATCH_GA(Lin1dOedCf, 0, 1)
-        CB200_DISPATCH_GA(Lin1dOedCf, 1, 1)
         CB200_DISPATCH_GA(Lin1dOedCf, 2, 1)
     default:
         return -1000;

@@ -7,7 +7,6 @@ int launch_lin1d_oed_ds(int G, int method, const DevLayer &L, const double *ps, 
 {
     switch (G) {
         CB200_DISPATCH_GA(Lin1dOedDs, 0, 1)
-        CB200_DISPATCH_GA(Lin1dOedDs, 1, 1)
         CB200_DISPATCH_GA(Lin1dOedDs, 2, 1)
     default:
         return -1000;

@@ -7,10 +7,7 @@ int launch_lotka2(int G, int method, const DevLayer &L, const double *ps, long l
 {
     switch (G) {
         CB200_DISPATCH_GA(Lotka2, 0, 1)
-        CB200_DISPATCH_GA(Lotka2, 1, 1)
         CB200_DISPATCH_GA(Lotka2, 2, 1)
-        CB200_DISPATCH_GA(Lotka2, 3, 1)
-        CB200_DISPATCH_GA(Lotka2, 4, 1)
     default:
         return -1000;
     }

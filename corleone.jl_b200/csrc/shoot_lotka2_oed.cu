@@ -8,7 +8,6 @@ int launch_lotka2_oed(int G, int method, const DevLayer &L, const double *ps, lo
     switch (G) {
         CB200_DISPATCH_GA(Lotka2Oed, 0, 5)  // 96 registers: 20 warps/SM; G x MINB sweep in profiles/
         CB200_DISPATCH_GA(Lotka2Oed, 1, 1)
-        CB200_DISPATCH_GA(Lotka2Oed, 2, 1)
     default:
         return -1000;
     }

@@ -8,7 +8,6 @@ int launch_lotka2_oed_ds(int G, int method, const DevLayer &L, const double *ps,
     switch (G) {
         CB200_DISPATCH_GA(Lotka2OedDs, 0, 1)
         CB200_DISPATCH_GA(Lotka2OedDs, 1, 1)
-        CB200_DISPATCH_GA(Lotka2OedDs, 2, 1)
     default:
         return -1000;
     }

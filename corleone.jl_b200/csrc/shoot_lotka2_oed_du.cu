@@ -8,7 +8,6 @@ int launch_lotka2_oed_du(int G, int method, const DevLayer &L, const double *ps,
     switch (G) {
         CB200_DISPATCH_GA(Lotka2OedDu, 0, 1)
         CB200_DISPATCH_GA(Lotka2OedDu, 1, 1)
-        CB200_DISPATCH_GA(Lotka2OedDu, 2, 1)
     default:
         return -1000;
     }

@@ -7,7 +7,6 @@ int launch_lotkacomp3(int G, int method, const DevLayer &L, const double *ps, lo
 {
     switch (G) {
         CB200_DISPATCH_GA(LotkaComp3, 0, 1)
-        CB200_DISPATCH_GA(LotkaComp3, 1, 1)
         CB200_DISPATCH_GA(LotkaComp3, 2, 1)
     default:
         return -1000;

@@ -7,8 +7,6 @@ int launch_lqr(int G, int method, const DevLayer &L, const double *ps, long long
 {
     switch (G) {
         CB200_DISPATCH_GA(Lqr, 0, 1)
-        CB200_DISPATCH_GA(Lqr, 1, 1)
-        CB200_DISPATCH_GA(Lqr, 2, 1)
         CB200_DISPATCH_GA(Lqr, 4, 4)  // 127 registers, no spills: 16 warps/SM (ptxas -v); best of the G x MINB sweep
         CB200_DISPATCH_GA(Lqr, 8, 1)
     default:

@@ -8,7 +8,6 @@ int launch_quadrotor7(int G, int method, const DevLayer &L, const double *ps, lo
     switch (G) {
         CB200_DISPATCH_GA(Quadrotor7, 0, 1)
         CB200_DISPATCH_GA(Quadrotor7, 1, 1)
-        CB200_DISPATCH_GA(Quadrotor7, 2, 1)
     default:
         return -1000;
     }

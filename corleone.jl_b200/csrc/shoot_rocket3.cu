@@ -7,7 +7,6 @@ int launch_rocket3(int G, int method, const DevLayer &L, const double *ps, long 
 {
     switch (G) {
         CB200_DISPATCH_GA(Rocket3, 0, 1)
-        CB200_DISPATCH_GA(Rocket3, 1, 1)
         CB200_DISPATCH_GA(Rocket3, 2, 1)
     default:
         return -1000;

@@ -7,7 +7,6 @@ int launch_threetank4(int G, int method, const DevLayer &L, const double *ps, lo
 {
     switch (G) {
         CB200_DISPATCH_GA(ThreeTank4, 0, 1)
-        CB200_DISPATCH_GA(ThreeTank4, 1, 1)
         CB200_DISPATCH_GA(ThreeTank4, 2, 1)
     default:
         return -1000;

@@ -7,7 +7,6 @@ int launch_vdp3(int G, int method, const DevLayer &L, const double *ps, long lon
 {
     switch (G) {
         CB200_DISPATCH_GA(Vdp3, 0, 1)
-        CB200_DISPATCH_GA(Vdp3, 1, 1)
         CB200_DISPATCH_GA(Vdp3, 2, 1)
     default:
         return -1000;

@@ -15,13 +15,17 @@ LIB_PATH = os.environ.get("CORLEONE_B200_LIB") or os.path.join(_HERE, "libcorleo
 _lib = None
 
 WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS, WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT, WANT_GRAD_COMPACT, WANT_TRAJ_SENS = 1, 2, 4, 8, 16, 32, 64, 128, 256, 512, 1024
-MEM_DEVICE, PS_SOA, OUT_SOA = 1, 2, 4
+MEM_DEVICE, PS_SOA, OUT_SOA, COMM_REDUCE, COMM_GATHER = 1, 2, 4, 8, 16
+TRANSPORT_NONE, TRANSPORT_NCCL, TRANSPORT_P2P = 0, 1, 2
+COMM_ID_BYTES = 128
 
 EXPORTS = (
     "cb200_version", "cb200_last_error", "cb200_create", "cb200_destroy", "cb200_get_sizes",
     "cb200_block_structure", "cb200_set_stream", "cb200_eval", "cb200_jac_structure",
     "cb200_last_kernel_ms", "cb200_kernel_ms_history", "cb200_launch_count", "cb200_probe_fp64_tflops",
     "cb200_probe_fp64_mma_tflops", "cb200_forward_init", "cb200_grad_structure", "cb200_set_interval_range",
+    "cb200_resident", "cb200_abi_layout", "cb200_comm_unique_id", "cb200_comm_init", "cb200_comm_init_host",
+    "cb200_comm_destroy", "cb200_comm_query", "cb200_comm_gathered",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -52,7 +56,18 @@ class Out(C.Structure):
         ("fim_sum", C.c_void_p), ("objective_sum", C.c_void_p), ("grad_sum", C.c_void_p),
         ("fim_init", C.c_void_p), ("objective_row", C.c_int32), ("reserved", C.c_int32),
         ("jac_vals", C.c_void_p), ("criteria", C.c_void_p), ("grad_compact", C.c_void_p), ("traj_sens", C.c_void_p), ("status", C.c_void_p),
+        ("defects_gathered", C.c_void_p), ("comm_B_total", C.c_int64), ("comm_b0", C.c_int64),
+        ("resident", C.c_uint32), ("reserved2", C.c_uint32),
     ]
+
+
+class CommInfo(C.Structure):
+    _fields_ = [("nranks", C.c_int32), ("rank", C.c_int32), ("transport", C.c_int32), ("reserved", C.c_int32),
+                ("epoch", C.c_int64), ("max_B_total", C.c_int64), ("error", C.c_int64)]
+
+
+# int (*)(void *ctx, const void *send, int64_t bytes, void *recv)
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p)
 
 
 class Sizes(C.Structure):
@@ -96,6 +111,14 @@ def lib():
         L.cb200_probe_fp64_tflops.restype = C.c_double
         L.cb200_probe_fp64_mma_tflops.argtypes = [C.c_int, C.c_int]
         L.cb200_probe_fp64_mma_tflops.restype = C.c_double
+        L.cb200_resident.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_void_p), _i64p]
+        L.cb200_abi_layout.argtypes = [C.c_int32, _i64p, C.c_int32]
+        L.cb200_comm_unique_id.argtypes = [C.c_void_p]
+        L.cb200_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int64]
+        L.cb200_comm_init_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, ALLGATHER_FN, C.c_void_p, C.c_int64]
+        L.cb200_comm_destroy.argtypes = [C.c_void_p]
+        L.cb200_comm_query.argtypes = [C.c_void_p, C.POINTER(CommInfo)]
+        L.cb200_comm_gathered.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
         _lib = L
     return _lib
 
@@ -184,6 +207,49 @@ class NativeLayer:
         except Exception:
             pass
 
+    # ---- multi-GPU data plane (cb200_comm_*)
+    def comm_init(self, nranks: int, rank: int, unique_id: bytes, max_B_total: int = 0):
+        """collective: NCCL bootstrap from the 128-byte id rank 0 made with comm_unique_id()"""
+        buf = C.create_string_buffer(bytes(unique_id), COMM_ID_BYTES)
+        _check(lib().cb200_comm_init(self._h, nranks, rank, buf, int(max_B_total)), "cb200_comm_init")
+
+    def comm_init_host(self, nranks: int, rank: int, allgather, max_B_total: int = 0):
+        """collective: `allgather(send: bytes) -> list[bytes]` is the host's bootstrap channel (a torch.distributed
+        all_gather_object, MPI, a threading.Barrier between threads ...)"""
+        def _fn(_ctx, send, nbytes, recv):
+            try:
+                parts = allgather(C.string_at(send, nbytes))
+                assert len(parts) == nranks and all(len(p) == nbytes for p in parts)
+                C.memmove(recv, b"".join(parts), nbytes * nranks)
+                return 0
+            except Exception:   # never let an exception cross the C frame
+                import traceback
+                traceback.print_exc()
+                return 1
+        cb = ALLGATHER_FN(_fn)
+        self._comm_cb = cb   # keep the trampoline alive as long as the communicator may call it (only during init)
+        _check(lib().cb200_comm_init_host(self._h, nranks, rank, cb, None, int(max_B_total)), "cb200_comm_init_host")
+
+    def comm_destroy(self):
+        _check(lib().cb200_comm_destroy(self._h), "cb200_comm_destroy")
+
+    def comm_info(self) -> dict:
+        ci = CommInfo()
+        _check(lib().cb200_comm_query(self._h, C.byref(ci)), "cb200_comm_query")
+        return {n: int(getattr(ci, n)) for n, _ in CommInfo._fields_ if n != "reserved"}
+
+    def comm_gathered(self):
+        """(device pointer, leading dimension) of the all-gathered defects [q * ld + b] in the handle's window"""
+        p, ld = C.c_void_p(), C.c_int64()
+        _check(lib().cb200_comm_gathered(self._h, C.byref(p), C.byref(ld)), "cb200_comm_gathered")
+        return int(p.value), int(ld.value)
+
+    def resident(self, want_bit: int):
+        """(device pointer, leading dimension) of a result the last evaluation left on the device (Out.resident)"""
+        p, ld = C.c_void_p(), C.c_int64()
+        _check(lib().cb200_resident(self._h, want_bit, C.byref(p), C.byref(ld)), "cb200_resident")
+        return int(p.value), int(ld.value)
+
     def set_interval_range(self, first: int, last: int):
         """restrict the following evaluations to intervals first:last (1-based, inclusive; 1:I = all)"""
         _check(lib().cb200_set_interval_range(self._h, int(first), int(last)), "cb200_set_interval_range")
@@ -239,12 +305,15 @@ class NativeLayer:
                     defects_kind=self.n_defects, defects_stage=self.n_defects, objective=1, grad=self.nvars,
                     fim=self.fim_n * self.fim_n, jac_vals=self.jac_nnz_var, criteria=6, traj_sens=self.n_traj_sens)
 
-    def eval_raw(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1):
-        """Raw pointer call (host or device pointers as `flags` says). ptrs: field name -> int address."""
+    def eval_raw(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1,
+                 resident: int = 0, comm_B_total: int = 0, comm_b0: int = 0):
+        """Raw pointer call (host or device pointers as `flags` says). ptrs: field name -> int address.
+        resident: want-bits of results that stay on the device (NativeLayer.resident)."""
         o = Out()
         for k, v in ptrs.items():
             setattr(o, k, v)
         o.objective_row = objective_row
+        o.resident, o.comm_B_total, o.comm_b0 = resident, comm_B_total, comm_b0
         _check(lib().cb200_eval(self._h, C.c_void_p(ps_ptr), B, ldb, want, flags, C.byref(o)), "cb200_eval")
 
     def eval_host(self, ps, want: int, objective_row: int = 1, fim_init=None, pinned_out: dict | None = None,
@@ -296,6 +365,19 @@ class NativeLayer:
             ps = np.zeros((B, 1))
         self.eval_raw(ps.ctypes.data, B, max(self.nvars, 1), want, 0, ptrs, objective_row)
         return res
+
+
+def comm_unique_id() -> bytes:
+    """the 128-byte NCCL id rank 0 creates and the host hands to the other ranks"""
+    buf = C.create_string_buffer(COMM_ID_BYTES)
+    _check(lib().cb200_comm_unique_id(buf), "cb200_comm_unique_id")
+    return buf.raw
+
+
+def abi_layout(which: int) -> list:
+    v = (C.c_int64 * 16)()
+    n = lib().cb200_abi_layout(which, v, 16)
+    return [int(x) for x in v[:n]]
 
 
 def probe_fp64_tflops(device: int = 0, iters: int = 20000) -> float:

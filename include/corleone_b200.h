@@ -36,14 +36,15 @@
 extern "C" {
 #endif
 
-#define CB200_VERSION 100
+#define CB200_VERSION 200
 
 typedef enum {
     CB200_OK = 0,
     CB200_ERR_ARG = -1,      /* bad descriptor / argument */
     CB200_ERR_CUDA = -2,     /* CUDA runtime failure (message has the CUDA error string) */
     CB200_ERR_UNSUPPORTED = -3, /* model/method/feature combination not compiled in */
-    CB200_ERR_NOMEM = -4
+    CB200_ERR_NOMEM = -4,
+    CB200_ERR_COMM = -5      /* multi-GPU data plane: NCCL failure, a peer window that cannot be mapped, a rank that never arrived */
 } cb200_status;
 
 /* compiled-in model registry (the reference integrates arbitrary Julia closures; a C-ABI CUDA library
@@ -187,6 +188,13 @@ typedef enum {
                                        ps[b*ldb + v], i.e. a Julia nvars x B Matrix with leading dim ldb) */
 #define CB200_OUT_SOA 0x4u          /* outputs are quantity-major out[q*B + b] (default candidate-major
                                        out[b*n + q], i.e. Julia n x B matrices) */
+/* multi-GPU flags (the handle has a communicator, cb200_comm_init*).  An evaluation with either flag is COLLECTIVE: every
+ * rank issues the same sequence of such calls (B may differ from rank to rank) */
+#define CB200_COMM_REDUCE 0x8u      /* objective_sum, grad_sum and fim_sum are all-reduced over the ranks: every rank
+                                       receives the sums over the candidates of ALL ranks (bit-identical everywhere) */
+#define CB200_COMM_GATHER 0x10u     /* the kind-major shooting defects of all ranks are all-gathered into every rank's
+                                       window: cb200_out.defects_gathered / cb200_comm_gathered (needs WANT_DEFECTS,
+                                       cb200_out.comm_B_total and comm_b0) */
 
 /*
  * Output buffers; NULL = not wanted.  Sizes in doubles, n = the leading count, per candidate:
@@ -235,6 +243,17 @@ typedef struct {
                                    end state on some interval (in the adaptive mode also: more than 1e5 steps in a piece or a
                                    step below resolution -- OrdinaryDiffEq's MaxIters / DtLessThanMin / Unstable).  The reference
                                    never inspects the solver's retcode. */
+    /* ---- version 200 */
+    double *defects_gathered;   /* CB200_COMM_GATHER: n = n_defects, the candidates of ALL ranks in global order:
+                                   [q * comm_B_total + b] (CB200_OUT_SOA) or [b * n_defects + q]; NULL = leave the result in
+                                   the handle's window (cb200_comm_gathered) */
+    int64_t comm_B_total;       /* CB200_COMM_GATHER: candidates of all ranks together */
+    int64_t comm_b0;            /* CB200_COMM_GATHER: global index of this rank's first candidate */
+    uint32_t resident;          /* want-bits (CB200_WANT_*) of results that stay on the device: their buffer pointers above are
+                                   ignored, the result is kept in handle-owned memory, quantity-major [q * B + b], until the
+                                   next evaluation (cb200_resident) -- e.g. the constraint-Jacobian values of 65 536
+                                   candidates never cross PCIe when the consumer factorises them on the device */
+    uint32_t reserved2;
 } cb200_out;
 
 typedef struct {
@@ -295,6 +314,58 @@ int cb200_forward_init(cb200_handle *h, double *ps, int64_t B, int64_t ldb, uint
  * src >= 0: 0-based row into `sens`;  src == -1: constant +1;  src == -2: constant -1.  The jac_nnz_var entries
  * with src >= 0 come first, in the order of `jac_vals`. */
 int cb200_jac_structure(const cb200_handle *h, int64_t *rows, int64_t *cols, int64_t *src);
+
+/* Device-resident results of the last cb200_eval (cb200_out.resident): *ptr = device pointer of the result selected by ONE
+ * CB200_WANT_* bit (for CB200_WANT_DEFECTS: defects_kind), laid out [q * (*ld) + b]; valid until the next evaluation on
+ * the handle.  Work enqueued on the handle's stream (cb200_set_stream) is ordered after the evaluation. */
+int cb200_resident(const cb200_handle *h, uint32_t want_bit, double **ptr, int64_t *ld);
+
+/* ------------------------------------------------------------------------------------------------------------------
+ * Multi-GPU data plane: one rank (process or thread) per GPU of one box.  Replaces mythreadmap(::EnsembleDistributed) =
+ * pmap over intervals (src/Corleone.jl:24, src/multiple_shooting.jl:118-130), whose per-interval results travel to the
+ * master over TCP: here every rank evaluates a contiguous slice of the candidate axis and only the cross-candidate sums
+ * (objective, gradient, Fisher information: all-reduce) and the shooting defects (all-gather) cross NVLink, written by
+ * the evaluation's own kernels into peer-mapped windows (no collective library call per evaluation; NCCL is the
+ * fallback transport and one of two ways to bootstrap).
+ * ------------------------------------------------------------------------------------------------------------------ */
+#define CB200_COMM_ID_BYTES 128
+#define CB200_TRANSPORT_NONE 0
+#define CB200_TRANSPORT_NCCL 1   /* ncclAllReduce / ncclAllGather on the handle's stream after the kernels */
+#define CB200_TRANSPORT_P2P 2    /* fused: P2P stores + one-shot all-reduce in the tail of the evaluation's last kernel */
+
+/* all-gather provided by the host: every rank contributes `bytes` at `send`, `recv` receives nranks * bytes in rank
+ * order; returns 0.  (Julia: MPI.Allgather!, or a Distributed.jl remotecall_fetch round; tests: a threading.Barrier.) */
+typedef int (*cb200_allgather_fn)(void *ctx, const void *send, int64_t bytes, void *recv);
+
+typedef struct {
+    int32_t nranks, rank;
+    int32_t transport;      /* CB200_TRANSPORT_* */
+    int32_t reserved;
+    int64_t epoch;          /* collective evaluations so far */
+    int64_t max_B_total;    /* capacity of the gather window in candidates */
+    int64_t error;          /* != 0: a peer timed out (also reported by the next cb200_eval as CB200_ERR_COMM) */
+} cb200_comm_info;
+
+/* rank 0 creates the 128-byte id (ncclGetUniqueId) and the host hands it to the other ranks */
+int cb200_comm_unique_id(void *id /* CB200_COMM_ID_BYTES */);
+/* Collective over the nranks handles of one layer (same descriptor on every rank, each on its own device): creates the
+ * communicator (ncclCommInitRank), the handle's windows and the peer mappings.  max_B_total: the largest
+ * cb200_out.comm_B_total a CB200_COMM_GATHER evaluation will use (0 = no gather window). */
+int cb200_comm_init(cb200_handle *h, int32_t nranks, int32_t rank, const void *id, int64_t max_B_total);
+/* the same without NCCL: the host provides the bootstrap all-gather (P2P transport only; the ranks may be threads of one
+ * process, then the windows are shared by plain peer access) */
+int cb200_comm_init_host(cb200_handle *h, int32_t nranks, int32_t rank, cb200_allgather_fn allgather, void *ctx,
+                         int64_t max_B_total);
+int cb200_comm_destroy(cb200_handle *h);
+int cb200_comm_query(const cb200_handle *h, cb200_comm_info *info);
+/* the all-gathered defects of the last CB200_COMM_GATHER evaluation, in the handle's window: [q * (*ld) + b], *ld =
+ * comm_B_total.  Valid until the second-next collective evaluation (the window is double-buffered). */
+int cb200_comm_gathered(const cb200_handle *h, double **ptr, int64_t *ld);
+
+/* layout self-check for bindings that restate the structs by hand (julia/CorleoneB200.jl): sizeof and the offsets of
+ * the last fields; which: 0 = cb200_desc, 1 = cb200_out, 2 = cb200_sizes, 3 = cb200_comm_info.  Returns the number
+ * of values written to `vals` (sizeof first), at most n. */
+int cb200_abi_layout(int32_t which, int64_t *vals, int32_t n);
 
 /* Device time of the last cb200_eval's integration kernel(s) in milliseconds (CUDA events on the
  * handle's stream); < 0 if none. */

@@ -27,13 +27,19 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/corleone_b200.h but not exported"
     assert set(names) == set(native.EXPORTS)
-    assert native.lib().cb200_version() == 100
+    assert native.lib().cb200_version() == 200
 
 
 def test_struct_layouts_match_header():
     assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8 + 2 * 4 + 2 * 8 + 2 * 8
-    assert ctypes.sizeof(native.Out) == 12 * 8 + 8 + 8 + 8 + 8 + 8 + 8
+    assert ctypes.sizeof(native.Out) == 12 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 3 * 8 + 2 * 4
     assert ctypes.sizeof(native.Sizes) == 9 * 8
+    # the library reports sizeof and the offsets of the trailing fields of every struct a binding restates by hand
+    # (julia/CorleoneB200.jl asserts the same numbers at load time)
+    for which, T, fields in ((0, native.Desc, ("u0", "model_data_len", "observation_grid", "reltol")),
+                             (1, native.Out, ("objective_row", "jac_vals", "status", "defects_gathered", "comm_b0", "resident")),
+                             (2, native.Sizes, ("n_traj_sens",)), (3, native.CommInfo, ("epoch", "error"))):
+        assert native.abi_layout(which) == [ctypes.sizeof(T)] + [getattr(T, f).offset for f in fields], which
 
 
 def test_bad_descriptor_is_rejected_before_any_device_work():

@@ -90,6 +90,66 @@ def main():
         print(f"ms24 B=1 world={world} interval-sharded ({res['_shard'].size} intervals on rank 0): max abs diff {errs}, "
               f"objective rel {eo:.1e}; wall {t_shard * 1e6:.0f} us sharded vs {t_one * 1e6:.0f} us on one GPU")
         ok &= all(v == 0.0 for v in errs.values()) and eo < 1e-14
+    # (4) the library's own data plane (cb200_comm_*): the bench's N > 1 workload in small -- dense 20-state model,
+    #     candidates sharded over the ranks, allreduce(objective_sum, grad_sum) + allgather(defects) fused into the kernels
+    #     (P2P transport) and through NCCL (fallback transport); compared with rank 0 evaluating the whole batch alone
+    for transport in ("p2p", "nccl"):
+        os.environ["CB200_COMM_TRANSPORT"] = transport
+        spec = P.dense20_spec(8, np.random.default_rng(21))
+        lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2), device=local)
+        Bl = 40
+        B_total, b0 = Bl * world, Bl * rank
+        rng2 = np.random.default_rng(22)
+        ps = cb.to_vec(ps_t)[None, :] + 0.1 * rng2.standard_normal((B_total, N.nvars))
+        ident = [nat.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        try:
+            N.comm_init(world, rank, ident[0], max_B_total=B_total)
+        except nat.NativeError as e:
+            if transport == "p2p":
+                print(f"rank {rank}: p2p transport unavailable here: {e}")
+                ok = False
+            raise
+        info = N.comm_info()
+        want = nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_XEND
+        d_ps = torch.from_numpy(np.ascontiguousarray(ps[b0:b0 + Bl].T)).to(dev)
+        d_sums = torch.zeros(1 + N.nvars, dtype=torch.float64, device=dev)
+        d_gat = torch.full((N.n_defects, B_total), float("nan"), dtype=torch.float64, device=dev)
+        d_x = torch.empty((N.nx * N.I, Bl), dtype=torch.float64, device=dev)
+        N.set_stream(torch.cuda.current_stream().cuda_stream)
+        for _ in range(3):
+            N.eval_raw(d_ps.data_ptr(), Bl, Bl, want, nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA | nat.COMM_REDUCE | nat.COMM_GATHER,
+                       dict(xend=d_x.data_ptr(), objective_sum=d_sums.data_ptr(), grad_sum=d_sums.data_ptr() + 8,
+                            defects_gathered=d_gat.data_ptr()), 3, comm_B_total=B_total, comm_b0=b0)
+        torch.cuda.synchronize()
+        # host pointers as well (candidate-major), results in host memory
+        rows = np.ascontiguousarray(ps[b0:b0 + Bl])
+        h_gat, h_sums = np.full((B_total, N.n_defects), np.nan), np.zeros(1 + N.nvars)
+        N.eval_raw(rows.ctypes.data, Bl, N.nvars, want, nat.COMM_REDUCE | nat.COMM_GATHER,
+                   dict(objective_sum=h_sums.ctypes.data, grad_sum=h_sums.ctypes.data + 8, defects_gathered=h_gat.ctypes.data), 3,
+                   comm_B_total=B_total, comm_b0=b0)
+        sums = d_sums.cpu().numpy()
+        same = [torch.zeros_like(d_sums) for _ in range(world)]
+        dist.all_gather(same, d_sums)
+        identical = all(bool(torch.equal(t, same[0])) for t in same)
+        dist.barrier()
+        N.comm_destroy()
+        if rank == 0:
+            lay1, ps_t1, st1, N1 = P.native_from_spec(spec, cb.Tsit5(2), device=local)
+            full = N1.eval_host(ps, want, objective_row=3, with_sums=True)
+            e1 = abs(sums[0] - full["objective_sum"][0]) / abs(full["objective_sum"][0])
+            e2 = np.max(np.abs(sums[1:] - full["grad_sum"])) / max(1e-300, np.max(np.abs(full["grad_sum"])))
+            e3 = float(np.max(np.abs(d_gat.cpu().numpy() - full["defects_kind"].T)))
+            e4 = float(np.max(np.abs(h_gat - full["defects_kind"])))
+            e5 = float(np.max(np.abs(h_sums - sums)))
+            names = {1: "nccl", 2: "p2p"}
+            print(f"comm dense20 B={B_total} world={world} transport={names.get(info['transport'])}: objective_sum rel {e1:.2e}, "
+                  f"grad_sum rel {e2:.2e}, gathered defects max abs diff {e3:.1e} (device) {e4:.1e} (host), host sums vs device sums "
+                  f"{e5:.1e}, sums bit-identical on all ranks: {identical}")
+            ok &= e1 < 1e-12 and e2 < 1e-12 and e3 == 0.0 and e4 == 0.0 and e5 <= 1e-12 * np.max(np.abs(sums)) and identical
+            ok &= names.get(info["transport"]) == transport
+    os.environ.pop("CB200_COMM_TRANSPORT", None)
+    if rank == 0:
         print("multi_gpu_check", "ok" if ok else "FAILED")
     dist.barrier()
     dist.destroy_process_group()
