@@ -84,6 +84,8 @@ def test_fused_allreduce_and_allgather_device_pointers(nranks, model):
     for rep in range(3):   # three epochs: the windows are double-buffered by epoch parity
         outs, b0 = [], 0
         streams = [torch.cuda.Stream() for _ in range(nranks)]
+        # buffers first, launches second: a rank's tail spins until every peer has arrived, so nothing that synchronises
+        # the device (allocation, pageable copies) may sit between the launches of one host thread
         for r, (lay, ps_t, N) in enumerate(ranks):
             B = shards[r]
             d_ps = torch.from_numpy(np.ascontiguousarray(ps[b0:b0 + B].T)).to(dev)
@@ -92,14 +94,20 @@ def test_fused_allreduce_and_allgather_device_pointers(nranks, model):
             d_dk = torch.empty((N.n_defects, B), dtype=torch.float64, device=dev)
             d_sums = torch.full((1 + N.nvars,), np.nan, dtype=torch.float64, device=dev)
             d_gat = torch.full((N.n_defects, B_total), np.nan, dtype=torch.float64, device=dev)
-            torch.cuda.synchronize()
             N.set_stream(streams[r].cuda_stream)
+            if rep == 0:   # grow the handle's workspaces outside the collective sequence
+                N.eval_raw(d_ps.data_ptr(), B, B, want, flags & ~(nat.COMM_REDUCE | nat.COMM_GATHER),
+                           dict(objective=d_obj.data_ptr(), jac_vals=d_jac.data_ptr(), defects_kind=d_dk.data_ptr(),
+                                objective_sum=d_sums.data_ptr(), grad_sum=d_sums.data_ptr() + 8), obj_row)
+            outs.append((d_ps, d_obj, d_jac, d_dk, d_sums, d_gat, b0, B))
+            b0 += B
+        torch.cuda.synchronize()
+        for r, (d_ps, d_obj, d_jac, d_dk, d_sums, d_gat, b0, B) in enumerate(outs):
+            N = ranks[r][2]
             N.eval_raw(d_ps.data_ptr(), B, B, want, flags,
                        dict(objective=d_obj.data_ptr(), jac_vals=d_jac.data_ptr(), defects_kind=d_dk.data_ptr(),
                             objective_sum=d_sums.data_ptr(), grad_sum=d_sums.data_ptr() + 8, defects_gathered=d_gat.data_ptr()),
                        obj_row, comm_B_total=B_total, comm_b0=b0)
-            outs.append((d_ps, d_obj, d_jac, d_dk, d_sums, d_gat, b0, B))
-            b0 += B
         torch.cuda.synchronize()
         ref_dk = full["defects_kind"].T          # [n_defects, B_total]
         sums0 = outs[0][4].cpu().numpy()
@@ -139,6 +147,7 @@ def test_comm_host_pointers_threads():
     ps_t1, st1 = cb.setup(None, lay1)
     full = lay1._native(st1, ps_t1).eval_host(ps, want, objective_row=3, with_sums=True)
     res = [None] * nranks
+    ready = threading.Barrier(nranks)
 
     def work(r):
         N = ranks[r][2]
@@ -147,6 +156,14 @@ def test_comm_host_pointers_threads():
         rows = np.ascontiguousarray(ps[b0:b0 + B])
         out = dict(defects_kind=np.empty((B, N.n_defects)), objective=np.empty((B, 1)), objective_sum=np.zeros(1),
                    grad_sum=np.zeros(N.nvars), defects_gathered=np.full((B_total, N.n_defects), np.nan))
+        # ranks that share ONE device (this test only): a first launch loads its kernel lazily, which synchronises the
+        # device -- and would wait for a peer's tail that is spinning for this rank.  Load and allocate everything with
+        # a non-collective call first; ranks on their own GPUs (tests/test_gpu_multi.py) need no such care
+        # (with the WHOLE batch, so that no workspace has to grow -- free + allocate synchronises too -- later on)
+        warm = dict(defects_kind=np.empty((B_total, N.n_defects)), objective=np.empty((B_total, 1)), objective_sum=np.zeros(1),
+                    grad_sum=np.zeros(N.nvars))
+        N.eval_raw(ps.ctypes.data, B_total, N.nvars, want, 0, {k: v.ctypes.data for k, v in warm.items()}, 3)
+        ready.wait()
         for _ in range(2):
             N.eval_raw(rows.ctypes.data, B, N.nvars, want, nat.COMM_REDUCE | nat.COMM_GATHER,
                        {k: v.ctypes.data for k, v in out.items()}, 3, comm_B_total=B_total, comm_b0=b0)
@@ -205,17 +222,21 @@ def test_fim_sum_allreduce_and_fused_readout():
     [t.join() for t in ths]
     dev = torch.device("cuda:0")
     outs, b0 = [], 0
-    for r in range(nranks):
+    fl = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA
+    for r in range(nranks):   # buffers and a non-collective warm-up first (nothing that synchronises the device between the launches)
         N = ranks[r][3]
         Br = shards[r]
         d_ps = torch.from_numpy(np.ascontiguousarray(ps[b0:b0 + Br].T)).to(dev)
         d_fim = torch.empty((4, Br), dtype=torch.float64, device=dev)
         d_fs = torch.full((4,), np.nan, dtype=torch.float64, device=dev)
-        torch.cuda.synchronize()
-        N.eval_raw(d_ps.data_ptr(), Br, Br, nat.WANT_FIM, nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA | nat.COMM_REDUCE,
-                   dict(fim=d_fim.data_ptr(), fim_sum=d_fs.data_ptr()), 1)
+        N.eval_raw(d_ps.data_ptr(), Br, Br, nat.WANT_FIM, fl, dict(fim=d_fim.data_ptr(), fim_sum=d_fs.data_ptr()), 1)
         outs.append((d_ps, d_fim, d_fs))
         b0 += Br
+    torch.cuda.synchronize()
+    for r in range(nranks):
+        d_ps, d_fim, d_fs = outs[r]
+        ranks[r][3].eval_raw(d_ps.data_ptr(), shards[r], shards[r], nat.WANT_FIM, fl | nat.COMM_REDUCE,
+                             dict(fim=d_fim.data_ptr(), fim_sum=d_fs.data_ptr()), 1)
     torch.cuda.synchronize()
     for r in range(nranks):
         s = outs[r][2].cpu().numpy()

@@ -29,7 +29,7 @@ def test_config2_lqr_full_size():
     lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2))
     O = po.OracleLayer(spec)
     B = 4096
-    ps = bench.make_inputs(N.nvars, cb.to_vec(ps_t), B, rng)
+    ps = bench.lqr_inputs(N.nvars, cb.to_vec(ps_t), B, rng)
     want = nat.WANT_XEND | nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
     r = N.eval_host(ps, want, objective_row=2, with_sums=True)
     r2 = N.eval_host(ps, want, objective_row=2, with_sums=True)

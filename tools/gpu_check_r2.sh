@@ -1,0 +1,20 @@
+#!/bin/bash
+# One gpurun call (round 2): GPU tests, ncu launch list of the bench command, --set full captures of the three dominant kernels.
+# usage: gpurun --timeout 1500 -- 'bash tools/gpu_check_r2.sh <tag> [notest]'
+tag=${1:-r2}
+mkdir -p gpurun_out
+if [ "$2" != "notest" ]; then
+  timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu_$tag.log 2>&1; echo "pytest rc=$?" >> gpurun_out/pytest_gpu_$tag.log
+  tail -8 gpurun_out/pytest_gpu_$tag.log
+fi
+CMD="python bench.py --steps 3 --warmup 3 --no-cpu-baseline"
+$CMD > gpurun_out/plain_$tag.log 2>&1 &&
+ncu --metrics gpu__time_duration.sum --clock-control none -c 800 --csv --log-file gpurun_out/launches_$tag.csv $CMD > gpurun_out/ncu1_$tag.log 2>&1
+for cfg in "4:shoot_dense:--candidates 2960:1" "3:shoot_kernel:--steps 20:6" "2:shoot_kernel:--steps 20:6"; do
+  IFS=: read only kre extra skip <<< "$cfg"
+  C2="python bench.py --only $only --warmup 3 --no-cpu-baseline --steps 3 $extra"
+  $C2 > gpurun_out/plain_${tag}_c$only.log 2>&1 &&
+  ncu --set full --clock-control none --import-source on -k regex:$kre -s $skip -c 1 -f -o gpurun_out/prof_${tag}_c$only $C2 > gpurun_out/ncu_${tag}_c$only.log 2>&1
+  tail -c 600 gpurun_out/plain_${tag}_c$only.log | head -c 300; echo
+done
+ls -la gpurun_out
