@@ -262,7 +262,7 @@ def run_config4(args, torch, dev, local_rank, clk, n_candidates=65536, e2e=True)
            "value": units * args.steps / (ms_total * 1e-3), "unit": "units/s", "ms_per_step": ms_total / args.steps,
            "kernel_ms": kern_ms, "steps": args.steps,
            "outputs": f"sens ({8 * sz['sens'] * B / 1e9:.1f} GB, resident in HBM), defects_kind, xend",
-           "chunking": "none on the device-resident arm: one persistent launch over all units of the step"}
+           "chunking": "none on the device-resident arm: one persistent launch over all units of the step (items of 8 candidates x 1 interval)"}
     res["_launches_timed"] = launches
     res["_N"] = N
     e2e_res = None
@@ -658,7 +658,7 @@ def run_scale(args, torch, dist, dev, world, rank, local_rank):
                                                           "gather_leading_dimension": gld}),
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline_entry(WORK["dense20"], I * B, kern_ms, peak, peak_src, hbm_peak, hbm_src,
-                                       "shoot_dense_mma_pipe_kernel<Tsit5,uniform> (FP64 tensor path) incl. fused defect all-gather "
+                                       "shoot_dense_mma_queue_kernel<Tsit5,uniform,16 warps> (FP64 tensor path) incl. fused defect all-gather "
                                        "stores, per rank", "dense20"),
             "secondary": secondary,
         }
@@ -762,7 +762,7 @@ def main():
             clocks = clk.summary()
             units = c4["units_per_step"]
             c4["roofline"] = roofline_entry(WORK["dense20"], units, c4["kernel_ms"], peak, peak_src, hbm_peak, hbm_src,
-                                            "shoot_dense_mma_pipe_kernel<Tsit5,uniform> (FP64 tensor path, mma.sync.m8n8k4.f64) "
+                                            "shoot_dense_mma_queue_kernel<Tsit5,uniform,16 warps> (FP64 tensor path, mma.sync.m8n8k4.f64; persistent blocks, tile queue) "
                                             "incl. fused defect epilogue", "dense20")
             line = {"metric": METRIC, "value": c4["value"], "unit": "units/s", "n_gpus": 1, "steps": args.steps,
                     "warmup": max(3, args.warmup), "ms_per_step": c4["ms_per_step"], "higher_is_better": True,

@@ -5,20 +5,26 @@
 // the same 20x20 matrix W applied to all 1 + ns columns of every unit at every stage (north_star: "tensor cores
 // only if the Jacobian-matrix products become a real dense contraction at large state dimension").  On B200 DMMA
 // and DFMA share one FP64 datapath (tools/dmma_micro.cu), but DMMA reaches the nominal 64 FMA/clk/SM with 1/8 of
-// the issue slots and keeps W in 15 fragment registers per lane instead of constant-bank operands.
+// the issue slots and keeps W in 15 fragment registers per lane instead of constant-bank operands.  (The wider PTX
+// shapes m16n8k4 / k8 / k16 .f64 lower to the same DMMA.8x8x4 SASS on sm_100a: nothing to gain there.)
 //
-// Mapping.  A block owns CPB = 5 consecutive candidates of one interval: 125 columns [x | S_1..S_24] x 5 in
-// 16 warps (register files are allotted in units of 4 warps, so 16 is the size that wastes none):
-//   warp 0      (x tile): columns g = 0..4 = the states x of candidates b0 + g (columns 5..7 idle)
-//   warp w >= 1 (S tile): column c = 8(w-1) + g of the 120 sensitivity columns = direction c / 5 of candidate b0 + c % 5
-// A tile is the A operand (rows = columns of Y, k = state) of  D[col][i] = sum_j Y[j][col] W[i][j]; W^T is the B
-// operand.  Lane (g = lane/4, t = lane%4) owns the five states 5t..5t+4 of column g in every vector of the
-// integrator: as A fragment it supplies state 5t+kt in k-tile kt, and the state order of the three n-tiles is
-// permuted (n-slot 2t+e of tile nt <-> state 5t+2nt+e, the sixth slot is zero padding) so that the D fragments it
-// receives are exactly its own five states.  No shuffle, no shared-memory transpose: the stage derivative lands
-// in the registers of the lane that needs it.  The only exchange is x -> S tiles (the -3 x^2 S term): the x tile
-// publishes its stage input in shared memory (100 doubles, double-buffered), one __syncthreads per stage.  Loads and
-// stores of a warp touch 5 consecutive candidates per row.
+// A tile = 8 columns of Y = [x | S_1..S_ns] = the A operand (rows = columns of Y, k = state) of
+// D[col][i] = sum_j Y[j][col] W[i][j]; W^T is the B operand.  Lane (g = lane/4, t = lane%4) owns the five states
+// 5t..5t+4 of column g in every vector of the integrator: as A fragment it supplies state 5t+kt in k-tile kt, and the
+// state order of the three n-tiles is permuted (n-slot 2t+e of tile nt <-> state 5t+2nt+e, the sixth slot is zero
+// padding) so that the D fragments it receives are exactly its own five states.  No shuffle, no shared-memory
+// transpose: the stage derivative lands in the registers of the lane that needs it.  The only exchange is x -> S tiles
+// (the -3 x^2 S term), through shared memory.
+//
+// Two kernels:
+//   * shoot_dense_mma_queue_kernel (the throughput path): persistent blocks, an ITEM = 8 consecutive candidates of one
+//     interval = one x tile (8 state columns: every MMA row is live) + ns S tiles (tile tau = direction tau of the 8
+//     candidates: direction, piece forcing and table look-ups are warp-uniform, stores touch 8 consecutive candidates
+//     per row).  The warps of a block pull tile tasks from a queue in shared memory; the x task of item K+2 is queued
+//     among the S tasks of item K and leaves -3 x^2 of all stages in one of three ring slots, so the S tiles never wait
+//     for the states, no warp is tied to a role, and the hardware balances the four sub-partitions by itself.
+//   * shoot_dense_mma_kernel (lockstep; layers whose stage count does not fit the ring): a block owns 5 candidates of
+//     one interval, warp 0 = x tile, warps 1..15 = 120 sensitivity columns, one __syncthreads per stage.
 //
 // Reference semantics as in shoot.cuh (pieces, FSAL restart per piece, accumulator-form Tsit5, fused K3/K5 epilogue).
 #pragma once
@@ -103,13 +109,13 @@ __device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, c
     }
 }
 
-// slot of the next right-hand-side call: two alternating slots (lockstep) or one slot per call of the item (pipelined);
+// slot of the next right-hand-side call: two alternating slots (lockstep) or one slot per call of the item (ring);
 // sp walks the lane's entries of the slots, sp_alt is the lockstep partner
 #define DM_RHS(y)                                      \
     do {                                               \
         dense_rhs<PIPE, IS_X>(T, y, binit, k, sp);     \
         if constexpr (PIPE) {                          \
-            sp += DM_CPB * DM_NX;                      \
+            sp += slot_stride;                         \
         } else {                                       \
             double *tmp_ = sp;                         \
             sp = sp_alt;                               \
@@ -117,35 +123,21 @@ __device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, c
         }                                              \
     } while (0)
 
-// One unit group (CPB candidates of interval i, direction round `round`) for the calling warp's tile.
-// xc: stage-exchange slots in shared memory.
+// One column per lane group of the calling warp's tile, across the pieces of interval i: the state x of candidate b
+// (IS_X) or its sensitivity with respect to local variable `dir`.  col_on: the column exists (else it integrates
+// zeros); store: it writes results (a live candidate); x_results: the x tile writes the unit's results (first
+// direction round only).  sp / sp_alt / slot_stride: the lane's entries of the stage-exchange slots (DM_RHS).
 template <int METHOD, bool UNI, bool PIPE, bool IS_X>
-__device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__restrict__ ps, long long ldb, long long B,
-                                           const ShootOut &o, int i, int round, long long b0, double *xc, DenseTile &T)
+__device__ __forceinline__ void dense_column(const DevLayer &L, const double *__restrict__ ps, long long ldb,
+                                             const ShootOut &o, int i, int nu0, int ns, int dir, long long b, bool col_on,
+                                             bool store, bool x_results, double *sp, double *sp_alt, int slot_stride,
+                                             DenseTile &T)
 {
     constexpr int NX = DM_NX, NCF = METHOD == 0 ? 21 : 4;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-
-    const int nu0 = __ldg(L.n_u0 + i), nc = __ldg(L.n_c + i);
-    const int ns = nu0 + L.ntp + nc;
-    if (round > 0 && round * DM_DPR >= ns) return;   // uniform over the block
-    // pipelined: an S tile without a live column (the first interval has only the control directions) has nothing to
-    // integrate or to store -- the hand-over barriers live in the caller
-    if (PIPE && !IS_X && round * DM_DPR + (8 * (warp - 1)) / DM_CPB >= ns) return;   // warp-uniform
-
-    const int col = 8 * (warp - 1) + g;                                // S tiles: column among the 120 of this round
-    const int cand = IS_X ? (g < DM_CPB ? g : 0) : col % DM_CPB;
-    const int dir = round * DM_DPR + col / DM_CPB;                     // S tiles: direction of this lane's column
-    long long b = b0 + cand;
-    const bool cand_live = b < B;
-    if (!cand_live) b = B - 1;
-    T.col_on = IS_X ? (g < DM_CPB) : (dir < ns);
-    const bool store = T.col_on && cand_live;
-    // the lane's five entries of the exchange slots
-    double *sp = xc + cand * DM_NX + 5 * t;
-    double *sp_alt = sp + DM_CPB * DM_NX;
+    const int t = threadIdx.x & 3;
     (void)sp_alt;
-
+    (void)slot_stride;
+    T.col_on = col_on;
     const int voff = __ldg(L.var_off + i);
     const double *__restrict__ v = ps + (long long)voff * ldb + b;
     // ---- initial values of the lane's five entries
@@ -189,7 +181,7 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
 #pragma unroll
             for (int s = 0; s < 5; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
         }
-        if (o.traj && IS_X && store && round == 0 && j == 0) {  // save_start = (j == 1)
+        if (o.traj && IS_X && store && x_results && j == 0) {  // save_start = (j == 1)
             double *tr = o.traj + ((long long)so * nrow) * o.ldo + b;
 #pragma unroll
             for (int s = 0; s < 5; s++) tr[(long long)(5 * t + s) * o.ldo] = yd[s];
@@ -287,7 +279,7 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
 #pragma unroll
             for (int s = 0; s < 5; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
         }
-        if (o.traj && IS_X && store && round == 0 && (j + 1 < M || last_interval)) {
+        if (o.traj && IS_X && store && x_results && (j + 1 < M || last_interval)) {
             double *tr = o.traj + ((long long)(so + j + 1) * nrow) * o.ldo + b;
 #pragma unroll
             for (int s = 0; s < 5; s++) tr[(long long)(5 * t + s) * o.ldo] = yd[s];
@@ -298,7 +290,7 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
     // ---- results (fused K3 / K5 epilogue, as in shoot.cuh)
     if (!store) return;
     if constexpr (IS_X) {
-        if (round != 0) return;
+        if (!x_results) return;
         if (o.status) {
             bool ok = true;
 #pragma unroll
@@ -358,7 +350,8 @@ __device__ __forceinline__ void dense_unit(const DevLayer &L, const double *__re
 
 #undef DM_RHS
 
-// Lockstep kernel: one block per unit group, x and S tiles exchange through two alternating slots.
+// Lockstep kernel: one block per unit group (5 candidates of one interval, direction round blockIdx.z), x and S tiles
+// exchange through two alternating slots; both branches meet at the same barrier once per right-hand-side call.
 template <int METHOD, bool UNI>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
@@ -367,55 +360,112 @@ shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restr
     __shared__ double sx[2 * DM_CPB * DM_NX];
     DenseTile T;
     dense_load_w(L, T);
-    if ((threadIdx.x >> 5) == 0)   // both branches meet at the same barrier (id 0), once per right-hand-side call
-        dense_unit<METHOD, UNI, false, true>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx, T);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int i = blockIdx.y + L.i0, round = blockIdx.z;
+    const long long b0 = (long long)blockIdx.x * DM_CPB;
+    const int nu0 = __ldg(L.n_u0 + i), ns = nu0 + L.ntp + __ldg(L.n_c + i);
+    if (round > 0 && round * DM_DPR >= ns) return;   // uniform over the block
+    const bool is_x = warp == 0;
+    const int col = 8 * (warp - 1) + g;                                 // S tiles: column among the 120 of this round
+    const int cand = is_x ? (g < DM_CPB ? g : 0) : col % DM_CPB;
+    const int dir = round * DM_DPR + col / DM_CPB;                      // S tiles: direction of this lane's column
+    long long b = b0 + cand;
+    const bool cand_live = b < B;
+    if (!cand_live) b = B - 1;
+    const bool col_on = is_x ? (g < DM_CPB) : (dir < ns);
+    double *sp = sx + cand * DM_NX + 5 * t;
+    if (is_x)
+        dense_column<METHOD, UNI, false, true>(L, ps, ldb, o, i, nu0, ns, 0, b, col_on, col_on && cand_live, round == 0, sp,
+                                               sp + DM_CPB * DM_NX, 0, T);
     else
-        dense_unit<METHOD, UNI, false, false>(L, ps, ldb, B, o, blockIdx.y + L.i0, blockIdx.z, (long long)blockIdx.x * DM_CPB, sx, T);
+        dense_column<METHOD, UNI, false, false>(L, ps, ldb, o, i, nu0, ns, dir, b, col_on, col_on && cand_live, false, sp,
+                                                sp + DM_CPB * DM_NX, 0, T);
 }
 
-__device__ __forceinline__ void dm_bar_sync(int id) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
-__device__ __forceinline__ void dm_bar_arrive(int id) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(DM_THREADS) : "memory"); }
+// ---- queue kernel
+constexpr int DQ_CPI = 8;   // candidates per item = rows of the MMA
+constexpr int DQ_MAXRING = 3;
 
-// Pipelined persistent kernel: one block per SM walks the unit groups; the x tile (warp 0) integrates the states
-// of later groups -- they do not depend on the sensitivities -- and leaves -3 x^2 of every stage in one of NBUF
-// shared-memory item buffers while the 15 S tiles integrate an earlier group from another buffer WITHOUT any barrier
-// between stages: the S warps drift apart and the DMMA phases of some overlap the DFMA phases of others.
-// Hand-over per item: named barriers FULL[buf] (x arrives, S wait) and EMPTY[buf] (S arrive, x waits); with NBUF
-// buffers the x tile may be up to NBUF - 1 items ahead.  The W fragments are loaded once per kernel.
-template <int METHOD, bool UNI, int NBUF>
-__global__ void __launch_bounds__(DM_THREADS, 1)
-shoot_dense_mma_pipe_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
-                            const ShootOut o, long long n_items, int rounds, int nst)
+__device__ __forceinline__ unsigned dq_peek(const unsigned *p) { return *(const volatile unsigned *)p; }
+
+// Persistent blocks; block `blockIdx.x` owns items blockIdx.x, blockIdx.x + gridDim.x, ... (item -> interval fastest).
+// Item K of the block = one x task + n_tiles S tasks.  Task order in the queue: x_0 .. x_{la-1}, then for every item K
+// its S tasks with x_{K+la} inserted after the px-th (la = nring - 1): when a warp picks x_{K+la}, the S tasks of item
+// K - 1 -- the previous users of its ring slot -- were queued more than a block's worth of warps earlier and have all
+// but certainly finished, and the result is needed only a whole item later.  Every wait is on a task EARLIER in the
+// queue (already running or done), so the order is deadlock-free.
+//   s_full[slot] = K + 1 once x_K has filled the slot;  s_done[slot] counts the finished S tasks on the slot.
+template <int METHOD, bool UNI, int NWARPS>
+__global__ void __launch_bounds__(NWARPS * 32, 1)
+shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
+                             const ShootOut o, long long n_items, int n_tiles, int nst, int nring)
 {
-    extern __shared__ double xcbuf[];   // [NBUF][nst][CPB][20]
-    const bool is_x = (threadIdx.x >> 5) == 0;   // the oldest warp: schedulers that favour older warps keep it ahead
-    const int per = nst * DM_CPB * DM_NX;
+    extern __shared__ double ring[];   // [nring][nst][8 candidates][20]
+    __shared__ unsigned q_head, s_full[DQ_MAXRING], s_done[DQ_MAXRING];
+    if (threadIdx.x == 0) {
+        q_head = 0;
+        for (int r = 0; r < DQ_MAXRING; r++) s_full[r] = s_done[r] = 0;
+    }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+    const int per = nst * DQ_CPI * DM_NX;
+    const unsigned nk = n_items > blockIdx.x ? (unsigned)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
+    const unsigned la = (unsigned)nring - 1u, row = (unsigned)n_tiles + 1u;
+    const unsigned px = (unsigned)min(nring == 3 ? 16 : 8, n_tiles);
+    const unsigned n_tasks = la + nk * row;
     DenseTile T;
     dense_load_w(L, T);
-    long long kcount = 0;
-    int buf = 0;
-    for (long long n = blockIdx.x; n < n_items; n += gridDim.x, kcount++) {
-        // item -> (group, interval, round); intervals fastest so that a block's consecutive items share nothing but W
-        const int i = (int)(n % L.In) + L.i0;
-        const long long rest = n / L.In;
-        const int round = (int)(rest % rounds);
-        const long long grp = rest / rounds;
-        double *xc = xcbuf + buf * per;
-        if (is_x) {
-            if (kcount >= NBUF) dm_bar_sync(1 + NBUF + buf);    // EMPTY[buf]: the S tiles are done with item kcount - NBUF
-            dense_unit<METHOD, UNI, true, true>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc, T);
-            __threadfence_block();
-            dm_bar_arrive(1 + buf);                               // FULL[buf]
+    for (;;) {
+        unsigned tk = 0;
+        if (lane == 0) tk = atomicAdd(&q_head, 1u);
+        tk = __shfl_sync(0xffffffffu, tk, 0);
+        if (tk >= n_tasks) break;
+        unsigned K;
+        int tau = -1;   // -1: x task
+        if (tk < la) {
+            K = tk;
         } else {
-            dm_bar_sync(1 + buf);                                 // FULL[buf]
-            dense_unit<METHOD, UNI, true, false>(L, ps, ldb, B, o, i, round, grp * DM_CPB, xc, T);
-            dm_bar_arrive(1 + NBUF + buf);                        // EMPTY[buf]
+            const unsigned q = tk - la;
+            K = q / row;
+            const unsigned r = q - K * row;
+            if (r == px)
+                K += la;
+            else
+                tau = (int)(r < px ? r : r - 1);
         }
-        buf = (buf + 1 == NBUF) ? 0 : buf + 1;
-    }
-    if (is_x) {   // consume the EMPTY signals of the last items so that no barrier is left half-arrived
-        const long long first = kcount >= NBUF ? kcount - NBUF : 0;
-        for (long long kk = first; kk < kcount; kk++) dm_bar_sync(1 + NBUF + (int)(kk % NBUF));
+        if (K >= nk) continue;   // x tasks past the last item
+        const long long n = blockIdx.x + (long long)K * gridDim.x;
+        const int i = (int)(n % L.In) + L.i0;
+        long long b = (n / L.In) * DQ_CPI + g;
+        const bool cand_live = b < B;
+        if (!cand_live) b = B - 1;
+        const int slot = (int)(K % (unsigned)nring);
+        double *sp = ring + (long long)slot * per + g * DM_NX + 5 * t;
+        const int nu0 = __ldg(L.n_u0 + i), ns = nu0 + L.ntp + __ldg(L.n_c + i);
+        if (tau < 0) {
+            const unsigned need = (unsigned)n_tiles * (K / (unsigned)nring);   // S tasks of the slot's earlier items
+            while (dq_peek(&s_done[slot]) < need) __nanosleep(64);
+            __threadfence_block();
+            dense_column<METHOD, UNI, true, true>(L, ps, ldb, o, i, nu0, ns, 0, b, true, cand_live, true, sp, nullptr,
+                                                  DQ_CPI * DM_NX, T);
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                *(volatile unsigned *)&s_full[slot] = K + 1u;
+            }
+        } else {
+            if (tau < ns) {
+                while (dq_peek(&s_full[slot]) < K + 1u) __nanosleep(64);
+                __threadfence_block();
+                dense_column<METHOD, UNI, true, false>(L, ps, ldb, o, i, nu0, ns, tau, b, true, cand_live, false, sp, nullptr,
+                                                       DQ_CPI * DM_NX, T);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                __threadfence_block();
+                atomicAdd(&s_done[slot], 1u);
+            }
+        }
     }
 }
 
@@ -425,39 +475,42 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
 {
     if (L.nact != 1 || L.ntp != 0 || L.nx != DM_NX || !L.model_data) return -1000;
     if (B <= 0) return 0;
-    const long long gx = (B + DM_CPB - 1) / DM_CPB;
-    int rounds = (max_ns + DM_DPR - 1) / DM_DPR;
-    if (rounds < 1) rounds = 1;
+    if (max_ns < 1) max_ns = 1;
     // right-hand-side calls per interval: Tsit5 6K per piece (FSAL after the last step skipped), RK4 4K
     const int nst = max_pieces * (method == 0 ? 6 : 4) * L.K;
-    const size_t per = sizeof(double) * (size_t)nst * DM_CPB * DM_NX;
+    const size_t per = sizeof(double) * (size_t)nst * DQ_CPI * DM_NX;
     static const bool lockstep = getenv("CB200_DENSE20_LOCKSTEP") != nullptr;
-    static const int nbuf_env = getenv("CB200_DENSE20_NBUF") ? atoi(getenv("CB200_DENSE20_NBUF")) : 0;
-    // three item buffers when they fit (the x tile may run two items ahead), else two
-    int nbuf = (nbuf_env == 2 || nbuf_env == 3) ? nbuf_env : 3;
-    if (nbuf == 3 && 3 * per > 200 * 1024) nbuf = 2;
-    if (!lockstep && nbuf * per <= 200 * 1024) {
+    static const int nring_env = getenv("CB200_DENSE20_NRING") ? atoi(getenv("CB200_DENSE20_NRING")) : 0;
+    static const int warps_env = getenv("CB200_DENSE20_WARPS") ? atoi(getenv("CB200_DENSE20_WARPS")) : 0;
+    const size_t smem_cap = 225 * 1024;
+    int nring = (nring_env == 2 || nring_env == 3) ? nring_env : 3;
+    if (nring == 3 && 3 * per > smem_cap) nring = 2;
+    if (!lockstep && nring * per <= smem_cap) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        const long long n_items = gx * L.In * rounds;
+        const long long n_items = ((B + DQ_CPI - 1) / DQ_CPI) * L.In;
         const unsigned grid = (unsigned)std::min<long long>(n_items, sms);
-        const size_t smem = nbuf * per;
+        const size_t smem = nring * per;
+        const int warps = (warps_env == 8 || warps_env == 12) ? warps_env : 16;
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<grid, DM_THREADS, smem, s>>>(L, ps, ldb, B, o, n_items, rounds, nst);
+            kern<<<grid, warps * 32, smem, s>>>(L, ps, ldb, B, o, n_items, max_ns, nst, nring);
         };
         if (method == 0) {
             if (L.uniform_h) {
-                if (nbuf == 3) go(shoot_dense_mma_pipe_kernel<0, true, 3>);
-                else go(shoot_dense_mma_pipe_kernel<0, true, 2>);
-            } else go(shoot_dense_mma_pipe_kernel<0, false, 2>);
+                if (warps == 8) go(shoot_dense_mma_queue_kernel<0, true, 8>);
+                else if (warps == 12) go(shoot_dense_mma_queue_kernel<0, true, 12>);
+                else go(shoot_dense_mma_queue_kernel<0, true, 16>);
+            } else go(shoot_dense_mma_queue_kernel<0, false, 16>);
         } else {
-            if (L.uniform_h) go(shoot_dense_mma_pipe_kernel<1, true, 2>);
-            else go(shoot_dense_mma_pipe_kernel<1, false, 2>);
+            if (L.uniform_h) go(shoot_dense_mma_queue_kernel<1, true, 16>);
+            else go(shoot_dense_mma_queue_kernel<1, false, 16>);
         }
         return (int)cudaGetLastError();
     }
+    const long long gx = (B + DM_CPB - 1) / DM_CPB;
+    const int rounds = (max_ns + DM_DPR - 1) / DM_DPR;
     if (gx > 2147483647LL || L.In > 65535 || rounds > 65535) return -1000;
     dim3 grid((unsigned)gx, (unsigned)L.In, (unsigned)rounds);
     if (method == 0) {

@@ -35,8 +35,8 @@ class ThreadGather:
 def make_ranks(spec, alg, nranks, max_B_total, device=0):
     import corleone_b200 as cb
     layers = []
-    for _ in range(nranks):
-        lay = P.product_layer(spec, alg, device=device)
+    for r in range(nranks):
+        lay = P.product_layer(spec, alg, device=device[r] if isinstance(device, (list, tuple)) else device)
         ps_t, st = cb.setup(None, lay)
         layers.append((lay, ps_t, lay._native(st, ps_t)))
     tg = ThreadGather(nranks)
@@ -132,14 +132,21 @@ def test_fused_allreduce_and_allgather_device_pointers(nranks, model):
 def test_comm_host_pointers_threads():
     """the same through host pointers (candidate-major, the Julia layout): every rank is a thread that calls cb200_eval and
     blocks until its results are back -- the all-reduced sums and the all-gathered defect matrix arrive in host memory"""
+    import torch
     import corleone_b200 as cb
     from corleone_b200 import native as nat
+    # Needs one GPU per rank: a host-pointer evaluation blocks its thread on synchronous (pageable) copies and queues
+    # device->host copies behind its tail, and ranks that SHARE a device share its copy engines and hardware queues
+    # (CUDA_DEVICE_MAX_CONNECTIONS) -- a rank's copies can end up behind the peer's tail, which spins for this rank.
+    # Here the ranks are threads of one process on two devices: windows by plain peer access (cudaDeviceEnablePeerAccess).
+    if torch.cuda.device_count() < 2:
+        pytest.skip("ranks with host pointers need a GPU each (tools/multi_gpu_check.py covers the same path with processes)")
     rng = np.random.default_rng(11)
     spec = P.lotka_spec(controls=rng.uniform(0, 1, 120), quadrature=True)
     alg = cb.Tsit5(2)
     nranks, shards = 2, [1500, 1203]          # the big shard takes the chunked, multi-stream host path
     B_total = sum(shards)
-    ranks = make_ranks(spec, alg, nranks, B_total)
+    ranks = make_ranks(spec, alg, nranks, B_total, device=[0, 1])
     N0 = ranks[0][2]
     ps = cb.to_vec(ranks[0][1])[None, :] + 0.05 * rng.standard_normal((B_total, N0.nvars))
     want = nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD
