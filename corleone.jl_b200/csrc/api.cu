@@ -708,6 +708,10 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     const int Gs = h->G_sens;
     const int Rmask = Gs > 0 ? std::max(1, (h->max_ns + Gs - 1) / Gs) : 1;
     std::vector<unsigned> act_mask((size_t)po * Rmask, 0u);
+    // the same table for one direction per thread: latency-bound evaluations (a few candidates, flat launch) spread the
+    // directions over more threads when the model has a G = 1 kernel
+    const int Rmask1 = std::max(1, h->max_ns);
+    std::vector<unsigned> act_mask1(Gs > 1 ? (size_t)po * Rmask1 : 0, 0u);
     for (int i = 0; i < I; i++) {
         const int nu0 = h->h_n_u0[i], nc = h->h_n_c[i], M = h->h_M[i], pof = h->h_piece_off[i], vof = h->h_var_off[i];
         const int nsi = h->ns[i];
@@ -750,6 +754,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                     const unsigned na = (unsigned)(sl % Gs) + 1u;
                     if ((w >> 24) < na) w = (w & 0xffffffu) | (na << 24);
                 }
+                if (!act_mask1.empty())
+                    act_mask1[(size_t)(pof + j) * Rmask1 + sl] = (forced ? 1u : 0u) | (j >= first[dd] ? 1u << 24 : 0u);
             }
         }
     }
@@ -891,7 +897,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
                  o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_tse = push(blob, h->h_tsens_off), o_so = push(blob, h->h_samp_off),
                  o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol), o_dperm = push(blob, dir_perm),
-                 o_am = push(blob, act_mask), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
+                 o_am = push(blob, act_mask), o_am1 = push(blob, act_mask1), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
                  o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos);
     std::vector<double> mdata;
     if (d->model_data && d->model_data_len > 0) mdata.assign(d->model_data, d->model_data + d->model_data_len);
@@ -956,6 +962,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.dir_pcol = (const signed char *)(base + o_dp);
     L.dir_perm = (const int *)(base + o_dperm);
     L.act_mask = (const unsigned *)(base + o_am);
+    h->act_mask1 = act_mask1.empty() ? nullptr : (const unsigned *)(base + o_am1);
     L.dpos_kind = (const int *)(base + o_dk);
     L.dpos_stage = (const int *)(base + o_dst);
     L.oth_off = (const int *)(base + o_oo);
@@ -1285,7 +1292,15 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     }
     const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
     CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], st));
-    int rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, st);
+    int rc = -1000;
+    if (G > 1 && B < 32 && h->act_mask1 && !h->no_g1) {   // latency-bound: one direction per thread, if the model has that kernel
+        DevLayer L1 = L;
+        L1.R = std::max(1, h->max_ns);
+        L1.act_mask = h->act_mask1;
+        rc = launch_model(h->model, 1, h->method, L1, d_ps, d_ldb, B, so, st);
+        if (rc == -1000) h->no_g1 = true;
+    }
+    if (rc == -1000) rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, st);
     if (rc == -1000)
         return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
                     h->method);

@@ -118,6 +118,8 @@ struct cb200_handle {
     int range_i0 = 0, range_n = -1;   // cb200_set_interval_range: intervals [i0, i0 + n); n < 0 = all
     bool d20_ref = false;             // holds a reference on the device's DENSE20 constant block
     int G_sens = 2;                   // sensitivity directions per thread
+    const unsigned *act_mask1 = nullptr;   // DevLayer::act_mask for one direction per thread (flat launches), or nullptr
+    bool no_g1 = false;               // the model has no G = 1 kernel
     void *tables = nullptr;           // one device allocation holding every table
     int *d_quad = nullptr;
     GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row

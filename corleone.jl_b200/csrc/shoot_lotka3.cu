@@ -7,6 +7,7 @@ int launch_lotka3(int G, int method, const DevLayer &L, const double *ps, long l
 {
     switch (G) {
         CB200_DISPATCH_GA(Lotka3, 0, 1)
+        CB200_DISPATCH_GA(Lotka3, 1, 1)
         CB200_DISPATCH_GA(Lotka3, 2, 1)
         CB200_DISPATCH_GA(Lotka3, 5, 1)
     default:

@@ -316,6 +316,24 @@ class NativeLayer:
         o.resident, o.comm_B_total, o.comm_b0 = resident, comm_B_total, comm_b0
         _check(lib().cb200_eval(self._h, C.c_void_p(ps_ptr), B, ldb, want, flags, C.byref(o)), "cb200_eval")
 
+    def prepare_call(self, ps_ptr: int, B: int, ldb: int, want: int, flags: int, ptrs: dict, objective_row: int = 1,
+                     resident: int = 0):
+        """The same call with the argument block built once: returns a function that issues cb200_eval and nothing else
+        (what a Julia `ccall` costs; eval_raw fills a ctypes struct per call, which is microseconds of Python)."""
+        o = Out()
+        for k, v in ptrs.items():
+            setattr(o, k, v)
+        o.objective_row = objective_row
+        o.resident = resident
+        fn, h, ref, psp = lib().cb200_eval, self._h, C.byref(o), C.c_void_p(ps_ptr)
+
+        def call():
+            rc = fn(h, psp, B, ldb, want, flags, ref)
+            if rc:
+                _check(rc, "cb200_eval")
+        call._keepalive = o
+        return call
+
     def eval_host(self, ps, want: int, objective_row: int = 1, fim_init=None, pinned_out: dict | None = None,
                   with_sums: bool = False):
         """ps: (B, nvars) C-contiguous float64 == a Julia nvars x B matrix. Returns dict of (B, n) arrays."""
