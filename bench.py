@@ -207,9 +207,10 @@ def roofline_entry(work, units, kern_ms, peak, peak_src, hbm_peak, hbm_src, kern
     gbs = work["bytes"] * units / (kern_ms * 1e-3) / 1e9
     tr = ncu_traffic(traffic_key)
     return {"bound": "fp64", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak if peak > 0 else None,
-            "traffic": tr["bytes_per_launch"] if tr else None,
+            "traffic": tr["bytes_per_unit"] * units if tr else None,
             "traffic_source": (f"{tr['file']} ({tr['date']}; ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum of one "
-                               f"launch on {tr['workload']})") if tr else None,
+                               f"launch on {tr['workload']}: {tr['bytes_per_launch']:.4g} B for {tr['units_in_capture']:.0f} units = "
+                               f"{tr['bytes_per_unit']:.1f} B per unit, times the units of this launch)") if tr else None,
             "algorithmic_bytes_per_launch": work["bytes"] * units, "kernel": kernel, "kernel_ms": kern_ms,
             "flops_per_unit": work["flops"], "bytes_per_unit": work["bytes"], "peak_source": peak_src,
             "hbm": {"achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak, "peak_source": hbm_src}}
@@ -258,7 +259,7 @@ def run_config4(args, torch, dev, local_rank, clk, n_candidates=65536, e2e=True)
     ms_total, launches = timed_steps(torch, stream, step, args.steps, max(3, args.warmup), N=N)
     kern_ms = float(np.mean(N.kernel_ms_history(min(256, args.steps))))
     units = I * B
-    res = {"workload": "dense20_256x65k" if B == 65536 else f"dense20_256x{B}", "units_per_step": units,
+    res = {"workload": "dense20_256x65k" if B == 65536 else f"dense20_256x{B}", "units_per_step": units, "e2e": None,
            "value": units * args.steps / (ms_total * 1e-3), "unit": "units/s", "ms_per_step": ms_total / args.steps,
            "kernel_ms": kern_ms, "steps": args.steps,
            "outputs": f"sens ({8 * sz['sens'] * B / 1e9:.1f} GB, resident in HBM), defects_kind, xend",
@@ -778,6 +779,14 @@ def main():
                 line["cpu_baseline"] = {"value": v, "unit": "units/s", "cores": cores, "kind": "port", "sample": sample}
             c4["_N"].close()
             all_configs.append(strip(c4))
+            torch.cuda.empty_cache()
+            # the N = 1 base of the strong-scaling sweep (`--gpus N`, N > 1): config 5's 2^20 units on one GPU, no collectives
+            c5 = run_config4(args, torch, dev, local_rank, clk, 4096, e2e=False)
+            c5["workload"] = "scale_1M on one GPU (256 intervals x 4096 candidates: the base of the N > 1 strong-scaling runs)"
+            c5["roofline"] = roofline_entry(WORK["dense20"], c5["units_per_step"], c5["kernel_ms"], peak, peak_src, hbm_peak, hbm_src,
+                                            c4["roofline"]["kernel"], "dense20")
+            c5["_N"].close()
+            all_configs.append(strip(c5))
             torch.cuda.empty_cache()
         sub_steps = max(20, args.steps)
         if "2" in only:

@@ -8,6 +8,6 @@ for l in sys.stdin:
         d=json.loads(l)
         for c in d['all_configs']:
             r=c.get('roofline') or {}
-            print(c['workload'], 'value %.4g' % c['value'], 'ms/step %.4f' % c['ms_per_step'], 'kernel_ms %.4f' % c['kernel_ms'], 'frac %.3f' % (r.get('frac') or 0), 'e2e %.4g' % c['e2e']['value'], 'lat_us', c.get('latency_us_per_call'))
+            print(c['workload'], 'value %.4g' % c['value'], 'ms/step %.4f' % c['ms_per_step'], 'kernel_ms %.4f' % c['kernel_ms'], 'frac %.3f' % (r.get('frac') or 0), 'e2e %.4g' % ((c.get('e2e') or {}).get('value') or 0), 'lat_us', c.get('latency_us_per_call'))
     elif 'rror' in l: print(l.rstrip())
 "

@@ -71,6 +71,30 @@ def main():
             lines.append(f"    FP64 share: {100.0 * fp / tot_i:.1f} % of instructions, {100.0 * fps / tot_s:.1f} % of samples")
     open(out, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines))
+    # optional: record the kernel's DRAM traffic per launch for bench.py's roofline.traffic
+    #   python tools/ncu_summary.py <rep> <txt> <traffic.json> <key> <units in the captured launch> <workload text>
+    if len(sys.argv) >= 7:
+        import datetime
+        import json
+        import os
+        jpath, key, units, workload = sys.argv[3], sys.argv[4], float(sys.argv[5]), sys.argv[6]
+        d = dict(zip(hdr, rows[2]))
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            tot += float(d[k]) * scale[units_of(hdr, units_row=units_row(rows), key=k)]
+        cur = json.load(open(jpath)) if os.path.exists(jpath) else {}
+        cur[key] = {"bytes_per_launch": tot, "units_in_capture": units, "bytes_per_unit": tot / units, "workload": workload,
+                    "file": os.path.relpath(out), "date": datetime.date.today().isoformat()}
+        json.dump(cur, open(jpath, "w"), indent=1)
+
+
+def units_row(rows):
+    return rows[1]
+
+
+def units_of(hdr, units_row, key):
+    return units_row[hdr.index(key)]
 
 
 if __name__ == "__main__":
