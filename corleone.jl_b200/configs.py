@@ -188,7 +188,8 @@ def doubleosc_spec(n_intervals=3, rng=None):
 def layer_from_spec(spec, alg, **kw):
     """Build the SingleShootingLayer / MultipleShootingLayer a spec describes."""
     prob = ODEProblem(spec["model"], spec["u0"], spec["tspan"], spec["p0"], model_data=spec.get("model_data"),
-                      kwargs=dict(spec.get("kwargs", {})))   # abstol / reltol of the adaptive mode ride here, as in the reference
+                      kwargs=dict(spec.get("kwargs", {}),   # abstol / reltol of the adaptive mode ride here, as in the reference
+                                  **({"saveat": list(spec["saveat"])} if spec.get("saveat") is not None else {})))
     names = spec.get("control_names") or [f"u{k + 1}" for k in range(len(spec["controls"]))]
     cb = spec.get("control_bounds") or [None] * len(spec["controls"])
     ctr = [(ci, ControlParameter(t, name=n, controls=(np.zeros(len(t)) if u is None else u),

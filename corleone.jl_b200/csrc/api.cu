@@ -101,7 +101,7 @@ __global__ void grad_kernel(const GradEntry *__restrict__ tab, int n, const doub
 // quadrature accumulation on the merged trajectory (src/multiple_shooting.jl:171-177)
 __global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const double *__restrict__ xend,
                                  long long ldx, long long B, int nx, int nrow, int I, const int *__restrict__ samp_off,
-                                 const int *__restrict__ M, const int *__restrict__ quad, int nquad)
+                                 const int *__restrict__ nsm, const int *__restrict__ quad, int nquad)
 {
     const long long b = blockIdx.x * (long long)blockDim.x + threadIdx.x;
     if (b >= B) return;
@@ -109,7 +109,7 @@ __global__ void traj_quad_kernel(double *__restrict__ traj, long long ldo, const
         const int k = quad[q];
         double run = xend[(long long)k * ldx + b];
         for (int i = 1; i < I; i++) {
-            const int nsmp = M[i] + (i == I - 1 ? 1 : 0);
+            const int nsmp = nsm[i];
             for (int j = 0; j < nsmp; j++) traj[((long long)(samp_off[i] + j) * nrow + k) * ldo + b] += run;
             run += xend[((long long)i * nx + k) * ldx + b];
         }
@@ -330,10 +330,10 @@ static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
     case CB200_MODEL_DOUBLEOSC6: *nx = 6; *np = 1; d = 5; break;
     case CB200_MODEL_LOTKA2_OED_CU: *nx = 9; *np = 3; d = 6; break;
     case CB200_MODEL_LOTKA2_OED_CF: *nx = 12; *np = 5; d = 6; break;
-    case CB200_MODEL_LOTKA2_OED_DS: *nx = 6; *np = 5; d = 6; break;
+    case CB200_MODEL_LOTKA2_OED_DS: *nx = 6; *np = 3; d = 6; break;
     case CB200_MODEL_LOTKA2_OED_DU: *nx = 6; *np = 3; d = 6; break;
     case CB200_MODEL_LIN1D_OED_CF: *nx = 3; *np = 2; d = 2; break;
-    case CB200_MODEL_LIN1D_OED_DS: *nx = 2; *np = 2; d = 2; break;
+    case CB200_MODEL_LIN1D_OED_DS: *nx = 2; *np = 1; d = 2; break;
     case CB200_MODEL_BRYSONDENHAM3: *nx = 3; *np = 1; d = 2; break;
     case CB200_MODEL_CATALYSTMIXING2: *nx = 2; *np = 1; d = 2; break;
     case CB200_MODEL_CUSHIONED3: *nx = 3; *np = 2; d = 2; break;
@@ -622,6 +622,18 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         }
     }
 
+    // saveat (problem.kwargs): sorted times; a piece saves those strictly inside it from the dense output
+    if (d->n_saveat < 0 || (d->n_saveat > 0 && !d->saveat)) {
+        delete h;
+        return fail(CB200_ERR_ARG, "n_saveat = %d without saveat times", d->n_saveat);
+    }
+    for (int k = 1; k < d->n_saveat; k++)
+        if (!(d->saveat[k] > d->saveat[k - 1])) {
+            delete h;
+            return fail(CB200_ERR_ARG, "saveat must be strictly ascending");
+        }
+    std::vector<int> psamp, nsm, sv_n, sv_off;
+    std::vector<double> sv_t;
     // per-interval tables
     std::vector<double> pt0, pt1, ph, ic_fix, ic_fix0;
     int po = 0, vo = 0, so = 0, co = 0, sio = 0;
@@ -642,14 +654,28 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         h->h_samp_off.push_back(so);
         h->h_sens_off.push_back(seo);
         h->h_tsens_off.push_back(h->n_tsens);
-        h->n_tsens += (long long)(M + (i == I - 1 ? 1 : 0)) * (d->n_u0[i] + ntp + d->n_local_controls[i]) * nx;
         const int nsi = d->n_u0[i] + ntp + d->n_local_controls[i];
+        int samp_i = 0;   // samples of this interval after its start sample
         h->ns.push_back(nsi);
         h->max_ns = std::max(h->max_ns, nsi);
         for (int j = 0; j < M; j++) {
             pt0.push_back(d->tspans[2 * (size_t)(po + j)]);
             pt1.push_back(d->tspans[2 * (size_t)(po + j) + 1]);
             ph.push_back((pt1.back() - pt0.back()) / (double)d->steps_per_piece);
+            sv_off.push_back((int)sv_t.size());
+            int nin = 0;
+            for (int k = 0; k < d->n_saveat; k++)
+                if (d->saveat[k] > pt0.back() && d->saveat[k] < pt1.back()) {
+                    sv_t.push_back(d->saveat[k]);
+                    nin++;
+                }
+            sv_n.push_back(nin);
+            if (nin > 0) h->has_saveat = true;
+            if (j == 0) h->h_sample_t.push_back(pt0.back());   // every interval keeps its start sample, the end sample of all but the last is dropped
+            for (int k = 0; k < nin; k++) h->h_sample_t.push_back(sv_t[sv_t.size() - (size_t)nin + (size_t)k]);
+            if (j + 1 < M || i == I - 1) h->h_sample_t.push_back(pt1.back());
+            samp_i += nin + 1;
+            psamp.push_back(samp_i);
             for (int r = 0; r < nact; r++) {
                 const long long ci = d->index_grid[igo + r + (long long)nact * j] - 1;
                 if (ci < 0 || ci >= d->n_local_controls[i]) {
@@ -689,11 +715,21 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         co += ncon;
         sidx_off[i + 1] = sidx_off[i] + d->n_shooting_indices[i];
         sio += d->n_shooting_indices[i];
+        nsm.push_back(samp_i + (i == I - 1 ? 1 : 0));
+        h->n_tsens += (long long)nsm.back() * nsi * nx;
         po += M;
         igo += (long long)nact * M;
         vo += nsi;
-        so += M;
+        so += samp_i;
         seo += (long long)nx * nsi;
+    }
+    if (h->has_saveat && d->method == CB200_RK4) {
+        delete h;
+        return fail(CB200_ERR_UNSUPPORTED, "saveat times inside a control piece need Tsit5's dense output (method 0 or 2)");
+    }
+    if (h->has_saveat && d->model == CB200_MODEL_DENSE20) {
+        delete h;
+        return fail(CB200_ERR_UNSUPPORTED, "saveat is not available for the dense tensor-path model");
     }
     (void)sio;
     L.nvars = vo;
@@ -870,7 +906,8 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         long long go = 0;
         for (int i = 0; i < I; i++) {
             const int rows = d->n_observation_rows[i];
-            const int max_rows = h->h_M[i] + ((i == I - 1 && h->fim_mode == CB200_FIM_DISCRETE_SAMPLED) ? 1 : 0);
+            // rows <-> samples of the interval in the merged trajectory (DISCRETE_SAMPLED) / its pieces (FIXED_CONTINUOUS)
+            const int max_rows = h->fim_mode == CB200_FIM_DISCRETE_SAMPLED ? nsm[(size_t)i] : h->h_M[i];
             if (rows < 0 || rows > max_rows) {
                 delete h;
                 return fail(CB200_ERR_ARG, "interval %d: %d observation rows, at most %d samples", i + 1, rows, max_rows);
@@ -896,6 +933,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
                  o_t1 = push(blob, pt1), o_ph = push(blob, ph), o_ci = push(blob, h->h_cidx), o_vo = push(blob, h->h_var_off),
                  o_nu = push(blob, h->h_n_u0), o_nc = push(blob, h->h_n_c), o_is = push(blob, h->h_ic_src),
                  o_if = push(blob, ic_fix), o_if0 = push(blob, ic_fix0), o_se = push(blob, h->h_sens_off), o_tse = push(blob, h->h_tsens_off), o_so = push(blob, h->h_samp_off),
+                 o_psamp = push(blob, psamp), o_nsm = push(blob, nsm), o_svn = push(blob, sv_n), o_svo = push(blob, sv_off), o_svt = push(blob, sv_t),
                  o_q = push(blob, h->quad0), o_dp = push(blob, dir_pcol), o_dperm = push(blob, dir_perm),
                  o_am = push(blob, act_mask), o_am1 = push(blob, act_mask1), o_dk = push(blob, h->dpos_kind), o_dst = push(blob, h->dpos_stage),
                  o_oo = push(blob, h->oth_off), o_ot = push(blob, h->oth), o_jp = push(blob, h->jpos);
@@ -959,6 +997,11 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     L.sens_off = (const long long *)(base + o_se);
     L.tsens_off = (const long long *)(base + o_tse);
     L.samp_off = (const int *)(base + o_so);
+    L.psamp = (const int *)(base + o_psamp);
+    L.nsm = (const int *)(base + o_nsm);
+    L.sv_n = h->has_saveat ? (const int *)(base + o_svn) : nullptr;
+    L.sv_off = (const int *)(base + o_svo);
+    L.sv_t = (const double *)(base + o_svt);
     L.dir_pcol = (const signed char *)(base + o_dp);
     L.dir_perm = (const int *)(base + o_dperm);
     L.act_mask = (const unsigned *)(base + o_am);
@@ -1321,7 +1364,7 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
         }
     }
     if (pl.need_traj && h->nquad > 0 && I > 1) {
-        traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, ldo, d.xend, ldo, B, nx, (int)nrow, I, L.samp_off, L.M,
+        traj_quad_kernel<<<nblk(B, 128), 128, 0, st>>>(d.traj, ldo, d.xend, ldo, B, nx, (int)nrow, I, L.samp_off, L.nsm,
                                                      h->d_quad, h->nquad);
         h->launches++;
     }
@@ -1910,6 +1953,13 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     return comm_check(h);
 }
 
+extern "C" int cb200_sample_times(const cb200_handle *h, double *t)
+{
+    if (!h || !t) return fail(CB200_ERR_ARG, "null argument");
+    for (size_t k = 0; k < h->h_sample_t.size(); k++) t[k] = h->h_sample_t[k];
+    return CB200_OK;
+}
+
 extern "C" int cb200_resident(const cb200_handle *h, uint32_t want_bit, double **ptr, int64_t *ld)
 {
     if (!h || !ptr) return fail(CB200_ERR_ARG, "null argument");
@@ -1941,7 +1991,8 @@ extern "C" int cb200_abi_layout(int32_t which, int64_t *vals, int32_t n)
     switch (which) {
     case 0:
         v = {(int64_t)sizeof(cb200_desc), (int64_t)offsetof(cb200_desc, u0), (int64_t)offsetof(cb200_desc, model_data_len),
-             (int64_t)offsetof(cb200_desc, observation_grid), (int64_t)offsetof(cb200_desc, reltol)};
+             (int64_t)offsetof(cb200_desc, observation_grid), (int64_t)offsetof(cb200_desc, reltol),
+             (int64_t)offsetof(cb200_desc, saveat), (int64_t)offsetof(cb200_desc, n_saveat)};
         break;
     case 1:
         v = {(int64_t)sizeof(cb200_out), (int64_t)offsetof(cb200_out, objective_row), (int64_t)offsetof(cb200_out, jac_vals),

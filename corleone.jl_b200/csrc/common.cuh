@@ -39,6 +39,11 @@ struct DevLayer {
     const long long *sens_off;  // [I] first row of the interval's block in `sens`
     const int *samp_off;     // [I] first merged-trajectory sample of the interval
     const long long *tsens_off;  // [I] first row of the interval's block in `traj_sens`
+    const int *psamp;        // [sum M] index of the piece's END sample among the samples of its interval (j + 1 without saveat)
+    const int *nsm;          // [I] samples of the interval in the merged trajectory (its end sample dropped unless it is the last)
+    const int *sv_n;         // [sum M] saveat times strictly inside the piece -- nullptr: the layer has none anywhere
+    const int *sv_off;       // [sum M] offset of the piece's times in sv_t
+    const double *sv_t;      // the saveat times, piece after piece
     const double *model_data;  // model constants in HBM (DENSE20: W row-major 20x20, then b[20]) or nullptr
     const signed char *dir_pcol;  // [nvars] 0-based p column that local variable (= direction) perturbs; -1: a u0 entry
     const int *dir_perm;          // [nvars] direction held by slot s of the interval (activation order, see shoot.cuh)

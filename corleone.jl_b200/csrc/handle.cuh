@@ -103,6 +103,8 @@ struct cb200_handle {
     std::vector<int> h_M, h_var_off, h_n_u0, h_n_c, h_samp_off, h_piece_off;
     std::vector<long long> h_sens_off, h_tsens_off;
     long long n_tsens = 0;
+    std::vector<double> h_sample_t;   // times of the merged trajectory's samples
+    bool has_saveat = false;
     std::vector<int> h_cidx, h_ic_src;
     std::vector<DefectEntry> defects;
     std::vector<int> dpos_kind, dpos_stage, oth_off, jpos;

@@ -32,6 +32,17 @@ struct FimTraits<M, decltype((void)M::FIM_N, void())> {
     static constexpr int N = M::FIM_N, OFF = M::FIM_OFF;
 };
 
+// SaveAtTraits<M>::ON: the shooting kernel is also instantiated with dense-output sampling at saveat times inside control
+// pieces (cb200_desc.saveat) for model M -- models that declare `static constexpr bool SAVEAT = true`
+template <class M, class = void>
+struct SaveAtTraits {
+    static constexpr bool ON = false;
+};
+template <class M>
+struct SaveAtTraits<M, decltype((void)M::SAVEAT, void())> {
+    static constexpr bool ON = M::SAVEAT;
+};
+
 #ifdef CB200_NEED_DENSE20_DATA
 // model constants for DENSE20 (W row-major 20x20, then b[20]); constant-bank operands of the FMAs
 __constant__ double c_dense20[420];
@@ -40,6 +51,7 @@ __constant__ double c_dense20[420];
 // ---- Lotka-Volterra fishing with Lagrange state (examples/lotka_fishing_optimal_control/main.jl:38-42)
 struct Lotka3 {
     static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 3;
+    static constexpr bool SAVEAT = true;   // also built with dense-output sampling (cb200_desc.saveat)
     static constexpr bool HAS_JVP = true;
     struct Ctx {
         double j00, j01, j10, j11, x12, q0, q1;
@@ -77,6 +89,7 @@ struct Lotka3 {
 // ---- Lotka-Volterra without the Lagrange state (lib/CorleoneOED/examples/lotka_oed/main.jl:61-65)
 struct Lotka2 {
     static constexpr int NX = 2, NXD = 2, NQ = 0, NP = 3;
+    static constexpr bool SAVEAT = true;   // also built with dense-output sampling (cb200_desc.saveat)
     static constexpr bool HAS_JVP = true;
     struct Ctx {
         double j00, j01, j10, j11, x12;
@@ -148,6 +161,7 @@ struct Lqr {
 // ---- 1-D linear problem (lib/CorleoneOED/test/core/1d_oed.jl:11-13)
 struct Lin1d {
     static constexpr int NX = 1, NXD = 1, NQ = 0, NP = 1;
+    static constexpr bool SAVEAT = true;   // also built with dense-output sampling (cb200_desc.saveat)
     static constexpr bool HAS_JVP = true;
     struct Ctx {};
     struct Force {
@@ -246,7 +260,11 @@ struct OedAug {
     static_assert(Base::NQ == 0, "OED base model must not carry quadrature states");
     static constexpr int BX = Base::NX, NF = Traits::NF, NOBS = Traits::NOBS, MODE = Traits::MODE;
     static constexpr int NTRI = NF * (NF + 1) / 2;
-    static constexpr int NW = (MODE == OED_CU || MODE == OED_DU) ? 0 : NOBS;   // weights appended to p
+    // weights appended to p: the continuous variants with measurements.  The discrete ones keep the base parameters
+    // (augmentation.jl:171-203): their measurement controls do not act on the dynamics, are filtered out of the index grid
+    // (src/single_shooting.jl:301-304) and weight the samples taken at the measurement times (saveat) in the read-out
+    static constexpr int NW = (MODE == OED_CU || MODE == OED_DU || MODE == OED_DS) ? 0 : NOBS;
+    static constexpr bool SAVEAT = (MODE == OED_DS || MODE == OED_DU);
     static constexpr int NXD = BX + BX * NF;
     static constexpr int NQ = (MODE == OED_DS || MODE == OED_DU) ? 0 : (MODE == OED_CF ? NOBS * NTRI : NTRI);
     static constexpr int NX = NXD + NQ, NP = Base::NP + NW;

@@ -177,6 +177,144 @@ __device__ __forceinline__ void integrate_piece(double *yd, double *yq, const do
     }
 }
 
+// ---- saveat: samples strictly inside a control piece come from the dense output of the step that contains them
+// (problem.kwargs saveat, lib/CorleoneOED/src/oed.jl:106-113; OrdinaryDiffEq interpolates, it does not cut steps).
+// Tsit5's interpolant (Tsitouras 2011, the 4th-order "free" continuous extension OrdinaryDiffEq uses for Tsit5):
+//   y(t + theta dt) = y + dt sum_i b_i(theta) k_i,  b_1 = theta (r11 + theta (r12 + theta (r13 + theta r14))),
+//   b_i = theta^2 (ri2 + theta (ri3 + theta ri4)), i = 2..7;  b_i(1) = a_7i (checked in tests/test_saveat_host.py)
+__device__ __forceinline__ void tsit5_interp_weights(double th, double *bw)
+{
+    constexpr double R[7][4] = {{1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+                                {0.0, 0.13169999999999998, -0.2234, 0.1017},
+                                {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+                                {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+                                {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+                                {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+                                {0.0, 1.5, -4.0, 2.5}};
+    const double th2 = th * th;
+    bw[0] = th * fma(th, fma(th, fma(th, R[0][3], R[0][2]), R[0][1]), R[0][0]);
+#pragma unroll
+    for (int i = 1; i < 7; i++) bw[i] = th2 * fma(th, fma(th, R[i][3], R[i][2]), R[i][1]);
+}
+
+template <class Mdl>
+__device__ __forceinline__ void save_sample(const DevLayer &L, const ShootOut &o, long long sample, int nrow, long long b,
+                                         const double *yd, const double *yq, const double *p);
+template <class Mdl, int G>
+__device__ __forceinline__ void save_sens_sample(const ShootOut &o, long long row0, long long b, const int *dmap,
+                                                 const double *yd, const double *yq);
+
+// no saveat: the integrators compile their sampling code away
+struct NoSampler {
+    static constexpr bool ON = false;
+    int n = 0;
+    __device__ __forceinline__ double time(int) const { return 0.0; }
+    __device__ __forceinline__ void emit(int, const double *, const double *) const {}
+};
+// the saveat times of one piece and where their samples go
+template <class Mdl, int G, bool TS>
+struct PieceSampler {
+    static constexpr bool ON = true;
+    const DevLayer *L;
+    const ShootOut *o;
+    const double *t;      // the piece's saveat times
+    int n;
+    long long b;
+    long long samp0;      // merged-trajectory index of the first of them
+    long long tsrow0;     // traj_sens row of the first of them
+    int ns, nrow;
+    const int *dmap;
+    const double *p;
+    bool write_traj, write_tsens;
+    __device__ __forceinline__ double time(int m) const { return __ldg(t + m); }
+    __device__ __forceinline__ void emit(int m, const double *zd, const double *zq) const
+    {
+        if (write_traj) save_sample<Mdl>(*L, *o, samp0 + m, nrow, b, zd, zq, p);
+        if constexpr (G > 0 && TS) {
+            if (write_tsens) save_sens_sample<Mdl, G>(*o, tsrow0 + (long long)m * ns * Mdl::NX, b, dmap, zd, zq);
+        }
+    }
+};
+
+// samples of the pending saveat times up to tnew from the step (tprev, dt) with start values (y0d, y0q) and stage
+// derivatives kd[7][ND], kq[7][NQ]; returns the new count of emitted samples
+template <int ND, int NQR, int NQA, class SMP>
+__device__ __forceinline__ int emit_pending(const SMP &smp, int m, double tprev, double dt, double tnew, const double *y0d,
+                                            const double *y0q, const double (*kd)[ND], const double (*kq)[NQA])
+{
+    while (m < smp.n && smp.time(m) <= tnew) {
+        double bw[7], zd[ND], zq[NQA];
+        tsit5_interp_weights((smp.time(m) - tprev) / dt, bw);
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            double acc = kd[0][c] * bw[0];
+#pragma unroll
+            for (int j = 1; j < 7; j++) acc = fma(kd[j][c], bw[j], acc);
+            zd[c] = fma(dt, acc, y0d[c]);
+        }
+#pragma unroll
+        for (int c = 0; c < NQR; c++) {
+            double acc = kq[0][c] * bw[0];
+#pragma unroll
+            for (int j = 1; j < 7; j++) acc = fma(kq[j][c], bw[j], acc);
+            zq[c] = fma(dt, acc, y0q[c]);
+        }
+        smp.emit(m, zd, zq);
+        m++;
+    }
+    return m;
+}
+
+// fixed-step Tsit5 over one piece WITH saveat samples: the textbook form that keeps every stage derivative of the step
+// (the accumulator form of integrate_piece folds them away).  Same arithmetic per stage, so the end state agrees with
+// integrate_piece to rounding.  Not a throughput path (the discrete OED layers).
+template <class Mdl, int G, class SMP>
+__device__ __noinline__ void integrate_piece_dense(double *yd, double *yq, const double *p, const typename Mdl::Force *F,
+                                                   double t0, double t1, int K, const SMP &smp)
+{
+    using namespace ts5;
+    constexpr int ND = Mdl::NXD * (1 + G), NQR = Mdl::NQ * (1 + G), NQA = NQR > 0 ? NQR : 1;
+    constexpr double A[7][6] = {{0, 0, 0, 0, 0, 0},         {a21, 0, 0, 0, 0, 0},       {a31, a32, 0, 0, 0, 0},
+                                {a41, a42, a43, 0, 0, 0},   {a51, a52, a53, a54, 0, 0}, {a61, a62, a63, a64, a65, 0},
+                                {a71, a72, a73, a74, a75, a76}};
+    double kd[7][ND], kq[7][NQA], td[ND], nq[NQA];
+    const double h = (t1 - t0) / (double)K;
+    int m = 0;
+    rhs_all<Mdl, G>(yd, p, F, kd[0], kq[0]);
+    for (int s = 0; s < K; s++) {
+#pragma unroll
+        for (int st = 1; st < 7; st++) {
+#pragma unroll
+            for (int c = 0; c < ND; c++) {
+                double acc = yd[c];
+#pragma unroll
+                for (int j = 0; j < st; j++) acc = fma(h * A[st][j], kd[j][c], acc);
+                td[c] = acc;
+            }
+            rhs_all<Mdl, G>(td, p, F, kd[st], kq[st]);
+        }
+#pragma unroll
+        for (int c = 0; c < NQR; c++) {
+            double acc = yq[c];
+#pragma unroll
+            for (int j = 0; j < 6; j++) acc = fma(h * A[6][j], kq[j][c], acc);
+            nq[c] = acc;
+        }
+        const double tprev = t0 + s * h, tnew = (s + 1 == K) ? t1 : t0 + (s + 1) * h;
+        m = emit_pending<ND, NQR, NQA>(smp, m, tprev, h, tnew, yd, yq, kd, kq);
+#pragma unroll
+        for (int c = 0; c < ND; c++) {
+            yd[c] = td[c];   // the 7th stage input is the new state
+            kd[0][c] = kd[6][c];
+        }
+#pragma unroll
+        for (int c = 0; c < NQR; c++) {
+            yq[c] = nq[c];
+            kq[0][c] = kq[6][c];
+        }
+    }
+}
+
 // ---- method 2: adaptive Tsit5, the reference's default mode (`solve(problem, Tsit5(); ...)` per control piece with the
 // problem's abstol / reltol, src/single_shooting.jl:443-453).  OrdinaryDiffEq's stepping restated from its published
 // algorithm (has the long form and the pin on the reference's golden vectors): Hairer's initial-step
@@ -201,10 +339,12 @@ __device__ __forceinline__ double cb_fastpow(double x, double y)
     return x == 0.0 ? 0.0 : (double)(float)exp2((double)__fmul_rn((float)y, cb_fastlog2((float)x)));
 }
 
-template <class Mdl, int G>
+template <class Mdl, int G, class SMP = NoSampler>
 __device__ __noinline__ void integrate_piece_adaptive(double *yd, double *yq, const double *p, const typename Mdl::Force *F,
-                                                      double t0, double t1, double abstol, double reltol)
+                                                      double t0, double t1, double abstol, double reltol, const SMP &smp = SMP())
 {
+    int n_emitted = 0;
+    (void)n_emitted;
     using namespace ts5;
     constexpr int NXD = Mdl::NXD, NQS = Mdl::NQ, NX = Mdl::NX;
     constexpr int ND = NXD * (1 + G), NQR = NQS * (1 + G), NQA = NQR > 0 ? NQR : 1, NQS1 = NQS > 0 ? NQS : 1;
@@ -318,6 +458,8 @@ __device__ __noinline__ void integrate_piece_adaptive(double *yd, double *yq, co
             double tt = t + dt;
             const double big = fabs(t1);
             if (fabs(tt - t1) < 100.0 * (__longlong_as_double(__double_as_longlong(big) + 1) - big)) tt = t1;   // 100 eps(t1)
+            if constexpr (SMP::ON)   // saveat times inside the accepted step: dense output, before the step's data is shifted
+                n_emitted = emit_pending<ND, NQR, NQA>(smp, n_emitted, t, dt, tt, yd, yq, kd, kq);
             t = tt;
 #pragma unroll
             for (int c = 0; c < ND; c++) {
@@ -396,7 +538,8 @@ __device__ __forceinline__ void save_sens_sample(const ShootOut &o, long long ro
 // per (model, G) in the model's dispatch table from ptxas -v (largest value without spills in the step loop).
 // TS: also store the sensitivities at every saved sample (WANT_TRAJ_SENS) -- a separate instantiation, so that the
 // common case keeps its register allocation and instruction schedule.
-template <class Mdl, int G, int METHOD, bool UNI, int MINB, bool TS>
+// SV: the layer has saveat times inside pieces (instantiated for the models that ask for it, SaveAtTraits).
+template <class Mdl, int G, int METHOD, bool UNI, int MINB, bool TS, bool SV = false>
 __global__ void __launch_bounds__(128, MINB)
 shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B, const ShootOut o)
 {
@@ -556,7 +699,35 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         if constexpr (G > 0 && TS) {
             if (o.tsens && live && j == 0) save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i), b, dmap, yd, yq);
         }
-        if constexpr (METHOD == 2) {
+        const int pse = __ldg(L.psamp + po + j);   // index of the piece's end sample within the interval
+        bool sampled = false;
+        if constexpr (SV && METHOD != 1) {
+            const int nsv = L.sv_n ? __ldg(L.sv_n + po + j) : 0;
+            if (nsv > 0) {   // warp-uniform
+                sampled = true;
+                PieceSampler<Mdl, G, TS> smp;
+                smp.L = &L;
+                smp.o = &o;
+                smp.t = L.sv_t + __ldg(L.sv_off + po + j);
+                smp.n = nsv;
+                smp.b = b;
+                smp.samp0 = (long long)so + pse - nsv;
+                smp.ns = ns;
+                smp.nrow = nrow;
+                smp.tsrow0 = __ldg(L.tsens_off + i) + (long long)(pse - nsv) * ns * NX;
+                smp.dmap = dmap;
+                smp.p = p;
+                smp.write_traj = o.traj && live && r == 0;
+                smp.write_tsens = o.tsens && live;
+                if constexpr (METHOD == 2)
+                    integrate_piece_adaptive<Mdl, G>(yd, yq, p, F, __ldg(L.pt0 + po + j), __ldg(L.pt1 + po + j), L.abstol, L.reltol, smp);
+                else
+                    integrate_piece_dense<Mdl, G>(yd, yq, p, F, __ldg(L.pt0 + po + j), __ldg(L.pt1 + po + j), L.K, smp);
+            }
+        }
+        if (sampled) {
+            // done above
+        } else if constexpr (METHOD == 2) {
             integrate_piece_adaptive<Mdl, G>(yd, yq, p, F, __ldg(L.pt0 + po + j), __ldg(L.pt1 + po + j), L.abstol, L.reltol);
         } else if constexpr (UNI) {
             if (r == 0)   // block-uniform: only the first direction group reports the state (and its quadratures)
@@ -574,10 +745,10 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
-            save_sample<Mdl>(L, o, (long long)(so + j + 1), nrow, b, yd, yq, p);
+            save_sample<Mdl>(L, o, (long long)(so + pse), nrow, b, yd, yq, p);
         if constexpr (G > 0 && TS) {
             if (o.tsens && live && (j + 1 < M || last_interval))
-                save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i) + (long long)(j + 1) * ns * NX, b, dmap, yd, yq);
+                save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i) + (long long)pse * ns * NX, b, dmap, yd, yq);
         }
     }
     // ---- results.  xs(k): end state component k (compile-time k)
@@ -825,6 +996,14 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
         grid = dim3((unsigned)((nthreads + bs - 1) / bs), 1, 1);
     else
         grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.In, (unsigned)L.R);
+    if (L.sv_n) {   // saveat samples inside pieces: the dense-output instantiation, for the models that carry one
+        if constexpr (SaveAtTraits<Mdl>::ON && METHOD != 1) {
+            shoot_kernel<Mdl, G, METHOD, false, 1, (G > 0), true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            return (int)cudaGetLastError();
+        } else {
+            return -1000;
+        }
+    }
     if constexpr (G > 0) {
         if (o.tsens) {
             if constexpr (METHOD != 2) {

@@ -99,7 +99,7 @@ class MultipleShootingLayer:
             o += nu + npar + nc
         # offsets = cumsum(lastindex(us[i])) of the *unmerged* pieces (:148)
         offsets = np.cumsum([len(_flatten_chunks(st[k]["tspans"])) + 1 for k in keys[:-1]]).astype(np.int64)
-        traj = Trajectory(st[keys[0]]["symcache"], u, np.asarray(ps[keys[0]]["p"], float), self._times(st),
+        traj = Trajectory(st[keys[0]]["symcache"], u, np.asarray(ps[keys[0]]["p"], float), nat.sample_times(),
                           shooting, offsets)
         return traj, st
 
@@ -109,6 +109,20 @@ class MultipleShootingLayer:
         ComponentArray order.  Returns a dict of (B, n) arrays."""
         nat = self._native(st, ps_like)
         return nat.eval_host(ps_batch, want, objective_row, fim_init)
+
+
+def sample_pieces(layer, sts):
+    """Per interval: the control piece (0-based) every sample of the MERGED trajectory belongs to -- the start sample and
+    the samples of piece 0 carry piece 0's controls, saveat samples inside a piece that piece's (single_shooting.jl:456;
+    `saveat` in problem.kwargs, lib/CorleoneOED/src/oed.jl:106-113); the end sample of all but the last interval is dropped."""
+    saveat = layer.problem.kwargs.get("saveat") or []
+    out = []
+    for i, sti in enumerate(sts):
+        pieces = [0]
+        for j, (a, bnd) in enumerate(_flatten_chunks(sti["tspans"])):
+            pieces += [j] * (1 + sum(1 for s in saveat if a < s < bnd))
+        out.append(np.asarray(pieces if i == len(sts) - 1 else pieces[:-1], dtype=np.int64))
+    return out
 
 
 def trajectory_jacobian(shooting, st, ps_like, result, b: int = 0) -> np.ndarray:
@@ -131,26 +145,26 @@ def trajectory_jacobian(shooting, st, ps_like, result, b: int = 0) -> np.ndarray
     J = np.zeros((nrow, nat.n_samples, nat.nvars))
     so = toff = soff = 0
     qacc = np.zeros((len(quad), nat.nvars))          # d(running quadrature sum)/d(variables of earlier intervals)
+    pieces = sample_pieces(layer, sts)
     for i in range(I):
         ns = int(blocks[i + 1] - blocks[i])
         grid = np.asarray(_flatten_chunks(sts[i]["index_grid"]), dtype=np.int64)
         nact = len(sts[i]["_control_indices"])
         grid = grid.reshape(nact, -1) if nact else np.zeros((0, len(_flatten_chunks(sts[i]["tspans"]))), dtype=np.int64)
-        M = grid.shape[1] if nact else len(_flatten_chunks(sts[i]["tspans"]))
-        nsmp = M + (1 if i == I - 1 else 0)
+        nsmp = len(pieces[i])
         c0 = blocks[i] + len(pss[i]["u0"]) + len(pss[i]["p"])
         blk = ts[toff:toff + nsmp * ns * nx].reshape(nsmp, ns, nx)
         for j in range(nsmp):
             J[:nx, so + j, blocks[i]:blocks[i + 1]] = blk[j].T
             for qi, q in enumerate(quad):
                 J[q, so + j, :] += qacc[qi]
-            piece = max(j - 1, 0)
+            piece = int(pieces[i][j])
             for r in range(nact):
                 J[nx + r, so + j, c0 + grid[r, piece] - 1] = 1.0
         send = se[soff:soff + nx * ns].reshape(ns, nx)
         for qi, q in enumerate(quad):
             qacc[qi, blocks[i]:blocks[i + 1]] += send[:, q]
-        so += M
+        so += nsmp - (1 if i == I - 1 else 0)
         toff += nsmp * ns * nx
         soff += nx * ns
     return J

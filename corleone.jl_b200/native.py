@@ -25,7 +25,7 @@ EXPORTS = (
     "cb200_last_kernel_ms", "cb200_kernel_ms_history", "cb200_launch_count", "cb200_probe_fp64_tflops",
     "cb200_probe_fp64_mma_tflops", "cb200_forward_init", "cb200_grad_structure", "cb200_set_interval_range",
     "cb200_resident", "cb200_abi_layout", "cb200_comm_unique_id", "cb200_comm_init", "cb200_comm_init_host",
-    "cb200_comm_destroy", "cb200_comm_query", "cb200_comm_gathered",
+    "cb200_comm_destroy", "cb200_comm_query", "cb200_comm_gathered", "cb200_sample_times",
 )
 
 _dp = C.POINTER(C.c_double)
@@ -46,6 +46,7 @@ class Desc(C.Structure):
         ("shooting_indices", _i64p), ("model_data", _dp), ("model_data_len", C.c_int64),
         ("fim_base_nx", C.c_int32), ("n_observed", C.c_int32), ("n_observation_rows", _i32p),
         ("observation_grid", _i64p), ("abstol", C.c_double), ("reltol", C.c_double),
+        ("saveat", _dp), ("n_saveat", C.c_int32), ("reserved_desc", C.c_int32),
     ]
 
 
@@ -119,6 +120,7 @@ def lib():
         L.cb200_comm_destroy.argtypes = [C.c_void_p]
         L.cb200_comm_query.argtypes = [C.c_void_p, C.POINTER(CommInfo)]
         L.cb200_comm_gathered.argtypes = [C.c_void_p, C.POINTER(C.c_void_p), _i64p]
+        L.cb200_sample_times.argtypes = [C.c_void_p, _dp]
         _lib = L
     return _lib
 
@@ -137,10 +139,11 @@ class NativeLayer:
 
     def __init__(self, *, model_id, method, steps_per_piece, nx, np_all, u0, tunable_p, control_indices,
                  quadrature_indices, intervals, device=0, fim_offset=0, fim_n=0, model_data=None, fim_mode=0,
-                 fim_base_nx=0, n_observed=0, observation_rows=None, abstol=1e-6, reltol=1e-3):
+                 fim_base_nx=0, n_observed=0, observation_rows=None, abstol=1e-6, reltol=1e-3, saveat=None):
         """intervals: list of dicts with tspans [(t0,t1)...], index_grid (n_controls x M int64 1-based),
         n_u0, n_c, is_shooting, sorting, constants, shooting_indices (all 1-based as the reference).
-        observation_rows: per interval an (rows x n_observed) int array = WeightedObservation.grid (fim_mode 2, 3)."""
+        observation_rows: per interval an (rows x n_observed) int array = WeightedObservation.grid (fim_mode 2, 3).
+        saveat: problem.kwargs saveat (sorted times) or None."""
         L = lib()
         nact = len(control_indices)
         keep = {}
@@ -178,6 +181,9 @@ class NativeLayer:
         if model_data is not None:
             put("model_data", model_data, np.float64, _dp)
             d.model_data_len = len(model_data)
+        if saveat is not None and len(saveat):
+            put("saveat", np.asarray(saveat, dtype=np.float64), np.float64, _dp)
+            d.n_saveat = len(saveat)
         if observation_rows is not None:
             rows = [np.asarray(r, dtype=np.int64).reshape(-1, n_observed) for r in observation_rows]
             put("n_observation_rows", [len(r) for r in rows], np.int32, _i32p)
@@ -195,6 +201,12 @@ class NativeLayer:
         self.fim_offset = fim_offset
         self.fim_mode = fim_mode
         self.device = device
+
+    def sample_times(self) -> np.ndarray:
+        """times of the merged trajectory's samples (piece starts / saveat times / piece ends)"""
+        t = np.empty(self.n_samples)
+        _check(lib().cb200_sample_times(self._h, t.ctypes.data_as(_dp)), "cb200_sample_times")
+        return t
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:

@@ -7,16 +7,14 @@ pair is a compiled-in model of libcorleone_b200.so (csrc/models.cuh `OedAug`):
     OEDLayer{false}, measurements          -> "<base>_oed"      [x; G; F_triu],            p = [base p; w]
     OEDLayer{false}, no measurements       -> "<base>_oed_cu"   [x; G; F_triu],            p = base p
     OEDLayer{false}, measurements, FIXED   -> "<base>_oed_cf"   [x; G; F_1 triu; F_2 ...], p = [base p; w]
-    OEDLayer{true},  measurements          -> "<base>_oed_ds"   [x; G],                    p = [base p; w]  (*)
+    OEDLayer{true},  measurements          -> "<base>_oed_ds"   [x; G],                    p = base p       (*)
     OEDLayer{true},  no measurements       -> "<base>_oed_du"   [x; G],                    p = base p
 
-(*) Deviation, on purpose.  In the reference the discrete variants do not append the weights to the problem's
-parameters (augmentation.jl:171-203), so the measurement controls are filtered out of the index grid
-(src/single_shooting.jl:301-304) and the samples at the measurement times come from `saveat` (oed.jl:106-113) --
-interpolated inside a solver step.  A fixed-step kernel has no business interpolating: here the weights ARE (inert)
-parameters of the `_ds` model, so the measurement grids cut the pieces and every measurement time is a step end.
-The flat parameter vector is the same (ps.controls holds the weights in both); the saved samples carry the weights as
-additional trailing control rows.
+(*) As in the reference, the discrete variants do not append the weights to the problem's parameters
+(augmentation.jl:171-203): the measurement controls (p index beyond length(p)) are filtered out of the index grid
+(src/single_shooting.jl:301-304), their values stay in ps.controls, and the samples at the measurement times come from
+`saveat` (oed.jl:106-113) -- Tsit5's dense output on the step that contains them (cb200_desc.saveat), not from cutting
+the pieces.
 
 Every evaluation goes through cb200_eval (`CB200_WANT_FIM` / `CB200_WANT_CRIT`); this module only builds tables.
 """
@@ -71,8 +69,14 @@ class OEDLayer:
         samplings = list(range(1, len(measurements) + 1))
         ctrls = list(zip(base.control_indices, base.controls)) + [(p_length + k, m) for k, m in zip(samplings, measurements)]
         self.sampling_indices = [k + len(base.controls) for k in samplings]                # (:93,135)
+        # "Replace the saveat with the sampling times" (:106-113): the measurement grids' points, else the ends of the horizon
+        if self.SAMPLED:
+            saveats = np.unique(np.concatenate([get_timegrid(m) for m in measurements]))
+        else:
+            saveats = np.asarray(prob.tspan, dtype=np.float64)
         newprob = prob.remake(model=model, u0=np.concatenate([prob.u0, np.zeros(nx_aug - bx)]),
-                              p=np.concatenate([prob.p, np.ones(np_aug - p_length)]))
+                              p=np.concatenate([prob.p, np.ones(np_aug - p_length)]),
+                              kwargs=dict(prob.kwargs, saveat=[float(t) for t in saveats]))
         if single:
             lb, ub = (np.concatenate([b, np.zeros(nx_aug - bx)]) for b in base.bounds_ic)  # (:117-122)
             self.layer = SingleShootingLayer(newprob, base.algorithm, controls=ctrls, tunable_ic=list(base.tunable_ic),
@@ -236,13 +240,15 @@ class OEDLayer:
         blocks = nat.block_structure()
         rows = []                                           # (sample, observed k, flat variable of the weight)
         if self.fim_mode != FIM_DISCRETE:
+            from .multiple_shooting import sample_pieces
             sts = [st] if self.single else list(st.values())
             pss = [ps_like] if self.single else list(ps_like.values())
+            pieces = sample_pieces(self._base_layer(), sts)
             s0 = 0
             for i, (sti, psi, grid) in enumerate(zip(sts, pss, first["_fim"]["rows"])):
                 c0 = int(blocks[i]) + len(psi["u0"]) + len(psi["p"])
                 rows += [(s0 + j, k, c0 + int(v) - 1) for j, row in enumerate(grid) for k, v in enumerate(row) if v > 0]
-                s0 += len(_flatten_chunks(sti["tspans"]))
+                s0 += len(pieces[i]) - (1 if i == len(sts) - 1 else 0)
         gi = bx + bx * np.arange(n)                         # state rows of g_k: gi + k
         ntri = n * (n + 1) // 2
         tri = np.array([[max(a, b) * (max(a, b) + 1) // 2 + min(a, b) for b in range(n)] for a in range(n)])

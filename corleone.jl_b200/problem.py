@@ -32,10 +32,10 @@ MODEL_REGISTRY = {
     "doubleosc6": (16, 6, 1),
     "lotka2_oed_cu": (17, 9, 3),
     "lotka2_oed_cf": (18, 12, 5),
-    "lotka2_oed_ds": (19, 6, 5),
+    "lotka2_oed_ds": (19, 6, 3),
     "lotka2_oed_du": (20, 6, 3),
     "lin1d_oed_cf": (21, 3, 2),
-    "lin1d_oed_ds": (22, 2, 2),
+    "lin1d_oed_ds": (22, 2, 1),
     "brysondenham3": (23, 3, 1),
     "catalystmixing2": (24, 2, 1),
     "cushioned3": (25, 3, 2),

@@ -215,6 +215,7 @@ class SingleShootingLayer:
             intervals=[self._interval_desc(s, l, is_shooting) for s, l in zip(interval_sts, interval_lengths)],
             device=self.device, model_data=prob.model_data,
             abstol=float(prob.kwargs.get("abstol", 1e-6)), reltol=float(prob.kwargs.get("reltol", 1e-3)),
+            saveat=prob.kwargs.get("saveat"),
             **(dict(fim_offset=fim["offset"], fim_n=fim["n"], fim_mode=fim["mode"], fim_base_nx=fim["base_nx"],
                     n_observed=fim["n_observed"], observation_rows=fim["rows"]) if isinstance(fim, dict)
                else dict(fim_offset=fim[0], fim_n=fim[1])))
@@ -236,8 +237,7 @@ class SingleShootingLayer:
         nat = self._native(st, ps, shooting_layer)
         vec = np.concatenate([np.asarray(ps["u0"], float), np.asarray(ps["p"], float), np.asarray(ps["controls"], float)])
         r = nat.eval_host(vec[None, :], native.WANT_TRAJ)
-        tsp = _flatten_chunks(st["tspans"])
-        t = np.array([tsp[0][0]] + [b for _, b in tsp])
+        t = nat.sample_times()   # piece starts / saveat times / piece ends (`saveat` in problem.kwargs, oed.jl:106-113)
         u = r["traj"][0].reshape(nat.n_samples, nat.n_row)
         return Trajectory(st["symcache"], u, np.asarray(ps["p"], float), t, {}, np.zeros(0, dtype=np.int64)), st
 

@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define CB200_VERSION 200
+#define CB200_VERSION 201
 
 typedef enum {
     CB200_OK = 0,
@@ -72,7 +72,7 @@ typedef enum {
        observed=u[1:2]; 1-D: params=[1], observed=[u[1]] */
     CB200_MODEL_LOTKA2_OED_CU = 17, /* Continuous, no measurements (:217-220): [x; G; F_triu], F' = (sum_i h_i G)'(sum_i h_i G) */
     CB200_MODEL_LOTKA2_OED_CF = 18, /* ContinuousSampled, fixed (:255-292): [x; G; F_1 triu; F_2 triu], p = (base p; w) */
-    CB200_MODEL_LOTKA2_OED_DS = 19, /* DiscreteSampled (:171-203): [x; G], p = (base p; w); information summed over samples */
+    CB200_MODEL_LOTKA2_OED_DS = 19, /* DiscreteSampled (:171-203): [x; G], p = base p; the measurement weights live in ps.controls only (filtered out of the index grid) and weight the samples at the measurement times (saveat) */
     CB200_MODEL_LOTKA2_OED_DU = 20, /* Discrete, no measurements (:171-203): [x; G], p = base p */
     CB200_MODEL_LIN1D_OED_CF = 21,
     CB200_MODEL_LIN1D_OED_DS = 22,
@@ -159,6 +159,18 @@ typedef struct {
                                            st.active_controls (oed.jl:352-362) and weights F(sample j+1) - F(sample j) */
     double abstol, reltol;              /* CB200_TSIT5_ADAPTIVE: problem.kwargs abstol / reltol (OrdinaryDiffEq defaults
                                            1e-6 / 1e-3); ignored by the fixed-step methods */
+    /* ---- version 201 */
+    const double *saveat;               /* [n_saveat] problem.kwargs saveat, sorted ascending, or NULL.  The discrete OED layers
+                                           with measurements put their measurement times here (lib/CorleoneOED/src/oed.jl:106-113):
+                                           every control piece -- a fresh `solve(...; save_start, save_end = true)`,
+                                           src/single_shooting.jl:443-453 -- additionally saves the state at the saveat times
+                                           STRICTLY inside it, taken from Tsit5's dense output on the step that contains them
+                                           (OrdinaryDiffEq's 4th-order interpolant; steps are NOT cut at these times).  The
+                                           samples of `traj` / `traj_sens` and the rows of observation_grid then run over
+                                           piece starts, saveat times and piece ends in time order (cb200_sample_times).
+                                           Tsit5 methods only (fixed step and adaptive) */
+    int32_t n_saveat;
+    int32_t reserved_desc;
 } cb200_desc;
 
 /* Fisher read-out (lib/CorleoneOED/src/oed.jl:381-461) */
@@ -276,6 +288,10 @@ const char *cb200_last_error(void);
 int cb200_create(const cb200_desc *desc, cb200_handle **out);
 int cb200_destroy(cb200_handle *h);
 int cb200_get_sizes(const cb200_handle *h, cb200_sizes *sizes);
+
+/* times of the n_samples samples of the merged trajectory (`traj`): piece starts / saveat times / piece ends in order, the
+ * duplicated boundary point of all but the last interval dropped (src/multiple_shooting.jl:145-147,178-180) */
+int cb200_sample_times(const cb200_handle *h, double *t /* n_samples */);
 
 /* block offsets of the flat variable vector, I+1 entries, 0-based offsets as get_block_structure returns */
 int cb200_block_structure(const cb200_handle *h, int64_t *blocks);

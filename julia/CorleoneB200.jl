@@ -59,6 +59,9 @@ struct Desc                      # cb200_desc
     observation_grid::Ptr{Int64}
     abstol::Float64
     reltol::Float64
+    saveat::Ptr{Float64}             # problem.kwargs saveat (sorted), or C_NULL  -- version 201
+    n_saveat::Int32
+    reserved_desc::Int32
 end
 
 struct Out                       # cb200_out
@@ -81,6 +84,21 @@ struct Out                       # cb200_out
     grad_compact::Ptr{Float64}
     traj_sens::Ptr{Float64}
     status::Ptr{Int32}
+    defects_gathered::Ptr{Float64}   # version 200: CB200_COMM_GATHER
+    comm_B_total::Int64
+    comm_b0::Int64
+    resident::UInt32                 # want-bits of results that stay on the device (cb200_resident)
+    reserved2::UInt32
+end
+
+struct CommInfo                  # cb200_comm_info
+    nranks::Int32
+    rank::Int32
+    transport::Int32
+    reserved::Int32
+    epoch::Int64
+    max_B_total::Int64
+    error::Int64
 end
 
 struct Sizes                     # cb200_sizes
@@ -97,6 +115,30 @@ end
 
 const WANT_XEND, WANT_SENS, WANT_TRAJ, WANT_DEFECTS = 0x001, 0x002, 0x004, 0x008
 const WANT_OBJ, WANT_GRAD, WANT_FIM, WANT_JAC, WANT_CRIT = 0x010, 0x020, 0x040, 0x080, 0x100
+const WANT_GRAD_COMPACT, WANT_TRAJ_SENS = 0x200, 0x400
+const MEM_DEVICE, PS_SOA, OUT_SOA, COMM_REDUCE, COMM_GATHER = 0x1, 0x2, 0x4, 0x8, 0x10
+const COMM_ID_BYTES = 128
+
+"""
+Layout self-check: the structs above restate include/corleone_b200.h by hand; the library reports sizeof and the offsets
+of the trailing fields of each (cb200_abi_layout) and a drift stops here instead of corrupting memory.
+"""
+function check_abi()
+    layout(which) = (v = zeros(Int64, 16); n = ccall((:cb200_abi_layout, LIB), Cint, (Int32, Ptr{Int64}, Int32), which, v, 16); v[1:n])
+    want = (
+        (0, Desc, (:u0, :model_data_len, :observation_grid, :reltol, :saveat, :n_saveat)),
+        (1, Out, (:objective_row, :jac_vals, :status, :defects_gathered, :comm_b0, :resident)),
+        (2, Sizes, (:n_traj_sens,)),
+        (3, CommInfo, (:epoch, :error)),
+    )
+    for (which, T, fields) in want
+        mine = vcat(sizeof(T), [fieldoffset(T, findfirst(==(f), fieldnames(T))) for f in fields])
+        theirs = layout(which)
+        mine == theirs || error("CorleoneB200: struct $(T) does not match libcorleone_b200 (header version " *
+                                "$(ccall((:cb200_version, LIB), Cint, ()))): $mine vs $theirs")
+    end
+    return true
+end
 
 const MODELS = Dict(:lotka3 => 0, :lqr => 1, :lotka2 => 2, :lotka2_oed => 3, :lin1d => 4, :lin1d_oed => 5,
                     :dense20 => 6, :egerstedt => 7, :vdp3 => 8, :cartpole5 => 9, :rocket3 => 10, :quadrotor7 => 11, :threetank4 => 12,
@@ -130,12 +172,13 @@ mutable struct EnsembleB200 <: SciMLBase.EnsembleAlgorithm
     handle::Ptr{Cvoid}
     sizes::Sizes
     nx::Int
+    abi_checked::Bool
 end
 function EnsembleB200(; model::Symbol, steps_per_piece = 1, method = :tsit5, device = 0,
         model_data = Float64[], fim = (0, 0), fim_mode = 0, fim_base_nx = 0, n_observed = 0)
     e = EnsembleB200(model, steps_per_piece, method, device, collect(Float64, model_data), fim, fim_mode,
         fim_base_nx, n_observed, C_NULL,
-        Sizes(0, 0, 0, 0, 0, 0, 0, 0, 0), 0)
+        Sizes(0, 0, 0, 0, 0, 0, 0, 0, 0), 0, false)
     finalizer(e) do x
         x.handle == C_NULL || ccall((:cb200_destroy, LIB), Cint, (Ptr{Cvoid},), x.handle)
     end
@@ -189,8 +232,11 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
         push!(n_obs_rows, length(sti.observation_grid.grid))
         foreach(row -> append!(obs_grid, row), sti.observation_grid.grid)
     end
+    # problem.kwargs saveat (the discrete OED layers put their measurement times there, lib/CorleoneOED/src/oed.jl:106-113)
+    saveat = haskey(prob.kwargs, :saveat) ? sort!(collect(Float64, prob.kwargs[:saveat])) : Float64[]
+    e.abi_checked || (check_abi(); e.abi_checked = true)
     h = Ref{Ptr{Cvoid}}(C_NULL)
-    GC.@preserve u0 tunable_p cidx quad n_pieces tsp grid n_u0 n_c is_sh sorting ncon cons nsi sidx md n_obs_rows obs_grid begin
+    GC.@preserve u0 tunable_p cidx quad n_pieces tsp grid n_u0 n_c is_sh sorting ncon cons nsi sidx md n_obs_rows obs_grid saveat begin
         d = Desc(sizeof(Desc), MODELS[e.model], e.method === :tsit5 ? 0 : (e.method === :rk4 ? 1 : 2), e.steps_per_piece, nx, np_all,
             length(cidx), length(tunable_p), I, length(quad), e.device, e.fim[1], e.fim[2], e.fim_mode,
             pointer(u0), pointer(tunable_p), pointer(cidx), pointer(quad), pointer(n_pieces), pointer(tsp),
@@ -199,7 +245,8 @@ function handle!(e::EnsembleB200, shooting::MultipleShootingLayer, ps, st::Named
             length(md), e.fim_base_nx, e.n_observed,
             isempty(n_obs_rows) ? Ptr{Int32}(C_NULL) : pointer(n_obs_rows),
             isempty(obs_grid) ? Ptr{Int64}(C_NULL) : pointer(obs_grid),
-            Float64(get(prob.kwargs, :abstol, 1.0e-6)), Float64(get(prob.kwargs, :reltol, 1.0e-3)))
+            Float64(get(prob.kwargs, :abstol, 1.0e-6)), Float64(get(prob.kwargs, :reltol, 1.0e-3)),
+            isempty(saveat) ? Ptr{Float64}(C_NULL) : pointer(saveat), length(saveat), 0)
         check(ccall((:cb200_create, LIB), Cint, (Ref{Desc}, Ref{Ptr{Cvoid}}), d, h), "cb200_create")
     end
     e.handle = h[]
@@ -241,7 +288,8 @@ function evaluate(e::EnsembleB200, P::Matrix{Float64}; want::Integer, objective_
     GC.@preserve P xend sens traj dk ds obj grad fim fsum fim_init jac crit status begin
         o = Out(ptr(xend), ptr(sens), ptr(traj), ptr(dk), ptr(ds), ptr(obj), ptr(grad), ptr(fim),
             (want & WANT_FIM) != 0 ? pointer(fsum) : Ptr{Float64}(C_NULL), C_NULL, C_NULL,
-            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), pointer(status))
+            fim_init === nothing ? Ptr{Float64}(C_NULL) : pointer(fim_init), objective_row, 0, ptr(jac), ptr(crit), Ptr{Float64}(C_NULL), Ptr{Float64}(C_NULL), pointer(status),
+            Ptr{Float64}(C_NULL), 0, 0, UInt32(0), UInt32(0))
         check(ccall((:cb200_eval, LIB), Cint,
                 (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, UInt32, UInt32, Ref{Out}),
                 e.handle, P, B, size(P, 1), want, 0, o), "cb200_eval")
@@ -260,13 +308,9 @@ function (shooting::MultipleShootingLayer{L, I, EnsembleB200})(u0, ps, st::Named
     s = e.sizes
     U = reshape(r.traj, Int(s.n_row), Int(s.n_samples))
     u = [U[:, k] for k in axes(U, 2)]
-    # time points: piece boundaries, duplicate interval boundaries dropped (:145-147)
-    t = Float64[]
-    for (i, f) in enumerate(fields)
-        ts = flat_tspans(getproperty(st, f).tspans)
-        ti = vcat(first(first(ts)), last.(ts))
-        append!(t, i == length(fields) ? ti : ti[1:(end - 1)])
-    end
+    # time points: piece boundaries and saveat times, duplicate interval boundaries dropped (:145-147)
+    t = Vector{Float64}(undef, Int(s.n_samples))
+    check(ccall((:cb200_sample_times, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}), e.handle, t), "cb200_sample_times")
     # split the stage-ordered defect vector into the (u0, p, controls) NamedTuple per stage (:149-169)
     nx = Corleone.statelength(getproperty(st, fields[1]).initial_condition)
     d, o = vec(r.defects_stage), 0
@@ -313,6 +357,52 @@ function b200_cons_j(e::EnsembleB200)
         end
         return J
     end
+end
+
+# ---------------------------------------------------------------- multi-GPU data plane (cb200_comm_*)
+# One Julia process (or task) per GPU; replaces mythreadmap(::EnsembleDistributed) = pmap over intervals (src/Corleone.jl:24).
+# Rank 0 creates the id and hands it to the others (Distributed.jl `remotecall_fetch`, MPI.bcast, ...); after comm_init!
+# an evaluation with COMM_REDUCE / COMM_GATHER finishes with the all-reduced sums and the all-gathered defects, written by
+# the evaluation's own kernels over NVLink -- no collective call on the host.
+function comm_unique_id()
+    id = zeros(UInt8, COMM_ID_BYTES)
+    check(ccall((:cb200_comm_unique_id, LIB), Cint, (Ptr{UInt8},), id), "cb200_comm_unique_id")
+    return id
+end
+comm_init!(e::EnsembleB200, nranks::Integer, rank::Integer, id::Vector{UInt8}; max_B_total::Integer = 0) =
+    check(ccall((:cb200_comm_init, LIB), Cint, (Ptr{Cvoid}, Int32, Int32, Ptr{UInt8}, Int64), e.handle, nranks, rank, id,
+            max_B_total), "cb200_comm_init")
+comm_destroy!(e::EnsembleB200) = check(ccall((:cb200_comm_destroy, LIB), Cint, (Ptr{Cvoid},), e.handle), "cb200_comm_destroy")
+function comm_info(e::EnsembleB200)
+    r = Ref(CommInfo(0, 0, 0, 0, 0, 0, 0))
+    check(ccall((:cb200_comm_query, LIB), Cint, (Ptr{Cvoid}, Ref{CommInfo}), e.handle, r), "cb200_comm_query")
+    return r[]
+end
+
+"""
+    evaluate_sharded(e, P, b0, B_total; objective_row)
+
+This rank's shard `P` (`nvars x B`, global candidates `b0 + 1 : b0 + B` of `B_total`) of a batch-sharded evaluation:
+returns the objective and gradient sums over ALL ranks' candidates (bit-identical on every rank) and the shooting
+constraints of all `B_total` candidates (`n_defects x B_total`).  Collective: every rank calls it.
+"""
+function evaluate_sharded(e::EnsembleB200, P::Matrix{Float64}, b0::Integer, B_total::Integer; objective_row::Integer = 1)
+    s = e.sizes
+    B = size(P, 2)
+    dk = Matrix{Float64}(undef, s.n_defects, B)
+    gathered = Matrix{Float64}(undef, s.n_defects, B_total)
+    obj = Matrix{Float64}(undef, 1, B)
+    osum = zeros(1)
+    gsum = zeros(s.nvars)
+    want = WANT_DEFECTS | WANT_OBJ | WANT_GRAD
+    N = Ptr{Float64}(C_NULL)
+    GC.@preserve P dk gathered obj osum gsum begin
+        o = Out(N, N, N, pointer(dk), N, pointer(obj), N, N, N, pointer(osum), pointer(gsum), N, objective_row, 0, N, N, N, N,
+            Ptr{Int32}(C_NULL), pointer(gathered), B_total, b0, UInt32(0), UInt32(0))
+        check(ccall((:cb200_eval, LIB), Cint, (Ptr{Cvoid}, Ptr{Float64}, Int64, Int64, UInt32, UInt32, Ref{Out}),
+                e.handle, P, B, size(P, 1), want, COMM_REDUCE | COMM_GATHER, o), "cb200_eval")
+    end
+    return (; objective = obj, objective_sum = osum[1], grad_sum = gsum, defects_kind = dk, defects_gathered = gathered)
 end
 
 end # module

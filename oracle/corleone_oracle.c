@@ -663,7 +663,46 @@ static double rms_state(const double *v, int n)
     for (int c = 0; c < n; c++) s += v[c] * v[c];
     return sqrt(s / (double)n);
 }
-static void integrate_piece_adaptive(const model_ctx *m, int nx, dual *x, const dual *p, double t0, double t1)
+/* Tsit5's continuous extension (Tsitouras 2011; OrdinaryDiffEq's interpolant for Tsit5, used by `saveat`):
+ *   y(t + theta dt) = y + dt sum_i b_i(theta) k_i,  b_1 = theta (r11 + theta (r12 + theta (r13 + theta r14))),
+ *   b_i = theta^2 (ri2 + theta (ri3 + theta ri4)), i = 2..7.  b_i(1) = a_7i and the order conditions up to 4 hold for every
+ *   theta (tests/test_saveat_host.py). */
+static const double TS_R[7][4] = {{1.0, -2.763706197274826, 2.9132554618219126, -1.0530884977290216},
+                                  {0.0, 0.13169999999999998, -0.2234, 0.1017},
+                                  {0.0, 3.9302962368947516, -5.941033872131505, 2.490627285651253},
+                                  {0.0, -12.411077166933676, 30.33818863028232, -16.548102889244902},
+                                  {0.0, 37.50931341651104, -88.1789048947664, 47.37952196281928},
+                                  {0.0, -27.896526289197286, 65.09189467479366, -34.87065786149661},
+                                  {0.0, 1.5, -4.0, 2.5}};
+void co_tsit5_interp_weights(double th, double *bw)
+{
+    bw[0] = th * (TS_R[0][0] + th * (TS_R[0][1] + th * (TS_R[0][2] + th * TS_R[0][3])));
+    for (int i = 1; i < 7; i++) bw[i] = th * th * (TS_R[i][1] + th * (TS_R[i][2] + th * TS_R[i][3]));
+}
+/* pending saveat times of one piece: sv[0..n), results into out[m * nx + c]; `done` counts the emitted ones */
+typedef struct {
+    int n, done;
+    const double *t;
+    dual *out;
+} sv_state;
+/* samples of the pending times <= tnew from the step (tprev, dt) that starts at y0 with stage derivatives k[7] */
+static void sv_emit(sv_state *sv, int nx, double tprev, double dt, double tnew, const dual *y0, dual (*k)[CO_MAX_NX])
+{
+    while (sv && sv->done < sv->n && sv->t[sv->done] <= tnew) {
+        double bw[7];
+        co_tsit5_interp_weights((sv->t[sv->done] - tprev) / dt, bw);
+        for (int c = 0; c < nx; c++) {
+            dual acc = dscale(k[0][c], bw[0]);
+            for (int j = 1; j < 7; j++) daxpy(&acc, bw[j], &k[j][c]);
+            dual z = y0[c];
+            daxpy(&z, dt, &acc);
+            sv->out[(size_t)sv->done * nx + c] = z;
+        }
+        sv->done++;
+    }
+}
+
+static void integrate_piece_adaptive(const model_ctx *m, int nx, dual *x, const dual *p, double t0, double t1, sv_state *sv)
 {
     dual k[7][CO_MAX_NX], tmp[CO_MAX_NX], xn[CO_MAX_NX];
     double w[CO_MAX_NX], sk[CO_MAX_NX];
@@ -748,6 +787,7 @@ static void integrate_piece_adaptive(const model_ctx *m, int nx, dual *x, const 
             double tt = t + dt;
             const double big = fabs(t1);
             if (fabs(tt - t1) < 100.0 * (nextafter(big, INFINITY) - big)) tt = t1;
+            sv_emit(sv, nx, t, dt, tt, x, k); /* saveat times inside the accepted step: dense output */
             t = tt;
             for (int c = 0; c < nx; c++) {
                 x[c] = xn[c];
@@ -762,17 +802,18 @@ static void integrate_piece_adaptive(const model_ctx *m, int nx, dual *x, const 
 }
 
 static void integrate_piece(const model_ctx *m, int nx, dual *x, const dual *p, double t0, double t1, int K,
-                            int method)
+                            int method, sv_state *sv)
 {
     if (method == CO_TSIT5_ADAPTIVE) {
-        integrate_piece_adaptive(m, nx, x, p, t0, t1);
+        integrate_piece_adaptive(m, nx, x, p, t0, t1, sv);
         return;
     }
-    dual k[7][CO_MAX_NX], tmp[CO_MAX_NX];
+    dual k[7][CO_MAX_NX], tmp[CO_MAX_NX], x0[CO_MAX_NX];
     double h = (t1 - t0) / (double)K;
     if (method == CO_TSIT5) {
         model_rhs(m, x, p, k[0]);
         for (int s = 0; s < K; s++) {
+            for (int c = 0; c < nx; c++) x0[c] = x[c];
             for (int st = 1; st < 7; st++) {
                 for (int c = 0; c < nx; c++) {
                     dual acc = x[c];
@@ -783,6 +824,8 @@ static void integrate_piece(const model_ctx *m, int nx, dual *x, const dual *p, 
                     for (int c = 0; c < nx; c++) x[c] = tmp[c];
                 model_rhs(m, tmp, p, k[st]);
             }
+            /* saveat times inside this step, from its dense output (the steps are not cut at them) */
+            sv_emit(sv, nx, t0 + s * h, h, (s + 1 == K) ? t1 : t0 + (s + 1) * h, x0, k);
             for (int c = 0; c < nx; c++) k[0][c] = k[6][c];
         }
     } else { /* classical RK4 */
@@ -932,6 +975,10 @@ typedef struct {
     int sidx[CO_MAX_NX + CO_MAX_CTRL]; /* shooting_indices, 1-based over [states; controls] */
     int var_off;                       /* offset of the block in the flat ps */
     double *c_init;                    /* default local controls */
+    int NS;                            /* samples after the start sample: M + saveat times strictly inside pieces */
+    int *sv_n;                         /* [M] saveat times strictly inside piece j */
+    int *sv_off;                       /* [M] offset of the piece's times in sv_t */
+    double *sv_t;                      /* those times */
 } interval;
 
 struct co_layer {
@@ -1020,6 +1067,7 @@ co_layer *co_layer_create(const co_problem *P)
         }
     }
     (void)allc;
+    (void)act_u;
 
     /* shooting intervals: sort!(unique!(vcat(tpoints, tspan))) -> consecutive pairs (multiple_shooting.jl:86-90) */
     double *pts = (double *)malloc(sizeof(double) * (size_t)(P->n_shoot + 2));
@@ -1074,16 +1122,37 @@ co_layer *co_layer_create(const co_problem *P)
         }
         sortperm_cat(it->ic_constants, it->n_const, tun, ntun, it->ic_sorting);
         it->n_u0 = ntun;
-        /* local controls (collect_local_controls, local_controls.jl:201-207) */
+        /* local controls (collect_local_controls, local_controls.jl:201-207) of EVERY control of the layer: controls that
+         * do not act on the dynamics are filtered out of the index grid only (single_shooting.jl:301-304), ps.controls
+         * keeps their values -- the measurement weights of the discrete OED layers.  The index grid of the active ones
+         * addresses this vector by the offsets of the FILTERED list, as the reference does. */
         it->n_c = 0;
-        for (int r = 0; r < L->nact; r++)
-            for (int k = 0; k < act_nt[r]; k++)
-                if (it->t0 <= act_t[r][k] && act_t[r][k] < it->t1) it->n_c++;
+        for (int r = 0; r < P->ncontrols; r++)
+            for (int k = 0; k < P->ctrl_nt[r]; k++)
+                if (it->t0 <= P->ctrl_t[r][k] && P->ctrl_t[r][k] < it->t1) it->n_c++;
         it->c_init = (double *)malloc(sizeof(double) * (size_t)(it->n_c > 0 ? it->n_c : 1));
         int q = 0;
-        for (int r = 0; r < L->nact; r++)
-            for (int k = 0; k < act_nt[r]; k++)
-                if (it->t0 <= act_t[r][k] && act_t[r][k] < it->t1) it->c_init[q++] = act_u[r] ? act_u[r][k] : 0.0;
+        for (int r = 0; r < P->ncontrols; r++)
+            for (int k = 0; k < P->ctrl_nt[r]; k++)
+                if (it->t0 <= P->ctrl_t[r][k] && P->ctrl_t[r][k] < it->t1)
+                    it->c_init[q++] = (P->ctrl_u && P->ctrl_u[r]) ? P->ctrl_u[r][k] : 0.0;
+        /* saveat (problem.kwargs; lib/CorleoneOED/src/oed.jl:106-113): every piece is a fresh solve that also saves at
+         * the saveat times strictly inside its span (OrdinaryDiffEq keeps t0 < t < tf; the ends follow save_start /
+         * save_end) */
+        it->sv_n = (int *)calloc((size_t)it->M, sizeof(int));
+        it->sv_off = (int *)calloc((size_t)it->M, sizeof(int));
+        it->sv_t = (double *)malloc(sizeof(double) * (size_t)(P->n_saveat > 0 ? P->n_saveat : 1));
+        it->NS = 0;
+        int nsv = 0;
+        for (int j = 0; j < it->M; j++) {
+            it->sv_off[j] = nsv;
+            for (int k = 0; k < P->n_saveat; k++)
+                if (P->saveat[k] > it->grid[j] && P->saveat[k] < it->grid[j + 1]) {
+                    it->sv_t[nsv++] = P->saveat[k];
+                    it->sv_n[j]++;
+                }
+            it->NS += it->sv_n[j] + 1;
+        }
         /* shooting_indices (:333-340): non-quadrature states; controls with no grid point at the interval start */
         it->n_sidx = 0;
         if (it->shooting) {
@@ -1103,7 +1172,7 @@ co_layer *co_layer_create(const co_problem *P)
     L->ndef = 0;
     L->nsamples = 1;
     for (int i = 0; i < L->I; i++) {
-        L->nsamples += L->iv[i].M;
+        L->nsamples += L->iv[i].NS;
         if (i > 0) L->ndef += L->iv[i].n_sidx + L->ntp;
     }
     free(pts);
@@ -1117,6 +1186,9 @@ void co_layer_destroy(co_layer *L)
         free(L->iv[i].grid);
         free(L->iv[i].idx);
         free(L->iv[i].c_init);
+        free(L->iv[i].sv_n);
+        free(L->iv[i].sv_off);
+        free(L->iv[i].sv_t);
     }
     free(L->iv);
     free(L);
@@ -1176,7 +1248,7 @@ void co_default_ps(const co_layer *L, double *ps)
 }
 
 /* one interval: (layer::SingleShootingLayer)(::Any, ps, st, shooting_layer) (single_shooting.jl:357-374)
- * followed by _sequential_solve (:421-471).  samples: (M+1) x nrow, sample-major. */
+ * followed by _sequential_solve (:421-471).  samples: (NS+1) x nrow, sample-major (NS = M without saveat). */
 static void solve_interval(const co_layer *L, int i, const dual *vars, int method, int K, dual *samples,
                            double *tsamp, int shooting_flag)
 {
@@ -1193,6 +1265,7 @@ static void solve_interval(const co_layer *L, int i, const dual *vars, int metho
         for (int k = 0; k < it->n_u0; k++) cat[it->n_const + k] = v_u0[k];
         for (int k = 0; k < nx; k++) x[k] = cat[it->ic_sorting[k] - 1];
     }
+    int ns = 0; /* samples written after the start sample */
     for (int j = 0; j < it->M; j++) {
         for (int r = 0; r < L->nact; r++) ctrl[r] = v_c[it->idx[r + (size_t)L->nact * j] - 1]; /* :439 */
         for (int q = 0; q < L->np_all; q++)
@@ -1202,11 +1275,25 @@ static void solve_interval(const co_layer *L, int i, const dual *vars, int metho
             for (int r = 0; r < L->nact; r++) samples[nx + r] = ctrl[r];
             if (tsamp) tsamp[0] = it->grid[0];
         }
-        integrate_piece(&L->m, nx, x, pfull, it->grid[j], it->grid[j + 1], K, method);
-        dual *s = samples + (size_t)(j + 1) * nrow; /* save_end; u = vcat(x, p_j) (:456) */
+        sv_state sv;
+        dual *svbuf = it->sv_n[j] > 0 ? (dual *)malloc(sizeof(dual) * (size_t)it->sv_n[j] * (size_t)nx) : NULL;
+        sv.n = it->sv_n[j];
+        sv.done = 0;
+        sv.t = it->sv_t + it->sv_off[j];
+        sv.out = svbuf;
+        integrate_piece(&L->m, nx, x, pfull, it->grid[j], it->grid[j + 1], K, method, sv.n > 0 ? &sv : NULL);
+        for (int q = 0; q < it->sv_n[j]; q++) { /* saveat samples of the piece: u = vcat(x(t), p_j) */
+            dual *s = samples + (size_t)(ns + 1 + q) * nrow;
+            for (int k = 0; k < nx; k++) s[k] = svbuf[(size_t)q * nx + k];
+            for (int r = 0; r < L->nact; r++) s[nx + r] = ctrl[r];
+            if (tsamp) tsamp[ns + 1 + q] = sv.t[q];
+        }
+        free(svbuf);
+        ns += it->sv_n[j] + 1;
+        dual *s = samples + (size_t)ns * nrow; /* save_end; u = vcat(x, p_j) (:456) */
         for (int k = 0; k < nx; k++) s[k] = x[k];
         for (int r = 0; r < L->nact; r++) s[nx + r] = ctrl[r];
-        if (tsamp) tsamp[j + 1] = it->grid[j + 1];
+        if (tsamp) tsamp[ns] = it->grid[j + 1];
     }
 }
 
@@ -1219,7 +1306,7 @@ int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int 
     const int nx = L->nx, nrow = nx + L->nact, I = L->I;
     int maxM = 0, maxv = 0;
     for (int i = 0; i < I; i++) {
-        if (L->iv[i].M > maxM) maxM = L->iv[i].M;
+        if (L->iv[i].NS > maxM) maxM = L->iv[i].NS;
         int nv = L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
         if (nv > maxv) maxv = nv;
     }
@@ -1234,18 +1321,18 @@ int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int 
             vars[k].v = ps[it->var_off + k];
             for (int d = 0; d < nd; d++) vars[k].d[d] = dps[(size_t)d * L->nvars + it->var_off + k];
         }
-        S[i] = (dual *)malloc(sizeof(dual) * (size_t)((it->M + 1) * nrow));
+        S[i] = (dual *)malloc(sizeof(dual) * (size_t)((it->NS + 1) * nrow));
         solve_interval(L, i, vars, method, K, S[i], ts, it->shooting);
         if (t_out) /* drop the duplicated boundary point of all but the last interval (:145-147) */
-            for (int j = 0; j < it->M + (i == I - 1); j++) t_out[so + j] = ts[j];
+            for (int j = 0; j < it->NS + (i == I - 1); j++) t_out[so + j] = ts[j];
         if (xend)
             for (int k = 0; k < nx; k++) {
-                xend[k + nx * i] = S[i][(size_t)it->M * nrow + k].v;
+                xend[k + nx * i] = S[i][(size_t)it->NS * nrow + k].v;
                 if (dxend)
                     for (int d = 0; d < nd; d++)
-                        dxend[k + nx * i + (size_t)d * nx * I] = S[i][(size_t)it->M * nrow + k].d[d];
+                        dxend[k + nx * i + (size_t)d * nx * I] = S[i][(size_t)it->NS * nrow + k].d[d];
             }
-        so += it->M;
+        so += it->NS;
     }
     /* shooting defects (multiple_shooting.jl:150-163) */
     if (defk || defs) {
@@ -1258,7 +1345,7 @@ int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int 
         int ou = 0, op = n_u, oc = n_u + n_p, os = 0;
         for (int i = 1; i < I; i++) {
             const interval *prev = &L->iv[i - 1], *it = &L->iv[i];
-            const dual *lastp = S[i - 1] + (size_t)prev->M * nrow, *first = S[i];
+            const dual *lastp = S[i - 1] + (size_t)prev->NS * nrow, *first = S[i];
             /* u0 matchings, then p, then controls within the stage */
             for (int pass = 0; pass < 3; pass++) {
                 if (pass == 1) {
@@ -1299,20 +1386,20 @@ int co_eval(const co_layer *L, const double *ps, const double *dps, int nd, int 
         const interval *prev = &L->iv[i - 1], *it = &L->iv[i];
         for (int q = 0; q < L->nquad; q++) {
             int r = L->quad[q] - 1;
-            dual qp = S[i - 1][(size_t)prev->M * nrow + r];
-            for (int j = 0; j <= it->M; j++) S[i][(size_t)j * nrow + r] = dadd(S[i][(size_t)j * nrow + r], qp);
+            dual qp = S[i - 1][(size_t)prev->NS * nrow + r];
+            for (int j = 0; j <= it->NS; j++) S[i][(size_t)j * nrow + r] = dadd(S[i][(size_t)j * nrow + r], qp);
         }
     }
     so = 0;
     for (int i = 0; i < I; i++) {
         const interval *it = &L->iv[i];
         if (u_out)
-            for (int j = 0; j < it->M + (i == I - 1); j++)
+            for (int j = 0; j < it->NS + (i == I - 1); j++)
                 for (int r = 0; r < nrow; r++) u_out[r + (size_t)nrow * (so + j)] = S[i][(size_t)j * nrow + r].v;
-        so += it->M;
+        so += it->NS;
     }
     if (last) {
-        const dual *l = S[I - 1] + (size_t)L->iv[I - 1].M * nrow;
+        const dual *l = S[I - 1] + (size_t)L->iv[I - 1].NS * nrow;
         for (int r = 0; r < nrow; r++) {
             last[r] = l[r].v;
             if (dlast)
@@ -1338,10 +1425,10 @@ int co_eval_traj(const co_layer *L, const double *ps, const double *dps, int nd,
     const int nx = L->nx, nrow = nx + L->nact, I = L->I;
     int maxM = 0, maxv = 0, nsamples = 1;
     for (int i = 0; i < I; i++) {
-        if (L->iv[i].M > maxM) maxM = L->iv[i].M;
+        if (L->iv[i].NS > maxM) maxM = L->iv[i].NS;
         int nv = L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
         if (nv > maxv) maxv = nv;
-        nsamples += L->iv[i].M;
+        nsamples += L->iv[i].NS;
     }
     dual **S = (dual **)malloc(sizeof(dual *) * (size_t)I);
     double *ts = (double *)malloc(sizeof(double) * (size_t)(maxM + 1));
@@ -1353,28 +1440,28 @@ int co_eval_traj(const co_layer *L, const double *ps, const double *dps, int nd,
             vars[k].v = ps[it->var_off + k];
             for (int d = 0; d < nd; d++) vars[k].d[d] = dps[(size_t)d * L->nvars + it->var_off + k];
         }
-        S[i] = (dual *)malloc(sizeof(dual) * (size_t)((it->M + 1) * nrow));
+        S[i] = (dual *)malloc(sizeof(dual) * (size_t)((it->NS + 1) * nrow));
         solve_interval(L, i, vars, method, K, S[i], ts, it->shooting);
     }
     for (int i = 1; i < I; i++) {
         const interval *prev = &L->iv[i - 1], *it = &L->iv[i];
         for (int q = 0; q < L->nquad; q++) {
             int r = L->quad[q] - 1;
-            dual qp = S[i - 1][(size_t)prev->M * nrow + r];
-            for (int j = 0; j <= it->M; j++) S[i][(size_t)j * nrow + r] = dadd(S[i][(size_t)j * nrow + r], qp);
+            dual qp = S[i - 1][(size_t)prev->NS * nrow + r];
+            for (int j = 0; j <= it->NS; j++) S[i][(size_t)j * nrow + r] = dadd(S[i][(size_t)j * nrow + r], qp);
         }
     }
     int so = 0;
     for (int i = 0; i < I; i++) {
         const interval *it = &L->iv[i];
-        for (int j = 0; j < it->M + (i == I - 1); j++)
+        for (int j = 0; j < it->NS + (i == I - 1); j++)
             for (int r = 0; r < nrow; r++) {
                 if (u_out) u_out[r + (size_t)nrow * (so + j)] = S[i][(size_t)j * nrow + r].v;
                 if (du_out)
                     for (int d = 0; d < nd; d++)
                         du_out[r + (size_t)nrow * ((so + j) + (size_t)nsamples * d)] = S[i][(size_t)j * nrow + r].d[d];
             }
-        so += it->M;
+        so += it->NS;
     }
     for (int i = 0; i < I; i++) free(S[i]);
     free(S);
@@ -1401,10 +1488,10 @@ int co_forward_init(const co_layer *L, double *ps, const int *fixed, int nfixed,
         }
         dual *vars = (dual *)malloc(sizeof(dual) * (size_t)(nv > 0 ? nv : 1));
         for (int k = 0; k < nv; k++) vars[k] = dconst(ps[it->var_off + k]);
-        dual *S = (dual *)malloc(sizeof(dual) * (size_t)((it->M + 1) * nrow));
+        dual *S = (dual *)malloc(sizeof(dual) * (size_t)((it->NS + 1) * nrow));
         /* layer(nothing, sps, sst): the shooting flag is NOT passed here, so fixval = problem.u0 (:165) */
         solve_interval(L, i, vars, method, K, S, NULL, 0);
-        for (int r = 0; r < nrow; r++) carry[r] = S[(size_t)it->M * nrow + r].v; /* pred.u[end] */
+        for (int r = 0; r < nrow; r++) carry[r] = S[(size_t)it->NS * nrow + r].v; /* pred.u[end] */
         ncarry = nrow;
         free(S);
         free(vars);
@@ -1435,7 +1522,7 @@ double co_bench_units(const co_layer *L, const double *ps_batch, int64_t B, int6
     const int I = L->I, nx = L->nx, nrow = nx + L->nact;
     int maxM = 0, maxv = 0;
     for (int i = 0; i < I; i++) {
-        if (L->iv[i].M > maxM) maxM = L->iv[i].M;
+        if (L->iv[i].NS > maxM) maxM = L->iv[i].NS;
         int nv = L->iv[i].n_u0 + L->ntp + L->iv[i].n_c;
         if (nv > maxv) maxv = nv;
     }
@@ -1469,7 +1556,7 @@ double co_bench_units(const co_layer *L, const double *ps_batch, int64_t B, int6
                     for (int d = 0; d < nd; d++) vars[k].d[d] = (k == d0 + d) ? 1.0 : 0.0;
                 }
                 solve_interval(L, i, vars, method, K, S, NULL, it->shooting);
-                const dual *e = S + (size_t)it->M * nrow;
+                const dual *e = S + (size_t)it->NS * nrow;
                 for (int k = 0; k < nx; k++) {
                     sum += e[k].v;
                     for (int d = 0; d < nd; d++) sum += e[k].d[d];

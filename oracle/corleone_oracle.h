@@ -108,6 +108,8 @@ typedef struct {
     int n_shoot;                    /* 0 -> single shooting */
     const double *shoot_pts;        /* tpoints of MultipleShootingLayer */
     const double *model_data;       /* CO_DENSE20: W (20x20 row-major) then b (20) */
+    int n_saveat;                   /* problem.kwargs saveat (lib/CorleoneOED/src/oed.jl:106-113): sorted times; every piece */
+    const double *saveat;           /* also saves at those strictly inside it, from Tsit5's dense output */
 } co_problem;
 
 typedef struct co_layer co_layer;
@@ -121,6 +123,9 @@ int co_build_index_grid(int ncontrols, const double *const *t, const int *nt, do
                         int64_t *idx, double *grid, int cap_pieces);
 /* get_subvector_indices (:120-147): writes 1-based (start,stop) pairs, returns chunk count */
 int co_subvector_indices(int M, int L, int *start_stop);
+
+/* Tsit5's interpolation weights b_1..b_7 at theta (OrdinaryDiffEq's dense output for Tsit5) */
+void co_tsit5_interp_weights(double theta, double *bw /* 7 */);
 
 /* ---- layer = SingleShootingLayer or MultipleShootingLayer + its `st` ---- */
 co_layer *co_layer_create(const co_problem *prob);

@@ -82,6 +82,8 @@ class _Problem(C.Structure):
         ("n_shoot", C.c_int),
         ("shoot_pts", C.POINTER(C.c_double)),
         ("model_data", C.POINTER(C.c_double)),
+        ("n_saveat", C.c_int),
+        ("saveat", C.POINTER(C.c_double)),
     ]
 
 
@@ -176,7 +178,8 @@ class OracleLayer:
     """A SingleShootingLayer (no shooting_points) or MultipleShootingLayer restated on the CPU.
 
     spec keys: model, u0, p0, tspan, controls=[(p_index_1based, t, u_or_None), ...], tunable_ic=[...1-based],
-    quadrature_indices=[...1-based], shooting_points=[...] or None, model_data (dense20: W.ravel() ++ b).
+    quadrature_indices=[...1-based], shooting_points=[...] or None, model_data (dense20: W.ravel() ++ b),
+    saveat=[sorted times] or None (problem.kwargs saveat: samples inside pieces from Tsit5's dense output).
     """
 
     def __init__(self, spec: dict):
@@ -212,7 +215,11 @@ class OracleLayer:
         md = spec.get("model_data")
         mda = None if md is None else np.ascontiguousarray(md, dtype=np.float64)
         P.model_data = _dp(mda) if mda is not None else None
-        self._keep += [u0, p0, cidx, ts, us, nt, tarr, uarr, tic, quad, spa, mda, P]
+        sv = spec.get("saveat")
+        sva = np.ascontiguousarray(sv if sv is not None and len(sv) else [0.0], dtype=np.float64)
+        P.n_saveat = 0 if sv is None else len(sv)
+        P.saveat = _dp(sva)
+        self._keep += [u0, p0, cidx, ts, us, nt, tarr, uarr, tic, quad, spa, mda, sva, P]
         self.h = lib().co_layer_create(C.byref(P))
         L = lib()
         self.nx = P.nx

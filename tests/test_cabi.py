@@ -27,16 +27,16 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(L, n), f"{n} declared in include/corleone_b200.h but not exported"
     assert set(names) == set(native.EXPORTS)
-    assert native.lib().cb200_version() == 200
+    assert native.lib().cb200_version() == 201
 
 
 def test_struct_layouts_match_header():
-    assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8 + 2 * 4 + 2 * 8 + 2 * 8
+    assert ctypes.sizeof(native.Desc) == 14 * 4 + 17 * 8 + 2 * 4 + 2 * 8 + 2 * 8 + 8 + 2 * 4   # ... + saveat, n_saveat, reserved
     assert ctypes.sizeof(native.Out) == 12 * 8 + 8 + 8 + 8 + 8 + 8 + 8 + 3 * 8 + 2 * 4
     assert ctypes.sizeof(native.Sizes) == 9 * 8
     # the library reports sizeof and the offsets of the trailing fields of every struct a binding restates by hand
     # (julia/CorleoneB200.jl asserts the same numbers at load time)
-    for which, T, fields in ((0, native.Desc, ("u0", "model_data_len", "observation_grid", "reltol")),
+    for which, T, fields in ((0, native.Desc, ("u0", "model_data_len", "observation_grid", "reltol", "saveat", "n_saveat")),
                              (1, native.Out, ("objective_row", "jac_vals", "status", "defects_gathered", "comm_b0", "resident")),
                              (2, native.Sizes, ("n_traj_sens",)), (3, native.CommInfo, ("epoch", "error"))):
         assert native.abi_layout(which) == [ctypes.sizeof(T)] + [getattr(T, f).offset for f in fields], which
@@ -117,3 +117,42 @@ def test_plain_c_client(tmp_path):
     res = _build_c_client(tmp_path)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "cabi_lin1d ok" in res.stdout
+
+
+def test_julia_binding_restates_the_header_structs_field_for_field():
+    """julia/CorleoneB200.jl cannot run here (no Julia in the image): at least its hand-written structs must list the
+    header's fields in the header's order with matching widths (it also asserts cb200_abi_layout at run time)."""
+    import re
+    hdr = open(os.path.join(ROOT, "include", "corleone_b200.h")).read()
+    jl = open(os.path.join(ROOT, "julia", "CorleoneB200.jl")).read()
+
+    def c_fields(name):
+        end = re.search(r"\}\s*" + name + r"\s*;", hdr).start()
+        body = hdr[hdr.rfind("typedef struct {", 0, end) + len("typedef struct {"):end]
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        out = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            ptr = "*" in decl
+            typ = decl.replace("const", "").replace("*", " ").split()[0]
+            for nm in decl.replace("*", " ").split(typ, 1)[1].split(","):
+                out.append((nm.strip(), "ptr" if ptr else typ))
+        return out
+
+    def jl_fields(name):
+        body = re.search(r"^struct " + name + r"\b.*?\n(.*?)^end", jl, re.S | re.M).group(1)
+        out = []
+        for line in body.splitlines():
+            m = re.match(r"\s*(\w+)::([\w{}]+)", line)
+            if m:
+                out.append((m.group(1), m.group(2)))
+        return out
+
+    width = {"int32_t": "Int32", "uint32_t": "UInt32", "int64_t": "Int64", "double": "Float64"}
+    for cname, jname in (("cb200_desc", "Desc"), ("cb200_out", "Out"), ("cb200_sizes", "Sizes"), ("cb200_comm_info", "CommInfo")):
+        c, j = c_fields(cname), jl_fields(jname)
+        assert [n for n, _ in c] == [n for n, _ in j], (cname, [n for n, _ in c], [n for n, _ in j])
+        for (n, ct), (_, jt) in zip(c, j):
+            assert jt.startswith("Ptr{") if ct == "ptr" else jt == width[ct], (cname, n, ct, jt)

@@ -134,7 +134,11 @@ def test_adaptive_parity_other_models(name):
         spec, row, scale = P.vdp_spec(5, rng), 3, 0.05
     elif name == "discrete_oed":
         spec = dict(P.lotka_oed_spec(shooting_points=[0.0, 3.0, 6.0, 9.0], fishing=rng.uniform(0, 1, 48)))
-        spec.update(model="lotka2_oed_ds", u0=[0.5, 0.7] + [0.0] * 4)
+        # the discrete layer as the reference builds it (lib/CorleoneOED/src/oed.jl:87-113): [x; G] with the base parameters,
+        # the measurement controls (p index 4, 5: beyond length(p)) stay in ps.controls without cutting the pieces, and
+        # their grid points are saveat times -- sampled from the dense output of the adaptive steps
+        spec.update(model="lotka2_oed_ds", u0=[0.5, 0.7] + [0.0] * 4, p0=[0.0, 1.0, 1.0],
+                    saveat=np.union1d(spec["controls"][1][1], spec["controls"][2][1]))
         spec.pop("fim", None)
         row, scale = 1, 0.02
     else:

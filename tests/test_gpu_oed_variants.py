@@ -64,7 +64,9 @@ CASES = [
 @pytest.mark.parametrize("name,discrete,sampled,shooting,fixed", CASES, ids=[c[0] for c in CASES])
 def test_fisher_information_of_every_variant(name, discrete, sampled, shooting, fixed):
     from oracle import pyoracle as po
-    K = 2
+    # the fixed discrete layer has no control: its horizon is ONE piece and the measurement times are saveat samples inside
+    # it (oed.jl:106-113) -- the fixed step has to resolve 12 time units by itself
+    K = 96 if (fixed and discrete) else 2
     meas = ()
     if sampled:
         meas = measurements()
@@ -147,7 +149,8 @@ def test_discrete_1d_closed_form_on_the_device():
     prim = lambda s: np.exp(-4.0 * s) * (-(s * s) / 4.0 - s / 8.0 - 1.0 / 32.0)
     edges = np.r_[t, 1.0]
     for discrete in (True, False):
-        o = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(4)), discrete,
+        # discrete: one piece, the 99 inner measurement times come from the dense output of its 256 steps
+        o = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(256 if discrete else 4)), discrete,
                           [cb.ControlParameter(t, controls=np.ones(100), bounds=(0.0, 1.0))])
         ps, st = o.setup(None)
         X = np.tile(cb.to_vec(ps), (64, 1))

@@ -64,8 +64,10 @@ def test_weighting_grid_matches_the_oracle_restatement(shooting):
         ig = pyoracle.build_index_grid(grids, *tspan)[0]
         ref = pyoracle.weighting_grid(grids, [2, 3], ig, tspan, shooting is not None)
         assert np.array_equal(sti["observation_grid"], np.asarray(ref, dtype=np.int64))
-        # every row belongs to a saved sample of the interval: one per piece start (+ the final time, single shooting)
-        assert len(ref) == len(tsp) + (1 if shooting is None else 0)
+        # every row belongs to a saved sample of the interval: its start, the measurement times inside its pieces (saveat)
+        # and the piece ends (+ the final time, single shooting): the union of the control and the measurement grids
+        n_inside = sum(1 for a, b in tsp for t in np.union1d(T1, T2) if a < t < b)
+        assert len(ref) == len(tsp) + n_inside + (1 if shooting is None else 0)
     # the final time carries no measurement (t0 <= t < t1, src/local_controls.jl:53-57)
     if shooting is None:
         assert not st["observation_grid"][-1].any()
@@ -98,7 +100,7 @@ def _oracle_spec(o, ps):
     ctr = [(ci, c.t, np.asarray(c.controls, dtype=np.float64) if not callable(c.controls) else None)
            for ci, c in zip(lay.control_indices, lay.controls)]
     return dict(model=o.model, u0=lay.problem.u0, p0=lay.problem.p, tspan=lay.problem.tspan, controls=ctr,
-                tunable_ic=lay.tunable_ic, quadrature_indices=[],
+                tunable_ic=lay.tunable_ic, quadrature_indices=[], saveat=lay.problem.kwargs.get("saveat"),
                 shooting_points=None if o.single else [t[0] for t in o.layer.shooting_intervals])
 
 
@@ -109,12 +111,16 @@ def test_discrete_information_of_the_1d_problem_is_the_closed_form():
     rng = np.random.default_rng(5)
     w = rng.uniform(0, 1, 100)
     prob = cb.ODEProblem("lin1d", [1.0], (0.0, 1.0), [-2.0])
-    o = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(4)), True, [cb.ControlParameter(t, controls=w, bounds=(0.0, 1.0))])
+    # the layer has no control, so the horizon is ONE piece and all 99 inner measurement times are saveat samples from the
+    # dense output of the 256 steps (4th-order interpolant: 3e-15 at this step size, 1e-5 at K = 4)
+    o = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(256)), True, [cb.ControlParameter(t, controls=w, bounds=(0.0, 1.0))])
     ps, st = o.setup(None)
     assert o.FIXED and o.model == "lin1d_oed_ds"
+    assert np.array_equal(o.layer.problem.kwargs["saveat"], t) and np.array_equal(o.layer.problem.p, [-2.0])
     orc = pyoracle.OracleLayer(_oracle_spec(o, ps))
     x = cb.to_vec(ps)
-    r = orc.eval(x, K=4)
+    r = orc.eval(x, K=256)
+    assert np.array_equal(r["t"], np.r_[t, 1.0])
     F = pyoracle.fisher_discrete_sampled(ps["controls"], st["observation_grid"].tolist(), r["u"], 0, 1, 1, 1)
     exact = np.sum((w * t * np.exp(-2.0 * t)) ** 2)
     assert abs(F[0, 0] - exact) <= 1e-12 * exact
@@ -130,22 +136,25 @@ def test_discrete_information_of_the_1d_problem_is_the_closed_form():
     assert abs(F2[0, 0] - exact2) <= 1e-11 * exact2
 
 
-def test_cut_pieces_equal_uncut_pieces_with_proportionally_more_steps():
-    """The documented deviation of the discrete layers: the measurement grids cut the pieces here, where the reference
-    saves inside a piece (`saveat`).  With a constant control, K steps on each of the m sub-pieces are bit-for-bit the
-    mK steps of the uncut piece (k1 re-evaluated at a cut equals the FSAL k7: same state, same parameters)."""
+def test_saveat_samples_on_step_ends_equal_the_cut_pieces():
+    """The discrete layers sample inside a piece (`saveat`, oed.jl:106-113) instead of cutting it.  When the measurement
+    times fall on step ends the dense output at theta = 1 is the step's own result: the samples equal those of a layer
+    whose control grid cuts the pieces there (same steps: k1 re-evaluated at a cut equals the FSAL k7)."""
     prob = cb.ODEProblem("lotka2", [0.5, 0.7], (0.0, 12.0), [0.0, 1.0, 1.0])
-    cg = 1.0 * np.arange(12)
-    fishing = cb.ControlParameter(cg, name="fishing", controls=np.linspace(0.1, 0.9, 12), bounds=(0.0, 1.0))
+    vals = np.linspace(0.1, 0.9, 12)
+    fishing = cb.ControlParameter(1.0 * np.arange(12), name="fishing", controls=vals, bounds=(0.0, 1.0))
+    fine = cb.ControlParameter(0.25 * np.arange(48), name="fishing", controls=np.repeat(vals, 4), bounds=(0.0, 1.0))
     meas = [cb.ControlParameter(0.25 * np.arange(48), controls=np.ones(48), bounds=(0.0, 1.0)) for _ in range(2)]
-    cut = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(2), controls=[(1, fishing)]), True, meas)
-    uncut = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(8), controls=[(1, fishing)]), True)
+    sampled = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(8), controls=[(1, fishing)]), True, meas)
+    cut = oedm.OEDLayer(cb.SingleShootingLayer(prob, cb.Tsit5(2), controls=[(1, fine)]), True)
+    ps_s, st_s = sampled.setup(None)
     ps_c, _ = cut.setup(None)
-    ps_u, _ = uncut.setup(None)
-    a = pyoracle.OracleLayer(_oracle_spec(cut, ps_c)).eval(cb.to_vec(ps_c), K=2)
-    b = pyoracle.OracleLayer(_oracle_spec(uncut, ps_u)).eval(cb.to_vec(ps_u), K=8)
-    assert a["u"].shape[1] == 49 and b["u"].shape[1] == 13
-    assert np.array_equal(a["u"][:6, ::4], b["u"][:6, :])
+    assert len(oedm._flatten_chunks(st_s["tspans"])) == 12          # the measurement grids do not cut the pieces
+    a = pyoracle.OracleLayer(_oracle_spec(sampled, ps_s)).eval(cb.to_vec(ps_s), K=8)
+    b = pyoracle.OracleLayer(_oracle_spec(cut, ps_c)).eval(cb.to_vec(ps_c), K=2)
+    assert a["u"].shape[1] == b["u"].shape[1] == 49 and np.array_equal(a["t"], b["t"])
+    assert np.max(np.abs(a["u"][:6] - b["u"][:6])) <= 1e-14
+    assert np.array_equal(a["u"][:6, ::4], b["u"][:6, ::4])          # the piece ends themselves: bit for bit
 
 
 def test_multi_experiment_layer_structure():
