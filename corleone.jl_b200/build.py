@@ -19,9 +19,14 @@ NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 # -Xfatbin -compress-all: the device code is stored compressed (the driver inflates it at module load): 3x smaller
 # objects -- with the per-model instantiation lists trimmed to G in {0, default} the library is ~35 MB instead of 198 MB
 FLAGS = [
-    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "-ccbin", "/usr/bin/g++", "-Xfatbin", "-compress-all",
 ]
+# -lineinfo (ncu's source page) only for the translation units whose kernels are profiled (profiles/): the BASELINE
+# configs' models and the host-side kernels; it is a fifth of the size of the others
+LINEINFO = {"api.cu", "comm.cu", "shoot_dense20.cu", "shoot_lqr.cu", "shoot_lotka2_oed.cu", "shoot_lotka3.cu"}
+if os.environ.get("CB200_LINEINFO_ALL"):
+    LINEINFO = None
 
 
 def _stale(target: str, deps: list[str]) -> bool:
@@ -39,7 +44,8 @@ def build(force: bool = False, ptxas_v: bool = False) -> str:
     for src in sources:
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + ".o")
         if force or _stale(obj, [src] + headers):
-            cmd = [NVCC] + FLAGS + EXTRA + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
+            li = ["-lineinfo"] if (LINEINFO is None or os.path.basename(src) in LINEINFO) else []
+            cmd = [NVCC] + FLAGS + li + EXTRA + (["-Xptxas", "-v"] if ptxas_v else []) + ["-c", src, "-o", obj]
             jobs.append((src, cmd))
     if jobs:
         with cf.ThreadPoolExecutor(max_workers=min(8, len(jobs))) as ex:

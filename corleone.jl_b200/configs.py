@@ -67,20 +67,21 @@ def config3_lotka_oed(n_intervals=64, rng=None):
     return s
 
 
-def dense20_data(seed=SEED0 + 4):
+def dense20_data(seed=SEED0 + 4, nx=20):
     rng = np.random.default_rng(seed)
-    W = 0.5 * rng.standard_normal((20, 20)) / np.sqrt(20.0)
-    return np.concatenate([W.ravel(), rng.standard_normal(20)])
+    W = 0.5 * rng.standard_normal((nx, nx)) / np.sqrt(float(nx))
+    return np.concatenate([W.ravel(), rng.standard_normal(nx)])
 
 
-def config4_dense20(n_intervals=256, rng=None):
-    """config 4 (synthetic): x' = W x - x^3 + b u, 20 states, M = 4 pieces per interval of length 0.5."""
+def config4_dense20(n_intervals=256, rng=None, nx=20):
+    """config 4 (synthetic): x' = W x - x^3 + b u, 20 states, M = 4 pieces per interval of length 0.5
+    (nx = 16, 24, 32: the same family at the other sizes of the tensor-path kernel)."""
     rng = np.random.default_rng(SEED0 + 4) if rng is None else rng
     nctl = 4 * n_intervals
     t = np.arange(nctl) / 8.0
-    return dict(model="dense20", u0=list(rng.uniform(-1, 1, 20)), p0=[0.0], tspan=(0.0, nctl / 8.0),
+    return dict(model=f"dense{nx}", u0=list(rng.uniform(-1, 1, nx)), p0=[0.0], tspan=(0.0, nctl / 8.0),
                 controls=[(1, t, rng.uniform(-1, 1, nctl))], tunable_ic=[], quadrature_indices=[],
-                shooting_points=[(4 * k) / 8.0 for k in range(n_intervals)], model_data=dense20_data())
+                shooting_points=[(4 * k) / 8.0 for k in range(n_intervals)], model_data=dense20_data(nx=nx))
 
 
 def lin1d_oed_spec():

@@ -26,13 +26,28 @@ struct NvtxRange {
 };
 struct D20Slot {
     int refs = 0;
-    double data[420];
+    double data[32 * 32 + 32];
 };
 std::mutex g_d20_mu;
-D20Slot g_d20[64];   // per device ordinal
+D20Slot g_d20[4][64];   // per dense model (dense_slot) and device ordinal
 }  // namespace
 
 using namespace cb200;
+
+// the dense family: slot of the model's __constant__ block, states; -1: not a dense model
+static int dense_slot(int model, int *nx = nullptr)
+{
+    int s = -1, n = 0;
+    switch (model) {
+    case CB200_MODEL_DENSE20: s = 0; n = 20; break;
+    case CB200_MODEL_DENSE16: s = 1; n = 16; break;
+    case CB200_MODEL_DENSE24: s = 2; n = 24; break;
+    case CB200_MODEL_DENSE32: s = 3; n = 32; break;
+    default: break;
+    }
+    if (nx) *nx = n;
+    return s;
+}
 
 // ------------------------------------------------------------------ errors
 static thread_local std::string g_err;
@@ -275,7 +290,7 @@ static int default_G(int model)
     case CB200_MODEL_LOTKACOMP3: return 2;
     case CB200_MODEL_F8AIRCRAFT4: return 2;
     case CB200_MODEL_DOUBLEOSC6: return 1;
-    case CB200_MODEL_DENSE20: return 1;
+    case CB200_MODEL_DENSE20: case CB200_MODEL_DENSE16: case CB200_MODEL_DENSE24: case CB200_MODEL_DENSE32: return 1;
     case CB200_MODEL_LOTKA2_OED: return 1;   // second-order sensitivities of [x; G; F]: 12 dynamic + 6 quadrature per thread (G = 2 spills)
     case CB200_MODEL_LIN1D_OED: return 2;
     case CB200_MODEL_LOTKA2_OED_CU: return 1;
@@ -318,6 +333,9 @@ static int model_dims(int model, int *nx, int *np, int *nxd = nullptr)
     case CB200_MODEL_LIN1D: *nx = 1; *np = 1; d = 1; break;
     case CB200_MODEL_LIN1D_OED: *nx = 3; *np = 2; d = 2; break;
     case CB200_MODEL_DENSE20: *nx = 20; *np = 1; d = 20; break;
+    case CB200_MODEL_DENSE16: *nx = 16; *np = 1; d = 16; break;
+    case CB200_MODEL_DENSE24: *nx = 24; *np = 1; d = 24; break;
+    case CB200_MODEL_DENSE32: *nx = 32; *np = 1; d = 32; break;
     case CB200_MODEL_EGERSTEDT: *nx = 3; *np = 3; d = 2; break;
     case CB200_MODEL_VDP3: *nx = 3; *np = 1; d = 2; break;
     case CB200_MODEL_CARTPOLE5: *nx = 5; *np = 1; d = 4; break;
@@ -370,6 +388,9 @@ static int launch_model(int model, int G, int method, const DevLayer &L, const d
     case CB200_MODEL_LIN1D: return launch_lin1d(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_LIN1D_OED: return launch_lin1d_oed(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_DENSE20: return launch_dense20(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DENSE16: return launch_dense16(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DENSE24: return launch_dense24(G, method, L, ps, ldb, B, o, s);
+    case CB200_MODEL_DENSE32: return launch_dense32(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_EGERSTEDT: return launch_egerstedt(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_VDP3: return launch_vdp3(G, method, L, ps, ldb, B, o, s);
     case CB200_MODEL_CARTPOLE5: return launch_cartpole5(G, method, L, ps, ldb, B, o, s);
@@ -420,6 +441,9 @@ static int forward_model(int model, int method, const DevLayer &L, double *ps, l
     case CB200_MODEL_LIN1D: return forward_lin1d(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_LIN1D_OED: return forward_lin1d_oed(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_DENSE20: return forward_dense20(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DENSE16: return forward_dense16(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DENSE24: return forward_dense24(method, L, ps, ldb, B, fixed, s);
+    case CB200_MODEL_DENSE32: return forward_dense32(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_EGERSTEDT: return forward_egerstedt(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_VDP3: return forward_vdp3(method, L, ps, ldb, B, fixed, s);
     case CB200_MODEL_CARTPOLE5: return forward_cartpole5(method, L, ps, ldb, B, fixed, s);
@@ -487,8 +511,6 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         return fail(CB200_ERR_UNSUPPORTED, "unknown method");
     if (d->steps_per_piece < 1) return fail(CB200_ERR_ARG, "steps_per_piece must be >= 1");
     if (d->method == CB200_TSIT5_ADAPTIVE) {
-        if (d->model == CB200_MODEL_DENSE20)
-            return fail(CB200_ERR_UNSUPPORTED, "model %d has no adaptive-step kernel (the tensor-path kernel is fixed-step)", d->model);
         if (!(d->abstol > 0.0) || !(d->reltol > 0.0)) return fail(CB200_ERR_ARG, "adaptive Tsit5 needs abstol > 0 and reltol > 0");
     }
     if (d->n_intervals < 1) return fail(CB200_ERR_ARG, "n_intervals must be >= 1");
@@ -727,7 +749,7 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
         delete h;
         return fail(CB200_ERR_UNSUPPORTED, "saveat times inside a control piece need Tsit5's dense output (method 0 or 2)");
     }
-    if (h->has_saveat && d->model == CB200_MODEL_DENSE20) {
+    if (h->has_saveat && dense_slot(d->model) >= 0) {
         delete h;
         return fail(CB200_ERR_UNSUPPORTED, "saveat is not available for the dense tensor-path model");
     }
@@ -1015,25 +1037,32 @@ extern "C" int cb200_create(const cb200_desc *d, cb200_handle **out)
     h->d_quad = (int *)(base + o_q);
     h->d_grad = (GradEntry *)(base + o_gr);
 
-    if (d->model == CB200_MODEL_DENSE20) {
-        if (!d->model_data || d->model_data_len != 420) {
+    int dnx = 0;
+    const int dslot = dense_slot(d->model, &dnx);
+    if (dslot >= 0) {
+        const long long want_len = (long long)dnx * dnx + dnx;
+        if (!d->model_data || d->model_data_len != want_len) {
             cb200_destroy(h);
-            return fail(CB200_ERR_ARG, "DENSE20 needs model_data of 420 doubles (W row-major, then b)");
+            return fail(CB200_ERR_ARG, "the dense %d-state model needs model_data of %lld doubles (W row-major, then b)", dnx, want_len);
         }
-        {   // the thread-per-direction kernels read W, b from ONE __constant__ block per device: live DENSE20 handles on
-            // a device must share their data (the tensor-path kernel reads the handle's own table and has no such limit)
+        {   // the thread-per-unit kernels read W, b from ONE __constant__ block per model and device: live handles of a
+            // dense model on a device must share their data (the tensor-path kernel reads the handle's own table and has
+            // no such limit)
             std::lock_guard<std::mutex> lk(g_d20_mu);
-            D20Slot &slot = g_d20[d->device & 63];
-            if (slot.refs > 0 && memcmp(slot.data, d->model_data, sizeof slot.data) != 0) {
+            D20Slot &slot = g_d20[dslot][d->device & 63];
+            if (slot.refs > 0 && memcmp(slot.data, d->model_data, sizeof(double) * (size_t)want_len) != 0) {
                 cb200_destroy(h);
-                return fail(CB200_ERR_UNSUPPORTED, "another DENSE20 layer with different model_data is alive on device %d", d->device);
+                return fail(CB200_ERR_UNSUPPORTED, "another dense %d-state layer with different model_data is alive on device %d", dnx, d->device);
             }
-            memcpy(slot.data, d->model_data, sizeof slot.data);
+            memcpy(slot.data, d->model_data, sizeof(double) * (size_t)want_len);
             slot.refs++;
             h->d20_ref = true;
         }
-        int rc = dense20_set_data(d->model_data, d->model_data_len);
-        if (rc != 0) return bail("cudaMemcpyToSymbol(dense20)", (cudaError_t)rc);
+        int rc = dslot == 0   ? dense20_set_data(d->model_data, d->model_data_len)
+                 : dslot == 1 ? dense16_set_data(d->model_data, d->model_data_len)
+                 : dslot == 2 ? dense24_set_data(d->model_data, d->model_data_len)
+                              : dense32_set_data(d->model_data, d->model_data_len);
+        if (rc != 0) return bail("cudaMemcpyToSymbol(dense model data)", (cudaError_t)rc);
     }
     {   // accumulators of the cross-candidate sums, zero at rest (handle.cuh)
         const size_t n_acc = (size_t)(1 + L.nvars + h->fim_n * h->fim_n);
@@ -1078,7 +1107,7 @@ extern "C" int cb200_destroy(cb200_handle *h)
     if (h->acc) cudaFree(h->acc);
     if (h->d20_ref) {
         std::lock_guard<std::mutex> lk(g_d20_mu);
-        g_d20[h->device & 63].refs--;
+        g_d20[dense_slot(h->model)][h->device & 63].refs--;
         h->d20_ref = false;
     }
     for (DevBuf *b : {&h->ws_ps, &h->ws_in, &h->ws_xend, &h->ws_sens, &h->ws_traj, &h->ws_dk, &h->ws_ds, &h->ws_obj,

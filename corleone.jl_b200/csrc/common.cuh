@@ -298,5 +298,15 @@ int launch_hangglider4(int G, int method, const DevLayer &L, const double *ps, l
 int forward_hangglider4(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s);
 int dense20_set_data(const double *host_data, long long n);
+#define CB200_DECL_DENSE(NXV)                                                                                             \
+    int launch_dense##NXV(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B, const ShootOut &o, \
+                          cudaStream_t s);                                                                                \
+    int forward_dense##NXV(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,   \
+                           cudaStream_t s);                                                                               \
+    int dense##NXV##_set_data(const double *host_data, long long n);
+CB200_DECL_DENSE(16)
+CB200_DECL_DENSE(24)
+CB200_DECL_DENSE(32)
+#undef CB200_DECL_DENSE
 
 }  // namespace cb200

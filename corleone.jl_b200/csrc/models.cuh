@@ -44,8 +44,9 @@ struct SaveAtTraits<M, decltype((void)M::SAVEAT, void())> {
 };
 
 #ifdef CB200_NEED_DENSE20_DATA
-// model constants for DENSE20 (W row-major 20x20, then b[20]); constant-bank operands of the FMAs
-__constant__ double c_dense20[420];
+// model constants of the dense family (W row-major NX x NX, then b[NX]; NX <= 32) for the thread-per-unit kernels of the
+// including translation unit: constant-bank operands of the FMAs (one copy per translation unit = per NX)
+static __constant__ double c_dense[32 * 32 + 32];
 #endif
 
 // ---- Lotka-Volterra fishing with Lagrange state (examples/lotka_fishing_optimal_control/main.jl:38-42)
@@ -210,9 +211,11 @@ struct Egerstedt {
 };
 
 #ifdef CB200_NEED_DENSE20_DATA
-// ---- synthetic 20-state problem of BASELINE config 4: x' = W x - x.^3 + b u, p = (u)
-struct Dense20 {
-    static constexpr int NX = 20, NXD = 20, NQ = 0, NP = 1;
+// ---- synthetic dense problems: x' = W x - x.^3 + b u, p = (u).  NX = 20 is BASELINE config 4; 16, 24 and 32 are the same
+//      family at the other sizes the tensor-path kernel is built for
+template <int N>
+struct DenseN {
+    static constexpr int NX = N, NXD = N, NQ = 0, NP = 1;
     static constexpr bool HAS_JVP = true;
     struct Ctx {};
     struct Force {
@@ -221,10 +224,10 @@ struct Dense20 {
     CB_DEV void f(const double *x, const double *p, double *dx, Ctx &)
     {
 #pragma unroll
-        for (int i = 0; i < 20; i++) {
-            double acc = c_dense20[400 + i] * p[0];
+        for (int i = 0; i < N; i++) {
+            double acc = c_dense[N * N + i] * p[0];
 #pragma unroll
-            for (int j = 0; j < 20; j++) acc = fma(c_dense20[i * 20 + j], x[j], acc);
+            for (int j = 0; j < N; j++) acc = fma(c_dense[i * N + j], x[j], acc);
             dx[i] = acc - x[i] * x[i] * x[i];
         }
     }
@@ -232,14 +235,15 @@ struct Dense20 {
     CB_DEV void jvp(const double *x, const double *, const Ctx &, const double *v, const Force &F, double *dv)
     {
 #pragma unroll
-        for (int i = 0; i < 20; i++) {
-            double acc = F.w * c_dense20[400 + i];
+        for (int i = 0; i < N; i++) {
+            double acc = F.w * c_dense[N * N + i];
 #pragma unroll
-            for (int j = 0; j < 20; j++) acc = fma(c_dense20[i * 20 + j], v[j], acc);
+            for (int j = 0; j < N; j++) acc = fma(c_dense[i * N + j], v[j], acc);
             dv[i] = fma(-3.0 * x[i] * x[i], v[i], acc);
         }
     }
 };
+using Dense20 = DenseN<20>;
 #endif
 
 // ---- OED augmentation (lib/CorleoneOED/src/augmentation.jl).  State [x; vec(G) column-major nx x NF; F ...],

@@ -35,7 +35,14 @@
 
 namespace cb200 {
 
-constexpr int DM_NX = 20;        // states
+// NX (template parameter): states, a multiple of 4: 16, 20, 24, 32.  Lane (g, t) owns the S = NX/4 states S t .. S t + S - 1;
+// k-tiles KT = S (k-tile kt = states {S t + kt}), n-tiles NT = ceil(S / 2) (n-slot 2 tau + e of tile nt <-> state
+// S tau + 2 nt + e; for odd S the last slot is zero padding).
+template <int NX>
+struct DenseDims {
+    static_assert(NX % 4 == 0 && NX >= 8 && NX <= 32, "dense tensor path: NX must be a multiple of 4 in 8..32");
+    static constexpr int S = NX / 4, KT = S, NT = (S + 1) / 2;
+};
 constexpr int DM_CPB = 5;        // candidates per block
 constexpr int DM_SW = 15;        // S-tile warps: 15 * 8 = 24 * 5 columns per round
 constexpr int DM_DPR = 24;       // directions per round
@@ -49,26 +56,29 @@ __device__ __forceinline__ void dmma884(double &c0, double &c1, double a, double
                  : "d"(a), "d"(b));
 }
 
+template <int NX>
 struct DenseTile {
-    double Wf[15];   // B fragments of W^T: [kt*3 + nt]
+    double Wf[DenseDims<NX>::KT * DenseDims<NX>::NT];   // B fragments of W^T: [kt*NT + nt]
     bool col_on;     // this lane's column is live
     int t;           // lane % 4
 };
 
 // the lane's W^T fragments in the permuted state order (see header); loaded once per kernel
-__device__ __forceinline__ void dense_load_w(const DevLayer &L, DenseTile &T)
+template <int NX>
+__device__ __forceinline__ void dense_load_w(const DevLayer &L, DenseTile<NX> &T)
 {
+    constexpr int S = DenseDims<NX>::S, KT = DenseDims<NX>::KT, NT = DenseDims<NX>::NT;
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const double *W = L.model_data;   // row-major 20x20, then b[20]
+    const double *W = L.model_data;   // row-major NX x NX, then b[NX]
     T.t = t;
 #pragma unroll
-    for (int kt = 0; kt < 5; kt++)
+    for (int kt = 0; kt < KT; kt++)
 #pragma unroll
-        for (int nt = 0; nt < 3; nt++) {
-            // B[k = t][n = g]: k-state 5t + kt; n-slot g = 2 tau + e -> state 5 tau + 2 nt + e (nt = 2, e = 1: padding)
+        for (int nt = 0; nt < NT; nt++) {
+            // B[k = t][n = g]: k-state S t + kt; n-slot g = 2 tau + e -> state S tau + 2 nt + e (beyond S: padding)
             const int tau = g >> 1, e = g & 1;
-            const int sn = 5 * tau + 2 * nt + e;
-            T.Wf[kt * 3 + nt] = (nt == 2 && e == 1) ? 0.0 : __ldg(W + sn * DM_NX + (5 * t + kt));
+            const int sn = S * tau + 2 * nt + e;
+            T.Wf[kt * NT + nt] = (2 * nt + e >= S) ? 0.0 : __ldg(W + sn * NX + (S * t + kt));
         }
 }
 
@@ -78,34 +88,36 @@ __device__ __forceinline__ void dense_load_w(const DevLayer &L, DenseTile &T)
 // __syncthreads per call (every warp of the block calls this the same number of times).  PIPE = true: the x tile ran
 // ahead, `slot` already holds its value.  No predicate on idle tiles: a tile without live columns integrates zeros
 // (lockstep) or never gets here (pipelined), so the stage body is straight-line.
-template <bool PIPE, bool IS_X>
-__device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, const double *binit, double *k, double *slot)
+template <int NX, bool PIPE, bool IS_X>
+__device__ __forceinline__ void dense_rhs(const DenseTile<NX> &T, const double *y, const double *binit, double *k, double *slot)
 {
-    double q[5];
+    constexpr int S = DenseDims<NX>::S, KT = DenseDims<NX>::KT, NT = DenseDims<NX>::NT;
+    double q[S];
     if constexpr (IS_X) {
 #pragma unroll
-        for (int s = 0; s < 5; s++) q[s] = y[s] * y[s];
+        for (int s = 0; s < S; s++) q[s] = y[s] * y[s];
         if (T.col_on) {
 #pragma unroll
-            for (int s = 0; s < 5; s++) slot[s] = -3.0 * q[s];
+            for (int s = 0; s < S; s++) slot[s] = -3.0 * q[s];
         }
     }
     // the accumulators start from the b-term of the piece: b u for the states, b for the running piece's control
     // direction, 0 otherwise (the C operand of the first DMMA of each chain)
-    double d[6] = {binit[0], binit[1], binit[2], binit[3], binit[4], 0.0};
+    double d[2 * NT];
 #pragma unroll
-    for (int kt = 0; kt < 5; kt++) {
-        dmma884(d[0], d[1], y[kt], T.Wf[kt * 3 + 0]);
-        dmma884(d[2], d[3], y[kt], T.Wf[kt * 3 + 1]);
-        dmma884(d[4], d[5], y[kt], T.Wf[kt * 3 + 2]);
+    for (int s = 0; s < 2 * NT; s++) d[s] = s < S ? binit[s < S ? s : 0] : 0.0;
+#pragma unroll
+    for (int kt = 0; kt < KT; kt++) {
+#pragma unroll
+        for (int nt = 0; nt < NT; nt++) dmma884(d[2 * nt], d[2 * nt + 1], y[kt], T.Wf[kt * NT + nt]);
     }
     if constexpr (!PIPE) __syncthreads();
     if constexpr (IS_X) {  // f(x) = W x - x^3 + b u
 #pragma unroll
-        for (int s = 0; s < 5; s++) k[s] = fma(-q[s], y[s], d[s]);
+        for (int s = 0; s < S; s++) k[s] = fma(-q[s], y[s], d[s]);
     } else {               // f_x v + f_u = W v - 3 x^2 v (+ b)
 #pragma unroll
-        for (int s = 0; s < 5; s++) k[s] = fma(slot[s], y[s], d[s]);
+        for (int s = 0; s < S; s++) k[s] = fma(slot[s], y[s], d[s]);
     }
 }
 
@@ -113,7 +125,7 @@ __device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, c
 // sp walks the lane's entries of the slots, sp_alt is the lockstep partner
 #define DM_RHS(y)                                      \
     do {                                               \
-        dense_rhs<PIPE, IS_X>(T, y, binit, k, sp);     \
+        dense_rhs<NX, PIPE, IS_X>(T, y, binit, k, sp);     \
         if constexpr (PIPE) {                          \
             sp += slot_stride;                         \
         } else {                                       \
@@ -127,13 +139,13 @@ __device__ __forceinline__ void dense_rhs(const DenseTile &T, const double *y, c
 // (IS_X) or its sensitivity with respect to local variable `dir`.  col_on: the column exists (else it integrates
 // zeros); store: it writes results (a live candidate); x_results: the x tile writes the unit's results (first
 // direction round only).  sp / sp_alt / slot_stride: the lane's entries of the stage-exchange slots (DM_RHS).
-template <int METHOD, bool UNI, bool PIPE, bool IS_X>
+template <int NX, int METHOD, bool UNI, bool PIPE, bool IS_X>
 __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__restrict__ ps, long long ldb,
                                              const ShootOut &o, int i, int nu0, int ns, int dir, long long b, bool col_on,
                                              bool store, bool x_results, double *sp, double *sp_alt, int slot_stride,
-                                             DenseTile &T)
+                                             DenseTile<NX> &T)
 {
-    constexpr int NX = DM_NX, NCF = METHOD == 0 ? 21 : 4;
+    constexpr int S = DenseDims<NX>::S, NCF = METHOD == 0 ? 21 : 4;
     const int t = threadIdx.x & 3;
     (void)sp_alt;
     (void)slot_stride;
@@ -141,10 +153,10 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
     const int voff = __ldg(L.var_off + i);
     const double *__restrict__ v = ps + (long long)voff * ldb + b;
     // ---- initial values of the lane's five entries
-    double yd[5];
+    double yd[S];
 #pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int k = 5 * t + s;
+    for (int s = 0; s < S; s++) {
+        const int k = S * t + s;
         const int src = __ldg(L.ic_src + i * NX + k);
         if (IS_X)
             yd[s] = (src >= 0) ? v[(long long)src * ldb] : __ldg(L.ic_fix + i * NX + k);
@@ -153,7 +165,7 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
     }
     if (!T.col_on) {
 #pragma unroll
-        for (int s = 0; s < 5; s++) yd[s] = 0.0;
+        for (int s = 0; s < S; s++) yd[s] = 0.0;
     }
     const int cdir = dir - nu0 - L.ntp;   // local control index this column differentiates with respect to (< 0: a u0 direction)
     const int M = __ldg(L.M + i), po = __ldg(L.piece_off + i), so = __ldg(L.samp_off + i);
@@ -170,21 +182,21 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
             ci_nx = __ldg(L.cidx + (long long)(po + j + 1) * L.nact);
             u_nx = vc[(long long)ci_nx * ldb];
         }
-        double binit[5];   // b-term of this piece for the lane's states
+        double binit[S];   // b-term of this piece for the lane's states
         {
             const double w = IS_X ? u : ((T.col_on && cdir == ci) ? 1.0 : 0.0);
 #pragma unroll
-            for (int s = 0; s < 5; s++) binit[s] = w * __ldg(L.model_data + NX * NX + 5 * t + s);
+            for (int s = 0; s < S; s++) binit[s] = w * __ldg(L.model_data + NX * NX + S * t + s);
         }
         if (!IS_X && o.tsens && store && j == 0) {   // sensitivities at the interval's start sample
-            const long long row0 = __ldg(L.tsens_off + i) + (long long)dir * NX + 5 * t;
+            const long long row0 = __ldg(L.tsens_off + i) + (long long)dir * NX + S * t;
 #pragma unroll
-            for (int s = 0; s < 5; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
+            for (int s = 0; s < S; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
         }
         if (o.traj && IS_X && store && x_results && j == 0) {  // save_start = (j == 1)
             double *tr = o.traj + ((long long)so * nrow) * o.ldo + b;
 #pragma unroll
-            for (int s = 0; s < 5; s++) tr[(long long)(5 * t + s) * o.ldo] = yd[s];
+            for (int s = 0; s < S; s++) tr[(long long)(S * t + s) * o.ldo] = yd[s];
             if (t == 0) tr[(long long)NX * o.ldo] = u;
         }
         double cf[NCF];
@@ -198,13 +210,15 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
             else
                 rk4_coeffs(h, cf);
         }
-        double k[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+        double k[S];
+#pragma unroll
+        for (int c = 0; c < S; c++) k[c] = 0.0;
         if constexpr (METHOD == 0) {   // accumulator-form Tsit5 (shoot.cuh), five components per lane
-            double s2[5], s3[5], s4[5], s5[5], s6[5];
+            double s2[S], s3[S], s4[S], s5[S], s6[S];
             DM_RHS(yd);
             for (int st = 0; st < L.K; st++) {
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     s2[c] = fma(cf[0], k[c], yd[c]);
                     s3[c] = fma(cf[1], k[c], yd[c]);
                     s4[c] = fma(cf[3], k[c], yd[c]);
@@ -214,7 +228,7 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
                 }
                 DM_RHS(s2);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     s3[c] = fma(cf[2], k[c], s3[c]);
                     s4[c] = fma(cf[4], k[c], s4[c]);
                     s5[c] = fma(cf[7], k[c], s5[c]);
@@ -223,7 +237,7 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
                 }
                 DM_RHS(s3);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     s4[c] = fma(cf[5], k[c], s4[c]);
                     s5[c] = fma(cf[8], k[c], s5[c]);
                     s6[c] = fma(cf[12], k[c], s6[c]);
@@ -231,58 +245,58 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
                 }
                 DM_RHS(s4);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     s5[c] = fma(cf[9], k[c], s5[c]);
                     s6[c] = fma(cf[13], k[c], s6[c]);
                     yd[c] = fma(cf[18], k[c], yd[c]);
                 }
                 DM_RHS(s5);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     s6[c] = fma(cf[14], k[c], s6[c]);
                     yd[c] = fma(cf[19], k[c], yd[c]);
                 }
                 DM_RHS(s6);
 #pragma unroll
-                for (int c = 0; c < 5; c++) yd[c] = fma(cf[20], k[c], yd[c]);
+                for (int c = 0; c < S; c++) yd[c] = fma(cf[20], k[c], yd[c]);
                 if (st + 1 < L.K) DM_RHS(yd);   // FSAL
             }
         } else {   // classical RK4
-            double acc[5], td[5];
+            double acc[S], td[S];
             for (int st = 0; st < L.K; st++) {
                 DM_RHS(yd);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     acc[c] = fma(cf[2], k[c], yd[c]);
                     td[c] = fma(cf[0], k[c], yd[c]);
                 }
                 DM_RHS(td);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     acc[c] = fma(cf[3], k[c], acc[c]);
                     td[c] = fma(cf[0], k[c], yd[c]);
                 }
                 DM_RHS(td);
 #pragma unroll
-                for (int c = 0; c < 5; c++) {
+                for (int c = 0; c < S; c++) {
                     acc[c] = fma(cf[3], k[c], acc[c]);
                     td[c] = fma(cf[1], k[c], yd[c]);
                 }
                 DM_RHS(td);
 #pragma unroll
-                for (int c = 0; c < 5; c++) yd[c] = fma(cf[2], k[c], acc[c]);
+                for (int c = 0; c < S; c++) yd[c] = fma(cf[2], k[c], acc[c]);
             }
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (!IS_X && o.tsens && store && (j + 1 < M || last_interval)) {
-            const long long row0 = __ldg(L.tsens_off + i) + ((long long)(j + 1) * ns + dir) * NX + 5 * t;
+            const long long row0 = __ldg(L.tsens_off + i) + ((long long)(j + 1) * ns + dir) * NX + S * t;
 #pragma unroll
-            for (int s = 0; s < 5; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
+            for (int s = 0; s < S; s++) o.tsens[(row0 + s) * o.ldo + b] = yd[s];
         }
         if (o.traj && IS_X && store && x_results && (j + 1 < M || last_interval)) {
             double *tr = o.traj + ((long long)(so + j + 1) * nrow) * o.ldo + b;
 #pragma unroll
-            for (int s = 0; s < 5; s++) tr[(long long)(5 * t + s) * o.ldo] = yd[s];
+            for (int s = 0; s < S; s++) tr[(long long)(S * t + s) * o.ldo] = yd[s];
             if (t == 0) tr[(long long)NX * o.ldo] = u;
         }
     }
@@ -294,20 +308,20 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
         if (o.status) {
             bool ok = true;
 #pragma unroll
-            for (int s = 0; s < 5; s++) ok = ok && isfinite(yd[s]);
+            for (int s = 0; s < S; s++) ok = ok && isfinite(yd[s]);
             if (!ok) atomicOr(o.status + b, 1);
         }
 #pragma unroll
-        for (int s = 0; s < 5; s++) {
-            const int k = 5 * t + s;
+        for (int s = 0; s < S; s++) {
+            const int k = S * t + s;
             if (o.xend) o.xend[((long long)i * NX + k) * o.ldo + b] = yd[s];
             if (o.objq && k == o.obj_state) o.objq[(long long)i * o.ldo + b] = yd[s];
         }
         if ((o.dk || o.dst) && i + 1 < L.I) {
             const int vn = __ldg(L.var_off + i + 1);
 #pragma unroll
-            for (int s = 0; s < 5; s++) {
-                const int k = 5 * t + s;
+            for (int s = 0; s < S; s++) {
+                const int k = S * t + s;
                 const int pk = __ldg(L.dpos_kind + i * NX + k);
                 if (pk >= 0) {
                     const int src = __ldg(L.ic_src + (i + 1) * NX + k);
@@ -332,8 +346,8 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
     const long long s0 = __ldg(L.sens_off + i);
     const bool inc = o.obj_all || i == L.I - 1;
 #pragma unroll
-    for (int s = 0; s < 5; s++) {
-        const int k = 5 * t + s;
+    for (int s = 0; s < S; s++) {
+        const int k = S * t + s;
         if (o.sens) o.sens[(s0 + (long long)dir * NX + k) * o.ldo + b] = yd[s];
         if (o.jac && i + 1 < L.I) {
             const int jp = __ldg(L.jpos + i * NX + k);
@@ -352,13 +366,13 @@ __device__ __forceinline__ void dense_column(const DevLayer &L, const double *__
 
 // Lockstep kernel: one block per unit group (5 candidates of one interval, direction round blockIdx.z), x and S tiles
 // exchange through two alternating slots; both branches meet at the same barrier once per right-hand-side call.
-template <int METHOD, bool UNI>
+template <int NX, int METHOD, bool UNI>
 __global__ void __launch_bounds__(DM_THREADS, 1)
 shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
                        const ShootOut o)
 {
-    __shared__ double sx[2 * DM_CPB * DM_NX];
-    DenseTile T;
+    __shared__ double sx[2 * DM_CPB * NX];
+    DenseTile<NX> T;
     dense_load_w(L, T);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
     const int i = blockIdx.y + L.i0, round = blockIdx.z;
@@ -373,13 +387,13 @@ shoot_dense_mma_kernel(const __grid_constant__ DevLayer L, const double *__restr
     const bool cand_live = b < B;
     if (!cand_live) b = B - 1;
     const bool col_on = is_x ? (g < DM_CPB) : (dir < ns);
-    double *sp = sx + cand * DM_NX + 5 * t;
+    double *sp = sx + cand * NX + DenseDims<NX>::S * t;
     if (is_x)
-        dense_column<METHOD, UNI, false, true>(L, ps, ldb, o, i, nu0, ns, 0, b, col_on, col_on && cand_live, round == 0, sp,
-                                               sp + DM_CPB * DM_NX, 0, T);
+        dense_column<NX, METHOD, UNI, false, true>(L, ps, ldb, o, i, nu0, ns, 0, b, col_on, col_on && cand_live, round == 0, sp,
+                                               sp + DM_CPB * NX, 0, T);
     else
-        dense_column<METHOD, UNI, false, false>(L, ps, ldb, o, i, nu0, ns, dir, b, col_on, col_on && cand_live, false, sp,
-                                                sp + DM_CPB * DM_NX, 0, T);
+        dense_column<NX, METHOD, UNI, false, false>(L, ps, ldb, o, i, nu0, ns, dir, b, col_on, col_on && cand_live, false, sp,
+                                                sp + DM_CPB * NX, 0, T);
 }
 
 // ---- queue kernel
@@ -395,7 +409,7 @@ __device__ __forceinline__ unsigned dq_peek(const unsigned *p) { return *(const 
 // but certainly finished, and the result is needed only a whole item later.  Every wait is on a task EARLIER in the
 // queue (already running or done), so the order is deadlock-free.
 //   s_full[slot] = K + 1 once x_K has filled the slot;  s_done[slot] counts the finished S tasks on the slot.
-template <int METHOD, bool UNI, int NWARPS>
+template <int NX, int METHOD, bool UNI, int NWARPS>
 __global__ void __launch_bounds__(NWARPS * 32, 1)
 shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B,
                              const ShootOut o, long long n_items, int n_tiles, int nst, int nring)
@@ -408,12 +422,12 @@ shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *_
     }
     __syncthreads();
     const int lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
-    const int per = nst * DQ_CPI * DM_NX;
+    const int per = nst * DQ_CPI * NX;
     const unsigned nk = n_items > blockIdx.x ? (unsigned)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     const unsigned la = (unsigned)nring - 1u, row = (unsigned)n_tiles + 1u;
     const unsigned px = (unsigned)min(nring == 3 ? 16 : 8, n_tiles);
     const unsigned n_tasks = la + nk * row;
-    DenseTile T;
+    DenseTile<NX> T;
     dense_load_w(L, T);
     for (;;) {
         unsigned tk = 0;
@@ -440,14 +454,14 @@ shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *_
         const bool cand_live = b < B;
         if (!cand_live) b = B - 1;
         const int slot = (int)(K % (unsigned)nring);
-        double *sp = ring + (long long)slot * per + g * DM_NX + 5 * t;
+        double *sp = ring + (long long)slot * per + g * NX + DenseDims<NX>::S * t;
         const int nu0 = __ldg(L.n_u0 + i), ns = nu0 + L.ntp + __ldg(L.n_c + i);
         if (tau < 0) {
             const unsigned need = (unsigned)n_tiles * (K / (unsigned)nring);   // S tasks of the slot's earlier items
             while (dq_peek(&s_done[slot]) < need) __nanosleep(64);
             __threadfence_block();
-            dense_column<METHOD, UNI, true, true>(L, ps, ldb, o, i, nu0, ns, 0, b, true, cand_live, true, sp, nullptr,
-                                                  DQ_CPI * DM_NX, T);
+            dense_column<NX, METHOD, UNI, true, true>(L, ps, ldb, o, i, nu0, ns, 0, b, true, cand_live, true, sp, nullptr,
+                                                  DQ_CPI * NX, T);
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
@@ -457,8 +471,8 @@ shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *_
             if (tau < ns) {
                 while (dq_peek(&s_full[slot]) < K + 1u) __nanosleep(64);
                 __threadfence_block();
-                dense_column<METHOD, UNI, true, false>(L, ps, ldb, o, i, nu0, ns, tau, b, true, cand_live, false, sp, nullptr,
-                                                       DQ_CPI * DM_NX, T);
+                dense_column<NX, METHOD, UNI, true, false>(L, ps, ldb, o, i, nu0, ns, tau, b, true, cand_live, false, sp, nullptr,
+                                                       DQ_CPI * NX, T);
             }
             __syncwarp();
             if (lane == 0) {
@@ -469,19 +483,20 @@ shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *_
     }
 }
 
-// returns cudaError_t as int; -1000 if the layer does not fit this kernel
+// returns cudaError_t as int; -1000 if the layer does not fit this kernel.  WARPS: warps per block of the queue kernel
+// (the register budget per lane grows with NX: 16 warps x 128 registers up to NX = 20, 12 x 168 for 24, 8 x 255 for 32)
+template <int NX, int WARPS>
 inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, long long ldb, long long B, const ShootOut &o,
                             int max_ns, int max_pieces, cudaStream_t s)
 {
-    if (L.nact != 1 || L.ntp != 0 || L.nx != DM_NX || !L.model_data) return -1000;
+    if (L.nact != 1 || L.ntp != 0 || L.nx != NX || !L.model_data) return -1000;
     if (B <= 0) return 0;
     if (max_ns < 1) max_ns = 1;
     // right-hand-side calls per interval: Tsit5 6K per piece (FSAL after the last step skipped), RK4 4K
     const int nst = max_pieces * (method == 0 ? 6 : 4) * L.K;
-    const size_t per = sizeof(double) * (size_t)nst * DQ_CPI * DM_NX;
+    const size_t per = sizeof(double) * (size_t)nst * DQ_CPI * NX;
     static const bool lockstep = getenv("CB200_DENSE20_LOCKSTEP") != nullptr;
     static const int nring_env = getenv("CB200_DENSE20_NRING") ? atoi(getenv("CB200_DENSE20_NRING")) : 0;
-    static const int warps_env = getenv("CB200_DENSE20_WARPS") ? atoi(getenv("CB200_DENSE20_WARPS")) : 0;
     const size_t smem_cap = 225 * 1024;
     int nring = (nring_env == 2 || nring_env == 3) ? nring_env : 3;
     if (nring == 3 && 3 * per > smem_cap) nring = 2;
@@ -492,39 +507,38 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
         const long long n_items = ((B + DQ_CPI - 1) / DQ_CPI) * L.In;
         const unsigned grid = (unsigned)std::min<long long>(n_items, sms);
         const size_t smem = nring * per;
-        const int warps = (warps_env == 8 || warps_env == 12) ? warps_env : 16;
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-            kern<<<grid, warps * 32, smem, s>>>(L, ps, ldb, B, o, n_items, max_ns, nst, nring);
+            kern<<<grid, WARPS * 32, smem, s>>>(L, ps, ldb, B, o, n_items, max_ns, nst, nring);
         };
         if (method == 0) {
-            if (L.uniform_h) {
-                if (warps == 8) go(shoot_dense_mma_queue_kernel<0, true, 8>);
-                else if (warps == 12) go(shoot_dense_mma_queue_kernel<0, true, 12>);
-                else go(shoot_dense_mma_queue_kernel<0, true, 16>);
-            } else go(shoot_dense_mma_queue_kernel<0, false, 16>);
+            if (L.uniform_h) go(shoot_dense_mma_queue_kernel<NX, 0, true, WARPS>);
+            else go(shoot_dense_mma_queue_kernel<NX, 0, false, WARPS>);
         } else {
-            if (L.uniform_h) go(shoot_dense_mma_queue_kernel<1, true, 16>);
-            else go(shoot_dense_mma_queue_kernel<1, false, 16>);
+            if (L.uniform_h) go(shoot_dense_mma_queue_kernel<NX, 1, true, WARPS>);
+            else go(shoot_dense_mma_queue_kernel<NX, 1, false, WARPS>);
         }
         return (int)cudaGetLastError();
     }
-    const long long gx = (B + DM_CPB - 1) / DM_CPB;
-    const int rounds = (max_ns + DM_DPR - 1) / DM_DPR;
-    if (gx > 2147483647LL || L.In > 65535 || rounds > 65535) return -1000;
-    dim3 grid((unsigned)gx, (unsigned)L.In, (unsigned)rounds);
-    if (method == 0) {
-        if (L.uniform_h)
-            shoot_dense_mma_kernel<0, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
-        else
-            shoot_dense_mma_kernel<0, false><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
-    } else {
-        if (L.uniform_h)
-            shoot_dense_mma_kernel<1, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
-        else
-            shoot_dense_mma_kernel<1, false><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+    if constexpr (NX <= 20) {   // lockstep fallback (stage count beyond the ring): 16 warps x 128 registers
+        const long long gx = (B + DM_CPB - 1) / DM_CPB;
+        const int rounds = (max_ns + DM_DPR - 1) / DM_DPR;
+        if (gx > 2147483647LL || L.In > 65535 || rounds > 65535) return -1000;
+        dim3 grid((unsigned)gx, (unsigned)L.In, (unsigned)rounds);
+        if (method == 0) {
+            if (L.uniform_h)
+                shoot_dense_mma_kernel<NX, 0, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+            else
+                shoot_dense_mma_kernel<NX, 0, false><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+        } else {
+            if (L.uniform_h)
+                shoot_dense_mma_kernel<NX, 1, true><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+            else
+                shoot_dense_mma_kernel<NX, 1, false><<<grid, DM_THREADS, 0, s>>>(L, ps, ldb, B, o);
+        }
+        return (int)cudaGetLastError();
     }
-    return (int)cudaGetLastError();
+    return -1000;
 }
 
 }  // namespace cb200

@@ -55,6 +55,9 @@ MODEL_REGISTRY = {
     "ocean4": (39, 4, 2),
     "ductedfan7": (40, 7, 3),
     "hangglider4": (41, 4, 2),
+    "dense16": (42, 16, 1),
+    "dense24": (43, 24, 1),
+    "dense32": (44, 32, 1),
 }
 
 # base model -> (augmented model, Fisher parameter indices (1-based), number of observed functions)

@@ -95,7 +95,12 @@ typedef enum {
     CB200_MODEL_TUBULARREACTOR2 = 38,   /* tubular_reactor.jl:9-22; states (x1, x2), p = (u) */
     CB200_MODEL_OCEAN4 = 39,   /* ocean.jl:9-64; states (S, R, tau, cost), p = (u1, u2) */
     CB200_MODEL_DUCTEDFAN7 = 40,   /* ducted_fan.jl:9-61; states (x1, v1, x2, v2, alpha, valpha, cost), p = (t_s, u1, u2) */
-    CB200_MODEL_HANGGLIDER4 = 41   /* hang_glider.jl:9-66; states (x, y, vx, vy), p = (T, cL) */
+    CB200_MODEL_HANGGLIDER4 = 41,  /* hang_glider.jl:9-66; states (x, y, vx, vy), p = (T, cL) */
+    /* the dense family x' = W x - x^3 + b u at the other sizes the FP64 tensor-path kernel is built for (model_data = W
+       row-major nx x nx, then b[nx]) */
+    CB200_MODEL_DENSE16 = 42,
+    CB200_MODEL_DENSE24 = 43,
+    CB200_MODEL_DENSE32 = 44
 } cb200_model;
 
 typedef enum {
@@ -104,7 +109,7 @@ typedef enum {
     CB200_TSIT5_ADAPTIVE = 2    /* the reference's default: adaptive Tsit5 with the problem's abstol / reltol, every piece a
                                    fresh `solve` (src/single_shooting.jl:443-453); OrdinaryDiffEq's controller restated --
                                    reproduces the reference's golden vectors to ~1e-15.  steps_per_piece is ignored.
-                                   Every model but DENSE20 */
+                                   DENSE20 runs this mode on the generic kernel (thread per direction), not on the tensor path */
 } cb200_method;
 
 /*
@@ -142,8 +147,8 @@ typedef struct {
     const int64_t *ic_constants;        /* [sum ic_n_constants] InitialConditionRemaker.constants, 1-based */
     const int32_t *n_shooting_indices;  /* [I] */
     const int64_t *shooting_indices;    /* [sum] st.shooting_indices, 1-based over [states; controls] */
-    const double *model_data;           /* model constants (DENSE20: W row-major 20x20, then b[20]) or NULL.  Live DENSE20
-                                           handles on one device must carry the same data (one __constant__ block) */
+    const double *model_data;           /* model constants (DENSEnn: W row-major nx x nx, then b[nx]) or NULL.  Live handles of one
+                                           dense model on one device must carry the same data (one __constant__ block) */
     int64_t model_data_len;
     /* sample-based Fisher read-outs (fim_mode != 0); G = the nx_base x fim_n block behind the base states, the
        observed functions are the leading n_observed base states */

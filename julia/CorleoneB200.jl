@@ -145,7 +145,8 @@ const MODELS = Dict(:lotka3 => 0, :lqr => 1, :lotka2 => 2, :lotka2_oed => 3, :li
                     :batchreactor2 => 13, :lotkacomp3 => 14, :f8aircraft4 => 15, :doubleosc6 => 16,
                     :lotka2_oed_cu => 17, :lotka2_oed_cf => 18, :lotka2_oed_ds => 19, :lotka2_oed_du => 20,
                     :lin1d_oed_cf => 21, :lin1d_oed_ds => 22,
-                    :brysondenham3 => 23, :catalystmixing2 => 24, :cushioned3 => 25, :denbigh3 => 26, :dielectrophoretic3 => 27, :electriccar4 => 28, :fuller3 => 29, :jackson3 => 30, :mountaincar3 => 31, :particlesteering5 => 32, :raomease2 => 33, :robbins4 => 34, :moonlanding3 => 35, :lotkashared4 => 36, :hangingchain3 => 37, :tubularreactor2 => 38, :ocean4 => 39, :ductedfan7 => 40, :hangglider4 => 41)
+                    :brysondenham3 => 23, :catalystmixing2 => 24, :cushioned3 => 25, :denbigh3 => 26, :dielectrophoretic3 => 27, :electriccar4 => 28, :fuller3 => 29, :jackson3 => 30, :mountaincar3 => 31, :particlesteering5 => 32, :raomease2 => 33, :robbins4 => 34, :moonlanding3 => 35, :lotkashared4 => 36, :hangingchain3 => 37, :tubularreactor2 => 38, :ocean4 => 39, :ductedfan7 => 40, :hangglider4 => 41,
+                    :dense16 => 42, :dense24 => 43, :dense32 => 44)
 
 lasterror() = unsafe_string(ccall((:cb200_last_error, LIB), Cstring, ()))
 check(rc, what) = rc == 0 || error("$what failed ($rc): $(lasterror())")

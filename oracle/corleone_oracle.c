@@ -180,13 +180,13 @@ static void rhs_egerstedt(const dual *u, const dual *p, dual *du)
     du[1] = dadd(dadd(dmul(x2y, p[0]), dmul(xm2y, p[1])), dmul(xpy, p[2]));
     du[2] = dadd(dmul(x, x), dmul(y, y));
 }
-/* synthetic BASELINE config 4: x' = W x - x.^3 + b u ; p = (u) */
-static void rhs_dense20(const dual *x, const dual *p, dual *du, const double *data)
+/* synthetic BASELINE config 4: x' = W x - x.^3 + b u ; p = (u); n = 20, and the same family at 16, 24, 32 */
+static void rhs_dense(int n, const dual *x, const dual *p, dual *du, const double *data)
 {
-    const double *W = data, *b = data + 400;
-    for (int i = 0; i < 20; i++) {
+    const double *W = data, *b = data + n * n;
+    for (int i = 0; i < n; i++) {
         dual acc = dscale(p[0], b[i]);
-        for (int j = 0; j < 20; j++) daxpy(&acc, W[i * 20 + j], &x[j]);
+        for (int j = 0; j < n; j++) daxpy(&acc, W[i * n + j], &x[j]);
         dual x3 = dmul(dmul(x[i], x[i]), x[i]);
         du[i] = dsub(acc, x3);
     }
@@ -542,7 +542,10 @@ static void model_rhs(const model_ctx *m, const dual *u, const dual *p, dual *du
     case CO_LOTKA2_OED: rhs_oed(rhs_lotka2, jac_lotka2, 2, 3, 2, 2, AUG_CS, u, p, du); break;
     case CO_LIN1D: rhs_lin1d(u, p, du); break;
     case CO_LIN1D_OED: rhs_oed(rhs_lin1d, jac_lin1d, 1, 1, 1, 1, AUG_CS, u, p, du); break;
-    case CO_DENSE20: rhs_dense20(u, p, du, m->data); break;
+    case CO_DENSE20: rhs_dense(20, u, p, du, m->data); break;
+    case CO_DENSE16: rhs_dense(16, u, p, du, m->data); break;
+    case CO_DENSE24: rhs_dense(24, u, p, du, m->data); break;
+    case CO_DENSE32: rhs_dense(32, u, p, du, m->data); break;
     case CO_EGERSTEDT: rhs_egerstedt(u, p, du); break;
     case CO_VDP3: rhs_vdp3(u, p, du); break;
     case CO_CARTPOLE5: rhs_cartpole5(u, p, du); break;

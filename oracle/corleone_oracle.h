@@ -83,7 +83,10 @@ enum co_model {
     CO_TUBULARREACTOR2 = 38,
     CO_OCEAN4 = 39,
     CO_DUCTEDFAN7 = 40,
-    CO_HANGGLIDER4 = 41
+    CO_HANGGLIDER4 = 41,
+    CO_DENSE16 = 42, /* the dense family at the other sizes of the tensor-path kernel */
+    CO_DENSE24 = 43,
+    CO_DENSE32 = 44
 };
 
 enum co_method { CO_TSIT5 = 0, CO_RK4 = 1, CO_TSIT5_ADAPTIVE = 2 /* the reference's default mode; K is ignored */ };

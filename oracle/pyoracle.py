@@ -57,6 +57,9 @@ MODELS = {
     "ocean4": 39,
     "ductedfan7": 40,
     "hangglider4": 41,
+    "dense16": 42,
+    "dense24": 43,
+    "dense32": 44,
 }
 METHODS = {"tsit5": 0, "rk4": 1, "tsit5_adaptive": 2}
 CO_ND = 16

@@ -19,8 +19,8 @@ def lqr_spec(n_intervals=100, rng=None):
     return config2_lqr(n_intervals, rng)
 
 
-def dense20_spec(n_intervals=8, rng=None):
-    return config4_dense20(n_intervals, rng)
+def dense20_spec(n_intervals=8, rng=None, nx=20):
+    return config4_dense20(n_intervals, rng, nx=nx)
 
 
 def product_layer(spec, alg, **kw):

@@ -116,13 +116,13 @@ def test_adaptive_oed_fisher_information_parity(shooting):
         off += O.nx * ns
 
 
-def test_models_without_an_adaptive_kernel_say_so():
+def test_adaptive_mode_of_the_dense_model():
+    """the 20-state model in the reference's default mode: the tensor-path kernel is fixed-step, the adaptive mode runs
+    on the generic kernel (one thread per candidate, interval and direction) -- same parity bar"""
     import corleone_b200 as cb
-    from corleone_b200 import native as nat
-    lay = P.product_layer(P.dense20_spec(4), cb.Tsit5(adaptive=True))
-    ps, st = cb.setup(None, lay)
-    with pytest.raises(nat.NativeError, match="adaptive-step kernel"):
-        lay._native(st, ps)
+    rng = np.random.default_rng(41)
+    spec = dict(P.dense20_spec(3, rng), kwargs=dict(abstol=1e-9, reltol=1e-8))
+    assert_ok(full_compare(spec, cb.Tsit5(adaptive=True), 3, rng, objective_row=3))
 
 
 @pytest.mark.parametrize("name", ["vdp", "fuller", "hangglider", "ductedfan", "discrete_oed"])

@@ -154,6 +154,20 @@ def test_dense20_parity_small():
     assert_ok(full_compare(spec, cb.Tsit5(2), 3, rng, objective_row=1, check_traj=False))
 
 
+@pytest.mark.parametrize("nx", [16, 24, 32])
+@pytest.mark.parametrize("method", ["tsit5", "rk4"])
+def test_dense_family_on_the_tensor_path(nx, method):
+    """the dense family x' = W x - x^3 + b u at the other sizes the FP64 tensor-path kernel is instantiated for (lane
+    ownership S = nx/4 states: 4 -- no padding, 6, 8; 12 and 8 warps per block for 24 and 32): full parity, a batch that
+    is not a multiple of the 8-candidate item, more items than SMs"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(20261019 + nx)
+    spec = P.dense20_spec(5, rng, nx=nx)
+    alg = cb.Tsit5(2) if method == "tsit5" else cb.RK4(2)
+    assert_ok(full_compare(spec, alg, 3, rng, objective_row=2, check_traj=True))
+    assert_ok(full_compare(spec, alg, 261, rng, objective_row=nx, check_traj=False))
+
+
 def test_lotka_oed_fim_parity():
     """states-only integration of [x; G; F_triu]; FIM read-out (oed.jl:388-398) and its sum over candidates"""
     import corleone_b200 as cb
