@@ -149,6 +149,61 @@ def main():
             ok &= e1 < 1e-12 and e2 < 1e-12 and e3 == 0.0 and e4 == 0.0 and e5 <= 1e-12 * np.max(np.abs(sums)) and identical
             ok &= names.get(info["transport"]) == transport
     os.environ.pop("CB200_COMM_TRANSPORT", None)
+    # (5) the bench's N > 1 workload at FULL size (BASELINE config 5: 256 intervals x 4096 candidates of the dense 20-state
+    #     model = 2^20 units, candidates sharded over the ranks, fused all-reduce + all-gather): the reduced sums and the
+    #     gathered defect matrix against rank 0 evaluating the whole batch alone
+    if os.environ.get("CB200_CHECK_FULL", "1") != "0" and 4096 % world == 0:
+        from corleone_b200 import configs
+        import bench
+        spec = configs.config4_dense20(256)
+        lay, ps_t, st, N = configs.native_from_spec(spec, cb.Tsit5(2), device=local)
+        B_total = 4096
+        Bl, b0 = B_total // world, rank * (B_total // world)
+        full = bench.dense20_inputs_soa(torch, dev, cb.to_vec(ps_t), B_total, configs.SEED0 + 5)     # [nvars, B_total], same on every rank
+        d_ps = full[:, b0:b0 + Bl].contiguous()
+        ident = [nat.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        N.comm_init(world, rank, ident[0], max_B_total=B_total)
+        want = nat.WANT_SENS | nat.WANT_DEFECTS | nat.WANT_XEND | nat.WANT_OBJ | nat.WANT_GRAD
+        flags = nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA | nat.COMM_REDUCE | nat.COMM_GATHER
+        d_sums = torch.zeros(1 + N.nvars, dtype=torch.float64, device=dev)
+        d_x = torch.empty((N.nx * N.I, Bl), dtype=torch.float64, device=dev)
+        d_obj = torch.empty((1, Bl), dtype=torch.float64, device=dev)
+        N.set_stream(torch.cuda.current_stream().cuda_stream)
+        n_def = N.n_defects
+        gathered = torch.full((n_def, B_total), float("nan"), dtype=torch.float64, device=dev)
+        for _ in range(2):
+            N.eval_raw(d_ps.data_ptr(), Bl, Bl, want, flags,
+                       dict(xend=d_x.data_ptr(), objective=d_obj.data_ptr(), objective_sum=d_sums.data_ptr(), grad_sum=d_sums.data_ptr() + 8,
+                            defects_gathered=gathered.data_ptr()),
+                       1, resident=nat.WANT_SENS, comm_B_total=B_total, comm_b0=b0)
+        torch.cuda.synchronize()
+        gp, gld = N.comm_gathered()
+        assert gld == B_total and gp != 0
+        same = [torch.zeros_like(d_sums) for _ in range(world)]
+        dist.all_gather(same, d_sums)
+        identical = all(bool(torch.equal(t, same[0])) for t in same)
+        dist.barrier()
+        N.comm_destroy()
+        if rank == 0:
+            lay1, ps_t1, st1, N1 = configs.native_from_spec(spec, cb.Tsit5(2), device=local)
+            N1.set_stream(torch.cuda.current_stream().cuda_stream)
+            r_dk = torch.empty((n_def, B_total), dtype=torch.float64, device=dev)
+            r_sums = torch.zeros(1 + N1.nvars, dtype=torch.float64, device=dev)
+            r_obj = torch.empty((1, B_total), dtype=torch.float64, device=dev)
+            N1.eval_raw(full.data_ptr(), B_total, B_total, nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD, nat.MEM_DEVICE | nat.PS_SOA | nat.OUT_SOA,
+                        dict(defects_kind=r_dk.data_ptr(), objective=r_obj.data_ptr(), objective_sum=r_sums.data_ptr(),
+                             grad_sum=r_sums.data_ptr() + 8), 1)
+            torch.cuda.synchronize()
+            e_d = float((gathered - r_dk).abs().max().item())
+            rs, ss = r_sums.cpu().numpy(), d_sums.cpu().numpy()
+            e_o = abs(ss[0] - rs[0]) / abs(rs[0])
+            e_g = np.max(np.abs(ss[1:] - rs[1:])) / np.max(np.abs(rs[1:]))
+            e_l = float((d_obj - r_obj[:, b0:b0 + Bl]).abs().max().item())
+            print(f"config 5 at full size (2^20 units) world={world}: gathered defects max abs diff {e_d:.1e}, objective_sum rel {e_o:.2e}, "
+                  f"grad_sum rel {e_g:.2e}, local objectives max abs diff {e_l:.1e}, sums bit-identical on all ranks: {identical}")
+            ok &= e_d == 0.0 and e_o < 1e-12 and e_g < 1e-12 and e_l == 0.0 and identical
+        del full
     if rank == 0:
         print("multi_gpu_check", "ok" if ok else "FAILED")
     dist.barrier()
