@@ -699,11 +699,13 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         if constexpr (G > 0 && TS) {
             if (o.tsens && live && j == 0) save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i), b, dmap, yd, yq);
         }
-        const int pse = __ldg(L.psamp + po + j);   // index of the piece's end sample within the interval
+        // (index of the piece's end sample within the interval: L.psamp[po + j], j + 1 without saveat -- loaded only where a
+        // sample is written, the common path carries no extra load)
         bool sampled = false;
         if constexpr (SV && METHOD != 1) {
             const int nsv = L.sv_n ? __ldg(L.sv_n + po + j) : 0;
             if (nsv > 0) {   // warp-uniform
+                const int pse = __ldg(L.psamp + po + j);
                 sampled = true;
                 PieceSampler<Mdl, G, TS> smp;
                 smp.L = &L;
@@ -745,10 +747,11 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
         }
         // save_end; the end sample of a non-final interval is dropped by the merge (multiple_shooting.jl:178-180)
         if (o.traj && live && r == 0 && (j + 1 < M || last_interval))
-            save_sample<Mdl>(L, o, (long long)(so + pse), nrow, b, yd, yq, p);
+            save_sample<Mdl>(L, o, (long long)(so + (SV ? __ldg(L.psamp + po + j) : j + 1)), nrow, b, yd, yq, p);
         if constexpr (G > 0 && TS) {
             if (o.tsens && live && (j + 1 < M || last_interval))
-                save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i) + (long long)pse * ns * NX, b, dmap, yd, yq);
+                save_sens_sample<Mdl, G>(o, __ldg(L.tsens_off + i) + (long long)(SV ? __ldg(L.psamp + po + j) : j + 1) * ns * NX, b,
+                                         dmap, yd, yq);
         }
     }
     // ---- results.  xs(k): end state component k (compile-time k)
