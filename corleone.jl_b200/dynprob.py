@@ -35,11 +35,9 @@ class CorleoneDynamicOptProblem:
         if loss not in self.sys.variables:
             raise KeyError(f"loss {loss!r} is not a trajectory variable: {sorted(self.sys.variables)}")
         self.loss_row = self.sys.variables[loss] + 1            # 1-based row of a trajectory sample
-        tpoints = []
-        for n, s in enumerate(sts):                              # piece starts of every interval + the final end
-            tsp = _flatten_chunks(s["tspans"])
-            tpoints += [a for a, _ in tsp] + ([tsp[-1][1]] if n == len(sts) - 1 else [])
-        self.tpoints = np.asarray(tpoints)                       # == traj.t of the merged trajectory
+        self.nat = layer._native(self.st, self.ps0)
+        # traj.t of the merged trajectory: piece starts of every interval (and saveat times inside pieces) + the final end
+        self.tpoints = self.nat.sample_times()
         self.point = []                                          # (row 0-based, sample indices 0-based)
         lb, ub = [], []
         for expr, specs in constraints:
@@ -59,7 +57,6 @@ class CorleoneDynamicOptProblem:
             self.lcons, self.ucons = np.concatenate(lb), np.concatenate(ub)
         else:
             self.lcons = self.ucons = None
-        self.nat = layer._native(self.st, self.ps0)
         self.u0 = to_vec(self.ps0)
         blo, bhi = get_bounds(layer)
         self.lb, self.ub = to_vec(blo), to_vec(bhi)
@@ -76,7 +73,9 @@ class CorleoneDynamicOptProblem:
             want |= native.WANT_GRAD | native.WANT_JAC
             if self.point:
                 want |= native.WANT_TRAJ_SENS | native.WANT_SENS
-        return self.nat.eval_host(X, want, objective_row=self.loss_row)
+        r = self.nat.eval_host(X, want, objective_row=self.loss_row)
+        native.check_status(r, "CorleoneDynamicOptProblem")   # a failed integration must not reach the optimiser as NaN
+        return r
 
     def _cons_from(self, r, b):
         parts = []

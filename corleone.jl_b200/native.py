@@ -80,6 +80,23 @@ class NativeError(RuntimeError):
     pass
 
 
+class IntegrationFailure(RuntimeError):
+    """Some candidates could not be integrated (cb200_out.status: a non-finite end state; in the adaptive mode also
+    OrdinaryDiffEq's MaxIters / DtLessThanMin / Unstable).  The reference never inspects the solver's return code and would
+    hand NaN objectives, gradients and Jacobians to the optimiser; the host mirror refuses instead."""
+
+    def __init__(self, where, bad):
+        self.candidates = bad
+        super().__init__(f"{where}: the integration failed for candidate(s) {bad[:8].tolist()}"
+                         f"{' ...' if len(bad) > 8 else ''} (status flags set; non-finite or diverging trajectory)")
+
+
+def check_status(result, where="cb200_eval"):
+    st = result.get("status")
+    if st is not None and np.any(st):
+        raise IntegrationFailure(where, np.nonzero(np.asarray(st).ravel())[0])
+
+
 def lib():
     """Load libcorleone_b200.so; raises if it has not been built (python corleone.jl_b200/build.py)."""
     global _lib

@@ -180,6 +180,7 @@ class OEDLayer:
         X = np.atleast_2d(np.asarray(X, dtype=np.float64))
         want = native.WANT_FIM | (native.WANT_CRIT if criteria else 0)
         r = nat.eval_host(X, want, fim_init=first["F_init"] if add_initial else None)
+        native.check_status(r, "OEDLayer.fisher_information")
         F = r["fim"].reshape(X.shape[0], self.n_fisher, self.n_fisher)
         return (F, r["criteria"]) if criteria else F
 

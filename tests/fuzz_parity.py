@@ -20,7 +20,13 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))   # lives with the tests: it use
 
 def random_spec(rng):
     import problems as P
-    kind = rng.choice(["lotka3", "lqr", "lotka2", "bench", "bench", "oed"])
+    kind = rng.choice(["lotka3", "lqr", "lotka2", "bench", "bench", "oed", "dense"])
+    if kind == "dense":   # the dense family on the tensor-path kernel: every size it is instantiated for
+        nx = int(rng.choice([16, 20, 24, 32]))
+        spec = P.dense20_spec(int(rng.integers(1, 5)), rng, nx=nx)
+        if len(spec["shooting_points"]) == 1:
+            spec["shooting_points"] = None
+        return f"dense{nx}", spec, int(rng.integers(1, nx + 1)), 0.05
     if kind == "bench":
         name = str(rng.choice(sorted(P.BENCH_TABLE)))
         spec, row, scale = P.bench_spec(name, int(rng.integers(1, 5)), rng)
@@ -54,6 +60,8 @@ def random_spec(rng):
         spec = dict(model="lotka3", u0=[0.5, 0.7, 0.0], p0=[0.0, 1.0, 1.0], tspan=(0.0, T),
                     controls=[(1, grid, rng.uniform(0, 1, len(grid)))], tunable_ic=tic,
                     quadrature_indices=[3] if quad else [], shooting_points=sp)
+        if rng.integers(0, 2):   # saveat times inside pieces: samples from Tsit5's dense output (dropped again for RK4 in main)
+            spec["saveat"] = list(np.unique(np.round(np.sort(rng.uniform(0.0, T, int(rng.integers(1, 30)))), 3)))
         return "lotka3", spec, 3, 0.05
     if kind == "lqr":
         spec = dict(model="lqr", u0=[1.0, 0.0], p0=[-1.0, 1.0, 0.0], tspan=(0.0, T),
@@ -63,6 +71,8 @@ def random_spec(rng):
     spec = dict(model="lotka2", u0=[0.5, 0.7], p0=[0.0, 1.0, 1.0], tspan=(0.0, T),
                 controls=[(1, grid, rng.uniform(0, 1, len(grid)))], tunable_ic=[1, 2] if rng.integers(0, 2) else [],
                 quadrature_indices=[], shooting_points=sp)
+    if rng.integers(0, 2):
+        spec["saveat"] = list(np.unique(np.round(np.sort(rng.uniform(0.0, T, int(rng.integers(1, 30)))), 3)))
     return "lotka2", spec, int(rng.integers(1, 3)), 0.05
 
 
@@ -126,6 +136,10 @@ def main():
         name, spec, row, scale = random_spec(rng)
         m = int(rng.integers(0, 3))
         alg = [cb.Tsit5(int(rng.integers(1, 5))), cb.RK4(int(rng.integers(2, 6))), cb.Tsit5(adaptive=True)][m]
+        if m == 2 and name.startswith("dense") and name != "dense20":
+            m, alg = 0, cb.Tsit5(2)          # the adaptive mode of the dense family is built for the 20-state model only
+        if m == 1 and "saveat" in spec:
+            spec = {k: v for k, v in spec.items() if k != "saveat"}     # RK4 has no dense output: refused by cb200_create
         if m == 2:
             tol = float(10.0 ** rng.uniform(-9, -4))
             spec = dict(spec, kwargs=dict(abstol=tol * 1e-2, reltol=tol))
@@ -163,7 +177,8 @@ def main():
         if not e <= 1e-10:
             bad.append((c, name, errs))
         tag = ['tsit5', 'rk4', 'adaptive'][m] + (f"({spec['kwargs']['reltol']:.0e})" if m == 2 else "")
-        print(f"case {c:3d} {name:18s} I={O.I} nvars={O.nvars:4d} B={B:3d} method={tag:15s} max err {e:.2e}", flush=True)
+        tag += " saveat" if "saveat" in spec else ""
+        print(f"case {c:3d} {name:18s} I={O.I} nvars={O.nvars:4d} B={B:3d} method={tag:22s} max err {e:.2e}", flush=True)
     print(f"fuzz_parity: {a.cases} cases, worst {worst:.2e} (scaled to the 1e-10 bound), {len(bad)} above their bound, {time.time() - t0:.0f} s")
     for b in bad:
         print("  BAD", b)

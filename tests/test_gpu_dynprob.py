@@ -158,3 +158,32 @@ def test_lotka_oed_design_optimum_in_the_default_adaptive_mode():
     Fgold = np.array([[38.58695777364362, 5.304118558316029], [5.304118558316029, 92.03122059902915]])
     assert np.allclose(res.fim, Fgold, rtol=1e-5), res.fim
     assert np.all(A @ res.x <= 4.0 + 1e-8)
+
+
+def test_a_failed_integration_is_reported_not_handed_to_the_optimiser():
+    """the reference never inspects the solver's return code: a diverging candidate would reach the NLP solver as NaN
+    objective / constraints / Jacobian.  The host mirror checks the device's status flags and refuses."""
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    lay = _lotka_layer(cb, [0.0, 3.0, 6.0, 9.0], 8, bounds_ic=([0.1, 0.1, 0.0], [100.0, 100.0, 100.0]))
+    prob = cb.CorleoneDynamicOptProblem(lay, "x₃")
+    assert np.isfinite(prob.objective(prob.u0))
+    bad = prob.u0.copy()
+    bad[3] = 1e200                      # a node value: x' ~ -x y overflows at once
+    with pytest.raises(nat.IntegrationFailure, match="candidate"):
+        prob.objective(bad)
+    with pytest.raises(nat.IntegrationFailure):
+        prob.constraints(bad)
+    # the OED read-out checks the same flags
+    from corleone_b200 import oed as oedm
+    base = cb.SingleShootingLayer(cb.ODEProblem("lotka2", [0.5, 0.7], (0.0, 12.0), [0.0, 1.0, 1.0]), cb.Tsit5(4),
+                                  controls=[(1, cb.ControlParameter(0.25 * np.arange(48), name="fishing", bounds=(0.0, 1.0)))],
+                                  bounds_p=([1.0, 1.0],) * 2)
+    o = oedm.OEDLayer(base, False)
+    ps, st = o.setup(None)
+    X = np.tile(cb.to_vec(ps), (3, 1))
+    assert np.isfinite(o.fisher_information(X, ps, st)).all()
+    X[1, 0] = np.nan
+    with pytest.raises(nat.IntegrationFailure) as e:
+        o.fisher_information(X, ps, st)
+    assert list(e.value.candidates) == [1]
