@@ -31,6 +31,6 @@ int dense20_set_data(const double *host_data, long long n)
 int forward_dense20(int method, const DevLayer &L, double *ps, long long ldb, long long B, const unsigned char *fixed,
         cudaStream_t s)
 {
-    return launch_forward<DenseN<20>>(method, L, ps, ldb, B, fixed, s);
+    return launch_forward<DenseN<20>, true>(method, L, ps, ldb, B, fixed, s);
 }
 }  // namespace cb200

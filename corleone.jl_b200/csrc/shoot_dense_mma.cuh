@@ -425,7 +425,8 @@ shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *_
     const int per = nst * DQ_CPI * NX;
     const unsigned nk = n_items > blockIdx.x ? (unsigned)((n_items - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0u;
     const unsigned la = (unsigned)nring - 1u, row = (unsigned)n_tiles + 1u;
-    const unsigned px = (unsigned)min(nring == 3 ? 16 : 8, n_tiles);
+    // (nring == 1, layers with very many stages: no look-ahead, the x task of an item opens its row)
+    const unsigned px = nring == 1 ? 0u : (unsigned)min(nring == 3 ? 16 : 8, n_tiles);
     const unsigned n_tasks = la + nk * row;
     DenseTile<NX> T;
     dense_load_w(L, T);
@@ -498,8 +499,8 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
     static const bool lockstep = getenv("CB200_DENSE20_LOCKSTEP") != nullptr;
     static const int nring_env = getenv("CB200_DENSE20_NRING") ? atoi(getenv("CB200_DENSE20_NRING")) : 0;
     const size_t smem_cap = 225 * 1024;
-    int nring = (nring_env == 2 || nring_env == 3) ? nring_env : 3;
-    if (nring == 3 && 3 * per > smem_cap) nring = 2;
+    int nring = (nring_env >= 1 && nring_env <= 3) ? nring_env : 3;
+    while (nring > 1 && nring * per > smem_cap) nring--;
     if (!lockstep && nring * per <= smem_cap) {
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
@@ -520,7 +521,7 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
         }
         return (int)cudaGetLastError();
     }
-    if constexpr (NX <= 20) {   // lockstep fallback (stage count beyond the ring): 16 warps x 128 registers
+    {   // lockstep fallback (stage count beyond even one ring slot): 16 warps x 128 registers -- spills beyond nx = 20
         const long long gx = (B + DM_CPB - 1) / DM_CPB;
         const int rounds = (max_ns + DM_DPR - 1) / DM_DPR;
         if (gx > 2147483647LL || L.In > 65535 || rounds > 65535) return -1000;
@@ -538,7 +539,6 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
         }
         return (int)cudaGetLastError();
     }
-    return -1000;
 }
 
 }  // namespace cb200

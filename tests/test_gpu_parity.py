@@ -168,6 +168,17 @@ def test_dense_family_on_the_tensor_path(nx, method):
     assert_ok(full_compare(spec, alg, 261, rng, objective_row=nx, check_traj=False))
 
 
+@pytest.mark.parametrize("nx,alg_name,K", [(32, "rk4", 5), (32, "tsit5", 5), (24, "tsit5", 4), (20, "tsit5", 8)])
+def test_dense_family_with_many_stages_per_interval(nx, alg_name, K):
+    """layers whose stage count does not fit three ring slots of the tile-queue kernel: two slots, one slot (no look-ahead),
+    and beyond that the lockstep kernel -- the same results"""
+    import corleone_b200 as cb
+    rng = np.random.default_rng(7 * nx + K)
+    spec = P.dense20_spec(3, rng, nx=nx)
+    alg = cb.Tsit5(K) if alg_name == "tsit5" else cb.RK4(K)
+    assert_ok(full_compare(spec, alg, 19, rng, objective_row=1, check_traj=True))
+
+
 def test_lotka_oed_fim_parity():
     """states-only integration of [x; G; F_triu]; FIM read-out (oed.jl:388-398) and its sum over candidates"""
     import corleone_b200 as cb
