@@ -358,6 +358,15 @@ def run_config2(args, torch, dev, local_rank, steps, rank=0):
     # the consumer that factorises cons_j on the device: only f, c and the compact gradient cross PCIe
     slim = ("defects_kind", "objective", "grad_compact")
     dt_slim = time_host(lambda: host_eval(nat.WANT_JAC, slim))
+    # the consumer of the cross-candidate sums only: every per-candidate result stays in HBM
+    h_sums = np.zeros(1 + nvars)
+
+    def sums_eval():
+        N.eval_raw(pin_ps.data_ptr(), B, nvars, want | nat.WANT_GRAD, 0,
+                   {"objective_sum": h_sums.ctypes.data, "grad_sum": h_sums.ctypes.data + 8}, 2,
+                   resident=nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD_COMPACT | nat.WANT_GRAD)
+
+    dt_sums = time_host(sums_eval)
     out = {"workload": "lqr_ms100_b4096", "units_per_step": units, "value": units * steps / (ms_total * 1e-3), "unit": "units/s",
            "ms_per_step": ms_total / steps, "kernel_ms": kern_ms, "steps": steps,
            "l2": f"inputs larger than L2: {nsets} rotating buffer sets of {set_bytes / 1e6:.0f} MB",
@@ -368,6 +377,10 @@ def run_config2(args, torch, dev, local_rank, steps, rank=0):
                                 "d2h_bytes_per_step": 8 * B * sum(sz[f] for f in slim), "steps": e2e_steps,
                                 "ms_per_step": 1e3 * dt_slim,
                                 "api": "the same with cons_j kept on the device (cb200_out.resident = CB200_WANT_JAC)"},
+           "e2e_sums_only": {"value": units / dt_sums, "unit": "units/s", "h2d_bytes_per_step": 8 * B * nvars,
+                             "d2h_bytes_per_step": 8 * (1 + nvars), "steps": e2e_steps, "ms_per_step": 1e3 * dt_sums,
+                             "api": "the same with every per-candidate result device-resident; objective_sum and grad_sum "
+                                    "(6.4 KB) return to the host"},
            "gpu_launches": launches, "_N": N, "_spec": spec, "_ps_host": ps_host}
     return out
 
@@ -529,7 +542,7 @@ def run_reference(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": "units/s", "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps, "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": dense20_config(workload, n_gpu_candidates, args.gpus, sample=sample),
+        "config": dense20_config(workload, n_gpu_candidates, args.gpus),   # identical to our arm's `config`
         "cpu_baseline": {"value": value, "unit": "units/s", "cores": nthreads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "units/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -655,9 +668,10 @@ def run_scale(args, torch, dist, dev, world, rank, local_rank):
             "metric": METRIC, "value": value, "unit": "units/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": dense20_config("scale_1M", B_total, world, candidates_per_gpu=B, transport=tmap[info["transport"]],
-                                     collectives_checked={"reduced_sums_identical_on_all_ranks": sums_identical,
-                                                          "gather_leading_dimension": gld}),
+            "config": dense20_config("scale_1M", B_total, world),
+            "config_details": {"candidates_per_gpu": B, "transport": tmap[info["transport"]],
+                               "collectives_checked": {"reduced_sums_identical_on_all_ranks": sums_identical,
+                                                       "gather_leading_dimension": gld}},
             "e2e": e2e, "gpu_launches": int(launches), "clocks": clocks,
             "roofline": roofline_entry(WORK["dense20"], I * B, kern_ms, peak, peak_src, hbm_peak, hbm_src,
                                        "shoot_dense_mma_queue_kernel<Tsit5,uniform,16 warps> (FP64 tensor path) incl. fused defect all-gather "
@@ -708,10 +722,38 @@ def run_config2_weak(args, torch, dist, dev, world, rank, local_rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
     barrier()
+    # ---- e2e of the consumer that needs only the sums across all ranks (an expectation-type objective and its gradient):
+    # every rank feeds its 4096 candidates from pinned host memory, f / c / cons_j / the per-candidate gradients stay in HBM
+    # (cb200_out.resident), the all-reduced sums (6.4 KB) come back to the host
+    pin_ps = torch.from_numpy(ps_host).pin_memory()
+    h_sums = np.zeros(1 + nvars)
+    hp = {"objective_sum": h_sums.ctypes.data, "grad_sum": h_sums.ctypes.data + 8}
+    res_bits = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD_COMPACT | nat.WANT_GRAD
+    e2e_steps = 10
+
+    def host_eval():
+        N.eval_raw(pin_ps.data_ptr(), B, nvars, want, nat.COMM_REDUCE, hp, 2, resident=res_bits)
+
+    for _ in range(3):
+        host_eval()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        host_eval()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    t = torch.tensor([dt], dtype=torch.float64, device=dev)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dt = float(t.item())
+    barrier()
     N.comm_destroy()
     return {"workload": "lqr_ms100_b4096 per GPU (weak scaling, round 1's bench)", "value": I * B * world * steps / (ms_total * 1e-3),
             "unit": "units/s", "ms_per_step": ms_total / steps, "steps": steps,
-            "collective": "all-reduce of (objective_sum, grad_sum) fused into the tail of the objective kernel"}
+            "collective": "all-reduce of (objective_sum, grad_sum) fused into the tail of the objective kernel",
+            "e2e_sums_only": {"value": I * B * world * e2e_steps / dt, "unit": "units/s", "ms_per_step": 1e3 * dt / e2e_steps,
+                              "h2d_bytes_per_step": 8 * B * nvars * world, "d2h_bytes_per_step": 8 * (1 + nvars) * world,
+                              "api": "cb200_eval with pinned host candidates per rank + CB200_COMM_REDUCE; every per-candidate "
+                                     "result stays device-resident, the all-reduced sums return to the host"}}
 
 
 # ================================================================================================== main
@@ -769,7 +811,8 @@ def main():
             line = {"metric": METRIC, "value": c4["value"], "unit": "units/s", "n_gpus": 1, "steps": args.steps,
                     "warmup": max(3, args.warmup), "ms_per_step": c4["ms_per_step"], "higher_is_better": True,
                     "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                    "config": dense20_config(c4["workload"], args.candidates, 1, chunking=c4["chunking"], outputs=c4["outputs"]),
+                    "config": dense20_config(c4["workload"], args.candidates, 1),
+                    "config_details": {"chunking": c4["chunking"], "outputs": c4["outputs"]},
                     "e2e": c4["e2e"], "gpu_launches": int(c4["_launches_timed"]),
                     "clocks": clocks, "roofline": c4["roofline"]}
             if not args.no_cpu_baseline:

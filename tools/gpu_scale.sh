@@ -17,8 +17,8 @@ for n in $ns; do
 import json
 try:
     d=json.loads(open("gpurun_out/bench_${tag}_n$n.json").read().strip().splitlines()[-1])
-    print("N=%d value %.4g units/s  ms/step %.3f  kernel_ms %.3f  frac %.3f  e2e %.4g  transport %s  clocks %s" % (d["n_gpus"], d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["e2e"]["value"], d["config"]["transport"][:8], d["clocks"]["sm_mhz"]))
-    if d.get("secondary"): print("   secondary", d["secondary"]["workload"][:40], "%.4g" % d["secondary"]["value"])
+    print("N=%d value %.4g units/s  ms/step %.3f  kernel_ms %.3f  frac %.3f  e2e %.4g  transport %s  clocks %s" % (d["n_gpus"], d["value"], d["ms_per_step"], d["roofline"]["kernel_ms"], d["roofline"]["frac"], d["e2e"]["value"], d["config_details"]["transport"][:8], d["clocks"]["sm_mhz"]))
+    if d.get("secondary"): print("   secondary", d["secondary"]["workload"][:40], "%.4g" % d["secondary"]["value"], "e2e sums only %.4g" % d["secondary"]["e2e_sums_only"]["value"])
 except Exception as e:
     print("no line", e); print(open("gpurun_out/bench_${tag}_n$n.err").read()[-1500:])
 PY
