@@ -682,22 +682,31 @@ def run_scale(args, torch, dist, dev, world, rank, local_rank):
 
 
 def run_config2_weak(args, torch, dist, dev, world, rank, local_rank):
+    """round 1's workload: config 2, 4096 candidates per GPU, sums all-reduced by the fused tail.  A 0.12 ms evaluation is
+    short against the exchange's synchronisation (7-20 us: flags over NVLink + the slowest of N GPUs), so the batch consumer
+    keeps TWO evaluations in flight -- two handles of the layer on two streams, each with its own communicator: the tail of
+    evaluation k waits for its peers while the shooting kernel of evaluation k+1 runs"""
     from corleone_b200 import Tsit5, configs, native as nat, to_vec
     I, B, K = 100, 4096, 2
     spec = configs.config2_lqr()
-    lay, ps_t, st, N = configs.native_from_spec(spec, Tsit5(K), device=local_rank)
-    nvars = N.nvars
     rng = np.random.default_rng(configs.SEED0 + 2 + 1000 * rank)
+    streams = [torch.cuda.current_stream(), torch.cuda.Stream(device=dev)]
+    Ns = []
+    for q in range(2):
+        lay, ps_t, st, Nq = configs.native_from_spec(spec, Tsit5(K), device=local_rank)
+        Nq.set_stream(streams[q].cuda_stream)
+        ident = [nat.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(ident, src=0)
+        Nq.comm_init(world, rank, ident[0], max_B_total=0)
+        Ns.append(Nq)
+    N = Ns[0]
+    nvars = N.nvars
     ps_host = lqr_inputs(nvars, to_vec(ps_t), B, rng)
-    stream = torch.cuda.current_stream()
-    N.set_stream(stream.cuda_stream)
-    ident = [nat.comm_unique_id() if rank == 0 else None]
-    dist.broadcast_object_list(ident, src=0)
-    N.comm_init(world, rank, ident[0], max_B_total=0)
+    stream = streams[0]
     sz = N.out_sizes()
     fields = ("jac_vals", "defects_kind", "objective", "grad_compact")
     sz["grad_compact"] = N.grad_structure(2)[1]
-    nsets = 5
+    nsets = 6
     d_ps = [torch.from_numpy(np.ascontiguousarray(np.roll(ps_host, s, axis=0).T)).to(dev) for s in range(nsets)]
     d_out = [{f: torch.empty((sz[f], B), dtype=torch.float64, device=dev) for f in fields} for _ in range(nsets)]
     d_sums = [torch.zeros(nvars + 1, dtype=torch.float64, device=dev) for _ in range(nsets)]
@@ -709,7 +718,7 @@ def run_config2_weak(args, torch, dist, dev, world, rank, local_rank):
         ptrs = {f: d_out[k][f].data_ptr() for f in fields}
         ptrs["objective_sum"] = d_sums[k].data_ptr()
         ptrs["grad_sum"] = d_sums[k].data_ptr() + 8
-        N.eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, 2)
+        Ns[s % 2].eval_raw(d_ps[k].data_ptr(), B, B, want, flags, ptrs, 2)
 
     def barrier():
         torch.cuda.synchronize()
@@ -717,10 +726,29 @@ def run_config2_weak(args, torch, dist, dev, world, rank, local_rank):
         torch.cuda.synchronize()
 
     steps = max(20, args.steps)
-    ms_total, _ = timed_steps(torch, stream, step, steps, 5, barrier)
+    steps += steps % 2
+    for s_ in range(6):
+        step(s_)
+    barrier()
+    e0, e1, ej = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+    e0.record(streams[0])
+    streams[1].wait_event(e0)
+    for s_ in range(steps):
+        step(s_)
+    ej.record(streams[1])
+    streams[0].wait_event(ej)
+    e1.record(streams[0])
+    barrier()
+    ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_total = float(t.item())
+    # the sums of the last evaluations are the same on every rank
+    chk = d_sums[(steps - 1) % nsets][:4].clone()
+    lo, hi = chk.clone(), chk.clone()
+    dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+    dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+    sums_identical = bool(torch.equal(lo, hi))
     barrier()
     # ---- e2e of the consumer that needs only the sums across all ranks (an expectation-type objective and its gradient):
     # every rank feeds its 4096 candidates from pinned host memory, f / c / cons_j / the per-candidate gradients stay in HBM
@@ -746,10 +774,13 @@ def run_config2_weak(args, torch, dist, dev, world, rank, local_rank):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dt = float(t.item())
     barrier()
-    N.comm_destroy()
+    for Nq in Ns:
+        Nq.comm_destroy()
     return {"workload": "lqr_ms100_b4096 per GPU (weak scaling, round 1's bench)", "value": I * B * world * steps / (ms_total * 1e-3),
             "unit": "units/s", "ms_per_step": ms_total / steps, "steps": steps,
-            "collective": "all-reduce of (objective_sum, grad_sum) fused into the tail of the objective kernel",
+            "collective": "all-reduce of (objective_sum, grad_sum) fused into the tail of the objective kernel; two evaluations in "
+                          "flight (two handles on two streams): the exchange of one overlaps the shooting kernel of the next",
+            "reduced_sums_identical_on_all_ranks": sums_identical,
             "e2e_sums_only": {"value": I * B * world * e2e_steps / dt, "unit": "units/s", "ms_per_step": 1e3 * dt / e2e_steps,
                               "h2d_bytes_per_step": 8 * B * nvars * world, "d2h_bytes_per_step": 8 * (1 + nvars) * world,
                               "api": "cb200_eval with pinned host candidates per rank + CB200_COMM_REDUCE; every per-candidate "

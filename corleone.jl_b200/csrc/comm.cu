@@ -482,6 +482,10 @@ int comm_begin(cb200_handle *h, bool reduce, bool gather, long long B, long long
         tail->peers = c->dp;
         tail->exchange = reduce ? 1 : 0;
         tail->barrier = 1;   // every collective evaluation closes its epoch: keeps the ranks within one epoch of each other
+        // measurement knobs (tools/gpu_tail_probe.sh): what the tail costs without the exchange / without any peer traffic
+        static const int probe = getenv("CB200_TAIL_PROBE") ? atoi(getenv("CB200_TAIL_PROBE")) : 0;
+        if (probe == 1) tail->exchange = 0;                       // flags only
+        if (probe == 2) { tail->exchange = 0; tail->barrier = 0; }   // local tail (results are NOT reduced: timing only)
         if (gather) {
             *dk_local = (double *)c->gat + par * c->gat_cap + b0;
             so->ldk = B_total;
