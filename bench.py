@@ -111,7 +111,7 @@ class ClockSampler:
     def __enter__(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.index)], stdout=subprocess.PIPE,
+                                          "-lms", "50", "-i", str(self.index)], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._read, daemon=True)
             self.thr.start()
@@ -609,6 +609,11 @@ def run_scale(args, torch, dist, dev, world, rank, local_rank):
         t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
+        # the timed region is tens of milliseconds at N = 8: keep the same workload running (untimed, the same number of
+        # steps on every rank) until nvidia-smi has sampled the clocks under it
+        for _ in range(max(0, int(np.ceil(400.0 / max(ms_total / args.steps, 1e-3))) - args.steps)):
+            step(0)
+        barrier()
         clocks = clk.summary()
     units = I * B_total
     value = units * args.steps / (ms_total * 1e-3)
