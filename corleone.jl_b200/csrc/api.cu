@@ -1259,6 +1259,13 @@ struct EvalPlan {
     bool fused_fim;             // the shooting kernel does the Fisher read-out itself (OED models, FIM_END)
     bool reduce, gather;        // CB200_COMM_REDUCE / CB200_COMM_GATHER
     long long B_total, b0;      // all-gather: candidates of all ranks, this rank's first
+    // small evaluation as ONE kernel (shoot.cuh small_tail): the shooting kernel's last block computes the objective and
+    // copies the result block [st_src, st_src + st_n) to the caller's pinned mirror st_dst.  eval_core clears `fuse_small`
+    // when the model has no such kernel and runs the usual pipeline
+    mutable bool fuse_small;
+    const double *st_src;
+    double *st_dst;
+    int st_n;
 };
 
 // where the kind-major defects of one batch (or chunk) go: the compact block of the evaluation, or this rank's columns
@@ -1364,15 +1371,34 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     }
     const int ev_slot = (int)(h->n_timed % cb200_handle::EV_RING);
     CUDA_TRY(cudaEventRecord(h->ev0[ev_slot], st));
-    int rc = -1000;
-    if (G > 1 && B < 32 && h->act_mask1 && !h->no_g1) {   // latency-bound: one direction per thread, if the model has that kernel
-        DevLayer L1 = L;
-        L1.R = std::max(1, h->max_ns);
-        L1.act_mask = h->act_mask1;
-        rc = launch_model(h->model, 1, h->method, L1, d_ps, d_ldb, B, so, st);
-        if (rc == -1000) h->no_g1 = true;
+    auto launch = [&](const ShootOut &so_) {
+        int r_ = -1000;
+        if (G > 1 && B < 32 && h->act_mask1 && !h->no_g1) {   // latency-bound: one direction per thread, if the model has that kernel
+            DevLayer L1 = L;
+            L1.R = std::max(1, h->max_ns);
+            L1.act_mask = h->act_mask1;
+            r_ = launch_model(h->model, 1, h->method, L1, d_ps, d_ldb, B, so_, st);
+            if (r_ == -1000) h->no_g1 = true;
+        }
+        if (r_ == -1000) r_ = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so_, st);
+        return r_;
+    };
+    if (pl.fuse_small && !h->no_small_tail) {
+        so.st_counter = h->tail_counter;
+        so.st_obj = ((pl.obj) && pl.obj_state >= 0) ? d.obj : nullptr;
+        so.st_src = pl.st_src;
+        so.st_dst = pl.st_dst;
+        so.st_n = pl.st_n;
+    } else {
+        pl.fuse_small = false;
     }
-    if (rc == -1000) rc = launch_model(h->model, G, h->method, L, d_ps, d_ldb, B, so, st);
+    int rc = launch(so);
+    if (rc == -1001) {   // the model has no kernel with the small-evaluation tail: the usual pipeline
+        h->no_small_tail = true;
+        pl.fuse_small = false;
+        so.st_counter = nullptr;
+        rc = launch(so);
+    }
     if (rc == -1000)
         return fail(CB200_ERR_UNSUPPORTED, "model %d: no kernel for %d directions/thread, method %d", h->model, G,
                     h->method);
@@ -1413,7 +1439,9 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
                                                            h->d_obs_sample, h->d_obs_var, d.finit, d.fim, ldo, d.fsum, d.crit, ta);
         h->launches++;
     }
-    if ((pl.obj || pl.osum) && !run_obj) {
+    if (pl.fuse_small) {
+        // objective and copy-out were the shooting kernel's tail
+    } else if ((pl.obj || pl.osum) && !run_obj) {
         if (d.obj) CUDA_TRY(cudaMemsetAsync(d.obj, 0, sizeof(double) * (size_t)B, st));
     } else if (run_obj) {
         objective_kernel<<<nblk(B, 256), 256, 0, st>>>(d.objq, ldo, d_ps, d_ldb, B, I, pl.obj_state >= 0, pl.obj_quad,
@@ -1731,7 +1759,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
         const size_t status_doubles = out->status ? ((size_t)B * sizeof(int) + sizeof(double) - 1) / sizeof(double) : 0;
         const size_t tot = sizeof(double) * (out_doubles + sums_doubles + in_doubles + status_doubles);
         if (ps_soa && out_soa && ldb == B && tot <= cb200_handle::PIN_BYTES) {
-            if (!h->pin) CUDA_TRY(cudaHostAlloc(&h->pin, cb200_handle::PIN_BYTES, cudaHostAllocDefault));
+            if (!h->pin) CUDA_TRY(cudaHostAlloc(&h->pin, cb200_handle::PIN_BYTES, cudaHostAllocMapped | cudaHostAllocPortable));   // the small-evaluation tail writes it from the device
             if (h->ws_small.reserve(tot)) return fail(CB200_ERR_NOMEM, "device out of memory");
             double *hp = (double *)h->pin, *dp = (double *)h->ws_small.p;
             // layout (doubles): [inputs | status ints (zeroed on the host: they travel with the inputs) | results ... | sums]
@@ -1759,6 +1787,15 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
             rc = plan_tail(dst_o, dst_g, dst_f);
             if (rc) return rc;
             const size_t back = sizeof(double) * (off - in_doubles);
+            // one kernel instead of kernel + objective kernel + copy node when the pipeline is just those: a few candidates
+            // (flat launch), a state row as objective (or none), no cross-candidate sums, no read-out / quadrature kernels
+            pl.fuse_small = !collective && !partial && B < 32 && sums_doubles == 0 && !any_fim && !pl.tsens &&
+                            !(pl.need_traj && h->nquad > 0 && I > 1) && !((pl.grad || pl.gsum) && !pl.fused_grad) &&
+                            (!(pl.obj || pl.osum) || pl.obj_state >= 0) && h->method != CB200_TSIT5_ADAPTIVE && !h->has_saveat &&
+                            back > 0 && back / sizeof(double) < (1u << 30) && !getenv("CB200_NO_SMALL_TAIL");
+            pl.st_src = dp + in_doubles;
+            pl.st_dst = hp + in_doubles;
+            pl.st_n = (int)(off - in_doubles);
             // the whole evaluation as one CUDA graph (captured once per shape of the request): a single launch instead
             // of two copies and two to four kernels -- the call is latency-bound (BASELINE config 1)
             SmallGraph *sg = nullptr;
@@ -1787,7 +1824,7 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
                     ce = cudaMemcpyAsync(dp, hp, sizeof(double) * (in_doubles + status_doubles), cudaMemcpyHostToDevice, h->stream);
                 if (ce == cudaSuccess) {
                     rc = eval_core(h, h->stream, in_doubles ? dp : nullptr, B, B, B, pl, d, &tail);
-                    if (rc == CB200_OK && back)
+                    if (rc == CB200_OK && back && !pl.fuse_small)   // (fused: the kernel's tail wrote the mirror itself)
                         ce = cudaMemcpyAsync(hp + in_doubles, dp + in_doubles, back, cudaMemcpyDeviceToHost, h->stream);
                 }
                 if (capture) {

@@ -125,6 +125,12 @@ struct ShootOut {
     double *crit;      // [6][ldo] or nullptr
     const double *finit;
     int fim_fused;     // 1: the kernel does the read-out
+    // small-evaluation tail (shoot.cuh small_tail): the last block computes the objective and copies the result block out
+    unsigned *st_counter;   // nullptr: the kernel carries no such tail
+    double *st_obj;         // [B] objective inside the result block, or nullptr
+    const double *st_src;   // device result block
+    double *st_dst;         // the caller's pinned mirror (device-accessible host memory)
+    int st_n;               // doubles to copy
 };
 
 // launchers, one per model translation unit; return cudaError_t as int, or -1000 if (G, method) is not

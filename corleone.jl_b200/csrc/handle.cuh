@@ -122,6 +122,7 @@ struct cb200_handle {
     int G_sens = 2;                   // sensitivity directions per thread
     const unsigned *act_mask1 = nullptr;   // DevLayer::act_mask for one direction per thread (flat launches), or nullptr
     bool no_g1 = false;               // the model has no G = 1 kernel
+    bool no_small_tail = false;       // the model has no kernel with the small-evaluation tail
     void *tables = nullptr;           // one device allocation holding every table
     int *d_quad = nullptr;
     GradEntry *d_grad = nullptr;      // gradient gather table of the cached objective row

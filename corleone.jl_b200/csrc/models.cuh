@@ -43,6 +43,17 @@ struct SaveAtTraits<M, decltype((void)M::SAVEAT, void())> {
     static constexpr bool ON = M::SAVEAT;
 };
 
+// SmallTailTraits<M>::ON: the shooting kernel is also built with the small-evaluation tail (one-kernel evaluations of a few
+// candidates) -- models that declare `static constexpr bool SMALL_TAIL = true`
+template <class M, class = void>
+struct SmallTailTraits {
+    static constexpr bool ON = false;
+};
+template <class M>
+struct SmallTailTraits<M, decltype((void)M::SMALL_TAIL, void())> {
+    static constexpr bool ON = M::SMALL_TAIL;
+};
+
 #ifdef CB200_NEED_DENSE20_DATA
 // model constants of the dense family (W row-major NX x NX, then b[NX]; NX <= 32) for the thread-per-unit kernels of the
 // including translation unit: constant-bank operands of the FMAs (one copy per translation unit = per NX)
@@ -52,6 +63,7 @@ static __constant__ double c_dense[32 * 32 + 32];
 // ---- Lotka-Volterra fishing with Lagrange state (examples/lotka_fishing_optimal_control/main.jl:38-42)
 struct Lotka3 {
     static constexpr int NX = 3, NXD = 2, NQ = 1, NP = 3;
+    static constexpr bool SMALL_TAIL = true;   // single-candidate evaluations are one kernel (shoot.cuh small_tail)
     static constexpr bool SAVEAT = true;   // also built with dense-output sampling (cb200_desc.saveat)
     static constexpr bool HAS_JVP = true;
     struct Ctx {
@@ -90,6 +102,7 @@ struct Lotka3 {
 // ---- Lotka-Volterra without the Lagrange state (lib/CorleoneOED/examples/lotka_oed/main.jl:61-65)
 struct Lotka2 {
     static constexpr int NX = 2, NXD = 2, NQ = 0, NP = 3;
+    static constexpr bool SMALL_TAIL = true;   // single-candidate evaluations are one kernel (shoot.cuh small_tail)
     static constexpr bool SAVEAT = true;   // also built with dense-output sampling (cb200_desc.saveat)
     static constexpr bool HAS_JVP = true;
     struct Ctx {
@@ -128,6 +141,7 @@ struct Lotka2 {
 // ---- linear-quadratic regulator (examples/linear_quadratic/main.jl:45-50), p = (a, b, u)
 struct Lqr {
     static constexpr int NX = 2, NXD = 1, NQ = 1, NP = 3;
+    static constexpr bool SMALL_TAIL = true;
     static constexpr bool HAS_JVP = true;
     struct Ctx {
         double j10;

@@ -539,9 +539,9 @@ __device__ __forceinline__ void save_sens_sample(const ShootOut &o, long long ro
 // TS: also store the sensitivities at every saved sample (WANT_TRAJ_SENS) -- a separate instantiation, so that the
 // common case keeps its register allocation and instruction schedule.
 // SV: the layer has saveat times inside pieces (instantiated for the models that ask for it, SaveAtTraits).
-template <class Mdl, int G, int METHOD, bool UNI, int MINB, bool TS, bool SV = false>
-__global__ void __launch_bounds__(128, MINB)
-shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B, const ShootOut o)
+template <class Mdl, int G, int METHOD, bool UNI, bool TS, bool SV>
+__device__ __forceinline__ void shoot_unit(const DevLayer &L, const double *__restrict__ ps, long long ldb, long long B,
+                                           const ShootOut &o)
 {
     constexpr int NX = Mdl::NX, NXD = Mdl::NXD, NQ = Mdl::NQ, NP = Mdl::NP;
     constexpr int ND = NXD * (1 + G), NQA = (NQ * (1 + G) > 0) ? NQ * (1 + G) : 1;
@@ -878,6 +878,50 @@ shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, 
 #undef CB200_SS
 }
 
+// Tail of a SMALL evaluation (a few candidates, flat launch; BASELINE config 1): the last block to finish computes the
+// objective (the ordered sum over the intervals, src/multiple_shooting.jl:171-177, src/dynprob.jl:70-71) and copies the whole
+// result block to the caller's pinned mirror -- the evaluation is ONE kernel instead of kernel + objective kernel + copy node
+// (tools/latency_micro.cu: 8.3 us around the kernel instead of 17.7).
+__device__ __forceinline__ void small_tail(const DevLayer &L, const ShootOut &o, long long B)
+{
+    __shared__ int is_last;
+    __threadfence();   // this thread's results are visible before the block is counted
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned total = gridDim.x * gridDim.y * gridDim.z;
+        const unsigned prev = atomicAdd(o.st_counter, 1u);
+        is_last = (prev == total - 1);
+        if (is_last) *o.st_counter = 0;   // zero at rest
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (o.st_obj) {
+        for (long long b = threadIdx.x; b < B; b += blockDim.x) {
+            double v;
+            if (o.obj_all) {
+                v = __ldcg(o.objq + b);
+                for (int i = 1; i < L.I; i++) v = __ldcg(o.objq + (long long)i * o.ldo + b) + v;
+            } else {
+                v = __ldcg(o.objq + (long long)(L.I - 1) * o.ldo + b);
+            }
+            o.st_obj[b] = v;
+        }
+        __syncthreads();
+    }
+    for (int j = threadIdx.x; j < o.st_n; j += blockDim.x) o.st_dst[j] = __ldcg(o.st_src + j);
+    __threadfence_system();
+}
+
+// FT: the kernel carries the small-evaluation tail (a separate instantiation: the throughput kernels stay as they are)
+template <class Mdl, int G, int METHOD, bool UNI, int MINB, bool TS, bool SV = false, bool FT = false>
+__global__ void __launch_bounds__(128, MINB)
+shoot_kernel(const __grid_constant__ DevLayer L, const double *__restrict__ ps, long long ldb, long long B, const ShootOut o)
+{
+    shoot_unit<Mdl, G, METHOD, UNI, TS, SV>(L, ps, ldb, B, o);
+    if constexpr (FT) small_tail(L, o, B);
+}
+
 // Forward initialisation sweep (src/node_initialization.jl:152-170): one thread per candidate walks the intervals
 // in order, overwrites the node values ps.interval_i.u0 with the leading entries of the previous interval's end
 // sample (unless the interval is listed in fixed_indices) and integrates on.  As in the reference the sweep calls
@@ -999,6 +1043,18 @@ int launch_one(const DevLayer &L, const double *ps, long long ldb, long long B, 
         grid = dim3((unsigned)((nthreads + bs - 1) / bs), 1, 1);
     else
         grid = dim3((unsigned)((B + bs - 1) / bs), (unsigned)L.In, (unsigned)L.R);
+    if (o.st_counter) {   // small evaluation with the fused tail: for the models that carry that instantiation
+        if constexpr (SmallTailTraits<Mdl>::ON && METHOD != 2) {
+            if (L.sv_n || o.tsens || !L2.flat) return -1001;
+            if (L.uniform_h)
+                shoot_kernel<Mdl, G, METHOD, true, 1, false, false, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            else
+                shoot_kernel<Mdl, G, METHOD, false, 1, false, false, true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);
+            return (int)cudaGetLastError();
+        } else {
+            return -1001;
+        }
+    }
     if (L.sv_n) {   // saveat samples inside pieces: the dense-output instantiation, for the models that carry one
         if constexpr (SaveAtTraits<Mdl>::ON && METHOD != 1) {
             shoot_kernel<Mdl, G, METHOD, false, 1, (G > 0), true><<<grid, bs, 0, s>>>(L2, ps, ldb, B, o);

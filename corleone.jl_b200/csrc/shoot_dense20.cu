@@ -8,6 +8,7 @@ namespace cb200 {
 int launch_dense20(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
         const ShootOut &o, cudaStream_t s)
 {
+    if (o.st_counter) return -1001;   // no kernel of this model carries the small-evaluation tail
     // adaptive mode (the reference's default `solve`; a fidelity path, not a throughput one): every unit picks its own
     // steps, so it runs on the generic kernel, one thread per (candidate, interval, direction)
     if (method == 2) {

@@ -8,6 +8,7 @@ namespace cb200 {
 int launch_dense32(int G, int method, const DevLayer &L, const double *ps, long long ldb, long long B,
         const ShootOut &o, cudaStream_t s)
 {
+    if (o.st_counter) return -1001;   // no kernel of this model carries the small-evaluation tail
     if (method == 2) return -1000;   // the adaptive mode of the dense family is built for the 20-state model only
     // with sensitivities: the tensor-path kernel (shoot_dense_mma.cuh); without, the generic kernel integrates x
     if (G > 0) return launch_dense_mma<32, 8>(method, L, ps, ldb, B, o, L.R * G, L.max_M, s);
