@@ -179,6 +179,46 @@ def test_dense_family_with_many_stages_per_interval(nx, alg_name, K):
     assert_ok(full_compare(spec, alg, 19, rng, objective_row=1, check_traj=True))
 
 
+@pytest.mark.parametrize("model", ["lotka3", "lqr"])
+@pytest.mark.parametrize("B", [1, 2, 7, 31])
+def test_small_evaluation_in_one_kernel_equals_the_pipeline(model, B):
+    """a few candidates through host pointers: the shooting kernel's last block computes the objective and copies the result
+    block out (small_tail) -- bit for bit what shooting kernel + objective kernel + copy node deliver, on repeated calls
+    (the captured graph is replayed) and with a quadrature row as objective (ordered sum over the intervals)"""
+    import os
+    import corleone_b200 as cb
+    from corleone_b200 import native as nat
+    rng = np.random.default_rng(B)
+    spec = P.lotka_spec(controls=rng.uniform(0, 1, 120), quadrature=True) if model == "lotka3" else P.lqr_spec(7, rng)
+    spec = dict(spec, quadrature_indices=[3] if model == "lotka3" else [2])
+    row = 3 if model == "lotka3" else 2
+    lay, ps_t, st, N = P.native_from_spec(spec, cb.Tsit5(2))
+    ps = cb.to_vec(ps_t)[None, :] + 0.05 * rng.standard_normal((B, N.nvars))
+    psT = np.ascontiguousarray(ps.T)                       # variable-major: the small path
+    want = nat.WANT_JAC | nat.WANT_DEFECTS | nat.WANT_OBJ | nat.WANT_GRAD | nat.WANT_XEND
+    sz = N.out_sizes()
+    fields = ("jac_vals", "defects_kind", "objective", "grad", "xend")
+
+    def run():
+        out = {f: np.full((sz[f], B), np.nan) for f in fields}
+        for _ in range(3):
+            N.eval_raw(psT.ctypes.data, B, B, want, nat.PS_SOA | nat.OUT_SOA, {f: out[f].ctypes.data for f in fields}, row)
+        return out
+
+    fused = run()
+    os.environ["CB200_NO_SMALL_TAIL"] = "1"
+    try:
+        lay2, ps_t2, st2, N2 = P.native_from_spec(spec, cb.Tsit5(2))
+        N_keep, N = N, N2
+        plain = run()
+    finally:
+        del os.environ["CB200_NO_SMALL_TAIL"]
+    for f in fields:
+        assert np.array_equal(fused[f], plain[f]), f
+        assert np.isfinite(fused[f]).all()
+    assert N_keep.launch_count() < N2.launch_count()       # one kernel per call instead of two
+
+
 def test_lotka_oed_fim_parity():
     """states-only integration of [x; G; F_triu]; FIM read-out (oed.jl:388-398) and its sum over candidates"""
     import corleone_b200 as cb
