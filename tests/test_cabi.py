@@ -156,3 +156,27 @@ def test_julia_binding_restates_the_header_structs_field_for_field():
         assert [n for n, _ in c] == [n for n, _ in j], (cname, [n for n, _ in c], [n for n, _ in j])
         for (n, ct), (_, jt) in zip(c, j):
             assert jt.startswith("Ptr{") if ct == "ptr" else jt == width[ct], (cname, n, ct, jt)
+
+
+def test_new_entry_points_reject_bad_arguments_without_a_device():
+    """version 200 / 201 entry points (data plane, resident results, sample times): NULL handles and buffers are refused with
+    CB200_ERR_ARG and a message -- no device work, no crash"""
+    L = native.lib()
+    L.cb200_comm_query.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    L.cb200_comm_unique_id.argtypes = [ctypes.c_void_p]
+    L.cb200_comm_init.argtypes = [ctypes.c_void_p, ctypes.c_int32, ctypes.c_int32, ctypes.c_void_p, ctypes.c_int64]
+    L.cb200_comm_gathered.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    L.cb200_resident.argtypes = [ctypes.c_void_p, ctypes.c_uint32, ctypes.c_void_p, ctypes.c_void_p]
+    L.cb200_sample_times.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    info = native.CommInfo()
+    assert L.cb200_comm_query(None, ctypes.byref(info)) == -1 and b"null" in L.cb200_last_error()
+    assert L.cb200_comm_unique_id(None) == -1
+    buf = ctypes.create_string_buffer(native.COMM_ID_BYTES)
+    assert L.cb200_comm_init(None, 2, 0, buf, 0) == -1
+    p = ctypes.c_void_p()
+    assert L.cb200_comm_gathered(None, ctypes.byref(p), None) == -1
+    assert L.cb200_resident(None, native.WANT_SENS, ctypes.byref(p), None) == -1
+    assert L.cb200_sample_times(None, None) == -1
+    assert L.cb200_comm_destroy(None) == 0                     # destroying nothing is fine
+    assert native.abi_layout(7) == []                          # unknown struct id
+    assert native.lib().cb200_version() == 201
