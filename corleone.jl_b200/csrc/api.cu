@@ -1262,6 +1262,7 @@ struct EvalPlan {
     // small evaluation as ONE kernel (shoot.cuh small_tail): the shooting kernel's last block computes the objective and
     // copies the result block [st_src, st_src + st_n) to the caller's pinned mirror st_dst.  eval_core clears `fuse_small`
     // when the model has no such kernel and runs the usual pipeline
+    int sm_reserve;             // chunks of the host pipeline: SMs a persistent kernel leaves to the neighbours' conversions
     mutable bool fuse_small;
     const double *st_src;
     double *st_dst;
@@ -1310,6 +1311,7 @@ static int eval_core(cb200_handle *h, cudaStream_t st, const double *d_ps, long 
     const long long nrow = nx + L0.nact;
     const long long ndef = (long long)h->defects.size();
     DevLayer L = L0;
+    L.sm_reserve = pl.sm_reserve;
     int G = 0;
     if (pl.need_sens) {
         G = h->G_sens;
@@ -1889,12 +1891,24 @@ extern "C" int cb200_eval(cb200_handle *h, const double *ps, int64_t B, int64_t 
     if (!ps_soa && !out_soa && B >= 1024) {
         Bc = ((B + 7) / 8 + 31) / 32 * 32;   // ~8 chunks, multiples of a warp
         if (Bc < 256) Bc = 256;
+    } else if (!ps_soa && !out_soa && B >= 128 && h->n_sens >= 20000 && pl.need_sens) {
+        // fewer candidates, but heavy ones (a rank's shard of BASELINE config 5: 512 candidates x 122 400 sensitivity
+        // entries, milliseconds of kernel per chunk): the copies of one chunk still hide behind the kernel of the next
+        Bc = ((B + 7) / 8 + 31) / 32 * 32;
+        if (Bc < 64) Bc = 64;
     }
     if (const char *e = getenv("CB200_HOST_CHUNK")) {
         const long long v = atoll(e);
         if (v > 0 && !ps_soa && !out_soa) Bc = std::min<long long>(B, (v + 31) / 32 * 32);
     }
     const int nchunks = (int)((B + Bc - 1) / Bc);
+    // A chunk's persistent kernel (the dense tensor-path kernel: 512 threads x 128 registers = the whole register file of every
+    // SM) would keep the layout conversions of the chunks before and after it off the GPU until it ends, and with them their
+    // copies: the chunks would run one after the other.  A few SMs stay free for them (tools/e2e_probe.py).
+    if (nchunks > 1) {
+        static const int reserve_env = getenv("CB200_SM_RESERVE") ? atoi(getenv("CB200_SM_RESERVE")) : -1;
+        pl.sm_reserve = reserve_env >= 0 ? reserve_env : 1;   // e2e_probe: 0 -> +24.5 ms on 170.7 ms, 1 -> +5.6, 2 -> +7.0, 3 -> +8.1, 4 -> +9.7, 8 -> +14.5
+    }
     if (nvars > 0) {
         const size_t bytes = sizeof(double) * (size_t)nvars * (size_t)B;
         if (h->ws_ps.reserve(bytes)) return fail(CB200_ERR_NOMEM, "device out of memory (ps, %zu bytes)", bytes);

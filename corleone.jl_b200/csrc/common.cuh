@@ -17,6 +17,8 @@ struct DevLayer {
     int max_M;               // largest number of pieces of an interval
     int flat;                // launch mapping: 1 = flat thread index (tiny batches), 0 = grid (b-tiles, i, r)
     int i0, In;              // intervals [i0, i0 + In) are integrated by this launch (cb200_set_interval_range); default 0, I
+    int sm_reserve;          // persistent kernels leave this many SMs free (host pipeline: the layout conversions of the
+                             // neighbouring chunks need somewhere to run while a chunk's kernel holds every register)
     int uniform_h;           // every piece of the layer has the same step size h = (t1 - t0)/K
     double hA[21];           // uniform_h: h * a_ij (Tsit5, slots as tsit5_coeffs) or the 4 RK4 factors
     double abstol, reltol;   // method 2 (adaptive Tsit5): the problem's tolerances

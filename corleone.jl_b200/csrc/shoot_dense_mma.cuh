@@ -506,7 +506,7 @@ inline int launch_dense_mma(int method, const DevLayer &L, const double *ps, lon
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         const long long n_items = ((B + DQ_CPI - 1) / DQ_CPI) * L.In;
-        const unsigned grid = (unsigned)std::min<long long>(n_items, sms);
+        const unsigned grid = (unsigned)std::min<long long>(n_items, std::max(1, sms - std::max(0, L.sm_reserve)));
         const size_t smem = nring * per;
         auto go = [&](auto kern) {
             cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
