@@ -469,12 +469,14 @@ shoot_dense_mma_queue_kernel(const __grid_constant__ DevLayer L, const double *_
                 *(volatile unsigned *)&s_full[slot] = K + 1u;
             }
         } else {
-            if (tau < ns) {
-                while (dq_peek(&s_full[slot]) < K + 1u) __nanosleep(64);
-                __threadfence_block();
+            // (a tile beyond the interval's directions has nothing to integrate, but it reports `done` only after the item's
+            // x task like everybody else: the x task that re-uses the slot counts reports, and a report of THIS item must
+            // not stand in for a missing one of the slot's previous item)
+            while (dq_peek(&s_full[slot]) < K + 1u) __nanosleep(64);
+            __threadfence_block();
+            if (tau < ns)
                 dense_column<NX, METHOD, UNI, true, false>(L, ps, ldb, o, i, nu0, ns, tau, b, true, cand_live, false, sp, nullptr,
                                                        DQ_CPI * NX, T);
-            }
             __syncwarp();
             if (lane == 0) {
                 __threadfence_block();
