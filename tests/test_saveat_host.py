@@ -92,3 +92,62 @@ def test_tangents_of_the_samples_are_the_derivative_of_the_interpolated_values()
     u, J = O.traj_jacobian(O.default_ps(), K=64)
     t = np.r_[0.0, sv, 1.0]
     assert np.max(np.abs(J[0, :, 0] - t * np.exp(-2.0 * t))) < 1e-10
+
+
+def test_saveat_samples_vs_extended_precision_restatement():
+    """An independent restatement of the fixed-step Tsit5 loop WITH its dense output in 40-digit arithmetic (mpmath): the
+    checker's saveat samples agree to rounding, so the C interpolation arithmetic (weights, step bookkeeping, which step a
+    time belongs to) is pinned by something that shares no code with it."""
+    mp = pytest.importorskip("mpmath")
+    mp.mp.dps = 40
+    Amp = [[mp.mpf(float(A[i, j])) for j in range(i)] for i in range(7)]
+    R = [["1.0", "-2.763706197274826", "2.9132554618219126", "-1.0530884977290216"],
+         ["0.0", "0.13169999999999998", "-0.2234", "0.1017"],
+         ["0.0", "3.9302962368947516", "-5.941033872131505", "2.490627285651253"],
+         ["0.0", "-12.411077166933676", "30.33818863028232", "-16.548102889244902"],
+         ["0.0", "37.50931341651104", "-88.1789048947664", "47.37952196281928"],
+         ["0.0", "-27.896526289197286", "65.09189467479366", "-34.87065786149661"],
+         ["0.0", "1.5", "-4.0", "2.5"]]
+    R = [[mp.mpf(float(x)) for x in row] for row in R]
+    rng = np.random.default_rng(9)
+    grid = np.array([0.0, 0.7, 1.3, 2.05])
+    ctrl = rng.uniform(0, 1, len(grid))
+    saveat = np.array([0.05, 0.31, 0.7, 0.99, 1.3000001, 2.0, 2.4, 2.9])     # inside pieces, on piece ends, just behind one
+    spec = dict(model="lotka3", u0=[0.5, 0.7, 0.0], p0=[0.0, 1.0, 1.0], tspan=(0.0, 3.0), controls=[(1, grid, ctrl)],
+                tunable_ic=[], quadrature_indices=[], shooting_points=None, saveat=list(saveat))
+    O = pyoracle.OracleLayer(spec)
+    K = 3
+    r = O.eval(O.default_ps(), K=K)
+
+    def ff(y, u):
+        x12 = y[0] * y[1]
+        return [y[0] - x12 - mp.mpf(0.4) * u * y[0], -y[1] + x12 - mp.mpf(0.2) * u * y[1], (y[0] - 1) ** 2 + (y[1] - 1) ** 2]
+
+    x = [mp.mpf("0.5"), mp.mpf("0.7"), mp.mpf(0)]
+    times, samples = [mp.mpf(0)], [list(x)]
+    edges = [mp.mpf(float(t)) for t in np.r_[grid, 3.0]]
+    for j in range(len(grid)):
+        t0, t1, u = edges[j], edges[j + 1], mp.mpf(float(ctrl[j]))
+        h = (t1 - t0) / K
+        inside = [mp.mpf(float(s)) for s in saveat if float(t0) < s < float(t1)]
+        for s in range(K):
+            ks = [ff(x, u)]
+            for st in range(1, 6):
+                ks.append(ff([x[c] + h * sum(Amp[st][m] * ks[m][c] for m in range(st)) for c in range(3)], u))
+            xn = [x[c] + h * sum(Amp[6][m] * ks[m][c] for m in range(6)) for c in range(3)]
+            ks.append(ff(xn, u))
+            tp, tn = t0 + s * h, (t1 if s == K - 1 else t0 + (s + 1) * h)
+            for sv in inside:
+                if tp < sv <= tn:
+                    th = (sv - tp) / h
+                    b = [th * (R[0][0] + th * (R[0][1] + th * (R[0][2] + th * R[0][3])))]
+                    b += [th * th * (R[i][1] + th * (R[i][2] + th * R[i][3])) for i in range(1, 7)]
+                    times.append(sv)
+                    samples.append([x[c] + h * sum(b[m] * ks[m][c] for m in range(7)) for c in range(3)])
+            x = xn
+        times.append(t1)
+        samples.append(list(x))
+    ref_t = np.array([float(t) for t in times])
+    ref_u = np.array([[float(v) for v in smp] for smp in samples]).T
+    assert np.array_equal(r["t"], ref_t)
+    assert np.max(np.abs(r["u"][:3] - ref_u) / np.maximum(1.0, np.abs(ref_u))) <= 1e-13
